@@ -1,0 +1,177 @@
+/* p2e.h -- C-ABI of the B200 witness / constraint engine for Weobe/plonky2-ecdsa's hot path.
+ *
+ * Every entry point replaces, in BATCHED form (n independent instances per call), one piece of
+ * the reference's SimpleGenerator::run_once / Gate::eval_unfiltered surface.  The reference
+ * interface each one stands in for is cited as file:line of the reference repository.
+ *
+ * Conventions
+ *   - All field elements on the boundary are canonical Goldilocks u64 (what a plonky2 wire
+ *     holds).  A nonnative value is 9 little-endian 29-bit limbs, one per wire.
+ *   - Matrices are WIRE-MAJOR ("structure of arrays"): element (wire w, instance i) lives at
+ *     ptr[w * stride + i], stride >= n, exactly plonky2's EvaluationVarsBaseBatch layout.
+ *   - `*_dev` entry points take DEVICE pointers and a cudaStream_t (as void*; NULL = the
+ *     library's stream) and only enqueue work.  The un-suffixed entry points take HOST
+ *     pointers, copy in, run, copy out and synchronise (stride == n).
+ *   - Return value: 0 on success, negative on CUDA / argument errors (p2e_last_error()).
+ *   - Per-instance contract violations (where the reference panics) never abort: they set
+ *     bits in err[i] (P2E_ERR_*), the analogue of the reference's panic for that instance.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef P2E_H
+#define P2E_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P2E_SECP256K1_BASE 0   /* plonky2::field::secp256k1_base::Secp256K1Base   */
+#define P2E_SECP256K1_SCALAR 1 /* plonky2::field::secp256k1_scalar::Secp256K1Scalar */
+
+#define P2E_ERR_U32 1u             /* "Value doesn't fit in u32"      gates/mul_nonnative.rs:262,271 */
+#define P2E_ERR_LIMB_RANGE 2u      /* assert limb < 2^29              gates/mul_nonnative.rs:275-276 */
+#define P2E_ERR_NONCANONICAL 4u    /* from_noncanonical_biguint >= 2^256 (plonky2 field)             */
+#define P2E_ERR_INVERSE_ZERO 8u    /* FF::inverse() of zero           gadgets/nonnative.rs:863       */
+#define P2E_ERR_CARRY_RANGE 16u    /* assert b_i + 2^33 < 2^34        gates/mul_nonnative.rs:527     */
+#define P2E_ERR_DIV_ZERO 32u       /* BigUint div_rem by zero         gadgets/biguint.rs:515         */
+#define P2E_ERR_LIMBS_OVERFLOW 64u /* assert num_limbs >= limbs.len() gadgets/biguint.rs:473         */
+#define P2E_ERR_CONNECT 128u       /* a connect_* / assert_* of the gadget cannot be satisfied       */
+#define P2E_ERR_INTERNAL 256u      /* device-side self check failed                                  */
+
+/* rows of the output matrix of p2e_mul_nonnative_witness (gate wire order, mul_nonnative.rs:41-59,384-390) */
+#define P2E_MUL_OUT_R 0          /* 9 rows : MulNonnativeGate wires 18..26            */
+#define P2E_MUL_OUT_Q 9          /* 9 rows : MulNonnativeGate wires 27..35            */
+#define P2E_MUL_OUT_CHECK_SUM 18 /* 17 rows: MulNonnativeGate wires 36..52 (= CheckSumGate a) */
+#define P2E_MUL_OUT_CARRY 35     /* 16 rows: CheckSumGate wires 17..32 (b_i + 2^33)   */
+#define P2E_MUL_OUT_ROWS 51
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int p2e_init(int device);      /* bind this process to CUDA device `device`, create the stream */
+void p2e_shutdown(void);
+const char* p2e_last_error(void);
+int p2e_device_count(void);
+int p2e_synchronize(void);
+
+/* device / pinned-host memory for callers that are not torch (Rust/C hosts) */
+int p2e_malloc(void** dptr, size_t bytes);
+int p2e_free(void* dptr);
+int p2e_host_alloc(void** hptr, size_t bytes); /* pinned */
+int p2e_host_free(void* hptr);
+int p2e_memcpy_h2d(void* dst, const void* src, size_t bytes);
+int p2e_memcpy_d2h(void* dst, const void* src, size_t bytes);
+
+/* ---- witness generation --------------------------------------------------------------- */
+
+/* MulNonnativeGenerator::run_once + CheckSumGenerator::run_once
+ * (gates/mul_nonnative.rs:249-324, 513-531).  x, y: [9][stride] wires.  out: [51][stride]
+ * (rows P2E_MUL_OUT_*).  err: [n]. */
+int p2e_mul_nonnative_witness_dev(int modulus, size_t n, const uint64_t* x, const uint64_t* y,
+                                  size_t in_stride, uint64_t* out, size_t out_stride,
+                                  uint32_t* err, void* stream);
+int p2e_mul_nonnative_witness(int modulus, size_t n, const uint64_t* x, const uint64_t* y,
+                              uint64_t* out, uint32_t* err);
+
+/* CheckSumGenerator::run_once alone (gates/mul_nonnative.rs:513-531): a [17][stride] -> b [16][stride] */
+int p2e_check_sum_witness_dev(size_t n, const uint64_t* a, size_t in_stride, uint64_t* b,
+                              size_t out_stride, uint32_t* err, void* stream);
+int p2e_check_sum_witness(size_t n, const uint64_t* a, uint64_t* b, uint32_t* err);
+
+/* NonNativeAdditionGenerator::run_once (gadgets/nonnative.rs:626-645).
+ * a: [a_limbs][stride], b: [b_limbs][stride] (limb counts 0..9, as the BigUintTargets have);
+ * out: [10][stride] = sum[9], overflow. */
+int p2e_add_nonnative_witness_dev(int modulus, size_t n, const uint64_t* a, int a_limbs,
+                                  const uint64_t* b, int b_limbs, size_t in_stride, uint64_t* out,
+                                  size_t out_stride, uint32_t* err, void* stream);
+int p2e_add_nonnative_witness(int modulus, size_t n, const uint64_t* a, int a_limbs,
+                              const uint64_t* b, int b_limbs, uint64_t* out, uint32_t* err);
+
+/* NonNativeSubtractionGenerator::run_once (gadgets/nonnative.rs:792-810): out = diff[9], overflow */
+int p2e_sub_nonnative_witness_dev(int modulus, size_t n, const uint64_t* a, int a_limbs,
+                                  const uint64_t* b, int b_limbs, size_t in_stride, uint64_t* out,
+                                  size_t out_stride, uint32_t* err, void* stream);
+int p2e_sub_nonnative_witness(int modulus, size_t n, const uint64_t* a, int a_limbs,
+                              const uint64_t* b, int b_limbs, uint64_t* out, uint32_t* err);
+
+/* NonNativeMultipleAddsGenerator::run_once (gadgets/nonnative.rs:696-728).
+ * summands: [k][9][stride] (k summands of 9 limbs each); out = sum[9], overflow (u32). */
+int p2e_add_many_nonnative_witness_dev(int modulus, size_t n, int k, const uint64_t* summands,
+                                       size_t in_stride, uint64_t* out, size_t out_stride,
+                                       uint32_t* err, void* stream);
+int p2e_add_many_nonnative_witness(int modulus, size_t n, int k, const uint64_t* summands,
+                                   uint64_t* out, uint32_t* err);
+
+/* NonNativeInverseGenerator::run_once (gadgets/nonnative.rs:857-872).
+ * x: [9][stride]; out: [18][stride] = div[9], inv[9] (the order of the generator's set_* calls). */
+int p2e_inv_nonnative_witness_dev(int modulus, size_t n, const uint64_t* x, size_t in_stride,
+                                  uint64_t* out, size_t out_stride, uint32_t* err, void* stream);
+int p2e_inv_nonnative_witness(int modulus, size_t n, const uint64_t* x, uint64_t* out, uint32_t* err);
+
+/* GLVDecompositionGenerator::run_once (gadgets/glv.rs:128-142 -> curve/glv.rs:39-77).
+ * k: [9][stride]; out: [12][stride] = k1[5], k2[5], k1_neg, k2_neg. */
+int p2e_glv_decompose_witness_dev(size_t n, const uint64_t* k, size_t in_stride, uint64_t* out,
+                                  size_t out_stride, uint32_t* err, void* stream);
+int p2e_glv_decompose_witness(size_t n, const uint64_t* k, uint64_t* out, uint32_t* err);
+
+/* BigUintDivRemGenerator::run_once (gadgets/biguint.rs:508-518), BITS = 29.
+ * a: [a_limbs][stride], b: [b_limbs][stride], a_limbs <= 18, 1 <= b_limbs <= 18;
+ * out: [div_limbs + b_limbs][stride] = div, rem with div_limbs = (b_limbs > a_limbs + 1) ? 0 :
+ * a_limbs - b_limbs + 1 (biguint.rs:391-399). */
+int p2e_biguint_div_rem_witness_dev(size_t n, const uint64_t* a, int a_limbs, const uint64_t* b,
+                                    int b_limbs, size_t in_stride, uint64_t* out,
+                                    size_t out_stride, uint32_t* err, void* stream);
+int p2e_biguint_div_rem_witness(size_t n, const uint64_t* a, int a_limbs, const uint64_t* b,
+                                int b_limbs, uint64_t* out, uint32_t* err);
+
+/* ---- constraint evaluation ------------------------------------------------------------ */
+
+/* MulNonnativeGate::eval_unfiltered over a batch of base-field points, i.e. plonky2's
+ * eval_unfiltered_base_batch for this gate (gates/mul_nonnative.rs:101-130).
+ * wires: [53][stride] (x 0..8, y 9..17, r 18..26, q 27..35, check_sum 36..52); out: [17][stride]. */
+int p2e_eval_mul_nonnative_dev(int modulus, size_t n_rows, const uint64_t* wires, size_t stride,
+                               uint64_t* out, size_t out_stride, void* stream);
+int p2e_eval_mul_nonnative(int modulus, size_t n_rows, const uint64_t* wires, uint64_t* out);
+
+/* CheckSumGate::eval_unfiltered (gates/mul_nonnative.rs:411-427).
+ * wires: [33][stride] (a 0..16, b 17..32); out: [17][stride]. */
+int p2e_eval_check_sum_dev(size_t n_rows, const uint64_t* wires, size_t stride, uint64_t* out,
+                           size_t out_stride, void* stream);
+int p2e_eval_check_sum(size_t n_rows, const uint64_t* wires, uint64_t* out);
+
+/* ---- ECDSA verification circuit witness (tape) ----------------------------------------- */
+
+/* Number of u64 slots one verify_secp256k1_message_circuit witness occupies in tape order
+ * (gadgets/ecdsa.rs:30-53 and callees): inputs excluded. */
+size_t p2e_ecdsa_tape_slots(void);
+/* Fills kinds[i] / offsets[i] for generator instance i of the tape; returns the instance count
+ * (call with NULLs to query).  kinds: 0 ADD 1 ADDMANY 2 SUB 3 INV 4 MUL 5 CHECKSUM 6 GLV. */
+size_t p2e_ecdsa_tape_layout(uint32_t* kinds, uint32_t* offsets);
+
+/* Witness of n independent verify_secp256k1_message_circuit instances.
+ * msg, r, s: [9][stride] scalar-field limbs; pkx, pky: [9][stride] base-field limbs.
+ * out: [p2e_ecdsa_tape_slots()][out_stride] every in-tree generator's output tuple in gadget
+ * call order.  err: [n]. */
+int p2e_ecdsa_witness_dev(size_t n, const uint64_t* msg, const uint64_t* r, const uint64_t* s,
+                          const uint64_t* pkx, const uint64_t* pky, size_t in_stride,
+                          uint64_t* out, size_t out_stride, uint32_t* err, void* stream);
+int p2e_ecdsa_witness(size_t n, const uint64_t* msg, const uint64_t* r, const uint64_t* s,
+                      const uint64_t* pkx, const uint64_t* pky, uint64_t* out, uint32_t* err);
+
+/* glv_mul(p, k) sub-circuit alone (gadgets/glv.rs:87-104): GLV decomposition + MSM chain. */
+size_t p2e_glv_mul_tape_slots(void);
+size_t p2e_glv_mul_tape_layout(uint32_t* kinds, uint32_t* offsets);
+int p2e_glv_mul_witness_dev(size_t n, const uint64_t* k, const uint64_t* px, const uint64_t* py,
+                            size_t in_stride, uint64_t* out, size_t out_stride, uint32_t* err,
+                            void* stream);
+int p2e_glv_mul_witness(size_t n, const uint64_t* k, const uint64_t* px, const uint64_t* py,
+                        uint64_t* out, uint32_t* err);
+
+/* ---- measurement helpers ---------------------------------------------------------------- */
+/* Dependent-free IMAD / IMAD.WIDE throughput microbenchmark on the current device; returns
+ * giga-ops per second (one op = one 32-bit lane multiply-add), or a negative error. */
+double p2e_bench_imad(int wide, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P2E_H */

@@ -1,0 +1,853 @@
+// p2e_kernels.cu -- batched witness-generator kernels (one instance per thread, limbs in
+// registers, wire-major coalesced loads/stores), the gate constraint evaluators over
+// Goldilocks LDE rows, and their extern "C" entry points (include/p2e.h).
+#include "../../include/p2e.h"
+#include "p2e_common.h"
+#include "p2e_field.cuh"
+
+namespace p2e {
+
+// ------------------------------------------------------------------------------------------
+// context
+Context& ctx() {
+  static Context c;
+  return c;
+}
+int set_error(const char* where, cudaError_t e) {
+  ctx().last_error = std::string(where) + ": " + cudaGetErrorString(e);
+  return -(int)e - 1000;
+}
+int set_error_msg(const char* msg) {
+  ctx().last_error = msg;
+  return -1;
+}
+int ensure_ready() {
+  if (!ctx().ready) return set_error_msg("p2e_init() has not been called (no CUDA device bound; there is no CPU fallback)");
+  return 0;
+}
+int get_scratch(int slot, size_t bytes, void** out) {
+  Context& c = ctx();
+  if (bytes == 0) bytes = 16;
+  if (c.scratch_bytes[slot] < bytes) {
+    if (c.scratch[slot]) P2E_CUDA(cudaFree(c.scratch[slot]));
+    c.scratch[slot] = nullptr;
+    c.scratch_bytes[slot] = 0;
+    P2E_CUDA(cudaMalloc(&c.scratch[slot], bytes));
+    c.scratch_bytes[slot] = bytes;
+  }
+  *out = c.scratch[slot];
+  return 0;
+}
+
+constexpr int TPB = 128;
+static inline unsigned grid_for(size_t n) { return (unsigned)((n + TPB - 1) / TPB); }
+
+// ------------------------------------------------------------------------------------------
+// A8 + A9
+template <class MOD>
+__global__ void __launch_bounds__(TPB)
+k_mul_witness(size_t n, const u64* __restrict__ x, const u64* __restrict__ y, size_t is,
+              u64* __restrict__ out, size_t os, u32* __restrict__ err) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  u64 xw[NL], yw[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    xw[l] = x[l * is + i];
+    yw[l] = y[l * is + i];
+  }
+  u32 xa[NL], ya[NL];
+  u32 e = load_mul_wires(xw, xa) | load_mul_wires(yw, ya);
+  u32 r[NL], q[NL];
+  u64 cs[2 * NL - 1], b[2 * NL - 2];
+  if (e == 0) {
+    e = mul_witness_core<MOD>(xa, ya, r, q, cs, b);
+  } else {
+    // the reference panics before writing anything: emit zeros
+#pragma unroll
+    for (int l = 0; l < NL; l++) r[l] = q[l] = 0;
+#pragma unroll
+    for (int l = 0; l < 2 * NL - 1; l++) cs[l] = 0;
+#pragma unroll
+    for (int l = 0; l < 2 * NL - 2; l++) b[l] = 0;
+  }
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    out[(P2E_MUL_OUT_R + l) * os + i] = r[l];
+    out[(P2E_MUL_OUT_Q + l) * os + i] = q[l];
+  }
+#pragma unroll
+  for (int l = 0; l < 2 * NL - 1; l++) out[(P2E_MUL_OUT_CHECK_SUM + l) * os + i] = cs[l];
+#pragma unroll
+  for (int l = 0; l < 2 * NL - 2; l++) out[(P2E_MUL_OUT_CARRY + l) * os + i] = b[l];
+  err[i] = e;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_check_sum_witness(size_t n, const u64* __restrict__ a, size_t is, u64* __restrict__ out, size_t os,
+                    u32* __restrict__ err) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  u64 aw[2 * NL - 1], b[2 * NL - 2];
+#pragma unroll
+  for (int l = 0; l < 2 * NL - 1; l++) aw[l] = a[l * is + i];
+  u32 e = check_sum_core(aw, b);
+#pragma unroll
+  for (int l = 0; l < 2 * NL - 2; l++) out[l * os + i] = b[l];
+  err[i] = e;
+}
+
+// loads `nl` (0..9) wires of a nonnative operand, absent limbs = 0
+__device__ __forceinline__ void load_wires(const u64* __restrict__ p, int nl, size_t is, size_t i, u64 (&w)[NL]) {
+#pragma unroll
+  for (int l = 0; l < NL; l++) w[l] = (l < nl) ? p[l * is + i] : 0;
+}
+
+// A4 / A6
+template <class MOD, bool IS_SUB>
+__global__ void __launch_bounds__(TPB)
+k_addsub_witness(size_t n, const u64* __restrict__ a, int al, const u64* __restrict__ b, int bl, size_t is,
+                 u64* __restrict__ out, size_t os, u32* __restrict__ err) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  u64 aw[NL], bw[NL];
+  load_wires(a, al, is, i, aw);
+  load_wires(b, bl, is, i, bw);
+  u32 ac[NL], bc[NL], r[NL];
+  u32 e = load_canon<MOD>(aw, ac) | load_canon<MOD>(bw, bc);
+  u32 ov = 0;
+  if (e == 0) {
+    ov = IS_SUB ? sub_witness_core<MOD>(ac, bc, r) : add_witness_core<MOD>(ac, bc, r);
+  } else {
+    set_zero9(r);
+  }
+#pragma unroll
+  for (int l = 0; l < NL; l++) out[l * os + i] = r[l];
+  out[NL * os + i] = ov;
+  err[i] = e;
+}
+
+// A5: k summands, [k][9][stride]
+template <class MOD>
+__global__ void __launch_bounds__(TPB)
+k_add_many_witness(size_t n, int k, const u64* __restrict__ s, size_t is, u64* __restrict__ out, size_t os,
+                   u32* __restrict__ err) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  u32 acc[NL];
+  set_zero9(acc);
+  u32 ov = 0, e = 0;
+  for (int t = 0; t < k; t++) {
+    u64 w[NL];
+    load_wires(s + (size_t)t * NL * is, NL, is, i, w);
+    u32 v[NL], sum[NL];
+    e |= load_canon<MOD>(w, v);
+    add9(acc, v, sum);               // acc < M, v < M  ->  < 2M < 2^257
+    if (geq_mod<MOD>(sum)) {         // running div_rem: sum of k canonical values, quotient counts wraps
+      sub_mod9<MOD>(sum, acc);
+      ov++;
+    } else {
+      copy9(sum, acc);
+    }
+  }
+  if (e) { set_zero9(acc); ov = 0; }
+#pragma unroll
+  for (int l = 0; l < NL; l++) out[l * os + i] = acc[l];
+  out[NL * os + i] = ov;
+  err[i] = e;
+}
+
+// A7: one Fermat ladder per thread is the literal reference algorithm; the batched entry uses
+// Montgomery's trick over CHUNK consecutive instances per thread (inverse is unique => bit-exact).
+constexpr int INV_CHUNK = 8;
+template <class MOD>
+__global__ void __launch_bounds__(TPB)
+k_inv_witness(size_t n, const u64* __restrict__ x, size_t is, u64* __restrict__ out, size_t os,
+              u32* __restrict__ err) {
+  // thread t handles instances t, t + T, t + 2T, ... (T = total threads) so loads stay coalesced
+  size_t T = (size_t)gridDim.x * TPB;
+  size_t t0 = (size_t)blockIdx.x * TPB + threadIdx.x;
+  u32 xc[INV_CHUNK][NL];
+  u32 pre[INV_CHUNK][NL];      // prefix products
+  u32 e[INV_CHUNK];
+  u32 run[NL];
+  set_zero9(run);
+  run[0] = 1;
+  int cnt = 0;
+#pragma unroll
+  for (int c = 0; c < INV_CHUNK; c++) {
+    size_t i = t0 + (size_t)c * T;
+    e[c] = 0;
+    set_zero9(xc[c]);
+    if (i < n) {
+      u64 w[NL];
+      load_wires(x, NL, is, i, w);
+      e[c] = load_canon<MOD>(w, xc[c]);
+      if (e[c] == 0 && is_zero9(xc[c])) e[c] = ERR_INVERSE_ZERO;
+      cnt = c + 1;
+    } else {
+      e[c] = ERR_INTERNAL;       // marks "not present"
+    }
+    copy9(run, pre[c]);
+    if (e[c] == 0) {
+      u32 t[NL];
+      mulmod<MOD>(run, xc[c], t);
+      copy9(t, run);
+    }
+  }
+  if (cnt == 0) return;
+  u32 inv_run[NL];
+  inv_mod<MOD>(run, inv_run);
+#pragma unroll
+  for (int c = INV_CHUNK - 1; c >= 0; c--) {
+    size_t i = t0 + (size_t)c * T;
+    if (i >= n) continue;
+    u32 inv[NL], div[NL];
+    set_zero9(inv);
+    set_zero9(div);
+    u32 ee = e[c];
+    if (ee == 0) {
+      u32 t[NL];
+      mulmod<MOD>(inv_run, pre[c], inv);
+      mulmod<MOD>(inv_run, xc[c], t);
+      copy9(t, inv_run);
+      ee |= inv_div_core<MOD>(xc[c], inv, div);
+    }
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      out[l * os + i] = div[l];
+      out[(NL + l) * os + i] = inv[l];
+    }
+    err[i] = ee;
+  }
+}
+
+// A10
+__global__ void __launch_bounds__(TPB)
+k_glv_witness(size_t n, const u64* __restrict__ k, size_t is, u64* __restrict__ out, size_t os,
+              u32* __restrict__ err) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  u64 w[NL];
+  load_wires(k, NL, is, i, w);
+  u32 kc[NL], k1[NL], k2[NL], n1 = 0, n2 = 0;
+  u32 e = load_canon<ModN>(w, kc);
+  if (e == 0) {
+    glv_decompose_core(kc, k1, k2, n1, n2);
+    // set_biguint_target into 5-limb targets (glv.rs:62-63): must fit 145 bits
+    u32 hi = 0;
+#pragma unroll
+    for (int l = 5; l < NL; l++) hi |= k1[l] | k2[l];
+    if (hi) e |= ERR_LIMBS_OVERFLOW;
+  } else {
+    set_zero9(k1);
+    set_zero9(k2);
+  }
+#pragma unroll
+  for (int l = 0; l < 5; l++) {
+    out[l * os + i] = k1[l];
+    out[(5 + l) * os + i] = k2[l];
+  }
+  out[10 * os + i] = n1;
+  out[11 * os + i] = n2;
+  err[i] = e;
+}
+
+// A3: Knuth algorithm D in base 2^29 on local arrays (generic limb counts; not on the ECDSA path)
+constexpr int DR_MAX = 18;      // max wires per operand
+constexpr int DR_W = DR_MAX + 3; // normalised limbs an operand of DR_MAX raw u64 wires can need
+__device__ int dr_load(const u64* __restrict__ p, int nl, size_t is, size_t i, u32* v) {
+  // Horner over raw wires -> normalised limbs; returns significant limb count
+  u64 c = 0;
+  int top = 0;
+  for (int l = 0; l < DR_W; l++) {
+    u64 w = (l < nl) ? p[l * is + i] : 0;
+    u64 lo = w + c;
+    u64 ov = lo < w ? 1 : 0;
+    v[l] = (u32)lo & LMASK;
+    c = (lo >> LB) | (ov << (64 - LB));
+    if (v[l]) top = l + 1;
+  }
+  return top;
+}
+
+__global__ void __launch_bounds__(TPB)
+k_divrem_witness(size_t n, const u64* __restrict__ a, int al, const u64* __restrict__ b, int bl, size_t is,
+                 u64* __restrict__ out, size_t os, u32* __restrict__ err) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  const int div_limbs = (bl > al + 1) ? 0 : al - bl + 1;
+  u32 u[DR_W + 1], v[DR_W], q[DR_W];
+  int m = dr_load(a, al, is, i, u);
+  int nn = dr_load(b, bl, is, i, v);
+  u[DR_W] = 0;
+  for (int l = 0; l < DR_W; l++) q[l] = 0;
+  u32 e = 0;
+  if (nn == 0) {
+    e = ERR_DIV_ZERO;
+  } else if (m >= nn) {
+    if (nn == 1) {
+      u64 rem = 0;
+      for (int j = m - 1; j >= 0; j--) {
+        u64 cur = (rem << LB) | u[j];
+        q[j] = (u32)(cur / v[0]);
+        rem = cur % v[0];
+      }
+      for (int l = 0; l < DR_W; l++) u[l] = 0;
+      u[0] = (u32)rem;
+    } else {
+      int s = __clz(v[nn - 1]) - 3;            // shift so that v[nn-1] >= 2^28
+      if (s > 0) {
+        for (int l = nn - 1; l > 0; l--) v[l] = ((v[l] << s) | (v[l - 1] >> (LB - s))) & LMASK;
+        v[0] = (v[0] << s) & LMASK;
+        u[m] = u[m - 1] >> (LB - s);
+        for (int l = m - 1; l > 0; l--) u[l] = ((u[l] << s) | (u[l - 1] >> (LB - s))) & LMASK;
+        u[0] = (u[0] << s) & LMASK;
+      } else {
+        u[m] = 0;
+      }
+      for (int j = m - nn; j >= 0; j--) {
+        u64 num = ((u64)u[j + nn] << LB) | u[j + nn - 1];
+        u64 qh = num / v[nn - 1];
+        u64 rh = num % v[nn - 1];
+        while (qh >> LB || qh * v[nn - 2] > ((rh << LB) | u[j + nn - 2])) {
+          qh--;
+          rh += v[nn - 1];
+          if (rh >> LB) break;
+        }
+        i64 br = 0;
+        u64 cy = 0;
+        for (int l = 0; l < nn; l++) {
+          u64 p = qh * v[l] + cy;
+          cy = p >> LB;
+          i64 t = (i64)u[j + l] - (i64)(p & LMASK) + br;
+          u[j + l] = (u32)t & LMASK;
+          br = t >> LB;
+        }
+        i64 t = (i64)u[j + nn] - (i64)cy + br;
+        u[j + nn] = (u32)t & LMASK;
+        if (t < 0) {
+          qh--;
+          u32 c2 = 0;
+          for (int l = 0; l < nn; l++) {
+            u32 t2 = u[j + l] + v[l] + c2;
+            u[j + l] = t2 & LMASK;
+            c2 = t2 >> LB;
+          }
+          u[j + nn] = (u[j + nn] + c2) & LMASK;
+        }
+        q[j] = (u32)qh;
+      }
+      if (s > 0) {
+        for (int l = 0; l < nn; l++) u[l] = ((u[l] >> s) | (u[l + 1] << (LB - s))) & LMASK;
+      }
+      for (int l = nn; l <= DR_W; l++) u[l] = 0;
+    }
+  }
+  // set_biguint_target asserts (biguint.rs:473)
+  if (e == 0) {
+    for (int l = div_limbs; l < DR_W; l++) if (q[l]) e |= ERR_LIMBS_OVERFLOW;
+    for (int l = bl; l < DR_W; l++) if (u[l]) e |= ERR_LIMBS_OVERFLOW;
+  }
+  for (int l = 0; l < div_limbs; l++) out[l * os + i] = e ? 0 : q[l];
+  for (int l = 0; l < bl; l++) out[(div_limbs + l) * os + i] = e ? 0 : u[l];
+  err[i] = e;
+}
+
+// ------------------------------------------------------------------------------------------
+// Constraint evaluation over Goldilocks rows (A11, A12).  One LDE row per thread; wires are
+// arbitrary canonical field elements.  Column sums are accumulated un-reduced in 96-bit
+// accumulators per 32x32 partial-product class and reduced once per constraint.
+struct Acc3 {
+  u32 w0, w1, w2;
+};
+__device__ __forceinline__ void mac3(Acc3& a, u32 x, u32 y) {
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+      "addc.u32 %2, %2, 0;"
+      : "+r"(a.w0), "+r"(a.w1), "+r"(a.w2)
+      : "r"(x), "r"(y));
+}
+// (A + B*2^32 + C*2^64 + add) mod P
+__device__ __forceinline__ u64 reduce_abc(const Acc3& A, const Acc3& B, const Acc3& C, u64 add) {
+  u64 t = (u64)A.w0 + (u32)add;
+  u32 W0 = (u32)t;
+  t = (t >> 32) + A.w1 + B.w0 + (add >> 32);
+  u32 W1 = (u32)t;
+  t = (t >> 32) + A.w2 + B.w1 + C.w0;
+  u32 W2 = (u32)t;
+  t = (t >> 32) + B.w2 + C.w1;
+  u32 W3 = (u32)t;
+  u32 W4 = (u32)(t >> 32) + C.w2;
+  u64 r = gl_reduce128(((u64)W1 << 32) | W0, ((u64)W3 << 32) | W2);
+  return gl_sub(r, (u64)W4 << 32);     // 2^128 = -2^32 (mod P)
+}
+
+template <class MOD>
+__global__ void __launch_bounds__(TPB)
+k_eval_mul_nonnative(size_t n, const u64* __restrict__ wires, size_t is, u64* __restrict__ out, size_t os) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  u64 w[6 * NL - 1];
+#pragma unroll
+  for (int l = 0; l < 6 * NL - 1; l++) w[l] = wires[l * is + i];
+#pragma unroll
+  for (int c = 0; c < 2 * NL - 1; c++) {
+    Acc3 A = {0, 0, 0}, B = {0, 0, 0}, C = {0, 0, 0}, QA = {0, 0, 0}, QB = {0, 0, 0};
+    const Acc3 Z = {0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < NL; j++) {
+      const int k = c - j;
+      if (k >= 0 && k < NL) {
+        u32 xl = (u32)w[j], xh = (u32)(w[j] >> 32);
+        u32 yl = (u32)w[NL + k], yh = (u32)(w[NL + k] >> 32);
+        u32 ql = (u32)w[3 * NL + k], qh = (u32)(w[3 * NL + k] >> 32);
+        mac3(A, xl, yl);
+        mac3(B, xl, yh);
+        mac3(B, xh, yl);
+        mac3(C, xh, yh);
+        mac3(QA, MOD::m(j), ql);
+        mac3(QB, MOD::m(j), qh);
+      }
+    }
+    u64 neg = reduce_abc(A, B, C, w[4 * NL + c]);
+    u64 pos = reduce_abc(QA, QB, Z, c < NL ? w[2 * NL + c] : 0);
+    out[c * os + i] = gl_sub(pos, neg);
+  }
+}
+
+__global__ void __launch_bounds__(TPB)
+k_eval_check_sum(size_t n, const u64* __restrict__ wires, size_t is, u64* __restrict__ out, size_t os) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  u64 last = 0;
+#pragma unroll
+  for (int c = 0; c < 2 * NL - 1; c++) {
+    u64 a = wires[c * is + i];
+    u64 s = gl_add(a, last);
+    if (c < 2 * NL - 2) {
+      u64 o = gl_sub(wires[(2 * NL - 1 + c) * is + i], 1ull << 33);
+      u64 prod = gl_reduce128(o << LB, o >> (64 - LB));   // 2^29 * o
+      out[c * os + i] = gl_sub(s, prod);
+      last = o;
+    } else {
+      out[c * os + i] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// INT32 multiply-add peak microbenchmark (roofline denominator for the witness kernels)
+template <bool WIDE>
+__global__ void __launch_bounds__(256) k_imad_bench(int iters, u32 seed, u64* sink) {
+  constexpr int CH = 8;
+  u32 m = seed | 1u;
+  if (WIDE) {
+    u64 acc[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k++) acc[k] = threadIdx.x + k;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int k = 0; k < CH; k++) acc[k] = (u64)(u32)acc[k] * (u64)m + acc[k];   // IMAD.WIDE.U32
+    }
+    u64 s = 0;
+#pragma unroll
+    for (int k = 0; k < CH; k++) s ^= acc[k];
+    if (s == 0x1234567ull) sink[0] = s;
+  } else {
+    u32 acc[CH];
+#pragma unroll
+    for (int k = 0; k < CH; k++) acc[k] = threadIdx.x + k;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int k = 0; k < CH; k++) acc[k] = acc[k] * m + (u32)k;                    // IMAD
+    }
+    u32 s = 0;
+#pragma unroll
+    for (int k = 0; k < CH; k++) s ^= acc[k];
+    if (s == 0x1234567u) sink[0] = s;
+  }
+}
+
+}  // namespace p2e
+
+// ==========================================================================================
+// extern "C"
+using namespace p2e;
+
+#define P2E_CHECK_READY() \
+  do {                    \
+    int rc__ = ensure_ready(); \
+    if (rc__) return rc__;     \
+  } while (0)
+#define P2E_LAUNCH_CHECK() P2E_CUDA(cudaGetLastError())
+
+extern "C" {
+
+int p2e_init(int device) {
+  Context& c = ctx();
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess) return set_error("cudaGetDeviceCount", e);
+  if (cnt == 0) return set_error_msg("no CUDA device visible (there is no CPU fallback)");
+  if (device < 0 || device >= cnt) return set_error_msg("p2e_init: device index out of range");
+  P2E_CUDA(cudaSetDevice(device));
+  if (c.ready && c.device == device) return 0;
+  if (c.ready) p2e_shutdown();
+  cudaDeviceProp prop;
+  P2E_CUDA(cudaGetDeviceProperties(&prop, device));
+  c.sm_count = prop.multiProcessorCount;
+  P2E_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  c.device = device;
+  c.ready = true;
+  return 0;
+}
+
+void p2e_shutdown(void) {
+  Context& c = ctx();
+  if (!c.ready) return;
+  cudaStreamSynchronize(c.stream);
+  for (int i = 0; i < 4; i++) {
+    if (c.scratch[i]) cudaFree(c.scratch[i]);
+    c.scratch[i] = nullptr;
+    c.scratch_bytes[i] = 0;
+  }
+  cudaStreamDestroy(c.stream);
+  c.stream = nullptr;
+  c.ready = false;
+}
+
+const char* p2e_last_error(void) { return ctx().last_error.c_str(); }
+
+int p2e_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) return 0;
+  return cnt;
+}
+
+int p2e_synchronize(void) {
+  P2E_CHECK_READY();
+  P2E_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+int p2e_malloc(void** dptr, size_t bytes) {
+  P2E_CHECK_READY();
+  P2E_CUDA(cudaMalloc(dptr, bytes ? bytes : 16));
+  return 0;
+}
+int p2e_free(void* dptr) {
+  P2E_CUDA(cudaFree(dptr));
+  return 0;
+}
+int p2e_host_alloc(void** hptr, size_t bytes) {
+  P2E_CHECK_READY();
+  P2E_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 16, cudaHostAllocDefault));
+  return 0;
+}
+int p2e_host_free(void* hptr) {
+  P2E_CUDA(cudaFreeHost(hptr));
+  return 0;
+}
+int p2e_memcpy_h2d(void* dst, const void* src, size_t bytes) {
+  P2E_CHECK_READY();
+  P2E_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx().stream));
+  P2E_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+int p2e_memcpy_d2h(void* dst, const void* src, size_t bytes) {
+  P2E_CHECK_READY();
+  P2E_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx().stream));
+  P2E_CUDA(cudaStreamSynchronize(ctx().stream));
+  return 0;
+}
+
+static int bad_modulus(int m) {
+  if (m != P2E_SECP256K1_BASE && m != P2E_SECP256K1_SCALAR) return set_error_msg("unknown modulus id");
+  return 0;
+}
+static int bad_limbs(int l) {
+  if (l < 0 || l > NL) return set_error_msg("limb count must be in 0..9");
+  return 0;
+}
+
+// ---- device-pointer entry points
+int p2e_mul_nonnative_witness_dev(int modulus, size_t n, const uint64_t* x, const uint64_t* y, size_t is,
+                                  uint64_t* out, size_t os, uint32_t* err, void* stream) {
+  P2E_CHECK_READY();
+  if (bad_modulus(modulus)) return -1;
+  if (n == 0) return 0;
+  if (is < n || os < n) return set_error_msg("stride < n");
+  cudaStream_t st = pick_stream(stream);
+  if (modulus == P2E_SECP256K1_BASE)
+    k_mul_witness<ModP><<<grid_for(n), TPB, 0, st>>>(n, x, y, is, out, os, err);
+  else
+    k_mul_witness<ModN><<<grid_for(n), TPB, 0, st>>>(n, x, y, is, out, os, err);
+  P2E_LAUNCH_CHECK();
+  return 0;
+}
+
+int p2e_check_sum_witness_dev(size_t n, const uint64_t* a, size_t is, uint64_t* b, size_t os, uint32_t* err,
+                              void* stream) {
+  P2E_CHECK_READY();
+  if (n == 0) return 0;
+  if (is < n || os < n) return set_error_msg("stride < n");
+  k_check_sum_witness<<<grid_for(n), TPB, 0, pick_stream(stream)>>>(n, a, is, b, os, err);
+  P2E_LAUNCH_CHECK();
+  return 0;
+}
+
+int p2e_add_nonnative_witness_dev(int modulus, size_t n, const uint64_t* a, int al, const uint64_t* b, int bl,
+                                  size_t is, uint64_t* out, size_t os, uint32_t* err, void* stream) {
+  P2E_CHECK_READY();
+  if (bad_modulus(modulus) || bad_limbs(al) || bad_limbs(bl)) return -1;
+  if (n == 0) return 0;
+  if (is < n || os < n) return set_error_msg("stride < n");
+  cudaStream_t st = pick_stream(stream);
+  if (modulus == P2E_SECP256K1_BASE)
+    k_addsub_witness<ModP, false><<<grid_for(n), TPB, 0, st>>>(n, a, al, b, bl, is, out, os, err);
+  else
+    k_addsub_witness<ModN, false><<<grid_for(n), TPB, 0, st>>>(n, a, al, b, bl, is, out, os, err);
+  P2E_LAUNCH_CHECK();
+  return 0;
+}
+
+int p2e_sub_nonnative_witness_dev(int modulus, size_t n, const uint64_t* a, int al, const uint64_t* b, int bl,
+                                  size_t is, uint64_t* out, size_t os, uint32_t* err, void* stream) {
+  P2E_CHECK_READY();
+  if (bad_modulus(modulus) || bad_limbs(al) || bad_limbs(bl)) return -1;
+  if (n == 0) return 0;
+  if (is < n || os < n) return set_error_msg("stride < n");
+  cudaStream_t st = pick_stream(stream);
+  if (modulus == P2E_SECP256K1_BASE)
+    k_addsub_witness<ModP, true><<<grid_for(n), TPB, 0, st>>>(n, a, al, b, bl, is, out, os, err);
+  else
+    k_addsub_witness<ModN, true><<<grid_for(n), TPB, 0, st>>>(n, a, al, b, bl, is, out, os, err);
+  P2E_LAUNCH_CHECK();
+  return 0;
+}
+
+int p2e_add_many_nonnative_witness_dev(int modulus, size_t n, int k, const uint64_t* s, size_t is, uint64_t* out,
+                                       size_t os, uint32_t* err, void* stream) {
+  P2E_CHECK_READY();
+  if (bad_modulus(modulus)) return -1;
+  if (k < 2) return set_error_msg("add_many needs k >= 2 summands (k == 1 returns its input, nonnative.rs:315-317)");
+  if (n == 0) return 0;
+  if (is < n || os < n) return set_error_msg("stride < n");
+  cudaStream_t st = pick_stream(stream);
+  if (modulus == P2E_SECP256K1_BASE)
+    k_add_many_witness<ModP><<<grid_for(n), TPB, 0, st>>>(n, k, s, is, out, os, err);
+  else
+    k_add_many_witness<ModN><<<grid_for(n), TPB, 0, st>>>(n, k, s, is, out, os, err);
+  P2E_LAUNCH_CHECK();
+  return 0;
+}
+
+int p2e_inv_nonnative_witness_dev(int modulus, size_t n, const uint64_t* x, size_t is, uint64_t* out, size_t os,
+                                  uint32_t* err, void* stream) {
+  P2E_CHECK_READY();
+  if (bad_modulus(modulus)) return -1;
+  if (n == 0) return 0;
+  if (is < n || os < n) return set_error_msg("stride < n");
+  cudaStream_t st = pick_stream(stream);
+  size_t threads = (n + INV_CHUNK - 1) / INV_CHUNK;
+  if (modulus == P2E_SECP256K1_BASE)
+    k_inv_witness<ModP><<<grid_for(threads), TPB, 0, st>>>(n, x, is, out, os, err);
+  else
+    k_inv_witness<ModN><<<grid_for(threads), TPB, 0, st>>>(n, x, is, out, os, err);
+  P2E_LAUNCH_CHECK();
+  return 0;
+}
+
+int p2e_glv_decompose_witness_dev(size_t n, const uint64_t* k, size_t is, uint64_t* out, size_t os, uint32_t* err,
+                                  void* stream) {
+  P2E_CHECK_READY();
+  if (n == 0) return 0;
+  if (is < n || os < n) return set_error_msg("stride < n");
+  k_glv_witness<<<grid_for(n), TPB, 0, pick_stream(stream)>>>(n, k, is, out, os, err);
+  P2E_LAUNCH_CHECK();
+  return 0;
+}
+
+int p2e_biguint_div_rem_witness_dev(size_t n, const uint64_t* a, int al, const uint64_t* b, int bl, size_t is,
+                                    uint64_t* out, size_t os, uint32_t* err, void* stream) {
+  P2E_CHECK_READY();
+  if (al < 0 || al > DR_MAX || bl < 1 || bl > DR_MAX) return set_error_msg("div_rem: limb counts out of range");
+  if (n == 0) return 0;
+  if (is < n || os < n) return set_error_msg("stride < n");
+  k_divrem_witness<<<grid_for(n), TPB, 0, pick_stream(stream)>>>(n, a, al, b, bl, is, out, os, err);
+  P2E_LAUNCH_CHECK();
+  return 0;
+}
+
+int p2e_eval_mul_nonnative_dev(int modulus, size_t n, const uint64_t* wires, size_t is, uint64_t* out, size_t os,
+                               void* stream) {
+  P2E_CHECK_READY();
+  if (bad_modulus(modulus)) return -1;
+  if (n == 0) return 0;
+  if (is < n || os < n) return set_error_msg("stride < n");
+  cudaStream_t st = pick_stream(stream);
+  if (modulus == P2E_SECP256K1_BASE)
+    k_eval_mul_nonnative<ModP><<<grid_for(n), TPB, 0, st>>>(n, wires, is, out, os);
+  else
+    k_eval_mul_nonnative<ModN><<<grid_for(n), TPB, 0, st>>>(n, wires, is, out, os);
+  P2E_LAUNCH_CHECK();
+  return 0;
+}
+
+int p2e_eval_check_sum_dev(size_t n, const uint64_t* wires, size_t is, uint64_t* out, size_t os, void* stream) {
+  P2E_CHECK_READY();
+  if (n == 0) return 0;
+  if (is < n || os < n) return set_error_msg("stride < n");
+  k_eval_check_sum<<<grid_for(n), TPB, 0, pick_stream(stream)>>>(n, wires, is, out, os);
+  P2E_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- host-pointer entry points: H2D, kernel, D2H, synchronise (stride == n)
+struct HostIn {
+  const void* ptr;
+  size_t rows;
+};
+
+template <class Launch>
+static int run_host(size_t n, const HostIn* ins, int n_in, void* out, size_t out_rows, uint32_t* err, Launch launch) {
+  P2E_CHECK_READY();
+  if (n == 0) return 0;
+  cudaStream_t st = ctx().stream;
+  size_t in_rows = 0;
+  for (int k = 0; k < n_in; k++) in_rows += ins[k].rows;
+  void *din = nullptr, *dout = nullptr, *derr = nullptr;
+  int rc;
+  if ((rc = get_scratch(0, in_rows * n * 8, &din))) return rc;
+  if ((rc = get_scratch(1, out_rows * n * 8, &dout))) return rc;
+  if ((rc = get_scratch(2, n * 4, &derr))) return rc;
+  const uint64_t* dptr[8];
+  size_t off = 0;
+  for (int k = 0; k < n_in; k++) {
+    dptr[k] = (const uint64_t*)din + off;
+    if (ins[k].rows)
+      P2E_CUDA(cudaMemcpyAsync((uint64_t*)din + off, ins[k].ptr, ins[k].rows * n * 8, cudaMemcpyHostToDevice, st));
+    off += ins[k].rows * n;
+  }
+  if ((rc = launch(dptr, (uint64_t*)dout, (uint32_t*)derr, (void*)st))) return rc;
+  P2E_CUDA(cudaMemcpyAsync(out, dout, out_rows * n * 8, cudaMemcpyDeviceToHost, st));
+  if (err) P2E_CUDA(cudaMemcpyAsync(err, derr, n * 4, cudaMemcpyDeviceToHost, st));
+  P2E_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" {
+
+int p2e_mul_nonnative_witness(int modulus, size_t n, const uint64_t* x, const uint64_t* y, uint64_t* out,
+                              uint32_t* err) {
+  HostIn ins[2] = {{x, NL}, {y, NL}};
+  return run_host(n, ins, 2, out, P2E_MUL_OUT_ROWS, err, [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* s) {
+    return p2e_mul_nonnative_witness_dev(modulus, n, d[0], d[1], n, o, n, e, s);
+  });
+}
+
+int p2e_check_sum_witness(size_t n, const uint64_t* a, uint64_t* b, uint32_t* err) {
+  HostIn ins[1] = {{a, 2 * NL - 1}};
+  return run_host(n, ins, 1, b, 2 * NL - 2, err, [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* s) {
+    return p2e_check_sum_witness_dev(n, d[0], n, o, n, e, s);
+  });
+}
+
+int p2e_add_nonnative_witness(int modulus, size_t n, const uint64_t* a, int al, const uint64_t* b, int bl,
+                              uint64_t* out, uint32_t* err) {
+  if (bad_limbs(al) || bad_limbs(bl)) return -1;
+  HostIn ins[2] = {{a, (size_t)al}, {b, (size_t)bl}};
+  return run_host(n, ins, 2, out, NL + 1, err, [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* s) {
+    return p2e_add_nonnative_witness_dev(modulus, n, d[0], al, d[1], bl, n, o, n, e, s);
+  });
+}
+
+int p2e_sub_nonnative_witness(int modulus, size_t n, const uint64_t* a, int al, const uint64_t* b, int bl,
+                              uint64_t* out, uint32_t* err) {
+  if (bad_limbs(al) || bad_limbs(bl)) return -1;
+  HostIn ins[2] = {{a, (size_t)al}, {b, (size_t)bl}};
+  return run_host(n, ins, 2, out, NL + 1, err, [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* s) {
+    return p2e_sub_nonnative_witness_dev(modulus, n, d[0], al, d[1], bl, n, o, n, e, s);
+  });
+}
+
+int p2e_add_many_nonnative_witness(int modulus, size_t n, int k, const uint64_t* summands, uint64_t* out,
+                                   uint32_t* err) {
+  if (k < 2) return set_error_msg("add_many needs k >= 2 summands");
+  HostIn ins[1] = {{summands, (size_t)k * NL}};
+  return run_host(n, ins, 1, out, NL + 1, err, [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* s) {
+    return p2e_add_many_nonnative_witness_dev(modulus, n, k, d[0], n, o, n, e, s);
+  });
+}
+
+int p2e_inv_nonnative_witness(int modulus, size_t n, const uint64_t* x, uint64_t* out, uint32_t* err) {
+  HostIn ins[1] = {{x, NL}};
+  return run_host(n, ins, 1, out, 2 * NL, err, [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* s) {
+    return p2e_inv_nonnative_witness_dev(modulus, n, d[0], n, o, n, e, s);
+  });
+}
+
+int p2e_glv_decompose_witness(size_t n, const uint64_t* k, uint64_t* out, uint32_t* err) {
+  HostIn ins[1] = {{k, NL}};
+  return run_host(n, ins, 1, out, 12, err, [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* s) {
+    return p2e_glv_decompose_witness_dev(n, d[0], n, o, n, e, s);
+  });
+}
+
+int p2e_biguint_div_rem_witness(size_t n, const uint64_t* a, int al, const uint64_t* b, int bl, uint64_t* out,
+                                uint32_t* err) {
+  if (al < 0 || al > DR_MAX || bl < 1 || bl > DR_MAX) return set_error_msg("div_rem: limb counts out of range");
+  const int div_limbs = (bl > al + 1) ? 0 : al - bl + 1;
+  HostIn ins[2] = {{a, (size_t)al}, {b, (size_t)bl}};
+  return run_host(n, ins, 2, out, (size_t)(div_limbs + bl), err,
+                  [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* s) {
+                    return p2e_biguint_div_rem_witness_dev(n, d[0], al, d[1], bl, n, o, n, e, s);
+                  });
+}
+
+int p2e_eval_mul_nonnative(int modulus, size_t n, const uint64_t* wires, uint64_t* out) {
+  HostIn ins[1] = {{wires, 6 * NL - 1}};
+  return run_host(n, ins, 1, out, 2 * NL - 1, nullptr, [&](const uint64_t** d, uint64_t* o, uint32_t*, void* s) {
+    return p2e_eval_mul_nonnative_dev(modulus, n, d[0], n, o, n, s);
+  });
+}
+
+int p2e_eval_check_sum(size_t n, const uint64_t* wires, uint64_t* out) {
+  HostIn ins[1] = {{wires, 4 * NL - 3}};
+  return run_host(n, ins, 1, out, 2 * NL - 1, nullptr, [&](const uint64_t** d, uint64_t* o, uint32_t*, void* s) {
+    return p2e_eval_check_sum_dev(n, d[0], n, o, n, s);
+  });
+}
+
+double p2e_bench_imad(int wide, int iters) {
+  if (ensure_ready()) return -1.0;
+  Context& c = ctx();
+  void* sink;
+  if (get_scratch(3, 64, &sink)) return -1.0;
+  const int blocks = c.sm_count * 8, threads = 256;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; rep++) {
+    cudaEventRecord(e0, c.stream);
+    if (wide)
+      k_imad_bench<true><<<blocks, threads, 0, c.stream>>>(iters, 12345u + rep, (u64*)sink);
+    else
+      k_imad_bench<false><<<blocks, threads, 0, c.stream>>>(iters, 12345u + rep, (u64*)sink);
+    cudaEventRecord(e1, c.stream);
+    if (cudaEventSynchronize(e1) != cudaSuccess) return -2.0;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  double ops = (double)blocks * threads * 8.0 * (double)iters;
+  return ops / (best * 1e-3) / 1e9;
+}
+
+}  // extern "C"
