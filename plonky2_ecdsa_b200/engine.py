@@ -1,0 +1,281 @@
+"""ctypes binding of libp2e.so (include/p2e.h) plus the thin host-side mirror of the reference's
+generator / gate surface for the hot path.
+
+There is NO CPU path here: if the CUDA library is missing or no device is visible every call
+raises.  numpy arrays are the host buffers of the C-ABI; torch tensors (device memory / streams)
+are accepted by the *_dev methods.
+
+Method names follow the reference: `mul_nonnative` -> MulNonnativeGenerator + CheckSumGenerator
+(gates/mul_nonnative.rs:249-324, 513-531), `add_nonnative` / `sub_nonnative` /
+`add_many_nonnative` / `inv_nonnative` -> the four generators of gadgets/nonnative.rs:599-895,
+`div_rem_biguint` -> BigUintDivRemGenerator (gadgets/biguint.rs:483-548), `decompose_secp256k1_scalar`
+-> GLVDecompositionGenerator (gadgets/glv.rs:107-171), `eval_mul_nonnative_gate` /
+`eval_check_sum_gate` -> Gate::eval_unfiltered_base_batch of the two in-tree gates
+(gates/mul_nonnative.rs:101-130, 411-427), `verify_secp256k1_message_witness` -> the witness of
+verify_secp256k1_message_circuit (gadgets/ecdsa.rs:30-53).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+SECP256K1_BASE = 0
+SECP256K1_SCALAR = 1
+
+ERR_U32 = 1
+ERR_LIMB_RANGE = 2
+ERR_NONCANONICAL = 4
+ERR_INVERSE_ZERO = 8
+ERR_CARRY_RANGE = 16
+ERR_DIV_ZERO = 32
+ERR_LIMBS_OVERFLOW = 64
+ERR_CONNECT = 128
+ERR_INTERNAL = 256
+
+MUL_OUT_R, MUL_OUT_Q, MUL_OUT_CHECK_SUM, MUL_OUT_CARRY, MUL_OUT_ROWS = 0, 9, 18, 35, 51
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libp2e.so")
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_sz = ctypes.c_size_t
+_vp = ctypes.c_void_p
+_int = ctypes.c_int
+
+# name -> (restype, argtypes); every symbol include/p2e.h declares
+SIGNATURES = {
+    "p2e_init": (_int, [_int]),
+    "p2e_shutdown": (None, []),
+    "p2e_last_error": (ctypes.c_char_p, []),
+    "p2e_device_count": (_int, []),
+    "p2e_synchronize": (_int, []),
+    "p2e_malloc": (_int, [ctypes.POINTER(_vp), _sz]),
+    "p2e_free": (_int, [_vp]),
+    "p2e_host_alloc": (_int, [ctypes.POINTER(_vp), _sz]),
+    "p2e_host_free": (_int, [_vp]),
+    "p2e_memcpy_h2d": (_int, [_vp, _vp, _sz]),
+    "p2e_memcpy_d2h": (_int, [_vp, _vp, _sz]),
+    "p2e_mul_nonnative_witness_dev": (_int, [_int, _sz, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_mul_nonnative_witness": (_int, [_int, _sz, _vp, _vp, _vp, _vp]),
+    "p2e_check_sum_witness_dev": (_int, [_sz, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_check_sum_witness": (_int, [_sz, _vp, _vp, _vp]),
+    "p2e_add_nonnative_witness_dev": (_int, [_int, _sz, _vp, _int, _vp, _int, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_add_nonnative_witness": (_int, [_int, _sz, _vp, _int, _vp, _int, _vp, _vp]),
+    "p2e_sub_nonnative_witness_dev": (_int, [_int, _sz, _vp, _int, _vp, _int, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_sub_nonnative_witness": (_int, [_int, _sz, _vp, _int, _vp, _int, _vp, _vp]),
+    "p2e_add_many_nonnative_witness_dev": (_int, [_int, _sz, _int, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_add_many_nonnative_witness": (_int, [_int, _sz, _int, _vp, _vp, _vp]),
+    "p2e_inv_nonnative_witness_dev": (_int, [_int, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_inv_nonnative_witness": (_int, [_int, _sz, _vp, _vp, _vp]),
+    "p2e_glv_decompose_witness_dev": (_int, [_sz, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_glv_decompose_witness": (_int, [_sz, _vp, _vp, _vp]),
+    "p2e_biguint_div_rem_witness_dev": (_int, [_sz, _vp, _int, _vp, _int, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_biguint_div_rem_witness": (_int, [_sz, _vp, _int, _vp, _int, _vp, _vp]),
+    "p2e_eval_mul_nonnative_dev": (_int, [_int, _sz, _vp, _sz, _vp, _sz, _vp]),
+    "p2e_eval_mul_nonnative": (_int, [_int, _sz, _vp, _vp]),
+    "p2e_eval_check_sum_dev": (_int, [_sz, _vp, _sz, _vp, _sz, _vp]),
+    "p2e_eval_check_sum": (_int, [_sz, _vp, _vp]),
+    "p2e_ecdsa_tape_slots": (_sz, []),
+    "p2e_ecdsa_tape_layout": (_sz, [_vp, _vp]),
+    "p2e_ecdsa_witness_dev": (_int, [_sz, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_ecdsa_witness": (_int, [_sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "p2e_glv_mul_tape_slots": (_sz, []),
+    "p2e_glv_mul_tape_layout": (_sz, [_vp, _vp]),
+    "p2e_glv_mul_witness_dev": (_int, [_sz, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_glv_mul_witness": (_int, [_sz, _vp, _vp, _vp, _vp, _vp]),
+    "p2e_bench_imad": (ctypes.c_double, [_int, _int]),
+}
+
+
+class P2EError(RuntimeError):
+    pass
+
+
+def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
+    """dlopen libp2e.so and bind every symbol of include/p2e.h.  Fails loudly when absent."""
+    if not os.path.exists(path):
+        raise P2EError(
+            f"{path} not found: build it with `python -m plonky2_ecdsa_b200.build` "
+            "(nvcc, sm_100a).  This package has no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def _ptr(a):
+    """numpy array / torch tensor / None -> raw address."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()          # torch tensor
+
+
+def _host_u64(a, rows=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.ndim != 2:
+        raise ValueError("expected a [rows][n] wire-major matrix")
+    if rows is not None and a.shape[0] != rows:
+        raise ValueError(f"expected {rows} rows, got {a.shape[0]}")
+    return a
+
+
+class Engine:
+    """One process == one GPU.  `Engine(device)` binds the process to that CUDA device."""
+
+    def __init__(self, device: int = 0, lib_path: str = LIB_PATH):
+        self.lib = load_library(lib_path)
+        rc = self.lib.p2e_init(device)
+        if rc != 0:
+            raise P2EError(f"p2e_init({device}) failed: {self.last_error()}")
+        self.device = device
+
+    # ---------------------------------------------------------------- plumbing
+    def last_error(self) -> str:
+        return (self.lib.p2e_last_error() or b"").decode()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise P2EError(f"p2e call failed ({rc}): {self.last_error()}")
+
+    def synchronize(self):
+        self._check(self.lib.p2e_synchronize())
+
+    def close(self):
+        self.lib.p2e_shutdown()
+
+    # ---------------------------------------------------------------- witness generation (host buffers)
+    def mul_nonnative(self, modulus, x, y):
+        """x, y: [9][n] wires -> (out [51][n] rows r|q|check_sum|carry, err [n])."""
+        x, y = _host_u64(x, 9), _host_u64(y, 9)
+        n = x.shape[1]
+        out = np.empty((MUL_OUT_ROWS, n), dtype=np.uint64)
+        err = np.empty(n, dtype=np.uint32)
+        self._check(self.lib.p2e_mul_nonnative_witness(modulus, n, _ptr(x), _ptr(y), _ptr(out), _ptr(err)))
+        return out, err
+
+    def check_sum(self, a):
+        a = _host_u64(a, 17)
+        n = a.shape[1]
+        b = np.empty((16, n), dtype=np.uint64)
+        err = np.empty(n, dtype=np.uint32)
+        self._check(self.lib.p2e_check_sum_witness(n, _ptr(a), _ptr(b), _ptr(err)))
+        return b, err
+
+    def _addsub(self, fn, modulus, a, b):
+        a, b = _host_u64(a), _host_u64(b)
+        n = a.shape[1] if a.shape[0] else b.shape[1]
+        out = np.empty((10, n), dtype=np.uint64)
+        err = np.empty(n, dtype=np.uint32)
+        self._check(fn(modulus, n, _ptr(a), a.shape[0], _ptr(b), b.shape[0], _ptr(out), _ptr(err)))
+        return out, err
+
+    def add_nonnative(self, modulus, a, b):
+        """a: [a_limbs][n], b: [b_limbs][n] -> (out [10][n] = sum[9], overflow; err)."""
+        return self._addsub(self.lib.p2e_add_nonnative_witness, modulus, a, b)
+
+    def sub_nonnative(self, modulus, a, b):
+        return self._addsub(self.lib.p2e_sub_nonnative_witness, modulus, a, b)
+
+    def add_many_nonnative(self, modulus, summands):
+        """summands: [k][9][n] -> (out [10][n], err)."""
+        s = np.ascontiguousarray(summands, dtype=np.uint64)
+        k, nl, n = s.shape
+        assert nl == 9
+        out = np.empty((10, n), dtype=np.uint64)
+        err = np.empty(n, dtype=np.uint32)
+        self._check(self.lib.p2e_add_many_nonnative_witness(modulus, n, k, _ptr(s), _ptr(out), _ptr(err)))
+        return out, err
+
+    def inv_nonnative(self, modulus, x):
+        """x: [9][n] -> (out [18][n] = div[9], inv[9]; err)."""
+        x = _host_u64(x, 9)
+        n = x.shape[1]
+        out = np.empty((18, n), dtype=np.uint64)
+        err = np.empty(n, dtype=np.uint32)
+        self._check(self.lib.p2e_inv_nonnative_witness(modulus, n, _ptr(x), _ptr(out), _ptr(err)))
+        return out, err
+
+    def decompose_secp256k1_scalar(self, k):
+        """k: [9][n] -> (out [12][n] = k1[5], k2[5], k1_neg, k2_neg; err)."""
+        k = _host_u64(k, 9)
+        n = k.shape[1]
+        out = np.empty((12, n), dtype=np.uint64)
+        err = np.empty(n, dtype=np.uint32)
+        self._check(self.lib.p2e_glv_decompose_witness(n, _ptr(k), _ptr(out), _ptr(err)))
+        return out, err
+
+    def div_rem_biguint(self, a, b):
+        """a: [a_limbs][n], b: [b_limbs][n] -> (div [div_limbs][n], rem [b_limbs][n], err)."""
+        a, b = _host_u64(a), _host_u64(b)
+        al, bl = a.shape[0], b.shape[0]
+        n = b.shape[1]
+        dl = 0 if bl > al + 1 else al - bl + 1
+        out = np.empty((dl + bl, n), dtype=np.uint64)
+        err = np.empty(n, dtype=np.uint32)
+        self._check(self.lib.p2e_biguint_div_rem_witness(n, _ptr(a), al, _ptr(b), bl, _ptr(out), _ptr(err)))
+        return out[:dl], out[dl:], err
+
+    # ---------------------------------------------------------------- constraint evaluation (host buffers)
+    def eval_mul_nonnative_gate(self, modulus, wires):
+        """wires: [53][n_rows] -> constraints [17][n_rows]."""
+        w = _host_u64(wires, 53)
+        n = w.shape[1]
+        out = np.empty((17, n), dtype=np.uint64)
+        self._check(self.lib.p2e_eval_mul_nonnative(modulus, n, _ptr(w), _ptr(out)))
+        return out
+
+    def eval_check_sum_gate(self, wires):
+        """wires: [33][n_rows] -> constraints [17][n_rows]."""
+        w = _host_u64(wires, 33)
+        n = w.shape[1]
+        out = np.empty((17, n), dtype=np.uint64)
+        self._check(self.lib.p2e_eval_check_sum(n, _ptr(w), _ptr(out)))
+        return out
+
+    # ---------------------------------------------------------------- ECDSA circuit witness
+    def ecdsa_tape_layout(self):
+        cnt = self.lib.p2e_ecdsa_tape_layout(None, None)
+        kinds = np.empty(cnt, dtype=np.uint32)
+        offs = np.empty(cnt, dtype=np.uint32)
+        self.lib.p2e_ecdsa_tape_layout(_ptr(kinds), _ptr(offs))
+        return kinds, offs, int(self.lib.p2e_ecdsa_tape_slots())
+
+    def verify_secp256k1_message_witness(self, msg, r, s, pkx, pky):
+        """msg, r, s, pkx, pky: [9][n] -> (witness [slots][n] in tape order, err [n])."""
+        ins = [_host_u64(a, 9) for a in (msg, r, s, pkx, pky)]
+        n = ins[0].shape[1]
+        slots = int(self.lib.p2e_ecdsa_tape_slots())
+        out = np.empty((slots, n), dtype=np.uint64)
+        err = np.empty(n, dtype=np.uint32)
+        self._check(self.lib.p2e_ecdsa_witness(n, *[_ptr(a) for a in ins], _ptr(out), _ptr(err)))
+        return out, err
+
+    def glv_mul_tape_layout(self):
+        cnt = self.lib.p2e_glv_mul_tape_layout(None, None)
+        kinds = np.empty(cnt, dtype=np.uint32)
+        offs = np.empty(cnt, dtype=np.uint32)
+        self.lib.p2e_glv_mul_tape_layout(_ptr(kinds), _ptr(offs))
+        return kinds, offs, int(self.lib.p2e_glv_mul_tape_slots())
+
+    def glv_mul_witness(self, k, px, py):
+        ins = [_host_u64(a, 9) for a in (k, px, py)]
+        n = ins[0].shape[1]
+        slots = int(self.lib.p2e_glv_mul_tape_slots())
+        out = np.empty((slots, n), dtype=np.uint64)
+        err = np.empty(n, dtype=np.uint32)
+        self._check(self.lib.p2e_glv_mul_witness(n, *[_ptr(a) for a in ins], _ptr(out), _ptr(err)))
+        return out, err
+
+    # ---------------------------------------------------------------- measurement
+    def bench_imad(self, wide: bool, iters: int = 4096) -> float:
+        v = self.lib.p2e_bench_imad(1 if wide else 0, iters)
+        if v < 0:
+            raise P2EError(f"p2e_bench_imad failed: {self.last_error()}")
+        return v

@@ -1,0 +1,123 @@
+"""CPU tier: the device arithmetic cores of csrc/p2e_field.cuh, compiled for the host by
+tests/hostcheck, against the oracle.  (The CUDA kernels run the very same functions.)"""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+from oracle import spec as S
+from plonky2_ecdsa_b200 import workload as W
+from tests import util as U
+
+u64p = ctypes.POINTER(ctypes.c_uint64)
+u32p = ctypes.POINTER(ctypes.c_uint32)
+
+
+def P(a):
+    return a.ctypes.data_as(u64p if a.dtype == np.uint64 else u32p)
+
+
+def aos(m):
+    """wire-major [rows][n] -> instance-major [n][rows] (hostcheck's layout)."""
+    return np.ascontiguousarray(m.T)
+
+
+@pytest.mark.parametrize("modulus", [0, 1])
+def test_mul_witness_core(hostcheck, modulus):
+    n = 1500
+    x, y = W.mulmod_workload(n, modulus, seed=W.SEED + 17 * modulus)
+    out = np.zeros((n, 51), dtype=np.uint64)
+    err = np.zeros(n, dtype=np.uint32)
+    hostcheck.hc_mul_witness(modulus, ctypes.c_size_t(n), P(aos(x)), P(aos(y)), P(out), P(err))
+    eo, ee = U.expect_mul(x, y, modulus)
+    assert np.array_equal(out.T, eo)
+    assert np.array_equal(err, ee)
+    assert (ee != 0).any() and (ee == 0).any()      # both valid rows and would-panic rows covered
+
+
+@pytest.mark.parametrize("modulus", [0, 1])
+def test_mul_wire_checks(hostcheck, modulus):
+    x = np.zeros((3, 9), dtype=np.uint64)
+    y = np.ones((3, 9), dtype=np.uint64)
+    x[0, 0] = 1 << 29
+    x[1, 3] = 1 << 32
+    x[2, 8] = (1 << 64) - (1 << 32)       # p_GL - 1
+    out = np.zeros((3, 51), dtype=np.uint64)
+    err = np.zeros(3, dtype=np.uint32)
+    hostcheck.hc_mul_witness(modulus, ctypes.c_size_t(3), P(x), P(y), P(out), P(err))
+    assert list(err) == [2, 1, 1] and not out.any()
+
+
+@pytest.mark.parametrize("modulus", [0, 1])
+@pytest.mark.parametrize("is_sub", [0, 1])
+def test_addsub_core(hostcheck, modulus, is_sub):
+    M = S.MODULI[modulus]
+    rng = random.Random(100 + modulus * 2 + is_sub)
+    vals = [0, 1, M - 1, M, (1 << 256) - 1, M + 1, 2, M // 2, M // 2 + 1]
+    pairs = [(a, b) for a in vals for b in vals] + [(M - 5, 5), (5, M - 5), ((1 << 256) + 3, 5), (7, (1 << 261) - 1)]
+    pairs += [(rng.randrange(1 << 256), rng.randrange(1 << 256)) for _ in range(800)]
+    a = W.ints_to_limbs([p[0] for p in pairs])
+    b = W.ints_to_limbs([p[1] for p in pairs])
+    n = len(pairs)
+    out = np.zeros((n, 10), dtype=np.uint64)
+    err = np.zeros(n, dtype=np.uint32)
+    hostcheck.hc_addsub(modulus, is_sub, ctypes.c_size_t(n), P(aos(a)), P(aos(b)), P(out), P(err))
+    eo, ee = U.expect_addsub(a, b, modulus, is_sub)
+    assert np.array_equal(out.T, eo) and np.array_equal(err, ee)
+
+
+@pytest.mark.parametrize("modulus", [0, 1])
+def test_inverse_core(hostcheck, modulus):
+    M = S.MODULI[modulus]
+    rng = random.Random(200 + modulus)
+    xs = [1, 2, M - 1, M + 1, (1 << 256) - 1, 0, M, 1 << 256] + [rng.randrange(1 << 256) for _ in range(150)]
+    x = W.ints_to_limbs(xs)
+    n = len(xs)
+    out = np.zeros((n, 18), dtype=np.uint64)
+    err = np.zeros(n, dtype=np.uint32)
+    hostcheck.hc_inv(modulus, ctypes.c_size_t(n), P(aos(x)), P(out), P(err))
+    eo, ee = U.expect_inv(x, modulus)
+    assert np.array_equal(out.T, eo) and np.array_equal(err, ee)
+
+
+def test_glv_core(hostcheck):
+    rng = random.Random(300)
+    n_ = S.SECP_N
+    ks = [0, 1, n_ - 1, n_, n_ // 2, n_ // 2 + 1, (1 << 256) - 1] + [rng.randrange(1 << 256) for _ in range(1500)]
+    k = W.ints_to_limbs(ks)
+    n = len(ks)
+    out = np.zeros((n, 12), dtype=np.uint64)
+    err = np.zeros(n, dtype=np.uint32)
+    hostcheck.hc_glv(ctypes.c_size_t(n), P(aos(k)), P(out), P(err))
+    eo, ee = U.expect_glv(k)
+    assert np.array_equal(out.T, eo) and np.array_equal(err, ee)
+
+
+def test_check_sum_core(hostcheck):
+    x, y = W.mulmod_workload(600, 0, seed=77)
+    eo, _ = U.expect_mul(x, y, 0)
+    a = np.ascontiguousarray(eo[18:35])
+    n = a.shape[1]
+    # add rows of arbitrary field elements (always the slow path)
+    a[:, :40] = W.random_goldilocks(5, 17, 40)
+    b = np.zeros((n, 16), dtype=np.uint64)
+    err = np.zeros(n, dtype=np.uint32)
+    hostcheck.hc_check_sum(ctypes.c_size_t(n), P(aos(a)), P(b), P(err))
+    for i in range(n):
+        eb, panic = S.check_sum_gen_nopanic(U.col(a, i))
+        assert [int(v) for v in b[i]] == eb and bool(err[i] & 16) == panic
+
+
+def test_goldilocks_ops(hostcheck):
+    rng = random.Random(9)
+    p = S.GL_P
+    edge = [0, 1, p - 1, p - 2, 1 << 32, (1 << 32) - 1, (1 << 63), p >> 1]
+    cases = [(a, b) for a in edge for b in edge] + [(rng.randrange(p), rng.randrange(p)) for _ in range(5000)]
+    for a, b in cases:
+        assert hostcheck.hc_gl_mul(a, b) == a * b % p
+        assert hostcheck.hc_gl_add(a, b) == (a + b) % p
+        assert hostcheck.hc_gl_sub(a, b) == (a - b) % p
+    for _ in range(2000):
+        lo, hi = rng.getrandbits(64), rng.getrandbits(64)
+        assert hostcheck.hc_gl_reduce128(lo, hi) == ((hi << 64) | lo) % p
