@@ -121,8 +121,10 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = pkg.Engine(local_rank)
     lib = eng.lib
-    st = torch.cuda.current_stream()
+    st = torch.cuda.Stream()              # a real (non-NULL) stream: NULL would select the library's own
+    torch.cuda.set_stream(st)
     stream_ptr = st.cuda_stream
+    assert stream_ptr != 0
     peak_gbs, peak_kind = load_peaks()
 
     def dev(a):

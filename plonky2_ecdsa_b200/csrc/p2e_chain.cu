@@ -1,26 +1,740 @@
-// p2e_chain.cu -- ECDSA / glv_mul witness tapes (placeholder until the chain kernels land).
+// p2e_chain.cu -- witness generation for whole gadget chains (verify_secp256k1_message_circuit,
+// glv_mul) from the host-built tape (p2e_tape.h).
+//
+// The reference runs 312 Fermat ladders per signature, one per curve_add / curve_double
+// (gadgets/curve.rs:160-223 -> gadgets/nonnative.rs:857-872).  Every one of those inverses is
+// unique mod p, so it can be obtained differently without changing a single witness bit:
+//   K0 k_prep          per signature: interpreter over the non-curve generators (prep ops)
+//   K1 k_chain_replay  per signature: replays all curve ops in Jacobian coordinates (no inversion)
+//   K2 k_chain_invert  per signature: ONE field inversion for all Z's (Montgomery's trick)
+//   K3 k_chain_affine  per (signature, point): affine x, y and Z^3
+//   K4 k_chain_expand  per (signature, curve op): v_inv = Z1^3 Z2^3 / Z3 (add) or Z1^4 / Z3 (double),
+//                      then every generator of that curve op with the cores of p2e_field.cuh
+//   K5 k_chain_checks  per signature: the gadget's connect_* constraints -> ERR_CONNECT
+// Signatures are the fastest-varying index everywhere (coalesced wire-major accesses).
+#include <mutex>
+#include <vector>
+
 #include "../../include/p2e.h"
 #include "p2e_common.h"
+#include "p2e_field.cuh"
+#include "p2e_tape.h"
+
+namespace p2e {
+
+constexpr int32_t PID_INPUT_BASE = 1 << 19;
+
+struct DevTape {
+  const PrepOp* prep;
+  const PtOp* ptops;
+  const Check* checks;
+  const InputPoint* in_points;
+  const u32* const_limbs;
+  const u32* const_points;
+  int n_prep, n_ptops, n_checks, n_in_points;
+  int32_t pre_pid[16];
+  Ref fixed_scalar, msm_k1, msm_k2;
+  u32 fixed_table_base;
+};
+
+struct ChainArgs {
+  DevTape t;
+  size_t n;                 // signatures in this chunk
+  const u64* in[8];         // input nonnative values, [9][is] each
+  size_t is;
+  u64* out;                 // [n_slots][os]
+  size_t os;
+  u32* err;
+  // scratch (stride = cap)
+  size_t cap;
+  u32 *JX, *JY, *JZ;        // [n_ptops + n_in_points][9][cap]
+  u32* ZINV;                // [n_ptops][9][cap]
+  u32 *AX, *AY, *ZC;        // [n_ptops + n_in_points][9][cap]
+  int32_t *SRC1, *SRC2;     // [n_ptops][cap]
+  uint8_t* FLG;             // [n_ptops][cap]
+};
+
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 load_wire(const ChainArgs& A, uint8_t space, u32 off, size_t i) {
+  if (space == SP_OUT) return A.out[(size_t)off * A.os + i];
+  if (space == SP_IN) return A.in[off / 9][(size_t)(off % 9) * A.is + i];
+  return A.t.const_limbs[off];
+}
+
+__device__ __forceinline__ void load_ref(const ChainArgs& A, const Ref& r, size_t i, u64 (&w)[NL]) {
+  u64 bm = 1;
+  if (r.bspace != SP_NONE) bm = (load_wire(A, r.bspace, r.boff, i) ^ (u64)r.binv) & 1;
+#pragma unroll
+  for (int l = 0; l < NL; l++) w[l] = (l < r.nl) ? load_wire(A, r.space, r.off + l, i) * bm : 0;
+}
+
+__device__ __forceinline__ void st9(const ChainArgs& A, u32 slot, size_t i, const u32 (&v)[NL]) {
+#pragma unroll
+  for (int l = 0; l < NL; l++) A.out[(size_t)(slot + l) * A.os + i] = v[l];
+}
+__device__ __forceinline__ void st1(const ChainArgs& A, u32 slot, size_t i, u64 v) { A.out[(size_t)slot * A.os + i] = v; }
+
+// MulNonnative row tuple (r, q, check_sum) followed by the CheckSum tuple (b): 51 slots
+template <class MOD>
+__device__ __forceinline__ u32 do_mul(const ChainArgs& A, u32 slot, size_t i, const u32 (&x)[NL], const u32 (&y)[NL],
+                                      u32 (&r)[NL]) {
+  u32 q[NL];
+  u64 cs[2 * NL - 1], b[2 * NL - 2];
+  u32 e = mul_witness_core<MOD>(x, y, r, q, cs, b);
+  st9(A, slot, i, r);
+  st9(A, slot + 9, i, q);
+#pragma unroll
+  for (int l = 0; l < 2 * NL - 1; l++) st1(A, slot + 18 + l, i, cs[l]);
+#pragma unroll
+  for (int l = 0; l < 2 * NL - 2; l++) st1(A, slot + 35 + l, i, b[l]);
+  return e;
+}
+template <class MOD>
+__device__ __forceinline__ void do_add(const ChainArgs& A, u32 slot, size_t i, const u32 (&a)[NL], const u32 (&b)[NL],
+                                       u32 (&r)[NL]) {
+  u32 ov = add_witness_core<MOD>(a, b, r);
+  st9(A, slot, i, r);
+  st1(A, slot + 9, i, ov);
+}
+template <class MOD>
+__device__ __forceinline__ void do_sub(const ChainArgs& A, u32 slot, size_t i, const u32 (&a)[NL], const u32 (&b)[NL],
+                                       u32 (&r)[NL]) {
+  u32 ov = sub_witness_core<MOD>(a, b, r);
+  st9(A, slot, i, r);
+  st1(A, slot + 9, i, ov);
+}
+// NonNativeInverseGenerator tuple (div, inv) when the inverse is already known
+template <class MOD>
+__device__ __forceinline__ u32 do_inv_known(const ChainArgs& A, u32 slot, size_t i, const u32 (&xc)[NL],
+                                            const u32 (&inv)[NL]) {
+  u32 div[NL];
+  u32 e = inv_div_core<MOD>(xc, inv, div);
+  st9(A, slot, i, div);
+  st9(A, slot + 9, i, inv);
+  return e;
+}
+
+// ------------------------------------------------------------------------------------------
+// K0: prep-op interpreter
+template <class MOD>
+__device__ u32 prep_exec(const ChainArgs& A, const PrepOp& op, size_t i) {
+  u64 aw[NL], bw[NL];
+  load_ref(A, op.a, i, aw);
+  load_ref(A, op.b, i, bw);
+  u32 a[NL], b[NL], r[NL];
+  u32 e = 0;
+  switch (op.opcode) {
+    case OP_MUL: {
+      e = load_mul_wires(aw, a) | load_mul_wires(bw, b);
+      if (e == 0) {
+        e = do_mul<MOD>(A, op.slot, i, a, b, r);
+      } else {
+        for (int l = 0; l < 51; l++) st1(A, op.slot + l, i, 0);
+      }
+      break;
+    }
+    case OP_ADD:
+    case OP_SUB: {
+      e = load_canon<MOD>(aw, a) | load_canon<MOD>(bw, b);
+      if (e) { set_zero9(a); set_zero9(b); }
+      if (op.opcode == OP_ADD) do_add<MOD>(A, op.slot, i, a, b, r);
+      else do_sub<MOD>(A, op.slot, i, a, b, r);
+      break;
+    }
+    case OP_INV: {
+      e = load_canon<MOD>(aw, a);
+      if (e == 0 && is_zero9(a)) e = ERR_INVERSE_ZERO;
+      u32 inv[NL];
+      set_zero9(inv);
+      if (e == 0) {
+        inv_mod<MOD>(a, inv);
+        e |= do_inv_known<MOD>(A, op.slot, i, a, inv);
+      } else {
+        st9(A, op.slot, i, inv);
+        st9(A, op.slot + 9, i, inv);
+      }
+      break;
+    }
+    default: break;
+  }
+  return e;
+}
+
+__global__ void __launch_bounds__(32) k_prep(ChainArgs A) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  u32 err = 0;
+  for (int k = 0; k < A.t.n_prep; k++) {
+    const PrepOp op = A.t.prep[k];
+    if (op.opcode == OP_GLV) {
+      u64 w[NL];
+      load_ref(A, op.a, i, w);
+      u32 kc[NL], k1[NL], k2[NL], n1 = 0, n2 = 0;
+      u32 e = load_canon<ModN>(w, kc);
+      set_zero9(k1);
+      set_zero9(k2);
+      if (e == 0) {
+        glv_decompose_core(kc, k1, k2, n1, n2);
+        u32 hi = 0;
+        for (int l = 5; l < NL; l++) hi |= k1[l] | k2[l];
+        if (hi) e |= ERR_LIMBS_OVERFLOW;
+      }
+      for (int l = 0; l < 5; l++) {
+        st1(A, op.slot + l, i, k1[l]);
+        st1(A, op.slot + 5 + l, i, k2[l]);
+      }
+      st1(A, op.slot + 10, i, n1);
+      st1(A, op.slot + 11, i, n2);
+      err |= e;
+    } else if (op.mod == 0) {
+      err |= prep_exec<ModP>(A, op, i);
+    } else {
+      err |= prep_exec<ModN>(A, op, i);
+    }
+  }
+  A.err[i] = err;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: Jacobian replay (secp256k1: a = 0).  x = X/Z^2, y = Y/Z^3.
+struct Jac {
+  u32 X[NL], Y[NL], Z[NL];
+};
+
+__device__ __forceinline__ int pt_index(const ChainArgs& A, int32_t pid) {
+  return pid < PID_INPUT_BASE ? pid : A.t.n_ptops + (pid - PID_INPUT_BASE);
+}
+
+__device__ __forceinline__ void ld9(const u32* __restrict__ base, int idx, size_t cap, size_t i, u32 (&v)[NL]) {
+#pragma unroll
+  for (int l = 0; l < NL; l++) v[l] = base[((size_t)idx * NL + l) * cap + i];
+}
+__device__ __forceinline__ void sv9(u32* __restrict__ base, int idx, size_t cap, size_t i, const u32 (&v)[NL]) {
+#pragma unroll
+  for (int l = 0; l < NL; l++) base[((size_t)idx * NL + l) * cap + i] = v[l];
+}
+
+__device__ __forceinline__ void load_jac(const ChainArgs& A, int32_t pid, size_t i, Jac& P) {
+  if (pid >= PID_CONST_BASE) {
+    const u32* c = A.t.const_points + (size_t)(pid - PID_CONST_BASE) * 18;
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      P.X[l] = c[l];
+      P.Y[l] = c[NL + l];
+      P.Z[l] = (l == 0) ? 1u : 0u;
+    }
+  } else {
+    int idx = pt_index(A, pid);
+    ld9(A.JX, idx, A.cap, i, P.X);
+    ld9(A.JY, idx, A.cap, i, P.Y);
+    ld9(A.JZ, idx, A.cap, i, P.Z);
+  }
+}
+
+// R = P + Q, Z3 = Z1*Z2*H with H = X2*Z1^2 - X1*Z2^2 (so x2 - x1 = Z3 / (Z1^3 Z2^3))
+__device__ __noinline__ void jac_add(const Jac& P, const Jac& Q, Jac& R) {
+  u32 z1z1[NL], z2z2[NL], u1[NL], u2[NL], s1[NL], s2[NL], h[NL], r[NL], t[NL], hh[NL], hhh[NL], v[NL];
+  sqrmod<ModP>(P.Z, z1z1);
+  sqrmod<ModP>(Q.Z, z2z2);
+  mulmod<ModP>(P.X, z2z2, u1);
+  mulmod<ModP>(Q.X, z1z1, u2);
+  mulmod<ModP>(P.Y, Q.Z, t);
+  mulmod<ModP>(t, z2z2, s1);
+  mulmod<ModP>(Q.Y, P.Z, t);
+  mulmod<ModP>(t, z1z1, s2);
+  submod<ModP>(u2, u1, h);
+  submod<ModP>(s2, s1, r);
+  sqrmod<ModP>(h, hh);
+  mulmod<ModP>(h, hh, hhh);
+  mulmod<ModP>(u1, hh, v);
+  // X3 = r^2 - hhh - 2v
+  sqrmod<ModP>(r, t);
+  submod<ModP>(t, hhh, u2);
+  addmod<ModP>(v, v, t);
+  submod<ModP>(u2, t, R.X);
+  // Y3 = r (v - X3) - s1 hhh
+  submod<ModP>(v, R.X, t);
+  mulmod<ModP>(r, t, u2);
+  mulmod<ModP>(s1, hhh, t);
+  submod<ModP>(u2, t, R.Y);
+  // Z3 = Z1 Z2 h
+  mulmod<ModP>(P.Z, Q.Z, t);
+  mulmod<ModP>(t, h, R.Z);
+}
+
+// R = 2P, Z3 = 2*Y1*Z1 (so 2y = Z3 / Z1^4)
+__device__ __noinline__ void jac_dbl(const Jac& P, Jac& R) {
+  u32 xx[NL], yy[NL], yyyy[NL], s[NL], m[NL], t[NL], t2[NL];
+  sqrmod<ModP>(P.X, xx);
+  sqrmod<ModP>(P.Y, yy);
+  sqrmod<ModP>(yy, yyyy);
+  mulmod<ModP>(P.X, yy, t);
+  addmod<ModP>(t, t, t2);
+  addmod<ModP>(t2, t2, s);             // S = 4 X YY
+  addmod<ModP>(xx, xx, t);
+  addmod<ModP>(t, xx, m);              // M = 3 XX
+  sqrmod<ModP>(m, t);
+  addmod<ModP>(s, s, t2);
+  submod<ModP>(t, t2, R.X);            // X3 = M^2 - 2S
+  submod<ModP>(s, R.X, t);
+  mulmod<ModP>(m, t, t2);
+  addmod<ModP>(yyyy, yyyy, t);
+  addmod<ModP>(t, t, yy);
+  addmod<ModP>(yy, yy, t);             // 8 YYYY
+  mulmod<ModP>(P.Y, P.Z, xx);
+  submod<ModP>(t2, t, R.Y);            // Y3 = M (S - X3) - 8 YYYY
+  addmod<ModP>(xx, xx, R.Z);           // Z3 = 2 Y1 Z1
+}
+
+// digit of `bits` bits at bit position `pos` of a little-endian 29-bit-limb value (nl limbs)
+__device__ __forceinline__ u32 digit_at(const u32* limbs, int nl, int pos, int bits) {
+  int l = pos / LB, sh = pos % LB;
+  u32 lo = l < nl ? limbs[l] : 0u;
+  u32 hi = (l + 1) < nl ? limbs[l + 1] : 0u;
+  u64 v = ((u64)hi << LB) | lo;
+  return (u32)(v >> sh) & ((1u << bits) - 1u);
+}
+
+__device__ __forceinline__ u32 load_scalar_limbs(const ChainArgs& A, const Ref& r, size_t i, u32* limbs) {
+  // split_le_base::<2>(limb, 29) asserts each limb fits 29 bits (split_nonnative.rs:29-37)
+  u32 e = 0;
+  for (int l = 0; l < NL; l++) {
+    u64 w = (l < r.nl && r.space != SP_NONE) ? load_wire(A, r.space, r.off + l, i) : 0;
+    if (w >> LB) e |= ERR_LIMB_RANGE;
+    limbs[l] = (u32)w & LMASK;
+  }
+  return e;
+}
+
+__global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  u32 err = 0;
+  // per-signature affine input points (Z = 1)
+  for (int j = 0; j < A.t.n_in_points; j++) {
+    u64 w[NL];
+    u32 x[NL], y[NL], one[NL];
+    load_ref(A, A.t.in_points[j].x, i, w);
+    err |= load_canon<ModP>(w, x);
+    load_ref(A, A.t.in_points[j].y, i, w);
+    err |= load_canon<ModP>(w, y);
+    set_zero9(one);
+    one[0] = 1;
+    int idx = A.t.n_ptops + j;
+    sv9(A.JX, idx, A.cap, i, x);
+    sv9(A.JY, idx, A.cap, i, y);
+    sv9(A.JZ, idx, A.cap, i, one);
+    sv9(A.AX, idx, A.cap, i, x);
+    sv9(A.AY, idx, A.cap, i, y);
+    sv9(A.ZC, idx, A.cap, i, one);
+  }
+  u32 fs[NL], k1[NL], k2[NL];
+  err |= load_scalar_limbs(A, A.t.fixed_scalar, i, fs);
+  err |= load_scalar_limbs(A, A.t.msm_k1, i, k1);
+  err |= load_scalar_limbs(A, A.t.msm_k2, i, k2);
+
+  int32_t cur = -1;
+  for (int k = 0; k < A.t.n_ptops; k++) {
+    const PtOp op = A.t.ptops[k];
+    int32_t p1 = (op.flags & PF_P1_CUR) ? cur : op.p1;
+    int32_t p2 = (op.flags & PF_P2_CUR) ? cur : op.p2;
+    u32 flag = 1;
+    if (op.type == PT_CADD_FIXED) {
+      u32 d = digit_at(fs, NL, 4 * op.aux, 4);
+      p2 = PID_CONST_BASE + (int32_t)(A.t.fixed_table_base + 16u * op.aux + d);
+      flag = d != 0;
+    } else if (op.type == PT_CADD_MSM) {
+      u32 d = 4u * digit_at(k2, 5, 2 * op.aux, 2) + digit_at(k1, 5, 2 * op.aux, 2);
+      p2 = A.t.pre_pid[d];
+      flag = d != 0;
+    }
+    Jac P, R;
+    load_jac(A, p1, i, P);
+    if (op.type == PT_DBL) {
+      jac_dbl(P, R);
+      p2 = p1;
+    } else {
+      Jac Q;
+      load_jac(A, p2, i, Q);
+      jac_add(P, Q, R);
+    }
+    sv9(A.JX, k, A.cap, i, R.X);
+    sv9(A.JY, k, A.cap, i, R.Y);
+    sv9(A.JZ, k, A.cap, i, R.Z);
+    A.SRC1[(size_t)k * A.cap + i] = p1;
+    A.SRC2[(size_t)k * A.cap + i] = p2;
+    A.FLG[(size_t)k * A.cap + i] = (uint8_t)flag;
+    if (op.flags & PF_SET_CUR) cur = flag ? k : p1;
+  }
+  if (err) A.err[i] |= err;
+}
+
+// K2: one inversion per signature for all Z3's
+__global__ void __launch_bounds__(32) k_chain_invert(ChainArgs A) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int n = A.t.n_ptops;
+  u32 run[NL], z[NL], t[NL];
+  set_zero9(run);
+  run[0] = 1;
+  for (int k = 0; k < n; k++) {
+    sv9(A.ZINV, k, A.cap, i, run);      // prefix product of Z_0..Z_{k-1}
+    ld9(A.JZ, k, A.cap, i, z);
+    mulmod<ModP>(run, z, t);
+    copy9(t, run);
+  }
+  if (is_zero9(run)) {
+    // some curve op had x1 == x2 (or y == 0): the reference's inverse() panics
+    A.err[i] |= ERR_INVERSE_ZERO;
+    set_zero9(t);
+    for (int k = 0; k < n; k++) sv9(A.ZINV, k, A.cap, i, t);
+    return;
+  }
+  u32 inv[NL];
+  inv_p(run, inv);
+  for (int k = n - 1; k >= 0; k--) {
+    u32 pre[NL], zi[NL];
+    ld9(A.ZINV, k, A.cap, i, pre);
+    ld9(A.JZ, k, A.cap, i, z);
+    mulmod<ModP>(inv, pre, zi);
+    sv9(A.ZINV, k, A.cap, i, zi);
+    mulmod<ModP>(inv, z, t);
+    copy9(t, inv);
+  }
+}
+
+// K3: affine coordinates and Z^3 of every computed point
+__global__ void __launch_bounds__(128) k_chain_affine(ChainArgs A) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int k = blockIdx.y;
+  if (i >= A.n) return;
+  u32 zi[NL], zi2[NL], zi3[NL], v[NL], r[NL];
+  ld9(A.ZINV, k, A.cap, i, zi);
+  sqrmod<ModP>(zi, zi2);
+  mulmod<ModP>(zi2, zi, zi3);
+  ld9(A.JX, k, A.cap, i, v);
+  mulmod<ModP>(v, zi2, r);
+  sv9(A.AX, k, A.cap, i, r);
+  ld9(A.JY, k, A.cap, i, v);
+  mulmod<ModP>(v, zi3, r);
+  sv9(A.AY, k, A.cap, i, r);
+  ld9(A.JZ, k, A.cap, i, v);
+  sqrmod<ModP>(v, zi2);
+  mulmod<ModP>(zi2, v, r);
+  sv9(A.ZC, k, A.cap, i, r);
+}
+
+// K4: expand one curve op into all of its generators' output tuples
+__device__ __forceinline__ void load_affine(const ChainArgs& A, int32_t pid, size_t i, u32 (&x)[NL], u32 (&y)[NL],
+                                            u32 (&zc)[NL]) {
+  if (pid >= PID_CONST_BASE) {
+    const u32* c = A.t.const_points + (size_t)(pid - PID_CONST_BASE) * 18;
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      x[l] = c[l];
+      y[l] = c[NL + l];
+      zc[l] = (l == 0) ? 1u : 0u;
+    }
+  } else {
+    int idx = pt_index(A, pid);
+    ld9(A.AX, idx, A.cap, i, x);
+    ld9(A.AY, idx, A.cap, i, y);
+    ld9(A.ZC, idx, A.cap, i, zc);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_chain_expand(ChainArgs A) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int k = blockIdx.y;
+  if (i >= A.n) return;
+  const PtOp op = A.t.ptops[k];
+  const u32 s0 = op.slot;
+  int32_t p1 = A.SRC1[(size_t)k * A.cap + i];
+  u32 e = 0;
+  u32 x1[NL], y1[NL], zc1[NL], zinv[NL], vinv[NL], t[NL];
+  load_affine(A, p1, i, x1, y1, zc1);
+  ld9(A.ZINV, k, A.cap, i, zinv);
+  if (op.type == PT_DBL) {
+    // (2y)^-1 = Z1^4 / Z3
+    u32 z1[NL];
+    if (p1 >= PID_CONST_BASE) { set_zero9(z1); z1[0] = 1; }
+    else ld9(A.JZ, pt_index(A, p1), A.cap, i, z1);
+    mulmod<ModP>(zc1, z1, t);
+    mulmod<ModP>(t, zinv, vinv);
+    u32 dy[NL], xx[NL], tr[NL], lam[NL], lam2[NL], xd[NL], x3[NL], xdiff[NL], lx[NL], y3[NL];
+    do_add<ModP>(A, s0 + 0, i, y1, y1, dy);                       // double_y
+    canon9<ModP>(dy);
+    if (is_zero9(dy)) e |= ERR_INVERSE_ZERO;
+    e |= do_inv_known<ModP>(A, s0 + 10, i, dy, vinv);             // inv_double_y
+    e |= do_mul<ModP>(A, s0 + 28, i, x1, x1, xx);                 // x_squared
+    {                                                             // add_many([xx, xx, xx, A = 0])
+      u32 acc[NL], sum[NL], ov = 0;
+      copy9(xx, acc);
+#pragma unroll
+      for (int rep = 0; rep < 2; rep++) {
+        add9(acc, xx, sum);
+        if (geq_mod<ModP>(sum)) { sub_mod9<ModP>(sum, acc); ov++; }
+        else copy9(sum, acc);
+      }
+      copy9(acc, tr);
+      st9(A, s0 + 79, i, tr);
+      st1(A, s0 + 88, i, ov);
+    }
+    e |= do_mul<ModP>(A, s0 + 89, i, tr, vinv, lam);              // lambda
+    e |= do_mul<ModP>(A, s0 + 140, i, lam, lam, lam2);            // lambda_squared
+    do_add<ModP>(A, s0 + 191, i, x1, x1, xd);                     // x_double
+    canon9<ModP>(xd);
+    do_sub<ModP>(A, s0 + 201, i, lam2, xd, x3);                   // x3
+    do_sub<ModP>(A, s0 + 211, i, x1, x3, xdiff);                  // x_diff
+    e |= do_mul<ModP>(A, s0 + 221, i, lam, xdiff, lx);            // lambda_x_diff
+    do_sub<ModP>(A, s0 + 272, i, lx, y1, y3);                     // y3
+  } else {
+    int32_t p2 = A.SRC2[(size_t)k * A.cap + i];
+    u32 x2[NL], y2[NL], zc2[NL];
+    load_affine(A, p2, i, x2, y2, zc2);
+    // (x2 - x1)^-1 = Z1^3 Z2^3 / Z3
+    mulmod<ModP>(zc1, zc2, t);
+    mulmod<ModP>(t, zinv, vinv);
+    u32 u[NL], v[NL], s[NL], s2[NL], xs[NL], x3[NL], xd[NL], pr[NL], y3[NL];
+    do_sub<ModP>(A, s0 + 0, i, y2, y1, u);                        // u
+    do_sub<ModP>(A, s0 + 10, i, x2, x1, v);                       // v
+    if (is_zero9(v)) e |= ERR_INVERSE_ZERO;
+    e |= do_inv_known<ModP>(A, s0 + 20, i, v, vinv);              // v_inv
+    e |= do_mul<ModP>(A, s0 + 38, i, u, vinv, s);                 // s
+    e |= do_mul<ModP>(A, s0 + 89, i, s, s, s2);                   // s_squared
+    do_add<ModP>(A, s0 + 140, i, x2, x1, xs);                     // x_sum
+    canon9<ModP>(xs);
+    do_sub<ModP>(A, s0 + 150, i, s2, xs, x3);                     // x3
+    do_sub<ModP>(A, s0 + 160, i, x1, x3, xd);                     // x_diff
+    e |= do_mul<ModP>(A, s0 + 170, i, s, xd, pr);                 // prod
+    do_sub<ModP>(A, s0 + 221, i, pr, y1, y3);                     // y3
+    if (op.type != PT_ADD) {
+      // curve_conditional_add: x = sum.x * b + p1.x * !b (curve.rs:235-240)
+      u32 b = A.FLG[(size_t)k * A.cap + i];
+      u32 z[NL], r[NL];
+      set_zero9(z);
+      if (b) { do_add<ModP>(A, s0 + 231, i, x3, z, r); do_add<ModP>(A, s0 + 241, i, y3, z, r); }
+      else { do_add<ModP>(A, s0 + 231, i, z, x1, r); do_add<ModP>(A, s0 + 241, i, z, y1, r); }
+    }
+  }
+  if (e) atomicOr(&A.err[i], e);
+}
+
+// K5: connect_nonnative checks
+__global__ void __launch_bounds__(32) k_chain_checks(ChainArgs A) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  u32 bad = 0;
+  for (int c = 0; c < A.t.n_checks; c++) {
+    u64 a[NL], b[NL];
+    load_ref(A, A.t.checks[c].a, i, a);
+    load_ref(A, A.t.checks[c].b, i, b);
+    for (int l = 0; l < NL; l++) if (a[l] != b[l]) bad = 1;
+  }
+  if (bad) A.err[i] |= ERR_CONNECT;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: device copies of the tapes, scratch, launch sequence
+struct TapeOnDevice {
+  bool ready = false;
+  int device = -1;
+  DevTape d;
+  void* blob = nullptr;
+  size_t n_slots = 0;
+};
+
+static TapeOnDevice g_dev_tapes[2];
+static std::mutex g_mu;
+
+template <class T>
+static size_t align_up(size_t v) { return (v + alignof(T) - 1) / alignof(T) * alignof(T); }
+
+static int upload_tape(const Tape& t, TapeOnDevice& o) {
+  Context& c = ctx();
+  if (o.ready && o.device == c.device) return 0;
+  size_t off = 0;
+  auto reserve = [&](size_t bytes) { size_t at = (off + 15) / 16 * 16; off = at + bytes; return at; };
+  size_t o_prep = reserve(t.prep.size() * sizeof(PrepOp));
+  size_t o_pt = reserve(t.ptops.size() * sizeof(PtOp));
+  size_t o_chk = reserve(t.checks.size() * sizeof(Check));
+  size_t o_in = reserve(t.in_points.size() * sizeof(InputPoint));
+  size_t o_cl = reserve((t.const_limbs.size() + 1) * sizeof(u32));
+  size_t o_cp = reserve((t.const_points.size() + 1) * sizeof(u32));
+  std::vector<unsigned char> host(off + 16, 0);
+  memcpy(&host[o_prep], t.prep.data(), t.prep.size() * sizeof(PrepOp));
+  memcpy(&host[o_pt], t.ptops.data(), t.ptops.size() * sizeof(PtOp));
+  memcpy(&host[o_chk], t.checks.data(), t.checks.size() * sizeof(Check));
+  memcpy(&host[o_in], t.in_points.data(), t.in_points.size() * sizeof(InputPoint));
+  memcpy(&host[o_cl], t.const_limbs.data(), t.const_limbs.size() * sizeof(u32));
+  memcpy(&host[o_cp], t.const_points.data(), t.const_points.size() * sizeof(u32));
+  void* blob = nullptr;
+  P2E_CUDA(cudaMalloc(&blob, host.size()));
+  P2E_CUDA(cudaMemcpy(blob, host.data(), host.size(), cudaMemcpyHostToDevice));
+  unsigned char* b = (unsigned char*)blob;
+  o.d.prep = (const PrepOp*)(b + o_prep);
+  o.d.ptops = (const PtOp*)(b + o_pt);
+  o.d.checks = (const Check*)(b + o_chk);
+  o.d.in_points = (const InputPoint*)(b + o_in);
+  o.d.const_limbs = (const u32*)(b + o_cl);
+  o.d.const_points = (const u32*)(b + o_cp);
+  o.d.n_prep = (int)t.prep.size();
+  o.d.n_ptops = (int)t.ptops.size();
+  o.d.n_checks = (int)t.checks.size();
+  o.d.n_in_points = (int)t.in_points.size();
+  for (int i = 0; i < 16; i++) o.d.pre_pid[i] = t.pre_pid[i];
+  o.d.fixed_scalar = t.fixed_scalar;
+  o.d.msm_k1 = t.msm_k1;
+  o.d.msm_k2 = t.msm_k2;
+  o.d.fixed_table_base = t.fixed_table_base;
+  o.blob = blob;
+  o.n_slots = t.n_slots;
+  o.device = c.device;
+  o.ready = true;
+  return 0;
+}
+
+void chain_release_device_tapes() {
+  for (auto& o : g_dev_tapes) {
+    if (o.ready && o.blob) cudaFree(o.blob);
+    o.ready = false;
+    o.blob = nullptr;
+  }
+}
+
+static size_t chunk_capacity() {
+  const char* e = getenv("P2E_CHAIN_CHUNK");
+  size_t v = e ? (size_t)atoll(e) : 0;
+  return v ? v : 8192;
+}
+
+static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* ins, int n_in, size_t is, uint64_t* out,
+                    size_t os, uint32_t* err, void* stream) {
+  int rc = ensure_ready();
+  if (rc) return rc;
+  if (n == 0) return 0;
+  if (is < n || os < n) return set_error_msg("stride < n");
+  std::lock_guard<std::mutex> lock(g_mu);
+  TapeOnDevice& o = g_dev_tapes[which];
+  if ((rc = upload_tape(t, o))) return rc;
+  cudaStream_t st = pick_stream(stream);
+  const size_t cap = n < chunk_capacity() ? n : chunk_capacity();
+  const size_t np = (size_t)o.d.n_ptops + o.d.n_in_points, no = (size_t)o.d.n_ptops;
+  // scratch layout (u32 words)
+  size_t words = (np * 27 * 2 + no * 9) * cap;      // JX JY JZ AX AY ZC + ZINV
+  size_t bytes = words * 4 + no * cap * (4 + 4 + 1) + 64;
+  void* scratch = nullptr;
+  if ((rc = get_scratch(3, bytes, &scratch))) return rc;
+  ChainArgs A;
+  A.t = o.d;
+  A.is = is;
+  A.os = os;
+  A.cap = cap;
+  u32* w = (u32*)scratch;
+  A.JX = w; w += np * 9 * cap;
+  A.JY = w; w += np * 9 * cap;
+  A.JZ = w; w += np * 9 * cap;
+  A.AX = w; w += np * 9 * cap;
+  A.AY = w; w += np * 9 * cap;
+  A.ZC = w; w += np * 9 * cap;
+  A.ZINV = w; w += no * 9 * cap;
+  A.SRC1 = (int32_t*)w; w += no * cap;
+  A.SRC2 = (int32_t*)w; w += no * cap;
+  A.FLG = (uint8_t*)w;
+  for (size_t c0 = 0; c0 < n; c0 += cap) {
+    size_t cn = (n - c0 < cap) ? n - c0 : cap;
+    A.n = cn;
+    for (int k = 0; k < 8; k++) A.in[k] = (k < n_in) ? ins[k] + c0 : nullptr;
+    A.out = out + c0;
+    A.err = err + c0;
+    unsigned g32 = (unsigned)((cn + 31) / 32), g128 = (unsigned)((cn + 127) / 128);
+    k_prep<<<g32, 32, 0, st>>>(A);
+    if (no) {
+      k_chain_replay<<<g32, 32, 0, st>>>(A);
+      k_chain_invert<<<g32, 32, 0, st>>>(A);
+      k_chain_affine<<<dim3(g128, (unsigned)no), 128, 0, st>>>(A);
+      k_chain_expand<<<dim3(g128, (unsigned)no), 128, 0, st>>>(A);
+    }
+    k_chain_checks<<<g32, 32, 0, st>>>(A);
+    P2E_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+static size_t tape_layout(const Tape& t, uint32_t* kinds, uint32_t* offs) {
+  if (kinds && offs) {
+    for (size_t i = 0; i < t.gen_kind.size(); i++) {
+      kinds[i] = t.gen_kind[i];
+      offs[i] = t.gen_off[i];
+    }
+  }
+  return t.gen_kind.size();
+}
+
+template <class Launch>
+static int run_tape_host(const Tape& t, size_t n, const uint64_t* const* ins, int n_in, uint64_t* out, uint32_t* err,
+                         Launch launch) {
+  int rc = ensure_ready();
+  if (rc) return rc;
+  if (n == 0) return 0;
+  cudaStream_t st = ctx().stream;
+  void *din = nullptr, *dout = nullptr, *derr = nullptr;
+  if ((rc = get_scratch(0, (size_t)n_in * 9 * n * 8, &din))) return rc;
+  if ((rc = get_scratch(1, (size_t)t.n_slots * n * 8, &dout))) return rc;
+  if ((rc = get_scratch(2, n * 4, &derr))) return rc;
+  const uint64_t* dptr[8];
+  for (int k = 0; k < n_in; k++) {
+    dptr[k] = (const uint64_t*)din + (size_t)k * 9 * n;
+    P2E_CUDA(cudaMemcpyAsync((uint64_t*)din + (size_t)k * 9 * n, ins[k], 9 * n * 8, cudaMemcpyHostToDevice, st));
+  }
+  if ((rc = launch(dptr, (uint64_t*)dout, (uint32_t*)derr, (void*)st))) return rc;
+  P2E_CUDA(cudaMemcpyAsync(out, dout, (size_t)t.n_slots * n * 8, cudaMemcpyDeviceToHost, st));
+  if (err) P2E_CUDA(cudaMemcpyAsync(err, derr, n * 4, cudaMemcpyDeviceToHost, st));
+  P2E_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // namespace p2e
 
 using namespace p2e;
+
 extern "C" {
-size_t p2e_ecdsa_tape_slots(void) { return 0; }
-size_t p2e_ecdsa_tape_layout(uint32_t*, uint32_t*) { return 0; }
-int p2e_ecdsa_witness_dev(size_t, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*,
-                          size_t, uint64_t*, size_t, uint32_t*, void*) {
-  return set_error_msg("p2e_ecdsa_witness: chain kernels not built in this revision");
+
+size_t p2e_ecdsa_tape_slots(void) { return ecdsa_tape().n_slots; }
+size_t p2e_ecdsa_tape_layout(uint32_t* kinds, uint32_t* offsets) { return tape_layout(ecdsa_tape(), kinds, offsets); }
+
+int p2e_ecdsa_witness_dev(size_t n, const uint64_t* msg, const uint64_t* r, const uint64_t* s, const uint64_t* pkx,
+                          const uint64_t* pky, size_t is, uint64_t* out, size_t os, uint32_t* err, void* stream) {
+  const uint64_t* ins[5] = {msg, r, s, pkx, pky};
+  return run_tape(0, ecdsa_tape(), n, ins, 5, is, out, os, err, stream);
 }
-int p2e_ecdsa_witness(size_t, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*, const uint64_t*,
-                      uint64_t*, uint32_t*) {
-  return set_error_msg("p2e_ecdsa_witness: chain kernels not built in this revision");
+
+size_t p2e_glv_mul_tape_slots(void) { return glv_mul_tape().n_slots; }
+size_t p2e_glv_mul_tape_layout(uint32_t* kinds, uint32_t* offsets) { return tape_layout(glv_mul_tape(), kinds, offsets); }
+
+int p2e_glv_mul_witness_dev(size_t n, const uint64_t* k, const uint64_t* px, const uint64_t* py, size_t is,
+                            uint64_t* out, size_t os, uint32_t* err, void* stream) {
+  const uint64_t* ins[3] = {k, px, py};
+  return run_tape(1, glv_mul_tape(), n, ins, 3, is, out, os, err, stream);
 }
-size_t p2e_glv_mul_tape_slots(void) { return 0; }
-size_t p2e_glv_mul_tape_layout(uint32_t*, uint32_t*) { return 0; }
-int p2e_glv_mul_witness_dev(size_t, const uint64_t*, const uint64_t*, const uint64_t*, size_t, uint64_t*, size_t,
-                            uint32_t*, void*) {
-  return set_error_msg("p2e_glv_mul_witness: chain kernels not built in this revision");
+
+}  // extern "C"
+
+int p2e_ecdsa_witness(size_t n, const uint64_t* msg, const uint64_t* r, const uint64_t* s, const uint64_t* pkx,
+                      const uint64_t* pky, uint64_t* out, uint32_t* err);
+
+extern "C" int p2e_ecdsa_witness(size_t n, const uint64_t* msg, const uint64_t* r, const uint64_t* s,
+                                 const uint64_t* pkx, const uint64_t* pky, uint64_t* out, uint32_t* err) {
+  const uint64_t* ins[5] = {msg, r, s, pkx, pky};
+  return run_tape_host(ecdsa_tape(), n, ins, 5, out, err, [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* st) {
+    return run_tape(0, ecdsa_tape(), n, d, 5, n, o, n, e, st);
+  });
 }
-int p2e_glv_mul_witness(size_t, const uint64_t*, const uint64_t*, const uint64_t*, uint64_t*, uint32_t*) {
-  return set_error_msg("p2e_glv_mul_witness: chain kernels not built in this revision");
-}
+
+extern "C" int p2e_glv_mul_witness(size_t n, const uint64_t* k, const uint64_t* px, const uint64_t* py, uint64_t* out,
+                                   uint32_t* err) {
+  const uint64_t* ins[3] = {k, px, py};
+  return run_tape_host(glv_mul_tape(), n, ins, 3, out, err, [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* st) {
+    return run_tape(1, glv_mul_tape(), n, d, 3, n, o, n, e, st);
+  });
 }

@@ -32,6 +32,8 @@ int get_scratch(int slot, size_t bytes, void** out);
     if (e__ != cudaSuccess) return p2e::set_error(#call, e__); \
   } while (0)
 
+void chain_release_device_tapes();
+
 static inline cudaStream_t pick_stream(void* s) { return s ? (cudaStream_t)s : ctx().stream; }
 
 }  // namespace p2e

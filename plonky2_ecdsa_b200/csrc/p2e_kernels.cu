@@ -271,6 +271,18 @@ __device__ int dr_load(const u64* __restrict__ p, int nl, size_t is, size_t i, u
   return top;
 }
 
+// Length of convert_base(value.to_u32_digits(), 32, 29) (biguint.rs:27-51): the loop emits
+// floor(32 * n32 / 29) limbs -- possibly including zero top limbs -- plus one iff bits remain.
+__device__ int dr_conv_len(const u32* v) {
+  int top = -1;
+  for (int l = 0; l < DR_W; l++) if (v[l]) top = l;
+  if (top < 0) return 0;
+  int bits = LB * top + (32 - __clz(v[top]));
+  int n32 = (bits + 31) / 32;
+  int k = (32 * n32) / LB;
+  return k + (bits > LB * k ? 1 : 0);
+}
+
 __global__ void __launch_bounds__(TPB)
 k_divrem_witness(size_t n, const u64* __restrict__ a, int al, const u64* __restrict__ b, int bl, size_t is,
                  u64* __restrict__ out, size_t os, u32* __restrict__ err) {
@@ -344,10 +356,10 @@ k_divrem_witness(size_t n, const u64* __restrict__ a, int al, const u64* __restr
       for (int l = nn; l <= DR_W; l++) u[l] = 0;
     }
   }
-  // set_biguint_target asserts (biguint.rs:473)
+  // set_biguint_target asserts target.num_limbs() >= convert_base(32 -> 29).len() (biguint.rs:472-473)
   if (e == 0) {
-    for (int l = div_limbs; l < DR_W; l++) if (q[l]) e |= ERR_LIMBS_OVERFLOW;
-    for (int l = bl; l < DR_W; l++) if (u[l]) e |= ERR_LIMBS_OVERFLOW;
+    if (dr_conv_len(q) > div_limbs) e |= ERR_LIMBS_OVERFLOW;
+    if (dr_conv_len(u) > bl) e |= ERR_LIMBS_OVERFLOW;
   }
   for (int l = 0; l < div_limbs; l++) out[l * os + i] = e ? 0 : q[l];
   for (int l = 0; l < bl; l++) out[(div_limbs + l) * os + i] = e ? 0 : u[l];
@@ -507,6 +519,7 @@ void p2e_shutdown(void) {
   Context& c = ctx();
   if (!c.ready) return;
   cudaStreamSynchronize(c.stream);
+  chain_release_device_tapes();
   for (int i = 0; i < 4; i++) {
     if (c.scratch[i]) cudaFree(c.scratch[i]);
     c.scratch[i] = nullptr;

@@ -1,0 +1,474 @@
+// p2e_tape.cpp -- host-side mirror of the reference's gadget call graph; see p2e_tape.h.
+// Gadget methods below keep the reference's names and call order; each cites the reference
+// function it mirrors.  Circuit CONSTANTS (blinding point, fixed-base tables) are computed here
+// with native affine arithmetic, as the reference does at circuit-build time
+// (gadgets/curve_fixed_base.rs:24-52, gadgets/curve_msm.rs:33-39,74-76).
+#include "p2e_tape.h"
+
+#include <string.h>
+
+#include "p2e_field.cuh"
+
+namespace p2e {
+namespace {
+
+// ------------------------------------------------------------------ native field / curve (constants)
+struct Fe {
+  u32 l[NL];
+};
+static Fe fe_zero() { Fe r; memset(r.l, 0, sizeof r.l); return r; }
+static Fe fe_small(u32 v) { Fe r = fe_zero(); r.l[0] = v; return r; }
+static Fe fe_from_u64x4(const u64 (&w)[4]) {     // 256-bit little-endian words -> 29-bit limbs
+  Fe r;
+  for (int i = 0; i < NL; i++) {
+    int bit = LB * i, wi = bit >> 6, sh = bit & 63;
+    u64 v = w[wi] >> sh;
+    if (sh + LB > 64 && wi + 1 < 4) v |= w[wi + 1] << (64 - sh);
+    r.l[i] = (u32)v & LMASK;
+  }
+  return r;
+}
+static Fe fe_mul(const Fe& a, const Fe& b) { Fe r; mulmod<ModP>(a.l, b.l, r.l); return r; }
+static Fe fe_add(const Fe& a, const Fe& b) { Fe r; addmod<ModP>(a.l, b.l, r.l); return r; }
+static Fe fe_sub(const Fe& a, const Fe& b) { Fe r; submod<ModP>(a.l, b.l, r.l); return r; }
+static Fe fe_inv(const Fe& a) { Fe r; inv_p(a.l, r.l); return r; }
+static bool fe_eq(const Fe& a, const Fe& b) { return eq9(a.l, b.l); }
+static bool fe_is_zero(const Fe& a) { return is_zero9(a.l); }
+
+struct APoint {
+  Fe x, y;
+  bool inf;
+};
+static APoint ap_inf() { APoint p; p.x = fe_zero(); p.y = fe_zero(); p.inf = true; return p; }
+static APoint ap_neg(const APoint& p) { APoint r = p; if (!p.inf) r.y = fe_sub(fe_zero(), p.y); return r; }
+static APoint ap_double(const APoint& p) {                    // curve/curve_types.rs:83-102
+  if (p.inf || fe_is_zero(p.y)) return ap_inf();
+  Fe xx = fe_mul(p.x, p.x);
+  Fe lam = fe_mul(fe_add(fe_add(xx, xx), xx), fe_inv(fe_add(p.y, p.y)));
+  APoint r;
+  r.inf = false;
+  r.x = fe_sub(fe_mul(lam, lam), fe_add(p.x, p.x));
+  r.y = fe_sub(fe_mul(lam, fe_sub(p.x, r.x)), p.y);
+  return r;
+}
+static APoint ap_add(const APoint& p, const APoint& q) {      // curve/curve_adds.rs (affine + affine)
+  if (p.inf) return q;
+  if (q.inf) return p;
+  if (fe_eq(p.x, q.x)) return fe_eq(p.y, q.y) ? ap_double(p) : ap_inf();
+  Fe lam = fe_mul(fe_sub(q.y, p.y), fe_inv(fe_sub(q.x, p.x)));
+  APoint r;
+  r.inf = false;
+  r.x = fe_sub(fe_sub(fe_mul(lam, lam), p.x), q.x);
+  r.y = fe_sub(fe_mul(lam, fe_sub(p.x, r.x)), p.y);
+  return r;
+}
+static APoint ap_mul(const u64 (&k)[4], const APoint& p) {    // double-and-add, LSB first
+  APoint acc = ap_inf(), base = p;
+  for (int bit = 0; bit < 256; bit++) {
+    if ((k[bit >> 6] >> (bit & 63)) & 1) acc = ap_add(acc, base);
+    base = ap_double(base);
+  }
+  return acc;
+}
+
+static const u64 GEN_X[4] = {0x59F2815B16F81798ull, 0x029BFCDB2DCE28D9ull, 0x55A06295CE870B07ull, 0x79BE667EF9DCBBACull};
+static const u64 GEN_Y[4] = {0x9C47D08FFB10D4B8ull, 0xFD17B448A6855419ull, 0x5DA4FBFC0E1108A8ull, 0x483ADA7726A3C465ull};
+static const u64 SCALAR_N[4] = {0xBFD25E8CD0364141ull, 0xBAAEDCE6AF48A03Bull, 0xFFFFFFFFFFFFFFFEull, 0xFFFFFFFFFFFFFFFFull};
+// curve/glv.rs:11-23
+static const u64 GLV_BETA_W[4] = {13923278643952681454ull, 11308619431505398165ull, 7954561588662645993ull, 8856726876819556112ull};
+static const u64 GLV_S_W[4] = {16069571880186789234ull, 1310022930574435960ull, 11900229862571533402ull, 6008836872998760672ull};
+
+static APoint generator() {
+  APoint g;
+  u64 gx[4], gy[4];
+  memcpy(gx, GEN_X, 32);
+  memcpy(gy, GEN_Y, 32);
+  g.x = fe_from_u64x4(gx);
+  g.y = fe_from_u64x4(gy);
+  g.inf = false;
+  return g;
+}
+
+// ------------------------------------------------------------------ Keccak-256 (original 0x01 padding)
+static u64 rol64(u64 v, int n) { return n ? (v << n) | (v >> (64 - n)) : v; }
+static void keccak_f(u64 (&st)[25]) {
+  static const u64 RC[24] = {
+      0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808Aull, 0x8000000080008000ull,
+      0x000000000000808Bull, 0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull,
+      0x000000000000008Aull, 0x0000000000000088ull, 0x0000000080008009ull, 0x000000008000000Aull,
+      0x000000008000808Bull, 0x800000000000008Bull, 0x8000000000008089ull, 0x8000000000008003ull,
+      0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800Aull, 0x800000008000000Aull,
+      0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+  static const int ROT[25] = {0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14};
+  for (int rnd = 0; rnd < 24; rnd++) {
+    u64 c[5], d[5], b[25];
+    for (int x = 0; x < 5; x++) c[x] = st[x] ^ st[x + 5] ^ st[x + 10] ^ st[x + 15] ^ st[x + 20];
+    for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rol64(c[(x + 1) % 5], 1);
+    for (int i = 0; i < 25; i++) st[i] ^= d[i % 5];
+    for (int x = 0; x < 5; x++)
+      for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rol64(st[x + 5 * y], ROT[x + 5 * y]);
+    for (int x = 0; x < 5; x++)
+      for (int y = 0; y < 5; y++) st[x + 5 * y] = b[x + 5 * y] ^ (~b[(x + 1) % 5 + 5 * y] & b[(x + 2) % 5 + 5 * y]);
+    st[0] ^= RC[rnd];
+  }
+}
+// KeccakHash::<32>::hash_no_pad(&[F::ZERO]) -> BigUint::from_bytes_le -> from_noncanonical_biguint
+// (gadgets/curve_msm.rs:33-36): Keccak-256 of the 8 little-endian bytes of the field element 0.
+static void blinding_scalar(u64 (&k)[4]) {
+  u64 st[25];
+  memset(st, 0, sizeof st);
+  // message: 8 zero bytes, pad10*1 with 0x01 domain byte, rate 136 bytes
+  st[1] ^= 0x01ull;                 // byte 8
+  st[16] ^= 0x8000000000000000ull;  // byte 135
+  keccak_f(st);
+  for (int i = 0; i < 4; i++) k[i] = st[i];
+  // to_canonical: one conditional subtract of n
+  bool ge = true;
+  for (int i = 3; i >= 0; i--) {
+    if (k[i] != SCALAR_N[i]) { ge = k[i] > SCALAR_N[i]; break; }
+  }
+  if (ge) {
+    unsigned __int128 br = 0;
+    for (int i = 0; i < 4; i++) {
+      unsigned __int128 t = (unsigned __int128)k[i] - SCALAR_N[i] - br;
+      k[i] = (u64)t;
+      br = (t >> 64) & 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ builder
+constexpr int32_t PID_INPUT_BASE = 1 << 19;
+
+struct NNT {      // NonNativeTarget (gadgets/nonnative.rs:34-38)
+  Ref r;
+};
+struct BoolT {    // BoolTarget living in an output slot
+  uint8_t space;
+  uint32_t off;
+  bool inv;
+};
+struct PtT {      // AffinePointTarget (gadgets/curve.rs:15-19) + the chain engine's point id
+  int32_t pid;
+  NNT x, y;
+};
+
+static Ref mkref(uint8_t space, uint32_t off, uint8_t nl) {
+  Ref r;
+  r.space = space;
+  r.nl = nl;
+  r.bspace = SP_NONE;
+  r.binv = 0;
+  r.off = off;
+  r.boff = 0;
+  return r;
+}
+
+class Builder {
+ public:
+  Tape t;
+  APoint rando, neg_rando;
+
+  Builder() {
+    u64 k[4];
+    blinding_scalar(k);
+    rando = ap_mul(k, generator());
+    neg_rando = ap_neg(rando);
+    for (int i = 0; i < 16; i++) t.pre_pid[i] = -1;
+    t.fixed_scalar = mkref(SP_NONE, 0, 0);
+    t.msm_k1 = mkref(SP_NONE, 0, 0);
+    t.msm_k2 = mkref(SP_NONE, 0, 0);
+  }
+
+  uint32_t emit(GenKind k, uint32_t width) {
+    uint32_t off = t.n_slots;
+    t.gen_kind.push_back(k);
+    t.gen_off.push_back(off);
+    t.n_slots += width;
+    return off;
+  }
+
+  NNT input(uint32_t k) {
+    if (t.n_inputs < k + 1) t.n_inputs = k + 1;
+    NNT v;
+    v.r = mkref(SP_IN, 9 * k, 9);
+    return v;
+  }
+
+  // constant_nonnative (nonnative.rs:205-208 / biguint.rs:165-175): convert_base drops leading
+  // zero limbs, zero has NO limbs
+  NNT constant_nonnative(const Fe& v) {
+    int nl = NL;
+    while (nl > 0 && v.l[nl - 1] == 0) nl--;
+    NNT r;
+    r.r = mkref(SP_CONST, (uint32_t)t.const_limbs.size(), (uint8_t)nl);
+    for (int i = 0; i < nl; i++) t.const_limbs.push_back(v.l[i]);
+    return r;
+  }
+
+  void prep2(PrepOpcode op, int mod, uint32_t slot, const NNT& a, const NNT& b) {
+    PrepOp p;
+    p.opcode = op;
+    p.mod = (uint8_t)mod;
+    p.pad = 0;
+    p.slot = slot;
+    p.a = a.r;
+    p.b = b.r;
+    t.prep.push_back(p);
+  }
+
+  NNT add_nonnative(const NNT& a, const NNT& b, int mod) {          // nonnative.rs:245-276
+    uint32_t s = emit(G_ADD, 10);
+    prep2(OP_ADD, mod, s, a, b);
+    NNT r; r.r = mkref(SP_OUT, s, 9); return r;
+  }
+  NNT sub_nonnative(const NNT& a, const NNT& b, int mod) {          // nonnative.rs:356-388
+    uint32_t s = emit(G_SUB, 10);
+    prep2(OP_SUB, mod, s, a, b);
+    NNT r; r.r = mkref(SP_OUT, s, 9); return r;
+  }
+  NNT mul_nonnative(const NNT& a, const NNT& b, int mod) {          // nonnative.rs:390-464
+    uint32_t s = emit(G_MUL, 35);
+    emit(G_CHECKSUM, 16);
+    prep2(OP_MUL, mod, s, a, b);
+    NNT r; r.r = mkref(SP_OUT, s, 9); return r;                     // r occupies the first 9 slots
+  }
+  NNT inv_nonnative(const NNT& x, int mod) {                        // nonnative.rs:502-536
+    uint32_t s = emit(G_INV, 18);
+    prep2(OP_INV, mod, s, x, x);
+    NNT r; r.r = mkref(SP_OUT, s + 9, 9); return r;                 // [div, inv]
+  }
+  NNT neg_nonnative(const NNT& x, int mod) {                        // nonnative.rs:491-500
+    NNT zero; zero.r = mkref(SP_CONST, 0, 0);
+    return sub_nonnative(zero, x, mod);
+  }
+  NNT mul_nonnative_by_bool(const NNT& a, const BoolT& b) {         // nonnative.rs:278-295
+    NNT r = a;
+    r.r.bspace = b.space;
+    r.r.boff = b.off;
+    r.r.binv = b.inv ? 1 : 0;
+    return r;
+  }
+  NNT nonnative_conditional_neg(const NNT& x, const BoolT& b, int mod) {   // nonnative.rs:584-596
+    BoolT nb = b; nb.inv = !b.inv;
+    NNT neg = neg_nonnative(x, mod);
+    NNT xt = mul_nonnative_by_bool(neg, b);
+    NNT xf = mul_nonnative_by_bool(x, nb);
+    return add_nonnative(xt, xf, mod);
+  }
+  void connect_nonnative(const NNT& a, const NNT& b) {              // nonnative.rs:215-221
+    Check c; c.a = a.r; c.b = b.r;
+    t.checks.push_back(c);
+  }
+
+  // ---- curve gadgets
+  int32_t const_point(const APoint& p) {                            // constant_affine_point, curve.rs:99-105
+    int32_t idx = (int32_t)(t.const_points.size() / 18);
+    for (int i = 0; i < NL; i++) t.const_points.push_back(p.x.l[i]);
+    for (int i = 0; i < NL; i++) t.const_points.push_back(p.y.l[i]);
+    return PID_CONST_BASE + idx;
+  }
+  PtT input_point(const NNT& x, const NNT& y) {
+    InputPoint ip; ip.x = x.r; ip.y = y.r;
+    PtT p; p.pid = PID_INPUT_BASE + (int32_t)t.in_points.size(); p.x = x; p.y = y;
+    t.in_points.push_back(ip);
+    return p;
+  }
+
+  void curve_assert_valid(const NNT& px, const NNT& py) {           // curve.rs:123-135
+    NNT a = constant_nonnative(fe_zero());
+    NNT b = constant_nonnative(fe_small(7));
+    NNT y2 = mul_nonnative(py, py, 0);
+    NNT x2 = mul_nonnative(px, px, 0);
+    NNT x3 = mul_nonnative(x2, px, 0);
+    NNT ax = mul_nonnative(a, px, 0);
+    NNT axb = add_nonnative(ax, b, 0);
+    NNT rhs = add_nonnative(x3, axb, 0);
+    connect_nonnative(y2, rhs);
+  }
+
+  // generator emission inside curve_add (curve.rs:202-223):
+  // u SUB, v SUB, v_inv INV, s MUL+CS, s^2 MUL+CS, x_sum ADD, x3 SUB, x_diff SUB, prod MUL+CS, y3 SUB
+  uint32_t emit_curve_add() {
+    uint32_t s0 = emit(G_SUB, 10);
+    emit(G_SUB, 10);
+    emit(G_INV, 18);
+    emit(G_MUL, 35); emit(G_CHECKSUM, 16);
+    emit(G_MUL, 35); emit(G_CHECKSUM, 16);
+    emit(G_ADD, 10);
+    emit(G_SUB, 10);
+    emit(G_SUB, 10);
+    emit(G_MUL, 35); emit(G_CHECKSUM, 16);
+    emit(G_SUB, 10);
+    return s0;
+  }
+  PtT point_of_op(int32_t k, uint32_t xoff, uint32_t yoff) {
+    PtT p; p.pid = k;
+    p.x.r = mkref(SP_OUT, xoff, 9);
+    p.y.r = mkref(SP_OUT, yoff, 9);
+    return p;
+  }
+  PtT push_ptop(PtOpType type, uint8_t flags, uint16_t aux, int32_t p1, int32_t p2, uint32_t slot, uint32_t xo, uint32_t yo) {
+    PtOp o;
+    o.type = type; o.flags = flags; o.aux = aux; o.p1 = p1; o.p2 = p2; o.slot = slot;
+    int32_t k = (int32_t)t.ptops.size();
+    t.ptops.push_back(o);
+    return point_of_op(k, slot + xo, slot + yo);
+  }
+  PtT curve_add(int32_t p1, int32_t p2, uint8_t flags) {            // curve.rs:202-223
+    uint32_t s = emit_curve_add();
+    return push_ptop(PT_ADD, flags, 0, p1, p2, s, 150, 221);
+  }
+  PtT curve_double(int32_t p1, uint8_t flags) {                     // curve.rs:160-185
+    uint32_t s = emit(G_ADD, 10);                                    // double_y
+    emit(G_INV, 18);                                                 // inv_double_y
+    emit(G_MUL, 35); emit(G_CHECKSUM, 16);                           // x_squared
+    emit(G_ADDMANY, 10);                                             // triple_xx_a
+    emit(G_MUL, 35); emit(G_CHECKSUM, 16);                           // lambda
+    emit(G_MUL, 35); emit(G_CHECKSUM, 16);                           // lambda_squared
+    emit(G_ADD, 10);                                                 // x_double
+    emit(G_SUB, 10);                                                 // x3
+    emit(G_SUB, 10);                                                 // x_diff
+    emit(G_MUL, 35); emit(G_CHECKSUM, 16);                           // lambda_x_diff
+    emit(G_SUB, 10);                                                 // y3
+    return push_ptop(PT_DBL, flags, 0, p1, -1, s, 201, 272);
+  }
+  PtT curve_conditional_add(PtOpType type, uint8_t flags, uint16_t aux, int32_t p1) {   // curve.rs:225-243
+    uint32_t s = emit_curve_add();
+    emit(G_ADD, 10);
+    emit(G_ADD, 10);
+    return push_ptop(type, flags, aux, p1, -1, s, 231, 241);
+  }
+
+  // fixed_base_curve_mul_circuit (curve_fixed_base.rs:18-66), base = G
+  PtT fixed_base_curve_mul(const NNT& scalar) {
+    const int n_limbs4 = (9 * LB + 3) / 4;                           // 66 4-bit limbs (split_nonnative.rs:25-50)
+    t.fixed_scalar = scalar.r;
+    t.fixed_table_base = (uint32_t)(t.const_points.size() / 18);
+    APoint base = generator();
+    for (int w = 0; w < n_limbs4; w++) {
+      APoint acc = ap_inf();
+      APoint first = base;
+      for (int e = 0; e < 16; e++) {                                 // muls_point[e] = e * P_w, entry 0 := entry 1
+        if (e == 0) {
+          const_point(first);
+        } else {
+          acc = ap_add(base, acc);
+          const_point(acc);
+        }
+      }
+      for (int d = 0; d < 4; d++) base = ap_double(base);
+    }
+    int32_t rando_pid = const_point(rando);
+    int32_t neg_pid = const_point(neg_rando);
+    for (int w = 0; w < n_limbs4; w++) {
+      uint8_t fl = PF_SET_CUR | (w ? PF_P1_CUR : 0);
+      curve_conditional_add(PT_CADD_FIXED, fl, (uint16_t)w, rando_pid);
+    }
+    return curve_add(-1, neg_pid, PF_P1_CUR | PF_SET_CUR);
+  }
+
+  // curve_msm_circuit (curve_msm.rs:21-79)
+  PtT curve_msm(const PtT& p, const PtT& q, const NNT& n, const NNT& m) {
+    const int num_limbs = (5 * LB + 1) / 2;                          // 73 2-bit limbs
+    t.msm_k1 = n.r;
+    t.msm_k2 = m.r;
+    int32_t rando_pid = const_point(rando);
+    int32_t neg_pid = const_point(neg_rando);
+    int32_t pre[16];
+    for (int i = 0; i < 16; i++) pre[i] = p.pid;
+    int32_t cur_p = rando_pid, cur_q = rando_pid;
+    for (int i = 0; i < 4; i++) {
+      pre[i] = cur_p;
+      pre[4 * i] = cur_q;
+      cur_p = curve_add(cur_p, p.pid, 0).pid;
+      cur_q = curve_add(cur_q, q.pid, 0).pid;
+    }
+    for (int i = 1; i < 4; i++) {
+      pre[i] = curve_add(pre[i], neg_pid, 0).pid;
+      pre[4 * i] = curve_add(pre[4 * i], neg_pid, 0).pid;
+    }
+    for (int i = 1; i < 4; i++)
+      for (int j = 1; j < 4; j++) pre[i + 4 * j] = curve_add(pre[i], pre[4 * j], 0).pid;
+    for (int i = 0; i < 16; i++) t.pre_pid[i] = pre[i];
+    for (int d = num_limbs - 1; d >= 0; d--) {                       // .rev(): most significant digit first
+      bool first = (d == num_limbs - 1);
+      curve_double(first ? rando_pid : -1, PF_SET_CUR | (first ? 0 : PF_P1_CUR));
+      curve_double(-1, PF_SET_CUR | PF_P1_CUR);
+      curve_conditional_add(PT_CADD_MSM, PF_SET_CUR | PF_P1_CUR, (uint16_t)d, -1);
+    }
+    APoint spm = rando;
+    for (int i = 0; i < 2 * num_limbs; i++) spm = ap_double(spm);
+    int32_t to_add = const_point(ap_neg(spm));
+    return curve_add(-1, to_add, PF_P1_CUR | PF_SET_CUR);
+  }
+
+  // decompose_secp256k1_scalar + glv_mul (glv.rs:53-104)
+  PtT glv_mul(const NNT& px, const NNT& py, const NNT& k) {
+    uint32_t gs = emit(G_GLV, 12);
+    {
+      PrepOp p;
+      p.opcode = OP_GLV; p.mod = 1; p.pad = 0; p.slot = gs; p.a = k.r; p.b = k.r;
+      t.prep.push_back(p);
+    }
+    NNT k1; k1.r = mkref(SP_OUT, gs, 5);
+    NNT k2; k2.r = mkref(SP_OUT, gs + 5, 5);
+    BoolT k1_neg = {SP_OUT, gs + 10, false};
+    BoolT k2_neg = {SP_OUT, gs + 11, false};
+    NNT k1_raw = nonnative_conditional_neg(k1, k1_neg, 1);
+    NNT k2_raw = nonnative_conditional_neg(k2, k2_neg, 1);
+    u64 sw[4], bw[4];
+    memcpy(sw, GLV_S_W, 32);
+    memcpy(bw, GLV_BETA_W, 32);
+    NNT s = constant_nonnative(fe_from_u64x4(sw));
+    NNT sbk = mul_nonnative(s, k2_raw, 1);
+    sbk = add_nonnative(sbk, k1_raw, 1);
+    connect_nonnative(sbk, k);
+    NNT beta = constant_nonnative(fe_from_u64x4(bw));
+    NNT beta_px = mul_nonnative(beta, px, 0);
+    NNT pnegy = nonnative_conditional_neg(py, k1_neg, 0);            // curve_conditional_neg(p, k1_neg)
+    NNT spnegy = nonnative_conditional_neg(py, k2_neg, 0);           // curve_conditional_neg(sp, k2_neg)
+    PtT p_neg = input_point(px, pnegy);
+    PtT sp_neg = input_point(beta_px, spnegy);
+    return curve_msm(p_neg, sp_neg, k1, k2);
+  }
+
+  // verify_secp256k1_message_circuit (ecdsa.rs:30-53)
+  void verify_secp256k1_message() {
+    NNT msg = input(0), r = input(1), s = input(2), pkx = input(3), pky = input(4);
+    curve_assert_valid(pkx, pky);
+    NNT c = inv_nonnative(s, 1);
+    NNT u1 = mul_nonnative(msg, c, 1);
+    NNT u2 = mul_nonnative(r, c, 1);
+    PtT point1 = fixed_base_curve_mul(u1);
+    PtT point2 = glv_mul(pkx, pky, u2);
+    (void)point2;
+    PtT point = curve_add(point1.pid, -1, PF_P2_CUR | PF_SET_CUR);
+    connect_nonnative(r, point.x);
+  }
+};
+
+}  // namespace
+
+const Tape& ecdsa_tape() {
+  static Tape* tape = nullptr;
+  if (!tape) {
+    Builder b;
+    b.verify_secp256k1_message();
+    tape = new Tape(b.t);
+  }
+  return *tape;
+}
+
+const Tape& glv_mul_tape() {
+  static Tape* tape = nullptr;
+  if (!tape) {
+    Builder b;
+    NNT k = b.input(0), px = b.input(1), py = b.input(2);
+    b.glv_mul(px, py, k);
+    tape = new Tape(b.t);
+  }
+  return *tape;
+}
+
+}  // namespace p2e

@@ -1,0 +1,82 @@
+// p2e_tape.h -- the "tape": a host-side C++ mirror of the reference's gadget call graph
+// (src/gadgets/{nonnative,curve,curve_fixed_base,curve_msm,glv,ecdsa}.rs).  Calling the mirrored
+// gadget methods records, in gadget call order,
+//   * every in-tree generator instance with the slot offset of its output tuple (the witness layout),
+//   * "prep ops": nonnative generators outside curve arithmetic, run by a per-signature interpreter,
+//   * "point ops": curve_add / curve_double / curve_conditional_add instances, run by the
+//     projective chain-replay + batched-inversion + expansion kernels (p2e_chain.cu),
+//   * "checks": connect_nonnative constraints the witness must satisfy (ERR_CONNECT otherwise).
+// The tape is identical for every signature, is built once on the host and lives in device memory.
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+namespace p2e {
+
+enum GenKind : uint32_t { G_ADD = 0, G_ADDMANY = 1, G_SUB = 2, G_INV = 3, G_MUL = 4, G_CHECKSUM = 5, G_GLV = 6 };
+
+enum Space : uint8_t { SP_NONE = 0, SP_OUT = 1, SP_IN = 2, SP_CONST = 3 };
+
+// A nonnative / BigUint target: `nl` limbs starting at `off` in `space`, optionally multiplied by
+// a bool target (mul_nonnative_by_bool, nonnative.rs:278-295), itself optionally negated (builder.not).
+struct Ref {
+  uint8_t space;
+  uint8_t nl;
+  uint8_t bspace;   // SP_NONE: no bool factor
+  uint8_t binv;
+  uint32_t off;
+  uint32_t boff;
+};
+
+enum PrepOpcode : uint8_t { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_INV = 3, OP_GLV = 4 };
+struct PrepOp {
+  uint8_t opcode;
+  uint8_t mod;
+  uint16_t pad;
+  uint32_t slot;    // first output slot
+  Ref a, b;
+};
+
+struct Check {      // connect_nonnative(a, b): limb-wise equality, missing limbs must be zero
+  Ref a, b;
+};
+
+enum PtOpType : uint8_t { PT_ADD = 0, PT_DBL = 1, PT_CADD_FIXED = 2, PT_CADD_MSM = 3 };
+enum PtFlags : uint8_t { PF_P1_CUR = 1, PF_P2_CUR = 2, PF_SET_CUR = 4 };
+constexpr int32_t PID_CONST_BASE = 1 << 20;     // pid >= this: affine constant #(pid - base)
+struct PtOp {
+  uint8_t type;
+  uint8_t flags;
+  uint16_t aux;     // window index (fixed base) or 2-bit digit index (msm)
+  int32_t p1, p2;   // point ids (ignored when the *_CUR flag is set)
+  uint32_t slot;    // first output slot of this curve op's generators
+};
+
+struct InputPoint {  // per-signature affine point whose coordinates are nonnative targets
+  Ref x, y;
+};
+
+struct Tape {
+  // layout
+  std::vector<uint32_t> gen_kind, gen_off;
+  uint32_t n_slots = 0;
+  uint32_t n_inputs = 0;            // input nonnative values (9 wires each)
+  // programs
+  std::vector<PrepOp> prep;
+  std::vector<PtOp> ptops;
+  std::vector<Check> checks;
+  std::vector<InputPoint> in_points;    // pid = ptops.size() + index
+  std::vector<uint32_t> const_limbs;    // SP_CONST pool (u32 limbs)
+  std::vector<uint32_t> const_points;   // affine constants: 18 limbs each (x[9], y[9])
+  int32_t pre_pid[16];                  // msm table entries (curve_msm.rs:41-62)
+  Ref fixed_scalar;                     // u1 (9 limbs) or space NONE
+  Ref msm_k1, msm_k2;                   // 5 limbs each or space NONE
+  uint32_t fixed_table_base = 0;        // const point index of window 0 entry 0
+};
+
+// verify_secp256k1_message_circuit (gadgets/ecdsa.rs:30-53); inputs msg, r, s, pk.x, pk.y
+const Tape& ecdsa_tape();
+// glv_mul(p, k) (gadgets/glv.rs:87-104); inputs k, p.x, p.y
+const Tape& glv_mul_tape();
+
+}  // namespace p2e

@@ -1,0 +1,47 @@
+"""CPU tier: the host-built tape (C++ mirror of the gadget call graph) lays generators out exactly
+in the oracle's gadget call order (same kinds, same tuple widths, same slot offsets)."""
+import numpy as np
+
+from oracle import spec as S
+import plonky2_ecdsa_b200 as pkg
+
+
+def _layout(fn_layout, fn_slots):
+    cnt = fn_layout(None, None)
+    kinds = np.empty(cnt, dtype=np.uint32)
+    offs = np.empty(cnt, dtype=np.uint32)
+    fn_layout(kinds.ctypes.data, offs.ctypes.data)
+    return kinds, offs, int(fn_slots())
+
+
+def _oracle_layout(tape):
+    kinds, offs, off = [], [], 0
+    for k, vals in tape:
+        kinds.append(k)
+        offs.append(off)
+        off += len(vals)
+    return kinds, offs, off
+
+
+def test_ecdsa_tape_layout_matches_oracle():
+    lib = pkg.load_library()
+    kinds, offs, slots = _layout(lib.p2e_ecdsa_tape_layout, lib.p2e_ecdsa_tape_slots)
+    sk, msg, k = 0x1234567 << 200 | 99, 0xabcdef << 180 | 5, 0x777 << 222 | 1
+    pk = S.pt_mul(sk, S.G)
+    r, s = S.sign_message(msg, sk, k)
+    ok, oo, oslots = _oracle_layout(S.ecdsa_witness(msg, r, s, pk).tape)
+    assert slots == oslots == 82615
+    assert list(kinds) == ok
+    assert list(offs) == oo
+
+
+def test_glv_mul_tape_layout_matches_oracle():
+    lib = pkg.load_library()
+    kinds, offs, slots = _layout(lib.p2e_glv_mul_tape_layout, lib.p2e_glv_mul_tape_slots)
+    wb = S.WitnessBuilder()
+    P = S.pt_mul(7, S.G)
+    kk = 0x1357 << 240 | 12345
+    wb.glv_mul(wb.constant_affine_point(P), wb.constant_nonnative(kk, S.SECP_N))
+    ok, oo, oslots = _oracle_layout(wb.tape)
+    assert slots == oslots
+    assert list(kinds) == ok and list(offs) == oo
