@@ -380,7 +380,21 @@ __device__ __forceinline__ void mac3(Acc3& a, u32 x, u32 y) {
       : "+r"(a.w0), "+r"(a.w1), "+r"(a.w2)
       : "r"(x), "r"(y));
 }
-// (A + B*2^32 + C*2^64 + add) mod P
+// (w0 + w1 2^32 + w2 2^64 + w3 2^96 + w4 2^128) mod P, w4 < 2^8, canonical result.
+// 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32 (mod P)  =>  V = (w1:w0) + (w2 << 32) - (w2 + w3 + (w4 << 32))
+__device__ __forceinline__ u64 gl_reduce5(u32 w0, u32 w1, u32 w2, u32 w3, u32 w4) {
+  u64 a = ((u64)w1 << 32) | w0;
+  u64 b = (u64)w2 << 32;
+  u64 c = (u64)w2 + (u64)w3 + ((u64)w4 << 32);       // < 2^41
+  u64 t = a - c;
+  if (a < c) t -= GL_EPS;                            // + P
+  u64 r = t + b;
+  if (r < b) r += GL_EPS;                            // - 2^64 + eps
+  if (r >= GL_P) r -= GL_P;
+  return r;
+}
+
+// (A + B*2^32 + C*2^64 + add) mod P for 96-bit accumulators A, B, C
 __device__ __forceinline__ u64 reduce_abc(const Acc3& A, const Acc3& B, const Acc3& C, u64 add) {
   u64 t = (u64)A.w0 + (u32)add;
   u32 W0 = (u32)t;
@@ -391,39 +405,57 @@ __device__ __forceinline__ u64 reduce_abc(const Acc3& A, const Acc3& B, const Ac
   t = (t >> 32) + B.w2 + C.w1;
   u32 W3 = (u32)t;
   u32 W4 = (u32)(t >> 32) + C.w2;
-  u64 r = gl_reduce128(((u64)W1 << 32) | W0, ((u64)W3 << 32) | W2);
-  return gl_sub(r, (u64)W4 << 32);     // 2^128 = -2^32 (mod P)
+  return gl_reduce5(W0, W1, W2, W3, W4);
+}
+
+// (QA0 + QA1 + (QB0 + QB1)*2^32 + add) mod P for carry-free 64-bit partial sums
+__device__ __forceinline__ u64 reduce_q(u64 qa0, u64 qa1, u64 qb0, u64 qb1, u64 add) {
+  u64 t = (u64)(u32)qa0 + (u32)qa1 + (u32)add;
+  u32 W0 = (u32)t;
+  t = (t >> 32) + (qa0 >> 32) + (qa1 >> 32) + (add >> 32) + (u32)qb0 + (u32)qb1;
+  u32 W1 = (u32)t;
+  t = (t >> 32) + (qb0 >> 32) + (qb1 >> 32);
+  return gl_reduce5(W0, W1, (u32)t, (u32)(t >> 32), 0);
 }
 
 template <class MOD>
-__global__ void __launch_bounds__(TPB)
+__global__ void __launch_bounds__(TPB, 4)
 k_eval_mul_nonnative(size_t n, const u64* __restrict__ wires, size_t is, u64* __restrict__ out, size_t os) {
   size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
-  u64 w[6 * NL - 1];
+  u32 xl[NL], xh[NL], yl[NL], yh[NL], ql[NL], qh[NL];
 #pragma unroll
-  for (int l = 0; l < 6 * NL - 1; l++) w[l] = wires[l * is + i];
+  for (int l = 0; l < NL; l++) {
+    u64 x = wires[l * is + i], y = wires[(NL + l) * is + i], q = wires[(3 * NL + l) * is + i];
+    xl[l] = (u32)x; xh[l] = (u32)(x >> 32);
+    yl[l] = (u32)y; yh[l] = (u32)(y >> 32);
+    ql[l] = (u32)q; qh[l] = (u32)(q >> 32);
+  }
 #pragma unroll
   for (int c = 0; c < 2 * NL - 1; c++) {
-    Acc3 A = {0, 0, 0}, B = {0, 0, 0}, C = {0, 0, 0}, QA = {0, 0, 0}, QB = {0, 0, 0};
-    const Acc3 Z = {0, 0, 0};
+    const u64 csw = wires[(4 * NL + c) * is + i];
+    const u64 rw = c < NL ? wires[(2 * NL + c) * is + i] : 0;
+    Acc3 A = {0, 0, 0}, B = {0, 0, 0}, C = {0, 0, 0};
+    u64 qa0 = 0, qa1 = 0, qb0 = 0, qb1 = 0;     // m_j < 2^29: five terms stay below 2^64
 #pragma unroll
     for (int j = 0; j < NL; j++) {
       const int k = c - j;
       if (k >= 0 && k < NL) {
-        u32 xl = (u32)w[j], xh = (u32)(w[j] >> 32);
-        u32 yl = (u32)w[NL + k], yh = (u32)(w[NL + k] >> 32);
-        u32 ql = (u32)w[3 * NL + k], qh = (u32)(w[3 * NL + k] >> 32);
-        mac3(A, xl, yl);
-        mac3(B, xl, yh);
-        mac3(B, xh, yl);
-        mac3(C, xh, yh);
-        mac3(QA, MOD::m(j), ql);
-        mac3(QB, MOD::m(j), qh);
+        mac3(A, xl[j], yl[k]);
+        mac3(B, xl[j], yh[k]);
+        mac3(B, xh[j], yl[k]);
+        mac3(C, xh[j], yh[k]);
+        if (j < 5) {
+          qa0 += (u64)MOD::m(j) * ql[k];
+          qb0 += (u64)MOD::m(j) * qh[k];
+        } else {
+          qa1 += (u64)MOD::m(j) * ql[k];
+          qb1 += (u64)MOD::m(j) * qh[k];
+        }
       }
     }
-    u64 neg = reduce_abc(A, B, C, w[4 * NL + c]);
-    u64 pos = reduce_abc(QA, QB, Z, c < NL ? w[2 * NL + c] : 0);
+    u64 neg = reduce_abc(A, B, C, csw);
+    u64 pos = reduce_q(qa0, qa1, qb0, qb1, rw);
     out[c * os + i] = gl_sub(pos, neg);
   }
 }
