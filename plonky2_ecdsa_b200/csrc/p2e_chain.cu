@@ -35,6 +35,7 @@ struct DevTape {
   int32_t pre_pid[16];
   Ref fixed_scalar, msm_k1, msm_k2;
   u32 fixed_table_base;
+  int32_t chain_begin[N_CHAINS], chain_end[N_CHAINS];
 };
 
 struct ChainArgs {
@@ -196,32 +197,35 @@ __global__ void __launch_bounds__(32) k_prep(ChainArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: Jacobian replay (secp256k1: a = 0).  x = X/Z^2, y = Y/Z^3.
-struct Jac {
-  u32 X[NL], Y[NL], Z[NL];
+// K1: Jacobian replay (secp256k1: a = 0) in lazy arithmetic.  x = X/Z^2, y = Y/Z^3.
+// One thread per (signature, chain); chains are independent op ranges of the tape.
+struct JacL {
+  i32 X[NL], Y[NL], Z[NL];
 };
 
 __device__ __forceinline__ int pt_index(const ChainArgs& A, int32_t pid) {
   return pid < PID_INPUT_BASE ? pid : A.t.n_ptops + (pid - PID_INPUT_BASE);
 }
 
-__device__ __forceinline__ void ld9(const u32* __restrict__ base, int idx, size_t cap, size_t i, u32 (&v)[NL]) {
+template <class T>
+__device__ __forceinline__ void ld9(const u32* __restrict__ base, int idx, size_t cap, size_t i, T (&v)[NL]) {
 #pragma unroll
-  for (int l = 0; l < NL; l++) v[l] = base[((size_t)idx * NL + l) * cap + i];
+  for (int l = 0; l < NL; l++) v[l] = (T)base[((size_t)idx * NL + l) * cap + i];
 }
-__device__ __forceinline__ void sv9(u32* __restrict__ base, int idx, size_t cap, size_t i, const u32 (&v)[NL]) {
+template <class T>
+__device__ __forceinline__ void sv9(u32* __restrict__ base, int idx, size_t cap, size_t i, const T (&v)[NL]) {
 #pragma unroll
-  for (int l = 0; l < NL; l++) base[((size_t)idx * NL + l) * cap + i] = v[l];
+  for (int l = 0; l < NL; l++) base[((size_t)idx * NL + l) * cap + i] = (u32)v[l];
 }
 
-__device__ __forceinline__ void load_jac(const ChainArgs& A, int32_t pid, size_t i, Jac& P) {
+__device__ __forceinline__ void load_jac(const ChainArgs& A, int32_t pid, size_t i, JacL& P) {
   if (pid >= PID_CONST_BASE) {
     const u32* c = A.t.const_points + (size_t)(pid - PID_CONST_BASE) * 18;
 #pragma unroll
     for (int l = 0; l < NL; l++) {
-      P.X[l] = c[l];
-      P.Y[l] = c[NL + l];
-      P.Z[l] = (l == 0) ? 1u : 0u;
+      P.X[l] = (i32)c[l];
+      P.Y[l] = (i32)c[NL + l];
+      P.Z[l] = (l == 0) ? 1 : 0;
     }
   } else {
     int idx = pt_index(A, pid);
@@ -231,59 +235,111 @@ __device__ __forceinline__ void load_jac(const ChainArgs& A, int32_t pid, size_t
   }
 }
 
-// R = P + Q, Z3 = Z1*Z2*H with H = X2*Z1^2 - X1*Z2^2 (so x2 - x1 = Z3 / (Z1^3 Z2^3))
-__device__ __noinline__ void jac_add(const Jac& P, const Jac& Q, Jac& R) {
-  u32 z1z1[NL], z2z2[NL], u1[NL], u2[NL], s1[NL], s2[NL], h[NL], r[NL], t[NL], hh[NL], hhh[NL], v[NL];
-  sqrmod<ModP>(P.Z, z1z1);
-  sqrmod<ModP>(Q.Z, z2z2);
-  mulmod<ModP>(P.X, z2z2, u1);
-  mulmod<ModP>(Q.X, z1z1, u2);
-  mulmod<ModP>(P.Y, Q.Z, t);
-  mulmod<ModP>(t, z2z2, s1);
-  mulmod<ModP>(Q.Y, P.Z, t);
-  mulmod<ModP>(t, z1z1, s2);
-  submod<ModP>(u2, u1, h);
-  submod<ModP>(s2, s1, r);
-  sqrmod<ModP>(h, hh);
-  mulmod<ModP>(h, hh, hhh);
-  mulmod<ModP>(u1, hh, v);
-  // X3 = r^2 - hhh - 2v
-  sqrmod<ModP>(r, t);
-  submod<ModP>(t, hhh, u2);
-  addmod<ModP>(v, v, t);
-  submod<ModP>(u2, t, R.X);
-  // Y3 = r (v - X3) - s1 hhh
-  submod<ModP>(v, R.X, t);
-  mulmod<ModP>(r, t, u2);
-  mulmod<ModP>(s1, hhh, t);
-  submod<ModP>(u2, t, R.Y);
-  // Z3 = Z1 Z2 h
-  mulmod<ModP>(P.Z, Q.Z, t);
-  mulmod<ModP>(t, h, R.Z);
+// The replay kernels run ~1 warp per SM through thousands of multiplications: keep the multiply /
+// square bodies as real functions so the whole loop stays inside the instruction cache (fully
+// inlined, one point addition was ~64 KB of straight-line code and instruction-fetch bound).
+__device__ __noinline__ void lzm(const i32* __restrict__ a, const i32* __restrict__ b, i32* __restrict__ r) {
+  i32 x[NL], y[NL], z[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) { x[l] = a[l]; y[l] = b[l]; }
+  lz_mul(x, y, z);
+#pragma unroll
+  for (int l = 0; l < NL; l++) r[l] = z[l];
+}
+__device__ __noinline__ void lzs(const i32* __restrict__ a, i32* __restrict__ r) {
+  i32 x[NL], z[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) x[l] = a[l];
+  lz_sqr(x, z);
+#pragma unroll
+  for (int l = 0; l < NL; l++) r[l] = z[l];
+}
+#define lz_mul(a, b, r) lzm(a, b, r)
+#define lz_sqr(a, r) lzs(a, r)
+
+__device__ __forceinline__ void lzs_n(i32* x, int n) {
+  for (int k = 0; k < n; k++) {
+    i32 t[NL];
+    lzs(x, t);
+#pragma unroll
+    for (int l = 0; l < NL; l++) x[l] = t[l];
+  }
+}
+// x^(p-2) with the addition chain of p2e_field.cuh::lz_inv, through the out-of-line mul / sqr
+__device__ void lz_inv_calls(const i32 (&a)[NL], i32 (&r)[NL]) {
+  i32 x2[NL], x3[NL], x22[NL], x44[NL], x88[NL], t[NL], u[NL];
+  lzs(a, t); lzm(t, a, x2);
+  lzs(x2, t); lzm(t, a, x3);
+  lz_copy(x3, t); lzs_n(t, 3); lzm(t, x3, u);
+  lz_copy(u, t); lzs_n(t, 3); lzm(t, x3, u);
+  lz_copy(u, t); lzs_n(t, 2); lzm(t, x2, u);
+  lz_copy(u, t); lzs_n(t, 11); lzm(t, u, x22);
+  lz_copy(x22, t); lzs_n(t, 22); lzm(t, x22, x44);
+  lz_copy(x44, t); lzs_n(t, 44); lzm(t, x44, x88);
+  lz_copy(x88, t); lzs_n(t, 88); lzm(t, x88, u);
+  lz_copy(u, t); lzs_n(t, 44); lzm(t, x44, u);
+  lz_copy(u, t); lzs_n(t, 3); lzm(t, x3, u);
+  lz_copy(u, t); lzs_n(t, 23); lzm(t, x22, u);
+  lz_copy(u, t); lzs_n(t, 5); lzm(t, a, u);
+  lz_copy(u, t); lzs_n(t, 3); lzm(t, x2, u);
+  lz_copy(u, t); lzs_n(t, 2); lzm(t, a, r);
 }
 
-// R = 2P, Z3 = 2*Y1*Z1 (so 2y = Z3 / Z1^4)
-__device__ __noinline__ void jac_dbl(const Jac& P, Jac& R) {
-  u32 xx[NL], yy[NL], yyyy[NL], s[NL], m[NL], t[NL], t2[NL];
-  sqrmod<ModP>(P.X, xx);
-  sqrmod<ModP>(P.Y, yy);
-  sqrmod<ModP>(yy, yyyy);
-  mulmod<ModP>(P.X, yy, t);
-  addmod<ModP>(t, t, t2);
-  addmod<ModP>(t2, t2, s);             // S = 4 X YY
-  addmod<ModP>(xx, xx, t);
-  addmod<ModP>(t, xx, m);              // M = 3 XX
-  sqrmod<ModP>(m, t);
-  addmod<ModP>(s, s, t2);
-  submod<ModP>(t, t2, R.X);            // X3 = M^2 - 2S
-  submod<ModP>(s, R.X, t);
-  mulmod<ModP>(m, t, t2);
-  addmod<ModP>(yyyy, yyyy, t);
-  addmod<ModP>(t, t, yy);
-  addmod<ModP>(yy, yy, t);             // 8 YYYY
-  mulmod<ModP>(P.Y, P.Z, xx);
-  submod<ModP>(t2, t, R.Y);            // Y3 = M (S - X3) - 8 YYYY
-  addmod<ModP>(xx, xx, R.Z);           // Z3 = 2 Y1 Z1
+// R = P + Q with Z3 = Z1*Z2*H, H = X2*Z1^2 - X1*Z2^2  (so x2 - x1 = Z3 / (Z1^3 Z2^3)).
+// Q_AFFINE: Z2 == 1 (mixed addition).
+template <bool Q_AFFINE>
+__device__ __forceinline__ void jac_add(const JacL& P, const JacL& Q, JacL& R) {
+  i32 z1z1[NL], u1[NL], u2[NL], s1[NL], s2[NL], h[NL], r[NL], t[NL], hh[NL], hhh[NL], v[NL];
+  lz_sqr(P.Z, z1z1);
+  if (Q_AFFINE) {
+    lz_copy(P.X, u1);
+    lz_copy(P.Y, s1);
+  } else {
+    i32 z2z2[NL];
+    lz_sqr(Q.Z, z2z2);
+    lz_mul(P.X, z2z2, u1);
+    lz_mul(P.Y, Q.Z, t);
+    lz_mul(t, z2z2, s1);
+  }
+  lz_mul(Q.X, z1z1, u2);
+  lz_mul(Q.Y, P.Z, t);
+  lz_mul(t, z1z1, s2);
+  lz_sub(u2, u1, h);
+  lz_sub(s2, s1, r);
+  lz_sqr(h, hh);
+  lz_mul(h, hh, hhh);
+  lz_mul(u1, hh, v);
+  lz_sqr(r, t);
+  lz_sub(t, hhh, u2);
+  lz_lin(u2, 1, v, 2, R.X);            // X3 = r^2 - hhh - 2v
+  lz_sub(v, R.X, t);
+  lz_mul(r, t, u2);
+  lz_mul(s1, hhh, t);
+  lz_sub(u2, t, R.Y);                  // Y3 = r (v - X3) - s1 hhh
+  if (Q_AFFINE) {
+    lz_mul(P.Z, h, R.Z);
+  } else {
+    lz_mul(P.Z, Q.Z, t);
+    lz_mul(t, h, R.Z);
+  }
+}
+
+// R = 2P with Z3 = 2*Y1*Z1  (so 2y = Z3 / Z1^4)
+__device__ __forceinline__ void jac_dbl(const JacL& P, JacL& R) {
+  i32 xx[NL], yy[NL], yyyy[NL], s[NL], m[NL], t[NL], t2[NL];
+  lz_sqr(P.X, xx);
+  lz_sqr(P.Y, yy);
+  lz_sqr(yy, yyyy);
+  lz_mul(P.X, yy, t);
+  lz_lin(t, 4, t, 0, s);               // S = 4 X YY
+  lz_lin(xx, 3, xx, 0, m);             // M = 3 XX
+  lz_sqr(m, t);
+  lz_lin(t, 1, s, 2, R.X);             // X3 = M^2 - 2S
+  lz_sub(s, R.X, t);
+  lz_mul(m, t, t2);
+  lz_lin(t2, 1, yyyy, 8, R.Y);         // Y3 = M (S - X3) - 8 YYYY
+  lz_mul(P.Y, P.Z, t);
+  lz_lin(t, 2, t, 0, R.Z);             // Z3 = 2 Y1 Z1
 }
 
 // digit of `bits` bits at bit position `pos` of a little-endian 29-bit-limb value (nl limbs)
@@ -306,11 +362,14 @@ __device__ __forceinline__ u32 load_scalar_limbs(const ChainArgs& A, const Ref& 
   return e;
 }
 
-__global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A) {
+__global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A, int chain0) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int chain = chain0 + blockIdx.y;
   if (i >= A.n) return;
+  const int k_begin = A.t.chain_begin[chain], k_end = A.t.chain_end[chain];
+  if (k_begin == k_end) return;
   u32 err = 0;
-  // per-signature affine input points (Z = 1)
+  // per-signature affine input points (Z = 1); every chain writes the same values (benign)
   for (int j = 0; j < A.t.n_in_points; j++) {
     u64 w[NL];
     u32 x[NL], y[NL], one[NL];
@@ -334,7 +393,7 @@ __global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A) {
   err |= load_scalar_limbs(A, A.t.msm_k2, i, k2);
 
   int32_t cur = -1;
-  for (int k = 0; k < A.t.n_ptops; k++) {
+  for (int k = k_begin; k < k_end; k++) {
     const PtOp op = A.t.ptops[k];
     int32_t p1 = (op.flags & PF_P1_CUR) ? cur : op.p1;
     int32_t p2 = (op.flags & PF_P2_CUR) ? cur : op.p2;
@@ -348,15 +407,16 @@ __global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A) {
       p2 = A.t.pre_pid[d];
       flag = d != 0;
     }
-    Jac P, R;
+    JacL P, R;
     load_jac(A, p1, i, P);
     if (op.type == PT_DBL) {
       jac_dbl(P, R);
       p2 = p1;
     } else {
-      Jac Q;
+      JacL Q;
       load_jac(A, p2, i, Q);
-      jac_add(P, Q, R);
+      if (op.flags & PF_P2_AFFINE) jac_add<true>(P, Q, R);
+      else jac_add<false>(P, Q, R);
     }
     sv9(A.JX, k, A.cap, i, R.X);
     sv9(A.JY, k, A.cap, i, R.Y);
@@ -366,63 +426,81 @@ __global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A) {
     A.FLG[(size_t)k * A.cap + i] = (uint8_t)flag;
     if (op.flags & PF_SET_CUR) cur = flag ? k : p1;
   }
-  if (err) A.err[i] |= err;
+  if (err) atomicOr(&A.err[i], err);
 }
 
-// K2: one inversion per signature for all Z3's
+// K2: Montgomery's trick over the Z3's of one signature, split in INV_GROUPS independent groups
+// (one field inversion per group) to shorten the dependency chain.
+constexpr int INV_GROUPS = 8;
 __global__ void __launch_bounds__(32) k_chain_invert(ChainArgs A) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
   const int n = A.t.n_ptops;
-  u32 run[NL], z[NL], t[NL];
-  set_zero9(run);
-  run[0] = 1;
-  for (int k = 0; k < n; k++) {
-    sv9(A.ZINV, k, A.cap, i, run);      // prefix product of Z_0..Z_{k-1}
+  const int per = (n + INV_GROUPS - 1) / INV_GROUPS;
+  const int k0 = blockIdx.y * per, k1 = (k0 + per < n) ? k0 + per : n;
+  if (k0 >= k1) return;
+  i32 run[NL], z[NL], t[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) run[l] = (l == 0);
+  for (int k = k0; k < k1; k++) {
+    sv9(A.ZINV, k, A.cap, i, run);      // prefix product of this group's Z's
     ld9(A.JZ, k, A.cap, i, z);
-    mulmod<ModP>(run, z, t);
-    copy9(t, run);
+    lz_mul(run, z, t);
+    lz_copy(t, run);
   }
-  if (is_zero9(run)) {
+  u32 rc[NL];
+  lz_canon(run, rc);
+  if (is_zero9(rc)) {
     // some curve op had x1 == x2 (or y == 0): the reference's inverse() panics
-    A.err[i] |= ERR_INVERSE_ZERO;
-    set_zero9(t);
-    for (int k = 0; k < n; k++) sv9(A.ZINV, k, A.cap, i, t);
+    atomicOr(&A.err[i], (u32)ERR_INVERSE_ZERO);
+    set_zero9(rc);
+    for (int k = k0; k < k1; k++) sv9(A.ZINV, k, A.cap, i, rc);
     return;
   }
-  u32 inv[NL];
-  inv_p(run, inv);
-  for (int k = n - 1; k >= 0; k--) {
-    u32 pre[NL], zi[NL];
+  i32 inv[NL];
+  lz_inv_calls(run, inv);
+  for (int k = k1 - 1; k >= k0; k--) {
+    i32 pre[NL], zi[NL];
     ld9(A.ZINV, k, A.cap, i, pre);
     ld9(A.JZ, k, A.cap, i, z);
-    mulmod<ModP>(inv, pre, zi);
+    lz_mul(inv, pre, zi);
     sv9(A.ZINV, k, A.cap, i, zi);
-    mulmod<ModP>(inv, z, t);
-    copy9(t, inv);
+    lz_mul(inv, z, t);
+    lz_copy(t, inv);
   }
 }
 
-// K3: affine coordinates and Z^3 of every computed point
+// K3: canonical affine coordinates, Z^3, Z and Z^-1 of every computed point
 __global__ void __launch_bounds__(128) k_chain_affine(ChainArgs A) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int k = blockIdx.y;
   if (i >= A.n) return;
-  u32 zi[NL], zi2[NL], zi3[NL], v[NL], r[NL];
+  i32 zi[NL], zi2[NL], zi3[NL], v[NL], r[NL];
+  u32 c[NL];
   ld9(A.ZINV, k, A.cap, i, zi);
-  sqrmod<ModP>(zi, zi2);
-  mulmod<ModP>(zi2, zi, zi3);
+  lz_sqr(zi, zi2);
+  lz_mul(zi2, zi, zi3);
   ld9(A.JX, k, A.cap, i, v);
-  mulmod<ModP>(v, zi2, r);
-  sv9(A.AX, k, A.cap, i, r);
+  lz_mul(v, zi2, r);
+  lz_canon(r, c);
+  sv9(A.AX, k, A.cap, i, c);
   ld9(A.JY, k, A.cap, i, v);
-  mulmod<ModP>(v, zi3, r);
-  sv9(A.AY, k, A.cap, i, r);
+  lz_mul(v, zi3, r);
+  lz_canon(r, c);
+  sv9(A.AY, k, A.cap, i, c);
   ld9(A.JZ, k, A.cap, i, v);
-  sqrmod<ModP>(v, zi2);
-  mulmod<ModP>(zi2, v, r);
-  sv9(A.ZC, k, A.cap, i, r);
+  lz_sqr(v, zi2);
+  lz_mul(zi2, v, r);
+  lz_canon(r, c);
+  sv9(A.ZC, k, A.cap, i, c);
+  lz_canon(v, c);
+  sv9(A.JZ, k, A.cap, i, c);           // canonical Z (read by K4 for doublings)
+  lz_canon(zi, c);
+  sv9(A.ZINV, k, A.cap, i, c);         // canonical Z^-1
 }
+
+#undef lz_mul
+#undef lz_sqr
 
 // K4: expand one curve op into all of its generators' output tuples
 __device__ __forceinline__ void load_affine(const ChainArgs& A, int32_t pid, size_t i, u32 (&x)[NL], u32 (&y)[NL],
@@ -587,6 +665,7 @@ static int upload_tape(const Tape& t, TapeOnDevice& o) {
   o.d.msm_k1 = t.msm_k1;
   o.d.msm_k2 = t.msm_k2;
   o.d.fixed_table_base = t.fixed_table_base;
+  for (int c = 0; c < N_CHAINS; c++) { o.d.chain_begin[c] = t.chain_begin[c]; o.d.chain_end[c] = t.chain_end[c]; }
   o.blob = blob;
   o.n_slots = t.n_slots;
   o.device = c.device;
@@ -650,8 +729,9 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
     unsigned g32 = (unsigned)((cn + 31) / 32), g128 = (unsigned)((cn + 127) / 128);
     k_prep<<<g32, 32, 0, st>>>(A);
     if (no) {
-      k_chain_replay<<<g32, 32, 0, st>>>(A);
-      k_chain_invert<<<g32, 32, 0, st>>>(A);
+      k_chain_replay<<<dim3(g32, 2), 32, 0, st>>>(A, 0);      // fixed-base and msm chains side by side
+      if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g32, 1), 32, 0, st>>>(A, 2);   // join
+      k_chain_invert<<<dim3(g32, INV_GROUPS), 32, 0, st>>>(A);
       k_chain_affine<<<dim3(g128, (unsigned)no), 128, 0, st>>>(A);
       k_chain_expand<<<dim3(g128, (unsigned)no), 128, 0, st>>>(A);
     }

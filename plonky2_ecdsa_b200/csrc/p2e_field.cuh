@@ -464,6 +464,148 @@ P2E_HD void inv_mod(const u32 (&a)[NL], u32 (&r)[NL]) {
 }
 
 // ------------------------------------------------------------------------------------------
+// "Lazy" base-field arithmetic for the latency-bound chain replay (p2e_chain.cu K1-K3).
+// A value is 9 SIGNED 32-bit limbs in redundant form, congruent to the field element mod p:
+//     invariant LZ:  -2^20 <= l_i <= 2^29 + 2^20
+// Products are reduced with 2^261 = d (mod p) using only limb-parallel carry passes (no serial
+// ripple), so a multiplication has a ~100-cycle dependency chain instead of ~1000.  Exact
+// canonical limbs are produced once per stored output by lz_canon().
+typedef int32_t i32;
+constexpr i64 LZ_D0 = 0x7a20, LZ_D1 = 0x100;      // ModP::d
+
+P2E_HD void lz_from_canon(const u32 (&a)[NL], i32 (&r)[NL]) {
+#pragma unroll
+  for (int i = 0; i < NL; i++) r[i] = (i32)a[i];
+}
+
+// columns (|col_i| < 2^62) -> LZ limbs
+P2E_HD void lz_reduce_cols(const i64 (&col)[2 * NL - 1], i32 (&r)[NL]) {
+  // pass A: split every column, push carries one limb up (all independent)
+  i64 n[2 * NL];
+  n[0] = col[0] & LMASK;
+#pragma unroll
+  for (int i = 1; i < 2 * NL - 1; i++) n[i] = (col[i] & LMASK) + (col[i - 1] >> LB);
+  n[2 * NL - 1] = col[2 * NL - 2] >> LB;
+  // fold A: limbs 9..17 times d = 2^261 mod p
+  i64 t[NL + 1];
+#pragma unroll
+  for (int i = 0; i < NL; i++) t[i] = n[i] + n[NL + i] * LZ_D0 + (i > 0 ? n[NL + i - 1] * LZ_D1 : 0);
+  t[NL] = n[2 * NL - 1] * LZ_D1;
+  // pass B
+  i64 u[NL + 2];
+  u[0] = t[0] & LMASK;
+#pragma unroll
+  for (int i = 1; i < NL + 1; i++) u[i] = (t[i] & LMASK) + (t[i - 1] >> LB);
+  u[NL + 1] = t[NL] >> LB;
+  // fold B: limbs 9, 10
+  i64 w0 = u[0] + u[NL] * LZ_D0;
+  i64 w1 = u[1] + u[NL] * LZ_D1 + u[NL + 1] * LZ_D0;
+  i64 w2 = u[2] + u[NL + 1] * LZ_D1;
+  // pass C on the three touched limbs
+  r[0] = (i32)(w0 & LMASK);
+  r[1] = (i32)((w1 & LMASK) + (w0 >> LB));
+  r[2] = (i32)((w2 & LMASK) + (w1 >> LB));
+  r[3] = (i32)(u[3] + (w2 >> LB));
+#pragma unroll
+  for (int i = 4; i < NL; i++) r[i] = (i32)u[i];
+}
+
+P2E_HD void lz_mul(const i32 (&a)[NL], const i32 (&b)[NL], i32 (&r)[NL]) {
+  i64 col[2 * NL - 1];
+#pragma unroll
+  for (int i = 0; i < 2 * NL - 1; i++) col[i] = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+#pragma unroll
+    for (int j = 0; j < NL; j++) col[i + j] += (i64)a[i] * (i64)b[j];
+  }
+  lz_reduce_cols(col, r);
+}
+
+P2E_HD void lz_sqr(const i32 (&a)[NL], i32 (&r)[NL]) {
+  i64 col[2 * NL - 1];
+#pragma unroll
+  for (int i = 0; i < 2 * NL - 1; i++) col[i] = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    col[2 * i] += (i64)a[i] * (i64)a[i];
+#pragma unroll
+    for (int j = i + 1; j < NL; j++) col[i + j] += (i64)(2 * a[i]) * (i64)a[j];
+  }
+  lz_reduce_cols(col, r);
+}
+
+// one limb-parallel carry pass on |l_i| < 2^34 -> LZ
+P2E_HD void lz_weak(const i64 (&l)[NL], i32 (&r)[NL]) {
+  const i64 c8 = l[NL - 1] >> LB;
+  r[0] = (i32)((l[0] & LMASK) + c8 * LZ_D0);
+  r[1] = (i32)((l[1] & LMASK) + (l[0] >> LB) + c8 * LZ_D1);
+#pragma unroll
+  for (int i = 2; i < NL; i++) r[i] = (i32)((l[i] & LMASK) + (l[i - 1] >> LB));
+}
+
+P2E_HD void lz_add(const i32 (&a)[NL], const i32 (&b)[NL], i32 (&r)[NL]) {
+  i64 t[NL];
+#pragma unroll
+  for (int i = 0; i < NL; i++) t[i] = (i64)a[i] + b[i];
+  lz_weak(t, r);
+}
+P2E_HD void lz_sub(const i32 (&a)[NL], const i32 (&b)[NL], i32 (&r)[NL]) {
+  i64 t[NL];
+#pragma unroll
+  for (int i = 0; i < NL; i++) t[i] = (i64)a[i] - b[i];
+  lz_weak(t, r);
+}
+// r = ka * a - kb * b for small non-negative constants (ka, kb <= 8)
+P2E_HD void lz_lin(const i32 (&a)[NL], int ka, const i32 (&b)[NL], int kb, i32 (&r)[NL]) {
+  i64 t[NL];
+#pragma unroll
+  for (int i = 0; i < NL; i++) t[i] = (i64)a[i] * ka - (i64)b[i] * kb;
+  lz_weak(t, r);
+}
+P2E_HD void lz_copy(const i32 (&a)[NL], i32 (&r)[NL]) {
+#pragma unroll
+  for (int i = 0; i < NL; i++) r[i] = a[i];
+}
+P2E_HD void lz_sqr_n(i32 (&x)[NL], int n) {
+  for (int i = 0; i < n; i++) {
+    i32 t[NL];
+    lz_sqr(x, t);
+    lz_copy(t, x);
+  }
+}
+
+// exact canonical limbs in [0, p): add 4p limb-wise (all limbs become non-negative), then the
+// exact fold / conditional-subtract tail of divmod_cols
+P2E_HD void lz_canon(const i32 (&a)[NL], u32 (&r)[NL]) {
+  u64 col[2 * NL - 1];
+#pragma unroll
+  for (int i = 0; i < 2 * NL - 1; i++) col[i] = (i < NL) ? (u64)((i64)a[i] + 4 * (i64)ModP::m(i)) : 0;
+  u32 q10[NL + 1];
+  divmod_cols<ModP, false>(col, r, q10);
+}
+
+// x^(p-2): same addition chain as inv_p, in lazy arithmetic
+P2E_HD void lz_inv(const i32 (&a)[NL], i32 (&r)[NL]) {
+  i32 x2[NL], x3[NL], x22[NL], x44[NL], x88[NL], t[NL], u[NL];
+  lz_sqr(a, t); lz_mul(t, a, x2);
+  lz_sqr(x2, t); lz_mul(t, a, x3);
+  lz_copy(x3, t); lz_sqr_n(t, 3); lz_mul(t, x3, u);          // x6
+  lz_copy(u, t); lz_sqr_n(t, 3); lz_mul(t, x3, u);           // x9
+  lz_copy(u, t); lz_sqr_n(t, 2); lz_mul(t, x2, u);           // x11
+  lz_copy(u, t); lz_sqr_n(t, 11); lz_mul(t, u, x22);         // x22
+  lz_copy(x22, t); lz_sqr_n(t, 22); lz_mul(t, x22, x44);     // x44
+  lz_copy(x44, t); lz_sqr_n(t, 44); lz_mul(t, x44, x88);     // x88
+  lz_copy(x88, t); lz_sqr_n(t, 88); lz_mul(t, x88, u);       // x176
+  lz_copy(u, t); lz_sqr_n(t, 44); lz_mul(t, x44, u);         // x220
+  lz_copy(u, t); lz_sqr_n(t, 3); lz_mul(t, x3, u);           // x223
+  lz_copy(u, t); lz_sqr_n(t, 23); lz_mul(t, x22, u);
+  lz_copy(u, t); lz_sqr_n(t, 5); lz_mul(t, a, u);
+  lz_copy(u, t); lz_sqr_n(t, 3); lz_mul(t, x2, u);
+  lz_copy(u, t); lz_sqr_n(t, 2); lz_mul(t, a, r);
+}
+
+// ------------------------------------------------------------------------------------------
 // A8 + A9 : MulNonnativeGenerator + CheckSumGenerator for one (x, y) pair.
 // q = low 9 limbs of floor(x*y / M) (10th limb dropped like the reference), r = x*y mod M,
 // cs[i] canonical Goldilocks, b[i] = carry_i + 2^33.

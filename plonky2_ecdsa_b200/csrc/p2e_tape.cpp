@@ -168,6 +168,7 @@ class Builder {
  public:
   Tape t;
   APoint rando, neg_rando;
+  int cur_chain = 0;
 
   Builder() {
     u64 k[4];
@@ -310,8 +311,14 @@ class Builder {
   }
   PtT push_ptop(PtOpType type, uint8_t flags, uint16_t aux, int32_t p1, int32_t p2, uint32_t slot, uint32_t xo, uint32_t yo) {
     PtOp o;
-    o.type = type; o.flags = flags; o.aux = aux; o.p1 = p1; o.p2 = p2; o.slot = slot;
+    o.type = type; o.aux = aux; o.p1 = p1; o.p2 = p2; o.slot = slot;
+    // operand 2 is statically affine (constant or per-signature input point): mixed addition
+    bool p2_affine = (type == PT_CADD_FIXED) ||
+                     (type == PT_ADD && !(flags & PF_P2_CUR) && p2 >= PID_INPUT_BASE);
+    o.flags = (uint8_t)(flags | (p2_affine ? PF_P2_AFFINE : 0) | (cur_chain << PF_CHAIN_SHIFT));
     int32_t k = (int32_t)t.ptops.size();
+    if (t.chain_end[cur_chain] == t.chain_begin[cur_chain]) t.chain_begin[cur_chain] = k;
+    t.chain_end[cur_chain] = k + 1;
     t.ptops.push_back(o);
     return point_of_op(k, slot + xo, slot + yo);
   }
@@ -343,6 +350,7 @@ class Builder {
   // fixed_base_curve_mul_circuit (curve_fixed_base.rs:18-66), base = G
   PtT fixed_base_curve_mul(const NNT& scalar) {
     const int n_limbs4 = (9 * LB + 3) / 4;                           // 66 4-bit limbs (split_nonnative.rs:25-50)
+    cur_chain = 0;
     t.fixed_scalar = scalar.r;
     t.fixed_table_base = (uint32_t)(t.const_points.size() / 18);
     APoint base = generator();
@@ -371,6 +379,7 @@ class Builder {
   // curve_msm_circuit (curve_msm.rs:21-79)
   PtT curve_msm(const PtT& p, const PtT& q, const NNT& n, const NNT& m) {
     const int num_limbs = (5 * LB + 1) / 2;                          // 73 2-bit limbs
+    cur_chain = 1;
     t.msm_k1 = n.r;
     t.msm_k2 = m.r;
     int32_t rando_pid = const_point(rando);
@@ -442,8 +451,8 @@ class Builder {
     NNT u2 = mul_nonnative(r, c, 1);
     PtT point1 = fixed_base_curve_mul(u1);
     PtT point2 = glv_mul(pkx, pky, u2);
-    (void)point2;
-    PtT point = curve_add(point1.pid, -1, PF_P2_CUR | PF_SET_CUR);
+    cur_chain = 2;                                                   // joins both chains: runs after them
+    PtT point = curve_add(point1.pid, point2.pid, 0);
     connect_nonnative(r, point.x);
   }
 };

@@ -42,7 +42,9 @@ struct Check {      // connect_nonnative(a, b): limb-wise equality, missing limb
 };
 
 enum PtOpType : uint8_t { PT_ADD = 0, PT_DBL = 1, PT_CADD_FIXED = 2, PT_CADD_MSM = 3 };
-enum PtFlags : uint8_t { PF_P1_CUR = 1, PF_P2_CUR = 2, PF_SET_CUR = 4 };
+enum PtFlags : uint8_t { PF_P1_CUR = 1, PF_P2_CUR = 2, PF_SET_CUR = 4, PF_P2_AFFINE = 8 };
+constexpr int PF_CHAIN_SHIFT = 4;               // flags bits 4-5: independent chain id (0 fixed-base, 1 msm, 2 tail)
+constexpr int N_CHAINS = 3;
 constexpr int32_t PID_CONST_BASE = 1 << 20;     // pid >= this: affine constant #(pid - base)
 struct PtOp {
   uint8_t type;
@@ -72,6 +74,7 @@ struct Tape {
   Ref fixed_scalar;                     // u1 (9 limbs) or space NONE
   Ref msm_k1, msm_k2;                   // 5 limbs each or space NONE
   uint32_t fixed_table_base = 0;        // const point index of window 0 entry 0
+  int32_t chain_begin[N_CHAINS] = {0, 0, 0}, chain_end[N_CHAINS] = {0, 0, 0};   // contiguous op ranges
 };
 
 // verify_secp256k1_message_circuit (gadgets/ecdsa.rs:30-53); inputs msg, r, s, pk.x, pk.y

@@ -111,6 +111,24 @@ void hc_glv(size_t n, const u64* k, u64* out, u32* err) {
   }
 }
 
+// lazy field: ops on raw signed limbs; out = canonical result + raw lazy limbs (for bound checks)
+// op: 0 mul, 1 sqr, 2 add, 3 sub, 4 lin(ka,kb), 5 inv
+void hc_lazy(int op, int ka, int kb, size_t n, const int32_t* a, const int32_t* b, u32* canon, int32_t* raw) {
+  for (size_t i = 0; i < n; i++) {
+    i32 x[NL], y[NL], r[NL];
+    for (int l = 0; l < NL; l++) { x[l] = a[9 * i + l]; y[l] = b[9 * i + l]; }
+    if (op == 0) lz_mul(x, y, r);
+    else if (op == 1) lz_sqr(x, r);
+    else if (op == 2) lz_add(x, y, r);
+    else if (op == 3) lz_sub(x, y, r);
+    else if (op == 4) lz_lin(x, ka, y, kb, r);
+    else lz_inv(x, r);
+    u32 c[NL];
+    lz_canon(r, c);
+    for (int l = 0; l < NL; l++) { canon[9 * i + l] = c[l]; raw[9 * i + l] = r[l]; }
+  }
+}
+
 u64 hc_gl_mul(u64 a, u64 b) { return gl_mul(a, b); }
 u64 hc_gl_add(u64 a, u64 b) { return gl_add(a, b); }
 u64 hc_gl_sub(u64 a, u64 b) { return gl_sub(a, b); }
