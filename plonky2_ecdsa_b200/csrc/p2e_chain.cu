@@ -75,44 +75,84 @@ __device__ __forceinline__ void st9(const ChainArgs& A, u32 slot, size_t i, cons
 }
 __device__ __forceinline__ void st1(const ChainArgs& A, u32 slot, size_t i, u64 v) { A.out[(size_t)slot * A.os + i] = v; }
 
+// The generator cores are kept OUT OF LINE: a curve op expands to 3-4 full mul witnesses plus a dozen
+// small generators, and fully inlined that is ~130 KB of straight-line code per thread -- the
+// expansion kernel was instruction-fetch bound (ncu: stall_no_instruction 7.5 per issue).
+// `o` points at out[slot][i]; consecutive tuple elements are `os` apart.
+
 // MulNonnative row tuple (r, q, check_sum) followed by the CheckSum tuple (b): 51 slots
+template <class MOD>
+__device__ __noinline__ u32 nl_mul(u64* __restrict__ o, size_t os, const u32* __restrict__ xp, const u32* __restrict__ yp,
+                                   u32* __restrict__ rp) {
+  u32 x[NL], y[NL], r[NL], q[NL];
+  u64 cs[2 * NL - 1], b[2 * NL - 2];
+#pragma unroll
+  for (int l = 0; l < NL; l++) { x[l] = xp[l]; y[l] = yp[l]; }
+  u32 e = mul_witness_core<MOD>(x, y, r, q, cs, b);
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    o[(size_t)l * os] = r[l];
+    o[(size_t)(9 + l) * os] = q[l];
+    rp[l] = r[l];
+  }
+#pragma unroll
+  for (int l = 0; l < 2 * NL - 1; l++) o[(size_t)(18 + l) * os] = cs[l];
+#pragma unroll
+  for (int l = 0; l < 2 * NL - 2; l++) o[(size_t)(35 + l) * os] = b[l];
+  return e;
+}
+// ADD / SUB tuple: value[9], overflow
+template <class MOD, bool IS_SUB>
+__device__ __noinline__ void nl_addsub(u64* __restrict__ o, size_t os, const u32* __restrict__ ap, const u32* __restrict__ bp,
+                                       u32* __restrict__ rp) {
+  u32 a[NL], b[NL], r[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) { a[l] = ap[l]; b[l] = bp[l]; }
+  u32 ov = IS_SUB ? sub_witness_core<MOD>(a, b, r) : add_witness_core<MOD>(a, b, r);
+#pragma unroll
+  for (int l = 0; l < NL; l++) { o[(size_t)l * os] = r[l]; rp[l] = r[l]; }
+  o[(size_t)9 * os] = ov;
+}
+// NonNativeInverseGenerator tuple (div, inv) when the inverse is already known
+template <class MOD>
+__device__ __noinline__ u32 nl_inv_known(u64* __restrict__ o, size_t os, const u32* __restrict__ xp, const u32* __restrict__ ip) {
+  u32 xc[NL], inv[NL], div[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) { xc[l] = xp[l]; inv[l] = ip[l]; }
+  u32 e = inv_div_core<MOD>(xc, inv, div);
+#pragma unroll
+  for (int l = 0; l < NL; l++) { o[(size_t)l * os] = div[l]; o[(size_t)(9 + l) * os] = inv[l]; }
+  return e;
+}
+template <class MOD>
+__device__ __noinline__ void nl_mulmod(const u32* __restrict__ ap, const u32* __restrict__ bp, u32* __restrict__ rp) {
+  u32 a[NL], b[NL], r[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) { a[l] = ap[l]; b[l] = bp[l]; }
+  mulmod<MOD>(a, b, r);
+#pragma unroll
+  for (int l = 0; l < NL; l++) rp[l] = r[l];
+}
+
 template <class MOD>
 __device__ __forceinline__ u32 do_mul(const ChainArgs& A, u32 slot, size_t i, const u32 (&x)[NL], const u32 (&y)[NL],
                                       u32 (&r)[NL]) {
-  u32 q[NL];
-  u64 cs[2 * NL - 1], b[2 * NL - 2];
-  u32 e = mul_witness_core<MOD>(x, y, r, q, cs, b);
-  st9(A, slot, i, r);
-  st9(A, slot + 9, i, q);
-#pragma unroll
-  for (int l = 0; l < 2 * NL - 1; l++) st1(A, slot + 18 + l, i, cs[l]);
-#pragma unroll
-  for (int l = 0; l < 2 * NL - 2; l++) st1(A, slot + 35 + l, i, b[l]);
-  return e;
+  return nl_mul<MOD>(A.out + (size_t)slot * A.os + i, A.os, x, y, r);
 }
 template <class MOD>
 __device__ __forceinline__ void do_add(const ChainArgs& A, u32 slot, size_t i, const u32 (&a)[NL], const u32 (&b)[NL],
                                        u32 (&r)[NL]) {
-  u32 ov = add_witness_core<MOD>(a, b, r);
-  st9(A, slot, i, r);
-  st1(A, slot + 9, i, ov);
+  nl_addsub<MOD, false>(A.out + (size_t)slot * A.os + i, A.os, a, b, r);
 }
 template <class MOD>
 __device__ __forceinline__ void do_sub(const ChainArgs& A, u32 slot, size_t i, const u32 (&a)[NL], const u32 (&b)[NL],
                                        u32 (&r)[NL]) {
-  u32 ov = sub_witness_core<MOD>(a, b, r);
-  st9(A, slot, i, r);
-  st1(A, slot + 9, i, ov);
+  nl_addsub<MOD, true>(A.out + (size_t)slot * A.os + i, A.os, a, b, r);
 }
-// NonNativeInverseGenerator tuple (div, inv) when the inverse is already known
 template <class MOD>
 __device__ __forceinline__ u32 do_inv_known(const ChainArgs& A, u32 slot, size_t i, const u32 (&xc)[NL],
                                             const u32 (&inv)[NL]) {
-  u32 div[NL];
-  u32 e = inv_div_core<MOD>(xc, inv, div);
-  st9(A, slot, i, div);
-  st9(A, slot + 9, i, inv);
-  return e;
+  return nl_inv_known<MOD>(A.out + (size_t)slot * A.os + i, A.os, xc, inv);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -537,8 +577,8 @@ __global__ void __launch_bounds__(128) k_chain_expand(ChainArgs A) {
     u32 z1[NL];
     if (p1 >= PID_CONST_BASE) { set_zero9(z1); z1[0] = 1; }
     else ld9(A.JZ, pt_index(A, p1), A.cap, i, z1);
-    mulmod<ModP>(zc1, z1, t);
-    mulmod<ModP>(t, zinv, vinv);
+    nl_mulmod<ModP>(zc1, z1, t);
+    nl_mulmod<ModP>(t, zinv, vinv);
     u32 dy[NL], xx[NL], tr[NL], lam[NL], lam2[NL], xd[NL], x3[NL], xdiff[NL], lx[NL], y3[NL];
     do_add<ModP>(A, s0 + 0, i, y1, y1, dy);                       // double_y
     canon9<ModP>(dy);
@@ -571,8 +611,8 @@ __global__ void __launch_bounds__(128) k_chain_expand(ChainArgs A) {
     u32 x2[NL], y2[NL], zc2[NL];
     load_affine(A, p2, i, x2, y2, zc2);
     // (x2 - x1)^-1 = Z1^3 Z2^3 / Z3
-    mulmod<ModP>(zc1, zc2, t);
-    mulmod<ModP>(t, zinv, vinv);
+    nl_mulmod<ModP>(zc1, zc2, t);
+    nl_mulmod<ModP>(t, zinv, vinv);
     u32 u[NL], v[NL], s[NL], s2[NL], xs[NL], x3[NL], xd[NL], pr[NL], y3[NL];
     do_sub<ModP>(A, s0 + 0, i, y2, y1, u);                        // u
     do_sub<ModP>(A, s0 + 10, i, x2, x1, v);                       // v
