@@ -1,14 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- `python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload ...]`
 
-One "step" = one pass of the hot path over one batch of synthetic input:
-  workload mulmod : 2^20 nonnative secp256k1 base-field mulmod witnesses (BASELINE.json configs[1])
-  workload ecdsa  : 4096 verify_secp256k1_message_circuit witnesses per GPU (configs[2])
-  workload eval   : MulNonnativeGate constraint evaluation over 2^20 LDE rows (configs[4])
-`value` is whole-job throughput with inputs resident in HBM; `e2e` is the same metric through the
-host-pointer C-ABI call (pinned host buffers, H2D + kernel + D2H inside the timed region).
-N > 1: one process per GPU (torchrun), the batch is replicated per rank (weak scaling, no data-path
-collective; a tiny NCCL all_reduce gathers the error counts at the end).
+One "step" = one pass of the hot path over one batch of synthetic input.  Workloads (BASELINE.json):
+  ecdsa  (default, configs[2]) 4096 verify_secp256k1_message_circuit witnesses per GPU, full tape
+  mulmod (configs[1])          2^20 nonnative secp256k1 base-field mulmod witnesses
+  eval   (configs[4])          MulNonnativeGate constraint evaluation over 2^20 Goldilocks LDE rows
+The headline line is the ecdsa workload ("ECDSA circuit witnesses/s"); the mulmod and eval workloads
+are measured in the same run and reported under "secondary" with their own rooflines
+("nonnative mulmod/s" is the second half of BASELINE.json's metric).
+`value` = whole-job throughput with inputs resident in HBM; `e2e` = the same metric through the
+host-pointer C-ABI call (pinned host buffers; H2D + kernels + D2H inside the timed region).
+N > 1: one process per GPU (torchrun); every rank owns its own batch (weak scaling, no data-path
+collective); a single NCCL all_reduce gathers timings / error counts at the end.
 """
 import argparse
 import json
@@ -21,7 +24,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALG_BYTES = {"mulmod": 552, "eval": 560}        # algorithmic bytes per unit (u64 wires in)
+WORKLOAD_NAMES = {
+    "ecdsa": "4096 independent verify_secp256k1_message_circuit witnesses per GPU (full tape: 82615 slots each)",
+    "mulmod": "2^20 secp256k1 base-field nonnative mulmod witnesses (29-bit limbs): q, r, check_sum, carries",
+    "eval": "MulNonnativeGate eval_unfiltered_base_batch over 2^20 Goldilocks LDE rows",
+}
+METRICS = {
+    "ecdsa": ("ecdsa_circuit_witnesses_per_s", "witnesses/s"),
+    "mulmod": ("nonnative_mulmod_witnesses_per_s", "mulmod/s"),
+    "eval": ("mul_nonnative_gate_rows_per_s", "rows/s"),
+}
 
 
 def load_peaks():
@@ -69,13 +81,15 @@ class ClockSampler(threading.Thread):
 
 # ----------------------------------------------------------------------------- reference arm (CPU)
 def run_reference(args):
-    """Times the oracle's C restatement of the reference's CPU generators (the Rust crate cannot be
-    built in this image: no cargo, un-vendored git deps) on all host cores, bounded sample."""
+    """Times the reference's CPU algorithms for the path on the box's host cores.  The Rust crate
+    cannot be built in this image (no cargo/rustc, un-vendored git deps), so this is the oracle's C
+    port of the reference's generators (oracle/p2e_oracle.c): kind == "port"."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import cpu_baseline
-    res = cpu_baseline.run(args.workload, steps=args.steps, warmup=args.warmup)
+    res = cpu_baseline.run(args.workload, steps=args.steps, warmup=min(args.warmup, 1),
+                           budget_s=float(os.environ.get("P2E_REF_BUDGET_S", "60")))
     line = {
         "impl": "reference", "metric": res["metric"], "value": res["value"], "unit": res["unit"],
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
@@ -90,213 +104,256 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- our arm (GPU)
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("P2E_BENCH_WORKLOAD", "mulmod"), choices=["mulmod", "ecdsa", "eval"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
-        return run_reference(args)
+class Bench:
+    def __init__(self, args):
+        import numpy as np
+        import torch
+        import plonky2_ecdsa_b200 as pkg
+        from plonky2_ecdsa_b200 import workload as W
+        self.np, self.torch, self.pkg, self.W = np, torch, pkg, W
+        self.args = args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+        self.eng = pkg.Engine(self.local_rank)
+        self.lib = self.eng.lib
+        self.st = torch.cuda.Stream()          # a real (non-NULL) stream: NULL selects the library's own
+        torch.cuda.set_stream(self.st)
+        self.sp = self.st.cuda_stream
+        assert self.sp != 0
+        self.peak_gbs, self.peak_kind = load_peaks()
 
-    import numpy as np
-    import torch
-    import plonky2_ecdsa_b200 as pkg
-    from plonky2_ecdsa_b200 import workload as W
+    def dev(self, a):
+        return self.torch.from_numpy(a.view(self.np.int64)).cuda()
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    eng = pkg.Engine(local_rank)
-    lib = eng.lib
-    st = torch.cuda.Stream()              # a real (non-NULL) stream: NULL would select the library's own
-    torch.cuda.set_stream(st)
-    stream_ptr = st.cuda_stream
-    assert stream_ptr != 0
-    peak_gbs, peak_kind = load_peaks()
+    def pinned(self, a):
+        return self.torch.from_numpy(a.view(self.np.int64)).pin_memory()
 
-    def dev(a):
-        return torch.from_numpy(a.view(np.int64)).cuda()
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    def pinned(a):
-        t = torch.from_numpy(a.view(np.int64)).pin_memory()
-        return t
+    def setup(self, wl):
+        """Returns dict(step, step_e2e, units, h2d, d2h, alg_bytes, kernel, launches, errs)."""
+        np, torch, pkg, W, lib, eng, sp = self.np, self.torch, self.pkg, self.W, self.lib, self.eng, self.sp
+        if wl == "mulmod":
+            n = 1 << 20
+            x, y = W.mulmod_workload(n, 0, seed=W.SEED + self.rank)
+            xd, yd = self.dev(x), self.dev(y)
+            od = torch.empty((pkg.MUL_OUT_ROWS, n), dtype=torch.int64, device="cuda")
+            ed = torch.empty(n, dtype=torch.int32, device="cuda")
 
-    wl = args.workload
-    launches_per_step = 1
-    if wl == "mulmod":
-        n = 1 << 20
-        x, y = W.mulmod_workload(n, 0, seed=W.SEED + rank)
-        xd, yd = dev(x), dev(y)
-        od = torch.empty((pkg.MUL_OUT_ROWS, n), dtype=torch.int64, device="cuda")
-        ed = torch.empty(n, dtype=torch.int32, device="cuda")
+            def step():
+                rc = lib.p2e_mul_nonnative_witness_dev(0, n, xd.data_ptr(), yd.data_ptr(), n, od.data_ptr(), n, ed.data_ptr(), sp)
+                assert rc == 0, eng.last_error()
+            hx, hy = self.pinned(x), self.pinned(y)
+            ho = torch.empty((pkg.MUL_OUT_ROWS, n), dtype=torch.int64).pin_memory()
+            he = torch.empty(n, dtype=torch.int32).pin_memory()
 
-        def step():
-            rc = lib.p2e_mul_nonnative_witness_dev(0, n, xd.data_ptr(), yd.data_ptr(), n, od.data_ptr(), n, ed.data_ptr(), stream_ptr)
-            assert rc == 0, eng.last_error()
-        hx, hy = pinned(x), pinned(y)
-        ho = torch.empty((pkg.MUL_OUT_ROWS, n), dtype=torch.int64).pin_memory()
-        he = torch.empty(n, dtype=torch.int32).pin_memory()
+            def step_e2e():
+                rc = lib.p2e_mul_nonnative_witness(0, n, hx.data_ptr(), hy.data_ptr(), ho.data_ptr(), he.data_ptr())
+                assert rc == 0, eng.last_error()
+            return dict(step=step, step_e2e=step_e2e, units=n, h2d=2 * 9 * 8 * n, d2h=pkg.MUL_OUT_ROWS * 8 * n + 4 * n,
+                        alg_bytes=552 * n, kernel="k_mul_witness<ModP>", launches=1, err=ed, dtype="u32 limbs / u64 (int)",
+                        keep=(xd, yd, od, hx, hy, ho, he))
+        if wl == "eval":
+            n = 1 << 20
+            w = W.random_goldilocks(W.SEED + self.rank, 53, n)
+            wd = self.dev(w)
+            od = torch.empty((17, n), dtype=torch.int64, device="cuda")
 
-        def step_e2e():
-            rc = lib.p2e_mul_nonnative_witness(0, n, hx.data_ptr(), hy.data_ptr(), ho.data_ptr(), he.data_ptr())
-            assert rc == 0, eng.last_error()
-        h2d, d2h = 2 * 9 * 8 * n, pkg.MUL_OUT_ROWS * 8 * n + 4 * n
-        units = n
-        metric, unit = "nonnative_mulmod_witnesses_per_s", "mulmod/s"
-        workload_name = "2^20 secp256k1 base-field nonnative mulmod witnesses (29-bit limbs): q, r, check_sum, carries"
-        alg_bytes = ALG_BYTES["mulmod"] * n
-        kernel_name = "k_mul_witness<ModP>"
-        dtype = "u32 limbs / u64 (int)"
-    elif wl == "eval":
-        n = 1 << 20
-        w = W.random_goldilocks(W.SEED + rank, 53, n)
-        wd = dev(w)
-        od = torch.empty((17, n), dtype=torch.int64, device="cuda")
+            def step():
+                rc = lib.p2e_eval_mul_nonnative_dev(0, n, wd.data_ptr(), n, od.data_ptr(), n, sp)
+                assert rc == 0, eng.last_error()
+            hw = self.pinned(w)
+            ho = torch.empty((17, n), dtype=torch.int64).pin_memory()
 
-        def step():
-            rc = lib.p2e_eval_mul_nonnative_dev(0, n, wd.data_ptr(), n, od.data_ptr(), n, stream_ptr)
-            assert rc == 0, eng.last_error()
-        hw = pinned(w)
-        ho = torch.empty((17, n), dtype=torch.int64).pin_memory()
-
-        def step_e2e():
-            rc = lib.p2e_eval_mul_nonnative(0, n, hw.data_ptr(), ho.data_ptr())
-            assert rc == 0, eng.last_error()
-        h2d, d2h = 53 * 8 * n, 17 * 8 * n
-        units = n
-        metric, unit = "mul_nonnative_gate_rows_per_s", "rows/s"
-        workload_name = "MulNonnativeGate eval_unfiltered_base_batch over 2^20 Goldilocks LDE rows"
-        alg_bytes = ALG_BYTES["eval"] * n
-        kernel_name = "k_eval_mul_nonnative<ModP>"
-        dtype = "u64 (Goldilocks)"
-    else:
+            def step_e2e():
+                rc = lib.p2e_eval_mul_nonnative(0, n, hw.data_ptr(), ho.data_ptr())
+                assert rc == 0, eng.last_error()
+            return dict(step=step, step_e2e=step_e2e, units=n, h2d=53 * 8 * n, d2h=17 * 8 * n, alg_bytes=560 * n,
+                        kernel="k_eval_mul_nonnative<ModP>", launches=1, err=None, dtype="u64 (Goldilocks)",
+                        keep=(wd, od, hw, ho))
         n = 4096
         slots = int(lib.p2e_ecdsa_tape_slots())
-        if slots == 0:
-            raise SystemExit("ecdsa workload: chain kernels not built")
-        d = W.ecdsa_workload(n, seed=W.SEED + rank)
+        d = W.ecdsa_workload(n, seed=W.SEED + self.rank)
         ins = [d[k] for k in ("msg", "r", "s", "pkx", "pky")]
-        ind = [dev(a) for a in ins]
+        ind = [self.dev(a) for a in ins]
         od = torch.empty((slots, n), dtype=torch.int64, device="cuda")
         ed = torch.empty(n, dtype=torch.int32, device="cuda")
 
         def step():
-            rc = lib.p2e_ecdsa_witness_dev(n, *[t.data_ptr() for t in ind], n, od.data_ptr(), n, ed.data_ptr(), stream_ptr)
+            rc = lib.p2e_ecdsa_witness_dev(n, *[t.data_ptr() for t in ind], n, od.data_ptr(), n, ed.data_ptr(), sp)
             assert rc == 0, eng.last_error()
-        hin = [pinned(a) for a in ins]
+        hin = [self.pinned(a) for a in ins]
         ho = torch.empty((slots, n), dtype=torch.int64).pin_memory()
         he = torch.empty(n, dtype=torch.int32).pin_memory()
 
         def step_e2e():
             rc = lib.p2e_ecdsa_witness(n, *[t.data_ptr() for t in hin], ho.data_ptr(), he.data_ptr())
             assert rc == 0, eng.last_error()
-        h2d, d2h = 5 * 9 * 8 * n, slots * 8 * n + 4 * n
-        units = n
-        metric, unit = "ecdsa_circuit_witnesses_per_s", "witnesses/s"
-        workload_name = "4096 independent verify_secp256k1_message_circuit witnesses per GPU (full tape)"
-        alg_bytes = (slots + 45) * 8 * n
-        kernel_name = "k_chain_expand"
-        dtype = "u32 limbs / u64 (int)"
-        launches_per_step = int(os.environ.get("P2E_ECDSA_LAUNCHES", "4"))
+        return dict(step=step, step_e2e=step_e2e, units=n, h2d=5 * 9 * 8 * n, d2h=slots * 8 * n + 4 * n,
+                    alg_bytes=slots * 8 * n, kernel="k_chain_expand", launches=7, err=ed, dtype="u32 limbs / u64 (int)",
+                    keep=(ind, od, hin, ho, he), slots=slots)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    e0.record(st)
-    for _ in range(args.steps):
-        step()
-    e1.record(st)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    # keep the sampler alive for at least a few samples under load
-    t_end = time.time() + 0.6
-    while time.time() < t_end:
-        step()
-    torch.cuda.synchronize()
-    sampler.stop_flag = True
-    sampler.join()
-    # ---- end-to-end timing through the host-pointer C-ABI
-    e2e_steps = max(2, min(args.steps, 5))
-    step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    def measure(self, wl, steps, warmup, e2e_steps, sample_clocks=False):
+        torch = self.torch
+        s = self.setup(wl)
+        step, step_e2e = s["step"], s["step_e2e"]
+        for _ in range(warmup):
+            step()
+        self.barrier()
+        sampler = None
+        if sample_clocks:
+            sampler = ClockSampler(self.local_rank)
+            sampler.start()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(self.st)
+        for _ in range(steps):
+            step()
+        e1.record(self.st)
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if sampler is not None:
+            t_end = time.time() + 0.7          # keep the load on until nvidia-smi has a few samples
+            while time.time() < t_end:
+                step()
+            torch.cuda.synchronize()
+            sampler.stop_flag = True
+            sampler.join()
+        kernel_ms = None
+        if wl == "ecdsa":
+            self.eng.set_profiling(True)
+            step()
+            kernel_ms = self.eng.last_kernel_times()
+            self.eng.set_profiling(False)
         step_e2e()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    errs = int((ed != 0).sum().item()) if wl != "eval" else 0
-
-    tms = torch.tensor([ms, e2e_ms, float(errs)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        mx = tms.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = tms.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)         # the only collective: final gather of error counts
-        ms, e2e_ms, errs = float(mx[0]), float(mx[1]), int(sm[2])
-    if rank == 0:
-        ms_per_step = ms / args.steps
-        value = units * world / (ms_per_step * 1e-3)
-        e2e_value = units * world / (e2e_ms / e2e_steps * 1e-3)
-        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-        line = {
-            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": dtype, "data": "synthetic",
-            "config": {"workload": workload_name, "units_per_step_per_gpu": units, "seed": hex(W.SEED),
-                       "l2": "inputs+outputs per step exceed the 126 MB L2 (no flush needed)" if wl != "ecdsa" else "outputs per step (2.7 GB) exceed L2",
-                       "error_rows": errs},
-            "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        self.barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        errs = int((s["err"] != 0).sum().item()) if s["err"] is not None else 0
+        t = torch.tensor([ms, e2e_ms, float(errs)], dtype=torch.float64, device="cuda")
+        if self.dist is not None:
+            mx = t.clone()
+            self.dist.all_reduce(mx, op=self.dist.ReduceOp.MAX)       # time = max over ranks
+            sm = t.clone()
+            self.dist.all_reduce(sm, op=self.dist.ReduceOp.SUM)       # final gather of the error counts
+            ms, e2e_ms, errs = float(mx[0]), float(mx[1]), int(sm[2])
+        ms_per_step = ms / steps
+        value = s["units"] * self.world / (ms_per_step * 1e-3)
+        e2e_value = s["units"] * self.world / (e2e_ms / e2e_steps * 1e-3)
+        res = {
+            "metric": METRICS[wl][0], "value": value, "unit": METRICS[wl][1], "ms_per_step": ms_per_step,
+            "dtype": s["dtype"], "units_per_step_per_gpu": s["units"], "error_rows": errs,
+            "e2e": {"value": e2e_value, "unit": METRICS[wl][1], "h2d_bytes_per_step": s["h2d"], "d2h_bytes_per_step": s["d2h"],
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
-            "gpu_launches": launches_per_step * args.steps,
-            "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": achieved / peak_gbs, "peak_kind": peak_kind, "traffic": None,
-                         "algorithmic_bytes_per_launch": alg_bytes},
+            "gpu_launches": s["launches"] * steps,
         }
+        if wl == "ecdsa" and kernel_ms:
+            names = self.eng.CHAIN_KERNELS
+            res["kernel_ms"] = {nm: round(v, 4) for nm, v in zip(names, kernel_ms)}
+            k_expand = kernel_ms[names.index("k_chain_expand")]
+            k_replay = kernel_ms[names.index("k_chain_replay")]
+            achieved = s["alg_bytes"] / (k_expand * 1e-3) / 1e9
+            res["roofline"] = {"bound": "hbm", "kernel": "k_chain_expand", "achieved": achieved, "peak": self.peak_gbs,
+                               "unit": "GB/s", "frac": achieved / self.peak_gbs, "peak_kind": self.peak_kind, "traffic": None,
+                               "algorithmic_bytes_per_launch": s["alg_bytes"], "kernel_ms": k_expand,
+                               "share_of_step": k_expand / sum(kernel_ms)}
+            # INT32 roof of the replay kernel: algorithmic work = 3263 field mults per signature (batched-inversion
+            # algorithm, DESIGN.md section 4) x 81 limb products
+            res["_replay"] = (k_replay, sum(kernel_ms))
+        else:
+            achieved = s["alg_bytes"] / (ms_per_step * 1e-3) / 1e9
+            res["roofline"] = {"bound": "hbm", "kernel": s["kernel"], "achieved": achieved, "peak": self.peak_gbs, "unit": "GB/s",
+                               "frac": achieved / self.peak_gbs, "peak_kind": self.peak_kind, "traffic": None,
+                               "algorithmic_bytes_per_launch": s["alg_bytes"]}
+        if sampler is not None:
+            res["clocks"] = sampler.summary()
+        del s
+        torch.cuda.empty_cache()
+        return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("P2E_BENCH_WORKLOAD", "ecdsa"), choices=["mulmod", "ecdsa", "eval"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    b = Bench(args)
+    wl = args.workload
+    main_res = b.measure(wl, args.steps, args.warmup, e2e_steps=max(2, min(args.steps, 5)), sample_clocks=True)
+    secondary = {}
+    if not args.no_secondary:
+        for w2 in ("mulmod", "eval", "ecdsa"):
+            if w2 != wl:
+                r2 = b.measure(w2, steps=min(args.steps, 20), warmup=3, e2e_steps=2)
+                r2.pop("_replay", None)
+                secondary[w2] = r2
+    if b.rank == 0:
+        line = {
+            "metric": main_res["metric"], "value": main_res["value"], "unit": main_res["unit"], "n_gpus": b.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": main_res["dtype"], "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAMES[wl], "units_per_step_per_gpu": main_res["units_per_step_per_gpu"],
+                       "seed": hex(b.W.SEED), "error_rows": main_res["error_rows"],
+                       "l2": "per-step inputs+outputs exceed the 126 MB L2 (no flush needed)"},
+            "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"], "clocks": main_res.get("clocks"),
+            "roofline": main_res["roofline"],
+        }
+        if "kernel_ms" in main_res:
+            line["kernel_ms"] = main_res["kernel_ms"]
         try:
-            imad = eng.bench_imad(False)
-            imadw = eng.bench_imad(True)
-            line["int32_peak"] = {"imad_gops": imad, "imad_wide_gops": imadw}
-            if wl == "mulmod":
-                line["roofline_int"] = {"bound": "int32", "achieved": 162 * value / 1e9, "peak": imadw, "unit": "G IMAD.WIDE/s",
-                                        "frac": 162 * value / 1e9 / imadw}
+            imad = b.eng.bench_imad(False)
+            imadw = b.eng.bench_imad(True)
+            line["int32_peak"] = {"imad_gops": imad, "imad_wide_gops": imadw, "how": "p2e_bench_imad: 8 independent chains/thread, best of 5"}
+            if "_replay" in main_res:
+                k_replay, _ = main_res["_replay"]
+                work = 3263 * 81 * main_res["units_per_step_per_gpu"]      # limb products per launch
+                line["roofline_int32"] = {"bound": "int32", "kernel": "k_chain_replay", "achieved": work / (k_replay * 1e-3) / 1e9,
+                                          "peak": imadw, "unit": "G IMAD.WIDE/s", "frac": work / (k_replay * 1e-3) / 1e9 / imadw,
+                                          "algorithmic_ops_per_launch": work, "kernel_ms": k_replay}
+            if "mulmod" in secondary or wl == "mulmod":
+                v = secondary["mulmod"]["value"] if "mulmod" in secondary else main_res["value"]
+                line.setdefault("secondary_notes", {})["mulmod_int32_frac"] = 162 * v / b.world / 1e9 / imadw
         except Exception as e:          # noqa: BLE001
             line["int32_peak"] = {"error": str(e)}
-        if not args.no_cpu_baseline and world == 1:
+        if secondary:
+            line["secondary"] = secondary
+        if not args.no_cpu_baseline and b.world == 1:
             try:
                 from oracle import cpu_baseline
-                cb = cpu_baseline.run(wl, steps=1, warmup=0, budget_s=12.0)
+                cb = cpu_baseline.run(wl, steps=1, warmup=0, budget_s=15.0)
                 line["cpu_baseline"] = {"value": cb["value"], "unit": cb["unit"], "cores": cb["cores"], "kind": cb["kind"],
                                         "sample": cb["sample"]}
             except Exception as e:      # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "error": str(e)}
         print(json.dumps(line))
-    eng.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    b.eng.close()
+    if b.dist is not None:
+        b.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

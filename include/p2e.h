@@ -167,6 +167,13 @@ int p2e_glv_mul_witness(size_t n, const uint64_t* k, const uint64_t* px, const u
                         uint64_t* out, uint32_t* err);
 
 /* ---- measurement helpers ---------------------------------------------------------------- */
+/* Per-kernel timing of the chain entry points: when enabled, CUDA events are recorded on the
+ * launching stream between the kernels of the NEXT chain call; p2e_last_kernel_times() then
+ * synchronises and returns their durations in ms, in launch order (k_prep, k_chain_replay,
+ * k_chain_replay(join), k_chain_invert, k_chain_affine, k_chain_expand, k_chain_checks).
+ * Returns the number of kernels written (<= cap), or a negative error. */
+int p2e_set_profiling(int on);
+int p2e_last_kernel_times(float* ms, int cap);
 /* Dependent-free IMAD / IMAD.WIDE throughput microbenchmark on the current device; returns
  * giga-ops per second (one op = one 32-bit lane multiply-add), or a negative error. */
 double p2e_bench_imad(int wide, int iters);

@@ -27,7 +27,8 @@ def load():
     lib.orc_inv_nonnative.argtypes = [ctypes.c_int, _sz, _sz, _sz, _u64p, _u64p, _u64p]
     lib.orc_eval_mul_nonnative.argtypes = [ctypes.c_int, _sz, _sz, _sz, _u64p, _u64p]
     lib.orc_eval_check_sum.argtypes = [_sz, _sz, _sz, _u64p, _u64p]
-    for f in ("orc_mul_nonnative", "orc_inv_nonnative", "orc_eval_mul_nonnative", "orc_eval_check_sum"):
+    lib.orc_ecdsa_witness.argtypes = [_sz, _sz, _sz] + [_u64p] * 9
+    for f in ("orc_mul_nonnative", "orc_inv_nonnative", "orc_eval_mul_nonnative", "orc_eval_check_sum", "orc_ecdsa_witness"):
         getattr(lib, f).restype = None
     return lib
 
@@ -70,6 +71,47 @@ def eval_check_sum(lib, w, threads=1):
     out = np.empty((17, n), dtype=np.uint64)
     _parallel(lambda a, b: lib.orc_eval_check_sum(n, a, b, w.ctypes.data, out.ctypes.data), n, threads)
     return out
+
+
+ECDSA_SLOTS = 82615
+_ECDSA_CONSTS = None
+
+
+def ecdsa_constants():
+    """Circuit constants of verify_secp256k1_message_circuit, computed once by the Python spec (the
+    reference computes them at circuit-build time): see the layout comment in p2e_oracle.c."""
+    global _ECDSA_CONSTS
+    if _ECDSA_CONSTS is None:
+        from oracle import spec as S
+        l9 = S.limbs9
+        rando = S.pt_mul(S.blinding_scalar(), S.G)
+        neg = S.pt_neg(rando)
+        spm = rando
+        for _ in range(146):
+            spm = S.pt_add(spm, spm)
+        nspm = S.pt_neg(spm)
+        c = []
+        for pt in (rando, neg, nspm):
+            c += l9(pt[0]) + l9(pt[1])
+        for v in (S.GLV_BETA, S.GLV_S, 2 * S.GLV_B2, 2 * S.GLV_MINUS_B1, S.GLV_A1, S.GLV_MINUS_B1, S.GLV_A2):
+            c += l9(v)
+        table = []
+        for w in range(66):
+            for pt in S.fixed_base_window(S.G, w):
+                table += l9(pt[0]) + l9(pt[1])
+        _ECDSA_CONSTS = (np.array(c, dtype=np.uint32), np.array(table, dtype=np.uint32))
+    return _ECDSA_CONSTS
+
+
+def ecdsa_witness(lib, msg, r, s, pkx, pky, threads=1):
+    n = msg.shape[1]
+    consts, table = ecdsa_constants()
+    out = np.empty((ECDSA_SLOTS, n), dtype=np.uint64)
+    err = np.empty(n, dtype=np.uint32)
+    ins = [np.ascontiguousarray(a, dtype=np.uint64) for a in (msg, r, s, pkx, pky)]
+    _parallel(lambda a, b: lib.orc_ecdsa_witness(n, a, b, *[x.ctypes.data for x in ins], consts.ctypes.data,
+                                                 table.ctypes.data, out.ctypes.data, err.ctypes.data), n, threads)
+    return out, err
 
 
 def run(workload: str, steps: int = 1, warmup: int = 0, budget_s: float = 15.0):
@@ -115,5 +157,27 @@ def run(workload: str, steps: int = 1, warmup: int = 0, budget_s: float = 15.0):
                 "cores": cores, "kind": "port", "dtype": "u64 (Goldilocks)",
                 "sample": f"first {n} of the 2^20 LDE rows per step; C port of eval_unfiltered per point, {cores} threads",
                 "config": {"workload": "MulNonnativeGate eval_unfiltered_base_batch over 2^20 Goldilocks LDE rows",
+                           "sample_units_per_step": n}}
+    if workload == "ecdsa":
+        full = 4096
+        ecdsa_constants()
+        cap = 1024
+        d = W.ecdsa_workload(cap)
+        ins = [d[k] for k in ("msg", "r", "s", "pkx", "pky")]
+        fn = lambda m: ecdsa_witness(lib, *[np.ascontiguousarray(a[:, :m]) for a in ins], threads=cores)   # noqa: E731
+        m0 = max(cores, 8)
+        t0 = time.perf_counter(); fn(m0); dt = time.perf_counter() - t0
+        n = int(min(cap, max(m0, (budget_s / max(steps + warmup, 1)) / dt * m0)))
+        n = max(cores, n // cores * cores)
+        for _ in range(warmup):
+            fn(n)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn(n)
+        dt = (time.perf_counter() - t0) / steps
+        return {"metric": "ecdsa_circuit_witnesses_per_s", "unit": "witnesses/s", "value": n / dt, "ms_per_step": dt * 1e3,
+                "cores": cores, "kind": "port", "dtype": "u32 words / u64 (int)",
+                "sample": f"first {n} of the 4096 signatures per step; C port of the reference's generators, one Fermat ladder per curve op (oracle/p2e_oracle.c), {cores} threads",
+                "config": {"workload": "4096 independent verify_secp256k1_message_circuit witnesses per GPU (full tape)",
                            "sample_units_per_step": n}}
     raise ValueError(f"no CPU baseline for workload {workload!r}")

@@ -721,6 +721,18 @@ void chain_release_device_tapes() {
   }
 }
 
+static bool g_profiling = false;
+static std::vector<cudaEvent_t> g_events;
+static cudaStream_t g_event_stream = nullptr;
+static void prof_mark(cudaStream_t st) {
+  if (!g_profiling) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, st);
+  g_events.push_back(e);
+  g_event_stream = st;
+}
+
 static size_t chunk_capacity() {
   const char* e = getenv("P2E_CHAIN_CHUNK");
   size_t v = e ? (size_t)atoll(e) : 0;
@@ -767,15 +779,28 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
     A.out = out + c0;
     A.err = err + c0;
     unsigned g32 = (unsigned)((cn + 31) / 32), g128 = (unsigned)((cn + 127) / 128);
+    if (g_profiling && c0 == 0) {
+      for (auto e : g_events) cudaEventDestroy(e);
+      g_events.clear();
+    }
+    const bool prof = g_profiling && c0 == 0;
+    if (prof) prof_mark(st);
     k_prep<<<g32, 32, 0, st>>>(A);
+    if (prof) prof_mark(st);
     if (no) {
       k_chain_replay<<<dim3(g32, 2), 32, 0, st>>>(A, 0);      // fixed-base and msm chains side by side
+      if (prof) prof_mark(st);
       if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g32, 1), 32, 0, st>>>(A, 2);   // join
+      if (prof) prof_mark(st);
       k_chain_invert<<<dim3(g32, INV_GROUPS), 32, 0, st>>>(A);
+      if (prof) prof_mark(st);
       k_chain_affine<<<dim3(g128, (unsigned)no), 128, 0, st>>>(A);
+      if (prof) prof_mark(st);
       k_chain_expand<<<dim3(g128, (unsigned)no), 128, 0, st>>>(A);
+      if (prof) prof_mark(st);
     }
     k_chain_checks<<<g32, 32, 0, st>>>(A);
+    if (prof) prof_mark(st);
     P2E_CUDA(cudaGetLastError());
   }
   return 0;
@@ -819,6 +844,25 @@ static int run_tape_host(const Tape& t, size_t n, const uint64_t* const* ins, in
 using namespace p2e;
 
 extern "C" {
+
+int p2e_set_profiling(int on) {
+  g_profiling = on != 0;
+  return 0;
+}
+
+int p2e_last_kernel_times(float* ms, int cap) {
+  int rc = ensure_ready();
+  if (rc) return rc;
+  if (g_events.size() < 2) return 0;
+  P2E_CUDA(cudaEventSynchronize(g_events.back()));
+  int k = 0;
+  for (size_t j = 0; j + 1 < g_events.size() && k < cap; j++, k++) {
+    float t = 0;
+    P2E_CUDA(cudaEventElapsedTime(&t, g_events[j], g_events[j + 1]));
+    ms[k] = t;
+  }
+  return k;
+}
 
 size_t p2e_ecdsa_tape_slots(void) { return ecdsa_tape().n_slots; }
 size_t p2e_ecdsa_tape_layout(uint32_t* kinds, uint32_t* offsets) { return tape_layout(ecdsa_tape(), kinds, offsets); }

@@ -86,6 +86,8 @@ SIGNATURES = {
     "p2e_glv_mul_tape_layout": (_sz, [_vp, _vp]),
     "p2e_glv_mul_witness_dev": (_int, [_sz, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),
     "p2e_glv_mul_witness": (_int, [_sz, _vp, _vp, _vp, _vp, _vp]),
+    "p2e_set_profiling": (_int, [_int]),
+    "p2e_last_kernel_times": (_int, [_vp, _int]),
     "p2e_bench_imad": (ctypes.c_double, [_int, _int]),
 }
 
@@ -274,6 +276,19 @@ class Engine:
         return out, err
 
     # ---------------------------------------------------------------- measurement
+    CHAIN_KERNELS = ["k_prep", "k_chain_replay", "k_chain_replay(join)", "k_chain_invert", "k_chain_affine",
+                     "k_chain_expand", "k_chain_checks"]
+
+    def set_profiling(self, on: bool):
+        self._check(self.lib.p2e_set_profiling(1 if on else 0))
+
+    def last_kernel_times(self):
+        buf = np.zeros(64, dtype=np.float32)
+        k = self.lib.p2e_last_kernel_times(_ptr(buf), 64)
+        if k < 0:
+            raise P2EError(f"p2e_last_kernel_times failed: {self.last_error()}")
+        return [float(v) for v in buf[:k]]
+
     def bench_imad(self, wide: bool, iters: int = 4096) -> float:
         v = self.lib.p2e_bench_imad(1 if wide else 0, iters)
         if v < 0:
