@@ -178,6 +178,6 @@ def run(workload: str, steps: int = 1, warmup: int = 0, budget_s: float = 15.0):
         return {"metric": "ecdsa_circuit_witnesses_per_s", "unit": "witnesses/s", "value": n / dt, "ms_per_step": dt * 1e3,
                 "cores": cores, "kind": "port", "dtype": "u32 words / u64 (int)",
                 "sample": f"first {n} of the 4096 signatures per step; C port of the reference's generators, one Fermat ladder per curve op (oracle/p2e_oracle.c), {cores} threads",
-                "config": {"workload": "4096 independent verify_secp256k1_message_circuit witnesses per GPU (full tape)",
+                "config": {"workload": "4096 independent verify_secp256k1_message_circuit witnesses per GPU (full tape: 82615 slots each)",
                            "sample_units_per_step": n}}
     raise ValueError(f"no CPU baseline for workload {workload!r}")
