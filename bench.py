@@ -192,8 +192,24 @@ class Bench:
         od = torch.empty((slots, n), dtype=torch.int64, device="cuda")
         ed = torch.empty(n, dtype=torch.int32, device="cuda")
 
+        # Independent batches are enqueued round-robin on S streams (async *_dev API, one output
+        # buffer + one scratch arena per stream) so the latency-bound per-signature kernels of one
+        # batch overlap the bandwidth-bound expansion of another.
+        S = max(1, int(os.environ.get("P2E_BENCH_STREAMS", "4")))
+        streams = [torch.cuda.Stream() for _ in range(S)]
+        ods = [od] + [torch.empty((slots, n), dtype=torch.int64, device="cuda") for _ in range(S - 1)]
+        eds = [ed] + [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(S - 1)]
+        ptrs = [t.data_ptr() for t in ind]
+        state = {"k": 0}
+
         def step():
-            rc = lib.p2e_ecdsa_witness_dev(n, *[t.data_ptr() for t in ind], n, od.data_ptr(), n, ed.data_ptr(), sp)
+            j = state["k"] % S
+            state["k"] += 1
+            rc = lib.p2e_ecdsa_witness_dev(n, *ptrs, n, ods[j].data_ptr(), n, eds[j].data_ptr(), streams[j].cuda_stream)
+            assert rc == 0, eng.last_error()
+
+        def step_single():
+            rc = lib.p2e_ecdsa_witness_dev(n, *ptrs, n, od.data_ptr(), n, ed.data_ptr(), sp)
             assert rc == 0, eng.last_error()
         hin = [self.pinned(a) for a in ins]
         ho = torch.empty((slots, n), dtype=torch.int64).pin_memory()
@@ -204,7 +220,7 @@ class Bench:
             assert rc == 0, eng.last_error()
         return dict(step=step, step_e2e=step_e2e, units=n, h2d=5 * 9 * 8 * n, d2h=slots * 8 * n + 4 * n,
                     alg_bytes=slots * 8 * n, kernel="k_chain_expand", launches=7, err=ed, dtype="u32 limbs / u64 (int)",
-                    keep=(ind, od, hin, ho, he), slots=slots)
+                    keep=(ind, ods, eds, hin, ho, he), slots=slots, streams=streams, step_single=step_single)
 
     def measure(self, wl, steps, warmup, e2e_steps, sample_clocks=False):
         torch = self.torch
@@ -217,14 +233,30 @@ class Bench:
         if sample_clocks:
             sampler = ClockSampler(self.local_rank)
             sampler.start()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record(self.st)
-        for _ in range(steps):
-            step()
-        e1.record(self.st)
-        self.barrier()
-        ms = e0.elapsed_time(e1)
+        streams = s.get("streams") or []
+
+        def timed(fn, k):
+            """k calls of fn between two events on the main stream; worker streams fork from / join into it."""
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(self.st)
+            for w in streams:
+                w.wait_event(e0)
+            for _ in range(k):
+                fn()
+            for w in streams:
+                ev = torch.cuda.Event()
+                ev.record(w)
+                self.st.wait_event(ev)
+            e1.record(self.st)
+            self.barrier()
+            return e0.elapsed_time(e1)
+        ms = timed(step, steps)
+        latency_ms = None
+        if "step_single" in s:
+            s["step_single"]()
+            self.barrier()
+            latency_ms = timed(s["step_single"], min(steps, 10)) / min(steps, 10)
         if sampler is not None:
             t_end = time.time() + 0.7          # keep the load on until nvidia-smi has a few samples
             while time.time() < t_end:
@@ -235,7 +267,7 @@ class Bench:
         kernel_ms = None
         if wl == "ecdsa":
             self.eng.set_profiling(True)
-            step()
+            s["step_single"]()
             kernel_ms = self.eng.last_kernel_times()
             self.eng.set_profiling(False)
         step_e2e()
@@ -263,6 +295,9 @@ class Bench:
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
             "gpu_launches": s["launches"] * steps,
         }
+        if streams:
+            res["streams"] = len(streams)
+            res["single_stream_ms_per_step"] = latency_ms
         if wl == "ecdsa" and kernel_ms:
             names = self.eng.CHAIN_KERNELS
             res["kernel_ms"] = {nm: round(v, 4) for nm, v in zip(names, kernel_ms)}
@@ -319,7 +354,11 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": main_res["dtype"], "data": "synthetic",
             "config": {"workload": WORKLOAD_NAMES[wl], "units_per_step_per_gpu": main_res["units_per_step_per_gpu"],
                        "seed": hex(b.W.SEED), "error_rows": main_res["error_rows"],
-                       "l2": "per-step inputs+outputs exceed the 126 MB L2 (no flush needed)"},
+                       "l2": "per-step inputs+outputs exceed the 126 MB L2 (no flush needed)",
+                       "streams": main_res.get("streams", 1),
+                       "pipelining": "steps are independent batches enqueued round-robin on `streams` CUDA streams through the async *_dev "
+                                     "entry point; ms_per_step = timed region / steps; single_stream_ms_per_step = one batch at a time",
+                       "single_stream_ms_per_step": main_res.get("single_stream_ms_per_step")},
             "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"], "clocks": main_res.get("clocks"),
             "roofline": main_res["roofline"],
         }

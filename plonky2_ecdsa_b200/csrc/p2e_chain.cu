@@ -713,7 +713,58 @@ static int upload_tape(const Tape& t, TapeOnDevice& o) {
   return 0;
 }
 
+// One scratch arena per launching stream, so independent batches enqueued on different streams
+// can overlap (the per-signature kernels K0-K2 are latency-bound and leave most SMs idle).
+struct Arena {
+  cudaStream_t stream = nullptr;
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  bool used = false;
+  // internal streams: the latency-bound per-signature kernels (K0-K2) run at high priority so their
+  // few small blocks are scheduled ahead of another batch's bandwidth-bound expansion (K3-K5)
+  cudaStream_t hi = nullptr, lo = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_mid = nullptr, ev_out = nullptr;
+};
+constexpr int MAX_ARENAS = 16;
+static Arena g_arenas[MAX_ARENAS];
+
+static int get_arena(cudaStream_t st, size_t bytes, Arena** out) {
+  Arena* a = nullptr;
+  for (auto& x : g_arenas) if (x.used && x.stream == st) { a = &x; break; }
+  if (!a) {
+    for (auto& x : g_arenas) if (!x.used) { a = &x; break; }
+    if (!a) return set_error_msg("too many distinct streams in flight (max 16 chain arenas)");
+    int lo_p = 0, hi_p = 0;
+    P2E_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));     // numerically lower = higher priority
+    P2E_CUDA(cudaStreamCreateWithPriority(&a->hi, cudaStreamNonBlocking, hi_p));
+    P2E_CUDA(cudaStreamCreateWithPriority(&a->lo, cudaStreamNonBlocking, lo_p));
+    P2E_CUDA(cudaEventCreateWithFlags(&a->ev_in, cudaEventDisableTiming));
+    P2E_CUDA(cudaEventCreateWithFlags(&a->ev_mid, cudaEventDisableTiming));
+    P2E_CUDA(cudaEventCreateWithFlags(&a->ev_out, cudaEventDisableTiming));
+    a->used = true;
+    a->stream = st;
+  }
+  if (a->bytes < bytes) {
+    if (a->ptr) P2E_CUDA(cudaFree(a->ptr));
+    a->ptr = nullptr;
+    a->bytes = 0;
+    P2E_CUDA(cudaMalloc(&a->ptr, bytes));
+    a->bytes = bytes;
+  }
+  *out = a;
+  return 0;
+}
+
 void chain_release_device_tapes() {
+  for (auto& a : g_arenas) {
+    if (a.ptr) cudaFree(a.ptr);
+    if (a.hi) cudaStreamDestroy(a.hi);
+    if (a.lo) cudaStreamDestroy(a.lo);
+    if (a.ev_in) cudaEventDestroy(a.ev_in);
+    if (a.ev_mid) cudaEventDestroy(a.ev_mid);
+    if (a.ev_out) cudaEventDestroy(a.ev_out);
+    a = Arena();
+  }
   for (auto& o : g_dev_tapes) {
     if (o.ready && o.blob) cudaFree(o.blob);
     o.ready = false;
@@ -754,8 +805,17 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
   // scratch layout (u32 words)
   size_t words = (np * 27 * 2 + no * 9) * cap;      // JX JY JZ AX AY ZC + ZINV
   size_t bytes = words * 4 + no * cap * (4 + 4 + 1) + 64;
-  void* scratch = nullptr;
-  if ((rc = get_scratch(3, bytes, &scratch))) return rc;
+  Arena* arena = nullptr;
+  if ((rc = get_arena(st, bytes, &arena))) return rc;
+  void* scratch = arena->ptr;
+  // profiling keeps everything on the caller's stream so the events bracket each kernel
+  const bool split = !g_profiling && getenv("P2E_CHAIN_NO_PRIORITY") == nullptr;
+  cudaStream_t s_hi = split ? arena->hi : st, s_lo = split ? arena->lo : st;
+  if (split) {
+    P2E_CUDA(cudaEventRecord(arena->ev_in, st));
+    P2E_CUDA(cudaStreamWaitEvent(s_hi, arena->ev_in, 0));
+    P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_in, 0));    // orders this call after the previous one's K3-K5 reads
+  }
   ChainArgs A;
   A.t = o.d;
   A.is = is;
@@ -785,23 +845,39 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
     }
     const bool prof = g_profiling && c0 == 0;
     if (prof) prof_mark(st);
-    k_prep<<<g32, 32, 0, st>>>(A);
+    k_prep<<<g32, 32, 0, s_hi>>>(A);
     if (prof) prof_mark(st);
     if (no) {
-      k_chain_replay<<<dim3(g32, 2), 32, 0, st>>>(A, 0);      // fixed-base and msm chains side by side
+      k_chain_replay<<<dim3(g32, 2), 32, 0, s_hi>>>(A, 0);      // fixed-base and msm chains side by side
       if (prof) prof_mark(st);
-      if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g32, 1), 32, 0, st>>>(A, 2);   // join
+      if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g32, 1), 32, 0, s_hi>>>(A, 2);   // join
       if (prof) prof_mark(st);
-      k_chain_invert<<<dim3(g32, INV_GROUPS), 32, 0, st>>>(A);
+      k_chain_invert<<<dim3(g32, INV_GROUPS), 32, 0, s_hi>>>(A);
       if (prof) prof_mark(st);
-      k_chain_affine<<<dim3(g128, (unsigned)no), 128, 0, st>>>(A);
+      if (split) {
+        P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
+        P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
+      }
+      k_chain_affine<<<dim3(g128, (unsigned)no), 128, 0, s_lo>>>(A);
       if (prof) prof_mark(st);
-      k_chain_expand<<<dim3(g128, (unsigned)no), 128, 0, st>>>(A);
+      k_chain_expand<<<dim3(g128, (unsigned)no), 128, 0, s_lo>>>(A);
       if (prof) prof_mark(st);
+    } else if (split) {
+      P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
+      P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
     }
-    k_chain_checks<<<g32, 32, 0, st>>>(A);
+    k_chain_checks<<<g32, 32, 0, s_lo>>>(A);
     if (prof) prof_mark(st);
+    if (split && c0 + cap < n) {
+      // next chunk reuses the scratch: its K0-K2 must not start before this chunk's K3-K5 are done
+      P2E_CUDA(cudaEventRecord(arena->ev_out, s_lo));
+      P2E_CUDA(cudaStreamWaitEvent(s_hi, arena->ev_out, 0));
+    }
     P2E_CUDA(cudaGetLastError());
+  }
+  if (split) {
+    P2E_CUDA(cudaEventRecord(arena->ev_out, s_lo));
+    P2E_CUDA(cudaStreamWaitEvent(st, arena->ev_out, 0));
   }
   return 0;
 }
