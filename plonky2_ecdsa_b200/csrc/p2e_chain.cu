@@ -471,12 +471,11 @@ __global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A, int chain0) {
 
 // K2: Montgomery's trick over the Z3's of one signature, split in INV_GROUPS independent groups
 // (one field inversion per group) to shorten the dependency chain.
-constexpr int INV_GROUPS = 8;
 __global__ void __launch_bounds__(32) k_chain_invert(ChainArgs A) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
   const int n = A.t.n_ptops;
-  const int per = (n + INV_GROUPS - 1) / INV_GROUPS;
+  const int per = (n + (int)gridDim.y - 1) / (int)gridDim.y;
   const int k0 = blockIdx.y * per, k1 = (k0 + per < n) ? k0 + per : n;
   if (k0 >= k1) return;
   i32 run[NL], z[NL], t[NL];
@@ -510,7 +509,8 @@ __global__ void __launch_bounds__(32) k_chain_invert(ChainArgs A) {
   }
 }
 
-// K3: canonical affine coordinates, Z^3, Z and Z^-1 of every computed point
+// K3: canonical affine coordinates of every computed point; Z^3 stays in lazy limbs (K4 folds it
+// into its own lazy product and canonicalises once)
 __global__ void __launch_bounds__(128) k_chain_affine(ChainArgs A) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int k = blockIdx.y;
@@ -531,27 +531,40 @@ __global__ void __launch_bounds__(128) k_chain_affine(ChainArgs A) {
   ld9(A.JZ, k, A.cap, i, v);
   lz_sqr(v, zi2);
   lz_mul(zi2, v, r);
-  lz_canon(r, c);
-  sv9(A.ZC, k, A.cap, i, c);
-  lz_canon(v, c);
-  sv9(A.JZ, k, A.cap, i, c);           // canonical Z (read by K4 for doublings)
-  lz_canon(zi, c);
-  sv9(A.ZINV, k, A.cap, i, c);         // canonical Z^-1
+  sv9(A.ZC, k, A.cap, i, r);
 }
 
 #undef lz_mul
 #undef lz_sqr
 
 // K4: expand one curve op into all of its generators' output tuples
+__device__ __noinline__ void nl_lzmul(const i32* __restrict__ ap, const i32* __restrict__ bp, i32* __restrict__ rp) {
+  i32 a[NL], b[NL], r[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) { a[l] = ap[l]; b[l] = bp[l]; }
+  lz_mul(a, b, r);
+#pragma unroll
+  for (int l = 0; l < NL; l++) rp[l] = r[l];
+}
+__device__ __noinline__ void nl_lzcanon(const i32* __restrict__ ap, u32* __restrict__ rp) {
+  i32 a[NL];
+  u32 r[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) a[l] = ap[l];
+  lz_canon(a, r);
+#pragma unroll
+  for (int l = 0; l < NL; l++) rp[l] = r[l];
+}
+
 __device__ __forceinline__ void load_affine(const ChainArgs& A, int32_t pid, size_t i, u32 (&x)[NL], u32 (&y)[NL],
-                                            u32 (&zc)[NL]) {
+                                            i32 (&zc)[NL]) {
   if (pid >= PID_CONST_BASE) {
     const u32* c = A.t.const_points + (size_t)(pid - PID_CONST_BASE) * 18;
 #pragma unroll
     for (int l = 0; l < NL; l++) {
       x[l] = c[l];
       y[l] = c[NL + l];
-      zc[l] = (l == 0) ? 1u : 0u;
+      zc[l] = (l == 0) ? 1 : 0;
     }
   } else {
     int idx = pt_index(A, pid);
@@ -569,16 +582,22 @@ __global__ void __launch_bounds__(128) k_chain_expand(ChainArgs A) {
   const u32 s0 = op.slot;
   int32_t p1 = A.SRC1[(size_t)k * A.cap + i];
   u32 e = 0;
-  u32 x1[NL], y1[NL], zc1[NL], zinv[NL], vinv[NL], t[NL];
+  u32 x1[NL], y1[NL], vinv[NL];
+  i32 zc1[NL], zinv[NL], t[NL], t2[NL];
   load_affine(A, p1, i, x1, y1, zc1);
   ld9(A.ZINV, k, A.cap, i, zinv);
   if (op.type == PT_DBL) {
     // (2y)^-1 = Z1^4 / Z3
-    u32 z1[NL];
-    if (p1 >= PID_CONST_BASE) { set_zero9(z1); z1[0] = 1; }
-    else ld9(A.JZ, pt_index(A, p1), A.cap, i, z1);
-    nl_mulmod<ModP>(zc1, z1, t);
-    nl_mulmod<ModP>(t, zinv, vinv);
+    i32 z1[NL];
+    if (p1 >= PID_CONST_BASE) {
+#pragma unroll
+      for (int l = 0; l < NL; l++) z1[l] = (l == 0);
+    } else {
+      ld9(A.JZ, pt_index(A, p1), A.cap, i, z1);
+    }
+    nl_lzmul(zc1, z1, t);
+    nl_lzmul(t, zinv, t2);
+    nl_lzcanon(t2, vinv);
     u32 dy[NL], xx[NL], tr[NL], lam[NL], lam2[NL], xd[NL], x3[NL], xdiff[NL], lx[NL], y3[NL];
     do_add<ModP>(A, s0 + 0, i, y1, y1, dy);                       // double_y
     canon9<ModP>(dy);
@@ -608,11 +627,13 @@ __global__ void __launch_bounds__(128) k_chain_expand(ChainArgs A) {
     do_sub<ModP>(A, s0 + 272, i, lx, y1, y3);                     // y3
   } else {
     int32_t p2 = A.SRC2[(size_t)k * A.cap + i];
-    u32 x2[NL], y2[NL], zc2[NL];
+    u32 x2[NL], y2[NL];
+    i32 zc2[NL];
     load_affine(A, p2, i, x2, y2, zc2);
     // (x2 - x1)^-1 = Z1^3 Z2^3 / Z3
-    nl_mulmod<ModP>(zc1, zc2, t);
-    nl_mulmod<ModP>(t, zinv, vinv);
+    nl_lzmul(zc1, zc2, t);
+    nl_lzmul(t, zinv, t2);
+    nl_lzcanon(t2, vinv);
     u32 u[NL], v[NL], s[NL], s2[NL], xs[NL], x3[NL], xd[NL], pr[NL], y3[NL];
     do_sub<ModP>(A, s0 + 0, i, y2, y1, u);                        // u
     do_sub<ModP>(A, s0 + 10, i, x2, x1, v);                       // v
@@ -784,6 +805,17 @@ static void prof_mark(cudaStream_t st) {
   g_event_stream = st;
 }
 
+static unsigned inv_groups() {
+  static int g = 0;
+  if (!g) {
+    const char* e = getenv("P2E_CHAIN_INV_GROUPS");
+    g = e ? atoi(e) : 8;
+    if (g < 1) g = 1;
+    if (g > 64) g = 64;
+  }
+  return (unsigned)g;
+}
+
 static size_t chunk_capacity() {
   const char* e = getenv("P2E_CHAIN_CHUNK");
   size_t v = e ? (size_t)atoll(e) : 0;
@@ -852,7 +884,7 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
       if (prof) prof_mark(st);
       if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g32, 1), 32, 0, s_hi>>>(A, 2);   // join
       if (prof) prof_mark(st);
-      k_chain_invert<<<dim3(g32, INV_GROUPS), 32, 0, s_hi>>>(A);
+      k_chain_invert<<<dim3(g32, inv_groups()), 32, 0, s_hi>>>(A);
       if (prof) prof_mark(st);
       if (split) {
         P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
