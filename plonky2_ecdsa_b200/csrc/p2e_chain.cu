@@ -80,79 +80,86 @@ __device__ __forceinline__ void st1(const ChainArgs& A, u32 slot, size_t i, u64 
 // expansion kernel was instruction-fetch bound (ncu: stall_no_instruction 7.5 per issue).
 // `o` points at out[slot][i]; consecutive tuple elements are `os` apart.
 
+// Operands and results cross the call boundary BY VALUE (structs of 9 limbs): ptxas keeps them in
+// registers, whereas pointer arguments forced every operand through local memory (ncu: the
+// expansion kernel wrote 3.45 GB to DRAM for 2.63 GB of output).
+struct W9 { u32 v[NL]; };
+struct I9 { i32 v[NL]; };
+struct W9E { W9 r; u32 e; };
+__device__ __forceinline__ W9 w9(const u32 (&a)[NL]) { W9 r;
+#pragma unroll
+  for (int l = 0; l < NL; l++) r.v[l] = a[l];
+  return r; }
+__device__ __forceinline__ I9 i9(const i32 (&a)[NL]) { I9 r;
+#pragma unroll
+  for (int l = 0; l < NL; l++) r.v[l] = a[l];
+  return r; }
+
 // MulNonnative row tuple (r, q, check_sum) followed by the CheckSum tuple (b): 51 slots
 template <class MOD>
-__device__ __noinline__ u32 nl_mul(u64* __restrict__ o, size_t os, const u32* __restrict__ xp, const u32* __restrict__ yp,
-                                   u32* __restrict__ rp) {
-  u32 x[NL], y[NL], r[NL], q[NL];
+__device__ __noinline__ W9E nl_mul(u64* __restrict__ o, size_t os, W9 x, W9 y) {
+  u32 r[NL], q[NL];
   u64 cs[2 * NL - 1], b[2 * NL - 2];
-#pragma unroll
-  for (int l = 0; l < NL; l++) { x[l] = xp[l]; y[l] = yp[l]; }
-  u32 e = mul_witness_core<MOD>(x, y, r, q, cs, b);
+  W9E ret;
+  ret.e = mul_witness_core<MOD>(x.v, y.v, r, q, cs, b);
 #pragma unroll
   for (int l = 0; l < NL; l++) {
     o[(size_t)l * os] = r[l];
     o[(size_t)(9 + l) * os] = q[l];
-    rp[l] = r[l];
+    ret.r.v[l] = r[l];
   }
 #pragma unroll
   for (int l = 0; l < 2 * NL - 1; l++) o[(size_t)(18 + l) * os] = cs[l];
 #pragma unroll
   for (int l = 0; l < 2 * NL - 2; l++) o[(size_t)(35 + l) * os] = b[l];
-  return e;
+  return ret;
 }
 // ADD / SUB tuple: value[9], overflow
 template <class MOD, bool IS_SUB>
-__device__ __noinline__ void nl_addsub(u64* __restrict__ o, size_t os, const u32* __restrict__ ap, const u32* __restrict__ bp,
-                                       u32* __restrict__ rp) {
-  u32 a[NL], b[NL], r[NL];
+__device__ __noinline__ W9 nl_addsub(u64* __restrict__ o, size_t os, W9 a, W9 b) {
+  W9 r;
+  u32 ov = IS_SUB ? sub_witness_core<MOD>(a.v, b.v, r.v) : add_witness_core<MOD>(a.v, b.v, r.v);
 #pragma unroll
-  for (int l = 0; l < NL; l++) { a[l] = ap[l]; b[l] = bp[l]; }
-  u32 ov = IS_SUB ? sub_witness_core<MOD>(a, b, r) : add_witness_core<MOD>(a, b, r);
-#pragma unroll
-  for (int l = 0; l < NL; l++) { o[(size_t)l * os] = r[l]; rp[l] = r[l]; }
+  for (int l = 0; l < NL; l++) o[(size_t)l * os] = r.v[l];
   o[(size_t)9 * os] = ov;
+  return r;
 }
 // NonNativeInverseGenerator tuple (div, inv) when the inverse is already known
 template <class MOD>
-__device__ __noinline__ u32 nl_inv_known(u64* __restrict__ o, size_t os, const u32* __restrict__ xp, const u32* __restrict__ ip) {
-  u32 xc[NL], inv[NL], div[NL];
+__device__ __noinline__ u32 nl_inv_known(u64* __restrict__ o, size_t os, W9 xc, W9 inv) {
+  u32 div[NL];
+  u32 e = inv_div_core<MOD>(xc.v, inv.v, div);
 #pragma unroll
-  for (int l = 0; l < NL; l++) { xc[l] = xp[l]; inv[l] = ip[l]; }
-  u32 e = inv_div_core<MOD>(xc, inv, div);
-#pragma unroll
-  for (int l = 0; l < NL; l++) { o[(size_t)l * os] = div[l]; o[(size_t)(9 + l) * os] = inv[l]; }
+  for (int l = 0; l < NL; l++) { o[(size_t)l * os] = div[l]; o[(size_t)(9 + l) * os] = inv.v[l]; }
   return e;
-}
-template <class MOD>
-__device__ __noinline__ void nl_mulmod(const u32* __restrict__ ap, const u32* __restrict__ bp, u32* __restrict__ rp) {
-  u32 a[NL], b[NL], r[NL];
-#pragma unroll
-  for (int l = 0; l < NL; l++) { a[l] = ap[l]; b[l] = bp[l]; }
-  mulmod<MOD>(a, b, r);
-#pragma unroll
-  for (int l = 0; l < NL; l++) rp[l] = r[l];
 }
 
 template <class MOD>
 __device__ __forceinline__ u32 do_mul(const ChainArgs& A, u32 slot, size_t i, const u32 (&x)[NL], const u32 (&y)[NL],
                                       u32 (&r)[NL]) {
-  return nl_mul<MOD>(A.out + (size_t)slot * A.os + i, A.os, x, y, r);
+  W9E t = nl_mul<MOD>(A.out + (size_t)slot * A.os + i, A.os, w9(x), w9(y));
+#pragma unroll
+  for (int l = 0; l < NL; l++) r[l] = t.r.v[l];
+  return t.e;
 }
 template <class MOD>
 __device__ __forceinline__ void do_add(const ChainArgs& A, u32 slot, size_t i, const u32 (&a)[NL], const u32 (&b)[NL],
                                        u32 (&r)[NL]) {
-  nl_addsub<MOD, false>(A.out + (size_t)slot * A.os + i, A.os, a, b, r);
+  W9 t = nl_addsub<MOD, false>(A.out + (size_t)slot * A.os + i, A.os, w9(a), w9(b));
+#pragma unroll
+  for (int l = 0; l < NL; l++) r[l] = t.v[l];
 }
 template <class MOD>
 __device__ __forceinline__ void do_sub(const ChainArgs& A, u32 slot, size_t i, const u32 (&a)[NL], const u32 (&b)[NL],
                                        u32 (&r)[NL]) {
-  nl_addsub<MOD, true>(A.out + (size_t)slot * A.os + i, A.os, a, b, r);
+  W9 t = nl_addsub<MOD, true>(A.out + (size_t)slot * A.os + i, A.os, w9(a), w9(b));
+#pragma unroll
+  for (int l = 0; l < NL; l++) r[l] = t.v[l];
 }
 template <class MOD>
 __device__ __forceinline__ u32 do_inv_known(const ChainArgs& A, u32 slot, size_t i, const u32 (&xc)[NL],
                                             const u32 (&inv)[NL]) {
-  return nl_inv_known<MOD>(A.out + (size_t)slot * A.os + i, A.os, xc, inv);
+  return nl_inv_known<MOD>(A.out + (size_t)slot * A.os + i, A.os, w9(xc), w9(inv));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -278,32 +285,34 @@ __device__ __forceinline__ void load_jac(const ChainArgs& A, int32_t pid, size_t
 // The replay kernels run ~1 warp per SM through thousands of multiplications: keep the multiply /
 // square bodies as real functions so the whole loop stays inside the instruction cache (fully
 // inlined, one point addition was ~64 KB of straight-line code and instruction-fetch bound).
-__device__ __noinline__ void lzm(const i32* __restrict__ a, const i32* __restrict__ b, i32* __restrict__ r) {
-  i32 x[NL], y[NL], z[NL];
-#pragma unroll
-  for (int l = 0; l < NL; l++) { x[l] = a[l]; y[l] = b[l]; }
-  lz_mul(x, y, z);
-#pragma unroll
-  for (int l = 0; l < NL; l++) r[l] = z[l];
+__device__ __noinline__ I9 lzm_v(I9 a, I9 b) {
+  I9 r;
+  lz_mul(a.v, b.v, r.v);
+  return r;
 }
-__device__ __noinline__ void lzs(const i32* __restrict__ a, i32* __restrict__ r) {
-  i32 x[NL], z[NL];
+__device__ __noinline__ I9 lzs_v(I9 a) {
+  I9 r;
+  lz_sqr(a.v, r.v);
+  return r;
+}
+__device__ __forceinline__ void lzm(const i32 (&a)[NL], const i32 (&b)[NL], i32 (&r)[NL]) {
+  I9 t = lzm_v(i9(a), i9(b));
 #pragma unroll
-  for (int l = 0; l < NL; l++) x[l] = a[l];
-  lz_sqr(x, z);
+  for (int l = 0; l < NL; l++) r[l] = t.v[l];
+}
+__device__ __forceinline__ void lzs(const i32 (&a)[NL], i32 (&r)[NL]) {
+  I9 t = lzs_v(i9(a));
 #pragma unroll
-  for (int l = 0; l < NL; l++) r[l] = z[l];
+  for (int l = 0; l < NL; l++) r[l] = t.v[l];
 }
 #define lz_mul(a, b, r) lzm(a, b, r)
 #define lz_sqr(a, r) lzs(a, r)
 
-__device__ __forceinline__ void lzs_n(i32* x, int n) {
-  for (int k = 0; k < n; k++) {
-    i32 t[NL];
-    lzs(x, t);
+__device__ __forceinline__ void lzs_n(i32 (&x)[NL], int n) {
+  I9 t = i9(x);
+  for (int k = 0; k < n; k++) t = lzs_v(t);
 #pragma unroll
-    for (int l = 0; l < NL; l++) x[l] = t[l];
-  }
+  for (int l = 0; l < NL; l++) x[l] = t.v[l];
 }
 // x^(p-2) with the addition chain of p2e_field.cuh::lz_inv, through the out-of-line mul / sqr
 __device__ void lz_inv_calls(const i32 (&a)[NL], i32 (&r)[NL]) {
@@ -538,22 +547,25 @@ __global__ void __launch_bounds__(128) k_chain_affine(ChainArgs A) {
 #undef lz_sqr
 
 // K4: expand one curve op into all of its generators' output tuples
-__device__ __noinline__ void nl_lzmul(const i32* __restrict__ ap, const i32* __restrict__ bp, i32* __restrict__ rp) {
-  i32 a[NL], b[NL], r[NL];
-#pragma unroll
-  for (int l = 0; l < NL; l++) { a[l] = ap[l]; b[l] = bp[l]; }
-  lz_mul(a, b, r);
-#pragma unroll
-  for (int l = 0; l < NL; l++) rp[l] = r[l];
+__device__ __noinline__ I9 nl_lzmul_v(I9 a, I9 b) {
+  I9 r;
+  lz_mul(a.v, b.v, r.v);
+  return r;
 }
-__device__ __noinline__ void nl_lzcanon(const i32* __restrict__ ap, u32* __restrict__ rp) {
-  i32 a[NL];
-  u32 r[NL];
+__device__ __noinline__ W9 nl_lzcanon_v(I9 a) {
+  W9 r;
+  lz_canon(a.v, r.v);
+  return r;
+}
+__device__ __forceinline__ void nl_lzmul(const i32 (&a)[NL], const i32 (&b)[NL], i32 (&r)[NL]) {
+  I9 t = nl_lzmul_v(i9(a), i9(b));
 #pragma unroll
-  for (int l = 0; l < NL; l++) a[l] = ap[l];
-  lz_canon(a, r);
+  for (int l = 0; l < NL; l++) r[l] = t.v[l];
+}
+__device__ __forceinline__ void nl_lzcanon(const i32 (&a)[NL], u32 (&r)[NL]) {
+  W9 t = nl_lzcanon_v(i9(a));
 #pragma unroll
-  for (int l = 0; l < NL; l++) rp[l] = r[l];
+  for (int l = 0; l < NL; l++) r[l] = t.v[l];
 }
 
 __device__ __forceinline__ void load_affine(const ChainArgs& A, int32_t pid, size_t i, u32 (&x)[NL], u32 (&y)[NL],
