@@ -36,6 +36,14 @@ METRICS = {
 }
 
 
+def load_traffic():
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:       # noqa: BLE001
+        return {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -131,6 +139,7 @@ class Bench:
         self.sp = self.st.cuda_stream
         assert self.sp != 0
         self.peak_gbs, self.peak_kind = load_peaks()
+        self.traffic = load_traffic()
 
     def dev(self, a):
         return self.torch.from_numpy(a.view(self.np.int64)).cuda()
@@ -235,13 +244,21 @@ class Bench:
             sampler.start()
         streams = s.get("streams") or []
 
+        stagger_cycles = 0
+
         def timed(fn, k):
             """k calls of fn between two events on the main stream; worker streams fork from / join into it."""
+            nonlocal stagger_cycles
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(self.st)
-            for w in streams:
+            for j, w in enumerate(streams):
                 w.wait_event(e0)
+                if stagger_cycles and j:
+                    # identical batches would otherwise run in lock-step (all latency-bound phases together,
+                    # then all bandwidth-bound phases together): offset stream j's start, inside the timed region
+                    with torch.cuda.stream(w):
+                        torch.cuda._sleep(int(j * stagger_cycles))
             for _ in range(k):
                 fn()
             for w in streams:
@@ -251,7 +268,10 @@ class Bench:
             e1.record(self.st)
             self.barrier()
             return e0.elapsed_time(e1)
+        stagger_ms = float(os.environ.get("P2E_BENCH_STAGGER_MS", "0")) if len(streams) > 1 else 0.0
+        stagger_cycles = stagger_ms * 1e-3 * 1.9e9
         ms = timed(step, steps)
+        stagger_cycles = 0
         latency_ms = None
         if "step_single" in s:
             s["step_single"]()
@@ -305,7 +325,8 @@ class Bench:
             k_replay = kernel_ms[names.index("k_chain_replay")]
             achieved = s["alg_bytes"] / (k_expand * 1e-3) / 1e9
             res["roofline"] = {"bound": "hbm", "kernel": "k_chain_expand", "achieved": achieved, "peak": self.peak_gbs,
-                               "unit": "GB/s", "frac": achieved / self.peak_gbs, "peak_kind": self.peak_kind, "traffic": None,
+                               "unit": "GB/s", "frac": achieved / self.peak_gbs, "peak_kind": self.peak_kind,
+                               "traffic": self.traffic.get("k_chain_expand"),
                                "algorithmic_bytes_per_launch": s["alg_bytes"], "kernel_ms": k_expand,
                                "share_of_step": k_expand / sum(kernel_ms)}
             # INT32 roof of the replay kernel: algorithmic work = 3263 field mults per signature (batched-inversion
@@ -314,7 +335,8 @@ class Bench:
         else:
             achieved = s["alg_bytes"] / (ms_per_step * 1e-3) / 1e9
             res["roofline"] = {"bound": "hbm", "kernel": s["kernel"], "achieved": achieved, "peak": self.peak_gbs, "unit": "GB/s",
-                               "frac": achieved / self.peak_gbs, "peak_kind": self.peak_kind, "traffic": None,
+                               "frac": achieved / self.peak_gbs, "peak_kind": self.peak_kind,
+                               "traffic": self.traffic.get(s["kernel"]),
                                "algorithmic_bytes_per_launch": s["alg_bytes"]}
         if sampler is not None:
             res["clocks"] = sampler.summary()

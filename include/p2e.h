@@ -138,6 +138,22 @@ int p2e_eval_check_sum_dev(size_t n_rows, const uint64_t* wires, size_t stride, 
                            size_t out_stride, void* stream);
 int p2e_eval_check_sum(size_t n_rows, const uint64_t* wires, uint64_t* out);
 
+/* ---- gadget-chain witnesses ("tapes") ---------------------------------------------------- */
+/* A tape is the ordered list of in-tree generator instances a gadget creates.  Generic entry
+ * points over the built-in tapes; every input is a [9][stride] wire matrix (a BoolTarget input
+ * uses wire 0 of its matrix), `inputs` is an array of p2e_tape_inputs(tape) pointers. */
+#define P2E_TAPE_ECDSA 0          /* verify_secp256k1_message_circuit  gadgets/ecdsa.rs:30-53 : msg, r, s, pk.x, pk.y */
+#define P2E_TAPE_GLV_MUL 1        /* glv_mul(p, k)                     gadgets/glv.rs:87-104  : k, p.x, p.y */
+#define P2E_TAPE_CURVE_ADD 2      /* curve_add(p1, p2)                 gadgets/curve.rs:202-223: x1, y1, x2, y2 */
+#define P2E_TAPE_CURVE_DOUBLE 3   /* curve_double(p)                   gadgets/curve.rs:160-185: x, y */
+#define P2E_TAPE_CURVE_COND_ADD 4 /* curve_conditional_add(p1, p2, b)  gadgets/curve.rs:225-243: x1, y1, x2, y2, b */
+size_t p2e_tape_slots(int tape);
+int p2e_tape_inputs(int tape);
+size_t p2e_tape_layout(int tape, uint32_t* kinds, uint32_t* offsets);
+int p2e_tape_witness_dev(int tape, size_t n, const uint64_t* const* inputs, size_t in_stride,
+                         uint64_t* out, size_t out_stride, uint32_t* err, void* stream);
+int p2e_tape_witness(int tape, size_t n, const uint64_t* const* inputs, uint64_t* out, uint32_t* err);
+
 /* ---- ECDSA verification circuit witness (tape) ----------------------------------------- */
 
 /* Number of u64 slots one verify_secp256k1_message_circuit witness occupies in tape order

@@ -455,6 +455,8 @@ __global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A, int chain0) {
       u32 d = 4u * digit_at(k2, 5, 2 * op.aux, 2) + digit_at(k1, 5, 2 * op.aux, 2);
       p2 = A.t.pre_pid[d];
       flag = d != 0;
+    } else if (op.type == PT_CADD_BOOL) {
+      flag = load_wire(A, SP_IN, 9u * op.aux, i) != 0;      // BoolTarget input (0 / 1)
     }
     JacL P, R;
     load_jac(A, p1, i, P);
@@ -695,7 +697,7 @@ struct TapeOnDevice {
   size_t n_slots = 0;
 };
 
-static TapeOnDevice g_dev_tapes[2];
+static TapeOnDevice g_dev_tapes[N_TAPES];
 static std::mutex g_mu;
 
 template <class T>
@@ -984,41 +986,57 @@ int p2e_last_kernel_times(float* ms, int cap) {
   return k;
 }
 
-size_t p2e_ecdsa_tape_slots(void) { return ecdsa_tape().n_slots; }
-size_t p2e_ecdsa_tape_layout(uint32_t* kinds, uint32_t* offsets) { return tape_layout(ecdsa_tape(), kinds, offsets); }
+static int bad_tape(int tape) {
+  if (tape < 0 || tape >= N_TAPES) return set_error_msg("unknown tape id");
+  return 0;
+}
 
+size_t p2e_tape_slots(int tape) { return bad_tape(tape) ? 0 : get_tape(tape).n_slots; }
+int p2e_tape_inputs(int tape) { return bad_tape(tape) ? -1 : (int)get_tape(tape).n_inputs; }
+size_t p2e_tape_layout(int tape, uint32_t* kinds, uint32_t* offsets) {
+  return bad_tape(tape) ? 0 : tape_layout(get_tape(tape), kinds, offsets);
+}
+
+int p2e_tape_witness_dev(int tape, size_t n, const uint64_t* const* inputs, size_t is, uint64_t* out, size_t os,
+                         uint32_t* err, void* stream) {
+  if (bad_tape(tape)) return -1;
+  const Tape& t = get_tape(tape);
+  return run_tape(tape, t, n, inputs, (int)t.n_inputs, is, out, os, err, stream);
+}
+
+int p2e_tape_witness(int tape, size_t n, const uint64_t* const* inputs, uint64_t* out, uint32_t* err) {
+  if (bad_tape(tape)) return -1;
+  const Tape& t = get_tape(tape);
+  const int n_in = (int)t.n_inputs;
+  return run_tape_host(t, n, inputs, n_in, out, err, [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* st) {
+    return run_tape(tape, t, n, d, n_in, n, o, n, e, st);
+  });
+}
+
+size_t p2e_ecdsa_tape_slots(void) { return p2e_tape_slots(TAPE_ECDSA); }
+size_t p2e_ecdsa_tape_layout(uint32_t* kinds, uint32_t* offsets) { return p2e_tape_layout(TAPE_ECDSA, kinds, offsets); }
 int p2e_ecdsa_witness_dev(size_t n, const uint64_t* msg, const uint64_t* r, const uint64_t* s, const uint64_t* pkx,
                           const uint64_t* pky, size_t is, uint64_t* out, size_t os, uint32_t* err, void* stream) {
   const uint64_t* ins[5] = {msg, r, s, pkx, pky};
-  return run_tape(0, ecdsa_tape(), n, ins, 5, is, out, os, err, stream);
+  return p2e_tape_witness_dev(TAPE_ECDSA, n, ins, is, out, os, err, stream);
+}
+int p2e_ecdsa_witness(size_t n, const uint64_t* msg, const uint64_t* r, const uint64_t* s, const uint64_t* pkx,
+                      const uint64_t* pky, uint64_t* out, uint32_t* err) {
+  const uint64_t* ins[5] = {msg, r, s, pkx, pky};
+  return p2e_tape_witness(TAPE_ECDSA, n, ins, out, err);
 }
 
-size_t p2e_glv_mul_tape_slots(void) { return glv_mul_tape().n_slots; }
-size_t p2e_glv_mul_tape_layout(uint32_t* kinds, uint32_t* offsets) { return tape_layout(glv_mul_tape(), kinds, offsets); }
-
+size_t p2e_glv_mul_tape_slots(void) { return p2e_tape_slots(TAPE_GLV_MUL); }
+size_t p2e_glv_mul_tape_layout(uint32_t* kinds, uint32_t* offsets) { return p2e_tape_layout(TAPE_GLV_MUL, kinds, offsets); }
 int p2e_glv_mul_witness_dev(size_t n, const uint64_t* k, const uint64_t* px, const uint64_t* py, size_t is,
                             uint64_t* out, size_t os, uint32_t* err, void* stream) {
   const uint64_t* ins[3] = {k, px, py};
-  return run_tape(1, glv_mul_tape(), n, ins, 3, is, out, os, err, stream);
+  return p2e_tape_witness_dev(TAPE_GLV_MUL, n, ins, is, out, os, err, stream);
+}
+int p2e_glv_mul_witness(size_t n, const uint64_t* k, const uint64_t* px, const uint64_t* py, uint64_t* out,
+                        uint32_t* err) {
+  const uint64_t* ins[3] = {k, px, py};
+  return p2e_tape_witness(TAPE_GLV_MUL, n, ins, out, err);
 }
 
 }  // extern "C"
-
-int p2e_ecdsa_witness(size_t n, const uint64_t* msg, const uint64_t* r, const uint64_t* s, const uint64_t* pkx,
-                      const uint64_t* pky, uint64_t* out, uint32_t* err);
-
-extern "C" int p2e_ecdsa_witness(size_t n, const uint64_t* msg, const uint64_t* r, const uint64_t* s,
-                                 const uint64_t* pkx, const uint64_t* pky, uint64_t* out, uint32_t* err) {
-  const uint64_t* ins[5] = {msg, r, s, pkx, pky};
-  return run_tape_host(ecdsa_tape(), n, ins, 5, out, err, [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* st) {
-    return run_tape(0, ecdsa_tape(), n, d, 5, n, o, n, e, st);
-  });
-}
-
-extern "C" int p2e_glv_mul_witness(size_t n, const uint64_t* k, const uint64_t* px, const uint64_t* py, uint64_t* out,
-                                   uint32_t* err) {
-  const uint64_t* ins[3] = {k, px, py};
-  return run_tape_host(glv_mul_tape(), n, ins, 3, out, err, [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* st) {
-    return run_tape(1, glv_mul_tape(), n, d, 3, n, o, n, e, st);
-  });
-}

@@ -314,7 +314,7 @@ class Builder {
     o.type = type; o.aux = aux; o.p1 = p1; o.p2 = p2; o.slot = slot;
     // operand 2 is statically affine (constant or per-signature input point): mixed addition
     bool p2_affine = (type == PT_CADD_FIXED) ||
-                     (type == PT_ADD && !(flags & PF_P2_CUR) && p2 >= PID_INPUT_BASE);
+                     ((type == PT_ADD || type == PT_CADD_BOOL) && !(flags & PF_P2_CUR) && p2 >= PID_INPUT_BASE);
     o.flags = (uint8_t)(flags | (p2_affine ? PF_P2_AFFINE : 0) | (cur_chain << PF_CHAIN_SHIFT));
     int32_t k = (int32_t)t.ptops.size();
     if (t.chain_end[cur_chain] == t.chain_begin[cur_chain]) t.chain_begin[cur_chain] = k;
@@ -340,11 +340,11 @@ class Builder {
     emit(G_SUB, 10);                                                 // y3
     return push_ptop(PT_DBL, flags, 0, p1, -1, s, 201, 272);
   }
-  PtT curve_conditional_add(PtOpType type, uint8_t flags, uint16_t aux, int32_t p1) {   // curve.rs:225-243
+  PtT curve_conditional_add(PtOpType type, uint8_t flags, uint16_t aux, int32_t p1, int32_t p2 = -1) {   // curve.rs:225-243
     uint32_t s = emit_curve_add();
     emit(G_ADD, 10);
     emit(G_ADD, 10);
-    return push_ptop(type, flags, aux, p1, -1, s, 231, 241);
+    return push_ptop(type, flags, aux, p1, p2, s, 231, 241);
   }
 
   // fixed_base_curve_mul_circuit (curve_fixed_base.rs:18-66), base = G
@@ -459,25 +459,41 @@ class Builder {
 
 }  // namespace
 
-const Tape& ecdsa_tape() {
-  static Tape* tape = nullptr;
-  if (!tape) {
+const Tape& get_tape(int id) {
+  static Tape* tapes[N_TAPES] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (id < 0 || id >= N_TAPES) id = 0;
+  if (!tapes[id]) {
     Builder b;
-    b.verify_secp256k1_message();
-    tape = new Tape(b.t);
+    b.cur_chain = 1;
+    switch (id) {
+      case TAPE_ECDSA:
+        b.verify_secp256k1_message();
+        break;
+      case TAPE_GLV_MUL: {
+        NNT k = b.input(0), px = b.input(1), py = b.input(2);
+        b.glv_mul(px, py, k);
+        break;
+      }
+      case TAPE_CURVE_ADD: {
+        PtT p1 = b.input_point(b.input(0), b.input(1)), p2 = b.input_point(b.input(2), b.input(3));
+        b.curve_add(p1.pid, p2.pid, 0);
+        break;
+      }
+      case TAPE_CURVE_DOUBLE: {
+        PtT p1 = b.input_point(b.input(0), b.input(1));
+        b.curve_double(p1.pid, 0);
+        break;
+      }
+      case TAPE_CURVE_COND_ADD: {
+        PtT p1 = b.input_point(b.input(0), b.input(1)), p2 = b.input_point(b.input(2), b.input(3));
+        b.input(4);
+        b.curve_conditional_add(PT_CADD_BOOL, 0, 4, p1.pid, p2.pid);
+        break;
+      }
+    }
+    tapes[id] = new Tape(b.t);
   }
-  return *tape;
-}
-
-const Tape& glv_mul_tape() {
-  static Tape* tape = nullptr;
-  if (!tape) {
-    Builder b;
-    NNT k = b.input(0), px = b.input(1), py = b.input(2);
-    b.glv_mul(px, py, k);
-    tape = new Tape(b.t);
-  }
-  return *tape;
+  return *tapes[id];
 }
 
 }  // namespace p2e

@@ -41,7 +41,7 @@ struct Check {      // connect_nonnative(a, b): limb-wise equality, missing limb
   Ref a, b;
 };
 
-enum PtOpType : uint8_t { PT_ADD = 0, PT_DBL = 1, PT_CADD_FIXED = 2, PT_CADD_MSM = 3 };
+enum PtOpType : uint8_t { PT_ADD = 0, PT_DBL = 1, PT_CADD_FIXED = 2, PT_CADD_MSM = 3, PT_CADD_BOOL = 4 };
 enum PtFlags : uint8_t { PF_P1_CUR = 1, PF_P2_CUR = 2, PF_SET_CUR = 4, PF_P2_AFFINE = 8 };
 constexpr int PF_CHAIN_SHIFT = 4;               // flags bits 4-5: independent chain id (0 fixed-base, 1 msm, 2 tail)
 constexpr int N_CHAINS = 3;
@@ -49,7 +49,7 @@ constexpr int32_t PID_CONST_BASE = 1 << 20;     // pid >= this: affine constant 
 struct PtOp {
   uint8_t type;
   uint8_t flags;
-  uint16_t aux;     // window index (fixed base) or 2-bit digit index (msm)
+  uint16_t aux;     // window index (fixed base), 2-bit digit index (msm) or input index of the BoolTarget
   int32_t p1, p2;   // point ids (ignored when the *_CUR flag is set)
   uint32_t slot;    // first output slot of this curve op's generators
 };
@@ -77,9 +77,16 @@ struct Tape {
   int32_t chain_begin[N_CHAINS] = {0, 0, 0}, chain_end[N_CHAINS] = {0, 0, 0};   // contiguous op ranges
 };
 
-// verify_secp256k1_message_circuit (gadgets/ecdsa.rs:30-53); inputs msg, r, s, pk.x, pk.y
-const Tape& ecdsa_tape();
-// glv_mul(p, k) (gadgets/glv.rs:87-104); inputs k, p.x, p.y
-const Tape& glv_mul_tape();
+enum TapeId : int {
+  TAPE_ECDSA = 0,        // verify_secp256k1_message_circuit (gadgets/ecdsa.rs:30-53); inputs msg, r, s, pk.x, pk.y
+  TAPE_GLV_MUL = 1,      // glv_mul(p, k) (gadgets/glv.rs:87-104); inputs k, p.x, p.y
+  TAPE_CURVE_ADD = 2,    // curve_add(p1, p2) (gadgets/curve.rs:202-223); inputs x1, y1, x2, y2
+  TAPE_CURVE_DOUBLE = 3, // curve_double(p) (gadgets/curve.rs:160-185); inputs x, y
+  TAPE_CURVE_COND_ADD = 4, // curve_conditional_add(p1, p2, b) (gadgets/curve.rs:225-243); inputs x1, y1, x2, y2, b
+  N_TAPES = 5
+};
+const Tape& get_tape(int id);
+inline const Tape& ecdsa_tape() { return get_tape(TAPE_ECDSA); }
+inline const Tape& glv_mul_tape() { return get_tape(TAPE_GLV_MUL); }
 
 }  // namespace p2e

@@ -78,6 +78,11 @@ SIGNATURES = {
     "p2e_eval_mul_nonnative": (_int, [_int, _sz, _vp, _vp]),
     "p2e_eval_check_sum_dev": (_int, [_sz, _vp, _sz, _vp, _sz, _vp]),
     "p2e_eval_check_sum": (_int, [_sz, _vp, _vp]),
+    "p2e_tape_slots": (_sz, [_int]),
+    "p2e_tape_inputs": (_int, [_int]),
+    "p2e_tape_layout": (_sz, [_int, _vp, _vp]),
+    "p2e_tape_witness_dev": (_int, [_int, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_tape_witness": (_int, [_int, _sz, _vp, _vp, _vp]),
     "p2e_ecdsa_tape_slots": (_sz, []),
     "p2e_ecdsa_tape_layout": (_sz, [_vp, _vp]),
     "p2e_ecdsa_witness_dev": (_int, [_sz, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),
@@ -240,6 +245,43 @@ class Engine:
         out = np.empty((17, n), dtype=np.uint64)
         self._check(self.lib.p2e_eval_check_sum(n, _ptr(w), _ptr(out)))
         return out
+
+    # ---------------------------------------------------------------- generic gadget tapes
+    TAPE_ECDSA, TAPE_GLV_MUL, TAPE_CURVE_ADD, TAPE_CURVE_DOUBLE, TAPE_CURVE_COND_ADD = range(5)
+
+    def tape_layout(self, tape):
+        cnt = self.lib.p2e_tape_layout(tape, None, None)
+        kinds = np.empty(cnt, dtype=np.uint32)
+        offs = np.empty(cnt, dtype=np.uint32)
+        self.lib.p2e_tape_layout(tape, _ptr(kinds), _ptr(offs))
+        return kinds, offs, int(self.lib.p2e_tape_slots(tape))
+
+    def tape_witness(self, tape, inputs):
+        """inputs: list of [9][n] wire matrices -> (witness [slots][n], err [n])."""
+        ins = [_host_u64(a, 9) for a in inputs]
+        if len(ins) != self.lib.p2e_tape_inputs(tape):
+            raise ValueError("wrong number of tape inputs")
+        n = ins[0].shape[1]
+        slots = int(self.lib.p2e_tape_slots(tape))
+        out = np.empty((slots, n), dtype=np.uint64)
+        err = np.empty(n, dtype=np.uint32)
+        arr = (ctypes.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
+        self._check(self.lib.p2e_tape_witness(tape, n, ctypes.cast(arr, ctypes.c_void_p), _ptr(out), _ptr(err)))
+        return out, err
+
+    def curve_add(self, x1, y1, x2, y2):
+        """curve_add(p1, p2) witness (gadgets/curve.rs:202-223): 231 slots per instance."""
+        return self.tape_witness(self.TAPE_CURVE_ADD, [x1, y1, x2, y2])
+
+    def curve_double(self, x, y):
+        """curve_double(p) witness (gadgets/curve.rs:160-185): 282 slots per instance."""
+        return self.tape_witness(self.TAPE_CURVE_DOUBLE, [x, y])
+
+    def curve_conditional_add(self, x1, y1, x2, y2, b):
+        """curve_conditional_add(p1, p2, b) witness (gadgets/curve.rs:225-243); b: [n] of 0/1."""
+        bm = np.zeros((9, len(b)), dtype=np.uint64)
+        bm[0] = np.asarray(b, dtype=np.uint64)
+        return self.tape_witness(self.TAPE_CURVE_COND_ADD, [x1, y1, x2, y2, bm])
 
     # ---------------------------------------------------------------- ECDSA circuit witness
     def ecdsa_tape_layout(self):

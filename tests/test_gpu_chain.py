@@ -77,3 +77,67 @@ def test_ecdsa_full_batch_properties(engine):
     for j in (0, 1777, 4095):
         ref = S.ecdsa_witness(i["msg"][j], i["r"][j], i["s"][j], (i["pkx"][j], i["pky"][j])).flat()
         assert _first_diff(wit[:, j], ref, kinds, offs) is None
+
+
+def _rand_points(n, seed):
+    import random
+    rng = random.Random(seed)
+    return [S.pt_mul(rng.randrange(1, S.SECP_N), S.G) for _ in range(n)]
+
+
+def test_curve_add_double_conditional_add_vs_oracle(engine):
+    """Mirrors the reference's test_curve_add / test_curve_double / test_curve_conditional_add
+    (gadgets/curve.rs:359-456): random points, result must equal the native sum, and here the whole
+    generator tape must equal the oracle's."""
+    n = 40
+    P, Q = _rand_points(n, 1), _rand_points(n, 2)
+    x1, y1 = W.ints_to_limbs([p[0] for p in P]), W.ints_to_limbs([p[1] for p in P])
+    x2, y2 = W.ints_to_limbs([p[0] for p in Q]), W.ints_to_limbs([p[1] for p in Q])
+    b = [j % 2 for j in range(n)]
+    wa, ea = engine.curve_add(x1, y1, x2, y2)
+    wd, ed = engine.curve_double(x1, y1)
+    wc, ec = engine.curve_conditional_add(x1, y1, x2, y2, b)
+    assert not ea.any() and not ed.any() and not ec.any()
+    for j in range(n):
+        wb = S.WitnessBuilder()
+        r = wb.curve_add(wb.constant_affine_point(P[j]), wb.constant_affine_point(Q[j]))
+        assert [int(v) for v in wa[:, j]] == wb.flat()
+        assert (S.get_biguint(r[0].limbs), S.get_biguint(r[1].limbs)) == S.pt_add(P[j], Q[j])
+        wb = S.WitnessBuilder()
+        r = wb.curve_double(wb.constant_affine_point(P[j]))
+        assert [int(v) for v in wd[:, j]] == wb.flat()
+        assert (S.get_biguint(r[0].limbs), S.get_biguint(r[1].limbs)) == S.pt_add(P[j], P[j])
+        wb = S.WitnessBuilder()
+        r = wb.curve_conditional_add(wb.constant_affine_point(P[j]), wb.constant_affine_point(Q[j]), b[j])
+        assert [int(v) for v in wc[:, j]] == wb.flat()
+        want = S.pt_add(P[j], Q[j]) if b[j] else P[j]
+        assert (S.get_biguint(r[0].limbs), S.get_biguint(r[1].limbs)) == want
+
+
+def test_curve_add_equal_x_flags_inverse_zero(engine):
+    """Adding a point to itself with the incomplete formulas: x2 - x1 = 0, the reference's inverse() panics."""
+    P = _rand_points(3, 3)
+    x, y = W.ints_to_limbs([p[0] for p in P]), W.ints_to_limbs([p[1] for p in P])
+    x2, y2 = x.copy(), y.copy()
+    Q = S.pt_mul(77, S.G)
+    x2[:, 1] = W.ints_to_limbs([Q[0]])[:, 0]
+    y2[:, 1] = W.ints_to_limbs([Q[1]])[:, 0]
+    _, err = engine.curve_add(x, y, x2, y2)
+    assert err[0] & 8 and err[2] & 8 and err[1] == 0
+
+
+def test_chain_chunking_is_transparent(engine, monkeypatch):
+    """Batches above the scratch chunk capacity are processed chunk by chunk: same bits."""
+    n = 300
+    ks = [(j * 0x9E3779B97F4A7C15 + 12345) % S.SECP_N for j in range(n)]
+    pts = _rand_points(4, 9)
+    k = W.ints_to_limbs(ks)
+    px = W.ints_to_limbs([pts[j % 4][0] for j in range(n)])
+    py = W.ints_to_limbs([pts[j % 4][1] for j in range(n)])
+    w1, e1 = engine.glv_mul_witness(k, px, py)
+    monkeypatch.setenv("P2E_CHAIN_CHUNK", "128")
+    w2, e2 = engine.glv_mul_witness(k, px, py)
+    assert np.array_equal(w1, w2) and np.array_equal(e1, e2) and not e1.any()
+    wb = S.WitnessBuilder()
+    wb.glv_mul(wb.constant_affine_point(pts[299 % 4]), wb.constant_nonnative(ks[299], S.SECP_N))
+    assert [int(v) for v in w2[:, 299]] == wb.flat()

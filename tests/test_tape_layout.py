@@ -45,3 +45,27 @@ def test_glv_mul_tape_layout_matches_oracle():
     ok, oo, oslots = _oracle_layout(wb.tape)
     assert slots == oslots
     assert list(kinds) == ok and list(offs) == oo
+
+
+def _tape(lib, tape):
+    cnt = lib.p2e_tape_layout(tape, None, None)
+    kinds = np.empty(cnt, dtype=np.uint32)
+    offs = np.empty(cnt, dtype=np.uint32)
+    lib.p2e_tape_layout(tape, kinds.ctypes.data, offs.ctypes.data)
+    return list(kinds), list(offs), int(lib.p2e_tape_slots(tape)), lib.p2e_tape_inputs(tape)
+
+
+def test_curve_op_tapes_match_oracle():
+    """curve_add / curve_double / curve_conditional_add (gadgets/curve.rs:160-243)."""
+    lib = pkg.load_library()
+    P, Q = S.pt_mul(5, S.G), S.pt_mul(9, S.G)
+    wb = S.WitnessBuilder()
+    wb.curve_add(wb.constant_affine_point(P), wb.constant_affine_point(Q))
+    assert _tape(lib, 2) == (*_oracle_layout(wb.tape), 4) and _tape(lib, 2)[2] == 231
+    wb = S.WitnessBuilder()
+    wb.curve_double(wb.constant_affine_point(P))
+    assert _tape(lib, 3) == (*_oracle_layout(wb.tape), 2) and _tape(lib, 3)[2] == 282
+    wb = S.WitnessBuilder()
+    wb.curve_conditional_add(wb.constant_affine_point(P), wb.constant_affine_point(Q), 1)
+    assert _tape(lib, 4) == (*_oracle_layout(wb.tape), 5) and _tape(lib, 4)[2] == 251
+    assert lib.p2e_tape_slots(99) == 0 and lib.p2e_tape_inputs(-1) == -1
