@@ -480,6 +480,184 @@ __global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A, int chain0) {
   if (err) atomicOr(&A.err[i], err);
 }
 
+// ------------------------------------------------------------------------------------------
+// K1 (cooperative form): 4 lanes per (signature, chain).  A Jacobian addition is 16 multiplications
+// but only 5 dependency levels deep (doubling: 7 -> 4), so the four lanes of a task execute the
+// independent multiplications of one level side by side; operands are staged in shared memory
+// (value registers of 9 lazy limbs each) and every level ends with a __syncwarp().  Each stage is
+// homogeneous (all MUL or all linear) so the lanes never diverge onto different code.
+enum : uint8_t { MO_NOP = 0, MO_MUL = 1, MO_LIN = 2 };
+struct MicroOp {
+  uint8_t opc, dst, a, b, ka, kb;
+};
+constexpr int SP_STAGES = 10, SP_LANES = 4, SP_REGS = 28, SP_TASKS = 32, SP_PITCH = SP_TASKS + 1;
+// value registers: 0-2 P (X1 Y1 Z1), 3-5 Q (X2 Y2 Z2), 6-8 result (X3 Y3 Z3), 9.. temporaries
+#define MUL_(d, a, b) {MO_MUL, d, a, b, 0, 0}
+#define LIN_(d, a, ka, b, kb) {MO_LIN, d, a, b, ka, kb}
+#define NOP_ {MO_NOP, 0, 0, 0, 0, 0}
+__constant__ MicroOp SP_TAB[3][SP_STAGES][SP_LANES] = {
+    // 0: general addition   A=9 B=10 C=11 D=12 U1=13 U2=14 S1=15 S2=16 H=17 R=18 HH=19 RR=20 ZZ=21 HHH=22 V=23 T=24 W=25 RW=26 SH=27
+    {{MUL_(9, 2, 2), MUL_(10, 5, 5), MUL_(11, 1, 5), MUL_(12, 4, 2)},
+     {MUL_(13, 0, 10), MUL_(14, 3, 9), MUL_(15, 11, 10), MUL_(16, 12, 9)},
+     {LIN_(17, 14, 1, 13, 1), LIN_(18, 16, 1, 15, 1), NOP_, NOP_},
+     {MUL_(19, 17, 17), MUL_(20, 18, 18), MUL_(21, 2, 5), NOP_},
+     {MUL_(22, 17, 19), MUL_(23, 13, 19), MUL_(8, 21, 17), NOP_},
+     {LIN_(24, 20, 1, 22, 1), NOP_, NOP_, NOP_},
+     {LIN_(6, 24, 1, 23, 2), NOP_, NOP_, NOP_},
+     {LIN_(25, 23, 1, 6, 1), NOP_, NOP_, NOP_},
+     {MUL_(26, 18, 25), MUL_(27, 15, 22), NOP_, NOP_},
+     {LIN_(7, 26, 1, 27, 1), NOP_, NOP_, NOP_}},
+    // 1: mixed addition (Z2 == 1): U1 = X1, S1 = Y1
+    {{MUL_(9, 2, 2), NOP_, NOP_, MUL_(12, 4, 2)},
+     {NOP_, MUL_(14, 3, 9), NOP_, MUL_(16, 12, 9)},
+     {LIN_(17, 14, 1, 0, 1), LIN_(18, 16, 1, 1, 1), NOP_, NOP_},
+     {MUL_(19, 17, 17), MUL_(20, 18, 18), NOP_, NOP_},
+     {MUL_(22, 17, 19), MUL_(23, 0, 19), MUL_(8, 2, 17), NOP_},
+     {LIN_(24, 20, 1, 22, 1), NOP_, NOP_, NOP_},
+     {LIN_(6, 24, 1, 23, 2), NOP_, NOP_, NOP_},
+     {LIN_(25, 23, 1, 6, 1), NOP_, NOP_, NOP_},
+     {MUL_(26, 18, 25), MUL_(27, 1, 22), NOP_, NOP_},
+     {LIN_(7, 26, 1, 27, 1), NOP_, NOP_, NOP_}},
+    // 2: doubling   XX=9 YY=10 YZ=11 YYYY=12 TT=13 S=14 M=15 MM=16 W=17 MW=18
+    {{MUL_(9, 0, 0), MUL_(10, 1, 1), MUL_(11, 1, 2), NOP_},
+     {MUL_(12, 10, 10), MUL_(13, 0, 10), NOP_, NOP_},
+     {LIN_(14, 13, 4, 13, 0), LIN_(15, 9, 3, 9, 0), LIN_(8, 11, 2, 11, 0), NOP_},
+     {MUL_(16, 15, 15), NOP_, NOP_, NOP_},
+     {LIN_(6, 16, 1, 14, 2), NOP_, NOP_, NOP_},
+     {LIN_(17, 14, 1, 6, 1), NOP_, NOP_, NOP_},
+     {MUL_(18, 15, 17), NOP_, NOP_, NOP_},
+     {LIN_(7, 18, 1, 12, 8), NOP_, NOP_, NOP_},
+     {NOP_, NOP_, NOP_, NOP_},
+     {NOP_, NOP_, NOP_, NOP_}}};
+__constant__ uint8_t SP_NSTAGE[3] = {10, 10, 8};
+#undef MUL_
+#undef LIN_
+#undef NOP_
+
+__device__ __forceinline__ void sp_ld(const i32* sh, int reg, int task, i32 (&v)[NL]) {
+#pragma unroll
+  for (int l = 0; l < NL; l++) v[l] = sh[(reg * NL + l) * SP_PITCH + task];
+}
+__device__ __forceinline__ void sp_st(i32* sh, int reg, int task, const i32 (&v)[NL]) {
+#pragma unroll
+  for (int l = 0; l < NL; l++) sh[(reg * NL + l) * SP_PITCH + task] = v[l];
+}
+
+// lane q in 0..2 loads coordinate q of point `pid` into value register base + q
+__device__ __forceinline__ void sp_load_point(const ChainArgs& A, i32* sh, int base, int32_t pid, int32_t resident_pid,
+                                              size_t i, int task, int q) {
+  if (q > 2) return;
+  i32 v[NL];
+  if (pid == resident_pid) {
+    sp_ld(sh, 6 + q, task, v);                         // the previous result is still in registers 6-8
+  } else if (pid >= PID_CONST_BASE) {
+    const u32* c = A.t.const_points + (size_t)(pid - PID_CONST_BASE) * 18;
+#pragma unroll
+    for (int l = 0; l < NL; l++) v[l] = (q == 0) ? (i32)c[l] : (q == 1) ? (i32)c[NL + l] : (l == 0);
+  } else {
+    int idx = pt_index(A, pid);
+    const u32* src = (q == 0) ? A.JX : (q == 1) ? A.JY : A.JZ;
+    ld9(src, idx, A.cap, i, v);
+  }
+  sp_st(sh, base + q, task, v);
+}
+
+__global__ void __launch_bounds__(128) k_chain_replay_coop(ChainArgs A, int chain0) {
+  __shared__ i32 sh[SP_REGS * NL * SP_PITCH];
+  const int q = threadIdx.x & 3;                       // lane role within the task
+  const int task = threadIdx.x >> 2;                   // 0..31
+  const size_t i_raw = (size_t)blockIdx.x * SP_TASKS + task;
+  const bool valid = i_raw < A.n;
+  const size_t i = valid ? i_raw : A.n - 1;            // out-of-range tasks shadow the last signature, store nothing
+  const int chain = chain0 + blockIdx.y;
+  const int k_begin = A.t.chain_begin[chain], k_end = A.t.chain_end[chain];
+  if (k_begin == k_end) return;
+  u32 err = 0;
+  if (q == 0 && valid) {
+    // per-signature affine input points (Z = 1); every chain writes the same values (benign)
+    for (int j = 0; j < A.t.n_in_points; j++) {
+      u64 w[NL];
+      u32 x[NL], y[NL], one[NL];
+      load_ref(A, A.t.in_points[j].x, i, w);
+      err |= load_canon<ModP>(w, x);
+      load_ref(A, A.t.in_points[j].y, i, w);
+      err |= load_canon<ModP>(w, y);
+      set_zero9(one);
+      one[0] = 1;
+      int idx = A.t.n_ptops + j;
+      sv9(A.JX, idx, A.cap, i, x);
+      sv9(A.JY, idx, A.cap, i, y);
+      sv9(A.JZ, idx, A.cap, i, one);
+      sv9(A.AX, idx, A.cap, i, x);
+      sv9(A.AY, idx, A.cap, i, y);
+      sv9(A.ZC, idx, A.cap, i, one);
+    }
+  }
+  __syncwarp();
+  u32 fs[NL], k1[NL], k2[NL];
+  err |= load_scalar_limbs(A, A.t.fixed_scalar, i, fs);
+  err |= load_scalar_limbs(A, A.t.msm_k1, i, k1);
+  err |= load_scalar_limbs(A, A.t.msm_k2, i, k2);
+
+  int32_t cur = -1, resident = -2;
+  for (int k = k_begin; k < k_end; k++) {
+    const PtOp op = A.t.ptops[k];
+    int32_t p1 = (op.flags & PF_P1_CUR) ? cur : op.p1;
+    int32_t p2 = (op.flags & PF_P2_CUR) ? cur : op.p2;
+    u32 flag = 1;
+    if (op.type == PT_CADD_FIXED) {
+      u32 d = digit_at(fs, NL, 4 * op.aux, 4);
+      p2 = PID_CONST_BASE + (int32_t)(A.t.fixed_table_base + 16u * op.aux + d);
+      flag = d != 0;
+    } else if (op.type == PT_CADD_MSM) {
+      u32 d = 4u * digit_at(k2, 5, 2 * op.aux, 2) + digit_at(k1, 5, 2 * op.aux, 2);
+      p2 = A.t.pre_pid[d];
+      flag = d != 0;
+    } else if (op.type == PT_CADD_BOOL) {
+      flag = load_wire(A, SP_IN, 9u * op.aux, i) != 0;
+    }
+    const int kind = (op.type == PT_DBL) ? 2 : (op.flags & PF_P2_AFFINE) ? 1 : 0;
+    // stage operands (the just-computed result may be reused straight from shared memory)
+    sp_load_point(A, sh, 0, p1, resident, i, task, q);
+    if (kind != 2) sp_load_point(A, sh, 3, p2, resident, i, task, q);
+    else p2 = p1;
+    __syncwarp();
+    const int nst = SP_NSTAGE[kind];
+    for (int st = 0; st < nst; st++) {
+      const MicroOp m = SP_TAB[kind][st][q];
+      if (m.opc == MO_MUL) {
+        i32 a[NL], b[NL];
+        sp_ld(sh, m.a, task, a);
+        sp_ld(sh, m.b, task, b);
+        I9 r = lzm_v(i9(a), i9(b));
+        sp_st(sh, m.dst, task, r.v);
+      } else if (m.opc == MO_LIN) {
+        i32 a[NL], b[NL], r[NL];
+        sp_ld(sh, m.a, task, a);
+        sp_ld(sh, m.b, task, b);
+        lz_lin(a, m.ka, b, m.kb, r);
+        sp_st(sh, m.dst, task, r);
+      }
+      __syncwarp();
+    }
+    if (valid && q < 3) {
+      i32 v[NL];
+      sp_ld(sh, 6 + q, task, v);
+      u32* dst = (q == 0) ? A.JX : (q == 1) ? A.JY : A.JZ;
+      sv9(dst, k, A.cap, i, v);
+    }
+    if (valid && q == 3) {
+      A.SRC1[(size_t)k * A.cap + i] = p1;
+      A.SRC2[(size_t)k * A.cap + i] = p2;
+      A.FLG[(size_t)k * A.cap + i] = (uint8_t)flag;
+    }
+    resident = k;
+    if (op.flags & PF_SET_CUR) cur = flag ? k : p1;
+    __syncwarp();
+  }
+  if (err && valid && q == 0) atomicOr(&A.err[i], err);
+}
+
 // K2: Montgomery's trick over the Z3's of one signature, split in INV_GROUPS independent groups
 // (one field inversion per group) to shorten the dependency chain.
 __global__ void __launch_bounds__(32) k_chain_invert(ChainArgs A) {
@@ -588,7 +766,8 @@ __device__ __forceinline__ void load_affine(const ChainArgs& A, int32_t pid, siz
   }
 }
 
-__global__ void __launch_bounds__(128) k_chain_expand(ChainArgs A) {
+// 3 CTAs / SM (<= 168 registers): measured best of {none, 2, 3, 4} on B200 (0.60 ms vs 0.66 ms for 4096 signatures)
+__global__ void __launch_bounds__(128, 3) k_chain_expand(ChainArgs A) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int k = blockIdx.y;
   if (i >= A.n) return;
@@ -819,6 +998,14 @@ static void prof_mark(cudaStream_t st) {
   g_event_stream = st;
 }
 
+static bool replay_coop() {
+  // Measured on B200 (4096 signatures): cooperative 1.39 ms vs one-thread-per-chain 1.13 ms -- the
+  // runtime-indexed shared-memory staging costs 2.9x the warp instructions (profiles/r01_notes.md),
+  // so the serial kernel is the default; P2E_CHAIN_REPLAY=coop selects the cooperative one.
+  const char* e = getenv("P2E_CHAIN_REPLAY");
+  return e && e[0] == 'c';
+}
+
 static unsigned inv_groups() {
   static int g = 0;
   if (!g) {
@@ -894,9 +1081,15 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
     k_prep<<<g32, 32, 0, s_hi>>>(A);
     if (prof) prof_mark(st);
     if (no) {
-      k_chain_replay<<<dim3(g32, 2), 32, 0, s_hi>>>(A, 0);      // fixed-base and msm chains side by side
-      if (prof) prof_mark(st);
-      if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g32, 1), 32, 0, s_hi>>>(A, 2);   // join
+      if (replay_coop()) {
+        k_chain_replay_coop<<<dim3(g32, 2), 128, 0, s_hi>>>(A, 0);    // 4 lanes per (signature, chain)
+        if (prof) prof_mark(st);
+        if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay_coop<<<dim3(g32, 1), 128, 0, s_hi>>>(A, 2);   // join
+      } else {
+        k_chain_replay<<<dim3(g32, 2), 32, 0, s_hi>>>(A, 0);    // fixed-base and msm chains side by side
+        if (prof) prof_mark(st);
+        if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g32, 1), 32, 0, s_hi>>>(A, 2);   // join
+      }
       if (prof) prof_mark(st);
       k_chain_invert<<<dim3(g32, inv_groups()), 32, 0, s_hi>>>(A);
       if (prof) prof_mark(st);

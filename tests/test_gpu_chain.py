@@ -141,3 +141,13 @@ def test_chain_chunking_is_transparent(engine, monkeypatch):
     wb = S.WitnessBuilder()
     wb.glv_mul(wb.constant_affine_point(pts[299 % 4]), wb.constant_nonnative(ks[299], S.SECP_N))
     assert [int(v) for v in w2[:, 299]] == wb.flat()
+
+
+def test_cooperative_replay_kernel_is_bit_exact(engine, monkeypatch):
+    """The opt-in 4-lanes-per-task replay kernel (P2E_CHAIN_REPLAY=coop) must give the same witness."""
+    wl = W.ecdsa_workload(70, seed=31)
+    args = (wl["msg"], wl["r"], wl["s"], wl["pkx"], wl["pky"])
+    w1, e1 = engine.verify_secp256k1_message_witness(*args)
+    monkeypatch.setenv("P2E_CHAIN_REPLAY", "coop")
+    w2, e2 = engine.verify_secp256k1_message_witness(*args)
+    assert np.array_equal(w1, w2) and np.array_equal(e1, e2) and not e1.any()
