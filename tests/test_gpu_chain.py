@@ -151,3 +151,44 @@ def test_cooperative_replay_kernel_is_bit_exact(engine, monkeypatch):
     monkeypatch.setenv("P2E_CHAIN_REPLAY", "coop")
     w2, e2 = engine.verify_secp256k1_message_witness(*args)
     assert np.array_equal(w1, w2) and np.array_equal(e1, e2) and not e1.any()
+
+
+def test_ecdsa_edge_inputs_match_reference_panics(engine):
+    """Rows where the reference would panic get an error bit; neighbours in the same batch are untouched.
+    s = 0 -> FF::inverse() of zero (nonnative.rs:863); s >= 2^256 -> from_noncanonical_biguint panics;
+    msg limb >= 2^29 -> MulNonnativeGenerator's limb assert (mul_nonnative.rs:275-276); a non-canonical
+    but < 2^256 message (msg + n) is legal for the generators and must reproduce the oracle's tape."""
+    n = 6
+    wl = W.ecdsa_workload(n, seed=77)
+    msg, r, s, pkx, pky = (wl[k].copy() for k in ("msg", "r", "s", "pkx", "pky"))
+    i = wl["ints"]
+    s[:, 1] = 0                                                     # inverse of zero
+    s[:, 2] = W.ints_to_limbs([(1 << 256) + 5])[:, 0]               # >= 2^256
+    msg[0, 3] = np.uint64(1 << 29)                                  # limb out of range
+    big = i["msg"][4] + S.SECP_N
+    if big < (1 << 256):
+        msg[:, 4] = W.ints_to_limbs([big])[:, 0]                    # non-canonical message
+    wit, err = engine.verify_secp256k1_message_witness(msg, r, s, pkx, pky)
+    assert err[0] == 0 and err[5] == 0
+    assert err[1] & 8, "s = 0 must raise ERR_INVERSE_ZERO"
+    assert err[2] & 4, "s >= 2^256 must raise ERR_NONCANONICAL"
+    assert err[3] & 2, "limb >= 2^29 must raise ERR_LIMB_RANGE"
+    for j in (0, 5):
+        ref = S.ecdsa_witness(i["msg"][j], i["r"][j], i["s"][j], (i["pkx"][j], i["pky"][j])).flat()
+        assert [int(v) for v in wit[:, j]] == ref
+    # oracle agrees on which rows panic
+    for j, exc in ((1, True), (2, True), (3, True)):
+        with pytest.raises(S.RefPanic):
+            wb = S.WitnessBuilder()
+            wb.verify_secp256k1_message(S.NN([int(v) for v in msg[:, j]]), S.NN([int(v) for v in r[:, j]]),
+                                        S.NN([int(v) for v in s[:, j]]),
+                                        (S.NN([int(v) for v in pkx[:, j]]), S.NN([int(v) for v in pky[:, j]])))
+    if big < (1 << 256):
+        wb = S.WitnessBuilder()
+        # u1 = (msg + n) * c mod n has the same r but a different quotient: the tape differs from row 4's canonical one
+        try:
+            wb.verify_secp256k1_message(S.NN(S.limbs9(big)), S.NN(S.limbs9(i["r"][4])), S.NN(S.limbs9(i["s"][4])),
+                                        (S.NN(S.limbs9(i["pkx"][4])), S.NN(S.limbs9(i["pky"][4]))))
+            assert [int(v) for v in wit[:, 4]] == wb.flat() and err[4] == 0
+        except S.RefPanic:
+            assert err[4] != 0
