@@ -5,6 +5,7 @@ One "step" = one pass of the hot path over one batch of synthetic input.  Worklo
   ecdsa  (default, configs[2]) 4096 verify_secp256k1_message_circuit witnesses per GPU, full tape
   mulmod (configs[1])          2^20 nonnative secp256k1 base-field mulmod witnesses
   eval   (configs[4])          MulNonnativeGate constraint evaluation over 2^20 Goldilocks LDE rows
+  glv    (configs[3])          GLV decomposition + curve MSM witness chain (glv_mul) for 2^16 scalars
 The headline line is the ecdsa workload ("ECDSA circuit witnesses/s"); the mulmod and eval workloads
 are measured in the same run and reported under "secondary" with their own rooflines
 ("nonnative mulmod/s" is the second half of BASELINE.json's metric).
@@ -28,11 +29,13 @@ WORKLOAD_NAMES = {
     "ecdsa": "4096 independent verify_secp256k1_message_circuit witnesses per GPU (full tape: 82615 slots each)",
     "mulmod": "2^20 secp256k1 base-field nonnative mulmod witnesses (29-bit limbs): q, r, check_sum, carries",
     "eval": "MulNonnativeGate eval_unfiltered_base_batch over 2^20 Goldilocks LDE rows",
+    "glv": "glv_mul witness chain (GLV decomposition + 2-scalar MSM) for 2^16 secp256k1 scalars, P = 7G",
 }
 METRICS = {
     "ecdsa": ("ecdsa_circuit_witnesses_per_s", "witnesses/s"),
     "mulmod": ("nonnative_mulmod_witnesses_per_s", "mulmod/s"),
     "eval": ("mul_nonnative_gate_rows_per_s", "rows/s"),
+    "glv": ("glv_mul_witness_chains_per_s", "chains/s"),
 }
 
 
@@ -193,6 +196,33 @@ class Bench:
             return dict(step=step, step_e2e=step_e2e, units=n, h2d=53 * 8 * n, d2h=17 * 8 * n, alg_bytes=560 * n,
                         kernel="k_eval_mul_nonnative<ModP>", launches=1, err=None, dtype="u64 (Goldilocks)",
                         keep=(wd, od, hw, ho))
+        if wl == "glv":
+            # device-resident only at full size (the 2^16 x 61.6k-slot witness is 32 GB); e2e on a 4096-scalar slice
+            n = 1 << 16
+            slots = int(lib.p2e_glv_mul_tape_slots())
+            k = W.random_field_limbs(W.SEED + 7 + self.rank, n, 1)
+            gx, gy = W._ec_mul_g(7)
+            px = np.repeat(W.ints_to_limbs([gx]), n, axis=1)
+            py = np.repeat(W.ints_to_limbs([gy]), n, axis=1)
+            ind = [self.dev(np.ascontiguousarray(a)) for a in (k, px, py)]
+            od = torch.empty((slots, n), dtype=torch.int64, device="cuda")
+            ed = torch.empty(n, dtype=torch.int32, device="cuda")
+            ptrs = [t.data_ptr() for t in ind]
+
+            def step():
+                rc = lib.p2e_glv_mul_witness_dev(n, *ptrs, n, od.data_ptr(), n, ed.data_ptr(), sp)
+                assert rc == 0, eng.last_error()
+            m = 4096
+            hin = [self.pinned(np.ascontiguousarray(a[:, :m])) for a in (k, px, py)]
+            ho = torch.empty((slots, m), dtype=torch.int64).pin_memory()
+            he = torch.empty(m, dtype=torch.int32).pin_memory()
+
+            def step_e2e():
+                rc = lib.p2e_glv_mul_witness(m, *[t.data_ptr() for t in hin], ho.data_ptr(), he.data_ptr())
+                assert rc == 0, eng.last_error()
+            return dict(step=step, step_e2e=step_e2e, units=n, e2e_units=m, h2d=3 * 9 * 8 * m, d2h=slots * 8 * m + 4 * m,
+                        alg_bytes=slots * 8 * n, kernel="k_chain_expand (8 chunks of 8192)", launches=7 * 8, err=ed,
+                        dtype="u32 limbs / u64 (int)", keep=(ind, od, hin, ho, he), slots=slots)
         n = 4096
         slots = int(lib.p2e_ecdsa_tape_slots())
         d = W.ecdsa_workload(n, seed=W.SEED + self.rank)
@@ -307,7 +337,7 @@ class Bench:
             ms, e2e_ms, errs = float(mx[0]), float(mx[1]), int(sm[2])
         ms_per_step = ms / steps
         value = s["units"] * self.world / (ms_per_step * 1e-3)
-        e2e_value = s["units"] * self.world / (e2e_ms / e2e_steps * 1e-3)
+        e2e_value = s.get("e2e_units", s["units"]) * self.world / (e2e_ms / e2e_steps * 1e-3)
         res = {
             "metric": METRICS[wl][0], "value": value, "unit": METRICS[wl][1], "ms_per_step": ms_per_step,
             "dtype": s["dtype"], "units_per_step_per_gpu": s["units"], "error_rows": errs,
@@ -351,7 +381,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("P2E_BENCH_WORKLOAD", "ecdsa"), choices=["mulmod", "ecdsa", "eval"])
+    ap.add_argument("--workload", default=os.environ.get("P2E_BENCH_WORKLOAD", "ecdsa"), choices=["mulmod", "ecdsa", "eval", "glv"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
@@ -364,9 +394,13 @@ def main():
     main_res = b.measure(wl, args.steps, args.warmup, e2e_steps=max(2, min(args.steps, 5)), sample_clocks=True)
     secondary = {}
     if not args.no_secondary:
-        for w2 in ("mulmod", "eval", "ecdsa"):
+        for w2 in ("mulmod", "eval", "glv", "ecdsa"):
             if w2 != wl:
-                r2 = b.measure(w2, steps=min(args.steps, 20), warmup=3, e2e_steps=2)
+                try:
+                    r2 = b.measure(w2, steps=min(args.steps, 20) if w2 != "glv" else 3, warmup=3, e2e_steps=2)
+                except Exception as e:      # noqa: BLE001  (e.g. not enough free HBM for the 32 GB glv witness)
+                    secondary[w2] = {"error": str(e)[:200]}
+                    continue
                 r2.pop("_replay", None)
                 secondary[w2] = r2
     if b.rank == 0:

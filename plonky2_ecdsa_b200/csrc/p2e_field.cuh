@@ -124,7 +124,7 @@ P2E_HD u64 gl_reduce128(u64 lo, u64 hi) {  // (hi:lo) mod P, canonical
 P2E_HD u64 gl_mul(u64 a, u64 b) { return gl_reduce128(a * b, umulhi64(a, b)); }
 
 // canonical Goldilocks representative of a signed integer |v| < 2^63
-P2E_HD u64 gl_from_i64(i64 v) { return v >= 0 ? (u64)v : (u64)v - GL_EPS; }
+P2E_HD u64 gl_from_i64(i64 v) { return (u64)v + ((u64)(v >> 63) & (0ull - GL_EPS)); }   // + P when negative (mod 2^64)
 
 // ------------------------------------------------------------------------------------------
 // limb helpers (u32 limbs are always < 2^29 unless stated)
@@ -642,7 +642,9 @@ P2E_HD u32 mul_witness_core(const u32 (&x)[NL], const u32 (&y)[NL], u32 (&r)[NL]
 #pragma unroll
     for (int j = 0; j < NL; j++) v[i + j] += (i64)((u64)q[i] * (u64)MOD::m(j));
   }
-  bool exact = true;
+  // exact carries: every partial sum must be a multiple of 2^29 and every offset carry must fit 34
+  // bits; both conditions are accumulated branch-free and tested once
+  u64 bad = 0;
   i64 c = 0;
   u32 err = 0;
 #pragma unroll
@@ -650,14 +652,14 @@ P2E_HD u32 mul_witness_core(const u32 (&x)[NL], const u32 (&y)[NL], u32 (&r)[NL]
     cs[i] = gl_from_i64(v[i]);
     if (i < 2 * NL - 2) {
       i64 s = v[i] + c;
-      if ((u64)s & LMASK) exact = false;
+      bad |= (u64)s & LMASK;
       c = s >> LB;
-      i64 o = c + ((i64)1 << 33);
-      b[i] = (u64)o;
-      if (o < 0 || o >= ((i64)1 << 34)) exact = false;
+      u64 o = (u64)(c + ((i64)1 << 33));
+      b[i] = o;
+      bad |= o >> 34;
     }
   }
-  if (!exact) err |= check_sum_slow(cs, b);
+  if (bad) err |= check_sum_slow(cs, b);
   return err;
 }
 
