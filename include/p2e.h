@@ -147,6 +147,8 @@ int p2e_eval_check_sum(size_t n_rows, const uint64_t* wires, uint64_t* out);
 #define P2E_TAPE_CURVE_ADD 2      /* curve_add(p1, p2)                 gadgets/curve.rs:202-223: x1, y1, x2, y2 */
 #define P2E_TAPE_CURVE_DOUBLE 3   /* curve_double(p)                   gadgets/curve.rs:160-185: x, y */
 #define P2E_TAPE_CURVE_COND_ADD 4 /* curve_conditional_add(p1, p2, b)  gadgets/curve.rs:225-243: x1, y1, x2, y2, b */
+#define P2E_TAPE_FIXED_BASE_MUL 5 /* fixed_base_curve_mul_circuit(G, s) gadgets/curve_fixed_base.rs:18-66: s */
+#define P2E_TAPE_CURVE_MSM 6      /* curve_msm_circuit(p, q, n, m)     gadgets/curve_msm.rs:21-79: p.x, p.y, q.x, q.y, n, m */
 size_t p2e_tape_slots(int tape);
 int p2e_tape_inputs(int tape);
 size_t p2e_tape_layout(int tape, uint32_t* kinds, uint32_t* offsets);

@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A, int chain0) {
       p2 = PID_CONST_BASE + (int32_t)(A.t.fixed_table_base + 16u * op.aux + d);
       flag = d != 0;
     } else if (op.type == PT_CADD_MSM) {
-      u32 d = 4u * digit_at(k2, 5, 2 * op.aux, 2) + digit_at(k1, 5, 2 * op.aux, 2);
+      u32 d = 4u * digit_at(k2, NL, 2 * op.aux, 2) + digit_at(k1, NL, 2 * op.aux, 2);
       p2 = A.t.pre_pid[d];
       flag = d != 0;
     } else if (op.type == PT_CADD_BOOL) {
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__(128) k_chain_replay_coop(ChainArgs A, int chai
       p2 = PID_CONST_BASE + (int32_t)(A.t.fixed_table_base + 16u * op.aux + d);
       flag = d != 0;
     } else if (op.type == PT_CADD_MSM) {
-      u32 d = 4u * digit_at(k2, 5, 2 * op.aux, 2) + digit_at(k1, 5, 2 * op.aux, 2);
+      u32 d = 4u * digit_at(k2, NL, 2 * op.aux, 2) + digit_at(k1, NL, 2 * op.aux, 2);
       p2 = A.t.pre_pid[d];
       flag = d != 0;
     } else if (op.type == PT_CADD_BOOL) {

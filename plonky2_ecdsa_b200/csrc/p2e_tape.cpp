@@ -378,7 +378,7 @@ class Builder {
 
   // curve_msm_circuit (curve_msm.rs:21-79)
   PtT curve_msm(const PtT& p, const PtT& q, const NNT& n, const NNT& m) {
-    const int num_limbs = (5 * LB + 1) / 2;                          // 73 2-bit limbs
+    const int num_limbs = (n.r.nl * LB + 1) / 2;                     // 2-bit limbs: 73 for the 5-limb GLV halves, 131 for 9 limbs
     cur_chain = 1;
     t.msm_k1 = n.r;
     t.msm_k2 = m.r;
@@ -460,7 +460,7 @@ class Builder {
 }  // namespace
 
 const Tape& get_tape(int id) {
-  static Tape* tapes[N_TAPES] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  static Tape* tapes[N_TAPES] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (id < 0 || id >= N_TAPES) id = 0;
   if (!tapes[id]) {
     Builder b;
@@ -482,6 +482,15 @@ const Tape& get_tape(int id) {
       case TAPE_CURVE_DOUBLE: {
         PtT p1 = b.input_point(b.input(0), b.input(1));
         b.curve_double(p1.pid, 0);
+        break;
+      }
+      case TAPE_FIXED_BASE_MUL: {
+        b.fixed_base_curve_mul(b.input(0));
+        break;
+      }
+      case TAPE_CURVE_MSM: {
+        PtT p1 = b.input_point(b.input(0), b.input(1)), p2 = b.input_point(b.input(2), b.input(3));
+        b.curve_msm(p1, p2, b.input(4), b.input(5));
         break;
       }
       case TAPE_CURVE_COND_ADD: {

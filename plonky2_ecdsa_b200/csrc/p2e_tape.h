@@ -83,7 +83,9 @@ enum TapeId : int {
   TAPE_CURVE_ADD = 2,    // curve_add(p1, p2) (gadgets/curve.rs:202-223); inputs x1, y1, x2, y2
   TAPE_CURVE_DOUBLE = 3, // curve_double(p) (gadgets/curve.rs:160-185); inputs x, y
   TAPE_CURVE_COND_ADD = 4, // curve_conditional_add(p1, p2, b) (gadgets/curve.rs:225-243); inputs x1, y1, x2, y2, b
-  N_TAPES = 5
+  TAPE_FIXED_BASE_MUL = 5, // fixed_base_curve_mul_circuit(G, scalar) (gadgets/curve_fixed_base.rs:18-66); input scalar
+  TAPE_CURVE_MSM = 6,    // curve_msm_circuit(p, q, n, m) (gadgets/curve_msm.rs:21-79); inputs p.x, p.y, q.x, q.y, n, m
+  N_TAPES = 7
 };
 const Tape& get_tape(int id);
 inline const Tape& ecdsa_tape() { return get_tape(TAPE_ECDSA); }

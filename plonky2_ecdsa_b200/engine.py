@@ -247,7 +247,8 @@ class Engine:
         return out
 
     # ---------------------------------------------------------------- generic gadget tapes
-    TAPE_ECDSA, TAPE_GLV_MUL, TAPE_CURVE_ADD, TAPE_CURVE_DOUBLE, TAPE_CURVE_COND_ADD = range(5)
+    (TAPE_ECDSA, TAPE_GLV_MUL, TAPE_CURVE_ADD, TAPE_CURVE_DOUBLE, TAPE_CURVE_COND_ADD, TAPE_FIXED_BASE_MUL,
+     TAPE_CURVE_MSM) = range(7)
 
     def tape_layout(self, tape):
         cnt = self.lib.p2e_tape_layout(tape, None, None)
@@ -282,6 +283,14 @@ class Engine:
         bm = np.zeros((9, len(b)), dtype=np.uint64)
         bm[0] = np.asarray(b, dtype=np.uint64)
         return self.tape_witness(self.TAPE_CURVE_COND_ADD, [x1, y1, x2, y2, bm])
+
+    def fixed_base_curve_mul(self, scalar):
+        """fixed_base_curve_mul_circuit(G, scalar) witness (gadgets/curve_fixed_base.rs:18-66)."""
+        return self.tape_witness(self.TAPE_FIXED_BASE_MUL, [scalar])
+
+    def curve_msm(self, px, py, qx, qy, n, m):
+        """curve_msm_circuit(p, q, n, m) witness = n*p + m*q (gadgets/curve_msm.rs:21-79), 9-limb scalars."""
+        return self.tape_witness(self.TAPE_CURVE_MSM, [px, py, qx, qy, n, m])
 
     # ---------------------------------------------------------------- ECDSA circuit witness
     def ecdsa_tape_layout(self):

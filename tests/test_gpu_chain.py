@@ -192,3 +192,37 @@ def test_ecdsa_edge_inputs_match_reference_panics(engine):
             assert [int(v) for v in wit[:, 4]] == wb.flat() and err[4] == 0
         except S.RefPanic:
             assert err[4] != 0
+
+
+def test_fixed_base_mul_vs_oracle(engine):
+    """Mirrors test_fixed_base (gadgets/curve_fixed_base.rs:86-116): result == scalar * G."""
+    import random
+    rng = random.Random(55)
+    ks = [rng.randrange(1, S.SECP_N) for _ in range(6)] + [1, S.SECP_N - 1, 16, (1 << 255) + 12345]
+    wit, err = engine.fixed_base_curve_mul(W.ints_to_limbs(ks))
+    assert not err.any()
+    for j, k in enumerate(ks):
+        wb = S.WitnessBuilder()
+        res = wb.fixed_base_curve_mul(S.G, S.NN(S.limbs9(k)))
+        assert [int(v) for v in wit[:, j]] == wb.flat()
+        assert (S.get_biguint(res[0].limbs), S.get_biguint(res[1].limbs)) == S.pt_mul(k, S.G)
+
+
+def test_curve_msm_vs_oracle(engine):
+    """Mirrors test_curve_msm (gadgets/curve_msm.rs:98-136): result == n*p + m*q with full-width scalars."""
+    import random
+    rng = random.Random(56)
+    cnt = 5
+    P, Q = _rand_points(cnt, 57), _rand_points(cnt, 58)
+    ns = [rng.randrange(1, S.SECP_N) for _ in range(cnt)]
+    ms = [rng.randrange(1, S.SECP_N) for _ in range(cnt)]
+    wit, err = engine.curve_msm(W.ints_to_limbs([p[0] for p in P]), W.ints_to_limbs([p[1] for p in P]),
+                                W.ints_to_limbs([p[0] for p in Q]), W.ints_to_limbs([p[1] for p in Q]),
+                                W.ints_to_limbs(ns), W.ints_to_limbs(ms))
+    assert not err.any()
+    for j in range(cnt):
+        wb = S.WitnessBuilder()
+        res = wb.curve_msm(wb.constant_affine_point(P[j]), wb.constant_affine_point(Q[j]), S.NN(S.limbs9(ns[j])), S.NN(S.limbs9(ms[j])))
+        assert [int(v) for v in wit[:, j]] == wb.flat()
+        want = S.pt_add(S.pt_mul(ns[j], P[j]), S.pt_mul(ms[j], Q[j]))
+        assert (S.get_biguint(res[0].limbs), S.get_biguint(res[1].limbs)) == want

@@ -69,3 +69,16 @@ def test_curve_op_tapes_match_oracle():
     wb.curve_conditional_add(wb.constant_affine_point(P), wb.constant_affine_point(Q), 1)
     assert _tape(lib, 4) == (*_oracle_layout(wb.tape), 5) and _tape(lib, 4)[2] == 251
     assert lib.p2e_tape_slots(99) == 0 and lib.p2e_tape_inputs(-1) == -1
+
+
+def test_fixed_base_and_msm_tapes_match_oracle():
+    """fixed_base_curve_mul_circuit (curve_fixed_base.rs:18-66) and curve_msm_circuit with 9-limb
+    scalars (curve_msm.rs:21-79: 131 two-bit digits)."""
+    lib = pkg.load_library()
+    wb = S.WitnessBuilder()
+    wb.fixed_base_curve_mul(S.G, S.NN(S.limbs9(0x1234 << 230 | 77)))
+    assert _tape(lib, 5) == (*_oracle_layout(wb.tape), 1)
+    P, Q = S.pt_mul(5, S.G), S.pt_mul(9, S.G)
+    wb = S.WitnessBuilder()
+    wb.curve_msm(wb.constant_affine_point(P), wb.constant_affine_point(Q), S.NN(S.limbs9(3 << 250 | 1)), S.NN(S.limbs9(5 << 249 | 2)))
+    assert _tape(lib, 6) == (*_oracle_layout(wb.tape), 6)
