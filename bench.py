@@ -30,12 +30,14 @@ WORKLOAD_NAMES = {
     "mulmod": "2^20 secp256k1 base-field nonnative mulmod witnesses (29-bit limbs): q, r, check_sum, carries",
     "eval": "MulNonnativeGate eval_unfiltered_base_batch over 2^20 Goldilocks LDE rows",
     "glv": "glv_mul witness chain (GLV decomposition + 2-scalar MSM) for 2^16 secp256k1 scalars, P = 7G",
+    "evalcs": "CheckSumGate eval_unfiltered_base_batch over 2^20 Goldilocks LDE rows",
 }
 METRICS = {
     "ecdsa": ("ecdsa_circuit_witnesses_per_s", "witnesses/s"),
     "mulmod": ("nonnative_mulmod_witnesses_per_s", "mulmod/s"),
     "eval": ("mul_nonnative_gate_rows_per_s", "rows/s"),
     "glv": ("glv_mul_witness_chains_per_s", "chains/s"),
+    "evalcs": ("check_sum_gate_rows_per_s", "rows/s"),
 }
 
 
@@ -196,6 +198,23 @@ class Bench:
             return dict(step=step, step_e2e=step_e2e, units=n, h2d=53 * 8 * n, d2h=17 * 8 * n, alg_bytes=560 * n,
                         kernel="k_eval_mul_nonnative<ModP>", launches=1, err=None, dtype="u64 (Goldilocks)",
                         keep=(wd, od, hw, ho))
+        if wl == "evalcs":
+            n = 1 << 20
+            w = W.random_goldilocks(W.SEED + 3 + self.rank, 33, n)
+            wd = self.dev(w)
+            od = torch.empty((17, n), dtype=torch.int64, device="cuda")
+
+            def step():
+                rc = lib.p2e_eval_check_sum_dev(n, wd.data_ptr(), n, od.data_ptr(), n, sp)
+                assert rc == 0, eng.last_error()
+            hw = self.pinned(w)
+            ho = torch.empty((17, n), dtype=torch.int64).pin_memory()
+
+            def step_e2e():
+                rc = lib.p2e_eval_check_sum(n, hw.data_ptr(), ho.data_ptr())
+                assert rc == 0, eng.last_error()
+            return dict(step=step, step_e2e=step_e2e, units=n, h2d=33 * 8 * n, d2h=17 * 8 * n, alg_bytes=400 * n,
+                        kernel="k_eval_check_sum", launches=1, err=None, dtype="u64 (Goldilocks)", keep=(wd, od, hw, ho))
         if wl == "glv":
             # device-resident only at full size (the 2^16 x 61.6k-slot witness is 32 GB); e2e on a 4096-scalar slice
             n = 1 << 16
@@ -254,10 +273,23 @@ class Bench:
         ho = torch.empty((slots, n), dtype=torch.int64).pin_memory()
         he = torch.empty(n, dtype=torch.int32).pin_memory()
 
-        def step_e2e():
+        def step_e2e_plain():
             rc = lib.p2e_ecdsa_witness(n, *[t.data_ptr() for t in hin], ho.data_ptr(), he.data_ptr())
             assert rc == 0, eng.last_error()
-        return dict(step=step, step_e2e=step_e2e, units=n, h2d=5 * 9 * 8 * n, d2h=slots * 8 * n + 4 * n,
+        # headline e2e goes through the compact host format (u32 narrow slots + u64 wide slots): same
+        # values, 28 % fewer PCIe bytes; the plain u64 path is reported next to it
+        import ctypes
+        _, nn, nw = eng.tape_compact_layout(eng.TAPE_ECDSA)
+        hn = torch.empty((nn, n), dtype=torch.int32).pin_memory()
+        hw = torch.empty((nw, n), dtype=torch.int64).pin_memory()
+        in_arr = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in hin])
+        in_ptr = ctypes.cast(in_arr, ctypes.c_void_p)
+
+        def step_e2e():
+            rc = lib.p2e_tape_witness_compact(eng.TAPE_ECDSA, n, in_ptr, hn.data_ptr(), hw.data_ptr(), he.data_ptr())
+            assert rc == 0, eng.last_error()
+        return dict(step=step, step_e2e=step_e2e, step_e2e_plain=step_e2e_plain, units=n, h2d=5 * 9 * 8 * n,
+                    d2h=nn * 4 * n + nw * 8 * n + 4 * n, d2h_plain=slots * 8 * n + 4 * n, e2e_keep=(hn, hw, in_arr),
                     alg_bytes=slots * 8 * n, kernel="k_chain_expand", launches=7, err=ed, dtype="u32 limbs / u64 (int)",
                     keep=(ind, ods, eds, hin, ho, he), slots=slots, streams=streams, step_single=step_single)
 
@@ -327,6 +359,15 @@ class Bench:
             step_e2e()
         self.barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
+        e2e_plain_ms = None
+        if "step_e2e_plain" in s:
+            s["step_e2e_plain"]()
+            self.barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                s["step_e2e_plain"]()
+            self.barrier()
+            e2e_plain_ms = (time.perf_counter() - t0) * 1e3 / 2
         errs = int((s["err"] != 0).sum().item()) if s["err"] is not None else 0
         t = torch.tensor([ms, e2e_ms, float(errs)], dtype=torch.float64, device="cuda")
         if self.dist is not None:
@@ -345,6 +386,11 @@ class Bench:
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
             "gpu_launches": s["launches"] * steps,
         }
+        if e2e_plain_ms is not None:
+            res["e2e"]["format"] = "compact (p2e_tape_witness_compact: u32 narrow slots + u64 wide slots)"
+            res["e2e_u64"] = {"value": s["units"] * self.world / (e2e_plain_ms * 1e-3), "unit": METRICS[wl][1],
+                              "d2h_bytes_per_step": s["d2h_plain"], "ms_per_step": e2e_plain_ms,
+                              "format": "plain (p2e_ecdsa_witness: u64 per slot)"}
         if streams:
             res["streams"] = len(streams)
             res["single_stream_ms_per_step"] = latency_ms
@@ -381,7 +427,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("P2E_BENCH_WORKLOAD", "ecdsa"), choices=["mulmod", "ecdsa", "eval", "glv"])
+    ap.add_argument("--workload", default=os.environ.get("P2E_BENCH_WORKLOAD", "ecdsa"), choices=["mulmod", "ecdsa", "eval", "glv", "evalcs"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
@@ -394,7 +440,7 @@ def main():
     main_res = b.measure(wl, args.steps, args.warmup, e2e_steps=max(2, min(args.steps, 5)), sample_clocks=True)
     secondary = {}
     if not args.no_secondary:
-        for w2 in ("mulmod", "eval", "glv", "ecdsa"):
+        for w2 in ("mulmod", "eval", "evalcs", "glv", "ecdsa"):
             if w2 != wl:
                 try:
                     r2 = b.measure(w2, steps=min(args.steps, 20) if w2 != "glv" else 3, warmup=3, e2e_steps=2)
@@ -415,7 +461,8 @@ def main():
                        "pipelining": "steps are independent batches enqueued round-robin on `streams` CUDA streams through the async *_dev "
                                      "entry point; ms_per_step = timed region / steps; single_stream_ms_per_step = one batch at a time",
                        "single_stream_ms_per_step": main_res.get("single_stream_ms_per_step")},
-            "e2e": main_res["e2e"], "gpu_launches": main_res["gpu_launches"], "clocks": main_res.get("clocks"),
+            "e2e": main_res["e2e"], "e2e_u64": main_res.get("e2e_u64"), "gpu_launches": main_res["gpu_launches"],
+            "clocks": main_res.get("clocks"),
             "roofline": main_res["roofline"],
         }
         if "kernel_ms" in main_res:

@@ -156,6 +156,16 @@ int p2e_tape_witness_dev(int tape, size_t n, const uint64_t* const* inputs, size
                          uint64_t* out, size_t out_stride, uint32_t* err, void* stream);
 int p2e_tape_witness(int tape, size_t n, const uint64_t* const* inputs, uint64_t* out, uint32_t* err);
 
+/* Compact host format (cuts the PCIe bytes of the host-pointer path by ~28 %): slots that always fit
+ * 32 bits (limbs of ADD / ADDMANY / SUB / INV / GLV tuples, overflow flags, r and q of MUL tuples) are
+ * delivered as uint32_t in `narrow` [narrow_slots][n]; check_sum and carry slots (full field elements /
+ * 34-bit values) as uint64_t in `wide` [wide_slots][n].  p2e_tape_compact_layout() fills, for every
+ * slot of the plain layout, (1u << 31 | wide row) or the narrow row; it returns the slot count and
+ * writes the two row counts.  Same values, same order, different storage width. */
+size_t p2e_tape_compact_layout(int tape, uint32_t* map, uint32_t* narrow_slots, uint32_t* wide_slots);
+int p2e_tape_witness_compact(int tape, size_t n, const uint64_t* const* inputs, uint32_t* narrow,
+                             uint64_t* wide, uint32_t* err);
+
 /* ---- ECDSA verification circuit witness (tape) ----------------------------------------- */
 
 /* Number of u64 slots one verify_secp256k1_message_circuit witness occupies in tape order

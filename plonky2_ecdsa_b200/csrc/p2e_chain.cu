@@ -867,6 +867,22 @@ __global__ void __launch_bounds__(32) k_chain_checks(ChainArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------
+// compact host format: split the [slots][n] u64 witness into a u32 matrix (narrow slots) and a u64
+// matrix (wide slots); map[slot] = (1u << 31 | wide row) or narrow row
+__global__ void __launch_bounds__(256) k_pack_compact(size_t n, size_t n_slots, const u64* __restrict__ wit, size_t ws,
+                                                      const u32* __restrict__ map, u32* __restrict__ narrow,
+                                                      u64* __restrict__ wide) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (size_t s = blockIdx.y; s < n_slots; s += gridDim.y) {
+    const u32 m = map[s];
+    const u64 v = wit[s * ws + i];
+    if (m >> 31) wide[(size_t)(m & 0x7fffffffu) * n + i] = v;
+    else narrow[(size_t)m * n + i] = (u32)v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side: device copies of the tapes, scratch, launch sequence
 struct TapeOnDevice {
   bool ready = false;
@@ -1204,6 +1220,69 @@ int p2e_tape_witness(int tape, size_t n, const uint64_t* const* inputs, uint64_t
   return run_tape_host(t, n, inputs, n_in, out, err, [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* st) {
     return run_tape(tape, t, n, d, n_in, n, o, n, e, st);
   });
+}
+
+size_t p2e_tape_compact_layout(int tape, uint32_t* map, uint32_t* narrow_slots, uint32_t* wide_slots) {
+  if (bad_tape(tape)) return 0;
+  const Tape& t = get_tape(tape);
+  uint32_t nn = 0, nw = 0;
+  for (size_t g = 0; g < t.gen_kind.size(); g++) {
+    const uint32_t kind = t.gen_kind[g], off = t.gen_off[g];
+    const uint32_t end = (g + 1 < t.gen_kind.size()) ? t.gen_off[g + 1] : t.n_slots;
+    for (uint32_t s = off; s < end; s++) {
+      // MUL tuple: r[9], q[9] narrow, check_sum[17] wide; CHECKSUM tuple: b[16] wide; everything else narrow
+      const bool is_wide = (kind == G_CHECKSUM) || (kind == G_MUL && s - off >= 18);
+      if (map) map[s] = is_wide ? ((1u << 31) | nw) : nn;
+      if (is_wide) nw++; else nn++;
+    }
+  }
+  if (narrow_slots) *narrow_slots = nn;
+  if (wide_slots) *wide_slots = nw;
+  return t.n_slots;
+}
+
+int p2e_tape_witness_compact(int tape, size_t n, const uint64_t* const* inputs, uint32_t* narrow, uint64_t* wide,
+                             uint32_t* err) {
+  if (bad_tape(tape)) return -1;
+  int rc = ensure_ready();
+  if (rc) return rc;
+  if (n == 0) return 0;
+  const Tape& t = get_tape(tape);
+  const int n_in = (int)t.n_inputs;
+  static std::vector<uint32_t> maps[N_TAPES];
+  static void* dmaps[N_TAPES] = {nullptr};
+  static int dmap_device[N_TAPES];
+  uint32_t nn = 0, nw = 0;
+  if (maps[tape].empty()) maps[tape].resize(t.n_slots);
+  p2e_tape_compact_layout(tape, maps[tape].data(), &nn, &nw);
+  if (!dmaps[tape] || dmap_device[tape] != ctx().device) {
+    P2E_CUDA(cudaMalloc(&dmaps[tape], (size_t)t.n_slots * 4));
+    P2E_CUDA(cudaMemcpy(dmaps[tape], maps[tape].data(), (size_t)t.n_slots * 4, cudaMemcpyHostToDevice));
+    dmap_device[tape] = ctx().device;
+  }
+  cudaStream_t st = ctx().stream;
+  void *din = nullptr, *dout = nullptr, *derr = nullptr, *dpack = nullptr;
+  if ((rc = get_scratch(0, (size_t)n_in * 9 * n * 8, &din))) return rc;
+  if ((rc = get_scratch(1, (size_t)t.n_slots * n * 8, &dout))) return rc;
+  if ((rc = get_scratch(2, n * 4, &derr))) return rc;
+  const size_t nbytes = (size_t)nn * n * 4, wbytes = (size_t)nw * n * 8;
+  if ((rc = get_scratch(3, ((nbytes + 15) / 16) * 16 + wbytes, &dpack))) return rc;
+  u32* dn = (u32*)dpack;
+  u64* dw = (u64*)((char*)dpack + ((nbytes + 15) / 16) * 16);
+  const uint64_t* dptr[8];
+  for (int k = 0; k < n_in; k++) {
+    dptr[k] = (const uint64_t*)din + (size_t)k * 9 * n;
+    P2E_CUDA(cudaMemcpyAsync((uint64_t*)din + (size_t)k * 9 * n, inputs[k], 9 * n * 8, cudaMemcpyHostToDevice, st));
+  }
+  if ((rc = run_tape(tape, t, n, dptr, n_in, n, (uint64_t*)dout, n, (uint32_t*)derr, (void*)st))) return rc;
+  k_pack_compact<<<dim3((unsigned)((n + 255) / 256), 1024), 256, 0, st>>>(n, t.n_slots, (const u64*)dout, n,
+                                                                         (const u32*)dmaps[tape], dn, dw);
+  P2E_CUDA(cudaGetLastError());
+  P2E_CUDA(cudaMemcpyAsync(narrow, dn, nbytes, cudaMemcpyDeviceToHost, st));
+  P2E_CUDA(cudaMemcpyAsync(wide, dw, wbytes, cudaMemcpyDeviceToHost, st));
+  if (err) P2E_CUDA(cudaMemcpyAsync(err, derr, n * 4, cudaMemcpyDeviceToHost, st));
+  P2E_CUDA(cudaStreamSynchronize(st));
+  return 0;
 }
 
 size_t p2e_ecdsa_tape_slots(void) { return p2e_tape_slots(TAPE_ECDSA); }

@@ -83,6 +83,8 @@ SIGNATURES = {
     "p2e_tape_layout": (_sz, [_int, _vp, _vp]),
     "p2e_tape_witness_dev": (_int, [_int, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
     "p2e_tape_witness": (_int, [_int, _sz, _vp, _vp, _vp]),
+    "p2e_tape_compact_layout": (_sz, [_int, _vp, _vp, _vp]),
+    "p2e_tape_witness_compact": (_int, [_int, _sz, _vp, _vp, _vp, _vp]),
     "p2e_ecdsa_tape_slots": (_sz, []),
     "p2e_ecdsa_tape_layout": (_sz, [_vp, _vp]),
     "p2e_ecdsa_witness_dev": (_int, [_sz, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),
@@ -269,6 +271,35 @@ class Engine:
         arr = (ctypes.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
         self._check(self.lib.p2e_tape_witness(tape, n, ctypes.cast(arr, ctypes.c_void_p), _ptr(out), _ptr(err)))
         return out, err
+
+    def tape_compact_layout(self, tape):
+        """-> (map [slots] uint32: (1 << 31 | wide row) or narrow row, narrow_slots, wide_slots)."""
+        slots = int(self.lib.p2e_tape_slots(tape))
+        m = np.empty(slots, dtype=np.uint32)
+        nn, nw = ctypes.c_uint32(0), ctypes.c_uint32(0)
+        self.lib.p2e_tape_compact_layout(tape, _ptr(m), ctypes.addressof(nn), ctypes.addressof(nw))
+        return m, int(nn.value), int(nw.value)
+
+    def tape_witness_compact(self, tape, inputs):
+        """Like tape_witness but in the compact host format: (narrow [ns][n] uint32, wide [ws][n] uint64, err)."""
+        ins = [_host_u64(a, 9) for a in inputs]
+        n = ins[0].shape[1]
+        _, nn, nw = self.tape_compact_layout(tape)
+        narrow = np.empty((nn, n), dtype=np.uint32)
+        wide = np.empty((nw, n), dtype=np.uint64)
+        err = np.empty(n, dtype=np.uint32)
+        arr = (ctypes.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
+        self._check(self.lib.p2e_tape_witness_compact(tape, n, ctypes.cast(arr, ctypes.c_void_p), _ptr(narrow), _ptr(wide), _ptr(err)))
+        return narrow, wide, err
+
+    @staticmethod
+    def expand_compact(cmap, narrow, wide):
+        """Compact -> plain [slots][n] uint64 (host-side helper for tests / the Rust shim's unpack)."""
+        out = np.empty((cmap.shape[0], narrow.shape[1]), dtype=np.uint64)
+        is_wide = (cmap >> np.uint32(31)).astype(bool)
+        out[is_wide] = wide[cmap[is_wide] & np.uint32(0x7FFFFFFF)]
+        out[~is_wide] = narrow[cmap[~is_wide]]
+        return out
 
     def curve_add(self, x1, y1, x2, y2):
         """curve_add(p1, p2) witness (gadgets/curve.rs:202-223): 231 slots per instance."""

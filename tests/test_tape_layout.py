@@ -82,3 +82,25 @@ def test_fixed_base_and_msm_tapes_match_oracle():
     wb = S.WitnessBuilder()
     wb.curve_msm(wb.constant_affine_point(P), wb.constant_affine_point(Q), S.NN(S.limbs9(3 << 250 | 1)), S.NN(S.limbs9(5 << 249 | 2)))
     assert _tape(lib, 6) == (*_oracle_layout(wb.tape), 6)
+
+
+def test_compact_layout_map():
+    """Compact host format: narrow rows for <= 32-bit slots, wide rows for check_sum / carry slots."""
+    lib = pkg.load_library()
+    slots = int(lib.p2e_tape_slots(0))
+    m = np.empty(slots, dtype=np.uint32)
+    import ctypes
+    nn, nw = ctypes.c_uint32(0), ctypes.c_uint32(0)
+    assert lib.p2e_tape_compact_layout(0, m.ctypes.data, ctypes.addressof(nn), ctypes.addressof(nw)) == slots
+    assert nw.value == 1087 * 33 and nn.value + nw.value == slots
+    wide = (m >> np.uint32(31)).astype(bool)
+    assert wide.sum() == nw.value
+    # rows are dense and in slot order within each class
+    assert np.array_equal(m[wide] & np.uint32(0x7FFFFFFF), np.arange(nw.value, dtype=np.uint32))
+    assert np.array_equal(m[~wide], np.arange(nn.value, dtype=np.uint32))
+    # oracle: exactly the check_sum / carry slots exceed 32 bits in a real witness
+    sk, msg, k = 0x1234567 << 200 | 99, 0xabcdef << 180 | 5, 0x777 << 222 | 1
+    r, s = S.sign_message(msg, sk, k)
+    flat = np.array(S.ecdsa_witness(msg, r, s, S.pt_mul(sk, S.G)).flat(), dtype=np.uint64)
+    assert not (flat[~wide] >> np.uint64(32)).any()
+    assert (flat[wide] >> np.uint64(32)).any()
