@@ -20,6 +20,10 @@
 #include "p2e_field.cuh"
 #include "p2e_tape.h"
 
+#ifndef P2E_DEFAULT_REPLAY
+#define P2E_DEFAULT_REPLAY 2
+#endif
+
 namespace p2e {
 
 constexpr int32_t PID_INPUT_BASE = 1 << 19;
@@ -478,6 +482,156 @@ __global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A, int chain0) {
     if (op.flags & PF_SET_CUR) cur = flag ? k : p1;
   }
   if (err) atomicOr(&A.err[i], err);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 (two-lane form): lanes 2j and 2j+1 serve the same (signature, chain).  Both keep every value in
+// registers; at each step of the point formulas the two lanes compute the two products of an
+// INDEPENDENT pair and swap the results with a 9-word shfl_xor, so a general addition is 8
+// sequential multiplications instead of 16 (mixed: 6 vs 11, doubling: 4 vs 7).  Static schedule,
+// no shared memory; linear steps are done redundantly by both lanes.
+__device__ __forceinline__ void duo_mul2(bool odd, const i32 (&a)[NL], const i32 (&b)[NL], i32 (&r1)[NL],
+                                         const i32 (&c)[NL], const i32 (&d)[NL], i32 (&r2)[NL]) {
+  I9 x, y;
+#pragma unroll
+  for (int l = 0; l < NL; l++) { x.v[l] = odd ? c[l] : a[l]; y.v[l] = odd ? d[l] : b[l]; }
+  I9 mine = lzm_v(x, y);
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    i32 other = __shfl_xor_sync(0xffffffffu, mine.v[l], 1);
+    r1[l] = odd ? other : mine.v[l];
+    r2[l] = odd ? mine.v[l] : other;
+  }
+}
+
+template <bool Q_AFFINE>
+__device__ __forceinline__ void duo_add(bool odd, const JacL& P, const JacL& Q, JacL& R) {
+  i32 z1z1[NL], u1[NL], u2[NL], s1[NL], s2[NL], h[NL], r[NL], t[NL], t2[NL], hh[NL], rr[NL], hhh[NL], v[NL], w[NL];
+  if (Q_AFFINE) {
+    lzs(P.Z, z1z1);
+    duo_mul2(odd, Q.Y, P.Z, t2, Q.X, z1z1, u2);
+    lz_sub(u2, P.X, h);
+    duo_mul2(odd, t2, z1z1, s2, h, h, hh);
+    lz_sub(s2, P.Y, r);
+    duo_mul2(odd, r, r, rr, h, hh, hhh);
+    duo_mul2(odd, P.X, hh, v, P.Z, h, R.Z);          // Z3 = Z1 h
+    lz_sub(rr, hhh, t);
+    lz_lin(t, 1, v, 2, R.X);                        // X3 = r^2 - hhh - 2v
+    lz_sub(v, R.X, w);
+    duo_mul2(odd, r, w, t, P.Y, hhh, t2);
+    lz_sub(t, t2, R.Y);                             // Y3 = r (v - X3) - Y1 hhh
+  } else {
+    i32 z2z2[NL], zz[NL];
+    duo_mul2(odd, P.Z, P.Z, z1z1, Q.Z, Q.Z, z2z2);
+    duo_mul2(odd, P.Y, Q.Z, t, Q.Y, P.Z, t2);
+    duo_mul2(odd, P.X, z2z2, u1, Q.X, z1z1, u2);
+    duo_mul2(odd, t, z2z2, s1, t2, z1z1, s2);
+    lz_sub(u2, u1, h);
+    lz_sub(s2, s1, r);
+    duo_mul2(odd, h, h, hh, r, r, rr);
+    duo_mul2(odd, P.Z, Q.Z, zz, h, hh, hhh);
+    duo_mul2(odd, u1, hh, v, zz, h, R.Z);            // Z3 = Z1 Z2 h
+    lz_sub(rr, hhh, t);
+    lz_lin(t, 1, v, 2, R.X);
+    lz_sub(v, R.X, w);
+    duo_mul2(odd, r, w, t, s1, hhh, t2);
+    lz_sub(t, t2, R.Y);
+  }
+}
+
+__device__ __forceinline__ void duo_dbl(bool odd, const JacL& P, JacL& R) {
+  i32 xx[NL], yy[NL], yyyy[NL], s[NL], m[NL], t[NL], t2[NL], yz[NL], mm[NL];
+  duo_mul2(odd, P.X, P.X, xx, P.Y, P.Y, yy);
+  lz_lin(xx, 3, xx, 0, m);             // M = 3 XX
+  duo_mul2(odd, yy, yy, yyyy, P.X, yy, t);
+  lz_lin(t, 4, t, 0, s);               // S = 4 X YY
+  duo_mul2(odd, P.Y, P.Z, yz, m, m, mm);
+  lz_lin(mm, 1, s, 2, R.X);            // X3 = M^2 - 2S
+  lz_sub(s, R.X, t);
+  lzm(m, t, t2);                       // both lanes (redundant): no partner product left
+  lz_lin(t2, 1, yyyy, 8, R.Y);         // Y3 = M (S - X3) - 8 YYYY
+  lz_lin(yz, 2, yz, 0, R.Z);           // Z3 = 2 Y1 Z1
+}
+
+__global__ void __launch_bounds__(64) k_chain_replay_duo(ChainArgs A, int chain0) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool odd = threadIdx.x & 1;
+  const size_t i_raw = tid >> 1;
+  const bool valid = i_raw < A.n;
+  const size_t i = valid ? i_raw : A.n - 1;       // the pair of an out-of-range task shadows the last signature
+  const bool writer = valid && !odd;
+  const int chain = chain0 + blockIdx.y;
+  const int k_begin = A.t.chain_begin[chain], k_end = A.t.chain_end[chain];
+  if (k_begin == k_end) return;
+  u32 err = 0;
+  if (writer) {
+    for (int j = 0; j < A.t.n_in_points; j++) {
+      u64 w[NL];
+      u32 x[NL], y[NL], one[NL];
+      load_ref(A, A.t.in_points[j].x, i, w);
+      err |= load_canon<ModP>(w, x);
+      load_ref(A, A.t.in_points[j].y, i, w);
+      err |= load_canon<ModP>(w, y);
+      set_zero9(one);
+      one[0] = 1;
+      int idx = A.t.n_ptops + j;
+      sv9(A.JX, idx, A.cap, i, x);
+      sv9(A.JY, idx, A.cap, i, y);
+      sv9(A.JZ, idx, A.cap, i, one);
+      sv9(A.AX, idx, A.cap, i, x);
+      sv9(A.AY, idx, A.cap, i, y);
+      sv9(A.ZC, idx, A.cap, i, one);
+    }
+  }
+  __syncwarp();                                    // the partner lane reads the input points just written
+  u32 fs[NL], k1[NL], k2[NL];
+  err |= load_scalar_limbs(A, A.t.fixed_scalar, i, fs);
+  err |= load_scalar_limbs(A, A.t.msm_k1, i, k1);
+  err |= load_scalar_limbs(A, A.t.msm_k2, i, k2);
+
+  int32_t cur = -1, resident = -2;
+  JacL R;
+  for (int k = k_begin; k < k_end; k++) {
+    const PtOp op = A.t.ptops[k];
+    int32_t p1 = (op.flags & PF_P1_CUR) ? cur : op.p1;
+    int32_t p2 = (op.flags & PF_P2_CUR) ? cur : op.p2;
+    u32 flag = 1;
+    if (op.type == PT_CADD_FIXED) {
+      u32 d = digit_at(fs, NL, 4 * op.aux, 4);
+      p2 = PID_CONST_BASE + (int32_t)(A.t.fixed_table_base + 16u * op.aux + d);
+      flag = d != 0;
+    } else if (op.type == PT_CADD_MSM) {
+      u32 d = 4u * digit_at(k2, NL, 2 * op.aux, 2) + digit_at(k1, NL, 2 * op.aux, 2);
+      p2 = A.t.pre_pid[d];
+      flag = d != 0;
+    } else if (op.type == PT_CADD_BOOL) {
+      flag = load_wire(A, SP_IN, 9u * op.aux, i) != 0;
+    }
+    // operands: the previous result is still in registers; anything else comes from global scratch,
+    // which only the even lane writes -> make those stores visible to the odd lane first
+    JacL P, Q;
+    if (p1 == resident) P = R; else load_jac(A, p1, i, P);
+    if (op.type == PT_DBL) {
+      duo_dbl(odd, P, R);
+      p2 = p1;
+    } else {
+      if (p2 == resident) Q = R; else load_jac(A, p2, i, Q);
+      if (op.flags & PF_P2_AFFINE) duo_add<true>(odd, P, Q, R);
+      else duo_add<false>(odd, P, Q, R);
+    }
+    if (writer) {
+      sv9(A.JX, k, A.cap, i, R.X);
+      sv9(A.JY, k, A.cap, i, R.Y);
+      sv9(A.JZ, k, A.cap, i, R.Z);
+      A.SRC1[(size_t)k * A.cap + i] = p1;
+      A.SRC2[(size_t)k * A.cap + i] = p2;
+      A.FLG[(size_t)k * A.cap + i] = (uint8_t)flag;
+    }
+    __syncwarp();
+    resident = k;
+    if (op.flags & PF_SET_CUR) cur = flag ? k : p1;
+  }
+  if (err && writer) atomicOr(&A.err[i], err);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1014,12 +1168,12 @@ static void prof_mark(cudaStream_t st) {
   g_event_stream = st;
 }
 
-static bool replay_coop() {
-  // Measured on B200 (4096 signatures): cooperative 1.39 ms vs one-thread-per-chain 1.13 ms -- the
-  // runtime-indexed shared-memory staging costs 2.9x the warp instructions (profiles/r01_notes.md),
-  // so the serial kernel is the default; P2E_CHAIN_REPLAY=coop selects the cooperative one.
+// replay kernel: 0 one thread per (signature, chain); 1 four lanes + shared memory (measured slower,
+// profiles/r01_notes.md); 2 two lanes + register shuffles.  P2E_CHAIN_REPLAY = serial | coop | duo.
+static int replay_mode() {
   const char* e = getenv("P2E_CHAIN_REPLAY");
-  return e && e[0] == 'c';
+  if (!e) return P2E_DEFAULT_REPLAY;
+  return e[0] == 'c' ? 1 : e[0] == 'd' ? 2 : 0;
 }
 
 static unsigned inv_groups() {
@@ -1097,7 +1251,12 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
     k_prep<<<g32, 32, 0, s_hi>>>(A);
     if (prof) prof_mark(st);
     if (no) {
-      if (replay_coop()) {
+      if (replay_mode() == 2) {
+        const unsigned g_duo = (unsigned)((2 * cn + 63) / 64);
+        k_chain_replay_duo<<<dim3(g_duo, 2), 64, 0, s_hi>>>(A, 0);      // 2 lanes per (signature, chain)
+        if (prof) prof_mark(st);
+        if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay_duo<<<dim3(g_duo, 1), 64, 0, s_hi>>>(A, 2);   // join
+      } else if (replay_mode() == 1) {
         k_chain_replay_coop<<<dim3(g32, 2), 128, 0, s_hi>>>(A, 0);    // 4 lanes per (signature, chain)
         if (prof) prof_mark(st);
         if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay_coop<<<dim3(g32, 1), 128, 0, s_hi>>>(A, 2);   // join

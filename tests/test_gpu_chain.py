@@ -143,14 +143,22 @@ def test_chain_chunking_is_transparent(engine, monkeypatch):
     assert [int(v) for v in w2[:, 299]] == wb.flat()
 
 
-def test_cooperative_replay_kernel_is_bit_exact(engine, monkeypatch):
-    """The opt-in 4-lanes-per-task replay kernel (P2E_CHAIN_REPLAY=coop) must give the same witness."""
-    wl = W.ecdsa_workload(70, seed=31)
+@pytest.mark.parametrize("mode", ["serial", "coop", "duo"])
+def test_replay_kernel_variants_are_bit_exact(engine, monkeypatch, mode):
+    """All replay kernels (one thread / two lanes + shuffles / four lanes + shared memory per
+    (signature, chain), P2E_CHAIN_REPLAY) must give the same witness; odd batch size on purpose."""
+    wl = W.ecdsa_workload(71, seed=31)
     args = (wl["msg"], wl["r"], wl["s"], wl["pkx"], wl["pky"])
-    w1, e1 = engine.verify_secp256k1_message_witness(*args)
-    monkeypatch.setenv("P2E_CHAIN_REPLAY", "coop")
+    monkeypatch.setenv("P2E_CHAIN_REPLAY", mode)
     w2, e2 = engine.verify_secp256k1_message_witness(*args)
-    assert np.array_equal(w1, w2) and np.array_equal(e1, e2) and not e1.any()
+    assert not e2.any()
+    i = wl["ints"]
+    for j in (0, 35, 70):
+        ref = S.ecdsa_witness(i["msg"][j], i["r"][j], i["s"][j], (i["pkx"][j], i["pky"][j])).flat()
+        assert [int(v) for v in w2[:, j]] == ref
+    monkeypatch.setenv("P2E_CHAIN_REPLAY", "serial")
+    w1, e1 = engine.verify_secp256k1_message_witness(*args)
+    assert np.array_equal(w1, w2) and np.array_equal(e1, e2)
 
 
 def test_ecdsa_edge_inputs_match_reference_panics(engine):
