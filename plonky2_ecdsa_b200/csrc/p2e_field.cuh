@@ -458,9 +458,88 @@ P2E_HD void inv_n(const u32 (&a)[NL], u32 (&r)[NL]) {
   copy9(acc, r);
 }
 
+// ------------------------------------------------------------------------------------------
+// Montgomery arithmetic mod n (scalar field) in 29-bit limbs, R = 2^261.  Because R > 32 n, products
+// of values below 2^258 stay below 2^257 without a final subtraction, so a whole exponentiation runs
+// on "almost reduced" values and is canonicalised once.  ~235 instructions per product with a
+// 9-step dependency chain, against ~600 (and serial carry ripples) for the exact special-form
+// reduction: this is what the per-signature scalar inverse c = s^-1 (ecdsa.rs:40) runs on.
+constexpr u32 MONT_N_PRIME = 0x1588b13fu;           // -n^-1 mod 2^29
+P2E_HD void mont_n_reduce(u64 (&col)[2 * NL], u32 (&r)[NL]) {
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    u32 m = ((u32)col[i] * MONT_N_PRIME) & LMASK;
+#pragma unroll
+    for (int j = 0; j < NL; j++) col[i + j] += (u64)m * (u64)ModN::m(j);
+    col[i + 1] += col[i] >> LB;                       // low 29 bits of col[i] are now zero
+  }
+  u64 c = 0;
+#pragma unroll
+  for (int j = 0; j < NL; j++) {
+    u64 v = col[NL + j] + c;
+    r[j] = (u32)v & LMASK;
+    c = v >> LB;
+  }
+}
+P2E_HD void mont_n_mul(const u32 (&a)[NL], const u32 (&b)[NL], u32 (&r)[NL]) {
+  u64 col[2 * NL];
+#pragma unroll
+  for (int i = 0; i < 2 * NL; i++) col[i] = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+#pragma unroll
+    for (int j = 0; j < NL; j++) col[i + j] += (u64)a[i] * (u64)b[j];
+  }
+  mont_n_reduce(col, r);
+}
+P2E_HD void mont_n_sqr(const u32 (&a)[NL], u32 (&r)[NL]) {
+  u64 col[2 * NL];
+#pragma unroll
+  for (int i = 0; i < 2 * NL; i++) col[i] = 0;
+#pragma unroll
+  for (int i = 0; i < NL; i++) {
+    col[2 * i] += (u64)a[i] * (u64)a[i];
+#pragma unroll
+    for (int j = i + 1; j < NL; j++) col[i + j] += (u64)(2 * a[i]) * (u64)a[j];
+  }
+  mont_n_reduce(col, r);
+}
+
+// x^(n-2) mod n, canonical: 4-bit fixed window over the constant exponent, in the Montgomery domain
+P2E_HD void inv_n_mont(const u32 (&a)[NL], u32 (&r)[NL]) {
+  const u32 R2[NL] = {0x09f6ab4bu, 0x1f300d1eu, 0x1c0bd5d8u, 0x0c8ada8cu, 0x11cefa2bu,
+                      0x08b79a0fu, 0x1e697f5eu, 0x00e34de2u, 0x009c7356u};          // R^2 mod n
+  const u32 e[8] = {0xd036413fu, 0xbfd25e8cu, 0xaf48a03bu, 0xbaaedce6u,
+                    0xfffffffeu, 0xffffffffu, 0xffffffffu, 0xffffffffu};              // n - 2
+  u32 tab[16][NL];
+  mont_n_mul(a, R2, tab[1]);                         // a R
+  copy9(tab[1], tab[0]);                             // slot 0 unused (window 0 skips the multiply)
+  for (int i = 2; i < 16; i++) mont_n_mul(tab[i - 1], tab[1], tab[i]);
+  u32 acc[NL], t[NL];
+  copy9(tab[15], acc);                               // top nibble of n-2 is 0xf
+  for (int nib = 62; nib >= 0; nib--) {
+    for (int k = 0; k < 4; k++) {
+      mont_n_sqr(acc, t);
+      copy9(t, acc);
+    }
+    u32 w = (e[nib >> 3] >> ((nib & 7) * 4)) & 15u;
+    if (w) {
+      mont_n_mul(acc, tab[w], t);
+      copy9(t, acc);
+    }
+  }
+  u32 one[NL];
+  set_zero9(one);
+  one[0] = 1;
+  mont_n_mul(acc, one, t);                           // leave the Montgomery domain: < 2^257
+  canon9<ModN>(t);
+  canon9<ModN>(t);
+  copy9(t, r);
+}
+
 template <class MOD>
 P2E_HD void inv_mod(const u32 (&a)[NL], u32 (&r)[NL]) {
-  if (MOD::ID == 0) inv_p(a, r); else inv_n(a, r);
+  if (MOD::ID == 0) inv_p(a, r); else inv_n_mont(a, r);
 }
 
 // ------------------------------------------------------------------------------------------
