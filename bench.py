@@ -301,7 +301,8 @@ class Bench:
             step()
         self.barrier()
         sampler = None
-        if sample_clocks:
+        if sample_clocks and self.rank == 0:
+            # rank 0 only: eight concurrent nvidia-smi pollers perturb every rank's launches
             sampler = ClockSampler(self.local_rank)
             sampler.start()
         streams = s.get("streams") or []
@@ -435,6 +436,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # stdout must carry exactly ONE JSON line: libraries (e.g. NCCL's version banner) write to fd 1,
+    # so everything until the final print goes to stderr at the file-descriptor level
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     b = Bench(args)
     wl = args.workload
     main_res = b.measure(wl, args.steps, args.warmup, e2e_steps=max(2, min(args.steps, 5)), sample_clocks=True)
@@ -492,7 +498,10 @@ def main():
                                         "sample": cb["sample"]}
             except Exception as e:      # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "error": str(e)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     b.eng.close()
     if b.dist is not None:
         b.dist.destroy_process_group()
