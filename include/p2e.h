@@ -156,6 +156,39 @@ int p2e_tape_witness_dev(int tape, size_t n, const uint64_t* const* inputs, size
                          uint64_t* out, size_t out_stride, uint32_t* err, void* stream);
 int p2e_tape_witness(int tape, size_t n, const uint64_t* const* inputs, uint64_t* out, uint32_t* err);
 
+/* Builder: the reference's CircuitBuilder extension traits (gadgets/nonnative.rs:53-164,
+ * gadgets/curve.rs:34-94, curve_fixed_base.rs, curve_msm.rs, glv.rs) as a handle-based C-API, so a
+ * host shim can mirror ANY composition of these gadgets and run its witness as a tape.  Value / point
+ * handles are small non-negative ints; every call returns a handle (or 0) on success and a negative
+ * number on error.  p2e_builder_finish() registers the tape and returns its id (>= 16) for
+ * p2e_tape_*().  Inputs are [9][n] wire matrices in p2e_builder_input() order.
+ * Limits of this version: nonnative ops may not consume coordinates of curve-op results (only
+ * connect_nonnative may); one fixed_base_curve_mul and one curve_msm / glv_mul per tape; the
+ * BoolTarget of curve_conditional_add must be an input; msm operands may not be curve-op results of
+ * the fixed-base or join chains. */
+int p2e_builder_new(void);
+int p2e_builder_free(int builder);
+int p2e_builder_input(int builder);                                            /* add_virtual_nonnative_target */
+int p2e_builder_constant_nonnative(int builder, const uint32_t* limbs9);       /* nonnative.rs:205-208 */
+int p2e_builder_add_nonnative(int builder, int modulus, int x, int y);         /* nonnative.rs:245-276 */
+int p2e_builder_sub_nonnative(int builder, int modulus, int x, int y);         /* nonnative.rs:356-388 */
+int p2e_builder_mul_nonnative(int builder, int modulus, int x, int y);         /* nonnative.rs:390-464 */
+int p2e_builder_inv_nonnative(int builder, int modulus, int x);                /* nonnative.rs:502-536 */
+int p2e_builder_neg_nonnative(int builder, int modulus, int x);                /* nonnative.rs:491-500 */
+int p2e_builder_connect_nonnative(int builder, int x, int y);                  /* nonnative.rs:215-221 */
+int p2e_builder_affine_point(int builder, int x, int y);                       /* AffinePointTarget { x, y } */
+int p2e_builder_constant_affine_point(int builder, const uint32_t* x9, const uint32_t* y9); /* curve.rs:99-105 */
+int p2e_builder_point_x(int builder, int point);
+int p2e_builder_point_y(int builder, int point);
+int p2e_builder_curve_assert_valid(int builder, int point);                    /* curve.rs:123-135 */
+int p2e_builder_curve_add(int builder, int p1, int p2);                        /* curve.rs:202-223 */
+int p2e_builder_curve_double(int builder, int p);                              /* curve.rs:160-185 */
+int p2e_builder_curve_conditional_add(int builder, int p1, int p2, int bool_input); /* curve.rs:225-243 */
+int p2e_builder_fixed_base_curve_mul(int builder, int scalar);                 /* curve_fixed_base.rs:18-66 (base = G) */
+int p2e_builder_curve_msm(int builder, int p, int q, int n, int m);            /* curve_msm.rs:21-79 */
+int p2e_builder_glv_mul(int builder, int p, int k);                            /* glv.rs:87-104 */
+int p2e_builder_finish(int builder);
+
 /* Compact host format (cuts the PCIe bytes of the host-pointer path by ~28 %): slots that always fit
  * 32 bits (limbs of ADD / ADDMANY / SUB / INV / GLV tuples, overflow flags, r and q of MUL tuples) are
  * delivered as uint32_t in `narrow` [narrow_slots][n]; check_sum and carry slots (full field elements /

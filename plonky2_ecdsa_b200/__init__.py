@@ -4,7 +4,7 @@ Weobe/plonky2-ecdsa (29-bit-limb nonnative secp256k1 generators, MulNonnative/Ch
 The compute path is CUDA only (plonky2_ecdsa_b200/libp2e.so, built by plonky2_ecdsa_b200.build).
 """
 from .engine import (  # noqa: F401
-    Engine, P2EError, load_library, LIB_PATH, SIGNATURES,
+    Engine, CircuitBuilder, P2EError, load_library, LIB_PATH, SIGNATURES,
     SECP256K1_BASE, SECP256K1_SCALAR,
     ERR_U32, ERR_LIMB_RANGE, ERR_NONCANONICAL, ERR_INVERSE_ZERO, ERR_CARRY_RANGE,
     ERR_DIV_ZERO, ERR_LIMBS_OVERFLOW, ERR_CONNECT, ERR_INTERNAL,

@@ -12,6 +12,7 @@
 //                      then every generator of that curve op with the cores of p2e_field.cuh
 //   K5 k_chain_checks  per signature: the gadget's connect_* constraints -> ERR_CONNECT
 // Signatures are the fastest-varying index everywhere (coalesced wire-major accesses).
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -45,7 +46,7 @@ struct DevTape {
 struct ChainArgs {
   DevTape t;
   size_t n;                 // signatures in this chunk
-  const u64* in[8];         // input nonnative values, [9][is] each
+  const u64* in[MAX_TAPE_INPUTS];   // input nonnative values, [9][is] each
   size_t is;
   u64* out;                 // [n_slots][os]
   size_t os;
@@ -258,6 +259,18 @@ __device__ __forceinline__ int pt_index(const ChainArgs& A, int32_t pid) {
   return pid < PID_INPUT_BASE ? pid : A.t.n_ptops + (pid - PID_INPUT_BASE);
 }
 
+// An explicit reference to the result of a curve_conditional_add means the SELECTED point
+// (b ? sum : p1, curve.rs:235-240): follow the recorded operands while the flag is clear.
+__device__ __forceinline__ int32_t resolve_pid(const ChainArgs& A, int32_t pid, size_t i) {
+  while (pid >= 0 && pid < PID_INPUT_BASE) {
+    const uint8_t ty = A.t.ptops[pid].type;
+    if (ty == PT_ADD || ty == PT_DBL) break;
+    if (A.FLG[(size_t)pid * A.cap + i]) break;
+    pid = A.SRC1[(size_t)pid * A.cap + i];
+  }
+  return pid;
+}
+
 template <class T>
 __device__ __forceinline__ void ld9(const u32* __restrict__ base, int idx, size_t cap, size_t i, T (&v)[NL]) {
 #pragma unroll
@@ -448,8 +461,9 @@ __global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A, int chain0) {
   int32_t cur = -1;
   for (int k = k_begin; k < k_end; k++) {
     const PtOp op = A.t.ptops[k];
-    int32_t p1 = (op.flags & PF_P1_CUR) ? cur : op.p1;
-    int32_t p2 = (op.flags & PF_P2_CUR) ? cur : op.p2;
+    if (((op.flags >> PF_CHAIN_SHIFT) & 3) != chain) continue;      // chains may interleave in op order
+    int32_t p1 = (op.flags & PF_P1_CUR) ? cur : resolve_pid(A, op.p1, i);
+    int32_t p2 = (op.flags & PF_P2_CUR) ? cur : resolve_pid(A, op.p2, i);
     u32 flag = 1;
     if (op.type == PT_CADD_FIXED) {
       u32 d = digit_at(fs, NL, 4 * op.aux, 4);
@@ -593,8 +607,9 @@ __global__ void __launch_bounds__(64) k_chain_replay_duo(ChainArgs A, int chain0
   JacL R;
   for (int k = k_begin; k < k_end; k++) {
     const PtOp op = A.t.ptops[k];
-    int32_t p1 = (op.flags & PF_P1_CUR) ? cur : op.p1;
-    int32_t p2 = (op.flags & PF_P2_CUR) ? cur : op.p2;
+    if (((op.flags >> PF_CHAIN_SHIFT) & 3) != chain) continue;      // chains may interleave in op order
+    int32_t p1 = (op.flags & PF_P1_CUR) ? cur : resolve_pid(A, op.p1, i);
+    int32_t p2 = (op.flags & PF_P2_CUR) ? cur : resolve_pid(A, op.p2, i);
     u32 flag = 1;
     if (op.type == PT_CADD_FIXED) {
       u32 d = digit_at(fs, NL, 4 * op.aux, 4);
@@ -756,8 +771,9 @@ __global__ void __launch_bounds__(128) k_chain_replay_coop(ChainArgs A, int chai
   int32_t cur = -1, resident = -2;
   for (int k = k_begin; k < k_end; k++) {
     const PtOp op = A.t.ptops[k];
-    int32_t p1 = (op.flags & PF_P1_CUR) ? cur : op.p1;
-    int32_t p2 = (op.flags & PF_P2_CUR) ? cur : op.p2;
+    if (((op.flags >> PF_CHAIN_SHIFT) & 3) != chain) continue;      // chains may interleave in op order
+    int32_t p1 = (op.flags & PF_P1_CUR) ? cur : resolve_pid(A, op.p1, i);
+    int32_t p2 = (op.flags & PF_P2_CUR) ? cur : resolve_pid(A, op.p2, i);
     u32 flag = 1;
     if (op.type == PT_CADD_FIXED) {
       u32 d = digit_at(fs, NL, 4 * op.aux, 4);
@@ -1046,7 +1062,7 @@ struct TapeOnDevice {
   size_t n_slots = 0;
 };
 
-static TapeOnDevice g_dev_tapes[N_TAPES];
+static std::map<int, TapeOnDevice> g_dev_tapes;
 static std::mutex g_mu;
 
 template <class T>
@@ -1140,6 +1156,12 @@ static int get_arena(cudaStream_t st, size_t bytes, Arena** out) {
 }
 
 void chain_release_device_tapes() {
+  for (auto& kv : g_dev_tapes) {
+    TapeOnDevice& o = kv.second;
+    if (o.ready && o.blob) cudaFree(o.blob);
+    o.ready = false;
+    o.blob = nullptr;
+  }
   for (auto& a : g_arenas) {
     if (a.ptr) cudaFree(a.ptr);
     if (a.hi) cudaStreamDestroy(a.hi);
@@ -1148,11 +1170,6 @@ void chain_release_device_tapes() {
     if (a.ev_mid) cudaEventDestroy(a.ev_mid);
     if (a.ev_out) cudaEventDestroy(a.ev_out);
     a = Arena();
-  }
-  for (auto& o : g_dev_tapes) {
-    if (o.ready && o.blob) cudaFree(o.blob);
-    o.ready = false;
-    o.blob = nullptr;
   }
 }
 
@@ -1199,6 +1216,7 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
   if (rc) return rc;
   if (n == 0) return 0;
   if (is < n || os < n) return set_error_msg("stride < n");
+  if (n_in > MAX_TAPE_INPUTS) return set_error_msg("tape has more than 16 inputs");
   std::lock_guard<std::mutex> lock(g_mu);
   TapeOnDevice& o = g_dev_tapes[which];
   if ((rc = upload_tape(t, o))) return rc;
@@ -1238,7 +1256,7 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
   for (size_t c0 = 0; c0 < n; c0 += cap) {
     size_t cn = (n - c0 < cap) ? n - c0 : cap;
     A.n = cn;
-    for (int k = 0; k < 8; k++) A.in[k] = (k < n_in) ? ins[k] + c0 : nullptr;
+    for (int k = 0; k < MAX_TAPE_INPUTS; k++) A.in[k] = (k < n_in) ? ins[k] + c0 : nullptr;
     A.out = out + c0;
     A.err = err + c0;
     unsigned g32 = (unsigned)((cn + 31) / 32), g128 = (unsigned)((cn + 127) / 128);
@@ -1317,7 +1335,7 @@ static int run_tape_host(const Tape& t, size_t n, const uint64_t* const* ins, in
   if ((rc = get_scratch(0, (size_t)n_in * 9 * n * 8, &din))) return rc;
   if ((rc = get_scratch(1, (size_t)t.n_slots * n * 8, &dout))) return rc;
   if ((rc = get_scratch(2, n * 4, &derr))) return rc;
-  const uint64_t* dptr[8];
+  const uint64_t* dptr[MAX_TAPE_INPUTS];
   for (int k = 0; k < n_in; k++) {
     dptr[k] = (const uint64_t*)din + (size_t)k * 9 * n;
     P2E_CUDA(cudaMemcpyAsync((uint64_t*)din + (size_t)k * 9 * n, ins[k], 9 * n * 8, cudaMemcpyHostToDevice, st));
@@ -1355,7 +1373,7 @@ int p2e_last_kernel_times(float* ms, int cap) {
 }
 
 static int bad_tape(int tape) {
-  if (tape < 0 || tape >= N_TAPES) return set_error_msg("unknown tape id");
+  if (!tape_exists(tape)) return set_error_msg("unknown tape id");
   return 0;
 }
 
@@ -1408,9 +1426,9 @@ int p2e_tape_witness_compact(int tape, size_t n, const uint64_t* const* inputs, 
   if (n == 0) return 0;
   const Tape& t = get_tape(tape);
   const int n_in = (int)t.n_inputs;
-  static std::vector<uint32_t> maps[N_TAPES];
-  static void* dmaps[N_TAPES] = {nullptr};
-  static int dmap_device[N_TAPES];
+  static std::map<int, std::vector<uint32_t>> maps;
+  static std::map<int, void*> dmaps;
+  static std::map<int, int> dmap_device;
   uint32_t nn = 0, nw = 0;
   if (maps[tape].empty()) maps[tape].resize(t.n_slots);
   p2e_tape_compact_layout(tape, maps[tape].data(), &nn, &nw);
@@ -1428,7 +1446,7 @@ int p2e_tape_witness_compact(int tape, size_t n, const uint64_t* const* inputs, 
   if ((rc = get_scratch(3, ((nbytes + 15) / 16) * 16 + wbytes, &dpack))) return rc;
   u32* dn = (u32*)dpack;
   u64* dw = (u64*)((char*)dpack + ((nbytes + 15) / 16) * 16);
-  const uint64_t* dptr[8];
+  const uint64_t* dptr[MAX_TAPE_INPUTS];
   for (int k = 0; k < n_in; k++) {
     dptr[k] = (const uint64_t*)din + (size_t)k * 9 * n;
     P2E_CUDA(cudaMemcpyAsync((uint64_t*)din + (size_t)k * 9 * n, inputs[k], 9 * n * 8, cudaMemcpyHostToDevice, st));

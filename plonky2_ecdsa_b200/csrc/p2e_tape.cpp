@@ -7,6 +7,11 @@
 
 #include <string.h>
 
+#include <mutex>
+#include <string>
+
+#include "../../include/p2e.h"
+#include "p2e_common.h"
 #include "p2e_field.cuh"
 
 namespace p2e {
@@ -169,6 +174,13 @@ class Builder {
   Tape t;
   APoint rando, neg_rando;
   int cur_chain = 0;
+  // dynamic (C-API) use: value / point handles
+  std::vector<NNT> vals;
+  std::vector<uint8_t> val_late;     // produced by a curve op: only connect_nonnative may consume it
+  std::vector<PtT> pts;
+  std::vector<int8_t> pt_chain;      // chain of the producing op, -1 for input / constant points
+  int n_fixed = 0, n_msm = 0;
+  std::string error;
 
   Builder() {
     u64 k[4];
@@ -459,8 +471,22 @@ class Builder {
 
 }  // namespace
 
+static std::vector<Tape*>& user_tapes() {
+  static std::vector<Tape*> v;
+  return v;
+}
+static std::mutex g_tape_mu;
+
+bool tape_exists(int id) {
+  if (id >= 0 && id < N_TAPES) return true;
+  std::lock_guard<std::mutex> lock(g_tape_mu);
+  return id >= TAPE_USER_BASE && (size_t)(id - TAPE_USER_BASE) < user_tapes().size();
+}
+
 const Tape& get_tape(int id) {
   static Tape* tapes[N_TAPES] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::lock_guard<std::mutex> lock(g_tape_mu);
+  if (id >= TAPE_USER_BASE && (size_t)(id - TAPE_USER_BASE) < user_tapes().size()) return *user_tapes()[id - TAPE_USER_BASE];
   if (id < 0 || id >= N_TAPES) id = 0;
   if (!tapes[id]) {
     Builder b;
@@ -505,4 +531,217 @@ const Tape& get_tape(int id) {
   return *tapes[id];
 }
 
+// ------------------------------------------------------------------ builder C-API (include/p2e.h)
+static std::vector<Builder*>& builders() {
+  static std::vector<Builder*> v;
+  return v;
+}
+static Builder* get_builder(int h) {
+  if (h < 0 || (size_t)h >= builders().size() || !builders()[h]) {
+    set_error_msg("p2e_builder: bad builder handle");
+    return nullptr;
+  }
+  return builders()[h];
+}
+static int berr(Builder* b, const char* msg) {
+  b->error = msg;
+  set_error_msg(msg);
+  return -1;
+}
+static int push_val(Builder* b, const NNT& v, bool late) {
+  b->vals.push_back(v);
+  b->val_late.push_back(late ? 1 : 0);
+  return (int)b->vals.size() - 1;
+}
+static int push_pt(Builder* b, const PtT& p, int chain) {
+  b->pts.push_back(p);
+  b->pt_chain.push_back((int8_t)chain);
+  return (int)b->pts.size() - 1;
+}
+static bool val_ok(Builder* b, int v, bool allow_late) {
+  return v >= 0 && (size_t)v < b->vals.size() && (allow_late || !b->val_late[v]);
+}
+static bool pt_ok(Builder* b, int p) { return p >= 0 && (size_t)p < b->pts.size(); }
+static bool mod_ok(int m) { return m == 0 || m == 1; }
+static Fe fe_from_limbs(const uint32_t* l) {
+  Fe r;
+  for (int i = 0; i < NL; i++) r.l[i] = l[i] & LMASK;
+  return r;
+}
+// chain of a new curve op: chain 1 unless an operand was produced by the fixed-base chain (0) or the join chain (2)
+static int op_chain(Builder* b, int p1, int p2) {
+  int c = 1;
+  for (int p : {p1, p2})
+    if (p >= 0 && (b->pt_chain[p] == 0 || b->pt_chain[p] == 2)) c = 2;
+  return c;
+}
+
 }  // namespace p2e
+
+using namespace p2e;
+#define P2E_B(h)                      \
+  std::lock_guard<std::mutex> lock__(g_builder_mu); \
+  Builder* b = get_builder(h);        \
+  if (!b) return -1
+static std::mutex g_builder_mu;
+
+extern "C" {
+
+int p2e_builder_new(void) {
+  std::lock_guard<std::mutex> lock(g_builder_mu);
+  Builder* b = new Builder();
+  b->cur_chain = 1;
+  builders().push_back(b);
+  return (int)builders().size() - 1;
+}
+
+int p2e_builder_free(int h) {
+  P2E_B(h);
+  delete b;
+  builders()[h] = nullptr;
+  return 0;
+}
+
+int p2e_builder_input(int h) {
+  P2E_B(h);
+  if (b->t.n_inputs >= (uint32_t)MAX_TAPE_INPUTS) return berr(b, "p2e_builder: at most 16 inputs per tape");
+  return push_val(b, b->input(b->t.n_inputs), false);
+}
+
+int p2e_builder_constant_nonnative(int h, const uint32_t* limbs9) {
+  P2E_B(h);
+  return push_val(b, b->constant_nonnative(fe_from_limbs(limbs9)), false);
+}
+
+static int binop(int h, int kind, int modulus, int x, int y) {
+  P2E_B(h);
+  if (!mod_ok(modulus)) return berr(b, "p2e_builder: unknown modulus");
+  if (!val_ok(b, x, false) || !val_ok(b, y, false))
+    return berr(b, "p2e_builder: operand is not a value handle, or is a curve-op output (only connect_nonnative may consume those)");
+  NNT r = kind == 0 ? b->add_nonnative(b->vals[x], b->vals[y], modulus)
+        : kind == 1 ? b->sub_nonnative(b->vals[x], b->vals[y], modulus)
+                    : b->mul_nonnative(b->vals[x], b->vals[y], modulus);
+  return push_val(b, r, false);
+}
+int p2e_builder_add_nonnative(int h, int modulus, int x, int y) { return binop(h, 0, modulus, x, y); }
+int p2e_builder_sub_nonnative(int h, int modulus, int x, int y) { return binop(h, 1, modulus, x, y); }
+int p2e_builder_mul_nonnative(int h, int modulus, int x, int y) { return binop(h, 2, modulus, x, y); }
+
+int p2e_builder_inv_nonnative(int h, int modulus, int x) {
+  P2E_B(h);
+  if (!mod_ok(modulus) || !val_ok(b, x, false)) return berr(b, "p2e_builder: bad operand for inv_nonnative");
+  if (b->vals[x].r.nl != NL) return berr(b, "p2e_builder: inv_nonnative needs a 9-limb operand");
+  return push_val(b, b->inv_nonnative(b->vals[x], modulus), false);
+}
+
+int p2e_builder_neg_nonnative(int h, int modulus, int x) {
+  P2E_B(h);
+  if (!mod_ok(modulus) || !val_ok(b, x, false)) return berr(b, "p2e_builder: bad operand for neg_nonnative");
+  return push_val(b, b->neg_nonnative(b->vals[x], modulus), false);
+}
+
+int p2e_builder_connect_nonnative(int h, int x, int y) {
+  P2E_B(h);
+  if (!val_ok(b, x, true) || !val_ok(b, y, true)) return berr(b, "p2e_builder: bad operand for connect_nonnative");
+  b->connect_nonnative(b->vals[x], b->vals[y]);
+  return 0;
+}
+
+int p2e_builder_affine_point(int h, int x, int y) {
+  P2E_B(h);
+  if (!val_ok(b, x, false) || !val_ok(b, y, false)) return berr(b, "p2e_builder: bad coordinates for affine_point");
+  return push_pt(b, b->input_point(b->vals[x], b->vals[y]), -1);
+}
+
+int p2e_builder_constant_affine_point(int h, const uint32_t* x9, const uint32_t* y9) {
+  P2E_B(h);
+  APoint a;
+  a.x = fe_from_limbs(x9);
+  a.y = fe_from_limbs(y9);
+  a.inf = false;
+  PtT p;
+  p.pid = b->const_point(a);
+  p.x = b->constant_nonnative(a.x);
+  p.y = b->constant_nonnative(a.y);
+  return push_pt(b, p, -1);
+}
+
+int p2e_builder_point_x(int h, int p) {
+  P2E_B(h);
+  if (!pt_ok(b, p)) return berr(b, "p2e_builder: bad point handle");
+  return push_val(b, b->pts[p].x, b->pt_chain[p] >= 0);
+}
+int p2e_builder_point_y(int h, int p) {
+  P2E_B(h);
+  if (!pt_ok(b, p)) return berr(b, "p2e_builder: bad point handle");
+  return push_val(b, b->pts[p].y, b->pt_chain[p] >= 0);
+}
+
+int p2e_builder_curve_add(int h, int p1, int p2) {
+  P2E_B(h);
+  if (!pt_ok(b, p1) || !pt_ok(b, p2)) return berr(b, "p2e_builder: bad point handle");
+  b->cur_chain = op_chain(b, p1, p2);
+  return push_pt(b, b->curve_add(b->pts[p1].pid, b->pts[p2].pid, 0), b->cur_chain);
+}
+
+int p2e_builder_curve_double(int h, int p) {
+  P2E_B(h);
+  if (!pt_ok(b, p)) return berr(b, "p2e_builder: bad point handle");
+  b->cur_chain = op_chain(b, p, -1);
+  return push_pt(b, b->curve_double(b->pts[p].pid, 0), b->cur_chain);
+}
+
+int p2e_builder_curve_conditional_add(int h, int p1, int p2, int bool_input) {
+  P2E_B(h);
+  if (!pt_ok(b, p1) || !pt_ok(b, p2)) return berr(b, "p2e_builder: bad point handle");
+  if (!val_ok(b, bool_input, false) || b->vals[bool_input].r.space != SP_IN)
+    return berr(b, "p2e_builder: the BoolTarget of curve_conditional_add must be an input value (wire 0 holds 0 / 1)");
+  b->cur_chain = op_chain(b, p1, p2);
+  uint16_t aux = (uint16_t)(b->vals[bool_input].r.off / 9);
+  return push_pt(b, b->curve_conditional_add(PT_CADD_BOOL, 0, aux, b->pts[p1].pid, b->pts[p2].pid), b->cur_chain);
+}
+
+int p2e_builder_fixed_base_curve_mul(int h, int scalar) {
+  P2E_B(h);
+  if (!val_ok(b, scalar, false)) return berr(b, "p2e_builder: bad scalar handle");
+  if (b->n_fixed++) return berr(b, "p2e_builder: only one fixed_base_curve_mul_circuit per tape in this version");
+  PtT r = b->fixed_base_curve_mul(b->vals[scalar]);     // sets cur_chain = 0
+  return push_pt(b, r, 0);
+}
+
+int p2e_builder_curve_msm(int h, int p, int q, int n, int m) {
+  P2E_B(h);
+  if (!pt_ok(b, p) || !pt_ok(b, q) || !val_ok(b, n, false) || !val_ok(b, m, false)) return berr(b, "p2e_builder: bad handle for curve_msm");
+  if (b->pt_chain[p] == 0 || b->pt_chain[p] == 2 || b->pt_chain[q] == 0 || b->pt_chain[q] == 2)
+    return berr(b, "p2e_builder: curve_msm operands may not come from the fixed-base / join chains in this version");
+  if (b->vals[n].r.nl != b->vals[m].r.nl) return berr(b, "p2e_builder: curve_msm scalars must have the same limb count");
+  if (b->n_msm++) return berr(b, "p2e_builder: only one curve_msm_circuit / glv_mul per tape in this version");
+  PtT r = b->curve_msm(b->pts[p], b->pts[q], b->vals[n], b->vals[m]);    // sets cur_chain = 1
+  return push_pt(b, r, 1);
+}
+
+int p2e_builder_glv_mul(int h, int p, int k) {
+  P2E_B(h);
+  if (!pt_ok(b, p) || !val_ok(b, k, false)) return berr(b, "p2e_builder: bad handle for glv_mul");
+  if (b->pt_chain[p] >= 0) return berr(b, "p2e_builder: glv_mul needs a point made of values (affine_point / constant)");
+  if (b->n_msm++) return berr(b, "p2e_builder: only one curve_msm_circuit / glv_mul per tape in this version");
+  PtT r = b->glv_mul(b->pts[p].x, b->pts[p].y, b->vals[k]);
+  return push_pt(b, r, 1);
+}
+
+int p2e_builder_curve_assert_valid(int h, int p) {
+  P2E_B(h);
+  if (!pt_ok(b, p) || b->pt_chain[p] >= 0) return berr(b, "p2e_builder: curve_assert_valid needs a point made of values");
+  b->curve_assert_valid(b->pts[p].x, b->pts[p].y);
+  return 0;
+}
+
+int p2e_builder_finish(int h) {
+  P2E_B(h);
+  if (!b->error.empty()) return berr(b, "p2e_builder: an earlier builder call failed");
+  std::lock_guard<std::mutex> lock(g_tape_mu);
+  user_tapes().push_back(new Tape(b->t));
+  return TAPE_USER_BASE + (int)user_tapes().size() - 1;
+}
+
+}  // extern "C"

@@ -87,7 +87,10 @@ enum TapeId : int {
   TAPE_CURVE_MSM = 6,    // curve_msm_circuit(p, q, n, m) (gadgets/curve_msm.rs:21-79); inputs p.x, p.y, q.x, q.y, n, m
   N_TAPES = 7
 };
+constexpr int MAX_TAPE_INPUTS = 16;  // input wire matrices per tape
+constexpr int TAPE_USER_BASE = 16;   // ids of tapes made with the builder C-API (p2e_builder_finish)
 const Tape& get_tape(int id);
+bool tape_exists(int id);
 inline const Tape& ecdsa_tape() { return get_tape(TAPE_ECDSA); }
 inline const Tape& glv_mul_tape() { return get_tape(TAPE_GLV_MUL); }
 

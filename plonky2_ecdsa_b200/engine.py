@@ -85,6 +85,28 @@ SIGNATURES = {
     "p2e_tape_witness": (_int, [_int, _sz, _vp, _vp, _vp]),
     "p2e_tape_compact_layout": (_sz, [_int, _vp, _vp, _vp]),
     "p2e_tape_witness_compact": (_int, [_int, _sz, _vp, _vp, _vp, _vp]),
+    "p2e_builder_new": (_int, []),
+    "p2e_builder_free": (_int, [_int]),
+    "p2e_builder_input": (_int, [_int]),
+    "p2e_builder_constant_nonnative": (_int, [_int, _vp]),
+    "p2e_builder_add_nonnative": (_int, [_int, _int, _int, _int]),
+    "p2e_builder_sub_nonnative": (_int, [_int, _int, _int, _int]),
+    "p2e_builder_mul_nonnative": (_int, [_int, _int, _int, _int]),
+    "p2e_builder_inv_nonnative": (_int, [_int, _int, _int]),
+    "p2e_builder_neg_nonnative": (_int, [_int, _int, _int]),
+    "p2e_builder_connect_nonnative": (_int, [_int, _int, _int]),
+    "p2e_builder_affine_point": (_int, [_int, _int, _int]),
+    "p2e_builder_constant_affine_point": (_int, [_int, _vp, _vp]),
+    "p2e_builder_point_x": (_int, [_int, _int]),
+    "p2e_builder_point_y": (_int, [_int, _int]),
+    "p2e_builder_curve_assert_valid": (_int, [_int, _int]),
+    "p2e_builder_curve_add": (_int, [_int, _int, _int]),
+    "p2e_builder_curve_double": (_int, [_int, _int]),
+    "p2e_builder_curve_conditional_add": (_int, [_int, _int, _int, _int]),
+    "p2e_builder_fixed_base_curve_mul": (_int, [_int, _int]),
+    "p2e_builder_curve_msm": (_int, [_int, _int, _int, _int, _int]),
+    "p2e_builder_glv_mul": (_int, [_int, _int, _int]),
+    "p2e_builder_finish": (_int, [_int]),
     "p2e_ecdsa_tape_slots": (_sz, []),
     "p2e_ecdsa_tape_layout": (_sz, [_vp, _vp]),
     "p2e_ecdsa_witness_dev": (_int, [_sz, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),
@@ -133,6 +155,95 @@ def _host_u64(a, rows=None) -> np.ndarray:
     if rows is not None and a.shape[0] != rows:
         raise ValueError(f"expected {rows} rows, got {a.shape[0]}")
     return a
+
+
+class CircuitBuilder:
+    """Host mirror of the reference's CircuitBuilder extension traits for the nonnative / curve gadgets
+    (CircuitBuilderNonNative gadgets/nonnative.rs:53-164, CircuitBuilderCurve gadgets/curve.rs:34-94,
+    fixed_base_curve_mul_circuit, curve_msm_circuit, CircuitBuilderGlv): records the gadget calls through
+    the p2e_builder_* C-API and `build()` returns a tape id for Engine.tape_witness().  Works without a GPU
+    (building a tape is host work); running it does not."""
+
+    def __init__(self, lib=None):
+        self.lib = lib if lib is not None else load_library()
+        self.h = self.lib.p2e_builder_new()
+        if self.h < 0:
+            raise P2EError("p2e_builder_new failed")
+
+    def _ok(self, rc):
+        if rc < 0:
+            raise P2EError((self.lib.p2e_last_error() or b"").decode())
+        return rc
+
+    @staticmethod
+    def _limbs(v):
+        return np.array([(int(v) >> (29 * i)) & 0x1FFFFFFF for i in range(9)], dtype=np.uint32)
+
+    def add_virtual_nonnative_target(self):
+        return self._ok(self.lib.p2e_builder_input(self.h))
+
+    def constant_nonnative(self, value: int):
+        l = self._limbs(value)
+        return self._ok(self.lib.p2e_builder_constant_nonnative(self.h, l.ctypes.data))
+
+    def add_nonnative(self, modulus, a, b):
+        return self._ok(self.lib.p2e_builder_add_nonnative(self.h, modulus, a, b))
+
+    def sub_nonnative(self, modulus, a, b):
+        return self._ok(self.lib.p2e_builder_sub_nonnative(self.h, modulus, a, b))
+
+    def mul_nonnative(self, modulus, a, b):
+        return self._ok(self.lib.p2e_builder_mul_nonnative(self.h, modulus, a, b))
+
+    def inv_nonnative(self, modulus, x):
+        return self._ok(self.lib.p2e_builder_inv_nonnative(self.h, modulus, x))
+
+    def neg_nonnative(self, modulus, x):
+        return self._ok(self.lib.p2e_builder_neg_nonnative(self.h, modulus, x))
+
+    def connect_nonnative(self, a, b):
+        self._ok(self.lib.p2e_builder_connect_nonnative(self.h, a, b))
+
+    def affine_point(self, x, y):
+        return self._ok(self.lib.p2e_builder_affine_point(self.h, x, y))
+
+    def constant_affine_point(self, pt):
+        x, y = self._limbs(pt[0]), self._limbs(pt[1])
+        return self._ok(self.lib.p2e_builder_constant_affine_point(self.h, x.ctypes.data, y.ctypes.data))
+
+    def point_x(self, p):
+        return self._ok(self.lib.p2e_builder_point_x(self.h, p))
+
+    def point_y(self, p):
+        return self._ok(self.lib.p2e_builder_point_y(self.h, p))
+
+    def curve_assert_valid(self, p):
+        self._ok(self.lib.p2e_builder_curve_assert_valid(self.h, p))
+
+    def curve_add(self, p1, p2):
+        return self._ok(self.lib.p2e_builder_curve_add(self.h, p1, p2))
+
+    def curve_double(self, p):
+        return self._ok(self.lib.p2e_builder_curve_double(self.h, p))
+
+    def curve_conditional_add(self, p1, p2, b):
+        return self._ok(self.lib.p2e_builder_curve_conditional_add(self.h, p1, p2, b))
+
+    def fixed_base_curve_mul_circuit(self, scalar):
+        return self._ok(self.lib.p2e_builder_fixed_base_curve_mul(self.h, scalar))
+
+    def curve_msm_circuit(self, p, q, n, m):
+        return self._ok(self.lib.p2e_builder_curve_msm(self.h, p, q, n, m))
+
+    def glv_mul(self, p, k):
+        return self._ok(self.lib.p2e_builder_glv_mul(self.h, p, k))
+
+    def build(self) -> int:
+        """Registers the recorded circuit as a tape; returns its id."""
+        tid = self._ok(self.lib.p2e_builder_finish(self.h))
+        self.lib.p2e_builder_free(self.h)
+        self.h = -1
+        return tid
 
 
 class Engine:
