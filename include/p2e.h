@@ -175,6 +175,9 @@ int p2e_builder_sub_nonnative(int builder, int modulus, int x, int y);         /
 int p2e_builder_mul_nonnative(int builder, int modulus, int x, int y);         /* nonnative.rs:390-464 */
 int p2e_builder_inv_nonnative(int builder, int modulus, int x);                /* nonnative.rs:502-536 */
 int p2e_builder_neg_nonnative(int builder, int modulus, int x);                /* nonnative.rs:491-500 */
+int p2e_builder_add_many_nonnative(int builder, int modulus, const int* xs, int k); /* nonnative.rs:310-353 */
+int p2e_builder_nonnative_conditional_neg(int builder, int modulus, int x, int bool_input); /* nonnative.rs:584-596 */
+int p2e_builder_if_nonnative(int builder, int modulus, int bool_input, int x, int y);       /* nonnative.rs:297-308 */
 int p2e_builder_connect_nonnative(int builder, int x, int y);                  /* nonnative.rs:215-221 */
 int p2e_builder_affine_point(int builder, int x, int y);                       /* AffinePointTarget { x, y } */
 int p2e_builder_constant_affine_point(int builder, const uint32_t* x9, const uint32_t* y9); /* curve.rs:99-105 */

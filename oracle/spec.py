@@ -529,6 +529,11 @@ class WitnessBuilder:
     def mul_nonnative_by_bool(self, a, b):
         return NN([l * b for l in a.limbs])                 # nonnative.rs:278-295, biguint.rs:360-374
 
+    def if_nonnative(self, b, x, y, m):
+        t = self.mul_nonnative_by_bool(x, b)                # nonnative.rs:297-308
+        f = self.mul_nonnative_by_bool(y, 1 - b)
+        return self.add_nonnative(t, f, m)
+
     def nonnative_conditional_neg(self, x, b, m):
         neg = self.neg_nonnative(x, m)                      # nonnative.rs:584-596
         t = self.mul_nonnative_by_bool(neg, b)

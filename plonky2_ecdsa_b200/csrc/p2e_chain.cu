@@ -34,6 +34,7 @@ struct DevTape {
   const PtOp* ptops;
   const Check* checks;
   const InputPoint* in_points;
+  const Ref* extra_refs;
   const u32* const_limbs;
   const u32* const_points;
   int n_prep, n_ptops, n_checks, n_in_points;
@@ -213,6 +214,27 @@ __device__ u32 prep_exec(const ChainArgs& A, const PrepOp& op, size_t i) {
   return e;
 }
 
+// NonNativeMultipleAddsGenerator (nonnative.rs:696-728) over op.pad summands
+template <class MOD>
+__device__ u32 prep_add_many(const ChainArgs& A, const PrepOp& op, size_t i) {
+  u32 acc[NL];
+  set_zero9(acc);
+  u32 ov = 0, e = 0;
+  for (int t = 0; t < op.pad; t++) {
+    u64 w[NL];
+    load_ref(A, A.t.extra_refs[op.a.boff + t], i, w);
+    u32 v[NL], sum[NL];
+    e |= load_canon<MOD>(w, v);
+    add9(acc, v, sum);
+    if (geq_mod<MOD>(sum)) { sub_mod9<MOD>(sum, acc); ov++; }
+    else copy9(sum, acc);
+  }
+  if (e) { set_zero9(acc); ov = 0; }
+  st9(A, op.slot, i, acc);
+  st1(A, op.slot + 9, i, ov);
+  return e;
+}
+
 __global__ void __launch_bounds__(32) k_prep(ChainArgs A) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
@@ -239,6 +261,8 @@ __global__ void __launch_bounds__(32) k_prep(ChainArgs A) {
       st1(A, op.slot + 10, i, n1);
       st1(A, op.slot + 11, i, n2);
       err |= e;
+    } else if (op.opcode == OP_ADDMANY) {
+      err |= (op.mod == 0) ? prep_add_many<ModP>(A, op, i) : prep_add_many<ModN>(A, op, i);
     } else if (op.mod == 0) {
       err |= prep_exec<ModP>(A, op, i);
     } else {
@@ -1077,6 +1101,7 @@ static int upload_tape(const Tape& t, TapeOnDevice& o) {
   size_t o_pt = reserve(t.ptops.size() * sizeof(PtOp));
   size_t o_chk = reserve(t.checks.size() * sizeof(Check));
   size_t o_in = reserve(t.in_points.size() * sizeof(InputPoint));
+  size_t o_xr = reserve((t.extra_refs.size() + 1) * sizeof(Ref));
   size_t o_cl = reserve((t.const_limbs.size() + 1) * sizeof(u32));
   size_t o_cp = reserve((t.const_points.size() + 1) * sizeof(u32));
   std::vector<unsigned char> host(off + 16, 0);
@@ -1084,6 +1109,7 @@ static int upload_tape(const Tape& t, TapeOnDevice& o) {
   memcpy(&host[o_pt], t.ptops.data(), t.ptops.size() * sizeof(PtOp));
   memcpy(&host[o_chk], t.checks.data(), t.checks.size() * sizeof(Check));
   memcpy(&host[o_in], t.in_points.data(), t.in_points.size() * sizeof(InputPoint));
+  memcpy(&host[o_xr], t.extra_refs.data(), t.extra_refs.size() * sizeof(Ref));
   memcpy(&host[o_cl], t.const_limbs.data(), t.const_limbs.size() * sizeof(u32));
   memcpy(&host[o_cp], t.const_points.data(), t.const_points.size() * sizeof(u32));
   void* blob = nullptr;
@@ -1094,6 +1120,7 @@ static int upload_tape(const Tape& t, TapeOnDevice& o) {
   o.d.ptops = (const PtOp*)(b + o_pt);
   o.d.checks = (const Check*)(b + o_chk);
   o.d.in_points = (const InputPoint*)(b + o_in);
+  o.d.extra_refs = (const Ref*)(b + o_xr);
   o.d.const_limbs = (const u32*)(b + o_cl);
   o.d.const_points = (const u32*)(b + o_cp);
   o.d.n_prep = (int)t.prep.size();

@@ -251,6 +251,25 @@ class Builder {
     prep2(OP_INV, mod, s, x, x);
     NNT r; r.r = mkref(SP_OUT, s + 9, 9); return r;                 // [div, inv]
   }
+  NNT add_many_nonnative(const std::vector<NNT>& xs, int mod) {     // nonnative.rs:310-353
+    if (xs.size() == 1) return xs[0];
+    uint32_t s = emit(G_ADDMANY, 10);
+    PrepOp p;
+    p.opcode = OP_ADDMANY;
+    p.mod = (uint8_t)mod;
+    p.pad = (uint16_t)xs.size();
+    p.slot = s;
+    p.a = mkref(SP_NONE, 0, 0);
+    p.a.boff = (uint32_t)t.extra_refs.size();
+    p.b = p.a;
+    for (const NNT& x : xs) t.extra_refs.push_back(x.r);
+    t.prep.push_back(p);
+    NNT r; r.r = mkref(SP_OUT, s, 9); return r;
+  }
+  NNT if_nonnative(const BoolT& b, const NNT& x, const NNT& y, int mod) {   // nonnative.rs:297-308
+    BoolT nb = b; nb.inv = !b.inv;
+    return add_nonnative(mul_nonnative_by_bool(x, b), mul_nonnative_by_bool(y, nb), mod);
+  }
   NNT neg_nonnative(const NNT& x, int mod) {                        // nonnative.rs:491-500
     NNT zero; zero.r = mkref(SP_CONST, 0, 0);
     return sub_nonnative(zero, x, mod);
@@ -638,6 +657,43 @@ int p2e_builder_neg_nonnative(int h, int modulus, int x) {
   P2E_B(h);
   if (!mod_ok(modulus) || !val_ok(b, x, false)) return berr(b, "p2e_builder: bad operand for neg_nonnative");
   return push_val(b, b->neg_nonnative(b->vals[x], modulus), false);
+}
+
+int p2e_builder_add_many_nonnative(int h, int modulus, const int* xs, int k) {
+  P2E_B(h);
+  if (!mod_ok(modulus) || k < 1 || k > 16) return berr(b, "p2e_builder: add_many_nonnative takes 1..16 summands");
+  std::vector<NNT> v;
+  for (int j = 0; j < k; j++) {
+    if (!val_ok(b, xs[j], false)) return berr(b, "p2e_builder: bad summand for add_many_nonnative");
+    v.push_back(b->vals[xs[j]]);
+  }
+  if (k == 1) return xs[0];
+  return push_val(b, b->add_many_nonnative(v, modulus), false);
+}
+
+// BoolTarget operands of the two gadgets below must be input values (wire 0 holds 0 / 1)
+static bool bool_of(Builder* b, int v, BoolT& out) {
+  if (!val_ok(b, v, false) || b->vals[v].r.space != SP_IN) return false;
+  out.space = SP_IN;
+  out.off = b->vals[v].r.off;
+  out.inv = false;
+  return true;
+}
+
+int p2e_builder_nonnative_conditional_neg(int h, int modulus, int x, int bool_input) {
+  P2E_B(h);
+  BoolT bt;
+  if (!mod_ok(modulus) || !val_ok(b, x, false) || !bool_of(b, bool_input, bt))
+    return berr(b, "p2e_builder: bad operand for nonnative_conditional_neg (the BoolTarget must be an input)");
+  return push_val(b, b->nonnative_conditional_neg(b->vals[x], bt, modulus), false);
+}
+
+int p2e_builder_if_nonnative(int h, int modulus, int bool_input, int x, int y) {
+  P2E_B(h);
+  BoolT bt;
+  if (!mod_ok(modulus) || !val_ok(b, x, false) || !val_ok(b, y, false) || !bool_of(b, bool_input, bt))
+    return berr(b, "p2e_builder: bad operand for if_nonnative (the BoolTarget must be an input)");
+  return push_val(b, b->if_nonnative(bt, b->vals[x], b->vals[y], modulus), false);
 }
 
 int p2e_builder_connect_nonnative(int h, int x, int y) {

@@ -28,11 +28,11 @@ struct Ref {
   uint32_t boff;
 };
 
-enum PrepOpcode : uint8_t { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_INV = 3, OP_GLV = 4 };
+enum PrepOpcode : uint8_t { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_INV = 3, OP_GLV = 4, OP_ADDMANY = 5 };
 struct PrepOp {
   uint8_t opcode;
   uint8_t mod;
-  uint16_t pad;
+  uint16_t pad;     // OP_ADDMANY: number of summands, stored at extra_refs[a.boff ...]
   uint32_t slot;    // first output slot
   Ref a, b;
 };
@@ -67,6 +67,7 @@ struct Tape {
   std::vector<PrepOp> prep;
   std::vector<PtOp> ptops;
   std::vector<Check> checks;
+  std::vector<Ref> extra_refs;          // operand lists of OP_ADDMANY
   std::vector<InputPoint> in_points;    // pid = ptops.size() + index
   std::vector<uint32_t> const_limbs;    // SP_CONST pool (u32 limbs)
   std::vector<uint32_t> const_points;   // affine constants: 18 limbs each (x[9], y[9])

@@ -94,6 +94,9 @@ SIGNATURES = {
     "p2e_builder_mul_nonnative": (_int, [_int, _int, _int, _int]),
     "p2e_builder_inv_nonnative": (_int, [_int, _int, _int]),
     "p2e_builder_neg_nonnative": (_int, [_int, _int, _int]),
+    "p2e_builder_add_many_nonnative": (_int, [_int, _int, _vp, _int]),
+    "p2e_builder_nonnative_conditional_neg": (_int, [_int, _int, _int, _int]),
+    "p2e_builder_if_nonnative": (_int, [_int, _int, _int, _int, _int]),
     "p2e_builder_connect_nonnative": (_int, [_int, _int, _int]),
     "p2e_builder_affine_point": (_int, [_int, _int, _int]),
     "p2e_builder_constant_affine_point": (_int, [_int, _vp, _vp]),
@@ -200,6 +203,16 @@ class CircuitBuilder:
 
     def neg_nonnative(self, modulus, x):
         return self._ok(self.lib.p2e_builder_neg_nonnative(self.h, modulus, x))
+
+    def add_many_nonnative(self, modulus, xs):
+        arr = np.array(list(xs), dtype=np.int32)
+        return self._ok(self.lib.p2e_builder_add_many_nonnative(self.h, modulus, arr.ctypes.data, len(arr)))
+
+    def nonnative_conditional_neg(self, modulus, x, b):
+        return self._ok(self.lib.p2e_builder_nonnative_conditional_neg(self.h, modulus, x, b))
+
+    def if_nonnative(self, modulus, b, x, y):
+        return self._ok(self.lib.p2e_builder_if_nonnative(self.h, modulus, b, x, y))
 
     def connect_nonnative(self, a, b):
         self._ok(self.lib.p2e_builder_connect_nonnative(self.h, a, b))

@@ -187,3 +187,52 @@ def test_builder_ecdsa_witness_equals_builtin(engine):
     w1, e1 = engine.verify_secp256k1_message_witness(*ins)
     w2, e2 = engine.tape_witness(tid, ins)
     assert np.array_equal(w1, w2) and np.array_equal(e1, e2) and not e1.any()
+
+
+def build_misc_nonnative(cb, modulus):
+    """test_nonnative_many_adds / conditional neg / if (gadgets/nonnative.rs:943-977, 584-596, 297-308)."""
+    a, b, c, d, flag = (cb.add_virtual_nonnative_target() for _ in range(5))
+    s = cb.add_many_nonnative(modulus, [a, b, c, d])
+    t = cb.nonnative_conditional_neg(modulus, s, flag)
+    u = cb.if_nonnative(modulus, flag, a, b)
+    v = cb.mul_nonnative(modulus, t, u)
+    one = cb.add_many_nonnative(modulus, [v])          # single summand: returns its input, no generator
+    assert one == v
+    return cb.build()
+
+
+def oracle_misc_nonnative(vals, flag, m):
+    wb = S.WitnessBuilder()
+    a, b, c, d = (S.NN(S.limbs9(v)) for v in vals)
+    s = wb.add_many_nonnative([a, b, c, d], m)
+    t = wb.nonnative_conditional_neg(s, flag, m)
+    u = wb.if_nonnative(flag, a, b, m)
+    wb.mul_nonnative(t, u, m)
+    return wb
+
+
+@pytest.mark.parametrize("modulus", [P_, N_])
+def test_builder_misc_nonnative_layout(modulus):
+    lib = pkg.load_library()
+    tid = build_misc_nonnative(pkg.CircuitBuilder(lib), modulus)
+    wb = oracle_misc_nonnative([5, 6, 7, 8], 1, S.MODULI[modulus])
+    assert _layout(lib, tid) == (*_oracle_layout(wb.tape), 5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("modulus", [P_, N_])
+def test_builder_misc_nonnative_witness(engine, modulus):
+    m = S.MODULI[modulus]
+    tid = build_misc_nonnative(pkg.CircuitBuilder(engine.lib), modulus)
+    rng = random.Random(4 + modulus)
+    n = 40
+    cols = [[rng.randrange(m) for _ in range(n)] for _ in range(4)]
+    cols[0][0] = cols[1][0] = cols[2][0] = cols[3][0] = m - 1          # overflow count 3
+    flags = [j % 2 for j in range(n)]
+    fm = np.zeros((9, n), dtype=np.uint64)
+    fm[0] = flags
+    wit, err = engine.tape_witness(tid, [W.ints_to_limbs(c) for c in cols] + [fm])
+    assert not err.any()
+    for j in range(n):
+        wb = oracle_misc_nonnative([c[j] for c in cols], flags[j], m)
+        assert [int(v) for v in wit[:, j]] == wb.flat()
