@@ -40,6 +40,7 @@ struct DevTape {
   int n_prep, n_ptops, n_checks, n_in_points;
   int32_t pre_pid[16];
   Ref fixed_scalar, msm_k1, msm_k2;
+  u32 fixed_round, msm_round;
   u32 fixed_table_base;
   int32_t chain_begin[N_CHAINS], chain_end[N_CHAINS];
 };
@@ -47,6 +48,7 @@ struct DevTape {
 struct ChainArgs {
   DevTape t;
   size_t n;                 // signatures in this chunk
+  int round;                // dependency round being executed (Tape::n_rounds)
   const u64* in[MAX_TAPE_INPUTS];   // input nonnative values, [9][is] each
   size_t is;
   u64* out;                 // [n_slots][os]
@@ -241,6 +243,7 @@ __global__ void __launch_bounds__(32) k_prep(ChainArgs A) {
   u32 err = 0;
   for (int k = 0; k < A.t.n_prep; k++) {
     const PrepOp op = A.t.prep[k];
+    if (op.round != A.round) continue;
     if (op.opcode == OP_GLV) {
       u64 w[NL];
       load_ref(A, op.a, i, w);
@@ -269,7 +272,8 @@ __global__ void __launch_bounds__(32) k_prep(ChainArgs A) {
       err |= prep_exec<ModN>(A, op, i);
     }
   }
-  A.err[i] = err;
+  if (A.round == 0) A.err[i] = err;
+  else if (err) A.err[i] |= err;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -441,11 +445,12 @@ __device__ __forceinline__ u32 digit_at(const u32* limbs, int nl, int pos, int b
   return (u32)(v >> sh) & ((1u << bits) - 1u);
 }
 
-__device__ __forceinline__ u32 load_scalar_limbs(const ChainArgs& A, const Ref& r, size_t i, u32* limbs) {
-  // split_le_base::<2>(limb, 29) asserts each limb fits 29 bits (split_nonnative.rs:29-37)
+__device__ __forceinline__ u32 load_scalar_limbs(const ChainArgs& A, const Ref& r, bool live, size_t i, u32* limbs) {
+  // split_le_base::<2>(limb, 29) asserts each limb fits 29 bits (split_nonnative.rs:29-37);
+  // `live`: the scalar-multiplication loop runs in this round (its scalar may not exist earlier)
   u32 e = 0;
   for (int l = 0; l < NL; l++) {
-    u64 w = (l < r.nl && r.space != SP_NONE) ? load_wire(A, r.space, r.off + l, i) : 0;
+    u64 w = (live && l < r.nl && r.space != SP_NONE) ? load_wire(A, r.space, r.off + l, i) : 0;
     if (w >> LB) e |= ERR_LIMB_RANGE;
     limbs[l] = (u32)w & LMASK;
   }
@@ -461,6 +466,7 @@ __global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A, int chain0) {
   u32 err = 0;
   // per-signature affine input points (Z = 1); every chain writes the same values (benign)
   for (int j = 0; j < A.t.n_in_points; j++) {
+    if ((int)A.t.in_points[j].round != A.round) continue;
     u64 w[NL];
     u32 x[NL], y[NL], one[NL];
     load_ref(A, A.t.in_points[j].x, i, w);
@@ -478,14 +484,14 @@ __global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A, int chain0) {
     sv9(A.ZC, idx, A.cap, i, one);
   }
   u32 fs[NL], k1[NL], k2[NL];
-  err |= load_scalar_limbs(A, A.t.fixed_scalar, i, fs);
-  err |= load_scalar_limbs(A, A.t.msm_k1, i, k1);
-  err |= load_scalar_limbs(A, A.t.msm_k2, i, k2);
+  err |= load_scalar_limbs(A, A.t.fixed_scalar, (int)A.t.fixed_round == A.round, i, fs);
+  err |= load_scalar_limbs(A, A.t.msm_k1, (int)A.t.msm_round == A.round, i, k1);
+  err |= load_scalar_limbs(A, A.t.msm_k2, (int)A.t.msm_round == A.round, i, k2);
 
   int32_t cur = -1;
   for (int k = k_begin; k < k_end; k++) {
     const PtOp op = A.t.ptops[k];
-    if (((op.flags >> PF_CHAIN_SHIFT) & 3) != chain) continue;      // chains may interleave in op order
+    if (((op.flags >> PF_CHAIN_SHIFT) & 3) != chain || (int)op.round != A.round) continue;   // chains / rounds interleave in op order
     int32_t p1 = (op.flags & PF_P1_CUR) ? cur : resolve_pid(A, op.p1, i);
     int32_t p2 = (op.flags & PF_P2_CUR) ? cur : resolve_pid(A, op.p2, i);
     u32 flag = 1;
@@ -604,6 +610,7 @@ __global__ void __launch_bounds__(64) k_chain_replay_duo(ChainArgs A, int chain0
   u32 err = 0;
   if (writer) {
     for (int j = 0; j < A.t.n_in_points; j++) {
+      if ((int)A.t.in_points[j].round != A.round) continue;
       u64 w[NL];
       u32 x[NL], y[NL], one[NL];
       load_ref(A, A.t.in_points[j].x, i, w);
@@ -623,15 +630,15 @@ __global__ void __launch_bounds__(64) k_chain_replay_duo(ChainArgs A, int chain0
   }
   __syncwarp();                                    // the partner lane reads the input points just written
   u32 fs[NL], k1[NL], k2[NL];
-  err |= load_scalar_limbs(A, A.t.fixed_scalar, i, fs);
-  err |= load_scalar_limbs(A, A.t.msm_k1, i, k1);
-  err |= load_scalar_limbs(A, A.t.msm_k2, i, k2);
+  err |= load_scalar_limbs(A, A.t.fixed_scalar, (int)A.t.fixed_round == A.round, i, fs);
+  err |= load_scalar_limbs(A, A.t.msm_k1, (int)A.t.msm_round == A.round, i, k1);
+  err |= load_scalar_limbs(A, A.t.msm_k2, (int)A.t.msm_round == A.round, i, k2);
 
   int32_t cur = -1, resident = -2;
   JacL R;
   for (int k = k_begin; k < k_end; k++) {
     const PtOp op = A.t.ptops[k];
-    if (((op.flags >> PF_CHAIN_SHIFT) & 3) != chain) continue;      // chains may interleave in op order
+    if (((op.flags >> PF_CHAIN_SHIFT) & 3) != chain || (int)op.round != A.round) continue;   // chains / rounds interleave in op order
     int32_t p1 = (op.flags & PF_P1_CUR) ? cur : resolve_pid(A, op.p1, i);
     int32_t p2 = (op.flags & PF_P2_CUR) ? cur : resolve_pid(A, op.p2, i);
     u32 flag = 1;
@@ -769,6 +776,7 @@ __global__ void __launch_bounds__(128) k_chain_replay_coop(ChainArgs A, int chai
   if (q == 0 && valid) {
     // per-signature affine input points (Z = 1); every chain writes the same values (benign)
     for (int j = 0; j < A.t.n_in_points; j++) {
+      if ((int)A.t.in_points[j].round != A.round) continue;
       u64 w[NL];
       u32 x[NL], y[NL], one[NL];
       load_ref(A, A.t.in_points[j].x, i, w);
@@ -788,14 +796,14 @@ __global__ void __launch_bounds__(128) k_chain_replay_coop(ChainArgs A, int chai
   }
   __syncwarp();
   u32 fs[NL], k1[NL], k2[NL];
-  err |= load_scalar_limbs(A, A.t.fixed_scalar, i, fs);
-  err |= load_scalar_limbs(A, A.t.msm_k1, i, k1);
-  err |= load_scalar_limbs(A, A.t.msm_k2, i, k2);
+  err |= load_scalar_limbs(A, A.t.fixed_scalar, (int)A.t.fixed_round == A.round, i, fs);
+  err |= load_scalar_limbs(A, A.t.msm_k1, (int)A.t.msm_round == A.round, i, k1);
+  err |= load_scalar_limbs(A, A.t.msm_k2, (int)A.t.msm_round == A.round, i, k2);
 
   int32_t cur = -1, resident = -2;
   for (int k = k_begin; k < k_end; k++) {
     const PtOp op = A.t.ptops[k];
-    if (((op.flags >> PF_CHAIN_SHIFT) & 3) != chain) continue;      // chains may interleave in op order
+    if (((op.flags >> PF_CHAIN_SHIFT) & 3) != chain || (int)op.round != A.round) continue;   // chains / rounds interleave in op order
     int32_t p1 = (op.flags & PF_P1_CUR) ? cur : resolve_pid(A, op.p1, i);
     int32_t p2 = (op.flags & PF_P2_CUR) ? cur : resolve_pid(A, op.p2, i);
     u32 flag = 1;
@@ -864,7 +872,11 @@ __global__ void __launch_bounds__(32) k_chain_invert(ChainArgs A) {
   i32 run[NL], z[NL], t[NL];
 #pragma unroll
   for (int l = 0; l < NL; l++) run[l] = (l == 0);
+  bool any = false;
+  for (int k = k0; k < k1; k++) any |= (int)A.t.ptops[k].round == A.round;
+  if (!any) return;                     // no curve op of this group in this round
   for (int k = k0; k < k1; k++) {
+    if ((int)A.t.ptops[k].round != A.round) continue;
     sv9(A.ZINV, k, A.cap, i, run);      // prefix product of this group's Z's
     ld9(A.JZ, k, A.cap, i, z);
     lz_mul(run, z, t);
@@ -876,12 +888,14 @@ __global__ void __launch_bounds__(32) k_chain_invert(ChainArgs A) {
     // some curve op had x1 == x2 (or y == 0): the reference's inverse() panics
     atomicOr(&A.err[i], (u32)ERR_INVERSE_ZERO);
     set_zero9(rc);
-    for (int k = k0; k < k1; k++) sv9(A.ZINV, k, A.cap, i, rc);
+    for (int k = k0; k < k1; k++)
+      if ((int)A.t.ptops[k].round == A.round) sv9(A.ZINV, k, A.cap, i, rc);
     return;
   }
   i32 inv[NL];
   lz_inv_calls(run, inv);
   for (int k = k1 - 1; k >= k0; k--) {
+    if ((int)A.t.ptops[k].round != A.round) continue;
     i32 pre[NL], zi[NL];
     ld9(A.ZINV, k, A.cap, i, pre);
     ld9(A.JZ, k, A.cap, i, z);
@@ -897,7 +911,7 @@ __global__ void __launch_bounds__(32) k_chain_invert(ChainArgs A) {
 __global__ void __launch_bounds__(128) k_chain_affine(ChainArgs A) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int k = blockIdx.y;
-  if (i >= A.n) return;
+  if (i >= A.n || (int)A.t.ptops[k].round != A.round) return;
   i32 zi[NL], zi2[NL], zi3[NL], v[NL], r[NL];
   u32 c[NL];
   ld9(A.ZINV, k, A.cap, i, zi);
@@ -966,6 +980,7 @@ __global__ void __launch_bounds__(128, 3) k_chain_expand(ChainArgs A) {
   int k = blockIdx.y;
   if (i >= A.n) return;
   const PtOp op = A.t.ptops[k];
+  if ((int)op.round != A.round) return;
   const u32 s0 = op.slot;
   int32_t p1 = A.SRC1[(size_t)k * A.cap + i];
   u32 e = 0;
@@ -1131,6 +1146,8 @@ static int upload_tape(const Tape& t, TapeOnDevice& o) {
   o.d.fixed_scalar = t.fixed_scalar;
   o.d.msm_k1 = t.msm_k1;
   o.d.msm_k2 = t.msm_k2;
+  o.d.fixed_round = t.fixed_round;
+  o.d.msm_round = t.msm_round;
   o.d.fixed_table_base = t.fixed_table_base;
   for (int c = 0; c < N_CHAINS; c++) { o.d.chain_begin[c] = t.chain_begin[c]; o.d.chain_end[c] = t.chain_end[c]; }
   o.blob = blob;
@@ -1293,37 +1310,47 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
     }
     const bool prof = g_profiling && c0 == 0;
     if (prof) prof_mark(st);
-    k_prep<<<g32, 32, 0, s_hi>>>(A);
-    if (prof) prof_mark(st);
-    if (no) {
-      if (replay_mode() == 2) {
-        const unsigned g_duo = (unsigned)((2 * cn + 63) / 64);
-        k_chain_replay_duo<<<dim3(g_duo, 2), 64, 0, s_hi>>>(A, 0);      // 2 lanes per (signature, chain)
-        if (prof) prof_mark(st);
-        if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay_duo<<<dim3(g_duo, 1), 64, 0, s_hi>>>(A, 2);   // join
-      } else if (replay_mode() == 1) {
-        k_chain_replay_coop<<<dim3(g32, 2), 128, 0, s_hi>>>(A, 0);    // 4 lanes per (signature, chain)
-        if (prof) prof_mark(st);
-        if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay_coop<<<dim3(g32, 1), 128, 0, s_hi>>>(A, 2);   // join
-      } else {
-        k_chain_replay<<<dim3(g32, 2), 32, 0, s_hi>>>(A, 0);    // fixed-base and msm chains side by side
-        if (prof) prof_mark(st);
-        if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g32, 1), 32, 0, s_hi>>>(A, 2);   // join
+    const int n_rounds = (int)t.n_rounds;
+    for (int round = 0; round < n_rounds; round++) {
+      // Round r: generators of round r (K0), then the curve ops of round r (K1-K4).  A later round
+      // consumes coordinates written by this round's expansion, so it waits for the low-priority stream.
+      A.round = round;
+      if (split && round > 0) {
+        P2E_CUDA(cudaEventRecord(arena->ev_out, s_lo));
+        P2E_CUDA(cudaStreamWaitEvent(s_hi, arena->ev_out, 0));
       }
+      k_prep<<<g32, 32, 0, s_hi>>>(A);
       if (prof) prof_mark(st);
-      k_chain_invert<<<dim3(g32, inv_groups()), 32, 0, s_hi>>>(A);
-      if (prof) prof_mark(st);
-      if (split) {
+      if (no) {
+        if (replay_mode() == 2) {
+          const unsigned g_duo = (unsigned)((2 * cn + 63) / 64);
+          k_chain_replay_duo<<<dim3(g_duo, 2), 64, 0, s_hi>>>(A, 0);      // 2 lanes per (signature, chain)
+          if (prof) prof_mark(st);
+          if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay_duo<<<dim3(g_duo, 1), 64, 0, s_hi>>>(A, 2);   // join
+        } else if (replay_mode() == 1) {
+          k_chain_replay_coop<<<dim3(g32, 2), 128, 0, s_hi>>>(A, 0);    // 4 lanes per (signature, chain)
+          if (prof) prof_mark(st);
+          if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay_coop<<<dim3(g32, 1), 128, 0, s_hi>>>(A, 2);   // join
+        } else {
+          k_chain_replay<<<dim3(g32, 2), 32, 0, s_hi>>>(A, 0);    // fixed-base and msm chains side by side
+          if (prof) prof_mark(st);
+          if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g32, 1), 32, 0, s_hi>>>(A, 2);   // join
+        }
+        if (prof) prof_mark(st);
+        k_chain_invert<<<dim3(g32, inv_groups()), 32, 0, s_hi>>>(A);
+        if (prof) prof_mark(st);
+        if (split) {
+          P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
+          P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
+        }
+        k_chain_affine<<<dim3(g128, (unsigned)no), 128, 0, s_lo>>>(A);
+        if (prof) prof_mark(st);
+        k_chain_expand<<<dim3(g128, (unsigned)no), 128, 0, s_lo>>>(A);
+        if (prof) prof_mark(st);
+      } else if (split) {
         P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
         P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
       }
-      k_chain_affine<<<dim3(g128, (unsigned)no), 128, 0, s_lo>>>(A);
-      if (prof) prof_mark(st);
-      k_chain_expand<<<dim3(g128, (unsigned)no), 128, 0, s_lo>>>(A);
-      if (prof) prof_mark(st);
-    } else if (split) {
-      P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
-      P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
     }
     k_chain_checks<<<g32, 32, 0, s_lo>>>(A);
     if (prof) prof_mark(st);

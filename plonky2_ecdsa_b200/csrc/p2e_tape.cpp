@@ -174,9 +174,11 @@ class Builder {
   Tape t;
   APoint rando, neg_rando;
   int cur_chain = 0;
+  int cur_round = 0;                 // round given to the prep / point ops emitted next
   // dynamic (C-API) use: value / point handles
   std::vector<NNT> vals;
-  std::vector<uint8_t> val_late;     // produced by a curve op: only connect_nonnative may consume it
+  std::vector<uint8_t> val_round;    // round from which the value is available
+  std::vector<uint8_t> pt_round;     // round of the op producing the point (or of its coordinate values)
   std::vector<PtT> pts;
   std::vector<int8_t> pt_chain;      // chain of the producing op, -1 for input / constant points
   int n_fixed = 0, n_msm = 0;
@@ -224,10 +226,12 @@ class Builder {
     p.opcode = op;
     p.mod = (uint8_t)mod;
     p.pad = 0;
+    p.round = (uint8_t)cur_round;
     p.slot = slot;
     p.a = a.r;
     p.b = b.r;
     t.prep.push_back(p);
+    if ((uint32_t)cur_round + 1 > t.n_rounds) t.n_rounds = cur_round + 1;
   }
 
   NNT add_nonnative(const NNT& a, const NNT& b, int mod) {          // nonnative.rs:245-276
@@ -257,7 +261,9 @@ class Builder {
     PrepOp p;
     p.opcode = OP_ADDMANY;
     p.mod = (uint8_t)mod;
-    p.pad = (uint16_t)xs.size();
+    p.pad = (uint8_t)xs.size();
+    p.round = (uint8_t)cur_round;
+    if ((uint32_t)cur_round + 1 > t.n_rounds) t.n_rounds = cur_round + 1;
     p.slot = s;
     p.a = mkref(SP_NONE, 0, 0);
     p.a.boff = (uint32_t)t.extra_refs.size();
@@ -301,7 +307,7 @@ class Builder {
     return PID_CONST_BASE + idx;
   }
   PtT input_point(const NNT& x, const NNT& y) {
-    InputPoint ip; ip.x = x.r; ip.y = y.r;
+    InputPoint ip; ip.x = x.r; ip.y = y.r; ip.round = (uint32_t)cur_round;
     PtT p; p.pid = PID_INPUT_BASE + (int32_t)t.in_points.size(); p.x = x; p.y = y;
     t.in_points.push_back(ip);
     return p;
@@ -342,7 +348,8 @@ class Builder {
   }
   PtT push_ptop(PtOpType type, uint8_t flags, uint16_t aux, int32_t p1, int32_t p2, uint32_t slot, uint32_t xo, uint32_t yo) {
     PtOp o;
-    o.type = type; o.aux = aux; o.p1 = p1; o.p2 = p2; o.slot = slot;
+    o.type = type; o.aux = aux; o.p1 = p1; o.p2 = p2; o.slot = slot; o.round = (uint32_t)cur_round;
+    if ((uint32_t)cur_round + 1 > t.n_rounds) t.n_rounds = cur_round + 1;
     // operand 2 is statically affine (constant or per-signature input point): mixed addition
     bool p2_affine = (type == PT_CADD_FIXED) ||
                      ((type == PT_ADD || type == PT_CADD_BOOL) && !(flags & PF_P2_CUR) && p2 >= PID_INPUT_BASE);
@@ -383,6 +390,7 @@ class Builder {
     const int n_limbs4 = (9 * LB + 3) / 4;                           // 66 4-bit limbs (split_nonnative.rs:25-50)
     cur_chain = 0;
     t.fixed_scalar = scalar.r;
+    t.fixed_round = (uint32_t)cur_round;
     t.fixed_table_base = (uint32_t)(t.const_points.size() / 18);
     APoint base = generator();
     for (int w = 0; w < n_limbs4; w++) {
@@ -413,6 +421,7 @@ class Builder {
     cur_chain = 1;
     t.msm_k1 = n.r;
     t.msm_k2 = m.r;
+    t.msm_round = (uint32_t)cur_round;
     int32_t rando_pid = const_point(rando);
     int32_t neg_pid = const_point(neg_rando);
     int32_t pre[16];
@@ -448,7 +457,7 @@ class Builder {
     uint32_t gs = emit(G_GLV, 12);
     {
       PrepOp p;
-      p.opcode = OP_GLV; p.mod = 1; p.pad = 0; p.slot = gs; p.a = k.r; p.b = k.r;
+      p.opcode = OP_GLV; p.mod = 1; p.pad = 0; p.round = (uint8_t)cur_round; p.slot = gs; p.a = k.r; p.b = k.r;
       t.prep.push_back(p);
     }
     NNT k1; k1.r = mkref(SP_OUT, gs, 5);
@@ -567,19 +576,21 @@ static int berr(Builder* b, const char* msg) {
   set_error_msg(msg);
   return -1;
 }
-static int push_val(Builder* b, const NNT& v, bool late) {
+constexpr int MAX_ROUNDS = 32;
+static int push_val(Builder* b, const NNT& v, int round) {
   b->vals.push_back(v);
-  b->val_late.push_back(late ? 1 : 0);
+  b->val_round.push_back((uint8_t)round);
   return (int)b->vals.size() - 1;
 }
-static int push_pt(Builder* b, const PtT& p, int chain) {
+static int push_pt(Builder* b, const PtT& p, int chain, int round) {
   b->pts.push_back(p);
   b->pt_chain.push_back((int8_t)chain);
+  b->pt_round.push_back((uint8_t)round);
   return (int)b->pts.size() - 1;
 }
-static bool val_ok(Builder* b, int v, bool allow_late) {
-  return v >= 0 && (size_t)v < b->vals.size() && (allow_late || !b->val_late[v]);
-}
+static bool val_ok(Builder* b, int v) { return v >= 0 && (size_t)v < b->vals.size(); }
+static int vround(Builder* b, int v) { return b->val_round[v]; }
+static int max2(int a, int c) { return a > c ? a : c; }
 static bool pt_ok(Builder* b, int p) { return p >= 0 && (size_t)p < b->pts.size(); }
 static bool mod_ok(int m) { return m == 0 || m == 1; }
 static Fe fe_from_limbs(const uint32_t* l) {
@@ -587,22 +598,31 @@ static Fe fe_from_limbs(const uint32_t* l) {
   for (int i = 0; i < NL; i++) r.l[i] = l[i] & LMASK;
   return r;
 }
-// chain of a new curve op: chain 1 unless an operand was produced by the fixed-base chain (0) or the join chain (2)
-static int op_chain(Builder* b, int p1, int p2) {
+// round from which the COORDINATE VALUES of a point can feed nonnative generators / new points
+static int pt_value_round(Builder* b, int p) { return b->pt_round[p] + (b->pt_chain[p] >= 0 ? 1 : 0); }
+// chain of a new curve op of round `round`: chain 1 unless an operand was produced IN THE SAME ROUND by
+// the fixed-base chain (0) or the join chain (2); results of earlier rounds are plain data
+static int op_chain(Builder* b, int round, int p1, int p2) {
   int c = 1;
   for (int p : {p1, p2})
-    if (p >= 0 && (b->pt_chain[p] == 0 || b->pt_chain[p] == 2)) c = 2;
+    if (p >= 0 && b->pt_round[p] == round && (b->pt_chain[p] == 0 || b->pt_chain[p] == 2)) c = 2;
   return c;
+}
+static bool round_ok(Builder* b, int round) {
+  if (round < MAX_ROUNDS) return true;
+  b->error = "p2e_builder: too many dependency rounds";
+  set_error_msg(b->error.c_str());
+  return false;
 }
 
 }  // namespace p2e
 
 using namespace p2e;
-#define P2E_B(h)                      \
-  std::lock_guard<std::mutex> lock__(g_builder_mu); \
-  Builder* b = get_builder(h);        \
-  if (!b) return -1
 static std::mutex g_builder_mu;
+#define P2E_B(h)                                    \
+  std::lock_guard<std::mutex> lock__(g_builder_mu); \
+  Builder* b = get_builder(h);                      \
+  if (!b) return -1
 
 extern "C" {
 
@@ -624,23 +644,25 @@ int p2e_builder_free(int h) {
 int p2e_builder_input(int h) {
   P2E_B(h);
   if (b->t.n_inputs >= (uint32_t)MAX_TAPE_INPUTS) return berr(b, "p2e_builder: at most 16 inputs per tape");
-  return push_val(b, b->input(b->t.n_inputs), false);
+  return push_val(b, b->input(b->t.n_inputs), 0);
 }
 
 int p2e_builder_constant_nonnative(int h, const uint32_t* limbs9) {
   P2E_B(h);
-  return push_val(b, b->constant_nonnative(fe_from_limbs(limbs9)), false);
+  return push_val(b, b->constant_nonnative(fe_from_limbs(limbs9)), 0);
 }
 
 static int binop(int h, int kind, int modulus, int x, int y) {
   P2E_B(h);
   if (!mod_ok(modulus)) return berr(b, "p2e_builder: unknown modulus");
-  if (!val_ok(b, x, false) || !val_ok(b, y, false))
-    return berr(b, "p2e_builder: operand is not a value handle, or is a curve-op output (only connect_nonnative may consume those)");
+  if (!val_ok(b, x) || !val_ok(b, y)) return berr(b, "p2e_builder: operand is not a value handle");
+  const int round = max2(vround(b, x), vround(b, y));
+  if (!round_ok(b, round)) return -1;
+  b->cur_round = round;
   NNT r = kind == 0 ? b->add_nonnative(b->vals[x], b->vals[y], modulus)
         : kind == 1 ? b->sub_nonnative(b->vals[x], b->vals[y], modulus)
                     : b->mul_nonnative(b->vals[x], b->vals[y], modulus);
-  return push_val(b, r, false);
+  return push_val(b, r, round);
 }
 int p2e_builder_add_nonnative(int h, int modulus, int x, int y) { return binop(h, 0, modulus, x, y); }
 int p2e_builder_sub_nonnative(int h, int modulus, int x, int y) { return binop(h, 1, modulus, x, y); }
@@ -648,32 +670,37 @@ int p2e_builder_mul_nonnative(int h, int modulus, int x, int y) { return binop(h
 
 int p2e_builder_inv_nonnative(int h, int modulus, int x) {
   P2E_B(h);
-  if (!mod_ok(modulus) || !val_ok(b, x, false)) return berr(b, "p2e_builder: bad operand for inv_nonnative");
+  if (!mod_ok(modulus) || !val_ok(b, x)) return berr(b, "p2e_builder: bad operand for inv_nonnative");
   if (b->vals[x].r.nl != NL) return berr(b, "p2e_builder: inv_nonnative needs a 9-limb operand");
-  return push_val(b, b->inv_nonnative(b->vals[x], modulus), false);
+  b->cur_round = vround(b, x);
+  return push_val(b, b->inv_nonnative(b->vals[x], modulus), b->cur_round);
 }
 
 int p2e_builder_neg_nonnative(int h, int modulus, int x) {
   P2E_B(h);
-  if (!mod_ok(modulus) || !val_ok(b, x, false)) return berr(b, "p2e_builder: bad operand for neg_nonnative");
-  return push_val(b, b->neg_nonnative(b->vals[x], modulus), false);
+  if (!mod_ok(modulus) || !val_ok(b, x)) return berr(b, "p2e_builder: bad operand for neg_nonnative");
+  b->cur_round = vround(b, x);
+  return push_val(b, b->neg_nonnative(b->vals[x], modulus), b->cur_round);
 }
 
 int p2e_builder_add_many_nonnative(int h, int modulus, const int* xs, int k) {
   P2E_B(h);
   if (!mod_ok(modulus) || k < 1 || k > 16) return berr(b, "p2e_builder: add_many_nonnative takes 1..16 summands");
   std::vector<NNT> v;
+  int round = 0;
   for (int j = 0; j < k; j++) {
-    if (!val_ok(b, xs[j], false)) return berr(b, "p2e_builder: bad summand for add_many_nonnative");
+    if (!val_ok(b, xs[j])) return berr(b, "p2e_builder: bad summand for add_many_nonnative");
     v.push_back(b->vals[xs[j]]);
+    round = max2(round, vround(b, xs[j]));
   }
   if (k == 1) return xs[0];
-  return push_val(b, b->add_many_nonnative(v, modulus), false);
+  b->cur_round = round;
+  return push_val(b, b->add_many_nonnative(v, modulus), round);
 }
 
-// BoolTarget operands of the two gadgets below must be input values (wire 0 holds 0 / 1)
+// BoolTarget operands must be input values (wire 0 holds 0 / 1)
 static bool bool_of(Builder* b, int v, BoolT& out) {
-  if (!val_ok(b, v, false) || b->vals[v].r.space != SP_IN) return false;
+  if (!val_ok(b, v) || b->vals[v].r.space != SP_IN) return false;
   out.space = SP_IN;
   out.off = b->vals[v].r.off;
   out.inv = false;
@@ -683,30 +710,35 @@ static bool bool_of(Builder* b, int v, BoolT& out) {
 int p2e_builder_nonnative_conditional_neg(int h, int modulus, int x, int bool_input) {
   P2E_B(h);
   BoolT bt;
-  if (!mod_ok(modulus) || !val_ok(b, x, false) || !bool_of(b, bool_input, bt))
+  if (!mod_ok(modulus) || !val_ok(b, x) || !bool_of(b, bool_input, bt))
     return berr(b, "p2e_builder: bad operand for nonnative_conditional_neg (the BoolTarget must be an input)");
-  return push_val(b, b->nonnative_conditional_neg(b->vals[x], bt, modulus), false);
+  b->cur_round = vround(b, x);
+  return push_val(b, b->nonnative_conditional_neg(b->vals[x], bt, modulus), b->cur_round);
 }
 
 int p2e_builder_if_nonnative(int h, int modulus, int bool_input, int x, int y) {
   P2E_B(h);
   BoolT bt;
-  if (!mod_ok(modulus) || !val_ok(b, x, false) || !val_ok(b, y, false) || !bool_of(b, bool_input, bt))
+  if (!mod_ok(modulus) || !val_ok(b, x) || !val_ok(b, y) || !bool_of(b, bool_input, bt))
     return berr(b, "p2e_builder: bad operand for if_nonnative (the BoolTarget must be an input)");
-  return push_val(b, b->if_nonnative(bt, b->vals[x], b->vals[y], modulus), false);
+  b->cur_round = max2(vround(b, x), vround(b, y));
+  return push_val(b, b->if_nonnative(bt, b->vals[x], b->vals[y], modulus), b->cur_round);
 }
 
 int p2e_builder_connect_nonnative(int h, int x, int y) {
   P2E_B(h);
-  if (!val_ok(b, x, true) || !val_ok(b, y, true)) return berr(b, "p2e_builder: bad operand for connect_nonnative");
+  if (!val_ok(b, x) || !val_ok(b, y)) return berr(b, "p2e_builder: bad operand for connect_nonnative");
   b->connect_nonnative(b->vals[x], b->vals[y]);
   return 0;
 }
 
 int p2e_builder_affine_point(int h, int x, int y) {
   P2E_B(h);
-  if (!val_ok(b, x, false) || !val_ok(b, y, false)) return berr(b, "p2e_builder: bad coordinates for affine_point");
-  return push_pt(b, b->input_point(b->vals[x], b->vals[y]), -1);
+  if (!val_ok(b, x) || !val_ok(b, y)) return berr(b, "p2e_builder: bad coordinates for affine_point");
+  const int round = max2(vround(b, x), vround(b, y));
+  if (!round_ok(b, round)) return -1;
+  b->cur_round = round;
+  return push_pt(b, b->input_point(b->vals[x], b->vals[y]), -1, round);
 }
 
 int p2e_builder_constant_affine_point(int h, const uint32_t* x9, const uint32_t* y9) {
@@ -719,75 +751,95 @@ int p2e_builder_constant_affine_point(int h, const uint32_t* x9, const uint32_t*
   p.pid = b->const_point(a);
   p.x = b->constant_nonnative(a.x);
   p.y = b->constant_nonnative(a.y);
-  return push_pt(b, p, -1);
+  return push_pt(b, p, -1, 0);
 }
 
 int p2e_builder_point_x(int h, int p) {
   P2E_B(h);
   if (!pt_ok(b, p)) return berr(b, "p2e_builder: bad point handle");
-  return push_val(b, b->pts[p].x, b->pt_chain[p] >= 0);
+  return push_val(b, b->pts[p].x, pt_value_round(b, p));
 }
 int p2e_builder_point_y(int h, int p) {
   P2E_B(h);
   if (!pt_ok(b, p)) return berr(b, "p2e_builder: bad point handle");
-  return push_val(b, b->pts[p].y, b->pt_chain[p] >= 0);
+  return push_val(b, b->pts[p].y, pt_value_round(b, p));
 }
 
 int p2e_builder_curve_add(int h, int p1, int p2) {
   P2E_B(h);
   if (!pt_ok(b, p1) || !pt_ok(b, p2)) return berr(b, "p2e_builder: bad point handle");
-  b->cur_chain = op_chain(b, p1, p2);
-  return push_pt(b, b->curve_add(b->pts[p1].pid, b->pts[p2].pid, 0), b->cur_chain);
+  const int round = max2(b->pt_round[p1], b->pt_round[p2]);
+  b->cur_round = round;
+  b->cur_chain = op_chain(b, round, p1, p2);
+  return push_pt(b, b->curve_add(b->pts[p1].pid, b->pts[p2].pid, 0), b->cur_chain, round);
 }
 
 int p2e_builder_curve_double(int h, int p) {
   P2E_B(h);
   if (!pt_ok(b, p)) return berr(b, "p2e_builder: bad point handle");
-  b->cur_chain = op_chain(b, p, -1);
-  return push_pt(b, b->curve_double(b->pts[p].pid, 0), b->cur_chain);
+  const int round = b->pt_round[p];
+  b->cur_round = round;
+  b->cur_chain = op_chain(b, round, p, -1);
+  return push_pt(b, b->curve_double(b->pts[p].pid, 0), b->cur_chain, round);
 }
 
 int p2e_builder_curve_conditional_add(int h, int p1, int p2, int bool_input) {
   P2E_B(h);
   if (!pt_ok(b, p1) || !pt_ok(b, p2)) return berr(b, "p2e_builder: bad point handle");
-  if (!val_ok(b, bool_input, false) || b->vals[bool_input].r.space != SP_IN)
+  if (!val_ok(b, bool_input) || b->vals[bool_input].r.space != SP_IN)
     return berr(b, "p2e_builder: the BoolTarget of curve_conditional_add must be an input value (wire 0 holds 0 / 1)");
-  b->cur_chain = op_chain(b, p1, p2);
+  const int round = max2(b->pt_round[p1], b->pt_round[p2]);
+  b->cur_round = round;
+  b->cur_chain = op_chain(b, round, p1, p2);
   uint16_t aux = (uint16_t)(b->vals[bool_input].r.off / 9);
-  return push_pt(b, b->curve_conditional_add(PT_CADD_BOOL, 0, aux, b->pts[p1].pid, b->pts[p2].pid), b->cur_chain);
+  return push_pt(b, b->curve_conditional_add(PT_CADD_BOOL, 0, aux, b->pts[p1].pid, b->pts[p2].pid), b->cur_chain, round);
 }
 
 int p2e_builder_fixed_base_curve_mul(int h, int scalar) {
   P2E_B(h);
-  if (!val_ok(b, scalar, false)) return berr(b, "p2e_builder: bad scalar handle");
+  if (!val_ok(b, scalar)) return berr(b, "p2e_builder: bad scalar handle");
   if (b->n_fixed++) return berr(b, "p2e_builder: only one fixed_base_curve_mul_circuit per tape in this version");
+  b->cur_round = vround(b, scalar);
   PtT r = b->fixed_base_curve_mul(b->vals[scalar]);     // sets cur_chain = 0
-  return push_pt(b, r, 0);
+  return push_pt(b, r, 0, b->cur_round);
+}
+
+// a point operand of a scalar-multiplication loop must be complete before the loop's chain starts:
+// if it is produced in the same round by the fixed-base / join chain, the loop moves to the next round
+static int loop_round(Builder* b, int round, int p) {
+  if (b->pt_round[p] == round && (b->pt_chain[p] == 0 || b->pt_chain[p] == 2)) return round + 1;
+  return round;
 }
 
 int p2e_builder_curve_msm(int h, int p, int q, int n, int m) {
   P2E_B(h);
-  if (!pt_ok(b, p) || !pt_ok(b, q) || !val_ok(b, n, false) || !val_ok(b, m, false)) return berr(b, "p2e_builder: bad handle for curve_msm");
-  if (b->pt_chain[p] == 0 || b->pt_chain[p] == 2 || b->pt_chain[q] == 0 || b->pt_chain[q] == 2)
-    return berr(b, "p2e_builder: curve_msm operands may not come from the fixed-base / join chains in this version");
+  if (!pt_ok(b, p) || !pt_ok(b, q) || !val_ok(b, n) || !val_ok(b, m)) return berr(b, "p2e_builder: bad handle for curve_msm");
   if (b->vals[n].r.nl != b->vals[m].r.nl) return berr(b, "p2e_builder: curve_msm scalars must have the same limb count");
   if (b->n_msm++) return berr(b, "p2e_builder: only one curve_msm_circuit / glv_mul per tape in this version");
+  int round = max2(max2(b->pt_round[p], b->pt_round[q]), max2(vround(b, n), vround(b, m)));
+  round = max2(loop_round(b, round, p), loop_round(b, round, q));
+  if (!round_ok(b, round)) return -1;
+  b->cur_round = round;
   PtT r = b->curve_msm(b->pts[p], b->pts[q], b->vals[n], b->vals[m]);    // sets cur_chain = 1
-  return push_pt(b, r, 1);
+  return push_pt(b, r, 1, round);
 }
 
 int p2e_builder_glv_mul(int h, int p, int k) {
   P2E_B(h);
-  if (!pt_ok(b, p) || !val_ok(b, k, false)) return berr(b, "p2e_builder: bad handle for glv_mul");
-  if (b->pt_chain[p] >= 0) return berr(b, "p2e_builder: glv_mul needs a point made of values (affine_point / constant)");
+  if (!pt_ok(b, p) || !val_ok(b, k)) return berr(b, "p2e_builder: bad handle for glv_mul");
   if (b->n_msm++) return berr(b, "p2e_builder: only one curve_msm_circuit / glv_mul per tape in this version");
+  const int round = max2(pt_value_round(b, p), vround(b, k));     // glv_mul works on the coordinate VALUES of p
+  if (!round_ok(b, round)) return -1;
+  b->cur_round = round;
   PtT r = b->glv_mul(b->pts[p].x, b->pts[p].y, b->vals[k]);
-  return push_pt(b, r, 1);
+  return push_pt(b, r, 1, round);
 }
 
 int p2e_builder_curve_assert_valid(int h, int p) {
   P2E_B(h);
-  if (!pt_ok(b, p) || b->pt_chain[p] >= 0) return berr(b, "p2e_builder: curve_assert_valid needs a point made of values");
+  if (!pt_ok(b, p)) return berr(b, "p2e_builder: bad point handle");
+  b->cur_round = pt_value_round(b, p);
+  if (!round_ok(b, b->cur_round)) return -1;
   b->curve_assert_valid(b->pts[p].x, b->pts[p].y);
   return 0;
 }

@@ -32,7 +32,8 @@ enum PrepOpcode : uint8_t { OP_ADD = 0, OP_SUB = 1, OP_MUL = 2, OP_INV = 3, OP_G
 struct PrepOp {
   uint8_t opcode;
   uint8_t mod;
-  uint16_t pad;     // OP_ADDMANY: number of summands, stored at extra_refs[a.boff ...]
+  uint8_t pad;      // OP_ADDMANY: number of summands, stored at extra_refs[a.boff ...]
+  uint8_t round;    // dependency round (see Tape::n_rounds)
   uint32_t slot;    // first output slot
   Ref a, b;
 };
@@ -52,10 +53,12 @@ struct PtOp {
   uint16_t aux;     // window index (fixed base), 2-bit digit index (msm) or input index of the BoolTarget
   int32_t p1, p2;   // point ids (ignored when the *_CUR flag is set)
   uint32_t slot;    // first output slot of this curve op's generators
+  uint32_t round;   // dependency round
 };
 
 struct InputPoint {  // per-signature affine point whose coordinates are nonnative targets
   Ref x, y;
+  uint32_t round;    // round from which the coordinates exist (loaded by that round's replay kernels)
 };
 
 struct Tape {
@@ -63,6 +66,11 @@ struct Tape {
   std::vector<uint32_t> gen_kind, gen_off;
   uint32_t n_slots = 0;
   uint32_t n_inputs = 0;            // input nonnative values (9 wires each)
+  // Rounds: a nonnative generator that consumes a coordinate of a curve-op result can only run after
+  // the chain kernels produced it.  Round r = prep ops of round r, then the curve ops of round r;
+  // values from curve ops of round r are usable by prep ops / points of round r + 1.  The built-in
+  // tapes (and most circuits) have a single round.
+  uint32_t n_rounds = 1;
   // programs
   std::vector<PrepOp> prep;
   std::vector<PtOp> ptops;
@@ -74,6 +82,7 @@ struct Tape {
   int32_t pre_pid[16];                  // msm table entries (curve_msm.rs:41-62)
   Ref fixed_scalar;                     // u1 (9 limbs) or space NONE
   Ref msm_k1, msm_k2;                   // 5 limbs each or space NONE
+  uint32_t fixed_round = 0, msm_round = 0;   // rounds of the fixed-base / msm loops (their scalars exist from then on)
   uint32_t fixed_table_base = 0;        // const point index of window 0 entry 0
   int32_t chain_begin[N_CHAINS] = {0, 0, 0}, chain_end[N_CHAINS] = {0, 0, 0};   // contiguous op ranges
 };

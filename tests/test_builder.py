@@ -127,12 +127,6 @@ def test_builder_curve_layout_matches_oracle():
 
 def test_builder_rejects_unsupported_dataflow():
     lib = pkg.load_library()
-    cb = pkg.CircuitBuilder(lib)
-    x, y = cb.add_virtual_nonnative_target(), cb.add_virtual_nonnative_target()
-    p = cb.affine_point(x, y)
-    d = cb.curve_double(p)
-    with pytest.raises(pkg.P2EError):
-        cb.mul_nonnative(P_, cb.point_x(d), x)          # nonnative op on a curve-op output
     cb2 = pkg.CircuitBuilder(lib)
     k = cb2.add_virtual_nonnative_target()
     cb2.fixed_base_curve_mul_circuit(k)
@@ -140,6 +134,49 @@ def test_builder_rejects_unsupported_dataflow():
         cb2.fixed_base_curve_mul_circuit(k)             # one per tape in this version
     with pytest.raises(pkg.P2EError):
         cb2.add_nonnative(7, k, k)                      # unknown modulus
+
+
+def build_multi_round(cb):
+    """Nonnative generators fed by curve-op outputs, and curve ops fed by those (three dependency
+    rounds): the pattern of curve_assert_valid(result) / chained gadgets in the reference's tests."""
+    x1, y1, x2, y2, k = (cb.add_virtual_nonnative_target() for _ in range(5))
+    p, q = cb.affine_point(x1, y1), cb.affine_point(x2, y2)
+    d = cb.curve_double(p)                                   # round 0
+    s = cb.curve_add(d, q)                                   # round 0
+    m = cb.mul_nonnative(P_, cb.point_x(s), x1)              # round 1 generator on a curve-op output
+    a = cb.add_nonnative(P_, m, cb.point_y(d))
+    cb.curve_assert_valid(s)                                 # round 1
+    w = cb.affine_point(cb.point_x(s), cb.point_y(s))        # round 1 point made of round-0 coordinates
+    u = cb.curve_double(w)                                   # round 1
+    v = cb.curve_add(u, d)                                   # round 1, operand from round 0
+    g = cb.glv_mul(v, k)                                     # round 2 (works on v's coordinate values)
+    z = cb.sub_nonnative(P_, cb.point_x(g), a)               # round 3
+    cb.inv_nonnative(P_, z)
+    return cb.build()
+
+
+def oracle_multi_round(P1, P2, kk):
+    m = S.SECP_P
+    wb = S.WitnessBuilder()
+    p, q = wb.constant_affine_point(P1), wb.constant_affine_point(P2)
+    d = wb.curve_double(p)
+    s = wb.curve_add(d, q)
+    mm = wb.mul_nonnative(s[0], p[0], m)
+    a = wb.add_nonnative(mm, d[1], m)
+    wb.curve_assert_valid(s)
+    u = wb.curve_double(s)
+    v = wb.curve_add(u, d)
+    g = wb.glv_mul(v, S.NN(S.limbs9(kk)))
+    z = wb.sub_nonnative(g[0], a, m)
+    wb.inv_nonnative(z, m)
+    return wb
+
+
+def test_builder_multi_round_layout_matches_oracle():
+    lib = pkg.load_library()
+    tid = build_multi_round(pkg.CircuitBuilder(lib))
+    wb = oracle_multi_round(S.pt_mul(3, S.G), S.pt_mul(5, S.G), 0x1234567)
+    assert _layout(lib, tid) == (*_oracle_layout(wb.tape), 5)
 
 
 # ------------------------------------------------------------------------------------------ GPU tier
@@ -235,4 +272,21 @@ def test_builder_misc_nonnative_witness(engine, modulus):
     assert not err.any()
     for j in range(n):
         wb = oracle_misc_nonnative([c[j] for c in cols], flags[j], m)
+        assert [int(v) for v in wit[:, j]] == wb.flat()
+
+
+@pytest.mark.gpu
+def test_builder_multi_round_witness(engine):
+    tid = build_multi_round(pkg.CircuitBuilder(engine.lib))
+    rng = random.Random(11)
+    n = 20
+    P1 = [S.pt_mul(rng.randrange(1, S.SECP_N), S.G) for _ in range(n)]
+    P2 = [S.pt_mul(rng.randrange(1, S.SECP_N), S.G) for _ in range(n)]
+    ks = [rng.randrange(1, S.SECP_N) for _ in range(n)]
+    ins = [W.ints_to_limbs([p[0] for p in P1]), W.ints_to_limbs([p[1] for p in P1]),
+           W.ints_to_limbs([p[0] for p in P2]), W.ints_to_limbs([p[1] for p in P2]), W.ints_to_limbs(ks)]
+    wit, err = engine.tape_witness(tid, ins)
+    assert not err.any()
+    for j in range(n):
+        wb = oracle_multi_round(P1[j], P2[j], ks[j])
         assert [int(v) for v in wit[:, j]] == wb.flat()
