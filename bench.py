@@ -31,6 +31,15 @@ WORKLOAD_NAMES = {
     "eval": "MulNonnativeGate eval_unfiltered_base_batch over 2^20 Goldilocks LDE rows",
     "glv": "glv_mul witness chain (GLV decomposition + 2-scalar MSM) for 2^16 secp256k1 scalars, P = 7G",
     "evalcs": "CheckSumGate eval_unfiltered_base_batch over 2^20 Goldilocks LDE rows",
+    "evalrc": "u29 range-check gate (9 limbs, 3-bit aux limbs; plonky2_ux spec unpinned) eval over 2^20 Goldilocks LDE rows",
+    "evalcmp": "u29 comparison gate (2-bit chunks; plonky2_ux spec unpinned) eval over 2^20 Goldilocks LDE rows",
+    "evaladd": "u29 add-many gate (3 addends, 5 ops / row; plonky2_ux spec unpinned) eval over 2^20 Goldilocks LDE rows",
+}
+# plonky2_ux eval workloads: (gate, bits, limb_bits, count, num_addends, kernel)
+UX_WORKLOADS = {
+    "evalrc": (0, 29, 3, 9, 0, "k_eval_ux_range_check<3>"),
+    "evalcmp": (1, 29, 2, 1, 0, "k_eval_ux_comparison<2>"),
+    "evaladd": (2, 29, 2, 5, 3, "k_eval_ux_add_many<2>"),
 }
 METRICS = {
     "ecdsa": ("ecdsa_circuit_witnesses_per_s", "witnesses/s"),
@@ -38,6 +47,9 @@ METRICS = {
     "eval": ("mul_nonnative_gate_rows_per_s", "rows/s"),
     "glv": ("glv_mul_witness_chains_per_s", "chains/s"),
     "evalcs": ("check_sum_gate_rows_per_s", "rows/s"),
+    "evalrc": ("ux_range_check_gate_rows_per_s", "rows/s"),
+    "evalcmp": ("ux_comparison_gate_rows_per_s", "rows/s"),
+    "evaladd": ("ux_add_many_gate_rows_per_s", "rows/s"),
 }
 
 
@@ -215,6 +227,25 @@ class Bench:
                 assert rc == 0, eng.last_error()
             return dict(step=step, step_e2e=step_e2e, units=n, h2d=33 * 8 * n, d2h=17 * 8 * n, alg_bytes=400 * n,
                         kernel="k_eval_check_sum", launches=1, err=None, dtype="u64 (Goldilocks)", keep=(wd, od, hw, ho))
+        if wl in UX_WORKLOADS:
+            gate, bits, lb, count, na, kname = UX_WORKLOADS[wl]
+            nw, nc, _ = eng.ux_gate_shape(gate, bits, lb, count, na)
+            n = 1 << 20
+            w = W.random_goldilocks(W.SEED + 11 + gate + self.rank, nw, n)
+            wd = self.dev(w)
+            od = torch.empty((nc, n), dtype=torch.int64, device="cuda")
+
+            def step():
+                rc = lib.p2e_eval_ux_dev(gate, bits, lb, count, na, n, wd.data_ptr(), n, od.data_ptr(), n, sp)
+                assert rc == 0, eng.last_error()
+            hw = self.pinned(w)
+            ho = torch.empty((nc, n), dtype=torch.int64).pin_memory()
+
+            def step_e2e():
+                rc = lib.p2e_eval_ux(gate, bits, lb, count, na, n, hw.data_ptr(), ho.data_ptr())
+                assert rc == 0, eng.last_error()
+            return dict(step=step, step_e2e=step_e2e, units=n, h2d=nw * 8 * n, d2h=nc * 8 * n, alg_bytes=(nw + nc) * 8 * n,
+                        kernel=kname, launches=1, err=None, dtype="u64 (Goldilocks)", keep=(wd, od, hw, ho))
         if wl == "glv":
             # device-resident only at full size (the 2^16 x 61.6k-slot witness is 32 GB); e2e on a 4096-scalar slice
             n = 1 << 16
@@ -428,7 +459,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("P2E_BENCH_WORKLOAD", "ecdsa"), choices=["mulmod", "ecdsa", "eval", "glv", "evalcs"])
+    ap.add_argument("--workload", default=os.environ.get("P2E_BENCH_WORKLOAD", "ecdsa"), choices=list(WORKLOAD_NAMES))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
@@ -446,7 +477,7 @@ def main():
     main_res = b.measure(wl, args.steps, args.warmup, e2e_steps=max(2, min(args.steps, 5)), sample_clocks=True)
     secondary = {}
     if not args.no_secondary:
-        for w2 in ("mulmod", "eval", "evalcs", "glv", "ecdsa"):
+        for w2 in ("mulmod", "eval", "evalcs", "evalrc", "evalcmp", "evaladd", "glv", "ecdsa"):
             if w2 != wl:
                 try:
                     r2 = b.measure(w2, steps=min(args.steps, 20) if w2 != "glv" else 3, warmup=3, e2e_steps=2)

@@ -162,10 +162,10 @@ int p2e_tape_witness(int tape, size_t n, const uint64_t* const* inputs, uint64_t
  * handles are small non-negative ints; every call returns a handle (or 0) on success and a negative
  * number on error.  p2e_builder_finish() registers the tape and returns its id (>= 16) for
  * p2e_tape_*().  Inputs are [9][n] wire matrices in p2e_builder_input() order.
- * Limits of this version: nonnative ops may not consume coordinates of curve-op results (only
- * connect_nonnative may); one fixed_base_curve_mul and one curve_msm / glv_mul per tape; the
- * BoolTarget of curve_conditional_add must be an input; msm operands may not be curve-op results of
- * the fixed-base or join chains. */
+ * Generators that consume coordinates of curve-op results (and points made of such values) are
+ * scheduled in a later dependency round automatically.
+ * Limits of this version: one fixed_base_curve_mul and one curve_msm / glv_mul per tape; BoolTargets
+ * must be inputs. */
 int p2e_builder_new(void);
 int p2e_builder_free(int builder);
 int p2e_builder_input(int builder);                                            /* add_virtual_nonnative_target */
@@ -229,6 +229,43 @@ int p2e_glv_mul_witness_dev(size_t n, const uint64_t* k, const uint64_t* px, con
                             void* stream);
 int p2e_glv_mul_witness(size_t n, const uint64_t* k, const uint64_t* px, const uint64_t* py,
                         uint64_t* out, uint32_t* err);
+
+/* ---- plonky2_ux gates (range check, comparison, add-many, subtraction, arithmetic) ------------
+ * PARITY UNPINNED: plonky2_ux is an un-vendored, un-pinned git dependency of the reference
+ * (Cargo.toml:19); these entry points implement the spec restated in oracle/ux_spec.py (upstream
+ * plonky2_u32's gates generalised to `bits`-wide limbs) with every geometry parameter an argument.
+ * They stand in for Gate::eval_unfiltered_base_batch / SimpleGenerator::run_once of the gates behind
+ *   range_check_ux_circuit  gadgets/nonnative.rs:330-331,373,454-460   (P2E_UX_RANGE_CHECK)
+ *   list_le_ux_circuit      gadgets/biguint.rs:222-229                 (P2E_UX_COMPARISON)
+ *   add_many_ux             gadgets/biguint.rs:261                     (P2E_UX_ADD_MANY)
+ *   sub_ux                  gadgets/biguint.rs:284                     (P2E_UX_SUBTRACTION)
+ *   mul_ux                  gadgets/biguint.rs:305,335                 (P2E_UX_ARITHMETIC)
+ * Geometry: `bits` = width of a UXTarget (29 / 34 in the reference; comparison: num_bits);
+ * `limb_bits` = width of the aux limbs / chunks (1..4); `count` = input limbs per row (range check),
+ * ops per row (add-many, subtraction, arithmetic) or 1 (comparison); `num_addends` (add-many only).
+ * Wire maps and constraint order: oracle/ux_spec.py.
+ *   p2e_ux_gate_shape : num_wires / num_constraints of the gate row, num_inputs of its generator.
+ *   p2e_eval_ux       : wires [num_wires][stride] -> out [num_constraints][stride].
+ *   p2e_ux_witness    : inputs [num_inputs][stride] -> complete gate rows [num_wires][stride], err [n].
+ *     inputs per gate: range check: the limbs; comparison: first, second; add-many: per op the
+ *     addends then the carry-in; subtraction: per op x, y, borrow-in; arithmetic: per op m0, m1, addend.
+ *     err[i] has P2E_ERR_LIMB_RANGE when a value does not fit its limbs (unsatisfiable row). */
+#define P2E_UX_RANGE_CHECK 0
+#define P2E_UX_COMPARISON 1
+#define P2E_UX_ADD_MANY 2
+#define P2E_UX_SUBTRACTION 3
+#define P2E_UX_ARITHMETIC 4
+int p2e_ux_gate_shape(int gate, int bits, int limb_bits, int count, int num_addends, int* num_wires,
+                      int* num_constraints, int* num_inputs);
+int p2e_eval_ux_dev(int gate, int bits, int limb_bits, int count, int num_addends, size_t n,
+                    const uint64_t* wires, size_t in_stride, uint64_t* out, size_t out_stride, void* stream);
+int p2e_eval_ux(int gate, int bits, int limb_bits, int count, int num_addends, size_t n,
+                const uint64_t* wires, uint64_t* out);
+int p2e_ux_witness_dev(int gate, int bits, int limb_bits, int count, int num_addends, size_t n,
+                       const uint64_t* inputs, size_t in_stride, uint64_t* row, size_t out_stride,
+                       uint32_t* err, void* stream);
+int p2e_ux_witness(int gate, int bits, int limb_bits, int count, int num_addends, size_t n,
+                   const uint64_t* inputs, uint64_t* row, uint32_t* err);
 
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* Per-kernel timing of the chain entry points: when enabled, CUDA events are recorded on the

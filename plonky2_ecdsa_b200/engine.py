@@ -34,6 +34,8 @@ ERR_LIMBS_OVERFLOW = 64
 ERR_CONNECT = 128
 ERR_INTERNAL = 256
 
+UX_RANGE_CHECK, UX_COMPARISON, UX_ADD_MANY, UX_SUBTRACTION, UX_ARITHMETIC = 0, 1, 2, 3, 4
+
 MUL_OUT_R, MUL_OUT_Q, MUL_OUT_CHECK_SUM, MUL_OUT_CARRY, MUL_OUT_ROWS = 0, 9, 18, 35, 51
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -118,6 +120,11 @@ SIGNATURES = {
     "p2e_glv_mul_tape_layout": (_sz, [_vp, _vp]),
     "p2e_glv_mul_witness_dev": (_int, [_sz, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),
     "p2e_glv_mul_witness": (_int, [_sz, _vp, _vp, _vp, _vp, _vp]),
+    "p2e_ux_gate_shape": (_int, [_int, _int, _int, _int, _int, _vp, _vp, _vp]),
+    "p2e_eval_ux_dev": (_int, [_int, _int, _int, _int, _int, _sz, _vp, _sz, _vp, _sz, _vp]),
+    "p2e_eval_ux": (_int, [_int, _int, _int, _int, _int, _sz, _vp, _vp]),
+    "p2e_ux_witness_dev": (_int, [_int, _int, _int, _int, _int, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_ux_witness": (_int, [_int, _int, _int, _int, _int, _sz, _vp, _vp, _vp]),
     "p2e_set_profiling": (_int, [_int]),
     "p2e_last_kernel_times": (_int, [_vp, _int]),
     "p2e_bench_imad": (ctypes.c_double, [_int, _int]),
@@ -371,6 +378,57 @@ class Engine:
         out = np.empty((17, n), dtype=np.uint64)
         self._check(self.lib.p2e_eval_check_sum(n, _ptr(w), _ptr(out)))
         return out
+
+    # ---------------------------------------------------------------- plonky2_ux gates (parity unpinned)
+    def ux_gate_shape(self, gate, bits, limb_bits, count=1, num_addends=0):
+        """(num_wires, num_constraints, num_inputs) of a plonky2_ux gate row."""
+        nw, nc, ni = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._check(self.lib.p2e_ux_gate_shape(gate, bits, limb_bits, count, num_addends, ctypes.addressof(nw),
+                                               ctypes.addressof(nc), ctypes.addressof(ni)))
+        return nw.value, nc.value, ni.value
+
+    def ux_gate_witness(self, gate, inputs, bits, limb_bits, count=1, num_addends=0):
+        """The gate's generator (SimpleGenerator::run_once) over n instances: inputs [num_inputs][n] ->
+        (complete gate rows [num_wires][n], err [n])."""
+        nw, _, ni = self.ux_gate_shape(gate, bits, limb_bits, count, num_addends)
+        x = _host_u64(inputs, ni)
+        n = x.shape[1]
+        row = np.empty((nw, n), dtype=np.uint64)
+        err = np.empty(n, dtype=np.uint32)
+        self._check(self.lib.p2e_ux_witness(gate, bits, limb_bits, count, num_addends, n, _ptr(x), _ptr(row), _ptr(err)))
+        return row, err
+
+    def eval_ux_gate(self, gate, wires, bits, limb_bits, count=1, num_addends=0):
+        """Gate::eval_unfiltered_base_batch: wires [num_wires][n_rows] -> constraints [num_constraints][n_rows]."""
+        nw, nc, _ = self.ux_gate_shape(gate, bits, limb_bits, count, num_addends)
+        w = _host_u64(wires, nw)
+        n = w.shape[1]
+        out = np.empty((nc, n), dtype=np.uint64)
+        self._check(self.lib.p2e_eval_ux(gate, bits, limb_bits, count, num_addends, n, _ptr(w), _ptr(out)))
+        return out
+
+    def range_check_ux_witness(self, limbs, bits=29, aux_bits=3):
+        """range_check_ux_circuit::<BITS>(limbs) (gadgets/nonnative.rs:454-460): one gate row per call."""
+        limbs = _host_u64(limbs)
+        return self.ux_gate_witness(UX_RANGE_CHECK, limbs, bits, aux_bits, limbs.shape[0])
+
+    def eval_range_check_ux_gate(self, wires, num_input_limbs, bits=29, aux_bits=3):
+        return self.eval_ux_gate(UX_RANGE_CHECK, wires, bits, aux_bits, num_input_limbs)
+
+    def comparison_ux_witness(self, first, second, num_bits=29, chunk_bits=2):
+        """One ComparisonGate row of list_le_ux_circuit (gadgets/biguint.rs:222-229): result = first <= second."""
+        x = np.stack([np.asarray(first, dtype=np.uint64), np.asarray(second, dtype=np.uint64)])
+        return self.ux_gate_witness(UX_COMPARISON, x, num_bits, chunk_bits, 1)
+
+    def eval_comparison_ux_gate(self, wires, num_bits=29, chunk_bits=2):
+        return self.eval_ux_gate(UX_COMPARISON, wires, num_bits, chunk_bits, 1)
+
+    def add_many_ux_witness(self, inputs, num_addends=3, num_ops=5, bits=29, limb_bits=2):
+        """add_many_ux (gadgets/biguint.rs:261): per op the addends then the carry-in."""
+        return self.ux_gate_witness(UX_ADD_MANY, inputs, bits, limb_bits, num_ops, num_addends)
+
+    def eval_add_many_ux_gate(self, wires, num_addends=3, num_ops=5, bits=29, limb_bits=2):
+        return self.eval_ux_gate(UX_ADD_MANY, wires, bits, limb_bits, num_ops, num_addends)
 
     # ---------------------------------------------------------------- generic gadget tapes
     (TAPE_ECDSA, TAPE_GLV_MUL, TAPE_CURVE_ADD, TAPE_CURVE_DOUBLE, TAPE_CURVE_COND_ADD, TAPE_FIXED_BASE_MUL,
