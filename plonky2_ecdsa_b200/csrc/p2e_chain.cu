@@ -1248,6 +1248,25 @@ static unsigned inv_groups() {
   return (unsigned)g;
 }
 
+// threads per block of the two full-GPU kernels (K3, K4): smaller blocks pack better next to the
+// resident one-warp blocks of other batches' K0-K2 (register file granularity)
+static unsigned wide_tpb() {
+  static unsigned v = 0;
+  if (!v) {
+    const char* e = getenv("P2E_CHAIN_WIDE_TPB");
+    v = e ? (unsigned)atoi(e) : 128u;
+    if (v != 32 && v != 64 && v != 128) v = 128;
+  }
+  return v;
+}
+
+// diagnostic only (wrong results when not 63): bit mask of the kernels to launch
+// 1 prep, 2 replay + join, 4 invert, 8 affine, 16 expand, 32 checks
+static unsigned phase_mask() {
+  const char* e = getenv("P2E_CHAIN_PHASES");     // read per call: the diagnostic script flips it in-process
+  return e ? (unsigned)atoi(e) : 63u;
+}
+
 static size_t chunk_capacity() {
   const char* e = getenv("P2E_CHAIN_CHUNK");
   size_t v = e ? (size_t)atoll(e) : 0;
@@ -1303,7 +1322,7 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
     for (int k = 0; k < MAX_TAPE_INPUTS; k++) A.in[k] = (k < n_in) ? ins[k] + c0 : nullptr;
     A.out = out + c0;
     A.err = err + c0;
-    unsigned g32 = (unsigned)((cn + 31) / 32), g128 = (unsigned)((cn + 127) / 128);
+    unsigned g32 = (unsigned)((cn + 31) / 32);
     if (g_profiling && c0 == 0) {
       for (auto e : g_events) cudaEventDestroy(e);
       g_events.clear();
@@ -1311,6 +1330,7 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
     const bool prof = g_profiling && c0 == 0;
     if (prof) prof_mark(st);
     const int n_rounds = (int)t.n_rounds;
+    const unsigned pm = phase_mask();
     for (int round = 0; round < n_rounds; round++) {
       // Round r: generators of round r (K0), then the curve ops of round r (K1-K4).  A later round
       // consumes coordinates written by this round's expansion, so it waits for the low-priority stream.
@@ -1319,10 +1339,11 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
         P2E_CUDA(cudaEventRecord(arena->ev_out, s_lo));
         P2E_CUDA(cudaStreamWaitEvent(s_hi, arena->ev_out, 0));
       }
-      k_prep<<<g32, 32, 0, s_hi>>>(A);
+      if (pm & 1) k_prep<<<g32, 32, 0, s_hi>>>(A);
       if (prof) prof_mark(st);
       if (no) {
-        if (replay_mode() == 2) {
+        if (!(pm & 2)) {
+        } else if (replay_mode() == 2) {
           const unsigned g_duo = (unsigned)((2 * cn + 63) / 64);
           k_chain_replay_duo<<<dim3(g_duo, 2), 64, 0, s_hi>>>(A, 0);      // 2 lanes per (signature, chain)
           if (prof) prof_mark(st);
@@ -1337,22 +1358,23 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
           if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g32, 1), 32, 0, s_hi>>>(A, 2);   // join
         }
         if (prof) prof_mark(st);
-        k_chain_invert<<<dim3(g32, inv_groups()), 32, 0, s_hi>>>(A);
+        if (pm & 4) k_chain_invert<<<dim3(g32, inv_groups()), 32, 0, s_hi>>>(A);
         if (prof) prof_mark(st);
         if (split) {
           P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
           P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
         }
-        k_chain_affine<<<dim3(g128, (unsigned)no), 128, 0, s_lo>>>(A);
+        const unsigned tpb = wide_tpb(), gw = (unsigned)((cn + tpb - 1) / tpb);
+        if (pm & 8) k_chain_affine<<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
         if (prof) prof_mark(st);
-        k_chain_expand<<<dim3(g128, (unsigned)no), 128, 0, s_lo>>>(A);
+        if (pm & 16) k_chain_expand<<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
         if (prof) prof_mark(st);
       } else if (split) {
         P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
         P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
       }
     }
-    k_chain_checks<<<g32, 32, 0, s_lo>>>(A);
+    if (pm & 32) k_chain_checks<<<g32, 32, 0, s_lo>>>(A);
     if (prof) prof_mark(st);
     if (split && c0 + cap < n) {
       // next chunk reuses the scratch: its K0-K2 must not start before this chunk's K3-K5 are done

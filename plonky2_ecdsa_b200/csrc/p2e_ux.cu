@@ -78,24 +78,59 @@ static int ux_shape(int gate, int bits, int lb, int count, int na, UxShape* s) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Goldilocks helpers
+// Lazy Goldilocks for the evaluators.  Wires are canonical; intermediates are ANY u64 congruent to
+// the value ("any"); every stored constraint is canonicalised once (glc).  The corrections use the
+// carry flag (sub.cc / subc, add.cc / addc) instead of 64-bit compares + selects, which is what the
+// range products were spending most of their ALU slots on.
+//   glm(any, any) -> any        gla(any, canonical) -> any        gls(any, canonical) -> any
+__device__ __forceinline__ u64 gl_red_lazy(u64 lo, u64 hi) {   // (hi:lo) mod P, result < 2^64
+  const u32 hh = (u32)(hi >> 32), hl = (u32)hi;
+  u64 t0, r;
+  u32 b, c;
+  asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(t0), "=r"(b) : "l"(lo), "l"((u64)hh));
+  t0 -= (u64)b;                                  // b = 0xffffffff = 2^64 mod P on borrow: + P
+  const u64 t1 = ((u64)hl << 32) - hl;           // hl * (2^32 - 1)
+  asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(t0), "l"(t1));
+  return r + (u64)(0u - c);                      // 2^64 = 2^32 - 1 (mod P) on carry
+}
+__device__ __forceinline__ u64 glm(u64 a, u64 b) { return gl_red_lazy(a * b, __umul64hi(a, b)); }
+__device__ __forceinline__ u64 gla(u64 a, u64 b) {             // b canonical
+  u64 r;
+  u32 c;
+  asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(a), "l"(b));
+  return r + (u64)(0u - c);
+}
+__device__ __forceinline__ u64 gls(u64 a, u64 b) {             // b canonical
+  u64 r;
+  u32 bw;
+  asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(r), "=r"(bw) : "l"(a), "l"(b));
+  return r - (u64)bw;
+}
+__device__ __forceinline__ u64 glc(u64 a) {                    // any -> canonical
+  u64 t;
+  u32 c;
+  asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(t), "=r"(c) : "l"(a), "l"(GL_EPS));   // a - P, carry iff a >= P
+  return c ? t : a;
+}
 template <int A>
-__device__ __forceinline__ u64 gl_shl(u64 v) { return gl_reduce128(v << A, v >> (64 - A)); }   // v * 2^A
-__device__ __forceinline__ u64 gl_shl_rt(u64 v, int a) { return gl_reduce128(v << a, v >> (64 - a)); }
+__device__ __forceinline__ u64 gl_shl(u64 v) { return gl_red_lazy(v << A, v >> (64 - A)); }     // any * 2^A -> any
+__device__ __forceinline__ u64 gl_shl_rt(u64 v, int a) { return gl_red_lazy(v << a, v >> (64 - a)); }
 
+// prod_{x < 2^A} (v - x) for a canonical wire v -> any
 template <int A>
 __device__ __forceinline__ u64 range_product(u64 v) {
   constexpr u64 B = 1ull << A;
-  u64 u = gl_mul(v, gl_sub(v, B - 1));
+  const u64 u = glm(v, gls(v, B - 1));            // (v - x)(v - (B-1-x)) = u + x (B-1-x)
+  if (A == 1) return u;
   if (A == 3) {
-    // u (u+6)(u+10)(u+12) = w (w + 4u + 60) with w = u (u + 12): three products for the degree-8 polynomial
-    const u64 w = gl_mul(u, gl_add(u, 12));
-    const u64 u2 = gl_add(u, u);
-    return gl_mul(w, gl_add(gl_add(w, gl_add(u2, u2)), 60));
+    // u (u+6)(u+10)(u+12) = (z^2 - 36)(z^2 + 4 z), z = u + 6: three products for the degree-8 polynomial
+    const u64 z = gla(u, 6);
+    const u64 zz = glm(z, z);
+    return glm(gls(zz, 36), gla(zz, glc(gl_shl<2>(z))));
   }
   u64 acc = u;
 #pragma unroll
-  for (u64 x = 1; x < B / 2; x++) acc = gl_mul(acc, gl_add(u, x * (B - 1 - x)));
+  for (u64 x = 1; x < B / 2; x++) acc = glm(acc, gla(u, x * (B - 1 - x)));
   return acc;
 }
 
@@ -127,10 +162,10 @@ k_eval_ux_range_check(UxShape s, size_t n, const u64* __restrict__ wires, size_t
 #pragma unroll 4
   for (int j = s.n_aux - 1; j >= 0; j--) {
     const u64 a = W(aux0 + j);
-    O(c0 + 1 + j) = range_product<A>(a);
-    acc = gl_add(gl_shl<A>(acc), a);
+    O(c0 + 1 + j) = glc(range_product<A>(a));
+    acc = gla(gl_shl<A>(acc), a);
   }
-  O(c0) = gl_sub(acc, W(u));
+  O(c0) = glc(gls(acc, W(u)));
 }
 
 template <int A>
@@ -141,36 +176,36 @@ k_eval_ux_comparison(UxShape s, size_t n, const u64* __restrict__ wires, size_t 
   const int nc = s.n_aux;
   u64 fa = 0, sa = 0;
   for (int c = nc - 1; c >= 0; c--) {
-    fa = gl_add(gl_shl<A>(fa), W(4 + c));
-    sa = gl_add(gl_shl<A>(sa), W(4 + nc + c));
+    fa = gla(gl_shl<A>(fa), W(4 + c));
+    sa = gla(gl_shl<A>(sa), W(4 + nc + c));
   }
-  O(0) = gl_sub(fa, W(0));
-  O(1) = gl_sub(sa, W(1));
-  u64 msd = 0;
+  O(0) = glc(gls(fa, W(0)));
+  O(1) = glc(gls(sa, W(1)));
+  u64 msd = 0;                                     // canonical throughout
 #pragma unroll 2
   for (int c = 0; c < nc; c++) {
     const u64 f = W(4 + c), sc = W(4 + nc + c);
     const u64 dummy = W(4 + 2 * nc + c), eq = W(4 + 3 * nc + c), inter = W(4 + 4 * nc + c);
-    const u64 diff = gl_sub(sc, f);
-    const u64 neq = gl_sub(1, eq);
-    O(2 + 5 * c) = range_product<A>(f);
-    O(3 + 5 * c) = range_product<A>(sc);
-    O(4 + 5 * c) = gl_sub(gl_mul(diff, dummy), neq);
-    O(5 + 5 * c) = gl_mul(eq, diff);
-    O(6 + 5 * c) = gl_sub(inter, gl_mul(eq, msd));
-    msd = gl_add(inter, gl_mul(neq, diff));
+    const u64 diff = gls(sc, f);                   // canonical - canonical -> canonical
+    const u64 neq = gls(1, eq);
+    O(2 + 5 * c) = glc(range_product<A>(f));
+    O(3 + 5 * c) = glc(range_product<A>(sc));
+    O(4 + 5 * c) = glc(gls(glm(diff, dummy), neq));
+    O(5 + 5 * c) = glc(glm(eq, diff));
+    O(6 + 5 * c) = gls(inter, glc(glm(eq, msd)));
+    msd = glc(gla(glm(neq, diff), inter));
   }
   const u64 msd_w = W(3);
-  O(2 + 5 * nc) = gl_sub(msd_w, msd);
+  O(2 + 5 * nc) = gls(msd_w, msd);
   u64 comb = 0, top = 0;
   for (int b = A; b >= 0; b--) {
     const u64 bit = W(4 + 5 * nc + b);
     if (b == A) top = bit;
-    O(3 + 5 * nc + b) = gl_mul(bit, gl_sub(1, bit));
-    comb = gl_add(gl_add(comb, comb), bit);
+    O(3 + 5 * nc + b) = glc(glm(bit, gls(1, bit)));
+    comb = gla(gl_shl<1>(comb), bit);
   }
-  O(4 + 5 * nc + A) = gl_sub(gl_add(1ull << A, msd_w), comb);
-  O(5 + 5 * nc + A) = gl_sub(W(2), top);
+  O(4 + 5 * nc + A) = glc(gls(gla(1ull << A, msd_w), glc(comb)));
+  O(5 + 5 * nc + A) = gls(W(2), top);
 }
 
 template <int A>
@@ -180,19 +215,19 @@ k_eval_ux_add_many(UxShape s, size_t n, const u64* __restrict__ wires, size_t is
   const int r0 = (s.na + 3) * u, nl = s.n_aux + s.n_carry;
   const int l0 = (s.na + 3) * s.count + nl * u, c0 = (3 + nl) * u;
   u64 computed = W(r0 + s.na);
-  for (int j = 0; j < s.na; j++) computed = gl_add(computed, W(r0 + j));
+  for (int j = 0; j < s.na; j++) computed = gla(computed, W(r0 + j));
   const u64 res = W(r0 + s.na + 1), car = W(r0 + s.na + 2);
-  O(c0) = gl_sub(gl_add(gl_shl_rt(car, s.bits), res), computed);
+  O(c0) = glc(gls(gla(gl_shl_rt(car, s.bits), res), glc(computed)));
   u64 cres = 0, ccar = 0;
 #pragma unroll 4
   for (int j = nl - 1; j >= 0; j--) {
     const u64 limb = W(l0 + j);
-    O(c0 + 1 + (nl - 1 - j)) = range_product<A>(limb);
-    if (j < s.n_aux) cres = gl_add(gl_shl<A>(cres), limb);
-    else ccar = gl_add(gl_shl<A>(ccar), limb);
+    O(c0 + 1 + (nl - 1 - j)) = glc(range_product<A>(limb));
+    if (j < s.n_aux) cres = gla(gl_shl<A>(cres), limb);
+    else ccar = gla(gl_shl<A>(ccar), limb);
   }
-  O(c0 + 1 + nl) = gl_sub(cres, res);
-  O(c0 + 2 + nl) = gl_sub(ccar, car);
+  O(c0 + 1 + nl) = glc(gls(cres, res));
+  O(c0 + 2 + nl) = glc(gls(ccar, car));
 }
 
 template <int A>
@@ -201,17 +236,17 @@ k_eval_ux_subtraction(UxShape s, size_t n, const u64* __restrict__ wires, size_t
   UX_ROW();
   const int nl = s.n_aux, l0 = 5 * s.count + nl * u, c0 = (3 + nl) * u;
   const u64 x = W(5 * u), y = W(5 * u + 1), bin = W(5 * u + 2), res = W(5 * u + 3), bout = W(5 * u + 4);
-  const u64 init = gl_sub(gl_sub(x, y), bin);
-  O(c0) = gl_sub(res, gl_add(init, gl_shl_rt(bout, s.bits)));
+  const u64 init = gls(gls(x, y), bin);            // canonical
+  O(c0) = gls(res, glc(gla(gl_shl_rt(bout, s.bits), init)));
   u64 comb = 0;
 #pragma unroll 4
   for (int j = nl - 1; j >= 0; j--) {
     const u64 limb = W(l0 + j);
-    O(c0 + 1 + (nl - 1 - j)) = range_product<A>(limb);
-    comb = gl_add(gl_shl<A>(comb), limb);
+    O(c0 + 1 + (nl - 1 - j)) = glc(range_product<A>(limb));
+    comb = gla(gl_shl<A>(comb), limb);
   }
-  O(c0 + 1 + nl) = gl_sub(comb, res);
-  O(c0 + 2 + nl) = gl_mul(bout, gl_sub(1, bout));
+  O(c0 + 1 + nl) = glc(gls(comb, res));
+  O(c0 + 2 + nl) = glc(glm(bout, gls(1, bout)));
 }
 
 template <int A>
@@ -220,21 +255,21 @@ k_eval_ux_arithmetic(UxShape s, size_t n, const u64* __restrict__ wires, size_t 
   UX_ROW();
   const int half = s.n_aux, nl = 2 * half, l0 = 6 * s.count + nl * u, c0 = (4 + nl) * u;
   const u64 m0 = W(6 * u), m1 = W(6 * u + 1), add = W(6 * u + 2), lo = W(6 * u + 3), hi = W(6 * u + 4), inv = W(6 * u + 5);
-  const u64 computed = gl_add(gl_mul(m0, m1), add);
+  const u64 computed = glc(gla(glm(m0, m1), add));
   const u64 ux_max = (1ull << s.bits) - 1;
-  const u64 hi_not_max = gl_sub(gl_mul(inv, gl_sub(ux_max, hi)), 1);
-  O(c0) = gl_mul(hi_not_max, lo);
-  O(c0 + 1) = gl_sub(gl_add(gl_shl_rt(hi, s.bits), lo), computed);
+  const u64 hi_not_max = gls(glm(inv, gls(ux_max, hi)), 1);
+  O(c0) = glc(glm(hi_not_max, lo));
+  O(c0 + 1) = glc(gls(gla(gl_shl_rt(hi, s.bits), lo), computed));
   u64 clo = 0, chi = 0;
 #pragma unroll 4
   for (int j = nl - 1; j >= 0; j--) {
     const u64 limb = W(l0 + j);
-    O(c0 + 2 + (nl - 1 - j)) = range_product<A>(limb);
-    if (j < half) clo = gl_add(gl_shl<A>(clo), limb);
-    else chi = gl_add(gl_shl<A>(chi), limb);
+    O(c0 + 2 + (nl - 1 - j)) = glc(range_product<A>(limb));
+    if (j < half) clo = gla(gl_shl<A>(clo), limb);
+    else chi = gla(gl_shl<A>(chi), limb);
   }
-  O(c0 + 2 + nl) = gl_sub(clo, lo);
-  O(c0 + 3 + nl) = gl_sub(chi, hi);
+  O(c0 + 2 + nl) = glc(gls(clo, lo));
+  O(c0 + 3 + nl) = glc(gls(chi, hi));
 }
 
 // ------------------------------------------------------------------------------------------
