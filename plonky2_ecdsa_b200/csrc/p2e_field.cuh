@@ -126,6 +126,42 @@ P2E_HD u64 gl_mul(u64 a, u64 b) { return gl_reduce128(a * b, umulhi64(a, b)); }
 // canonical Goldilocks representative of a signed integer |v| < 2^63
 P2E_HD u64 gl_from_i64(i64 v) { return (u64)v + ((u64)(v >> 63) & (0ull - GL_EPS)); }   // + P when negative (mod 2^64)
 
+#ifdef __CUDACC__
+// Lazy Goldilocks for the constraint evaluators: wires are canonical, intermediates are ANY u64
+// congruent to the value, every stored constraint is canonicalised once (glc).  The corrections use
+// the carry flag (sub.cc / subc, add.cc / addc) instead of 64-bit compares + selects.
+//   glm(any, any) -> any        gla(any, canonical) -> any        gls(any, canonical) -> any
+__device__ __forceinline__ u64 gl_red_lazy(u64 lo, u64 hi) {   // (hi:lo) mod P, result < 2^64
+  const u32 hh = (u32)(hi >> 32), hl = (u32)hi;
+  u64 t0, r;
+  u32 b, c;
+  asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(t0), "=r"(b) : "l"(lo), "l"((u64)hh));
+  t0 -= (u64)b;                                  // b = 0xffffffff = 2^64 mod P on borrow: + P
+  const u64 t1 = ((u64)hl << 32) - hl;           // hl * (2^32 - 1)
+  asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(t0), "l"(t1));
+  return r + (u64)(0u - c);                      // 2^64 = 2^32 - 1 (mod P) on carry
+}
+__device__ __forceinline__ u64 glm(u64 a, u64 b) { return gl_red_lazy(a * b, __umul64hi(a, b)); }
+__device__ __forceinline__ u64 gla(u64 a, u64 b) {             // b canonical
+  u64 r;
+  u32 c;
+  asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(a), "l"(b));
+  return r + (u64)(0u - c);
+}
+__device__ __forceinline__ u64 gls(u64 a, u64 b) {             // b canonical
+  u64 r;
+  u32 bw;
+  asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(r), "=r"(bw) : "l"(a), "l"(b));
+  return r - (u64)bw;
+}
+__device__ __forceinline__ u64 glc(u64 a) {                    // any -> canonical
+  u64 t;
+  u32 c;
+  asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(t), "=r"(c) : "l"(a), "l"(GL_EPS));   // a - P, carry iff a >= P
+  return c ? t : a;
+}
+#endif
+
 // ------------------------------------------------------------------------------------------
 // limb helpers (u32 limbs are always < 2^29 unless stated)
 P2E_HD void set_zero9(u32 (&a)[NL]) {
