@@ -284,7 +284,7 @@ class Bench:
         # Independent batches are enqueued round-robin on S streams (async *_dev API, one output
         # buffer + one scratch arena per stream) so the latency-bound per-signature kernels of one
         # batch overlap the bandwidth-bound expansion of another.
-        S = max(1, int(os.environ.get("P2E_BENCH_STREAMS", "4")))
+        S = max(1, int(os.environ.get("P2E_BENCH_STREAMS", "8")))
         streams = [torch.cuda.Stream() for _ in range(S)]
         ods = [od] + [torch.empty((slots, n), dtype=torch.int64, device="cuda") for _ in range(S - 1)]
         eds = [ed] + [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(S - 1)]
