@@ -1,0 +1,53 @@
+"""One invocation of each hot kernel, for `ncu` captures (never a bench number).
+Usage: python scripts/profile_once.py ecdsa | ux | std"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import plonky2_ecdsa_b200 as pkg
+from plonky2_ecdsa_b200 import workload as W
+
+what = sys.argv[1] if len(sys.argv) > 1 else "ecdsa"
+eng = pkg.Engine(0); lib = eng.lib
+dev = lambda a: torch.from_numpy(a.view(np.int64)).cuda()
+if what == "ecdsa":
+    n = 4096
+    slots = int(lib.p2e_ecdsa_tape_slots())
+    d = W.ecdsa_workload(n, seed=W.SEED)
+    ind = [dev(d[k]) for k in ("msg", "r", "s", "pkx", "pky")]
+    od = torch.empty((slots, n), dtype=torch.int64, device="cuda")
+    ed = torch.empty(n, dtype=torch.int32, device="cuda")
+    os.environ["P2E_CHAIN_NO_PRIORITY"] = "1"
+    for _ in range(2):
+        assert lib.p2e_ecdsa_witness_dev(n, *[t.data_ptr() for t in ind], n, od.data_ptr(), n, ed.data_ptr(), None) == 0
+    eng.synchronize()
+    assert not bool(ed.any())
+elif what == "ux":
+    n = 1 << 20
+    for gate, bits, lb, count, na in [(0, 29, 3, 9, 0), (0, 34, 3, 8, 0), (1, 29, 2, 1, 0), (2, 29, 2, 5, 3), (3, 29, 2, 6, 0), (4, 29, 2, 3, 0)]:
+        nw, nc, ni = eng.ux_gate_shape(gate, bits, lb, count, na)
+        w = dev(W.random_goldilocks(W.SEED + gate, nw, n))
+        o = torch.empty((nc, n), dtype=torch.int64, device="cuda")
+        for _ in range(2):
+            assert lib.p2e_eval_ux_dev(gate, bits, lb, count, na, n, w.data_ptr(), n, o.data_ptr(), n, None) == 0
+        x = dev(W.random_goldilocks(W.SEED + 9, ni, n) & np.uint64((1 << bits) - 1))
+        row = torch.empty((nw, n), dtype=torch.int64, device="cuda")
+        e = torch.empty(n, dtype=torch.int32, device="cuda")
+        assert lib.p2e_ux_witness_dev(gate, bits, lb, count, na, n, x.data_ptr(), n, row.data_ptr(), n, e.data_ptr(), None) == 0
+        eng.synchronize()
+        del w, o, x, row
+else:
+    n = 1 << 20
+    x, y = W.mulmod_workload(n, 0, seed=W.SEED)
+    xd, yd = dev(x), dev(y)
+    od = torch.empty((pkg.MUL_OUT_ROWS, n), dtype=torch.int64, device="cuda")
+    ed = torch.empty(n, dtype=torch.int32, device="cuda")
+    w = dev(W.random_goldilocks(W.SEED, 53, n))
+    o = torch.empty((17, n), dtype=torch.int64, device="cuda")
+    for _ in range(2):
+        assert lib.p2e_mul_nonnative_witness_dev(0, n, xd.data_ptr(), yd.data_ptr(), n, od.data_ptr(), n, ed.data_ptr(), None) == 0
+        assert lib.p2e_eval_mul_nonnative_dev(0, n, w.data_ptr(), n, o.data_ptr(), n, None) == 0
+        assert lib.p2e_eval_check_sum_dev(n, w.data_ptr(), n, o.data_ptr(), n, None) == 0
+    eng.synchronize()
+eng.close()
+print("done", what)
