@@ -70,7 +70,10 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs.  Uses NVML in-process (pynvml):
+    forking `nvidia-smi` from a process that holds tens of GB of pinned memory stalls the launching
+    thread for milliseconds (page-table copy) and showed up as 2x noise in ms_per_step.  Falls back to
+    ONE long-lived `nvidia-smi --loop-ms` child started before the timed region."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -79,29 +82,76 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.max_mhz = None
         self.stop_flag = False
+        self.nvml = None
+        self.handle = None
+        self.proc = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:       # noqa: BLE001
+            self.nvml = None
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(index),
+                                              "--loop-ms=50"], stdout=subprocess.PIPE, text=True)
+            except Exception:   # noqa: BLE001
+                self.proc = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self.stop_flag:
+        if self.nvml is not None:
+            n = self.nvml
+            bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown,
+                    "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown,
+                    "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+            while not self.stop_flag:
+                try:
+                    self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    for nm, b in bits.items():
+                        if r & b:
+                            self.reasons.add(nm)
+                except Exception:       # noqa: BLE001
+                    pass
+                time.sleep(0.02)
+            return
+        if self.proc is None:
+            return
+        for line in self.proc.stdout:
+            if self.stop_flag:
+                break
             try:
-                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                f = [t.strip() for t in o.split(",")]
+                f = [t.strip() for t in line.split(",")]
                 self.samples.append(float(f[0]))
                 self.max_mhz = float(f[1])
                 for nm, v in zip(names, f[2:6]):
                     if v.lower().startswith("active"):
                         self.reasons.add(nm)
-            except Exception:
+            except Exception:           # noqa: BLE001
                 pass
-            time.sleep(0.05)
+        try:
+            self.proc.terminate()
+        except Exception:               # noqa: BLE001
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:           # noqa: BLE001
+                pass
 
     def summary(self):
         s = sorted(self.samples)
         med = s[len(s) // 2] if s else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s),
+                "how": "nvml" if self.nvml is not None else "nvidia-smi --loop-ms"}
 
 
 # ----------------------------------------------------------------------------- reference arm (CPU)
@@ -328,13 +378,15 @@ class Bench:
         torch = self.torch
         s = self.setup(wl)
         step, step_e2e = s["step"], s["step_e2e"]
-        for _ in range(warmup):
-            step()
-        self.barrier()
         sampler = None
         if sample_clocks and self.rank == 0:
-            # rank 0 only: eight concurrent nvidia-smi pollers perturb every rank's launches
+            # rank 0 only; created before the warm-up so that nothing forks inside the timed region
             sampler = ClockSampler(self.local_rank)
+        # every stream's scratch arena is allocated on its first batch: warm up at least one batch per stream
+        for _ in range(max(warmup, len(s.get("streams") or []))):
+            step()
+        self.barrier()
+        if sampler is not None:
             sampler.start()
         streams = s.get("streams") or []
 
@@ -376,8 +428,8 @@ class Bench:
             while time.time() < t_end:
                 step()
             torch.cuda.synchronize()
-            sampler.stop_flag = True
-            sampler.join()
+            sampler.stop()
+            sampler.join(timeout=2.0)
         kernel_ms = None
         if wl == "ecdsa":
             self.eng.set_profiling(True)
@@ -419,7 +471,7 @@ class Bench:
             "gpu_launches": s["launches"] * steps,
         }
         if e2e_plain_ms is not None:
-            res["e2e"]["format"] = "compact (p2e_tape_witness_compact: u32 narrow slots + u64 wide slots)"
+            res["e2e"]["format"] = "compact (p2e_tape_witness_compact: u32 narrow slots, u64 check_sum slots, 34-bit carries as u32 + packed 2-bit tops)"
             res["e2e_u64"] = {"value": s["units"] * self.world / (e2e_plain_ms * 1e-3), "unit": METRICS[wl][1],
                               "d2h_bytes_per_step": s["d2h_plain"], "ms_per_step": e2e_plain_ms,
                               "format": "plain (p2e_ecdsa_witness: u64 per slot)"}

@@ -192,12 +192,16 @@ int p2e_builder_curve_msm(int builder, int p, int q, int n, int m);            /
 int p2e_builder_glv_mul(int builder, int p, int k);                            /* glv.rs:87-104 */
 int p2e_builder_finish(int builder);
 
-/* Compact host format (cuts the PCIe bytes of the host-pointer path by ~28 %): slots that always fit
+/* Compact host format (cuts the PCIe bytes of the host-pointer path by ~38 %): slots that always fit
  * 32 bits (limbs of ADD / ADDMANY / SUB / INV / GLV tuples, overflow flags, r and q of MUL tuples) are
- * delivered as uint32_t in `narrow` [narrow_slots][n]; check_sum and carry slots (full field elements /
- * 34-bit values) as uint64_t in `wide` [wide_slots][n].  p2e_tape_compact_layout() fills, for every
- * slot of the plain layout, (1u << 31 | wide row) or the narrow row; it returns the slot count and
- * writes the two row counts.  Same values, same order, different storage width. */
+ * delivered as uint32_t in `narrow` [narrow_rows][n]; check_sum slots (full field elements) as uint64_t
+ * in `wide` [wide_rows][n]; the 16 carries of a CheckSum tuple (b_j + 2^33 < 2^34,
+ * gates/mul_nonnative.rs:527) as 16 narrow rows of low words followed by ONE narrow row whose bits
+ * 2j, 2j+1 are the two top bits of carry j.  p2e_tape_compact_layout() fills, for every slot of the
+ * plain layout, (1u << 31 | wide row), (1u << 30 | narrow row of the low word; bit 29 marks the first
+ * carry of a tuple) or the narrow row; it returns the slot count and writes the two row counts.
+ * Same values, same order, different storage width (rows flagged in err[] may hold carries >= 2^34,
+ * which this format truncates -- the reference panics on those). */
 size_t p2e_tape_compact_layout(int tape, uint32_t* map, uint32_t* narrow_slots, uint32_t* wide_slots);
 int p2e_tape_witness_compact(int tape, size_t n, const uint64_t* const* inputs, uint32_t* narrow,
                              uint64_t* wide, uint32_t* err);

@@ -1185,7 +1185,8 @@ __global__ void __launch_bounds__(32) k_chain_checks(ChainArgs A) {
 
 // ------------------------------------------------------------------------------------------
 // compact host format: split the [slots][n] u64 witness into a u32 matrix (narrow slots) and a u64
-// matrix (wide slots); map[slot] = (1u << 31 | wide row) or narrow row
+// matrix (wide slots); map[slot] = (1u << 31 | wide row), (1u << 30 | narrow row) for a 34-bit carry
+// (bit 29 marks the first carry of a CheckSum tuple) or the narrow row
 __global__ void __launch_bounds__(256) k_pack_compact(size_t n, size_t n_slots, const u64* __restrict__ wit, size_t ws,
                                                       const u32* __restrict__ map, u32* __restrict__ narrow,
                                                       u64* __restrict__ wide) {
@@ -1194,8 +1195,22 @@ __global__ void __launch_bounds__(256) k_pack_compact(size_t n, size_t n_slots, 
   for (size_t s = blockIdx.y; s < n_slots; s += gridDim.y) {
     const u32 m = map[s];
     const u64 v = wit[s * ws + i];
-    if (m >> 31) wide[(size_t)(m & 0x7fffffffu) * n + i] = v;
-    else narrow[(size_t)m * n + i] = (u32)v;
+    if (m >> 31) {
+      wide[(size_t)(m & 0x7fffffffu) * n + i] = v;
+    } else if (m & (1u << 30)) {
+      // CheckSum carry b_j < 2^34: low word in its own narrow row; the 16 two-bit tops of the tuple share
+      // the narrow row after them, written by the thread that handles the tuple's first slot
+      const u32 row = m & 0x1fffffffu;
+      narrow[(size_t)row * n + i] = (u32)v;
+      if (m & (1u << 29)) {
+        u32 tops = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) tops |= ((u32)(wit[(s + j) * ws + i] >> 32) & 3u) << (2 * j);
+        narrow[(size_t)(row + 16) * n + i] = tops;
+      }
+    } else {
+      narrow[(size_t)m * n + i] = (u32)v;
+    }
   }
 }
 
@@ -1614,10 +1629,17 @@ size_t p2e_tape_compact_layout(int tape, uint32_t* map, uint32_t* narrow_slots, 
     const uint32_t kind = t.gen_kind[g], off = t.gen_off[g];
     const uint32_t end = (g + 1 < t.gen_kind.size()) ? t.gen_off[g + 1] : t.n_slots;
     for (uint32_t s = off; s < end; s++) {
-      // MUL tuple: r[9], q[9] narrow, check_sum[17] wide; CHECKSUM tuple: b[16] wide; everything else narrow
-      const bool is_wide = (kind == G_CHECKSUM) || (kind == G_MUL && s - off >= 18);
-      if (map) map[s] = is_wide ? ((1u << 31) | nw) : nn;
-      if (is_wide) nw++; else nn++;
+      // MUL tuple: r[9], q[9] narrow, check_sum[17] wide; CHECKSUM tuple: b[16] as 16 low words + one
+      // word of two-bit tops (b_j + 2^33 < 2^34, mul_nonnative.rs:527); everything else narrow
+      const bool is_wide = (kind == G_MUL && s - off >= 18);
+      if (kind == G_CHECKSUM) {
+        if (map) map[s] = (1u << 30) | (s == off ? (1u << 29) : 0u) | nn;
+        nn++;
+        if (s + 1 == end) nn++;          // the tuple's row of tops
+      } else {
+        if (map) map[s] = is_wide ? ((1u << 31) | nw) : nn;
+        if (is_wide) nw++; else nn++;
+      }
     }
   }
   if (narrow_slots) *narrow_slots = nn;

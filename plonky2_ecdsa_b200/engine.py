@@ -455,7 +455,9 @@ class Engine:
         return out, err
 
     def tape_compact_layout(self, tape):
-        """-> (map [slots] uint32: (1 << 31 | wide row) or narrow row, narrow_slots, wide_slots)."""
+        """-> (map [slots] uint32, narrow_rows, wide_rows).  map[slot] = (1 << 31 | wide row) for a full field
+        element, (1 << 30 | narrow row) for a 34-bit CheckSum carry (low word there; its two top bits are
+        bits 2j, 2j+1 of the narrow row that follows the tuple's 16 low words), else the narrow row."""
         slots = int(self.lib.p2e_tape_slots(tape))
         m = np.empty(slots, dtype=np.uint32)
         nn, nw = ctypes.c_uint32(0), ctypes.c_uint32(0)
@@ -479,8 +481,15 @@ class Engine:
         """Compact -> plain [slots][n] uint64 (host-side helper for tests / the Rust shim's unpack)."""
         out = np.empty((cmap.shape[0], narrow.shape[1]), dtype=np.uint64)
         is_wide = (cmap >> np.uint32(31)).astype(bool)
+        is_carry = ((cmap >> np.uint32(30)) & np.uint32(1)).astype(bool) & ~is_wide
+        plain = ~is_wide & ~is_carry
         out[is_wide] = wide[cmap[is_wide] & np.uint32(0x7FFFFFFF)]
-        out[~is_wide] = narrow[cmap[~is_wide]]
+        out[plain] = narrow[cmap[plain]]
+        # CheckSum carries: 16 low words, then one word holding the 16 two-bit tops of the tuple
+        rows = (cmap[is_carry] & np.uint32(0x1FFFFFFF)).astype(np.int64)
+        j = np.arange(rows.shape[0]) % 16
+        tops = (narrow[rows - j + 16].astype(np.uint64) >> (2 * j[:, None]).astype(np.uint64)) & np.uint64(3)
+        out[is_carry] = narrow[rows].astype(np.uint64) | (tops << np.uint64(32))
         return out
 
     def curve_add(self, x1, y1, x2, y2):

@@ -237,14 +237,17 @@ def test_curve_msm_vs_oracle(engine):
 
 
 def test_compact_host_format_round_trips(engine):
-    """The compact host format (u32 narrow slots + u64 wide slots) carries exactly the plain witness."""
+    """The compact host format (u32 narrow slots, u64 check_sum slots, packed 34-bit carries) carries exactly the plain witness."""
     wl = W.ecdsa_workload(37, seed=5)
     ins = [wl[k] for k in ("msg", "r", "s", "pkx", "pky")]
     plain, e1 = engine.verify_secp256k1_message_witness(*ins)
     cmap, nn, nw = engine.tape_compact_layout(engine.TAPE_ECDSA)
-    assert nn + nw == plain.shape[0] == 82615 and nw == 1087 * 33
+    assert nn + nw == plain.shape[0] + 1087 and plain.shape[0] == 82615 and nw == 1087 * 17
     narrow, wide, e2 = engine.tape_witness_compact(engine.TAPE_ECDSA, ins)
     assert narrow.shape == (nn, 37) and wide.shape == (nw, 37)
     assert np.array_equal(engine.expand_compact(cmap, narrow, wide), plain) and np.array_equal(e1, e2)
     # every narrow slot really fits 32 bits in the plain layout
-    assert not (plain[(cmap >> np.uint32(31)) == 0] >> np.uint64(32)).any()
+    assert not (plain[(cmap >> np.uint32(30)) == 0] >> np.uint64(32)).any()
+    # ... and every carry slot fits 34 bits (its two top bits travel in the tuple's packed row)
+    carry = (cmap >> np.uint32(30)) == 1
+    assert carry.sum() == 1087 * 16 and not (plain[carry] >> np.uint64(34)).any()

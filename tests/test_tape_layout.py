@@ -92,15 +92,20 @@ def test_compact_layout_map():
     import ctypes
     nn, nw = ctypes.c_uint32(0), ctypes.c_uint32(0)
     assert lib.p2e_tape_compact_layout(0, m.ctypes.data, ctypes.addressof(nn), ctypes.addressof(nw)) == slots
-    assert nw.value == 1087 * 33 and nn.value + nw.value == slots
+    assert nw.value == 1087 * 17 and nn.value + nw.value == slots + 1087      # one row of carry tops per CheckSum tuple
     wide = (m >> np.uint32(31)).astype(bool)
-    assert wide.sum() == nw.value
-    # rows are dense and in slot order within each class
+    carry = ((m >> np.uint32(30)) & np.uint32(1)).astype(bool) & ~wide
+    first = ((m >> np.uint32(29)) & np.uint32(1)).astype(bool) & carry
+    assert wide.sum() == nw.value and carry.sum() == 1087 * 16 and first.sum() == 1087
+    # rows are dense and in slot order within each class; every CheckSum tuple is followed by its row of tops
     assert np.array_equal(m[wide] & np.uint32(0x7FFFFFFF), np.arange(nw.value, dtype=np.uint32))
-    assert np.array_equal(m[~wide], np.arange(nn.value, dtype=np.uint32))
+    rows = np.where(carry, m & np.uint32(0x1FFFFFFF), m)[~wide].astype(np.int64)
+    gaps = np.diff(rows)
+    assert rows[0] == 0 and set(gaps.tolist()) <= {1, 2} and (gaps == 2).sum() == 1087 and rows[-1] < nn.value
     # oracle: exactly the check_sum / carry slots exceed 32 bits in a real witness
     sk, msg, k = 0x1234567 << 200 | 99, 0xabcdef << 180 | 5, 0x777 << 222 | 1
     r, s = S.sign_message(msg, sk, k)
     flat = np.array(S.ecdsa_witness(msg, r, s, S.pt_mul(sk, S.G)).flat(), dtype=np.uint64)
-    assert not (flat[~wide] >> np.uint64(32)).any()
+    assert not (flat[~wide & ~carry] >> np.uint64(32)).any()
     assert (flat[wide] >> np.uint64(32)).any()
+    assert not (flat[carry] >> np.uint64(34)).any() and (flat[carry] >> np.uint64(32)).any()
