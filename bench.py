@@ -34,6 +34,7 @@ WORKLOAD_NAMES = {
     "evalrc": "u29 range-check gate (9 limbs, 3-bit aux limbs; plonky2_ux spec unpinned) eval over 2^20 Goldilocks LDE rows",
     "evalcmp": "u29 comparison gate (2-bit chunks; plonky2_ux spec unpinned) eval over 2^20 Goldilocks LDE rows",
     "evaladd": "u29 add-many gate (3 addends, 5 ops / row; plonky2_ux spec unpinned) eval over 2^20 Goldilocks LDE rows",
+    "lde": "coset LDE (ifft 2^17 -> zero-pad -> coset fft 2^20, rate 8) of 135 wire polynomials: the matrix the gate evaluators read",
 }
 # plonky2_ux eval workloads: (gate, bits, limb_bits, count, num_addends, kernel)
 UX_WORKLOADS = {
@@ -50,6 +51,7 @@ METRICS = {
     "evalrc": ("ux_range_check_gate_rows_per_s", "rows/s"),
     "evalcmp": ("ux_comparison_gate_rows_per_s", "rows/s"),
     "evaladd": ("ux_add_many_gate_rows_per_s", "rows/s"),
+    "lde": ("coset_lde_output_elements_per_s", "elements/s"),
 }
 
 
@@ -296,6 +298,28 @@ class Bench:
                 assert rc == 0, eng.last_error()
             return dict(step=step, step_e2e=step_e2e, units=n, h2d=nw * 8 * n, d2h=nc * 8 * n, alg_bytes=(nw + nc) * 8 * n,
                         kernel=kname, launches=1, err=None, dtype="u64 (Goldilocks)", keep=(wd, od, hw, ho))
+        if wl == "lde":
+            log_n, rb, polys = 17, 3, 135
+            n, m = 1 << log_n, 1 << (log_n + rb)
+            v = W.random_goldilocks(W.SEED + 21 + self.rank, polys, n)
+            vd = self.dev(v)
+            od = torch.empty((polys, m), dtype=torch.int64, device="cuda")
+            scr = torch.empty(int(lib.p2e_ntt_scratch_bytes(log_n, rb, polys)) // 8, dtype=torch.int64, device="cuda")
+
+            def step():
+                rc = lib.p2e_coset_lde_dev(log_n, rb, polys, vd.data_ptr(), n, od.data_ptr(), m, scr.data_ptr(), sp)
+                assert rc == 0, eng.last_error()
+            hv = self.pinned(v)
+            ho = torch.empty((polys, m), dtype=torch.int64).pin_memory()
+
+            def step_e2e():
+                rc = lib.p2e_coset_lde(log_n, rb, polys, hv.data_ptr(), ho.data_ptr())
+                assert rc == 0, eng.last_error()
+            # algorithmic bytes: read the n values, write the 8 n LDE values (the two intermediate passes are the
+            # implementation's, not the algorithm's)
+            return dict(step=step, step_e2e=step_e2e, units=polys * m, h2d=polys * n * 8, d2h=polys * m * 8,
+                        alg_bytes=polys * (n + m) * 8, kernel="k_ntt_cols + k_ntt_rows (ifft 2^17, fft 2^20)", launches=4, err=None,
+                        dtype="u64 (Goldilocks)", keep=(vd, od, scr, hv, ho))
         if wl == "glv":
             # device-resident only at full size (the 2^16 x 61.6k-slot witness is 32 GB); e2e on a 4096-scalar slice
             n = 1 << 16
@@ -529,7 +553,7 @@ def main():
     main_res = b.measure(wl, args.steps, args.warmup, e2e_steps=max(2, min(args.steps, 5)), sample_clocks=True)
     secondary = {}
     if not args.no_secondary:
-        for w2 in ("mulmod", "eval", "evalcs", "evalrc", "evalcmp", "evaladd", "glv", "ecdsa"):
+        for w2 in ("mulmod", "eval", "evalcs", "evalrc", "evalcmp", "evaladd", "lde", "glv", "ecdsa"):
             if w2 != wl:
                 try:
                     r2 = b.measure(w2, steps=min(args.steps, 20) if w2 != "glv" else 3, warmup=3, e2e_steps=2)

@@ -271,6 +271,22 @@ int p2e_ux_witness_dev(int gate, int bits, int limb_bits, int count, int num_add
 int p2e_ux_witness(int gate, int bits, int limb_bits, int count, int num_addends, size_t n,
                    const uint64_t* inputs, uint64_t* row, uint32_t* err);
 
+/* ---- Goldilocks NTT / coset LDE (the step that feeds the gate evaluators) ---------
+ * plonky2 conventions (field crate, out of tree, restated): omega_n = POWER_OF_TWO_GENERATOR^(2^(32 - log_n)),
+ * POWER_OF_TWO_GENERATOR = 7^((p-1)/2^32) = 1753635133440165772; natural order in and out,
+ * X[k] = sum_i x[i] omega_n^(i k); the inverse divides by n.  p2e_coset_lde is
+ * PolynomialValues::lde_onto_coset: ifft, zero-pad by 2^rate_bits, coset fft with shift g = 7:
+ * out[j] = P(g * omega_(n << rate_bits)^j), wire-major [poly][lde_row] -- the matrix p2e_eval_* reads.
+ * Matrices are [n_polys][stride]; log_n 2..24; scratch: p2e_ntt_scratch_bytes() bytes of device memory
+ * (rate_bits = 0 for p2e_ntt_dev).  in and out may not alias. */
+size_t p2e_ntt_scratch_bytes(int log_n, int rate_bits, int n_polys);
+int p2e_ntt_dev(int log_n, int inverse, int n_polys, const uint64_t* in, size_t in_stride, uint64_t* out,
+                size_t out_stride, uint64_t* scratch, void* stream);
+int p2e_ntt(int log_n, int inverse, int n_polys, const uint64_t* in, uint64_t* out);
+int p2e_coset_lde_dev(int log_n, int rate_bits, int n_polys, const uint64_t* values, size_t in_stride,
+                      uint64_t* out, size_t out_stride, uint64_t* scratch, void* stream);
+int p2e_coset_lde(int log_n, int rate_bits, int n_polys, const uint64_t* values, uint64_t* out);
+
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* Per-kernel timing of the chain entry points: when enabled, CUDA events are recorded on the
  * launching stream between the kernels of the NEXT chain call; p2e_last_kernel_times() then

@@ -33,6 +33,7 @@ int get_scratch(int slot, size_t bytes, void** out);
   } while (0)
 
 void chain_release_device_tapes();
+void ntt_release_tables();
 
 static inline cudaStream_t pick_stream(void* s) { return s ? (cudaStream_t)s : ctx().stream; }
 

@@ -552,6 +552,7 @@ void p2e_shutdown(void) {
   if (!c.ready) return;
   cudaStreamSynchronize(c.stream);
   chain_release_device_tapes();
+  ntt_release_tables();
   for (int i = 0; i < 4; i++) {
     if (c.scratch[i]) cudaFree(c.scratch[i]);
     c.scratch[i] = nullptr;

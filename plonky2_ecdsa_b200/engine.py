@@ -125,6 +125,11 @@ SIGNATURES = {
     "p2e_eval_ux": (_int, [_int, _int, _int, _int, _int, _sz, _vp, _vp]),
     "p2e_ux_witness_dev": (_int, [_int, _int, _int, _int, _int, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
     "p2e_ux_witness": (_int, [_int, _int, _int, _int, _int, _sz, _vp, _vp, _vp]),
+    "p2e_ntt_scratch_bytes": (_sz, [_int, _int, _int]),
+    "p2e_ntt_dev": (_int, [_int, _int, _int, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_ntt": (_int, [_int, _int, _int, _vp, _vp]),
+    "p2e_coset_lde_dev": (_int, [_int, _int, _int, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_coset_lde": (_int, [_int, _int, _int, _vp, _vp]),
     "p2e_set_profiling": (_int, [_int]),
     "p2e_last_kernel_times": (_int, [_vp, _int]),
     "p2e_bench_imad": (ctypes.c_double, [_int, _int]),
@@ -429,6 +434,30 @@ class Engine:
 
     def eval_add_many_ux_gate(self, wires, num_addends=3, num_ops=5, bits=29, limb_bits=2):
         return self.eval_ux_gate(UX_ADD_MANY, wires, bits, limb_bits, num_ops, num_addends)
+
+    # ---------------------------------------------------------------- Goldilocks NTT / coset LDE
+    def fft(self, values, inverse=False):
+        """plonky2 `fft` / `ifft` of every row: values [n_polys][2^k] -> same shape, natural order."""
+        v = _host_u64(values)
+        n = v.shape[1]
+        log_n = n.bit_length() - 1
+        if 1 << log_n != n:
+            raise ValueError("row length must be a power of two")
+        out = np.empty_like(v)
+        self._check(self.lib.p2e_ntt(log_n, 1 if inverse else 0, v.shape[0], _ptr(v), _ptr(out)))
+        return out
+
+    def lde_onto_coset(self, values, rate_bits):
+        """PolynomialValues::lde_onto_coset(rate_bits) of every row: [n_polys][n] -> [n_polys][n << rate_bits],
+        out[p][j] = P_p(7 * omega^j): the wire-major LDE matrix the gate evaluators read."""
+        v = _host_u64(values)
+        n = v.shape[1]
+        log_n = n.bit_length() - 1
+        if 1 << log_n != n:
+            raise ValueError("row length must be a power of two")
+        out = np.empty((v.shape[0], n << rate_bits), dtype=np.uint64)
+        self._check(self.lib.p2e_coset_lde(log_n, rate_bits, v.shape[0], _ptr(v), _ptr(out)))
+        return out
 
     # ---------------------------------------------------------------- generic gadget tapes
     (TAPE_ECDSA, TAPE_GLV_MUL, TAPE_CURVE_ADD, TAPE_CURVE_DOUBLE, TAPE_CURVE_COND_ADD, TAPE_FIXED_BASE_MUL,

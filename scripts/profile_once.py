@@ -36,6 +36,15 @@ elif what == "ux":
         assert lib.p2e_ux_witness_dev(gate, bits, lb, count, na, n, x.data_ptr(), n, row.data_ptr(), n, e.data_ptr(), None) == 0
         eng.synchronize()
         del w, o, x, row
+elif what == "lde":
+    log_n, rb, polys = 17, 3, 135
+    n, m = 1 << log_n, 1 << (log_n + rb)
+    vd = dev(W.random_goldilocks(W.SEED + 21, polys, n))
+    od = torch.empty((polys, m), dtype=torch.int64, device="cuda")
+    scr = torch.empty(int(lib.p2e_ntt_scratch_bytes(log_n, rb, polys)) // 8, dtype=torch.int64, device="cuda")
+    for _ in range(2):
+        assert lib.p2e_coset_lde_dev(log_n, rb, polys, vd.data_ptr(), n, od.data_ptr(), m, scr.data_ptr(), None) == 0
+    eng.synchronize()
 else:
     n = 1 << 20
     x, y = W.mulmod_workload(n, 0, seed=W.SEED)
