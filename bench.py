@@ -345,7 +345,7 @@ class Bench:
                 rc = lib.p2e_glv_mul_witness(m, *[t.data_ptr() for t in hin], ho.data_ptr(), he.data_ptr())
                 assert rc == 0, eng.last_error()
             return dict(step=step, step_e2e=step_e2e, units=n, e2e_units=m, h2d=3 * 9 * 8 * m, d2h=slots * 8 * m + 4 * m,
-                        alg_bytes=slots * 8 * n, kernel="k_chain_expand (8 chunks of 8192)", launches=7 * 8, err=ed,
+                        alg_bytes=slots * 8 * n, kernel="k_chain_expand", launches=9, err=ed,
                         dtype="u32 limbs / u64 (int)", keep=(ind, od, hin, ho, he), slots=slots)
         n = 4096
         slots = int(lib.p2e_ecdsa_tape_slots())
@@ -395,7 +395,7 @@ class Bench:
             assert rc == 0, eng.last_error()
         return dict(step=step, step_e2e=step_e2e, step_e2e_plain=step_e2e_plain, units=n, h2d=5 * 9 * 8 * n,
                     d2h=nn * 4 * n + nw * 8 * n + 4 * n, d2h_plain=slots * 8 * n + 4 * n, e2e_keep=(hn, hw, in_arr),
-                    alg_bytes=slots * 8 * n, kernel="k_chain_expand", launches=7, err=ed, dtype="u32 limbs / u64 (int)",
+                    alg_bytes=slots * 8 * n, kernel="k_chain_expand", launches=9, err=ed, dtype="u32 limbs / u64 (int)",
                     keep=(ind, ods, eds, hin, ho, he), slots=slots, streams=streams, step_single=step_single)
 
     def measure(self, wl, steps, warmup, e2e_steps, sample_clocks=False):
