@@ -1019,23 +1019,25 @@ __global__ void __launch_bounds__(32) k_chain_invert_down(ChainArgs A) {
 __global__ void __launch_bounds__(128) k_chain_affine(ChainArgs A) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int k = blockIdx.y;
-  if (i >= A.n || (int)A.t.ptops[k].round != A.round) return;
-  i32 zi[NL], zi2[NL], zi3[NL], v[NL], r[NL];
+  if (i >= A.n) return;
+  // all four loads are addressed by (k, i) alone: issue them together, ahead of the tape lookup
+  i32 zi[NL], zi2[NL], zi3[NL], jx[NL], jy[NL], jz[NL], r[NL];
   u32 c[NL];
   ld9(A.ZINV, k, A.cap, i, zi);
+  ld9(A.JX, k, A.cap, i, jx);
+  ld9(A.JY, k, A.cap, i, jy);
+  ld9(A.JZ, k, A.cap, i, jz);
+  if ((int)A.t.ptops[k].round != A.round) return;
   lz_sqr(zi, zi2);
   lz_mul(zi2, zi, zi3);
-  ld9(A.JX, k, A.cap, i, v);
-  lz_mul(v, zi2, r);
+  lz_mul(jx, zi2, r);
   lz_canon(r, c);
   sv9(A.AX, k, A.cap, i, c);
-  ld9(A.JY, k, A.cap, i, v);
-  lz_mul(v, zi3, r);
+  lz_mul(jy, zi3, r);
   lz_canon(r, c);
   sv9(A.AY, k, A.cap, i, c);
-  ld9(A.JZ, k, A.cap, i, v);
-  lz_sqr(v, zi2);
-  lz_mul(zi2, v, r);
+  lz_sqr(jz, zi2);
+  lz_mul(zi2, jz, r);
   sv9(A.ZC, k, A.cap, i, r);
 }
 
@@ -1087,15 +1089,23 @@ __global__ void __launch_bounds__(128, 3) k_chain_expand(ChainArgs A) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int k = blockIdx.y;
   if (i >= A.n) return;
+  // Loads are issued in two dependent rounds, not five (ncu: a third of the stall samples sat on the
+  // chain tape -> SRC1 -> operand 1 -> SRC2 -> operand 2): everything addressed by (k, i) alone first ...
+  const size_t ki = (size_t)k * A.cap + i;
   const PtOp op = A.t.ptops[k];
+  const int32_t p1 = A.SRC1[ki];
+  const int32_t p2_any = A.SRC2[ki];              // meaningless for a doubling (never dereferenced then)
+  const u32 flg = A.FLG[ki];
+  i32 zinv[NL];
+  ld9(A.ZINV, k, A.cap, i, zinv);
   if ((int)op.round != A.round) return;
   const u32 s0 = op.slot;
-  int32_t p1 = A.SRC1[(size_t)k * A.cap + i];
   u32 e = 0;
-  u32 x1[NL], y1[NL], vinv[NL];
-  i32 zc1[NL], zinv[NL], t[NL], t2[NL];
+  u32 x1[NL], y1[NL], vinv[NL], x2[NL], y2[NL];
+  i32 zc1[NL], zc2[NL], t[NL], t2[NL];
+  // ... then both operands
   load_affine(A, p1, i, x1, y1, zc1);
-  ld9(A.ZINV, k, A.cap, i, zinv);
+  if (op.type != PT_DBL) load_affine(A, p2_any, i, x2, y2, zc2);
   if (op.type == PT_DBL) {
     // (2y)^-1 = Z1^4 / Z3
     i32 z1[NL];
@@ -1136,10 +1146,6 @@ __global__ void __launch_bounds__(128, 3) k_chain_expand(ChainArgs A) {
     e |= do_mul<ModP>(A, s0 + 221, i, lam, xdiff, lx);            // lambda_x_diff
     do_sub<ModP>(A, s0 + 272, i, lx, y1, y3);                     // y3
   } else {
-    int32_t p2 = A.SRC2[(size_t)k * A.cap + i];
-    u32 x2[NL], y2[NL];
-    i32 zc2[NL];
-    load_affine(A, p2, i, x2, y2, zc2);
     // (x2 - x1)^-1 = Z1^3 Z2^3 / Z3
     nl_lzmul(zc1, zc2, t);
     nl_lzmul(t, zinv, t2);
@@ -1159,7 +1165,7 @@ __global__ void __launch_bounds__(128, 3) k_chain_expand(ChainArgs A) {
     do_sub<ModP>(A, s0 + 221, i, pr, y1, y3);                     // y3
     if (op.type != PT_ADD) {
       // curve_conditional_add: x = sum.x * b + p1.x * !b (curve.rs:235-240)
-      u32 b = A.FLG[(size_t)k * A.cap + i];
+      const u32 b = flg;
       u32 z[NL], r[NL];
       set_zero9(z);
       if (b) { do_add<ModP>(A, s0 + 231, i, x3, z, r); do_add<ModP>(A, s0 + 241, i, y3, z, r); }
@@ -1668,27 +1674,55 @@ int p2e_tape_witness_compact(int tape, size_t n, const uint64_t* const* inputs, 
     dmap_device[tape] = ctx().device;
   }
   cudaStream_t st = ctx().stream;
+  // The batch is processed in chunks of signatures so that the D2H copy of chunk c (on a second stream,
+  // pitched copies into the caller's [rows][n] matrices) overlaps the kernels of chunk c + 1: the call
+  // costs about one chunk of compute plus the PCIe time instead of their sum.
+  static cudaStream_t cp = nullptr;
+  static int cp_device = -1;
+  static cudaEvent_t ev_done[8];
+  if (!cp || cp_device != ctx().device) {
+    P2E_CUDA(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
+    for (auto& e : ev_done) P2E_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cp_device = ctx().device;
+  }
+  size_t n_chunks = 1;
+  {
+    const char* e = getenv("P2E_HOST_CHUNKS");
+    n_chunks = e ? (size_t)atoi(e) : 4;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > 8) n_chunks = 8;
+    if (n < 256 * n_chunks) n_chunks = 1;
+  }
+  const size_t cn = (n + n_chunks - 1) / n_chunks;
   void *din = nullptr, *dout = nullptr, *derr = nullptr, *dpack = nullptr;
   if ((rc = get_scratch(0, (size_t)n_in * 9 * n * 8, &din))) return rc;
-  if ((rc = get_scratch(1, (size_t)t.n_slots * n * 8, &dout))) return rc;
+  if ((rc = get_scratch(1, (size_t)t.n_slots * cn * 8, &dout))) return rc;
   if ((rc = get_scratch(2, n * 4, &derr))) return rc;
-  const size_t nbytes = (size_t)nn * n * 4, wbytes = (size_t)nw * n * 8;
-  if ((rc = get_scratch(3, ((nbytes + 15) / 16) * 16 + wbytes, &dpack))) return rc;
-  u32* dn = (u32*)dpack;
-  u64* dw = (u64*)((char*)dpack + ((nbytes + 15) / 16) * 16);
+  const size_t nbytes = (size_t)nn * cn * 4, wbytes = (size_t)nw * cn * 8;          // per chunk
+  const size_t region = ((nbytes + 15) / 16) * 16 + ((wbytes + 15) / 16) * 16;
+  if ((rc = get_scratch(3, region * n_chunks, &dpack))) return rc;
   const uint64_t* dptr[MAX_TAPE_INPUTS];
-  for (int k = 0; k < n_in; k++) {
-    dptr[k] = (const uint64_t*)din + (size_t)k * 9 * n;
+  for (int k = 0; k < n_in; k++)
     P2E_CUDA(cudaMemcpyAsync((uint64_t*)din + (size_t)k * 9 * n, inputs[k], 9 * n * 8, cudaMemcpyHostToDevice, st));
+  for (size_t c = 0; c < n_chunks; c++) {
+    const size_t c0 = c * cn;
+    if (c0 >= n) break;
+    const size_t cc = (n - c0 < cn) ? n - c0 : cn;
+    u32* dn = (u32*)((char*)dpack + region * c);
+    u64* dw = (u64*)((char*)dn + ((nbytes + 15) / 16) * 16);
+    for (int k = 0; k < n_in; k++) dptr[k] = (const uint64_t*)din + (size_t)k * 9 * n + c0;
+    if ((rc = run_tape(tape, t, cc, dptr, n_in, n, (uint64_t*)dout, cn, (uint32_t*)derr + c0, (void*)st))) return rc;
+    k_pack_compact<<<dim3((unsigned)((cc + 255) / 256), 1024), 256, 0, st>>>(cc, t.n_slots, (const u64*)dout, cn,
+                                                                            (const u32*)dmaps[tape], dn, dw);
+    P2E_CUDA(cudaGetLastError());
+    P2E_CUDA(cudaEventRecord(ev_done[c], st));
+    P2E_CUDA(cudaStreamWaitEvent(cp, ev_done[c], 0));
+    P2E_CUDA(cudaMemcpy2DAsync(narrow + c0, n * 4, dn, cc * 4, cc * 4, nn, cudaMemcpyDeviceToHost, cp));
+    P2E_CUDA(cudaMemcpy2DAsync(wide + c0, n * 8, dw, cc * 8, cc * 8, nw, cudaMemcpyDeviceToHost, cp));
+    if (err) P2E_CUDA(cudaMemcpyAsync(err + c0, (uint32_t*)derr + c0, cc * 4, cudaMemcpyDeviceToHost, cp));
   }
-  if ((rc = run_tape(tape, t, n, dptr, n_in, n, (uint64_t*)dout, n, (uint32_t*)derr, (void*)st))) return rc;
-  k_pack_compact<<<dim3((unsigned)((n + 255) / 256), 1024), 256, 0, st>>>(n, t.n_slots, (const u64*)dout, n,
-                                                                         (const u32*)dmaps[tape], dn, dw);
-  P2E_CUDA(cudaGetLastError());
-  P2E_CUDA(cudaMemcpyAsync(narrow, dn, nbytes, cudaMemcpyDeviceToHost, st));
-  P2E_CUDA(cudaMemcpyAsync(wide, dw, wbytes, cudaMemcpyDeviceToHost, st));
-  if (err) P2E_CUDA(cudaMemcpyAsync(err, derr, n * 4, cudaMemcpyDeviceToHost, st));
   P2E_CUDA(cudaStreamSynchronize(st));
+  P2E_CUDA(cudaStreamSynchronize(cp));
   return 0;
 }
 

@@ -251,3 +251,21 @@ def test_compact_host_format_round_trips(engine):
     # ... and every carry slot fits 34 bits (its two top bits travel in the tuple's packed row)
     carry = (cmap >> np.uint32(30)) == 1
     assert carry.sum() == 1087 * 16 and not (plain[carry] >> np.uint64(34)).any()
+
+
+@pytest.mark.gpu
+def test_compact_host_format_chunked_copy(engine):
+    """Batches of >= 1024 signatures go through the chunked path (pitched D2H copies overlapping the next
+    chunk's kernels); ragged last chunk included."""
+    n = 1100 + 3
+    wl = W.ecdsa_workload(n, seed=8)
+    ins = [wl[k] for k in ("msg", "r", "s", "pkx", "pky")]
+    ins[2] = ins[2].copy()
+    ins[2][:, 777] = 0                                      # s = 0 in the third chunk -> ERR_INVERSE_ZERO there only
+    plain, e1 = engine.verify_secp256k1_message_witness(*ins)
+    cmap, nn, nw = engine.tape_compact_layout(engine.TAPE_ECDSA)
+    narrow, wide, e2 = engine.tape_witness_compact(engine.TAPE_ECDSA, ins)
+    assert np.array_equal(e1, e2) and e1[777] & 8 and not np.delete(e1, 777).any()
+    ok = np.ones(n, dtype=bool)
+    ok[777] = False
+    assert np.array_equal(engine.expand_compact(cmap, narrow, wide)[:, ok], plain[:, ok])
