@@ -269,3 +269,20 @@ def test_compact_host_format_chunked_copy(engine):
     ok = np.ones(n, dtype=bool)
     ok[777] = False
     assert np.array_equal(engine.expand_compact(cmap, narrow, wide)[:, ok], plain[:, ok])
+
+
+@pytest.mark.gpu
+def test_ecdsa_batch_vs_c_oracle(engine):
+    """Every slot of 768 complete witnesses against the C restatement of the reference's generators
+    (oracle/p2e_oracle.c, itself pinned to the Python spec by tests/test_oracle_c.py): one Fermat ladder
+    per curve op on the CPU side, batched inversion on the GPU side, identical bits."""
+    import os
+    from oracle import cpu_baseline as CB
+    lib = CB.load()
+    n = 768
+    wl = W.ecdsa_workload(n, seed=31337)
+    ins = [wl[k] for k in ("msg", "r", "s", "pkx", "pky")]
+    wit, err = engine.verify_secp256k1_message_witness(*ins)
+    ref, ref_err = CB.ecdsa_witness(lib, *ins, threads=os.cpu_count() or 1)
+    assert not err.any() and not ref_err.any()
+    assert np.array_equal(wit, ref)
