@@ -271,6 +271,36 @@ int p2e_ux_witness_dev(int gate, int bits, int limb_bits, int count, int num_add
 int p2e_ux_witness(int gate, int bits, int limb_bits, int count, int num_addends, size_t n,
                    const uint64_t* inputs, uint64_t* row, uint32_t* err);
 
+/* ---- selector filtering + alpha-combination around the gate evaluators ----------
+ * The step after Gate::eval_unfiltered_base_batch in plonky2's quotient stage (out of tree, restated in
+ * oracle/vanishing_spec.py): Gate::eval_filtered_base_batch multiplies a row's constraints by
+ *   filter(s) = prod_{j in [group_start, group_end), j != gate_index} (j - s) * (many_selectors ? (2^32-1 - s) : 1)
+ * (s = the row's selector constant; many_selectors = the circuit has more than one selector polynomial),
+ * evaluate_gate_constraints_base_batch adds the gates' vectors position by position, and
+ * eval_vanishing_poly_base_batch folds all terms with reduce_with_powers_multi (term t times alpha^t).
+ * One call does this for one gate type over n LDE rows:
+ *   out[a][row] (+)= filter(row) * sum_c constraint_c(row) * alphas[a]^(first_power + c),  a < n_alphas <= 4
+ * (`accumulate` != 0 adds to what `out` holds, so the gates of a circuit are summed call by call;
+ * first_power = number of vanishing terms that precede the gate constraints; selector == NULL: filter = 1).
+ * gate / params (int[5]): P2E_GATE_MUL_NONNATIVE {modulus}, P2E_GATE_CHECK_SUM {}, P2E_GATE_UX {ux gate,
+ * bits, limb_bits, count, num_addends}.  The two in-tree gates are fused (wires are read once, only
+ * n_alphas columns are written); P2E_GATE_UX goes through p2e_eval_ux_dev and needs
+ * p2e_eval_filtered_scratch_bytes() bytes of device scratch (NULL is fine for the fused gates). */
+#define P2E_GATE_MUL_NONNATIVE 0
+#define P2E_GATE_CHECK_SUM 1
+#define P2E_GATE_UX 2
+int p2e_gate_shape(int gate, const int* params, int* num_wires, int* num_constraints);
+size_t p2e_eval_filtered_scratch_bytes(int gate, const int* params, size_t n);
+int p2e_eval_filtered_combined_dev(int gate, const int* params, int gate_index, int group_start, int group_end,
+                                   int many_selectors, size_t n, const uint64_t* wires, size_t in_stride,
+                                   const uint64_t* selector, const uint64_t* alphas, int n_alphas,
+                                   uint64_t first_power, int accumulate, uint64_t* out, size_t out_stride,
+                                   uint64_t* scratch, void* stream);
+int p2e_eval_filtered_combined(int gate, const int* params, int gate_index, int group_start, int group_end,
+                               int many_selectors, size_t n, const uint64_t* wires, const uint64_t* selector,
+                               const uint64_t* alphas, int n_alphas, uint64_t first_power, int accumulate,
+                               uint64_t* out);
+
 /* ---- Goldilocks NTT / coset LDE (the step that feeds the gate evaluators) ---------
  * plonky2 conventions (field crate, out of tree, restated): omega_n = POWER_OF_TWO_GENERATOR^(2^(32 - log_n)),
  * POWER_OF_TWO_GENERATOR = 7^((p-1)/2^32) = 1753635133440165772; natural order in and out,

@@ -9,5 +9,6 @@ from .engine import (  # noqa: F401
     ERR_U32, ERR_LIMB_RANGE, ERR_NONCANONICAL, ERR_INVERSE_ZERO, ERR_CARRY_RANGE,
     ERR_DIV_ZERO, ERR_LIMBS_OVERFLOW, ERR_CONNECT, ERR_INTERNAL,
     UX_RANGE_CHECK, UX_COMPARISON, UX_ADD_MANY, UX_SUBTRACTION, UX_ARITHMETIC,
+    GATE_MUL_NONNATIVE, GATE_CHECK_SUM, GATE_UX,
     MUL_OUT_R, MUL_OUT_Q, MUL_OUT_CHECK_SUM, MUL_OUT_CARRY, MUL_OUT_ROWS,
 )

@@ -418,11 +418,9 @@ __device__ __forceinline__ u64 reduce_q(u64 qa0, u64 qa1, u64 qb0, u64 qb1, u64 
   return gl_reduce5(W0, W1, (u32)t, (u32)(t >> 32), 0);
 }
 
-template <class MOD>
-__global__ void __launch_bounds__(TPB, 4)
-k_eval_mul_nonnative(size_t n, const u64* __restrict__ wires, size_t is, u64* __restrict__ out, size_t os) {
-  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
+// One row of MulNonnativeGate::eval_unfiltered (gates/mul_nonnative.rs:101-130); constraint c goes to sink.put(c, v)
+template <class MOD, class SINK>
+__device__ __forceinline__ SINK eval_mul_nonnative_row(const u64* __restrict__ wires, size_t is, size_t i, SINK sink) {
   u32 xl[NL], xh[NL], yl[NL], yh[NL], ql[NL], qh[NL];
 #pragma unroll
   for (int l = 0; l < NL; l++) {
@@ -456,14 +454,14 @@ k_eval_mul_nonnative(size_t n, const u64* __restrict__ wires, size_t is, u64* __
     }
     u64 neg = reduce_abc(A, B, C, csw);
     u64 pos = reduce_q(qa0, qa1, qb0, qb1, rw);
-    out[c * os + i] = gl_sub(pos, neg);
+    sink.put(c, gl_sub(pos, neg));
   }
+  return sink;
 }
 
-__global__ void __launch_bounds__(TPB)
-k_eval_check_sum(size_t n, const u64* __restrict__ wires, size_t is, u64* __restrict__ out, size_t os) {
-  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
+// One row of CheckSumGate::eval_unfiltered (gates/mul_nonnative.rs:411-427)
+template <class SINK>
+__device__ __forceinline__ SINK eval_check_sum_row(const u64* __restrict__ wires, size_t is, size_t i, SINK sink) {
   u64 last = 0;
 #pragma unroll
   for (int c = 0; c < 2 * NL - 1; c++) {
@@ -472,11 +470,143 @@ k_eval_check_sum(size_t n, const u64* __restrict__ wires, size_t is, u64* __rest
     if (c < 2 * NL - 2) {
       u64 o = gl_sub(wires[(2 * NL - 1 + c) * is + i], 1ull << 33);
       u64 prod = gl_reduce128(o << LB, o >> (64 - LB));   // 2^29 * o
-      out[c * os + i] = gl_sub(s, prod);
+      sink.put(c, gl_sub(s, prod));
       last = o;
     } else {
-      out[c * os + i] = s;
+      sink.put(c, s);
     }
+  }
+  return sink;
+}
+
+// Gate::eval_unfiltered_base_batch: every constraint to its own column
+struct StoreSink {
+  u64* __restrict__ out;
+  size_t os, i;
+  __device__ __forceinline__ void put(int c, u64 v) { out[c * os + i] = v; }
+};
+
+template <class MOD>
+__global__ void __launch_bounds__(TPB, 4)
+k_eval_mul_nonnative(size_t n, const u64* __restrict__ wires, size_t is, u64* __restrict__ out, size_t os) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  StoreSink sink = {out, os, i};
+  eval_mul_nonnative_row<MOD>(wires, is, i, sink);
+}
+
+__global__ void __launch_bounds__(TPB)
+k_eval_check_sum(size_t n, const u64* __restrict__ wires, size_t is, u64* __restrict__ out, size_t os) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  StoreSink sink = {out, os, i};
+  eval_check_sum_row(wires, is, i, sink);
+}
+
+// ------------------------------------------------------------------------------------------
+// Selector filtering + alpha-combination around the gate evaluators.  plonky2 (out of tree,
+// restated; see include/p2e.h): Gate::eval_filtered_base_batch multiplies every constraint of a row by
+//   filter(s) = prod_{j in group_range, j != gate_index} (j - s) * (many_selectors ? (u32::MAX - s) : 1),
+// s = the row's selector constant; evaluate_gate_constraints_base_batch adds the gates' constraint vectors
+// position by position, and eval_vanishing_poly_base_batch folds the terms with reduce_with_powers_multi:
+// term t contributes term * alpha^t for every challenge alpha.  Fused here: one pass over the wires produces
+//   out[a][row] (+)= filter(row) * sum_c constraint_c(row) * alpha_a^(first_power + c)
+// so a gate costs (wires + 1 selector + n_alphas) columns of HBM traffic instead of (wires + constraints).
+constexpr int MAX_ALPHAS = 4;
+struct FilterArgs {
+  const u64* selector;       // [n] selector constants of the rows, or nullptr (filter = 1)
+  int gate_index, group_start, group_end, many_selectors;
+  int n_alphas, accumulate;
+};
+struct AlphaPow17 {
+  u64 p[MAX_ALPHAS][2 * NL - 1];
+};
+
+__device__ __forceinline__ u64 compute_filter(const FilterArgs& F, size_t i) {
+  if (!F.selector) return 1;
+  const u64 s = F.selector[i];
+  u64 f = 1;
+  for (int j = F.group_start; j < F.group_end; j++)
+    if (j != F.gate_index) f = gl_mul(f, gl_sub((u64)j, s));
+  if (F.many_selectors) f = gl_mul(f, gl_sub(0xFFFFFFFFull, s));
+  return f;
+}
+
+struct CombineSink17 {
+  const AlphaPow17* P;
+  int n_alphas;
+  u64 acc[MAX_ALPHAS];
+  __device__ __forceinline__ void put(int c, u64 v) {
+#pragma unroll
+    for (int a = 0; a < MAX_ALPHAS; a++)
+      if (a < n_alphas) acc[a] = gl_add(acc[a], gl_mul(v, P->p[a][c]));
+  }
+};
+
+__device__ __forceinline__ void store_combined(const FilterArgs& F, const u64* acc, u64 f, u64* __restrict__ out, size_t os,
+                                               size_t i) {
+#pragma unroll
+  for (int a = 0; a < MAX_ALPHAS; a++) {
+    if (a < F.n_alphas) {
+      u64 r = gl_mul(f, acc[a]);
+      if (F.accumulate) r = gl_add(r, out[a * os + i]);
+      out[a * os + i] = r;
+    }
+  }
+}
+
+template <class MOD>
+__global__ void __launch_bounds__(TPB, 4)
+k_eval_mul_nonnative_fc(size_t n, const u64* __restrict__ wires, size_t is, FilterArgs F, const __grid_constant__ AlphaPow17 P,
+                        u64* __restrict__ out, size_t os) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  CombineSink17 sink = {&P, F.n_alphas, {0, 0, 0, 0}};
+  sink = eval_mul_nonnative_row<MOD>(wires, is, i, sink);
+  store_combined(F, sink.acc, compute_filter(F, i), out, os, i);
+}
+
+__global__ void __launch_bounds__(TPB)
+k_eval_check_sum_fc(size_t n, const u64* __restrict__ wires, size_t is, FilterArgs F, const __grid_constant__ AlphaPow17 P,
+                    u64* __restrict__ out, size_t os) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  CombineSink17 sink = {&P, F.n_alphas, {0, 0, 0, 0}};
+  sink = eval_check_sum_row(wires, is, i, sink);
+  store_combined(F, sink.acc, compute_filter(F, i), out, os, i);
+}
+
+// generic form (any gate): constraints [C][n] already evaluated -> filter, combine with the power table [n_alphas][C]
+__global__ void __launch_bounds__(TPB)
+k_filter_combine(size_t n, int C, const u64* __restrict__ cons, size_t cs, const u64* __restrict__ pw, FilterArgs F,
+                 u64* __restrict__ out, size_t os) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  u64 acc[MAX_ALPHAS] = {0, 0, 0, 0};
+  for (int c = 0; c < C; c++) {
+    const u64 v = cons[(size_t)c * cs + i];
+#pragma unroll
+    for (int a = 0; a < MAX_ALPHAS; a++)
+      if (a < F.n_alphas) acc[a] = gl_add(acc[a], gl_mul(v, __ldg(pw + (size_t)a * C + c)));
+  }
+  store_combined(F, acc, compute_filter(F, i), out, os, i);
+}
+
+// pw[a][c] = alpha_a^(first_power + c)
+struct Alphas {
+  u64 v[MAX_ALPHAS];
+};
+__global__ void k_alpha_powers(Alphas al, int n_alphas, u64 first_power, int C, u64* __restrict__ pw) {
+  const int a = threadIdx.x;
+  if (a >= n_alphas) return;
+  u64 p = 1, b = al.v[a];
+  for (u64 e = first_power; e; e >>= 1) {
+    if (e & 1) p = gl_mul(p, b);
+    b = gl_mul(b, b);
+  }
+  for (int c = 0; c < C; c++) {
+    pw[(size_t)a * C + c] = p;
+    p = gl_mul(p, al.v[a]);
   }
 }
 
@@ -750,6 +880,95 @@ int p2e_eval_check_sum_dev(size_t n, const uint64_t* wires, size_t is, uint64_t*
   return 0;
 }
 
+
+// ---- filtered + alpha-combined evaluation
+static int gate_shape(int gate, const int* prm, int* wires, int* cons) {
+  if (!prm) return set_error_msg("eval_filtered: params is NULL");
+  switch (gate) {
+    case P2E_GATE_MUL_NONNATIVE:
+      if (bad_modulus(prm[0])) return -1;
+      *wires = 6 * NL - 1; *cons = 2 * NL - 1;
+      return 0;
+    case P2E_GATE_CHECK_SUM:
+      *wires = 4 * NL - 3; *cons = 2 * NL - 1;
+      return 0;
+    case P2E_GATE_UX: {
+      int ni;
+      return p2e_ux_gate_shape(prm[0], prm[1], prm[2], prm[3], prm[4], wires, cons, &ni);
+    }
+  }
+  return set_error_msg("eval_filtered: unknown gate");
+}
+
+int p2e_gate_shape(int gate, const int* params, int* num_wires, int* num_constraints) {
+  int w = 0, c = 0;
+  int rc = gate_shape(gate, params, &w, &c);
+  if (rc) return rc;
+  if (num_wires) *num_wires = w;
+  if (num_constraints) *num_constraints = c;
+  return 0;
+}
+
+size_t p2e_eval_filtered_scratch_bytes(int gate, const int* params, size_t n) {
+  int w = 0, c = 0;
+  if (gate != P2E_GATE_UX || gate_shape(gate, params, &w, &c)) return 16;
+  return ((size_t)c * n + (size_t)MAX_ALPHAS * c) * 8;
+}
+
+int p2e_eval_filtered_combined_dev(int gate, const int* params, int gate_index, int group_start, int group_end,
+                                   int many_selectors, size_t n, const uint64_t* wires, size_t is,
+                                   const uint64_t* selector, const uint64_t* alphas, int n_alphas, uint64_t first_power,
+                                   int accumulate, uint64_t* out, size_t os, uint64_t* scratch, void* stream) {
+  P2E_CHECK_READY();
+  int nw = 0, nc = 0, rc;
+  if ((rc = gate_shape(gate, params, &nw, &nc))) return rc;
+  if (n_alphas < 1 || n_alphas > MAX_ALPHAS || !alphas) return set_error_msg("eval_filtered: n_alphas must be 1..4");
+  if (selector && (group_end <= group_start || gate_index < group_start || gate_index >= group_end))
+    return set_error_msg("eval_filtered: gate_index outside its selector group");
+  if (n == 0) return 0;
+  if (is < n || os < n) return set_error_msg("stride < n");
+  for (int a = 0; a < n_alphas; a++)
+    if (alphas[a] >= GL_P) return set_error_msg("eval_filtered: alpha is not a canonical field element");
+  cudaStream_t st = pick_stream(stream);
+  FilterArgs F = {selector, gate_index, group_start, group_end, many_selectors ? 1 : 0, n_alphas, accumulate ? 1 : 0};
+  if (gate == P2E_GATE_UX) {
+    if (!scratch) return set_error_msg("eval_filtered: this gate needs p2e_eval_filtered_scratch_bytes() of scratch");
+    u64* pw = scratch;                                  // [n_alphas][nc]
+    u64* cons = scratch + (size_t)MAX_ALPHAS * nc;      // [nc][n]
+    Alphas al = {{0, 0, 0, 0}};
+    for (int a = 0; a < n_alphas; a++) al.v[a] = alphas[a];
+    k_alpha_powers<<<1, 32, 0, st>>>(al, n_alphas, first_power, nc, pw);
+    if ((rc = p2e_eval_ux_dev(params[0], params[1], params[2], params[3], params[4], n, wires, is, cons, n, (void*)st))) return rc;
+    k_filter_combine<<<grid_for(n), TPB, 0, st>>>(n, nc, cons, n, pw, F, out, os);
+    P2E_LAUNCH_CHECK();
+    return 0;
+  }
+  AlphaPow17 P;
+  for (int a = 0; a < MAX_ALPHAS; a++) {
+    u64 p = 0;
+    if (a < n_alphas) {
+      p = 1;
+      u64 b = alphas[a];
+      for (u64 e = first_power; e; e >>= 1) {
+        if (e & 1) p = gl_mul(p, b);
+        b = gl_mul(b, b);
+      }
+    }
+    for (int c = 0; c < 2 * NL - 1; c++) {
+      P.p[a][c] = p;
+      if (a < n_alphas) p = gl_mul(p, alphas[a]);
+    }
+  }
+  if (gate == P2E_GATE_CHECK_SUM)
+    k_eval_check_sum_fc<<<grid_for(n), TPB, 0, st>>>(n, wires, is, F, P, out, os);
+  else if (params[0] == P2E_SECP256K1_BASE)
+    k_eval_mul_nonnative_fc<ModP><<<grid_for(n), TPB, 0, st>>>(n, wires, is, F, P, out, os);
+  else
+    k_eval_mul_nonnative_fc<ModN><<<grid_for(n), TPB, 0, st>>>(n, wires, is, F, P, out, os);
+  P2E_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // extern "C"
 
 // ---- host-pointer entry points: H2D, kernel, D2H, synchronise (stride == n)
@@ -866,6 +1085,32 @@ int p2e_eval_check_sum(size_t n, const uint64_t* wires, uint64_t* out) {
   return run_host(n, ins, 1, out, 2 * NL - 1, nullptr, [&](const uint64_t** d, uint64_t* o, uint32_t*, void* s) {
     return p2e_eval_check_sum_dev(n, d[0], n, o, n, s);
   });
+}
+
+int p2e_eval_filtered_combined(int gate, const int* params, int gate_index, int group_start, int group_end,
+                               int many_selectors, size_t n, const uint64_t* wires, const uint64_t* selector,
+                               const uint64_t* alphas, int n_alphas, uint64_t first_power, int accumulate, uint64_t* out) {
+  P2E_CHECK_READY();
+  int nw = 0, nc = 0, rc;
+  if ((rc = gate_shape(gate, params, &nw, &nc))) return rc;
+  if (n_alphas < 1 || n_alphas > MAX_ALPHAS) return set_error_msg("eval_filtered: n_alphas must be 1..4");
+  if (n == 0) return 0;
+  cudaStream_t st = ctx().stream;
+  void *din = nullptr, *dout = nullptr, *dscr = nullptr;
+  if ((rc = get_scratch(0, ((size_t)nw + 1) * n * 8, &din))) return rc;
+  if ((rc = get_scratch(1, (size_t)n_alphas * n * 8, &dout))) return rc;
+  if ((rc = get_scratch(3, p2e_eval_filtered_scratch_bytes(gate, params, n), &dscr))) return rc;
+  u64* dsel = (u64*)din + (size_t)nw * n;
+  P2E_CUDA(cudaMemcpyAsync(din, wires, (size_t)nw * n * 8, cudaMemcpyHostToDevice, st));
+  if (selector) P2E_CUDA(cudaMemcpyAsync(dsel, selector, n * 8, cudaMemcpyHostToDevice, st));
+  if (accumulate) P2E_CUDA(cudaMemcpyAsync(dout, out, (size_t)n_alphas * n * 8, cudaMemcpyHostToDevice, st));
+  if ((rc = p2e_eval_filtered_combined_dev(gate, params, gate_index, group_start, group_end, many_selectors, n,
+                                           (const uint64_t*)din, n, selector ? dsel : nullptr, alphas, n_alphas,
+                                           first_power, accumulate, (uint64_t*)dout, n, (uint64_t*)dscr, (void*)st)))
+    return rc;
+  P2E_CUDA(cudaMemcpyAsync(out, dout, (size_t)n_alphas * n * 8, cudaMemcpyDeviceToHost, st));
+  P2E_CUDA(cudaStreamSynchronize(st));
+  return 0;
 }
 
 double p2e_bench_imad(int wide, int iters) {

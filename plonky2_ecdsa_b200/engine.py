@@ -35,6 +35,7 @@ ERR_CONNECT = 128
 ERR_INTERNAL = 256
 
 UX_RANGE_CHECK, UX_COMPARISON, UX_ADD_MANY, UX_SUBTRACTION, UX_ARITHMETIC = 0, 1, 2, 3, 4
+GATE_MUL_NONNATIVE, GATE_CHECK_SUM, GATE_UX = 0, 1, 2
 
 MUL_OUT_R, MUL_OUT_Q, MUL_OUT_CHECK_SUM, MUL_OUT_CARRY, MUL_OUT_ROWS = 0, 9, 18, 35, 51
 
@@ -46,6 +47,7 @@ _u32p = ctypes.POINTER(ctypes.c_uint32)
 _sz = ctypes.c_size_t
 _vp = ctypes.c_void_p
 _int = ctypes.c_int
+_u64 = ctypes.c_uint64
 
 # name -> (restype, argtypes); every symbol include/p2e.h declares
 SIGNATURES = {
@@ -125,6 +127,11 @@ SIGNATURES = {
     "p2e_eval_ux": (_int, [_int, _int, _int, _int, _int, _sz, _vp, _vp]),
     "p2e_ux_witness_dev": (_int, [_int, _int, _int, _int, _int, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
     "p2e_ux_witness": (_int, [_int, _int, _int, _int, _int, _sz, _vp, _vp, _vp]),
+    "p2e_gate_shape": (_int, [_int, _vp, _vp, _vp]),
+    "p2e_eval_filtered_scratch_bytes": (_sz, [_int, _vp, _sz]),
+    "p2e_eval_filtered_combined_dev": (_int, [_int, _vp, _int, _int, _int, _int, _sz, _vp, _sz, _vp, _vp, _int, _u64, _int,
+                                              _vp, _sz, _vp, _vp]),
+    "p2e_eval_filtered_combined": (_int, [_int, _vp, _int, _int, _int, _int, _sz, _vp, _vp, _vp, _int, _u64, _int, _vp]),
     "p2e_ntt_scratch_bytes": (_sz, [_int, _int, _int]),
     "p2e_ntt_dev": (_int, [_int, _int, _int, _vp, _sz, _vp, _sz, _vp, _vp]),
     "p2e_ntt": (_int, [_int, _int, _int, _vp, _vp]),
@@ -434,6 +441,41 @@ class Engine:
 
     def eval_add_many_ux_gate(self, wires, num_addends=3, num_ops=5, bits=29, limb_bits=2):
         return self.eval_ux_gate(UX_ADD_MANY, wires, bits, limb_bits, num_ops, num_addends)
+
+    # ---------------------------------------------------------------- selector filtering + alpha-combination
+    def gate_shape(self, gate, params=()):
+        """(num_wires, num_constraints) of GATE_MUL_NONNATIVE (modulus,), GATE_CHECK_SUM () or GATE_UX
+        (ux gate, bits, limb_bits, count, num_addends)."""
+        prm = (ctypes.c_int * 5)(*(list(params) + [0] * 5)[:5])
+        nw, nc = ctypes.c_int(), ctypes.c_int()
+        self._check(self.lib.p2e_gate_shape(gate, ctypes.addressof(prm), ctypes.addressof(nw), ctypes.addressof(nc)))
+        return nw.value, nc.value
+
+    def eval_filtered_combined(self, gate, params, wires, alphas, selector=None, gate_index=0, group_range=(0, 1),
+                               many_selectors=False, first_power=0, accumulate_into=None):
+        """plonky2's Gate::eval_filtered_base_batch followed by this gate's share of
+        reduce_with_powers_multi (include/p2e.h): wires [num_wires][n_rows], selector [n_rows] or None ->
+        [len(alphas)][n_rows]; `accumulate_into` (same shape) is added to, as
+        evaluate_gate_constraints_base_batch sums the gates of a circuit."""
+        nw, _ = self.gate_shape(gate, params)
+        w = _host_u64(wires, nw)
+        n = w.shape[1]
+        prm = (ctypes.c_int * 5)(*(list(params) + [0] * 5)[:5])
+        al = np.ascontiguousarray(np.asarray(alphas, dtype=np.uint64))
+        sel = None if selector is None else np.ascontiguousarray(np.asarray(selector, dtype=np.uint64))
+        if sel is not None and sel.shape != (n,):
+            raise ValueError("selector must hold one constant per row")
+        if accumulate_into is None:
+            out = np.empty((len(al), n), dtype=np.uint64)
+        else:
+            out = np.ascontiguousarray(np.asarray(accumulate_into, dtype=np.uint64)).copy()
+            if out.shape != (len(al), n):
+                raise ValueError("accumulate_into must be [n_alphas][n_rows]")
+        self._check(self.lib.p2e_eval_filtered_combined(gate, ctypes.addressof(prm), gate_index, group_range[0],
+                                                        group_range[1], int(many_selectors), n, _ptr(w),
+                                                        None if sel is None else _ptr(sel), _ptr(al), len(al),
+                                                        first_power, int(accumulate_into is not None), _ptr(out)))
+        return out
 
     # ---------------------------------------------------------------- Goldilocks NTT / coset LDE
     def fft(self, values, inverse=False):
