@@ -271,6 +271,54 @@ int p2e_ux_witness_dev(int gate, int bits, int limb_bits, int count, int num_add
 int p2e_ux_witness(int gate, int bits, int limb_bits, int count, int num_addends, size_t n,
                    const uint64_t* inputs, uint64_t* row, uint32_t* err);
 
+/* ---- serialized generator streams + level-scheduled executor -------------
+ * A stream is the concatenation of records  u32 tag | SimpleGenerator::serialize() bytes  -- what plonky2's
+ * WitnessGeneratorSerializer::write_generator emits for a registry whose indices are the P2E_GEN_* tags
+ * below (the FF type parameter of the nonnative generators is not part of serialize(), so it is part of
+ * the tag).  Bodies are the reference's own (file:line per tag); primitives are plonky2's
+ * util::serialization (out of tree, restated): usize and field elements 8 bytes LE, u32 4 bytes LE, bool
+ * 1 byte, Target = bool is_wire then usize row, usize column (wire) or usize index (virtual),
+ * target_vec = usize length then targets.
+ * Three record kinds are not in-tree generators: P2E_GEN_COPY (two Targets of one copy-constraint
+ * partition -- CircuitBuilder::connect), and two plonky2 generators restated so that the bool / select
+ * glue of the gadgets can run in the same pass: P2E_GEN_CONSTANT = ConstantGenerator {usize row, usize
+ * constant_index, usize wire_index, field constant} and P2E_GEN_ARITHMETIC = ArithmeticBaseGenerator
+ * {usize row, field const_0, field const_1, usize i}: wire 4i+3 = const_0 * wire 4i * wire 4i+1 + const_1 *
+ * wire 4i+2.
+ * p2e_genstream_load parses a stream, joins copy partitions into SLOTS (rows of the value table), orders the
+ * generators into dependency levels (dependencies() = the targets a record reads) and returns a handle.
+ * p2e_genstream_run* executes every generator once, level by level, for n independent circuits:
+ * inputs = values of the slots no generator produces (p2e_genstream_input_slots), table [slots][stride].
+ * A slot written twice must receive equal values (plonky2: "partition set twice with different values"),
+ * otherwise err[i] gets P2E_ERR_CONNECT; generator panics set the usual P2E_ERR_* bits. */
+#define P2E_GEN_MUL_NONNATIVE_BASE 0              /* MulNonnativeGenerator<F,D,Secp256K1Base>   gates/mul_nonnative.rs:326-330 */
+#define P2E_GEN_MUL_NONNATIVE_SCALAR 1            /* MulNonnativeGenerator<F,D,Secp256K1Scalar>                               */
+#define P2E_GEN_CHECK_SUM 2                       /* CheckSumGenerator                          gates/mul_nonnative.rs:533-536 */
+#define P2E_GEN_NONNATIVE_ADDITION_BASE 3         /* NonNativeAdditionGenerator                 gadgets/nonnative.rs:647-652   */
+#define P2E_GEN_NONNATIVE_ADDITION_SCALAR 4
+#define P2E_GEN_NONNATIVE_MULTIPLE_ADDS_BASE 5    /* NonNativeMultipleAddsGenerator             gadgets/nonnative.rs:730-740   */
+#define P2E_GEN_NONNATIVE_MULTIPLE_ADDS_SCALAR 6
+#define P2E_GEN_NONNATIVE_SUBTRACTION_BASE 7      /* NonNativeSubtractionGenerator              gadgets/nonnative.rs:812-817   */
+#define P2E_GEN_NONNATIVE_SUBTRACTION_SCALAR 8
+#define P2E_GEN_NONNATIVE_INVERSE_BASE 9          /* NonNativeInverseGenerator                  gadgets/nonnative.rs:874-878   */
+#define P2E_GEN_NONNATIVE_INVERSE_SCALAR 10
+#define P2E_GEN_BIGUINT_DIV_REM 11                /* BigUintDivRemGenerator                     gadgets/biguint.rs:520-526     */
+#define P2E_GEN_GLV_DECOMPOSITION 12              /* GLVDecompositionGenerator                  gadgets/glv.rs:144-150         */
+#define P2E_GEN_COPY 13
+#define P2E_GEN_CONSTANT 14
+#define P2E_GEN_ARITHMETIC 15
+int p2e_genstream_load(const uint8_t* bytes, size_t len);          /* handle >= 0, or < 0 (p2e_last_error) */
+int p2e_genstream_free(int handle);
+long p2e_genstream_info(int handle, int what); /* 0 slots, 1 generators, 2 levels, 3 launch groups, 4 input slots, 5 targets */
+long p2e_genstream_slot(int handle, int is_wire, uint64_t row_or_index, uint64_t column);
+long p2e_genstream_input_slots(int handle, uint32_t* out, size_t cap);
+long p2e_genstream_generator_levels(int handle, int32_t* out, size_t cap);   /* level of generator k, in stream order */
+int p2e_genstream_run_dev(int handle, size_t n, const uint32_t* in_slots /* host */, int n_in,
+                          const uint64_t* in_values /* device [n_in][in_stride] */, size_t in_stride,
+                          uint64_t* table /* device [slots][stride] */, size_t stride, uint32_t* err, void* stream);
+int p2e_genstream_run(int handle, size_t n, const uint32_t* in_slots, int n_in, const uint64_t* in_values,
+                      const uint32_t* out_slots, int n_out, uint64_t* out_values, uint32_t* err);
+
 /* ---- selector filtering + alpha-combination around the gate evaluators ----------
  * The step after Gate::eval_unfiltered_base_batch in plonky2's quotient stage (out of tree, restated in
  * oracle/vanishing_spec.py): Gate::eval_filtered_base_batch multiplies a row's constraints by

@@ -127,6 +127,14 @@ SIGNATURES = {
     "p2e_eval_ux": (_int, [_int, _int, _int, _int, _int, _sz, _vp, _vp]),
     "p2e_ux_witness_dev": (_int, [_int, _int, _int, _int, _int, _sz, _vp, _sz, _vp, _sz, _vp, _vp]),
     "p2e_ux_witness": (_int, [_int, _int, _int, _int, _int, _sz, _vp, _vp, _vp]),
+    "p2e_genstream_load": (_int, [_vp, _sz]),
+    "p2e_genstream_free": (_int, [_int]),
+    "p2e_genstream_info": (ctypes.c_long, [_int, _int]),
+    "p2e_genstream_slot": (ctypes.c_long, [_int, _int, _u64, _u64]),
+    "p2e_genstream_input_slots": (ctypes.c_long, [_int, _vp, _sz]),
+    "p2e_genstream_generator_levels": (ctypes.c_long, [_int, _vp, _sz]),
+    "p2e_genstream_run_dev": (_int, [_int, _sz, _vp, _int, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "p2e_genstream_run": (_int, [_int, _sz, _vp, _int, _vp, _vp, _int, _vp, _vp]),
     "p2e_gate_shape": (_int, [_int, _vp, _vp, _vp]),
     "p2e_eval_filtered_scratch_bytes": (_sz, [_int, _vp, _sz]),
     "p2e_eval_filtered_combined_dev": (_int, [_int, _vp, _int, _int, _int, _int, _sz, _vp, _sz, _vp, _vp, _int, _u64, _int,
@@ -441,6 +449,12 @@ class Engine:
 
     def eval_add_many_ux_gate(self, wires, num_addends=3, num_ops=5, bits=29, limb_bits=2):
         return self.eval_ux_gate(UX_ADD_MANY, wires, bits, limb_bits, num_ops, num_addends)
+
+    # ---------------------------------------------------------------- serialized generator streams
+    def load_generator_stream(self, data: bytes):
+        """p2e_genstream_load: the level-scheduled executor over a serialized generator list."""
+        from .genstream import GeneratorStream
+        return GeneratorStream(self.lib, data, P2EError)
 
     # ---------------------------------------------------------------- selector filtering + alpha-combination
     def gate_shape(self, gate, params=()):
