@@ -1195,14 +1195,26 @@ __global__ void __launch_bounds__(32) k_chain_checks(ChainArgs A) {
 // (bit 29 marks the first carry of a CheckSum tuple) or the narrow row
 __global__ void __launch_bounds__(256) k_pack_compact(size_t n, size_t n_slots, const u64* __restrict__ wit, size_t ws,
                                                       const u32* __restrict__ map, u32* __restrict__ narrow,
-                                                      u64* __restrict__ wide) {
+                                                      u64* __restrict__ wide, u32* __restrict__ err) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   for (size_t s = blockIdx.y; s < n_slots; s += gridDim.y) {
     const u32 m = map[s];
     const u64 v = wit[s * ws + i];
     if (m >> 31) {
-      wide[(size_t)(m & 0x7fffffffu) * n + i] = v;
+      if (wide) {
+        wide[(size_t)(m & 0x7fffffffu) * n + i] = v;
+      } else {
+        // derived form: check_sum column j of a MUL tuple is not shipped, the host rebuilds it from the carries of the
+        // CheckSum tuple that follows (a_j + c_{j-1} = 2^29 c_j exactly, c_j = b_j - 2^33; the last column is -c_15:
+        // gates/mul_nonnative.rs:411-427 with every constraint zero).  Verified here; a row that is not of this form
+        // (only rows whose generator already raised an error) is flagged.
+        const int j = (int)((m & 0x7fffffffu) % 17u);
+        const i64 cprev = j ? (i64)wit[(s + 16) * ws + i] - ((i64)1 << 33) : 0;
+        const i64 ccur = j < 16 ? (i64)wit[(s + 17) * ws + i] - ((i64)1 << 33) : 0;
+        const i64 expect = ccur * ((i64)1 << LB) - cprev;
+        if (gl_from_i64(expect) != v) atomicOr(&err[i], (u32)ERR_CARRY_RANGE);
+      }
     } else if (m & (1u << 30)) {
       // CheckSum carry b_j < 2^34: low word in its own narrow row; the 16 two-bit tops of the tuple share
       // the narrow row after them, written by the thread that handles the tuple's first slot
@@ -1698,7 +1710,7 @@ int p2e_tape_witness_compact(int tape, size_t n, const uint64_t* const* inputs, 
   if ((rc = get_scratch(0, (size_t)n_in * 9 * n * 8, &din))) return rc;
   if ((rc = get_scratch(1, (size_t)t.n_slots * cn * 8, &dout))) return rc;
   if ((rc = get_scratch(2, n * 4, &derr))) return rc;
-  const size_t nbytes = (size_t)nn * cn * 4, wbytes = (size_t)nw * cn * 8;          // per chunk
+  const size_t nbytes = (size_t)nn * cn * 4, wbytes = wide ? (size_t)nw * cn * 8 : 0;          // per chunk
   const size_t region = ((nbytes + 15) / 16) * 16 + ((wbytes + 15) / 16) * 16;
   if ((rc = get_scratch(3, region * n_chunks, &dpack))) return rc;
   const uint64_t* dptr[MAX_TAPE_INPUTS];
@@ -1713,12 +1725,13 @@ int p2e_tape_witness_compact(int tape, size_t n, const uint64_t* const* inputs, 
     for (int k = 0; k < n_in; k++) dptr[k] = (const uint64_t*)din + (size_t)k * 9 * n + c0;
     if ((rc = run_tape(tape, t, cc, dptr, n_in, n, (uint64_t*)dout, cn, (uint32_t*)derr + c0, (void*)st))) return rc;
     k_pack_compact<<<dim3((unsigned)((cc + 255) / 256), 1024), 256, 0, st>>>(cc, t.n_slots, (const u64*)dout, cn,
-                                                                            (const u32*)dmaps[tape], dn, dw);
+                                                                            (const u32*)dmaps[tape], dn, wide ? dw : nullptr,
+                                                                            (uint32_t*)derr + c0);
     P2E_CUDA(cudaGetLastError());
     P2E_CUDA(cudaEventRecord(ev_done[c], st));
     P2E_CUDA(cudaStreamWaitEvent(cp, ev_done[c], 0));
     P2E_CUDA(cudaMemcpy2DAsync(narrow + c0, n * 4, dn, cc * 4, cc * 4, nn, cudaMemcpyDeviceToHost, cp));
-    P2E_CUDA(cudaMemcpy2DAsync(wide + c0, n * 8, dw, cc * 8, cc * 8, nw, cudaMemcpyDeviceToHost, cp));
+    if (wide) P2E_CUDA(cudaMemcpy2DAsync(wide + c0, n * 8, dw, cc * 8, cc * 8, nw, cudaMemcpyDeviceToHost, cp));
     if (err) P2E_CUDA(cudaMemcpyAsync(err + c0, (uint32_t*)derr + c0, cc * 4, cudaMemcpyDeviceToHost, cp));
   }
   P2E_CUDA(cudaStreamSynchronize(st));

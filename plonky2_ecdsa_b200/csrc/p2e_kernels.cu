@@ -532,19 +532,74 @@ __device__ __forceinline__ u64 compute_filter(const FilterArgs& F, size_t i) {
   return f;
 }
 
+// sum_c v_c * alpha^(e0 + c) accumulated un-reduced: the four 32x32 partial-product classes of every
+// 64x64 product go to three 96-bit accumulators (17 terms stay far below 2^96), one reduction per challenge
+// at the end -- 12 instructions per (constraint, challenge) instead of a full Goldilocks multiply-reduce-add.
+template <int NA>
 struct CombineSink17 {
   const AlphaPow17* P;
-  int n_alphas;
-  u64 acc[MAX_ALPHAS];
-  __device__ __forceinline__ void put(int c, u64 v) {
+  Acc3 A[NA], B[NA], C[NA];
+  __device__ __forceinline__ void init() {
 #pragma unroll
-    for (int a = 0; a < MAX_ALPHAS; a++)
-      if (a < n_alphas) acc[a] = gl_add(acc[a], gl_mul(v, P->p[a][c]));
+    for (int a = 0; a < NA; a++) A[a] = B[a] = C[a] = Acc3{0, 0, 0};
   }
+  __device__ __forceinline__ void put(int c, u64 v) {
+    const u32 vl = (u32)v, vh = (u32)(v >> 32);
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+      const u64 pw = P->p[a][c];
+      const u32 pl = (u32)pw, ph = (u32)(pw >> 32);
+      mac3(A[a], vl, pl);
+      mac3(B[a], vl, ph);
+      mac3(B[a], vh, pl);
+      mac3(C[a], vh, ph);
+    }
+  }
+  __device__ __forceinline__ u64 result(int a) const { return reduce_abc(A[a], B[a], C[a], 0); }
 };
 
-__device__ __forceinline__ void store_combined(const FilterArgs& F, const u64* acc, u64 f, u64* __restrict__ out, size_t os,
-                                               size_t i) {
+template <int NA>
+__device__ __forceinline__ void store_combined(const FilterArgs& F, const CombineSink17<NA>& sink, u64 f, u64* __restrict__ out,
+                                               size_t os, size_t i) {
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+    if (a < F.n_alphas) {
+      u64 r = gl_mul(f, sink.result(a));
+      if (F.accumulate) r = gl_add(r, out[a * os + i]);
+      out[a * os + i] = r;
+    }
+  }
+}
+
+template <class MOD, int NA>
+__global__ void __launch_bounds__(TPB, 4)
+k_eval_mul_nonnative_fc(size_t n, const u64* __restrict__ wires, size_t is, FilterArgs F, const __grid_constant__ AlphaPow17 P,
+                        u64* __restrict__ out, size_t os) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  CombineSink17<NA> sink;
+  sink.P = &P;
+  sink.init();
+  sink = eval_mul_nonnative_row<MOD>(wires, is, i, sink);
+  store_combined<NA>(F, sink, compute_filter(F, i), out, os, i);
+}
+
+template <int NA>
+__global__ void __launch_bounds__(TPB)
+k_eval_check_sum_fc(size_t n, const u64* __restrict__ wires, size_t is, FilterArgs F, const __grid_constant__ AlphaPow17 P,
+                    u64* __restrict__ out, size_t os) {
+  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
+  if (i >= n) return;
+  CombineSink17<NA> sink;
+  sink.P = &P;
+  sink.init();
+  sink = eval_check_sum_row(wires, is, i, sink);
+  store_combined<NA>(F, sink, compute_filter(F, i), out, os, i);
+}
+
+// the generic kernel's per-row store
+__device__ __forceinline__ void store_combined_acc(const FilterArgs& F, const u64* acc, u64 f, u64* __restrict__ out, size_t os,
+                                                   size_t i) {
 #pragma unroll
   for (int a = 0; a < MAX_ALPHAS; a++) {
     if (a < F.n_alphas) {
@@ -553,27 +608,6 @@ __device__ __forceinline__ void store_combined(const FilterArgs& F, const u64* a
       out[a * os + i] = r;
     }
   }
-}
-
-template <class MOD>
-__global__ void __launch_bounds__(TPB, 4)
-k_eval_mul_nonnative_fc(size_t n, const u64* __restrict__ wires, size_t is, FilterArgs F, const __grid_constant__ AlphaPow17 P,
-                        u64* __restrict__ out, size_t os) {
-  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
-  CombineSink17 sink = {&P, F.n_alphas, {0, 0, 0, 0}};
-  sink = eval_mul_nonnative_row<MOD>(wires, is, i, sink);
-  store_combined(F, sink.acc, compute_filter(F, i), out, os, i);
-}
-
-__global__ void __launch_bounds__(TPB)
-k_eval_check_sum_fc(size_t n, const u64* __restrict__ wires, size_t is, FilterArgs F, const __grid_constant__ AlphaPow17 P,
-                    u64* __restrict__ out, size_t os) {
-  size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
-  if (i >= n) return;
-  CombineSink17 sink = {&P, F.n_alphas, {0, 0, 0, 0}};
-  sink = eval_check_sum_row(wires, is, i, sink);
-  store_combined(F, sink.acc, compute_filter(F, i), out, os, i);
 }
 
 // generic form (any gate): constraints [C][n] already evaluated -> filter, combine with the power table [n_alphas][C]
@@ -589,7 +623,7 @@ k_filter_combine(size_t n, int C, const u64* __restrict__ cons, size_t cs, const
     for (int a = 0; a < MAX_ALPHAS; a++)
       if (a < F.n_alphas) acc[a] = gl_add(acc[a], gl_mul(v, __ldg(pw + (size_t)a * C + c)));
   }
-  store_combined(F, acc, compute_filter(F, i), out, os, i);
+  store_combined_acc(F, acc, compute_filter(F, i), out, os, i);
 }
 
 // pw[a][c] = alpha_a^(first_power + c)
@@ -959,12 +993,20 @@ int p2e_eval_filtered_combined_dev(int gate, const int* params, int gate_index, 
       if (a < n_alphas) p = gl_mul(p, alphas[a]);
     }
   }
-  if (gate == P2E_GATE_CHECK_SUM)
-    k_eval_check_sum_fc<<<grid_for(n), TPB, 0, st>>>(n, wires, is, F, P, out, os);
-  else if (params[0] == P2E_SECP256K1_BASE)
-    k_eval_mul_nonnative_fc<ModP><<<grid_for(n), TPB, 0, st>>>(n, wires, is, F, P, out, os);
-  else
-    k_eval_mul_nonnative_fc<ModN><<<grid_for(n), TPB, 0, st>>>(n, wires, is, F, P, out, os);
+  // instantiated for 1, 2 and 4 challenges (3 runs as 4 with a zero power row; plonky2's standard config has 2)
+#define P2E_FC_LAUNCH(NA)                                                                                  \
+  do {                                                                                                     \
+    if (gate == P2E_GATE_CHECK_SUM)                                                                        \
+      k_eval_check_sum_fc<NA><<<grid_for(n), TPB, 0, st>>>(n, wires, is, F, P, out, os);                   \
+    else if (params[0] == P2E_SECP256K1_BASE)                                                              \
+      k_eval_mul_nonnative_fc<ModP, NA><<<grid_for(n), TPB, 0, st>>>(n, wires, is, F, P, out, os);         \
+    else                                                                                                   \
+      k_eval_mul_nonnative_fc<ModN, NA><<<grid_for(n), TPB, 0, st>>>(n, wires, is, F, P, out, os);         \
+  } while (0)
+  if (n_alphas == 1) P2E_FC_LAUNCH(1);
+  else if (n_alphas == 2) P2E_FC_LAUNCH(2);
+  else P2E_FC_LAUNCH(4);
+#undef P2E_FC_LAUNCH
   P2E_LAUNCH_CHECK();
   return 0;
 }

@@ -549,32 +549,48 @@ class Engine:
         self.lib.p2e_tape_compact_layout(tape, _ptr(m), ctypes.addressof(nn), ctypes.addressof(nw))
         return m, int(nn.value), int(nw.value)
 
-    def tape_witness_compact(self, tape, inputs):
-        """Like tape_witness but in the compact host format: (narrow [ns][n] uint32, wide [ws][n] uint64, err)."""
+    def tape_witness_compact(self, tape, inputs, derive_check_sum=False):
+        """Like tape_witness but in the compact host format: (narrow [ns][n] uint32, wide [ws][n] uint64, err).
+        derive_check_sum: the derived form -- no `wide` matrix is shipped (returned as None), the check_sum
+        slots are rebuilt from the carries by expand_compact (include/p2e.h)."""
         ins = [_host_u64(a, 9) for a in inputs]
         n = ins[0].shape[1]
         _, nn, nw = self.tape_compact_layout(tape)
         narrow = np.empty((nn, n), dtype=np.uint32)
-        wide = np.empty((nw, n), dtype=np.uint64)
+        wide = None if derive_check_sum else np.empty((nw, n), dtype=np.uint64)
         err = np.empty(n, dtype=np.uint32)
         arr = (ctypes.c_void_p * len(ins))(*[a.ctypes.data for a in ins])
-        self._check(self.lib.p2e_tape_witness_compact(tape, n, ctypes.cast(arr, ctypes.c_void_p), _ptr(narrow), _ptr(wide), _ptr(err)))
+        self._check(self.lib.p2e_tape_witness_compact(tape, n, ctypes.cast(arr, ctypes.c_void_p), _ptr(narrow),
+                                                      None if wide is None else _ptr(wide), _ptr(err)))
         return narrow, wide, err
 
     @staticmethod
-    def expand_compact(cmap, narrow, wide):
-        """Compact -> plain [slots][n] uint64 (host-side helper for tests / the Rust shim's unpack)."""
+    def expand_compact(cmap, narrow, wide=None):
+        """Compact -> plain [slots][n] uint64 (host-side helper for tests / the Rust shim's unpack).
+        wide=None: the derived form -- check_sum slots are rebuilt from the carries (include/p2e.h)."""
         out = np.empty((cmap.shape[0], narrow.shape[1]), dtype=np.uint64)
         is_wide = (cmap >> np.uint32(31)).astype(bool)
         is_carry = ((cmap >> np.uint32(30)) & np.uint32(1)).astype(bool) & ~is_wide
         plain = ~is_wide & ~is_carry
-        out[is_wide] = wide[cmap[is_wide] & np.uint32(0x7FFFFFFF)]
         out[plain] = narrow[cmap[plain]]
         # CheckSum carries: 16 low words, then one word holding the 16 two-bit tops of the tuple
         rows = (cmap[is_carry] & np.uint32(0x1FFFFFFF)).astype(np.int64)
         j = np.arange(rows.shape[0]) % 16
         tops = (narrow[rows - j + 16].astype(np.uint64) >> (2 * j[:, None]).astype(np.uint64)) & np.uint64(3)
         out[is_carry] = narrow[rows].astype(np.uint64) | (tops << np.uint64(32))
+        if wide is not None:
+            out[is_wide] = wide[cmap[is_wide] & np.uint32(0x7FFFFFFF)]
+        else:
+            # check_sum_j = c_j * 2^29 - c_{j-1} with c_j = b_j - 2^33 (c_{-1} = c_16 = 0), as a Goldilocks element;
+            # the carries of a MUL tuple's CheckSum tuple sit 17 slots after the matching check_sum slot
+            ws = np.nonzero(is_wide)[0]
+            jj = (cmap[ws] & np.uint32(0x7FFFFFFF)).astype(np.int64) % 17
+            off = np.int64(1) << np.int64(33)
+            cur = np.where((jj < 16)[:, None], out[np.minimum(ws + 17, cmap.shape[0] - 1)].astype(np.int64) - off, 0)
+            prev = np.where((jj > 0)[:, None], out[ws + 16].astype(np.int64) - off, 0)
+            v = cur * (np.int64(1) << np.int64(29)) - prev                     # |v| < 2^62
+            gl_p = np.uint64(0xFFFFFFFF00000001)
+            out[ws] = np.where(v < 0, (v.astype(np.uint64) + gl_p), v.astype(np.uint64))
         return out
 
     def curve_add(self, x1, y1, x2, y2):

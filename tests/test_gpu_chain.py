@@ -272,6 +272,28 @@ def test_compact_host_format_chunked_copy(engine):
 
 
 @pytest.mark.gpu
+def test_compact_derived_form_rebuilds_check_sum_from_carries(engine):
+    """Derived compact form (wide == NULL): the check_sum slots are not shipped; expand_compact rebuilds them from
+    the CheckSum carries and the result is the plain witness, bit for bit (chunked path, ragged last chunk)."""
+    n = 1100 + 3
+    wl = W.ecdsa_workload(n, seed=18)
+    ins = [wl[k] for k in ("msg", "r", "s", "pkx", "pky")]
+    plain, e1 = engine.verify_secp256k1_message_witness(*ins)
+    cmap, nn, nw = engine.tape_compact_layout(engine.TAPE_ECDSA)
+    narrow, wide, e2 = engine.tape_witness_compact(engine.TAPE_ECDSA, ins, derive_check_sum=True)
+    assert wide is None and narrow.shape == (nn, n)
+    assert not e1.any() and not e2.any()                    # the device verified the identity for every row
+    assert np.array_equal(engine.expand_compact(cmap, narrow), plain)
+    # the generic tapes as well (curve_add: 3 products)
+    wl = W.ecdsa_workload(5, seed=3)
+    pts = [wl["pkx"], wl["pky"], np.roll(wl["pkx"], 1, axis=1), np.roll(wl["pky"], 1, axis=1)]
+    plain, _ = engine.tape_witness(engine.TAPE_CURVE_ADD, pts)
+    cmap, nn, nw = engine.tape_compact_layout(engine.TAPE_CURVE_ADD)
+    narrow, _, e = engine.tape_witness_compact(engine.TAPE_CURVE_ADD, pts, derive_check_sum=True)
+    assert not e.any() and np.array_equal(engine.expand_compact(cmap, narrow), plain)
+
+
+@pytest.mark.gpu
 def test_ecdsa_batch_vs_c_oracle(engine):
     """Every slot of 768 complete witnesses against the C restatement of the reference's generators
     (oracle/p2e_oracle.c, itself pinned to the Python spec by tests/test_oracle_c.py): one Fermat ladder

@@ -109,3 +109,33 @@ def test_compact_layout_map():
     assert not (flat[~wide & ~carry] >> np.uint64(32)).any()
     assert (flat[wide] >> np.uint64(32)).any()
     assert not (flat[carry] >> np.uint64(34)).any() and (flat[carry] >> np.uint64(32)).any()
+
+
+def test_derived_compact_form_rebuilds_check_sum_slots_of_an_oracle_witness():
+    """Derived compact form (include/p2e.h, wide == NULL): the check_sum columns a MulNonnativeGenerator writes
+    (gates/mul_nonnative.rs:305-322) are exactly c_j 2^29 - c_{j-1} for the carries c_j = b_j - 2^33 the
+    CheckSumGenerator derives from them (:513-531); checked on a witness computed by the oracle with the
+    reference's literal arithmetic (Goldilocks column sums, field division per carry)."""
+    import ctypes
+    lib = pkg.load_library()
+    slots = int(lib.p2e_tape_slots(0))
+    m = np.empty(slots, dtype=np.uint32)
+    nn, nw = ctypes.c_uint32(0), ctypes.c_uint32(0)
+    lib.p2e_tape_compact_layout(0, m.ctypes.data, ctypes.addressof(nn), ctypes.addressof(nw))
+    sk, msg, k = 0x7654321 << 190 | 3, 0xfedcba << 170 | 11, 0x999 << 211 | 7
+    r, s = S.sign_message(msg, sk, k)
+    flat = np.array(S.ecdsa_witness(msg, r, s, S.pt_mul(sk, S.G)).flat(), dtype=np.uint64)
+    # pack what the device ships in the derived form: narrow rows only
+    narrow = np.zeros((nn.value, 1), dtype=np.uint32)
+    wide = (m >> np.uint32(31)).astype(bool)
+    carry = ((m >> np.uint32(30)) & np.uint32(1)).astype(bool) & ~wide
+    plain = ~wide & ~carry
+    narrow[m[plain], 0] = flat[plain].astype(np.uint32)
+    rows = (m[carry] & np.uint32(0x1FFFFFFF)).astype(np.int64)
+    narrow[rows, 0] = (flat[carry] & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    j = np.arange(rows.shape[0]) % 16
+    tops = ((flat[carry] >> np.uint64(32)) & np.uint64(3)).astype(np.uint32) << (2 * j).astype(np.uint32)
+    np.bitwise_or.at(narrow[:, 0], rows - j + 16, tops)
+    got = pkg.Engine.expand_compact(m, narrow)
+    assert np.array_equal(got[:, 0], flat)
+    assert (flat[wide] >> np.uint64(62)).any()              # negative columns (P - |v|) are among them
