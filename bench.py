@@ -35,6 +35,7 @@ WORKLOAD_NAMES = {
     "evalcmp": "u29 comparison gate (2-bit chunks; plonky2_ux spec unpinned) eval over 2^20 Goldilocks LDE rows",
     "evaladd": "u29 add-many gate (3 addends, 5 ops / row; plonky2_ux spec unpinned) eval over 2^20 Goldilocks LDE rows",
     "evalfc": "MulNonnativeGate eval_filtered_base_batch + alpha-combination (2 challenges, fused) over 2^20 Goldilocks LDE rows",
+    "evalcsfc": "CheckSumGate eval_filtered_base_batch + alpha-combination (2 challenges, fused) over 2^20 Goldilocks LDE rows",
     "lde": "coset LDE (ifft 2^17 -> zero-pad -> coset fft 2^20, rate 8) of 135 wire polynomials: the matrix the gate evaluators read",
 }
 # plonky2_ux eval workloads: (gate, bits, limb_bits, count, num_addends, kernel)
@@ -53,6 +54,7 @@ METRICS = {
     "evalcmp": ("ux_comparison_gate_rows_per_s", "rows/s"),
     "evaladd": ("ux_add_many_gate_rows_per_s", "rows/s"),
     "evalfc": ("mul_nonnative_gate_filtered_combined_rows_per_s", "rows/s"),
+    "evalcsfc": ("check_sum_gate_filtered_combined_rows_per_s", "rows/s"),
     "lde": ("coset_lde_output_elements_per_s", "elements/s"),
 }
 
@@ -281,31 +283,32 @@ class Bench:
                 assert rc == 0, eng.last_error()
             return dict(step=step, step_e2e=step_e2e, units=n, h2d=33 * 8 * n, d2h=17 * 8 * n, alg_bytes=400 * n,
                         kernel="k_eval_check_sum", launches=1, err=None, dtype="u64 (Goldilocks)", keep=(wd, od, hw, ho))
-        if wl == "evalfc":
+        if wl in ("evalfc", "evalcsfc"):
             import ctypes
+            gate, nw = (0, 53) if wl == "evalfc" else (1, 33)
             n = 1 << 20
-            w = W.random_goldilocks(W.SEED + 5 + self.rank, 54, n)      # 53 wires + the selector constant column
-            w[53, ::3] = 0                                               # a third of the rows select this gate exactly
+            w = W.random_goldilocks(W.SEED + 5 + gate + self.rank, nw + 1, n)      # the wires + the selector constant column
+            w[nw, ::3] = 0                                                          # a third of the rows select this gate exactly
             wd = self.dev(w)
             od = torch.empty((2, n), dtype=torch.int64, device="cuda")
             prm = (ctypes.c_int * 5)(0, 0, 0, 0, 0)
             alphas = np.array([0x0123456789ABCDEF, 0xFEDCBA9876543210 % ((1 << 64) - (1 << 32) + 1)], dtype=np.uint64)
-            sel_ptr = wd.data_ptr() + 53 * n * 8
+            sel_ptr = wd.data_ptr() + nw * n * 8
 
             def step():
-                rc = lib.p2e_eval_filtered_combined_dev(0, ctypes.addressof(prm), 0, 0, 4, 1, n, wd.data_ptr(), n, sel_ptr,
+                rc = lib.p2e_eval_filtered_combined_dev(gate, ctypes.addressof(prm), 0, 0, 4, 1, n, wd.data_ptr(), n, sel_ptr,
                                                         alphas.ctypes.data, 2, 4, 0, od.data_ptr(), n, None, sp)
                 assert rc == 0, eng.last_error()
             hw = self.pinned(w)
             ho = torch.empty((2, n), dtype=torch.int64).pin_memory()
 
             def step_e2e():
-                rc = lib.p2e_eval_filtered_combined(0, ctypes.addressof(prm), 0, 0, 4, 1, n, hw.data_ptr(), hw.data_ptr() + 53 * n * 8,
+                rc = lib.p2e_eval_filtered_combined(gate, ctypes.addressof(prm), 0, 0, 4, 1, n, hw.data_ptr(), hw.data_ptr() + nw * n * 8,
                                                     alphas.ctypes.data, 2, 4, 0, ho.data_ptr())
                 assert rc == 0, eng.last_error()
-            return dict(step=step, step_e2e=step_e2e, units=n, h2d=54 * 8 * n, d2h=2 * 8 * n, alg_bytes=(54 + 2) * 8 * n,
-                        kernel="k_eval_mul_nonnative_fc<ModP>", launches=1, err=None, dtype="u64 (Goldilocks)",
-                        keep=(wd, od, hw, ho, prm, alphas))
+            return dict(step=step, step_e2e=step_e2e, units=n, h2d=(nw + 1) * 8 * n, d2h=2 * 8 * n, alg_bytes=(nw + 1 + 2) * 8 * n,
+                        kernel="k_eval_mul_nonnative_fc<2>" if gate == 0 else "k_eval_check_sum_fc<2>", launches=1, err=None,
+                        dtype="u64 (Goldilocks)", keep=(wd, od, hw, ho, prm, alphas))
         if wl in UX_WORKLOADS:
             gate, bits, lb, count, na, kname = UX_WORKLOADS[wl]
             nw, nc, _ = eng.ux_gate_shape(gate, bits, lb, count, na)
@@ -601,7 +604,7 @@ def main():
     main_res = b.measure(wl, args.steps, args.warmup, e2e_steps=max(2, min(args.steps, 5)), sample_clocks=True)
     secondary = {}
     if not args.no_secondary:
-        for w2 in ("mulmod", "eval", "evalcs", "evalfc", "evalrc", "evalcmp", "evaladd", "lde", "glv", "ecdsa"):
+        for w2 in ("mulmod", "eval", "evalcs", "evalfc", "evalcsfc", "evalrc", "evalcmp", "evaladd", "lde", "glv", "ecdsa"):
             if w2 != wl:
                 try:
                     r2 = b.measure(w2, steps=min(args.steps, 20) if w2 != "glv" else 3, warmup=3, e2e_steps=2)

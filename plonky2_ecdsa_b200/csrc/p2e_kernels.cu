@@ -519,7 +519,11 @@ struct FilterArgs {
   int n_alphas, accumulate;
 };
 struct AlphaPow17 {
-  u64 p[MAX_ALPHAS][2 * NL - 1];
+  u64 p[MAX_ALPHAS][2 * NL - 1];   // alpha_a^c
+  u64 scale[MAX_ALPHAS];           // alpha_a^first_power
+  u64 ma[MAX_ALPHAS];              // MulNonnative: M(alpha_a) = sum_j m_j alpha_a^j for the gate's modulus
+                                   // CheckSum: alpha_a - 2^29
+  u64 kb[MAX_ALPHAS];              // CheckSum: 2^33 * sum_{i<16} alpha_a^i
 };
 
 __device__ __forceinline__ u64 compute_filter(const FilterArgs& F, size_t i) {
@@ -532,22 +536,24 @@ __device__ __forceinline__ u64 compute_filter(const FilterArgs& F, size_t i) {
   return f;
 }
 
-// sum_c v_c * alpha^(e0 + c) accumulated un-reduced: the four 32x32 partial-product classes of every
-// 64x64 product go to three 96-bit accumulators (17 terms stay far below 2^96), one reduction per challenge
-// at the end -- 12 instructions per (constraint, challenge) instead of a full Goldilocks multiply-reduce-add.
-template <int NA>
-struct CombineSink17 {
-  const AlphaPow17* P;
+// MulNonnativeGate, fused.  The alpha-combination of a convolution is a product of evaluations:
+//   sum_c alpha^c constraint_c = M(alpha) Q(alpha) - X(alpha) Y(alpha) + R(alpha) - CS(alpha),
+// X(alpha) = sum_j x_j alpha^j etc. (constraint_c = sum_j (m_j q_{c-j} - x_j y_{c-j}) + r_c - check_sum_c,
+// gates/mul_nonnative.rs:101-130) -- the same field element as evaluating the 17 constraints and folding them,
+// for 53 lazily accumulated products and 2 multiplications per challenge instead of 162 + 17.
+// res[a] = sum_{j < LEN} v[j] * alpha_a^(j) over already-loaded wires, accumulated un-reduced (three 96-bit
+// accumulators per challenge: 12 instructions per product), one reduction per challenge
+template <int NA, int LEN>
+__device__ __forceinline__ void poly_at_alphas(const u64 (&v)[LEN], const AlphaPow17& P, u64 (&res)[NA]) {
   Acc3 A[NA], B[NA], C[NA];
-  __device__ __forceinline__ void init() {
 #pragma unroll
-    for (int a = 0; a < NA; a++) A[a] = B[a] = C[a] = Acc3{0, 0, 0};
-  }
-  __device__ __forceinline__ void put(int c, u64 v) {
-    const u32 vl = (u32)v, vh = (u32)(v >> 32);
+  for (int a = 0; a < NA; a++) A[a] = B[a] = C[a] = Acc3{0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < LEN; j++) {
+    const u32 vl = (u32)v[j], vh = (u32)(v[j] >> 32);
 #pragma unroll
     for (int a = 0; a < NA; a++) {
-      const u64 pw = P->p[a][c];
+      const u64 pw = P.p[a][j];
       const u32 pl = (u32)pw, ph = (u32)(pw >> 32);
       mac3(A[a], vl, pl);
       mac3(B[a], vl, ph);
@@ -555,46 +561,81 @@ struct CombineSink17 {
       mac3(C[a], vh, ph);
     }
   }
-  __device__ __forceinline__ u64 result(int a) const { return reduce_abc(A[a], B[a], C[a], 0); }
-};
+#pragma unroll
+  for (int a = 0; a < NA; a++) res[a] = reduce_abc(A[a], B[a], C[a], 0);
+}
+template <int LEN>
+__device__ __forceinline__ void load_run(const u64* __restrict__ wires, size_t is, size_t i, int first_wire, u64 (&v)[LEN]) {
+#pragma unroll
+  for (int j = 0; j < LEN; j++) v[j] = wires[(size_t)(first_wire + j) * is + i];
+}
 
 template <int NA>
-__device__ __forceinline__ void store_combined(const FilterArgs& F, const CombineSink17<NA>& sink, u64 f, u64* __restrict__ out,
-                                               size_t os, size_t i) {
+__device__ __forceinline__ void store_scaled(const FilterArgs& F, const AlphaPow17& P, const u64 (&t)[NA], u64 f,
+                                             u64* __restrict__ out, size_t os, size_t i) {
 #pragma unroll
   for (int a = 0; a < NA; a++) {
     if (a < F.n_alphas) {
-      u64 r = gl_mul(f, sink.result(a));
+      u64 r = gl_mul(gl_mul(f, P.scale[a]), t[a]);
       if (F.accumulate) r = gl_add(r, out[a * os + i]);
       out[a * os + i] = r;
     }
   }
 }
 
-template <class MOD, int NA>
+// Loads are issued in two waves (x, y, r: 27 wires; q, check_sum: 26 wires) so that a warp keeps ~7 KB in flight:
+// the kernel is bound by load latency otherwise (ncu: long_scoreboard 10.6 per issue with 9-wire waves).
+template <int NA>
 __global__ void __launch_bounds__(TPB, 4)
 k_eval_mul_nonnative_fc(size_t n, const u64* __restrict__ wires, size_t is, FilterArgs F, const __grid_constant__ AlphaPow17 P,
                         u64* __restrict__ out, size_t os) {
   size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
-  CombineSink17<NA> sink;
-  sink.P = &P;
-  sink.init();
-  sink = eval_mul_nonnative_row<MOD>(wires, is, i, sink);
-  store_combined<NA>(F, sink, compute_filter(F, i), out, os, i);
+  u64 X[NA], Y[NA], R[NA], Q[NA], CS[NA];
+  {
+    u64 x[NL], y[NL], r[NL];
+    load_run<NL>(wires, is, i, 0, x);
+    load_run<NL>(wires, is, i, NL, y);
+    load_run<NL>(wires, is, i, 2 * NL, r);
+    poly_at_alphas<NA, NL>(x, P, X);
+    poly_at_alphas<NA, NL>(y, P, Y);
+    poly_at_alphas<NA, NL>(r, P, R);
+  }
+  {
+    u64 q[NL], cs[2 * NL - 1];
+    load_run<NL>(wires, is, i, 3 * NL, q);
+    load_run<2 * NL - 1>(wires, is, i, 4 * NL, cs);
+    poly_at_alphas<NA, NL>(q, P, Q);
+    poly_at_alphas<NA, 2 * NL - 1>(cs, P, CS);
+  }
+  const u64 f = compute_filter(F, i);
+  u64 t[NA];
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+    t[a] = gl_sub(gl_mul(Q[a], P.ma[a]), gl_mul(X[a], Y[a]));
+    t[a] = gl_sub(gl_add(t[a], R[a]), CS[a]);
+  }
+  store_scaled<NA>(F, P, t, f, out, os, i);
 }
 
+// CheckSumGate, fused: with o_i = b_i - 2^33 the constraints are c_i = a_i + o_{i-1} - 2^29 o_i (i < 16), c_16 = a_16 + o_15
+// (gates/mul_nonnative.rs:411-427), so  sum_i alpha^i c_i = A(alpha) + (alpha - 2^29) (B(alpha) - 2^33 sum_{i<16} alpha^i).
 template <int NA>
 __global__ void __launch_bounds__(TPB)
 k_eval_check_sum_fc(size_t n, const u64* __restrict__ wires, size_t is, FilterArgs F, const __grid_constant__ AlphaPow17 P,
                     u64* __restrict__ out, size_t os) {
   size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
-  CombineSink17<NA> sink;
-  sink.P = &P;
-  sink.init();
-  sink = eval_check_sum_row(wires, is, i, sink);
-  store_combined<NA>(F, sink, compute_filter(F, i), out, os, i);
+  u64 a[2 * NL - 1], b[2 * NL - 2];
+  load_run<2 * NL - 1>(wires, is, i, 0, a);
+  load_run<2 * NL - 2>(wires, is, i, 2 * NL - 1, b);
+  u64 Aa[NA], Bb[NA], t[NA];
+  poly_at_alphas<NA, 2 * NL - 1>(a, P, Aa);
+  poly_at_alphas<NA, 2 * NL - 2>(b, P, Bb);
+  const u64 f = compute_filter(F, i);
+#pragma unroll
+  for (int k = 0; k < NA; k++) t[k] = gl_add(Aa[k], gl_mul(P.ma[k], gl_sub(Bb[k], P.kb[k])));
+  store_scaled<NA>(F, P, t, f, out, os, i);
 }
 
 // the generic kernel's per-row store
@@ -616,13 +657,29 @@ k_filter_combine(size_t n, int C, const u64* __restrict__ cons, size_t cs, const
                  u64* __restrict__ out, size_t os) {
   size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
-  u64 acc[MAX_ALPHAS] = {0, 0, 0, 0};
+  // un-reduced accumulation (C <= 2^16 terms stay below 2^96 per accumulator), one reduction per challenge
+  Acc3 A[MAX_ALPHAS], B[MAX_ALPHAS], Cc[MAX_ALPHAS];
+#pragma unroll
+  for (int a = 0; a < MAX_ALPHAS; a++) A[a] = B[a] = Cc[a] = Acc3{0, 0, 0};
+#pragma unroll 4
   for (int c = 0; c < C; c++) {
     const u64 v = cons[(size_t)c * cs + i];
+    const u32 vl = (u32)v, vh = (u32)(v >> 32);
 #pragma unroll
-    for (int a = 0; a < MAX_ALPHAS; a++)
-      if (a < F.n_alphas) acc[a] = gl_add(acc[a], gl_mul(v, __ldg(pw + (size_t)a * C + c)));
+    for (int a = 0; a < MAX_ALPHAS; a++) {
+      if (a < F.n_alphas) {
+        const u64 pwv = __ldg(pw + (size_t)a * C + c);
+        const u32 pl = (u32)pwv, ph = (u32)(pwv >> 32);
+        mac3(A[a], vl, pl);
+        mac3(B[a], vl, ph);
+        mac3(B[a], vh, pl);
+        mac3(Cc[a], vh, ph);
+      }
+    }
   }
+  u64 acc[MAX_ALPHAS];
+#pragma unroll
+  for (int a = 0; a < MAX_ALPHAS; a++) acc[a] = reduce_abc(A[a], B[a], Cc[a], 0);
   store_combined_acc(F, acc, compute_filter(F, i), out, os, i);
 }
 
@@ -979,18 +1036,27 @@ int p2e_eval_filtered_combined_dev(int gate, const int* params, int gate_index, 
   }
   AlphaPow17 P;
   for (int a = 0; a < MAX_ALPHAS; a++) {
-    u64 p = 0;
-    if (a < n_alphas) {
-      p = 1;
-      u64 b = alphas[a];
-      for (u64 e = first_power; e; e >>= 1) {
-        if (e & 1) p = gl_mul(p, b);
-        b = gl_mul(b, b);
-      }
+    const u64 al = a < n_alphas ? alphas[a] : 0;
+    u64 sc = a < n_alphas ? 1 : 0, b = al;
+    for (u64 e = first_power; e; e >>= 1) {
+      if (e & 1) sc = gl_mul(sc, b);
+      b = gl_mul(b, b);
     }
+    P.scale[a] = sc;
+    u64 p = a < n_alphas ? 1 : 0, ma = 0;
     for (int c = 0; c < 2 * NL - 1; c++) {
       P.p[a][c] = p;
-      if (a < n_alphas) p = gl_mul(p, alphas[a]);
+      if (gate == P2E_GATE_MUL_NONNATIVE && c < NL)
+        ma = gl_add(ma, gl_mul(p, params[0] == P2E_SECP256K1_BASE ? ModP::m(c) : ModN::m(c)));
+      p = gl_mul(p, al);
+    }
+    P.ma[a] = ma;
+    P.kb[a] = 0;
+    if (gate == P2E_GATE_CHECK_SUM && a < n_alphas) {
+      u64 g16 = 0;
+      for (int c = 0; c < 2 * NL - 2; c++) g16 = gl_add(g16, P.p[a][c]);
+      P.ma[a] = gl_sub(al, 1ull << LB);
+      P.kb[a] = gl_mul(g16, 1ull << 33);
     }
   }
   // instantiated for 1, 2 and 4 challenges (3 runs as 4 with a zero power row; plonky2's standard config has 2)
@@ -998,10 +1064,8 @@ int p2e_eval_filtered_combined_dev(int gate, const int* params, int gate_index, 
   do {                                                                                                     \
     if (gate == P2E_GATE_CHECK_SUM)                                                                        \
       k_eval_check_sum_fc<NA><<<grid_for(n), TPB, 0, st>>>(n, wires, is, F, P, out, os);                   \
-    else if (params[0] == P2E_SECP256K1_BASE)                                                              \
-      k_eval_mul_nonnative_fc<ModP, NA><<<grid_for(n), TPB, 0, st>>>(n, wires, is, F, P, out, os);         \
     else                                                                                                   \
-      k_eval_mul_nonnative_fc<ModN, NA><<<grid_for(n), TPB, 0, st>>>(n, wires, is, F, P, out, os);         \
+      k_eval_mul_nonnative_fc<NA><<<grid_for(n), TPB, 0, st>>>(n, wires, is, F, P, out, os);               \
   } while (0)
   if (n_alphas == 1) P2E_FC_LAUNCH(1);
   else if (n_alphas == 2) P2E_FC_LAUNCH(2);

@@ -1,5 +1,5 @@
 """One invocation of each hot kernel, for `ncu` captures (never a bench number).
-Usage: python scripts/profile_once.py ecdsa | ux | std"""
+Usage: python scripts/profile_once.py ecdsa | ux | fc | lde | std"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -36,6 +36,20 @@ elif what == "ux":
         assert lib.p2e_ux_witness_dev(gate, bits, lb, count, na, n, x.data_ptr(), n, row.data_ptr(), n, e.data_ptr(), None) == 0
         eng.synchronize()
         del w, o, x, row
+elif what == "fc":
+    import ctypes
+    n = 1 << 20
+    w = dev(W.random_goldilocks(W.SEED + 5, 100, n))          # 99 wires (widest gate here) + a selector column
+    o = torch.empty((2, n), dtype=torch.int64, device="cuda")
+    al = np.array([0x0123456789ABCDEF, 0x0FEDCBA987654321], dtype=np.uint64)
+    sel = w.data_ptr() + 99 * n * 8
+    for gate, params in [(0, (0,)), (1, ()), (2, (0, 29, 3, 9, 0))]:
+        prm = (ctypes.c_int * 5)(*(list(params) + [0] * 5)[:5])
+        scr = torch.empty(int(lib.p2e_eval_filtered_scratch_bytes(gate, ctypes.addressof(prm), n)) // 8 + 2, dtype=torch.int64, device="cuda")
+        for _ in range(2):
+            assert lib.p2e_eval_filtered_combined_dev(gate, ctypes.addressof(prm), 1, 0, 4, 1, n, w.data_ptr(), n, sel, al.ctypes.data, 2, 4, 0,
+                                                      o.data_ptr(), n, scr.data_ptr(), None) == 0
+        eng.synchronize()
 elif what == "lde":
     log_n, rb, polys = 17, 3, 135
     n, m = 1 << log_n, 1 << (log_n + rb)

@@ -191,6 +191,7 @@ def test_ux_full_size_rows_vanish(engine):
     out = torch.empty((99, n), dtype=torch.int64, device="cuda")
     err = torch.empty(n, dtype=torch.int32, device="cuda")
     lib = engine.lib
+    torch.cuda.synchronize()      # torch's stream and the engine's stream are unordered
     assert lib.p2e_ux_witness_dev(pkg.UX_RANGE_CHECK, 29, 3, 9, 0, n, limbs.data_ptr(), n, row.data_ptr(), n, err.data_ptr(), None) == 0
     assert lib.p2e_eval_ux_dev(pkg.UX_RANGE_CHECK, 29, 3, 9, 0, n, row.data_ptr(), n, out.data_ptr(), n, None) == 0
     engine.synchronize()

@@ -149,6 +149,7 @@ def test_filtered_combined_vanishes_on_generated_rows_full_size(engine):
     rows[:9], rows[9:18] = x, y
     err = torch.empty(n, dtype=torch.int32, device="cuda")
     lib = engine.lib
+    torch.cuda.synchronize()      # torch's stream and the engine's stream are unordered: finish the fills first
     assert lib.p2e_mul_nonnative_witness_dev(pkg.SECP256K1_BASE, n, x.data_ptr(), y.data_ptr(), n, rows[18:].data_ptr(), n,
                                              err.data_ptr(), None) == 0
     sel = torch.zeros(n, dtype=torch.int64, device="cuda")
@@ -158,6 +159,7 @@ def test_filtered_combined_vanishes_on_generated_rows_full_size(engine):
     prm = (ctypes.c_int * 5)(pkg.SECP256K1_BASE, 0, 0, 0, 0)
 
     def run():
+        torch.cuda.synchronize()
         assert lib.p2e_eval_filtered_combined_dev(pkg.GATE_MUL_NONNATIVE, ctypes.addressof(prm), 0, 0, 2, 1, n, rows.data_ptr(), n,
                                                   sel.data_ptr(), alphas.ctypes.data, 2, 5, 0, out.data_ptr(), n, None, None) == 0
         engine.synchronize()
