@@ -564,10 +564,17 @@ __device__ __forceinline__ void poly_at_alphas(const u64 (&v)[LEN], const AlphaP
 #pragma unroll
   for (int a = 0; a < NA; a++) res[a] = reduce_abc(A[a], B[a], C[a], 0);
 }
+// A run of wires loaded as one wave: volatile asm keeps the loads together at the top (ptxas otherwise sinks each
+// load next to its first use to save registers and the kernel becomes latency-bound: long_scoreboard 15 per issue)
+__device__ __forceinline__ u64 ldg_wave(const u64* p) {
+  u64 v;
+  asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
 template <int LEN>
 __device__ __forceinline__ void load_run(const u64* __restrict__ wires, size_t is, size_t i, int first_wire, u64 (&v)[LEN]) {
 #pragma unroll
-  for (int j = 0; j < LEN; j++) v[j] = wires[(size_t)(first_wire + j) * is + i];
+  for (int j = 0; j < LEN; j++) v[j] = ldg_wave(wires + (size_t)(first_wire + j) * is + i);
 }
 
 template <int NA>
@@ -638,36 +645,29 @@ k_eval_check_sum_fc(size_t n, const u64* __restrict__ wires, size_t is, FilterAr
   store_scaled<NA>(F, P, t, f, out, os, i);
 }
 
-// the generic kernel's per-row store
-__device__ __forceinline__ void store_combined_acc(const FilterArgs& F, const u64* acc, u64 f, u64* __restrict__ out, size_t os,
-                                                   size_t i) {
-#pragma unroll
-  for (int a = 0; a < MAX_ALPHAS; a++) {
-    if (a < F.n_alphas) {
-      u64 r = gl_mul(f, acc[a]);
-      if (F.accumulate) r = gl_add(r, out[a * os + i]);
-      out[a * os + i] = r;
-    }
-  }
-}
-
-// generic form (any gate): constraints [C][n] already evaluated -> filter, combine with the power table [n_alphas][C]
+// generic form (any gate): constraints [C][n] already evaluated -> filter, combine with the power table [n_alphas][C].
+// Un-reduced accumulation (C <= 2^16 terms stay below 2^96 per accumulator), one reduction per challenge; the
+// constraint column is read in waves of 16 loads per thread.
+template <int NA>
 __global__ void __launch_bounds__(TPB)
 k_filter_combine(size_t n, int C, const u64* __restrict__ cons, size_t cs, const u64* __restrict__ pw, FilterArgs F,
                  u64* __restrict__ out, size_t os) {
   size_t i = (size_t)blockIdx.x * TPB + threadIdx.x;
   if (i >= n) return;
-  // un-reduced accumulation (C <= 2^16 terms stay below 2^96 per accumulator), one reduction per challenge
-  Acc3 A[MAX_ALPHAS], B[MAX_ALPHAS], Cc[MAX_ALPHAS];
+  Acc3 A[NA], B[NA], Cc[NA];
 #pragma unroll
-  for (int a = 0; a < MAX_ALPHAS; a++) A[a] = B[a] = Cc[a] = Acc3{0, 0, 0};
-#pragma unroll 4
-  for (int c = 0; c < C; c++) {
-    const u64 v = cons[(size_t)c * cs + i];
-    const u32 vl = (u32)v, vh = (u32)(v >> 32);
+  for (int a = 0; a < NA; a++) A[a] = B[a] = Cc[a] = Acc3{0, 0, 0};
+  constexpr int WAVE = 16;
+  for (int c0 = 0; c0 < C; c0 += WAVE) {
+    u64 v[WAVE];
 #pragma unroll
-    for (int a = 0; a < MAX_ALPHAS; a++) {
-      if (a < F.n_alphas) {
+    for (int k = 0; k < WAVE; k++) v[k] = (c0 + k < C) ? ldg_wave(cons + (size_t)(c0 + k) * cs + i) : 0;
+#pragma unroll
+    for (int k = 0; k < WAVE; k++) {
+      const u32 vl = (u32)v[k], vh = (u32)(v[k] >> 32);
+      const int c = (c0 + k < C) ? c0 + k : C - 1;        // padded terms multiply v = 0
+#pragma unroll
+      for (int a = 0; a < NA; a++) {
         const u64 pwv = __ldg(pw + (size_t)a * C + c);
         const u32 pl = (u32)pwv, ph = (u32)(pwv >> 32);
         mac3(A[a], vl, pl);
@@ -677,10 +677,15 @@ k_filter_combine(size_t n, int C, const u64* __restrict__ cons, size_t cs, const
       }
     }
   }
-  u64 acc[MAX_ALPHAS];
+  const u64 f = compute_filter(F, i);
 #pragma unroll
-  for (int a = 0; a < MAX_ALPHAS; a++) acc[a] = reduce_abc(A[a], B[a], Cc[a], 0);
-  store_combined_acc(F, acc, compute_filter(F, i), out, os, i);
+  for (int a = 0; a < NA; a++) {
+    if (a < F.n_alphas) {
+      u64 r = gl_mul(f, reduce_abc(A[a], B[a], Cc[a], 0));
+      if (F.accumulate) r = gl_add(r, out[a * os + i]);
+      out[a * os + i] = r;
+    }
+  }
 }
 
 // pw[a][c] = alpha_a^(first_power + c)
@@ -1030,7 +1035,9 @@ int p2e_eval_filtered_combined_dev(int gate, const int* params, int gate_index, 
     for (int a = 0; a < n_alphas; a++) al.v[a] = alphas[a];
     k_alpha_powers<<<1, 32, 0, st>>>(al, n_alphas, first_power, nc, pw);
     if ((rc = p2e_eval_ux_dev(params[0], params[1], params[2], params[3], params[4], n, wires, is, cons, n, (void*)st))) return rc;
-    k_filter_combine<<<grid_for(n), TPB, 0, st>>>(n, nc, cons, n, pw, F, out, os);
+    if (n_alphas == 1) k_filter_combine<1><<<grid_for(n), TPB, 0, st>>>(n, nc, cons, n, pw, F, out, os);
+    else if (n_alphas == 2) k_filter_combine<2><<<grid_for(n), TPB, 0, st>>>(n, nc, cons, n, pw, F, out, os);
+    else k_filter_combine<4><<<grid_for(n), TPB, 0, st>>>(n, nc, cons, n, pw, F, out, os);
     P2E_LAUNCH_CHECK();
     return 0;
   }
