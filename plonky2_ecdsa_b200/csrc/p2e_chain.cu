@@ -1412,6 +1412,23 @@ static unsigned wide_tpb() {
   return v;
 }
 
+// dynamic shared memory (bytes, unused by the kernels) requested for K3 / K4 to cap their CTAs per SM; 0 = no cap
+__global__ void k_chain_affine(ChainArgs A);
+__global__ void k_chain_expand(ChainArgs A);
+static size_t wide_smem() {
+  static long v = -1;
+  if (v < 0) {
+    const char* e = getenv("P2E_CHAIN_WIDE_SMEM");
+    v = e ? atol(e) : 0;
+    if (v < 0 || v > 200 * 1024) v = 0;
+    if (v > 48 * 1024) {
+      cudaFuncSetAttribute(k_chain_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v);
+      cudaFuncSetAttribute(k_chain_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v);
+    }
+  }
+  return (size_t)v;
+}
+
 // diagnostic only (wrong results when not 63): bit mask of the kernels to launch
 // 1 prep, 2 replay + join, 4 invert, 8 affine, 16 expand, 32 checks
 static unsigned phase_mask() {
@@ -1530,9 +1547,13 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
           P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
         }
         const unsigned tpb = wide_tpb(), gw = (unsigned)((cn + tpb - 1) / tpb);
-        if (pm & 8) k_chain_affine<<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
+        // Occupancy throttle for the two full-GPU kernels: unused dynamic shared memory caps their CTAs per SM so
+        // that the latency-bound kernels of OTHER batches (high-priority streams) find registers on every SM and
+        // run next to them instead of after them (K4 at 3 CTAs / SM owns the whole register file).
+        const size_t wsm = wide_smem();
+        if (pm & 8) k_chain_affine<<<dim3(gw, (unsigned)no), tpb, wsm, s_lo>>>(A);
         if (prof) prof_mark(st);
-        if (pm & 16) k_chain_expand<<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
+        if (pm & 16) k_chain_expand<<<dim3(gw, (unsigned)no), tpb, wsm, s_lo>>>(A);
         if (prof) prof_mark(st);
       } else if (split) {
         P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
