@@ -36,6 +36,8 @@ WORKLOAD_NAMES = {
     "evaladd": "u29 add-many gate (3 addends, 5 ops / row; plonky2_ux spec unpinned) eval over 2^20 Goldilocks LDE rows",
     "evalfc": "MulNonnativeGate eval_filtered_base_batch + alpha-combination (2 challenges, fused) over 2^20 Goldilocks LDE rows",
     "evalcsfc": "CheckSumGate eval_filtered_base_batch + alpha-combination (2 challenges, fused) over 2^20 Goldilocks LDE rows",
+    "genstream": "serialized generator stream (8 x curve_add + curve_double chained: 224 in-tree generators, target-level wiring of "
+                 "gadgets/curve.rs) run by the level-scheduled executor for 4096 circuits",
     "lde": "coset LDE (ifft 2^17 -> zero-pad -> coset fft 2^20, rate 8) of 135 wire polynomials: the matrix the gate evaluators read",
 }
 # plonky2_ux eval workloads: (gate, bits, limb_bits, count, num_addends, kernel)
@@ -55,6 +57,7 @@ METRICS = {
     "evaladd": ("ux_add_many_gate_rows_per_s", "rows/s"),
     "evalfc": ("mul_nonnative_gate_filtered_combined_rows_per_s", "rows/s"),
     "evalcsfc": ("check_sum_gate_filtered_combined_rows_per_s", "rows/s"),
+    "genstream": ("generator_stream_circuits_per_s", "circuits/s"),
     "lde": ("coset_lde_output_elements_per_s", "elements/s"),
 }
 
@@ -309,6 +312,46 @@ class Bench:
             return dict(step=step, step_e2e=step_e2e, units=n, h2d=(nw + 1) * 8 * n, d2h=2 * 8 * n, alg_bytes=(nw + 1 + 2) * 8 * n,
                         kernel="k_eval_mul_nonnative_fc<2>" if gate == 0 else "k_eval_check_sum_fc<2>", launches=1, err=None,
                         dtype="u64 (Goldilocks)", keep=(wd, od, hw, ho, prm, alphas))
+        if wl == "genstream":
+            b = pkg.TargetCircuitBuilder()
+            p0 = (b.add_virtual_nonnative_target(), b.add_virtual_nonnative_target())
+            q0 = (b.add_virtual_nonnative_target(), b.add_virtual_nonnative_target())
+            a_const = b.add_virtual_nonnative_target()
+            acc = p0
+            for _ in range(8):
+                acc = b.curve_double(b.curve_add(acc, q0), a_const)
+            gs = eng.load_generator_stream(b.bytes())
+            n = 4096
+            d = W.ecdsa_workload(n, seed=W.SEED + self.rank)
+            rolled = [np.ascontiguousarray(np.roll(d[k], 1, axis=1)) for k in ("pkx", "pky")]
+            in_t = list(p0[0]) + list(p0[1]) + list(q0[0]) + list(q0[1]) + list(a_const)
+            vals = np.concatenate([d["pkx"], d["pky"], rolled[0], rolled[1], np.zeros((9, n), dtype=np.uint64)], axis=0)
+            in_slots = np.array([gs.slot(t) for t in in_t], dtype=np.uint32)
+            out_t = list(acc[0]) + list(acc[1])
+            out_slots = np.array([gs.slot(t) for t in out_t], dtype=np.uint32)
+            n_slots = gs.num_slots
+            vd = self.dev(np.ascontiguousarray(vals))
+            table = torch.zeros((n_slots, n), dtype=torch.int64, device="cuda")
+            ed = torch.zeros(n, dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+
+            def step():
+                rc = lib.p2e_genstream_run_dev(gs.handle, n, in_slots.ctypes.data, len(in_slots), vd.data_ptr(), n, table.data_ptr(), n,
+                                               ed.data_ptr(), sp)
+                assert rc == 0, eng.last_error()
+            hv = self.pinned(np.ascontiguousarray(vals))
+            ho = torch.empty((len(out_slots), n), dtype=torch.int64).pin_memory()
+            he = torch.empty(n, dtype=torch.int32).pin_memory()
+
+            def step_e2e():
+                rc = lib.p2e_genstream_run(gs.handle, n, in_slots.ctypes.data, len(in_slots), hv.data_ptr(), out_slots.ctypes.data,
+                                           len(out_slots), ho.data_ptr(), he.data_ptr())
+                assert rc == 0, eng.last_error()
+            # algorithmic bytes: every slot of the value table is written once and read about once
+            return dict(step=step, step_e2e=step_e2e, units=n, h2d=len(in_slots) * 8 * n, d2h=len(out_slots) * 8 * n + 4 * n,
+                        alg_bytes=2 * n_slots * 8 * n, kernel="level schedule: %d generators, %d levels, %d launch groups (gather + witness kernel + scatter each), one CUDA graph"
+                        % (gs.num_generators, gs.num_levels, gs.num_groups), launches=3 * gs.num_groups, err=ed, dtype="u32 limbs / u64 (int)",
+                        keep=(gs, vd, table, hv, ho, he, in_slots, out_slots))
         if wl in UX_WORKLOADS:
             gate, bits, lb, count, na, kname = UX_WORKLOADS[wl]
             nw, nc, _ = eng.ux_gate_shape(gate, bits, lb, count, na)
@@ -604,7 +647,7 @@ def main():
     main_res = b.measure(wl, args.steps, args.warmup, e2e_steps=max(2, min(args.steps, 5)), sample_clocks=True)
     secondary = {}
     if not args.no_secondary:
-        for w2 in ("mulmod", "eval", "evalcs", "evalfc", "evalcsfc", "evalrc", "evalcmp", "evaladd", "lde", "glv", "ecdsa"):
+        for w2 in ("mulmod", "eval", "evalcs", "evalfc", "evalcsfc", "evalrc", "evalcmp", "evaladd", "lde", "genstream", "glv", "ecdsa"):
             if w2 != wl:
                 try:
                     r2 = b.measure(w2, steps=min(args.steps, 20) if w2 != "glv" else 3, warmup=3, e2e_steps=2)

@@ -12,4 +12,4 @@ from .engine import (  # noqa: F401
     GATE_MUL_NONNATIVE, GATE_CHECK_SUM, GATE_UX,
     MUL_OUT_R, MUL_OUT_Q, MUL_OUT_CHECK_SUM, MUL_OUT_CARRY, MUL_OUT_ROWS,
 )
-from .genstream import GeneratorStream, GeneratorStreamWriter, wire, virtual  # noqa: F401,E402
+from .genstream import GeneratorStream, GeneratorStreamWriter, TargetCircuitBuilder, wire, virtual  # noqa: F401,E402

@@ -214,6 +214,11 @@ struct GenStream {
   size_t stage_err_bytes = 0;
   u32* d_io = nullptr;
   size_t io_bytes = 0;
+  // CUDA graph of the last launch sequence (deep circuits are launch-bound: 3 launches per group); valid for
+  // the same (n, table, stride, err) and staging buffers
+  cudaGraphExec_t graph = nullptr;
+  size_t g_n = 0, g_vs = 0;
+  const void *g_V = nullptr, *g_err = nullptr, *g_stage = nullptr, *g_stage_err = nullptr;
   std::string error;
 
   u32 tid(const TargetKey& k) {
@@ -232,7 +237,12 @@ struct GenStream {
     }
     return x;
   }
+  void drop_graph() {
+    if (graph) cudaGraphExecDestroy(graph);
+    graph = nullptr;
+  }
   void release_device() {
+    drop_graph();
     if (d_idx) cudaFree(d_idx);
     if (d_consts) cudaFree(d_consts);
     if (d_stage) cudaFree(d_stage);
@@ -565,9 +575,31 @@ static int ensure_device(GenStream& S) {
   return 0;
 }
 
+static int per_launch(size_t n) {
+  int per = (int)std::max<size_t>(1, GS_MAX_STAGED / std::max<size_t>(n, 1));
+  return std::min(per, 65535);
+}
+
+// staging buffers for the widest group at this n (grown before any launch: nothing allocates inside a graph capture)
+static int size_staging(GenStream& S, size_t n) {
+  size_t need = 16, need_err = 16;
+  const int per = per_launch(n);
+  for (const GsGroup& G : S.groups) {
+    if (G.kind == K_ARITH || G.kind == K_CONST) continue;
+    const size_t M = (size_t)std::min(G.m, per) * n;
+    need = std::max(need, (size_t)(G.in_rows + G.out_rows) * M * 8);
+    need_err = std::max(need_err, M * 4);
+  }
+  int rc;
+  if ((rc = grow((void**)&S.d_stage, &S.stage_bytes, need))) return rc;
+  if ((rc = grow((void**)&S.d_stage_err, &S.stage_err_bytes, need_err))) return rc;
+  return 0;
+}
+
 static int run_groups(GenStream& S, size_t n, u64* V, size_t vs, u32* err, cudaStream_t st) {
   int rc;
   const unsigned gx = (unsigned)((n + GS_TPB - 1) / GS_TPB);
+  const int per = per_launch(n);
   for (const GsGroup& G : S.groups) {
     const u32* idx = S.d_idx + G.idx_off;
     const u32* oidx = S.d_idx + G.oidx_off;
@@ -577,20 +609,16 @@ static int run_groups(GenStream& S, size_t n, u64* V, size_t vs, u32* err, cudaS
         if (G.kind == K_CONST) {
           k_gs_const<<<dim3(gx, mc), GS_TPB, 0, st>>>(n, G.m, oidx + j0, S.d_consts + G.const_off + j0, V, vs, err);
         } else {
-          // idx rows m0, m1, addend are [3][m]; the kernel wants one [4][m] block: in_rows then the output row follow each other
+          // the index rows m0, m1, addend ([3][m]) and the output row follow each other in the pool: one [4][m] block
           k_gs_arith<<<dim3(gx, mc), GS_TPB, 0, st>>>(n, G.m, idx + j0, S.d_consts + G.const_off + j0, V, vs, err);
         }
       }
       P2E_CUDA(cudaGetLastError());
       continue;
     }
-    int per = (int)std::max<size_t>(1, GS_MAX_STAGED / std::max<size_t>(n, 1));
-    per = std::min(per, 65535);
     for (int j0 = 0; j0 < G.m; j0 += per) {
       const int mc = std::min(G.m - j0, per);
       const size_t M = (size_t)mc * n;
-      if ((rc = grow((void**)&S.d_stage, &S.stage_bytes, (size_t)(G.in_rows + G.out_rows) * M * 8))) return rc;
-      if ((rc = grow((void**)&S.d_stage_err, &S.stage_err_bytes, M * 4))) return rc;
       u64* sin = S.d_stage;
       u64* sout = S.d_stage + (size_t)G.in_rows * M;
       k_gs_gather<<<dim3(gx, mc), GS_TPB, 0, st>>>(n, G.m, mc, j0, G.in_rows, idx, V, vs, sin);
@@ -612,6 +640,47 @@ static int run_groups(GenStream& S, size_t n, u64* V, size_t vs, u32* err, cudaS
       P2E_CUDA(cudaGetLastError());
     }
   }
+  return 0;
+}
+
+static bool use_graph() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("P2E_GENSTREAM_GRAPH");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
+// the launch sequence as a CUDA graph, re-used while (n, table, stride, err, staging) stay the same
+static int run_groups_graphed(GenStream& S, size_t n, u64* V, size_t vs, u32* err, cudaStream_t st) {
+  int rc;
+  if ((rc = size_staging(S, n))) return rc;
+  if (!use_graph() || S.groups.size() < 8) return run_groups(S, n, V, vs, err, st);
+  const bool hit = S.graph && S.g_n == n && S.g_V == V && S.g_vs == vs && S.g_err == err && S.g_stage == S.d_stage &&
+                   S.g_stage_err == S.d_stage_err;
+  if (!hit) {
+    S.drop_graph();
+    cudaGraph_t g = nullptr;
+    P2E_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = run_groups(S, n, V, vs, err, st);
+    cudaError_t ce = cudaStreamEndCapture(st, &g);
+    if (rc || ce != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      if (rc) return rc;
+      return run_groups(S, n, V, vs, err, st);        // capture not possible on this stream: plain launches
+    }
+    ce = cudaGraphInstantiate(&S.graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) {
+      S.graph = nullptr;
+      cudaGetLastError();
+      return run_groups(S, n, V, vs, err, st);
+    }
+    S.g_n = n; S.g_V = V; S.g_vs = vs; S.g_err = err; S.g_stage = S.d_stage; S.g_stage_err = S.d_stage_err;
+  }
+  P2E_CUDA(cudaGraphLaunch(S.graph, st));
   return 0;
 }
 
@@ -733,7 +802,7 @@ int p2e_genstream_run_dev(int h, size_t n, const uint32_t* in_slots, int n_in, c
     }
     P2E_CUDA(cudaGetLastError());
   }
-  return run_groups(*S, n, table, stride, err, st);
+  return run_groups_graphed(*S, n, table, stride, err, st);
 }
 
 int p2e_genstream_run(int h, size_t n, const uint32_t* in_slots, int n_in, const uint64_t* in_values,

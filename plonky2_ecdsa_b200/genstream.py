@@ -213,3 +213,102 @@ class GeneratorStream:
         if rc != 0:
             raise self._err(self.lib.p2e_last_error().decode())
         return out_vals, err
+
+
+class TargetCircuitBuilder:
+    """The reference's gadgets at the TARGET level (what `CircuitBuilder` + the extension traits of
+    gadgets/nonnative.rs / gadgets/curve.rs do when a circuit is built): allocates virtual targets and gate
+    rows, records copy constraints, and emits every generator through a GeneratorStreamWriter -- i.e. the
+    byte stream a Rust host would hand to p2e_genstream_load for the same circuit.  A nonnative value is a
+    list of 9 limb targets."""
+
+    def __init__(self):
+        self.w = GeneratorStreamWriter()
+        self.n_virtual = 0
+        self.n_rows = 0
+
+    def add_virtual_targets(self, k):
+        v = [virtual(self.n_virtual + i) for i in range(k)]
+        self.n_virtual += k
+        return v
+
+    def add_virtual_nonnative_target(self):
+        return self.add_virtual_targets(9)
+
+    def add_gate(self):
+        self.n_rows += 1
+        return self.n_rows - 1
+
+    def connect(self, a, b):
+        self.w.copy(a, b)
+
+    def add_nonnative(self, modulus, a, b):
+        """gadgets/nonnative.rs:245-276"""
+        s, ov = self.add_virtual_targets(9), self.add_virtual_targets(1)[0]
+        self.w.nonnative_addition_generator(modulus, a, b, s, ov)
+        return s
+
+    def sub_nonnative(self, modulus, a, b):
+        """gadgets/nonnative.rs:356-388"""
+        d, ov = self.add_virtual_targets(9), self.add_virtual_targets(1)[0]
+        self.w.nonnative_subtraction_generator(modulus, a, b, d, ov)
+        return d
+
+    def add_many_nonnative(self, modulus, xs):
+        """gadgets/nonnative.rs:310-353"""
+        s, ov = self.add_virtual_targets(9), self.add_virtual_targets(1)[0]
+        self.w.nonnative_multiple_adds_generator(modulus, xs, s, ov)
+        return s
+
+    def mul_nonnative(self, modulus, x, y):
+        """gadgets/nonnative.rs:390-464: a MulNonnativeGate row and a CheckSumGate row, both fed by copies"""
+        row = self.add_gate()
+        for i in range(9):
+            self.connect(x[i], wire(row, i))
+            self.connect(y[i], wire(row, 9 + i))
+        self.w.mul_nonnative_generator(modulus, row)
+        row2 = self.add_gate()
+        for i in range(17):
+            self.connect(wire(row, 36 + i), wire(row2, i))
+        self.w.check_sum_generator(row2)
+        return [wire(row, 18 + i) for i in range(9)]
+
+    def inv_nonnative(self, modulus, x):
+        """gadgets/nonnative.rs:502-536"""
+        inv, div = self.add_virtual_targets(9), self.add_virtual_targets(9)
+        self.w.nonnative_inverse_generator(modulus, x, inv, div)
+        return inv
+
+    def curve_add(self, p1, p2):
+        """gadgets/curve.rs:202-223"""
+        (x1, y1), (x2, y2) = p1, p2
+        u = self.sub_nonnative(0, y2, y1)
+        v = self.sub_nonnative(0, x2, x1)
+        v_inv = self.inv_nonnative(0, v)
+        s = self.mul_nonnative(0, u, v_inv)
+        s2 = self.mul_nonnative(0, s, s)
+        x_sum = self.add_nonnative(0, x2, x1)
+        x3 = self.sub_nonnative(0, s2, x_sum)
+        x_diff = self.sub_nonnative(0, x1, x3)
+        prod = self.mul_nonnative(0, s, x_diff)
+        y3 = self.sub_nonnative(0, prod, y1)
+        return x3, y3
+
+    def curve_double(self, p, a_const):
+        """gadgets/curve.rs:160-185; a_const: the 9 limb targets of the curve constant A"""
+        x, y = p
+        double_y = self.add_nonnative(0, y, y)
+        inv_double_y = self.inv_nonnative(0, double_y)
+        x_squared = self.mul_nonnative(0, x, x)
+        triple = self.add_many_nonnative(0, [x_squared, x_squared, x_squared, a_const])
+        lam = self.mul_nonnative(0, triple, inv_double_y)
+        lam2 = self.mul_nonnative(0, lam, lam)
+        x_double = self.add_nonnative(0, x, x)
+        x3 = self.sub_nonnative(0, lam2, x_double)
+        x_diff = self.sub_nonnative(0, x, x3)
+        lx = self.mul_nonnative(0, lam, x_diff)
+        y3 = self.sub_nonnative(0, lx, y)
+        return x3, y3
+
+    def bytes(self) -> bytes:
+        return self.w.bytes()

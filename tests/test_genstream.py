@@ -191,6 +191,17 @@ def test_stream_bytes_follow_the_reference_serialize_bodies():
     assert len(b) == 4 + (8 + 9) + (8 + 17) + (8 + 9 * 9) + 9
 
 
+def test_product_side_builder_emits_the_same_stream():
+    """plonky2_ecdsa_b200.TargetCircuitBuilder (the host mirror bench.py uses) and this file's oracle-carrying
+    TargetCircuit wire the gadgets identically."""
+    c, _, _, _ = _curve_circuit()
+    b = pkg.TargetCircuitBuilder()
+    pts = [(b.add_virtual_nonnative_target(), b.add_virtual_nonnative_target()) for _ in range(2)]
+    a_const = b.add_virtual_nonnative_target()
+    b.curve_add(b.curve_double(b.curve_add(pts[0], pts[1]), a_const), pts[0])
+    assert b.bytes() == c.w.bytes()
+
+
 def test_load_partitions_levels_and_inputs():
     c, pts, a_const, t = _curve_circuit()
     lib = pkg.load_library()
