@@ -62,6 +62,11 @@ METRICS = {
 }
 
 
+# config 5 is quoted on a 2^20-row LDE; BASELINE.json's wording also admits trace 2^20 x rate 8 = 2^23 rows:
+# P2E_BENCH_LOG_ROWS=23 re-runs the gate-evaluation workloads at that size
+LOG_ROWS = int(os.environ.get("P2E_BENCH_LOG_ROWS", "20"))
+
+
 def load_traffic():
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
@@ -252,7 +257,7 @@ class Bench:
                         alg_bytes=552 * n, kernel="k_mul_witness<ModP>", launches=1, err=ed, dtype="u32 limbs / u64 (int)",
                         keep=(xd, yd, od, hx, hy, ho, he))
         if wl == "eval":
-            n = 1 << 20
+            n = 1 << LOG_ROWS
             w = W.random_goldilocks(W.SEED + self.rank, 53, n)
             wd = self.dev(w)
             od = torch.empty((17, n), dtype=torch.int64, device="cuda")
@@ -270,7 +275,7 @@ class Bench:
                         kernel="k_eval_mul_nonnative<ModP>", launches=1, err=None, dtype="u64 (Goldilocks)",
                         keep=(wd, od, hw, ho))
         if wl == "evalcs":
-            n = 1 << 20
+            n = 1 << LOG_ROWS
             w = W.random_goldilocks(W.SEED + 3 + self.rank, 33, n)
             wd = self.dev(w)
             od = torch.empty((17, n), dtype=torch.int64, device="cuda")
@@ -289,7 +294,7 @@ class Bench:
         if wl in ("evalfc", "evalcsfc"):
             import ctypes
             gate, nw = (0, 53) if wl == "evalfc" else (1, 33)
-            n = 1 << 20
+            n = 1 << LOG_ROWS
             w = W.random_goldilocks(W.SEED + 5 + gate + self.rank, nw + 1, n)      # the wires + the selector constant column
             w[nw, ::3] = 0                                                          # a third of the rows select this gate exactly
             wd = self.dev(w)
@@ -355,7 +360,7 @@ class Bench:
         if wl in UX_WORKLOADS:
             gate, bits, lb, count, na, kname = UX_WORKLOADS[wl]
             nw, nc, _ = eng.ux_gate_shape(gate, bits, lb, count, na)
-            n = 1 << 20
+            n = 1 << LOG_ROWS
             w = W.random_goldilocks(W.SEED + 11 + gate + self.rank, nw, n)
             wd = self.dev(w)
             od = torch.empty((nc, n), dtype=torch.int64, device="cuda")
@@ -661,7 +666,7 @@ def main():
             "metric": main_res["metric"], "value": main_res["value"], "unit": main_res["unit"], "n_gpus": b.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": main_res["dtype"], "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAMES[wl], "units_per_step_per_gpu": main_res["units_per_step_per_gpu"],
+            "config": {"workload": WORKLOAD_NAMES[wl].replace("2^20 Goldilocks", "2^%d Goldilocks" % LOG_ROWS), "units_per_step_per_gpu": main_res["units_per_step_per_gpu"],
                        "seed": hex(b.W.SEED), "error_rows": main_res["error_rows"],
                        "l2": "per-step inputs+outputs exceed the 126 MB L2 (no flush needed)",
                        "streams": main_res.get("streams", 1),
