@@ -42,6 +42,8 @@ struct NttPass {
   const u64* tw;                  // DIF twiddles of this pass's line length L: w_L^e, e < L / 2
   const u64 *cross_lo, *cross_hi; // pass A: w_n^e = cross_lo[e & (n2 - 1)] * cross_hi[e >> log_n2]
   const u64 *scale_lo, *scale_hi; // pass B: optional out[k] *= scale_lo[k & (n2 - 1)] * scale_hi[k >> log_n2]
+  const u64 *cross_full;          // pass A: w_n^e, e < n, as ONE table (n <= 2^22: one multiplication instead of two)
+  const u64 *scale_full;          // pass B: premul * base^k, k < n, likewise
 };
 
 __device__ __forceinline__ unsigned brev(unsigned v, int bits) { return __brev(v) >> (32 - bits); }
@@ -90,15 +92,88 @@ __device__ __forceinline__ void dif_round(u64* sm, int log_l, int log_t, int s, 
   __syncthreads();
 }
 
-// T radix-2 DIF NTTs of length L = 1 << log_l on sm[t * (L + 1) + j]; output in bit-reversed order
+// any * 2^A -> any
+template <int A>
+__device__ __forceinline__ u64 gl_shl(u64 v) { return gl_red_lazy(v << A, v >> (64 - A)); }
+
+// Three DIF stages (s .. s+2) as ONE radix-8 step: an 8-point DFT whose twiddles are powers of w_8, followed by one
+// general twiddle per output.  In this field w_8 = w_L^(L/8) = -2^24 for plonky2's roots (2^96 = -1, so 2^24 has
+// order 8; inverse transform: w_8^-1 = 2^72), i.e. the 5 non-trivial twiddles inside the DFT are shifts (the sign
+// is absorbed by swapping the operands of the subtraction) and only 7 of the 12 multiplications of three radix-2
+// stages remain -- none at all in the last step of a line, whose outer twiddles are 1.
+// Output r of the 8-point DFT lands where three radix-2 stages would have put it (position bitrev3(r)); its outer
+// twiddle is w_m^(lo r) = w_L^((lo r) << s), m = L >> s.  tw: the FULL table w_L^e, e < L.
+template <bool INV>
+__device__ __forceinline__ void dif_round8(u64* sm, int log_l, int log_t, int s, const u64* __restrict__ tw) {
+  const int L = 1 << log_l, ls = L + 1;
+  const int log_step = log_l - s - 3;
+  const int step = 1 << log_step;
+  const int per_line = L >> 3;
+  const int total = per_line << log_t;
+  for (int b = threadIdx.x; b < total; b += NTT_THREADS) {
+    const int t = b >> (log_l - 3), w = b & (per_line - 1);
+    const int lo = w & (step - 1), hi = w >> log_step;
+    u64* base = sm + t * ls + (hi << (log_l - s)) + lo;
+    u64 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = base[q << log_step];
+    // stage A: (q, q + 4), twiddle w_8^q
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const u64 a = v[q], c = v[q + 4];
+      v[q] = glc(gla(a, c));
+      u64 d;
+      if (q == 0) d = gls(a, c);
+      else if (q == 1) d = INV ? gl_shl<48>(gl_shl<24>(gls(a, c))) : gl_shl<24>(gls(c, a));      // 2^72 | -2^24
+      else if (q == 2) d = INV ? gl_shl<48>(gls(c, a)) : gl_shl<48>(gls(a, c));                   // -2^48 | 2^48
+      else d = INV ? gl_shl<24>(gls(a, c)) : gl_shl<48>(gl_shl<24>(gls(c, a)));                   // 2^24 | -2^72
+      v[q + 4] = glc(d);
+    }
+    // stage B: (q, q + 2) inside each half, twiddle w_4^q = w_8^(2q)
+#pragma unroll
+    for (int h = 0; h < 8; h += 4) {
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        const u64 a = v[h + q], c = v[h + q + 2];
+        v[h + q] = glc(gla(a, c));
+        u64 d;
+        if (q == 0) d = gls(a, c);
+        else d = INV ? gl_shl<48>(gls(c, a)) : gl_shl<48>(gls(a, c));
+        v[h + q + 2] = glc(d);
+      }
+    }
+    // stage C: (q, q + 1)
+#pragma unroll
+    for (int h = 0; h < 8; h += 2) {
+      const u64 a = v[h], c = v[h + 1];
+      v[h] = glc(gla(a, c));
+      v[h + 1] = glc(gls(a, c));
+    }
+    if (log_step > 0) {
+#pragma unroll
+      for (int qp = 1; qp < 8; qp++) {
+        const int r = ((qp & 1) << 2) | (qp & 2) | (qp >> 2);
+        v[qp] = glc(glm(v[qp], __ldg(tw + ((size_t)(lo * r) << s))));
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) base[q << log_step] = v[q];
+  }
+  __syncthreads();
+}
+
+// T DIF NTTs of length L = 1 << log_l on sm[t * (L + 1) + j]; output in bit-reversed order.  The (log_l mod 3)
+// leading stages run as radix-2 / radix-4 steps with general twiddles, the rest as radix-8 steps.
+template <bool INV>
 __device__ __forceinline__ void dif_lines(u64* sm, int log_l, int log_t, const u64* __restrict__ tw) {
-  int s = 0;
-  for (; s + 3 <= log_l; s += 3) dif_round<3>(sm, log_l, log_t, s, tw);
-  if (log_l - s == 2) dif_round<2>(sm, log_l, log_t, s, tw);
-  else if (log_l - s == 1) dif_round<1>(sm, log_l, log_t, s, tw);
+  const int rem = log_l % 3;
+  if (rem == 1) dif_round<1>(sm, log_l, log_t, 0, tw);
+  else if (rem == 2) dif_round<2>(sm, log_l, log_t, 0, tw);
+  for (int s = rem; s < log_l; s += 3) dif_round8<INV>(sm, log_l, log_t, s, tw);
 }
 
 // pass A: columns
+template <bool INV>
 __global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(NttPass P) {
   extern __shared__ u64 sm[];
   const int log_l = P.log_n1, L = 1 << log_l, ls = L + 1, T = 1 << P.log_t;
@@ -112,17 +187,19 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_cols(NttPass P) {
     sm[t * ls + j] = gi < P.n_in ? in[gi] : 0;
   }
   __syncthreads();
-  dif_lines(sm, log_l, P.log_t, P.tw);
+  dif_lines<INV>(sm, log_l, P.log_t, P.tw);
   for (int idx = threadIdx.x; idx < (L << P.log_t); idx += NTT_THREADS) {
     const int t = idx & (T - 1), k1 = idx >> P.log_t;
     u64 v = sm[t * ls + brev((unsigned)k1, log_l)];
     const size_t e = (c0 + t) * (size_t)k1;
-    v = glm(v, glm(__ldg(P.cross_lo + (e & (n2 - 1))), __ldg(P.cross_hi + (e >> P.log_n2))));
+    if (P.cross_full) v = glm(v, __ldg(P.cross_full + e));
+    else v = glm(v, glm(__ldg(P.cross_lo + (e & (n2 - 1))), __ldg(P.cross_hi + (e >> P.log_n2))));
     out[n2 * k1 + c0 + t] = glc(v);
   }
 }
 
 // pass B: rows
+template <bool INV>
 __global__ void __launch_bounds__(NTT_THREADS) k_ntt_rows(NttPass P) {
   extern __shared__ u64 sm[];
   const int log_l = P.log_n2, L = 1 << log_l, ls = L + 1, T = 1 << P.log_t;
@@ -135,12 +212,13 @@ __global__ void __launch_bounds__(NTT_THREADS) k_ntt_rows(NttPass P) {
     sm[t * ls + j] = in[n2 * (r0 + t) + j];
   }
   __syncthreads();
-  dif_lines(sm, log_l, P.log_t, P.tw);
+  dif_lines<INV>(sm, log_l, P.log_t, P.tw);
   for (int idx = threadIdx.x; idx < (L << P.log_t); idx += NTT_THREADS) {
     const int t = idx & (T - 1), k2 = idx >> P.log_t;
     u64 v = sm[t * ls + brev((unsigned)k2, log_l)];
     const size_t k = r0 + t + n1 * (size_t)k2;
-    if (P.scale_lo) v = glc(glm(v, glm(__ldg(P.scale_lo + (k & (n2 - 1))), __ldg(P.scale_hi + (k >> P.log_n2)))));
+    if (P.scale_full) v = glc(glm(v, __ldg(P.scale_full + k)));
+    else if (P.scale_lo) v = glc(glm(v, glm(__ldg(P.scale_lo + (k & (n2 - 1))), __ldg(P.scale_hi + (k >> P.log_n2)))));
     out[k] = v;
   }
 }
@@ -219,47 +297,69 @@ static int ilog_t(int log_l, int log_other) {
 // One NTT of size 2^log_n over n_polys polynomials: in -> tmp (pass A) -> out (pass B).
 // root: the primitive n-th root to use (omega or omega^-1); scale_base / scale_premul: out[k] *= premul * base^k
 // (0 = no scaling); n_in: input elements present (zero-padded beyond).
-static int ntt_run(int log_n, u64 root, u64 scale_base, u64 scale_premul, int n_polys, const u64* in, size_t in_stride,
+static int ntt_run(int log_n, bool inverse, u64 scale_base, u64 scale_premul, int n_polys, const u64* in, size_t in_stride,
                    size_t n_in, u64* tmp, size_t tmp_stride, u64* out, size_t out_stride, cudaStream_t st) {
   const int log_n1 = (log_n + 1) / 2, log_n2 = log_n / 2;
-  const size_t n1 = (size_t)1 << log_n1, n2 = (size_t)1 << log_n2;
+  const size_t n = (size_t)1 << log_n, n1 = (size_t)1 << log_n1, n2 = (size_t)1 << log_n2;
+  const u64 root = inverse ? h_inv(h_root(log_n)) : h_root(log_n);
+  // the radix-8 steps hard-code w_8 = -2^24 (inverse: 2^72): true for plonky2's roots, checked once
+  if (log_n >= 3) {
+    const u64 w8 = h_pow(root, n / 8);
+    if (w8 != (inverse ? h_pow(2, 72) : GL_P - h_pow(2, 24))) return set_error_msg("ntt: unexpected primitive 8th root of unity");
+  }
   NttPass A;
   A.log_n1 = log_n1;
   A.log_n2 = log_n2;
   int rc;
-  const u64 *tw1, *tw2, *clo, *chi, *slo = nullptr, *shi = nullptr;
-  // w_n1 = root^n2, w_n2 = root^n1
-  if ((rc = power_table(h_pow(root, n2), n1 / 2 ? n1 / 2 : 1, 1, &tw1))) return rc;
-  if ((rc = power_table(h_pow(root, n1), n2 / 2 ? n2 / 2 : 1, 1, &tw2))) return rc;
-  if ((rc = power_table(root, n2, 1, &clo))) return rc;
-  if ((rc = power_table(h_pow(root, n2), n1, 1, &chi))) return rc;
+  const u64 *tw1, *tw2, *clo = nullptr, *chi = nullptr, *slo = nullptr, *shi = nullptr, *cfull = nullptr, *sfull = nullptr;
+  const bool full = log_n <= 22;          // one-table twiddles up to 32 MB
+  // full tables of w_n1 = root^n2 and w_n2 = root^n1 (the radix-8 steps index up to 7/8 of a turn)
+  if ((rc = power_table(h_pow(root, n2), n1, 1, &tw1))) return rc;
+  if ((rc = power_table(h_pow(root, n1), n2, 1, &tw2))) return rc;
+  if (full) {
+    if ((rc = power_table(root, n, 1, &cfull))) return rc;
+  } else {
+    if ((rc = power_table(root, n2, 1, &clo))) return rc;
+    chi = tw1;
+  }
   if (scale_base) {
-    if ((rc = power_table(scale_base, n2, 1, &slo))) return rc;
-    if ((rc = power_table(h_pow(scale_base, n2), n1, scale_premul, &shi))) return rc;
+    if (full) {
+      if ((rc = power_table(scale_base, n, scale_premul, &sfull))) return rc;
+    } else {
+      if ((rc = power_table(scale_base, n2, 1, &slo))) return rc;
+      if ((rc = power_table(h_pow(scale_base, n2), n1, scale_premul, &shi))) return rc;
+    }
   }
   static bool attr_set = false;
   const size_t smem_max = (size_t)(NTT_TILE + 16) * 8;
   if (!attr_set) {
-    P2E_CUDA(cudaFuncSetAttribute(k_ntt_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    P2E_CUDA(cudaFuncSetAttribute(k_ntt_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    P2E_CUDA(cudaFuncSetAttribute(k_ntt_cols<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    P2E_CUDA(cudaFuncSetAttribute(k_ntt_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    P2E_CUDA(cudaFuncSetAttribute(k_ntt_cols<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    P2E_CUDA(cudaFuncSetAttribute(k_ntt_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     attr_set = true;
   }
   // pass A
   A.in = in; A.out = tmp; A.in_stride = in_stride; A.out_stride = tmp_stride; A.n_in = n_in;
   A.log_t = ilog_t(log_n1, log_n2);
   A.tw = tw1; A.cross_lo = clo; A.cross_hi = chi; A.scale_lo = nullptr; A.scale_hi = nullptr;
+  A.cross_full = cfull; A.scale_full = nullptr;
   {
     const size_t smem = (((size_t)n1 + 1) << A.log_t) * 8;
-    k_ntt_cols<<<dim3((unsigned)(n2 >> A.log_t), (unsigned)n_polys), NTT_THREADS, smem, st>>>(A);
+    const dim3 grid((unsigned)(n2 >> A.log_t), (unsigned)n_polys);
+    if (inverse) k_ntt_cols<true><<<grid, NTT_THREADS, smem, st>>>(A);
+    else k_ntt_cols<false><<<grid, NTT_THREADS, smem, st>>>(A);
   }
   // pass B
   NttPass B = A;
-  B.in = tmp; B.out = out; B.in_stride = tmp_stride; B.out_stride = out_stride; B.n_in = (size_t)1 << log_n;
+  B.in = tmp; B.out = out; B.in_stride = tmp_stride; B.out_stride = out_stride; B.n_in = n;
   B.log_t = ilog_t(log_n2, log_n1);
-  B.tw = tw2; B.scale_lo = slo; B.scale_hi = shi;
+  B.tw = tw2; B.scale_lo = slo; B.scale_hi = shi; B.scale_full = sfull;
   {
     const size_t smem = (((size_t)n2 + 1) << B.log_t) * 8;
-    k_ntt_rows<<<dim3((unsigned)(n1 >> B.log_t), (unsigned)n_polys), NTT_THREADS, smem, st>>>(B);
+    const dim3 grid((unsigned)(n1 >> B.log_t), (unsigned)n_polys);
+    if (inverse) k_ntt_rows<true><<<grid, NTT_THREADS, smem, st>>>(B);
+    else k_ntt_rows<false><<<grid, NTT_THREADS, smem, st>>>(B);
   }
   P2E_CUDA(cudaGetLastError());
   return 0;
@@ -292,9 +392,8 @@ int p2e_ntt_dev(int log_n, int inverse, int n_polys, const uint64_t* in, size_t 
   const size_t n = (size_t)1 << log_n;
   if (in_stride < n || out_stride < n) return set_error_msg("ntt: stride < n");
   std::lock_guard<std::mutex> lock(g_ntt_mu);
-  const u64 w = h_root(log_n);
-  if (inverse) return ntt_run(log_n, h_inv(w), 1, h_inv((u64)n % GL_P), n_polys, in, in_stride, n, scratch, n, out, out_stride, pick_stream(stream));
-  return ntt_run(log_n, w, 0, 0, n_polys, in, in_stride, n, scratch, n, out, out_stride, pick_stream(stream));
+  if (inverse) return ntt_run(log_n, true, 1, h_inv((u64)n % GL_P), n_polys, in, in_stride, n, scratch, n, out, out_stride, pick_stream(stream));
+  return ntt_run(log_n, false, 0, 0, n_polys, in, in_stride, n, scratch, n, out, out_stride, pick_stream(stream));
 }
 
 int p2e_coset_lde_dev(int log_n, int rate_bits, int n_polys, const uint64_t* values, size_t in_stride, uint64_t* out,
@@ -312,11 +411,11 @@ int p2e_coset_lde_dev(int log_n, int rate_bits, int n_polys, const uint64_t* val
   u64* coeffs = scratch + (size_t)n_polys * n;        // [n_polys][n]: c_k * g^k
   u64* tmp_m = coeffs + (size_t)n_polys * n;          // [n_polys][m]
   // ifft, with the coset shift folded into the output scaling: c_k * n^-1 * g^k
-  if ((rc = ntt_run(log_n, h_inv(h_root(log_n)), GL_COSET_SHIFT, h_inv((u64)n % GL_P), n_polys, values, in_stride, n, tmp_n, n,
+  if ((rc = ntt_run(log_n, true, GL_COSET_SHIFT, h_inv((u64)n % GL_P), n_polys, values, in_stride, n, tmp_n, n,
                     coeffs, n, st)))
     return rc;
   // fft of the zero-padded coefficients over the larger subgroup
-  return ntt_run(log_n + rate_bits, h_root(log_n + rate_bits), 0, 0, n_polys, coeffs, n, n, tmp_m, m, out, out_stride, st);
+  return ntt_run(log_n + rate_bits, false, 0, 0, n_polys, coeffs, n, n, tmp_m, m, out, out_stride, st);
 }
 
 // host-pointer forms

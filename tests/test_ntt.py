@@ -52,7 +52,7 @@ def test_ntt_cabi_rejects_bad_sizes():
 
 # ------------------------------------------------------------------------------------------ GPU tier
 @pytest.mark.gpu
-@pytest.mark.parametrize("log_n", [2, 3, 4, 5, 8, 9, 11, 12, 13])
+@pytest.mark.parametrize("log_n", [2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14])
 def test_fft_and_ifft_vs_oracle(engine, log_n):
     rng = random.Random(100 + log_n)
     n, polys = 1 << log_n, 3
