@@ -1,4 +1,4 @@
-# round-1 (session 3) evidence: bench lines, reference arm, launch list, ncu summaries, sanitizer pass on the new kernels
+# round-1 (session 3) evidence: bench lines, reference arm, launch list, ncu summaries
 set -x
 python bench.py --steps 20 --warmup 3 > gpurun_out/r01c_bench_n1.json 2> gpurun_out/r01c_bench_n1.err
 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/r01c_bench_reference_n1.json 2> gpurun_out/r01c_bench_reference_n1.err
@@ -9,6 +9,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k_prep|k_chain' -s 11 -c 11 -o gpurun_out/r01c_prof_chain -f \
     python scripts/profile_once.py ecdsa > gpurun_out/ncu_chain_full.log 2>&1
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_genstream.py tests/test_vanishing.py -m gpu -x -q -k "not full_size" > gpurun_out/r01c_sanitizer.log 2>&1; echo "sanitizer rc=$?" >> gpurun_out/r01c_sanitizer.log
 tail -n 3 gpurun_out/ncu_chain_full.log gpurun_out/r01c_sanitizer.log
 head -c 400 gpurun_out/r01c_bench_n1.json
