@@ -137,7 +137,8 @@ __device__ __forceinline__ u64 gl_red_lazy(u64 lo, u64 hi) {   // (hi:lo) mod P,
   u32 b, c;
   asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(t0), "=r"(b) : "l"(lo), "l"((u64)hh));
   t0 -= (u64)b;                                  // b = 0xffffffff = 2^64 mod P on borrow: + P
-  const u64 t1 = ((u64)hl << 32) - hl;           // hl * (2^32 - 1)
+  u64 t1;                                        // hl * (2^32 - 1) as ONE IMAD.WIDE: the evaluators / NTT are bound by the
+  asm("mul.wide.u32 %0, %1, 0xffffffff;" : "=l"(t1) : "r"(hl));   // ALU pipe (shift + 64-bit subtract), the IMAD pipe idles
   asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(t0), "l"(t1));
   return r + (u64)(0u - c);                      // 2^64 = 2^32 - 1 (mod P) on carry
 }
