@@ -36,6 +36,7 @@ WORKLOAD_NAMES = {
     "evaladd": "u29 add-many gate (3 addends, 5 ops / row; plonky2_ux spec unpinned) eval over 2^20 Goldilocks LDE rows",
     "evalfc": "MulNonnativeGate eval_filtered_base_batch + alpha-combination (2 challenges, fused) over 2^20 Goldilocks LDE rows",
     "evalcsfc": "CheckSumGate eval_filtered_base_batch + alpha-combination (2 challenges, fused) over 2^20 Goldilocks LDE rows",
+    "evalrcfc": "u29 range-check gate (9 limbs, 3-bit aux limbs; plonky2_ux spec unpinned) eval_filtered + alpha-combination (2 challenges, fused) over 2^20 Goldilocks LDE rows",
     "genstream": "serialized generator stream (8 x curve_add + curve_double chained: 224 in-tree generators, target-level wiring of "
                  "gadgets/curve.rs) run by the level-scheduled executor for 4096 circuits",
     "lde": "coset LDE (ifft 2^17 -> zero-pad -> coset fft 2^20, rate 8) of 135 wire polynomials: the matrix the gate evaluators read",
@@ -57,6 +58,7 @@ METRICS = {
     "evaladd": ("ux_add_many_gate_rows_per_s", "rows/s"),
     "evalfc": ("mul_nonnative_gate_filtered_combined_rows_per_s", "rows/s"),
     "evalcsfc": ("check_sum_gate_filtered_combined_rows_per_s", "rows/s"),
+    "evalrcfc": ("ux_range_check_gate_filtered_combined_rows_per_s", "rows/s"),
     "genstream": ("generator_stream_circuits_per_s", "circuits/s"),
     "lde": ("coset_lde_output_elements_per_s", "elements/s"),
 }
@@ -291,21 +293,22 @@ class Bench:
                 assert rc == 0, eng.last_error()
             return dict(step=step, step_e2e=step_e2e, units=n, h2d=33 * 8 * n, d2h=17 * 8 * n, alg_bytes=400 * n,
                         kernel="k_eval_check_sum", launches=1, err=None, dtype="u64 (Goldilocks)", keep=(wd, od, hw, ho))
-        if wl in ("evalfc", "evalcsfc"):
+        if wl in ("evalfc", "evalcsfc", "evalrcfc"):
             import ctypes
-            gate, nw = (0, 53) if wl == "evalfc" else (1, 33)
+            gate, nw = {"evalfc": (0, 53), "evalcsfc": (1, 33), "evalrcfc": (2, 99)}[wl]
             n = 1 << LOG_ROWS
             w = W.random_goldilocks(W.SEED + 5 + gate + self.rank, nw + 1, n)      # the wires + the selector constant column
             w[nw, ::3] = 0                                                          # a third of the rows select this gate exactly
             wd = self.dev(w)
             od = torch.empty((2, n), dtype=torch.int64, device="cuda")
-            prm = (ctypes.c_int * 5)(0, 0, 0, 0, 0)
+            prm = (ctypes.c_int * 5)(0, 29, 3, 9, 0) if gate == 2 else (ctypes.c_int * 5)(0, 0, 0, 0, 0)
             alphas = np.array([0x0123456789ABCDEF, 0xFEDCBA9876543210 % ((1 << 64) - (1 << 32) + 1)], dtype=np.uint64)
             sel_ptr = wd.data_ptr() + nw * n * 8
+            scr = torch.empty(int(lib.p2e_eval_filtered_scratch_bytes(gate, ctypes.addressof(prm), n)) // 8 + 2, dtype=torch.int64, device="cuda")
 
             def step():
                 rc = lib.p2e_eval_filtered_combined_dev(gate, ctypes.addressof(prm), 0, 0, 4, 1, n, wd.data_ptr(), n, sel_ptr,
-                                                        alphas.ctypes.data, 2, 4, 0, od.data_ptr(), n, None, sp)
+                                                        alphas.ctypes.data, 2, 4, 0, od.data_ptr(), n, scr.data_ptr(), sp)
                 assert rc == 0, eng.last_error()
             hw = self.pinned(w)
             ho = torch.empty((2, n), dtype=torch.int64).pin_memory()
@@ -315,8 +318,8 @@ class Bench:
                                                     alphas.ctypes.data, 2, 4, 0, ho.data_ptr())
                 assert rc == 0, eng.last_error()
             return dict(step=step, step_e2e=step_e2e, units=n, h2d=(nw + 1) * 8 * n, d2h=2 * 8 * n, alg_bytes=(nw + 1 + 2) * 8 * n,
-                        kernel="k_eval_mul_nonnative_fc<2>" if gate == 0 else "k_eval_check_sum_fc<2>", launches=1, err=None,
-                        dtype="u64 (Goldilocks)", keep=(wd, od, hw, ho, prm, alphas))
+                        kernel=["k_eval_mul_nonnative_fc<2>", "k_eval_check_sum_fc<2>", "k_eval_ux_range_check_fc<3, 2>"][gate],
+                        launches=1 if gate < 2 else 2, err=None, dtype="u64 (Goldilocks)", keep=(wd, od, hw, ho, prm, alphas, scr))
         if wl == "genstream":
             b = pkg.TargetCircuitBuilder()
             p0 = (b.add_virtual_nonnative_target(), b.add_virtual_nonnative_target())
@@ -652,7 +655,7 @@ def main():
     main_res = b.measure(wl, args.steps, args.warmup, e2e_steps=max(2, min(args.steps, 5)), sample_clocks=True)
     secondary = {}
     if not args.no_secondary:
-        for w2 in ("mulmod", "eval", "evalcs", "evalfc", "evalcsfc", "evalrc", "evalcmp", "evaladd", "lde", "genstream", "glv", "ecdsa"):
+        for w2 in ("mulmod", "eval", "evalcs", "evalfc", "evalcsfc", "evalrc", "evalrcfc", "evalcmp", "evaladd", "lde", "genstream", "glv", "ecdsa"):
             if w2 != wl:
                 try:
                     r2 = b.measure(w2, steps=min(args.steps, 20) if w2 != "glv" else 3, warmup=3, e2e_steps=2)

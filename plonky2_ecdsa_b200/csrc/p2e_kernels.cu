@@ -4,6 +4,7 @@
 #include "../../include/p2e.h"
 #include "p2e_common.h"
 #include "p2e_field.cuh"
+#include "p2e_fold.cuh"
 
 namespace p2e {
 
@@ -370,44 +371,6 @@ k_divrem_witness(size_t n, const u64* __restrict__ a, int al, const u64* __restr
 // Constraint evaluation over Goldilocks rows (A11, A12).  One LDE row per thread; wires are
 // arbitrary canonical field elements.  Column sums are accumulated un-reduced in 96-bit
 // accumulators per 32x32 partial-product class and reduced once per constraint.
-struct Acc3 {
-  u32 w0, w1, w2;
-};
-__device__ __forceinline__ void mac3(Acc3& a, u32 x, u32 y) {
-  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
-      "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
-      "addc.u32 %2, %2, 0;"
-      : "+r"(a.w0), "+r"(a.w1), "+r"(a.w2)
-      : "r"(x), "r"(y));
-}
-// (w0 + w1 2^32 + w2 2^64 + w3 2^96 + w4 2^128) mod P, w4 < 2^8, canonical result.
-// 2^64 = 2^32 - 1, 2^96 = -1, 2^128 = -2^32 (mod P)  =>  V = (w1:w0) + (w2 << 32) - (w2 + w3 + (w4 << 32))
-__device__ __forceinline__ u64 gl_reduce5(u32 w0, u32 w1, u32 w2, u32 w3, u32 w4) {
-  u64 a = ((u64)w1 << 32) | w0;
-  u64 b = (u64)w2 << 32;
-  u64 c = (u64)w2 + (u64)w3 + ((u64)w4 << 32);       // < 2^41
-  u64 t = a - c;
-  if (a < c) t -= GL_EPS;                            // + P
-  u64 r = t + b;
-  if (r < b) r += GL_EPS;                            // - 2^64 + eps
-  if (r >= GL_P) r -= GL_P;
-  return r;
-}
-
-// (A + B*2^32 + C*2^64 + add) mod P for 96-bit accumulators A, B, C
-__device__ __forceinline__ u64 reduce_abc(const Acc3& A, const Acc3& B, const Acc3& C, u64 add) {
-  u64 t = (u64)A.w0 + (u32)add;
-  u32 W0 = (u32)t;
-  t = (t >> 32) + A.w1 + B.w0 + (add >> 32);
-  u32 W1 = (u32)t;
-  t = (t >> 32) + A.w2 + B.w1 + C.w0;
-  u32 W2 = (u32)t;
-  t = (t >> 32) + B.w2 + C.w1;
-  u32 W3 = (u32)t;
-  u32 W4 = (u32)(t >> 32) + C.w2;
-  return gl_reduce5(W0, W1, W2, W3, W4);
-}
-
 // (QA0 + QA1 + (QB0 + QB1)*2^32 + add) mod P for carry-free 64-bit partial sums
 __device__ __forceinline__ u64 reduce_q(u64 qa0, u64 qa1, u64 qb0, u64 qb1, u64 add) {
   u64 t = (u64)(u32)qa0 + (u32)qa1 + (u32)add;
@@ -512,12 +475,6 @@ k_eval_check_sum(size_t n, const u64* __restrict__ wires, size_t is, u64* __rest
 // term t contributes term * alpha^t for every challenge alpha.  Fused here: one pass over the wires produces
 //   out[a][row] (+)= filter(row) * sum_c constraint_c(row) * alpha_a^(first_power + c)
 // so a gate costs (wires + 1 selector + n_alphas) columns of HBM traffic instead of (wires + constraints).
-constexpr int MAX_ALPHAS = 4;
-struct FilterArgs {
-  const u64* selector;       // [n] selector constants of the rows, or nullptr (filter = 1)
-  int gate_index, group_start, group_end, many_selectors;
-  int n_alphas, accumulate;
-};
 struct AlphaPow17 {
   u64 p[MAX_ALPHAS][2 * NL - 1];   // alpha_a^c
   u64 scale[MAX_ALPHAS];           // alpha_a^first_power
@@ -525,16 +482,6 @@ struct AlphaPow17 {
                                    // CheckSum: alpha_a - 2^29
   u64 kb[MAX_ALPHAS];              // CheckSum: 2^33 * sum_{i<16} alpha_a^i
 };
-
-__device__ __forceinline__ u64 compute_filter(const FilterArgs& F, size_t i) {
-  if (!F.selector) return 1;
-  const u64 s = F.selector[i];
-  u64 f = 1;
-  for (int j = F.group_start; j < F.group_end; j++)
-    if (j != F.gate_index) f = gl_mul(f, gl_sub((u64)j, s));
-  if (F.many_selectors) f = gl_mul(f, gl_sub(0xFFFFFFFFull, s));
-  return f;
-}
 
 // MulNonnativeGate, fused.  The alpha-combination of a convolution is a product of evaluations:
 //   sum_c alpha^c constraint_c = M(alpha) Q(alpha) - X(alpha) Y(alpha) + R(alpha) - CS(alpha),
@@ -1008,6 +955,7 @@ int p2e_gate_shape(int gate, const int* params, int* num_wires, int* num_constra
 size_t p2e_eval_filtered_scratch_bytes(int gate, const int* params, size_t n) {
   int w = 0, c = 0;
   if (gate != P2E_GATE_UX || gate_shape(gate, params, &w, &c)) return 16;
+  if (params[0] == P2E_UX_RANGE_CHECK) return (size_t)MAX_ALPHAS * c * 8;       // fused: only the table of powers
   return ((size_t)c * n + (size_t)MAX_ALPHAS * c) * 8;
 }
 
@@ -1034,6 +982,9 @@ int p2e_eval_filtered_combined_dev(int gate, const int* params, int gate_index, 
     Alphas al = {{0, 0, 0, 0}};
     for (int a = 0; a < n_alphas; a++) al.v[a] = alphas[a];
     k_alpha_powers<<<1, 32, 0, st>>>(al, n_alphas, first_power, nc, pw);
+    // the range-check gate has a fused form (one pass, nothing but the folded columns written)
+    rc = ux_eval_filtered_fused(params[0], params[1], params[2], params[3], params[4], n, wires, is, pw, F, out, os, st);
+    if (rc <= 0) return rc;
     if ((rc = p2e_eval_ux_dev(params[0], params[1], params[2], params[3], params[4], n, wires, is, cons, n, (void*)st))) return rc;
     if (n_alphas == 1) k_filter_combine<1><<<grid_for(n), TPB, 0, st>>>(n, nc, cons, n, pw, F, out, os);
     else if (n_alphas == 2) k_filter_combine<2><<<grid_for(n), TPB, 0, st>>>(n, nc, cons, n, pw, F, out, os);

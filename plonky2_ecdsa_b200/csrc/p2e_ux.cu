@@ -16,6 +16,7 @@
 #include "../../include/p2e.h"
 #include "p2e_common.h"
 #include "p2e_field.cuh"
+#include "p2e_fold.cuh"
 
 namespace p2e {
 
@@ -372,6 +373,81 @@ static u64 host_gl_inv(u64 x) {
     b = host_gl_mul(b, b);
   }
   return r;
+}
+
+// Range-check gate, fused with the selector filter and the challenge fold: one thread per LDE row walks the
+// `count` input limbs; every constraint (recomposition, then one range product per aux limb, in the gate's order) is
+// multiplied into un-reduced 96-bit accumulators per challenge instead of being canonicalised and stored -- 2 columns
+// written instead of num_constraints, and no second pass over them.  pw: [NA][num_constraints] powers of the challenges.
+template <int A, int NA>
+__global__ void __launch_bounds__(UX_TPB)
+k_eval_ux_range_check_fc(UxShape s, size_t n, const u64* __restrict__ wires, size_t is, const u64* __restrict__ pw,
+                         FilterArgs F, u64* __restrict__ out, size_t os) {
+  const size_t i = (size_t)blockIdx.x * UX_TPB + threadIdx.x;
+  if (i >= n) return;
+  Acc3 SA[NA], SB[NA], SC[NA];
+#pragma unroll
+  for (int a = 0; a < NA; a++) SA[a] = SB[a] = SC[a] = Acc3{0, 0, 0};
+  const int C = s.num_constraints;
+  auto fold = [&](u64 v, int c) {
+    const u32 vl = (u32)v, vh = (u32)(v >> 32);
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+      const u64 p = __ldg(pw + (size_t)a * C + c);
+      const u32 pl = (u32)p, ph = (u32)(p >> 32);
+      mac3(SA[a], vl, pl);
+      mac3(SB[a], vl, ph);
+      mac3(SB[a], vh, pl);
+      mac3(SC[a], vh, ph);
+    }
+  };
+  for (int u = 0; u < s.count; u++) {
+    const int aux0 = s.count + s.n_aux * u, c0 = u * (1 + s.n_aux);
+    const u64 input = W(u);
+    u64 acc = 0;
+#pragma unroll 4
+    for (int j = s.n_aux - 1; j >= 0; j--) {
+      const u64 a = W(aux0 + j);
+      fold(range_product<A>(a), c0 + 1 + j);
+      acc = gla(gl_shl<A>(acc), a);
+    }
+    fold(gls(acc, input), c0);
+  }
+  const u64 f = compute_filter(F, i);
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+    if (a < F.n_alphas) {
+      u64 r = gl_mul(f, reduce_abc(SA[a], SB[a], SC[a], 0));
+      if (F.accumulate) r = gl_add(r, out[a * os + i]);
+      out[a * os + i] = r;
+    }
+  }
+}
+
+template <int A>
+static void launch_rc_fc(const UxShape& s, size_t n, const u64* wires, size_t is, const u64* pw, const FilterArgs& F, u64* out,
+                         size_t os, cudaStream_t st) {
+  const unsigned g = (unsigned)((n + UX_TPB - 1) / UX_TPB);
+  if (F.n_alphas == 1) k_eval_ux_range_check_fc<A, 1><<<g, UX_TPB, 0, st>>>(s, n, wires, is, pw, F, out, os);
+  else if (F.n_alphas == 2) k_eval_ux_range_check_fc<A, 2><<<g, UX_TPB, 0, st>>>(s, n, wires, is, pw, F, out, os);
+  else k_eval_ux_range_check_fc<A, 4><<<g, UX_TPB, 0, st>>>(s, n, wires, is, pw, F, out, os);
+}
+
+// fused filter + fold for the range-check gate; returns 1 when this gate has no fused form (caller takes the generic path)
+int ux_eval_filtered_fused(int gate, int bits, int lb, int count, int na, size_t n, const u64* wires, size_t is, const u64* pw,
+                           const FilterArgs& F, u64* out, size_t os, cudaStream_t st) {
+  if (gate != P2E_UX_RANGE_CHECK) return 1;
+  UxShape s;
+  int rc = ux_shape(gate, bits, lb, count, na, &s);
+  if (rc) return rc;
+  switch (lb) {
+    case 1: launch_rc_fc<1>(s, n, wires, is, pw, F, out, os, st); break;
+    case 2: launch_rc_fc<2>(s, n, wires, is, pw, F, out, os, st); break;
+    case 3: launch_rc_fc<3>(s, n, wires, is, pw, F, out, os, st); break;
+    default: launch_rc_fc<4>(s, n, wires, is, pw, F, out, os, st); break;
+  }
+  P2E_CUDA(cudaGetLastError());
+  return 0;
 }
 
 template <int A>

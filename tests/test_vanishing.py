@@ -55,7 +55,9 @@ def test_gate_shape_cabi():
     prm = (ctypes.c_int * 5)(pkg.UX_RANGE_CHECK, 29, 3, 9, 0)
     assert lib.p2e_gate_shape(pkg.GATE_UX, ctypes.addressof(prm), ctypes.addressof(nw), ctypes.addressof(nc)) == 0
     assert (nw.value, nc.value) == (99, 99)
-    assert lib.p2e_eval_filtered_scratch_bytes(pkg.GATE_UX, ctypes.addressof(prm), 1000) == (99 * 1000 + 4 * 99) * 8
+    assert lib.p2e_eval_filtered_scratch_bytes(pkg.GATE_UX, ctypes.addressof(prm), 1000) == 4 * 99 * 8       # fused: powers only
+    prm = (ctypes.c_int * 5)(pkg.UX_COMPARISON, 29, 2, 1, 0)
+    assert lib.p2e_eval_filtered_scratch_bytes(pkg.GATE_UX, ctypes.addressof(prm), 1000) == (83 * 1000 + 4 * 83) * 8
     assert lib.p2e_gate_shape(7, ctypes.addressof(prm), None, None) < 0
     # no device: the compute entry fails loudly
     import torch
@@ -76,6 +78,10 @@ GATES = [
     ("mul_nonnative_n", pkg.GATE_MUL_NONNATIVE, (pkg.SECP256K1_SCALAR,), lambda w: S.mul_nonnative_gate_eval(w, S.SECP_N)),
     ("check_sum", pkg.GATE_CHECK_SUM, (), S.check_sum_gate_eval),
     ("ux_range_check", pkg.GATE_UX, (pkg.UX_RANGE_CHECK, 29, 3, 9, 0), U.UXRangeCheckGate(29, 3, 9).eval_unfiltered),
+    ("ux_range_check_34", pkg.GATE_UX, (pkg.UX_RANGE_CHECK, 34, 3, 8, 0), U.UXRangeCheckGate(34, 3, 8).eval_unfiltered),
+    ("ux_range_check_2bit", pkg.GATE_UX, (pkg.UX_RANGE_CHECK, 32, 2, 8, 0), U.UXRangeCheckGate(32, 2, 8).eval_unfiltered),
+    ("ux_range_check_1bit", pkg.GATE_UX, (pkg.UX_RANGE_CHECK, 7, 1, 3, 0), U.UXRangeCheckGate(7, 1, 3).eval_unfiltered),
+    ("ux_range_check_4bit", pkg.GATE_UX, (pkg.UX_RANGE_CHECK, 29, 4, 5, 0), U.UXRangeCheckGate(29, 4, 5).eval_unfiltered),
     ("ux_comparison", pkg.GATE_UX, (pkg.UX_COMPARISON, 29, 2, 1, 0), U.UXComparisonGate(29, chunk_bits=2).eval_unfiltered),
     ("ux_add_many", pkg.GATE_UX, (pkg.UX_ADD_MANY, 29, 2, 5, 3), U.UXAddManyGate(29, 2, 3, 5).eval_unfiltered),
     ("ux_subtraction", pkg.GATE_UX, (pkg.UX_SUBTRACTION, 29, 2, 6, 0), U.UXSubtractionGate(29, 2, 6).eval_unfiltered),
