@@ -339,8 +339,9 @@ int p2e_genstream_run(int handle, size_t n, const uint32_t* in_slots, int n_in, 
  * first_power = number of vanishing terms that precede the gate constraints; selector == NULL: filter = 1).
  * gate / params (int[5]): P2E_GATE_MUL_NONNATIVE {modulus}, P2E_GATE_CHECK_SUM {}, P2E_GATE_UX {ux gate,
  * bits, limb_bits, count, num_addends}.  The two in-tree gates are fused (wires are read once, only
- * n_alphas columns are written); P2E_GATE_UX goes through p2e_eval_ux_dev and needs
- * p2e_eval_filtered_scratch_bytes() bytes of device scratch (NULL is fine for the fused gates). */
+ * n_alphas columns are written), and so is the plonky2_ux range-check gate (scratch: only its table of challenge
+ * powers); the other P2E_GATE_UX gates go through p2e_eval_ux_dev into scratch and a generic fold kernel.
+ * scratch: p2e_eval_filtered_scratch_bytes() bytes of device memory (NULL is fine for the two in-tree gates). */
 #define P2E_GATE_MUL_NONNATIVE 0
 #define P2E_GATE_CHECK_SUM 1
 #define P2E_GATE_UX 2
