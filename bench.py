@@ -357,8 +357,8 @@ class Bench:
                 assert rc == 0, eng.last_error()
             # algorithmic bytes: every slot of the value table is written once and read about once
             return dict(step=step, step_e2e=step_e2e, units=n, h2d=len(in_slots) * 8 * n, d2h=len(out_slots) * 8 * n + 4 * n,
-                        alg_bytes=2 * n_slots * 8 * n, kernel="level schedule: %d generators, %d levels, %d launch groups (gather + witness kernel + scatter each), one CUDA graph"
-                        % (gs.num_generators, gs.num_levels, gs.num_groups), launches=3 * gs.num_groups, err=ed, dtype="u32 limbs / u64 (int)",
+                        alg_bytes=2 * n_slots * 8 * n, kernel="level schedule: %d generators, %d levels, %d launch groups (one fused kernel each), one CUDA graph"
+                        % (gs.num_generators, gs.num_levels, gs.num_groups), launches=gs.num_groups, err=ed, dtype="u32 limbs / u64 (int)",
                         keep=(gs, vd, table, hv, ho, he, in_slots, out_slots))
         if wl in UX_WORKLOADS:
             gate, bits, lb, count, na, kname = UX_WORKLOADS[wl]

@@ -15,9 +15,11 @@
 // P2E_GEN_COPY records feed a union-find and every partition becomes one SLOT, a row of the device table
 // V[slot][instance].  A generator's level is 1 + the highest level among the producers of the slots it
 // reads; generators of one level with the same kind / modulus / limb shape form a GROUP that runs as ONE
-// launch of the ordinary batched kernel over (instances of the group) x (n circuits): a gather kernel stages
-// the group's operand rows, the p2e_*_witness_dev entry runs on them, a scatter kernel writes the output
-// rows back (a slot that already holds a value is compared instead, like plonky2's "partition set twice").
+// launch over (instances of the group) x (n circuits): a fused kernel reads the operand rows through the group's
+// slot lists, runs the same arithmetic core as the standalone batched kernel and writes the output rows back (a
+// slot that already holds a value is compared instead, like plonky2's "partition set twice").  The staged form
+// (gather kernel -> p2e_*_witness_dev -> scatter kernel) remains for BigUint div_rem and as a cross-check
+// (P2E_GENSTREAM_FUSED=0).
 #include <algorithm>
 #include <map>
 #include <mutex>
@@ -26,11 +28,9 @@
 
 #include "../../include/p2e.h"
 #include "p2e_common.h"
+#include "p2e_field.cuh"
 
 namespace p2e {
-
-typedef uint32_t u32;
-typedef uint64_t u64;
 
 constexpr u32 GS_NONE = 0xFFFFFFFFu;      // absent operand limb (reads 0) / discarded output row
 constexpr u32 GS_CHECK = 0x80000000u;     // output slot already has a producer: compare, do not write
@@ -141,6 +141,174 @@ k_gs_get_outputs(size_t n, const u32* __restrict__ slots, const u64* __restrict_
   out[(size_t)blockIdx.y * os + i] = V[(size_t)slots[blockIdx.y] * vs + i];
 }
 
+// ---- fused group kernels ----------------------------------------------------------------------------------
+// One launch per group: thread (i, j) runs generator instance j of the group for circuit i, reading its operand
+// rows straight from the value table through the group's slot lists and writing (or, for a slot that already has a
+// producer, comparing) its outputs -- the same arithmetic cores as the standalone batched kernels (p2e_field.cuh),
+// without the gather / scatter launches and their staging traffic.
+struct GsIO {
+  const u32* idx;    // [in_rows][m] operand slots
+  const u32* oidx;   // [out_rows][m] output slots
+  u64* V;
+  size_t vs, n;
+  u32* err;
+  int m;
+  __device__ __forceinline__ u64 in(int row, int j, size_t i) const {
+    const u32 s = idx[(size_t)row * m + j];
+    return s == GS_NONE ? 0 : V[(size_t)s * vs + i];
+  }
+  __device__ __forceinline__ u32 out(int row, int j, size_t i, u64 v) const {
+    const u32 s = oidx[(size_t)row * m + j];
+    if (s == GS_NONE) return 0;
+    if (s & GS_CHECK) return V[(size_t)(s & ~GS_CHECK) * vs + i] != v ? (u32)P2E_ERR_CONNECT : 0u;
+    V[(size_t)s * vs + i] = v;
+    return 0;
+  }
+  __device__ __forceinline__ void fail(size_t i, u32 e) const {
+    if (e) atomicOr(&err[i], e);
+  }
+};
+#define GS_THREAD()                                              \
+  const size_t i = (size_t)blockIdx.x * GS_TPB + threadIdx.x;    \
+  const int j = j0 + blockIdx.y;                                 \
+  if (i >= io.n) return
+
+template <class MOD>
+__global__ void __launch_bounds__(GS_TPB) k_gs_mul(GsIO io, int j0) {
+  GS_THREAD();
+  u64 xw[NL], yw[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    xw[l] = io.in(l, j, i);
+    yw[l] = io.in(NL + l, j, i);
+  }
+  u32 xa[NL], ya[NL], r[NL], q[NL];
+  u64 cs[2 * NL - 1], b[2 * NL - 2];
+  u32 e = load_mul_wires(xw, xa) | load_mul_wires(yw, ya);
+  if (e == 0) {
+    e = mul_witness_core<MOD>(xa, ya, r, q, cs, b);
+  } else {
+#pragma unroll
+    for (int l = 0; l < NL; l++) r[l] = q[l] = 0;
+#pragma unroll
+    for (int l = 0; l < 2 * NL - 1; l++) cs[l] = 0;
+  }
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    e |= io.out(P2E_MUL_OUT_R + l, j, i, r[l]);
+    e |= io.out(P2E_MUL_OUT_Q + l, j, i, q[l]);
+  }
+#pragma unroll
+  for (int l = 0; l < 2 * NL - 1; l++) e |= io.out(P2E_MUL_OUT_CHECK_SUM + l, j, i, cs[l]);
+  io.fail(i, e);
+}
+
+__global__ void __launch_bounds__(GS_TPB) k_gs_check_sum(GsIO io, int j0) {
+  GS_THREAD();
+  u64 aw[2 * NL - 1], b[2 * NL - 2];
+#pragma unroll
+  for (int l = 0; l < 2 * NL - 1; l++) aw[l] = io.in(l, j, i);
+  u32 e = check_sum_core(aw, b);
+#pragma unroll
+  for (int l = 0; l < 2 * NL - 2; l++) e |= io.out(l, j, i, b[l]);
+  io.fail(i, e);
+}
+
+template <class MOD, bool IS_SUB>
+__global__ void __launch_bounds__(GS_TPB) k_gs_addsub(GsIO io, int j0, int al, int bl) {
+  GS_THREAD();
+  u64 aw[NL], bw[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    aw[l] = l < al ? io.in(l, j, i) : 0;
+    bw[l] = l < bl ? io.in(al + l, j, i) : 0;
+  }
+  u32 ac[NL], bc[NL], r[NL];
+  u32 e = load_canon<MOD>(aw, ac) | load_canon<MOD>(bw, bc);
+  u32 ov = 0;
+  if (e == 0) ov = IS_SUB ? sub_witness_core<MOD>(ac, bc, r) : add_witness_core<MOD>(ac, bc, r);
+  else set_zero9(r);
+#pragma unroll
+  for (int l = 0; l < NL; l++) e |= io.out(l, j, i, r[l]);
+  e |= io.out(NL, j, i, ov);
+  io.fail(i, e);
+}
+
+template <class MOD>
+__global__ void __launch_bounds__(GS_TPB) k_gs_add_many(GsIO io, int j0, int k) {
+  GS_THREAD();
+  u32 acc[NL];
+  set_zero9(acc);
+  u32 ov = 0, e = 0;
+  for (int t = 0; t < k; t++) {
+    u64 w[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) w[l] = io.in(t * NL + l, j, i);
+    u32 v[NL], sum[NL];
+    e |= load_canon<MOD>(w, v);
+    add9(acc, v, sum);
+    if (geq_mod<MOD>(sum)) { sub_mod9<MOD>(sum, acc); ov++; }
+    else copy9(sum, acc);
+  }
+  if (e) { set_zero9(acc); ov = 0; }
+#pragma unroll
+  for (int l = 0; l < NL; l++) e |= io.out(l, j, i, acc[l]);
+  e |= io.out(NL, j, i, ov);
+  io.fail(i, e);
+}
+
+// one Fermat ladder per instance: the reference's own algorithm (nonnative.rs:863); a group is small, its instances
+// run side by side
+template <class MOD>
+__global__ void __launch_bounds__(GS_TPB) k_gs_inv(GsIO io, int j0) {
+  GS_THREAD();
+  u64 w[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) w[l] = io.in(l, j, i);
+  u32 xc[NL], inv[NL], div[NL];
+  set_zero9(inv);
+  set_zero9(div);
+  u32 e = load_canon<MOD>(w, xc);
+  if (e == 0 && is_zero9(xc)) e = ERR_INVERSE_ZERO;
+  if (e == 0) {
+    inv_mod<MOD>(xc, inv);
+    e |= inv_div_core<MOD>(xc, inv, div);
+  }
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    e |= io.out(l, j, i, div[l]);
+    e |= io.out(NL + l, j, i, inv[l]);
+  }
+  io.fail(i, e);
+}
+
+__global__ void __launch_bounds__(GS_TPB) k_gs_glv(GsIO io, int j0) {
+  GS_THREAD();
+  u64 w[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) w[l] = io.in(l, j, i);
+  u32 kc[NL], k1[NL], k2[NL], n1 = 0, n2 = 0;
+  u32 e = load_canon<ModN>(w, kc);
+  if (e == 0) {
+    glv_decompose_core(kc, k1, k2, n1, n2);
+    u32 hi = 0;
+#pragma unroll
+    for (int l = 5; l < NL; l++) hi |= k1[l] | k2[l];
+    if (hi) e |= ERR_LIMBS_OVERFLOW;
+  } else {
+    set_zero9(k1);
+    set_zero9(k2);
+  }
+#pragma unroll
+  for (int l = 0; l < 5; l++) {
+    e |= io.out(l, j, i, k1[l]);
+    e |= io.out(5 + l, j, i, k2[l]);
+  }
+  e |= io.out(10, j, i, n1);
+  e |= io.out(11, j, i, n2);
+  io.fail(i, e);
+}
+
 // ---- host: stream parsing ---------------------------------------------------------------------------------
 struct TargetKey {
   u64 is_wire, a, b;
@@ -219,6 +387,7 @@ struct GenStream {
   cudaGraphExec_t graph = nullptr;
   size_t g_n = 0, g_vs = 0;
   const void *g_V = nullptr, *g_err = nullptr, *g_stage = nullptr, *g_stage_err = nullptr;
+  bool g_fused = false;
   std::string error;
 
   u32 tid(const TargetKey& k) {
@@ -575,6 +744,12 @@ static int ensure_device(GenStream& S) {
   return 0;
 }
 
+// 1 (default): one fused kernel per group; 0: gather -> standalone batched kernel -> scatter (BigUint div_rem always)
+static bool use_fused() {            // read per call: the tests run both paths in one process
+  const char* e = getenv("P2E_GENSTREAM_FUSED");
+  return !e || atoi(e) != 0;
+}
+
 static int per_launch(size_t n) {
   int per = (int)std::max<size_t>(1, GS_MAX_STAGED / std::max<size_t>(n, 1));
   return std::min(per, 65535);
@@ -616,6 +791,36 @@ static int run_groups(GenStream& S, size_t n, u64* V, size_t vs, u32* err, cudaS
       P2E_CUDA(cudaGetLastError());
       continue;
     }
+    if (use_fused() && G.kind != K_DIVREM) {
+      GsIO io = {idx, oidx, V, vs, n, err, G.m};
+      const bool base = G.modulus == P2E_SECP256K1_BASE;
+      for (int j0 = 0; j0 < G.m; j0 += 65535) {
+        const dim3 grid(gx, (unsigned)std::min(G.m - j0, 65535));
+        switch (G.kind) {
+          case K_MUL:
+            if (base) k_gs_mul<ModP><<<grid, GS_TPB, 0, st>>>(io, j0); else k_gs_mul<ModN><<<grid, GS_TPB, 0, st>>>(io, j0);
+            break;
+          case K_CHECKSUM: k_gs_check_sum<<<grid, GS_TPB, 0, st>>>(io, j0); break;
+          case K_ADD:
+            if (base) k_gs_addsub<ModP, false><<<grid, GS_TPB, 0, st>>>(io, j0, G.shape_a, G.shape_b);
+            else k_gs_addsub<ModN, false><<<grid, GS_TPB, 0, st>>>(io, j0, G.shape_a, G.shape_b);
+            break;
+          case K_SUB:
+            if (base) k_gs_addsub<ModP, true><<<grid, GS_TPB, 0, st>>>(io, j0, G.shape_a, G.shape_b);
+            else k_gs_addsub<ModN, true><<<grid, GS_TPB, 0, st>>>(io, j0, G.shape_a, G.shape_b);
+            break;
+          case K_MULTIADD:
+            if (base) k_gs_add_many<ModP><<<grid, GS_TPB, 0, st>>>(io, j0, G.shape_a); else k_gs_add_many<ModN><<<grid, GS_TPB, 0, st>>>(io, j0, G.shape_a);
+            break;
+          case K_INV:
+            if (base) k_gs_inv<ModP><<<grid, GS_TPB, 0, st>>>(io, j0); else k_gs_inv<ModN><<<grid, GS_TPB, 0, st>>>(io, j0);
+            break;
+          default: k_gs_glv<<<grid, GS_TPB, 0, st>>>(io, j0); break;
+        }
+      }
+      P2E_CUDA(cudaGetLastError());
+      continue;
+    }
     for (int j0 = 0; j0 < G.m; j0 += per) {
       const int mc = std::min(G.m - j0, per);
       const size_t M = (size_t)mc * n;
@@ -644,12 +849,8 @@ static int run_groups(GenStream& S, size_t n, u64* V, size_t vs, u32* err, cudaS
 }
 
 static bool use_graph() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("P2E_GENSTREAM_GRAPH");
-    v = e ? atoi(e) : 1;
-  }
-  return v != 0;
+  const char* e = getenv("P2E_GENSTREAM_GRAPH");
+  return !e || atoi(e) != 0;
 }
 
 // the launch sequence as a CUDA graph, re-used while (n, table, stride, err, staging) stay the same
@@ -657,7 +858,8 @@ static int run_groups_graphed(GenStream& S, size_t n, u64* V, size_t vs, u32* er
   int rc;
   if ((rc = size_staging(S, n))) return rc;
   if (!use_graph() || S.groups.size() < 8) return run_groups(S, n, V, vs, err, st);
-  const bool hit = S.graph && S.g_n == n && S.g_V == V && S.g_vs == vs && S.g_err == err && S.g_stage == S.d_stage &&
+  const bool fused = use_fused();
+  const bool hit = S.graph && S.g_fused == fused && S.g_n == n && S.g_V == V && S.g_vs == vs && S.g_err == err && S.g_stage == S.d_stage &&
                    S.g_stage_err == S.d_stage_err;
   if (!hit) {
     S.drop_graph();
@@ -678,7 +880,7 @@ static int run_groups_graphed(GenStream& S, size_t n, u64* V, size_t vs, u32* er
       cudaGetLastError();
       return run_groups(S, n, V, vs, err, st);
     }
-    S.g_n = n; S.g_V = V; S.g_vs = vs; S.g_err = err; S.g_stage = S.d_stage; S.g_stage_err = S.d_stage_err;
+    S.g_fused = fused; S.g_n = n; S.g_V = V; S.g_vs = vs; S.g_err = err; S.g_stage = S.d_stage; S.g_stage_err = S.d_stage_err;
   }
   P2E_CUDA(cudaGraphLaunch(S.graph, st));
   return 0;

@@ -256,8 +256,24 @@ def _rand_point(rng):
     return S.pt_mul(rng.randrange(1, N), S.G)
 
 
+@pytest.fixture(params=["fused", "staged", "staged-nograph"])
+def gs_mode(request):
+    """Both execution forms of a launch group (one fused kernel / gather -> batched kernel -> scatter), with and
+    without the CUDA graph."""
+    import os
+    old = {k: os.environ.get(k) for k in ("P2E_GENSTREAM_FUSED", "P2E_GENSTREAM_GRAPH")}
+    os.environ["P2E_GENSTREAM_FUSED"] = "1" if request.param == "fused" else "0"
+    os.environ["P2E_GENSTREAM_GRAPH"] = "0" if request.param.endswith("nograph") else "1"
+    yield request.param
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
 @pytest.mark.gpu
-def test_curve_chain_stream_vs_oracle_worklist(engine):
+def test_curve_chain_stream_vs_oracle_worklist(engine, gs_mode):
     c, pts, a_const, t = _curve_circuit()
     g = engine.load_generator_stream(c.w.bytes())
     rng = random.Random(2024)
@@ -285,7 +301,7 @@ def test_curve_chain_stream_vs_oracle_worklist(engine):
 
 
 @pytest.mark.gpu
-def test_stream_with_every_record_kind(engine):
+def test_stream_with_every_record_kind(engine, gs_mode):
     """GLV decomposition, BigUint div_rem, scalar-field generators, ConstantGenerator / ArithmeticBaseGenerator glue,
     short operands (absent limbs read as zero), a slot written twice with equal and with different values."""
     w = GeneratorStreamWriter()
@@ -339,7 +355,7 @@ def test_stream_with_every_record_kind(engine):
 
 
 @pytest.mark.gpu
-def test_stream_errors_and_missing_inputs(engine):
+def test_stream_errors_and_missing_inputs(engine, gs_mode):
     w = GeneratorStreamWriter()
     x, inv, div = [virtual(i) for i in range(9)], [virtual(9 + i) for i in range(9)], [virtual(18 + i) for i in range(9)]
     w.nonnative_inverse_generator(0, x, inv, div)
