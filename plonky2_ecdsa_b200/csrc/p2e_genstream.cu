@@ -271,7 +271,16 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_inv(GsIO io, int j0) {
   u32 e = load_canon<MOD>(w, xc);
   if (e == 0 && is_zero9(xc)) e = ERR_INVERSE_ZERO;
   if (e == 0) {
-    inv_mod<MOD>(xc, inv);
+    if (MOD::ID == 0) {
+      // base field: the ladder in lazy limbs (limb-parallel carry passes, ~1/3 of the dependency chain of the exact
+      // mulmod ladder -- this kernel is pure latency), one exact canonicalisation at the end; the inverse is unique
+      i32 lx[NL], li[NL];
+      lz_from_canon(xc, lx);
+      lz_inv(lx, li);
+      lz_canon(li, inv);
+    } else {
+      inv_mod<MOD>(xc, inv);
+    }
     e |= inv_div_core<MOD>(xc, inv, div);
   }
 #pragma unroll
