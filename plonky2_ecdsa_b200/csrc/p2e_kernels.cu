@@ -198,7 +198,15 @@ k_inv_witness(size_t n, const u64* __restrict__ x, size_t is, u64* __restrict__ 
   }
   if (cnt == 0) return;
   u32 inv_run[NL];
-  inv_mod<MOD>(run, inv_run);
+  if (MOD::ID == 0) {
+    // base field: the ladder in lazy limbs (~1/3 of the dependency chain of the exact-mulmod ladder), canonical once
+    i32 lx[NL], li[NL];
+    lz_from_canon(run, lx);
+    lz_inv(lx, li);
+    lz_canon(li, inv_run);
+  } else {
+    inv_mod<MOD>(run, inv_run);
+  }
 #pragma unroll
   for (int c = INV_CHUNK - 1; c >= 0; c--) {
     size_t i = t0 + (size_t)c * T;
