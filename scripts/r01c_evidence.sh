@@ -9,5 +9,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --no-secondary --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k_prep|k_chain' -s 11 -c 11 -o gpurun_out/r01c_prof_chain -f \
     python scripts/profile_once.py ecdsa > gpurun_out/ncu_chain_full.log 2>&1
-tail -n 3 gpurun_out/ncu_chain_full.log gpurun_out/r01c_sanitizer.log
+tail -n 3 gpurun_out/ncu_chain_full.log
 head -c 400 gpurun_out/r01c_bench_n1.json
