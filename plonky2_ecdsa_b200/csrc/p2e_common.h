@@ -34,6 +34,7 @@ int get_scratch(int slot, size_t bytes, void** out);
 
 void chain_release_device_tapes();
 void ntt_release_tables();
+void genstream_release_device();
 
 static inline cudaStream_t pick_stream(void* s) { return s ? (cudaStream_t)s : ctx().stream; }
 

@@ -723,6 +723,13 @@ static bool finalize(GenStream& S) {
   return true;
 }
 
+// p2e_shutdown(): device buffers and graphs of every loaded stream go with the context (the parsed streams stay)
+void genstream_release_device() {
+  std::lock_guard<std::mutex> lock(g_gs_mu);
+  for (GenStream* S : g_streams)
+    if (S) S->release_device();
+}
+
 static GenStream* get_stream(int h) {
   if (h < 0 || h >= (int)g_streams.size() || !g_streams[h]) {
     set_error_msg("genstream: bad handle");

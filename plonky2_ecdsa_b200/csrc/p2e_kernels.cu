@@ -734,6 +734,7 @@ void p2e_shutdown(void) {
   cudaStreamSynchronize(c.stream);
   chain_release_device_tapes();
   ntt_release_tables();
+  genstream_release_device();
   for (int i = 0; i < 4; i++) {
     if (c.scratch[i]) cudaFree(c.scratch[i]);
     c.scratch[i] = nullptr;
