@@ -69,3 +69,41 @@ def test_golden_ecdsa_witness_gpu(engine):
         assert col.shape[0] == d["slots"]
         assert [int(v) for v in col[:8]] == d["first8"] and [int(v) for v in col[-8:]] == d["last8"]
         assert hashlib.sha256(col.tobytes()).hexdigest() == d["sha256"]
+
+
+def test_golden_generator_stream_bytes_are_what_the_builder_emits():
+    """The committed stream is byte-for-byte what the product-side target-level builder writes for the same circuit."""
+    import plonky2_ecdsa_b200 as pkg
+    b = pkg.TargetCircuitBuilder()
+    pts = [(b.add_virtual_nonnative_target(), b.add_virtual_nonnative_target()) for _ in range(2)]
+    a_const = b.add_virtual_nonnative_target()
+    b.curve_add(b.curve_double(b.curve_add(pts[0], pts[1]), a_const), pts[0])
+    assert b.bytes().hex() == G["generator_stream"]["bytes_hex"]
+    gs = pkg.GeneratorStream(pkg.load_library(), bytes.fromhex(G["generator_stream"]["bytes_hex"]))
+    assert gs.num_generators == 41 and len(gs.input_slots) == 45
+    gs.close()
+
+
+@pytest.mark.gpu
+def test_golden_filtered_combined_lde_and_generator_stream_gpu(engine):
+    import plonky2_ecdsa_b200 as pkg
+    fc = G["filtered_combined"]
+    kw = dict(selector=fc["selector"], gate_index=fc["gate_index"], group_range=tuple(fc["group"]),
+              many_selectors=fc["many_selectors"], first_power=fc["first_power"])
+    got = engine.eval_filtered_combined(pkg.GATE_MUL_NONNATIVE, (0,), arr(G["eval_mul_nonnative_mod0"]["wires"]), fc["alphas"], **kw)
+    assert got.tolist() == fc["mul_nonnative_mod0"]
+    got = engine.eval_filtered_combined(pkg.GATE_CHECK_SUM, (), arr(G["eval_check_sum"]["wires"]), fc["alphas"], **kw)
+    assert got.tolist() == fc["check_sum"]
+    g = G["coset_lde"]
+    assert engine.lde_onto_coset(arr(g["values"]), g["rate_bits"]).tolist() == g["out"]
+    g = G["generator_stream"]
+    gs = engine.load_generator_stream(bytes.fromhex(g["bytes_hex"]))
+    ins = {tuple(k): v for k, v in g["inputs"]}
+    targets = [tuple(t) for t in g["targets"]]
+    got, err = gs.run(ins, targets)
+    assert not err.any()
+    for j, d in enumerate(g["sha256"]):
+        assert hashlib.sha256(np.ascontiguousarray(got[:, j]).tobytes()).hexdigest() == d
+    res, _ = gs.run(ins, [tuple(t) for t in g["result_targets"]])
+    assert res.T.tolist() == g["result"]
+    gs.close()
