@@ -251,6 +251,31 @@ def test_load_rejects_malformed_streams():
     assert empty.num_generators == 0 and empty.num_slots == 0
 
 
+def test_loader_survives_corrupted_streams():
+    """Random truncations / byte flips of a valid stream: the loader returns a handle or an error, never crashes, and
+    a handle it returns answers its queries."""
+    c, _, _, _ = _curve_circuit()
+    good = c.w.bytes()
+    lib = pkg.load_library()
+    rng = random.Random(77)
+    ok = bad = 0
+    for _ in range(300):
+        b = bytearray(good[: rng.randrange(len(good) + 1)] if rng.random() < 0.3 else good)
+        for _ in range(rng.randrange(1, 4)):
+            if b:
+                b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
+        try:
+            g = pkg.GeneratorStream(lib, bytes(b))
+        except RuntimeError as e:
+            assert "genstream" in str(e)
+            bad += 1
+            continue
+        assert g.num_slots >= 0 and len(g.generator_levels) == g.num_generators and len(g.input_slots) <= g.num_slots
+        g.close()
+        ok += 1
+    assert ok > 0 and bad > 0
+
+
 # ------------------------------------------------------------------------------------------ GPU tier
 def _rand_point(rng):
     return S.pt_mul(rng.randrange(1, N), S.G)

@@ -43,6 +43,30 @@ def test_reduce_with_powers_multi_is_a_power_sum():
         (x + y) % GL_P for x, y in zip(V.reduce_with_powers_multi(terms, alphas), V.reduce_with_powers_multi(t2, alphas))]
 
 
+def test_fold_of_the_in_tree_gates_is_a_product_of_evaluations():
+    """The identities the fused kernels compute instead of evaluate-then-fold, against the gate
+    evaluators of the oracle on arbitrary field elements, both moduli:
+      sum_c a^c MulNonnative_c = M(a) Q(a) - X(a) Y(a) + R(a) - CS(a)      (gates/mul_nonnative.rs:101-130)
+      sum_c a^c CheckSum_c     = A(a) + (a - 2^29) (B(a) - 2^33 sum_{i<16} a^i)   (gates/mul_nonnative.rs:411-427)"""
+    rng = random.Random(11)
+    ev = lambda v, a: sum(x * pow(a, j, GL_P) for j, x in enumerate(v)) % GL_P
+    for m in (S.SECP_P, S.SECP_N):
+        m29 = S.convert_base(S.to_u32_digits(m), 32, 29)
+        for _ in range(20):
+            w = [rng.randrange(GL_P) for _ in range(53)]
+            a = rng.choice([0, 1, GL_P - 1, rng.randrange(GL_P)])
+            lhs = V.reduce_with_powers_multi(S.mul_nonnative_gate_eval(w, m), [a])[0]
+            rhs = (ev(m29, a) * ev(w[27:36], a) - ev(w[0:9], a) * ev(w[9:18], a) + ev(w[18:27], a) - ev(w[36:53], a)) % GL_P
+            assert lhs == rhs
+    for _ in range(20):
+        w = [rng.randrange(GL_P) for _ in range(33)]
+        a = rng.choice([0, 1, 1 << 29, rng.randrange(GL_P)])
+        lhs = V.reduce_with_powers_multi(S.check_sum_gate_eval(w), [a])[0]
+        g16 = sum(pow(a, i, GL_P) for i in range(16))
+        rhs = (ev(w[:17], a) + (a - (1 << 29)) * (ev(w[17:33], a) - (1 << 33) * g16)) % GL_P
+        assert lhs == rhs
+
+
 def test_gate_shape_cabi():
     import ctypes
     lib = pkg.load_library()
