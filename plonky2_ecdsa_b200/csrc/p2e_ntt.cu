@@ -117,17 +117,22 @@ __device__ __forceinline__ void dif_round8(u64* sm, int log_l, int log_t, int s,
     u64 v[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) v[q] = base[q << log_step];
+    // Canonicalisation is needed only where a value becomes the SECOND operand of an addition / subtraction
+    // (gla / gls take any u64 as their first operand): positions with bit 1 set after stage A (plus the odd ones for
+    // the inverse transform, whose stage-B subtraction is swapped), odd positions after stage B.
     // stage A: (q, q + 4), twiddle w_8^q
 #pragma unroll
     for (int q = 0; q < 4; q++) {
       const u64 a = v[q], c = v[q + 4];
-      v[q] = glc(gla(a, c));
+      const bool canon = (q & 2) || (INV && (q & 1));
+      const u64 sum = gla(a, c);
+      v[q] = canon ? glc(sum) : sum;
       u64 d;
       if (q == 0) d = gls(a, c);
       else if (q == 1) d = INV ? gl_shl<48>(gl_shl<24>(gls(a, c))) : gl_shl<24>(gls(c, a));      // 2^72 | -2^24
       else if (q == 2) d = INV ? gl_shl<48>(gls(c, a)) : gl_shl<48>(gls(a, c));                   // -2^48 | 2^48
       else d = INV ? gl_shl<24>(gls(a, c)) : gl_shl<48>(gl_shl<24>(gls(c, a)));                   // 2^24 | -2^72
-      v[q + 4] = glc(d);
+      v[q + 4] = canon ? glc(d) : d;
     }
     // stage B: (q, q + 2) inside each half, twiddle w_4^q = w_8^(2q)
 #pragma unroll
@@ -135,19 +140,21 @@ __device__ __forceinline__ void dif_round8(u64* sm, int log_l, int log_t, int s,
 #pragma unroll
       for (int q = 0; q < 2; q++) {
         const u64 a = v[h + q], c = v[h + q + 2];
-        v[h + q] = glc(gla(a, c));
+        const u64 sum = gla(a, c);
+        v[h + q] = (q & 1) ? glc(sum) : sum;
         u64 d;
         if (q == 0) d = gls(a, c);
         else d = INV ? gl_shl<48>(gls(c, a)) : gl_shl<48>(gls(a, c));
-        v[h + q + 2] = glc(d);
+        v[h + q + 2] = (q & 1) ? glc(d) : d;
       }
     }
     // stage C: (q, q + 1)
 #pragma unroll
     for (int h = 0; h < 8; h += 2) {
       const u64 a = v[h], c = v[h + 1];
-      v[h] = glc(gla(a, c));
-      v[h + 1] = glc(gls(a, c));
+      const u64 sum = gla(a, c), d = gls(a, c);
+      v[h] = (h == 0 || log_step == 0) ? glc(sum) : sum;        // the others are canonicalised after their twiddle
+      v[h + 1] = log_step == 0 ? glc(d) : d;
     }
     if (log_step > 0) {
 #pragma unroll
