@@ -364,8 +364,8 @@ struct GsGen {
 
 struct GsGroup {
   int level, kind, modulus, shape_a, shape_b, m;
-  int in_rows, out_rows;
-  size_t idx_off, oidx_off, const_off;   // into the device index / constant pools
+  int in_rows = 0, out_rows = 0;
+  size_t idx_off = 0, oidx_off = 0, const_off = 0;   // into the device index / constant pools
 };
 
 struct GenStream {
@@ -480,7 +480,7 @@ static bool parse_record(GenStream& S, Reader& R) {
   g.modulus = P2E_SECP256K1_BASE;
   auto bad = [&](const char* m) { S.error = std::string("genstream: ") + m; return false; };
   switch (tag) {
-    case P2E_GEN_MUL_NONNATIVE_SCALAR: g.modulus = P2E_SECP256K1_SCALAR;   // fallthrough
+    case P2E_GEN_MUL_NONNATIVE_SCALAR: g.modulus = P2E_SECP256K1_SCALAR; [[fallthrough]];
     case P2E_GEN_MUL_NONNATIVE_BASE: {
       // MulNonnativeGenerator { row, num_limbs }: wires of the gate row, gates/mul_nonnative.rs:41-59
       const u64 row = R.u64le(), nl = R.u64le();
@@ -502,7 +502,7 @@ static bool parse_record(GenStream& S, Reader& R) {
       for (int c = 17; c < 33; c++) g.outs.push_back(wire(S, row, c));
       break;
     }
-    case P2E_GEN_NONNATIVE_ADDITION_SCALAR: case P2E_GEN_NONNATIVE_SUBTRACTION_SCALAR: g.modulus = P2E_SECP256K1_SCALAR;   // fallthrough
+    case P2E_GEN_NONNATIVE_ADDITION_SCALAR: case P2E_GEN_NONNATIVE_SUBTRACTION_SCALAR: g.modulus = P2E_SECP256K1_SCALAR; [[fallthrough]];
     case P2E_GEN_NONNATIVE_ADDITION_BASE: case P2E_GEN_NONNATIVE_SUBTRACTION_BASE: {
       // { a, b, sum | diff, overflow }: gadgets/nonnative.rs:647-652, 812-817
       g.kind = (tag == P2E_GEN_NONNATIVE_ADDITION_BASE || tag == P2E_GEN_NONNATIVE_ADDITION_SCALAR) ? K_ADD : K_SUB;
@@ -516,7 +516,7 @@ static bool parse_record(GenStream& S, Reader& R) {
       g.outs = s; g.outs.push_back(ov);
       break;
     }
-    case P2E_GEN_NONNATIVE_MULTIPLE_ADDS_SCALAR: g.modulus = P2E_SECP256K1_SCALAR;   // fallthrough
+    case P2E_GEN_NONNATIVE_MULTIPLE_ADDS_SCALAR: g.modulus = P2E_SECP256K1_SCALAR; [[fallthrough]];
     case P2E_GEN_NONNATIVE_MULTIPLE_ADDS_BASE: {
       // { summands_len, summands.., sum, overflow (UXTarget) }: gadgets/nonnative.rs:730-740
       const u64 k = R.u64le();
@@ -536,7 +536,7 @@ static bool parse_record(GenStream& S, Reader& R) {
       g.outs = s; g.outs.push_back(ov);
       break;
     }
-    case P2E_GEN_NONNATIVE_INVERSE_SCALAR: g.modulus = P2E_SECP256K1_SCALAR;   // fallthrough
+    case P2E_GEN_NONNATIVE_INVERSE_SCALAR: g.modulus = P2E_SECP256K1_SCALAR; [[fallthrough]];
     case P2E_GEN_NONNATIVE_INVERSE_BASE: {
       // { x, inv, div }: gadgets/nonnative.rs:874-878; the kernel's rows are div[9], inv[9] (set_* order :870-871)
       std::vector<u32> x, inv, div;
