@@ -29,6 +29,7 @@
 #include "../../include/p2e.h"
 #include "p2e_common.h"
 #include "p2e_field.cuh"
+#include "p2e_lzinv.cuh"
 
 namespace p2e {
 
@@ -257,44 +258,6 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_add_many(GsIO io, int j0, int k) 
   io.fail(i, e);
 }
 
-// Base-field Fermat ladder in lazy limbs through out-of-line multiply / square bodies: inlined, the ladder is ~160 KB
-// of straight-line code and the (latency-bound) kernel waits on instruction fetch (ncu: no_instruction 1.2 per issue).
-struct L9 {
-  i32 v[NL];
-};
-__device__ __noinline__ L9 gs_lzm(L9 a, L9 b) {
-  L9 r;
-  lz_mul(a.v, b.v, r.v);
-  return r;
-}
-__device__ __noinline__ L9 gs_lzs(L9 a) {
-  L9 r;
-  lz_sqr(a.v, r.v);
-  return r;
-}
-__device__ __forceinline__ L9 gs_lzs_n(L9 t, int n) {
-  for (int k = 0; k < n; k++) t = gs_lzs(t);
-  return t;
-}
-// x^(p-2), addition chain of p2e_field.cuh::lz_inv
-__device__ __forceinline__ L9 gs_lz_inv(L9 a) {
-  const L9 x2 = gs_lzm(gs_lzs(a), a);
-  const L9 x3 = gs_lzm(gs_lzs(x2), a);
-  L9 u = gs_lzm(gs_lzs_n(x3, 3), x3);                 // x6
-  u = gs_lzm(gs_lzs_n(u, 3), x3);                     // x9
-  u = gs_lzm(gs_lzs_n(u, 2), x2);                     // x11
-  const L9 x22 = gs_lzm(gs_lzs_n(u, 11), u);
-  const L9 x44 = gs_lzm(gs_lzs_n(x22, 22), x22);
-  const L9 x88 = gs_lzm(gs_lzs_n(x44, 44), x44);
-  u = gs_lzm(gs_lzs_n(x88, 88), x88);                 // x176
-  u = gs_lzm(gs_lzs_n(u, 44), x44);                   // x220
-  u = gs_lzm(gs_lzs_n(u, 3), x3);                     // x223
-  u = gs_lzm(gs_lzs_n(u, 23), x22);
-  u = gs_lzm(gs_lzs_n(u, 5), a);
-  u = gs_lzm(gs_lzs_n(u, 3), x2);
-  return gs_lzm(gs_lzs_n(u, 2), a);
-}
-
 // one Fermat ladder per instance: the reference's own algorithm (nonnative.rs:863); a group is small, its instances
 // run side by side
 template <class MOD>
@@ -312,10 +275,7 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_inv(GsIO io, int j0) {
     if (MOD::ID == 0) {
       // base field: the ladder in lazy limbs (limb-parallel carry passes, ~1/3 of the dependency chain of the exact
       // mulmod ladder -- this kernel is pure latency), one exact canonicalisation at the end; the inverse is unique
-      L9 lx;
-      lz_from_canon(xc, lx.v);
-      const L9 li = gs_lz_inv(lx);
-      lz_canon(li.v, inv);
+      inv_p_lazy(xc, inv);
     } else {
       inv_mod<MOD>(xc, inv);
     }
