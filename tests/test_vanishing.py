@@ -141,6 +141,16 @@ def test_filtered_combined_vs_spec(engine, g):
     for j in (0, 1, 7, n - 1):
         cons = ref_eval([int(v) for v in w[:, j]])
         assert [int(v) for v in got4[:, j]] == V.reduce_with_powers_multi(cons, al4)
+    # 1 and 3 challenges (3 runs through the 4-challenge instantiation), accumulating onto a previous result
+    for k in (1, 3):
+        prev = np.array([[rng.randrange(GL_P) for _ in range(n)] for _ in range(k)], dtype=np.uint64)
+        gotk = engine.eval_filtered_combined(gate, params, w, al4[:k], selector=sel, gate_index=me, group_range=group,
+                                             many_selectors=False, first_power=1, accumulate_into=prev)
+        assert gotk.shape == (k, n)
+        for j in (0, 3, 6, n - 1):
+            cons = ref_eval([int(v) for v in w[:, j]])
+            add = V.gate_terms_combined(cons, me, group, sel[j], False, al4[:k], 1)
+            assert [int(v) for v in gotk[:, j]] == [(int(prev[a, j]) + add[a]) % GL_P for a in range(k)]
 
 
 @pytest.mark.gpu
