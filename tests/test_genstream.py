@@ -251,6 +251,85 @@ def test_load_rejects_malformed_streams():
     assert empty.num_generators == 0 and empty.num_slots == 0
 
 
+def test_levels_of_random_generator_graphs_respect_the_dataflow():
+    """Host scheduling logic on random DAGs (no device): every generator sits strictly above the producers of the
+    partitions it reads, a second writer of a partition above the first, and the input slots are exactly the
+    partitions that are read but never produced -- with random copy constraints merging targets."""
+    lib = pkg.load_library()
+    rng = random.Random(4242)
+    for trial in range(12):
+        w = GeneratorStreamWriter()
+        n_virtual = 0
+
+        def fresh(k):
+            nonlocal n_virtual
+            v = [virtual(n_virtual + i) for i in range(k)]
+            n_virtual += k
+            return v
+        values = [fresh(9) for _ in range(4)]                 # pool of 9-limb values; the first four are inputs
+        gens = []                                             # (reads, writes) as target lists, stream order
+        copies = []
+        for _ in range(rng.randrange(20, 120)):
+            kind = rng.choice(["add", "sub", "inv", "mul", "copy"])
+            if kind == "copy":
+                a, b = rng.choice(values), rng.choice(values)
+                l = rng.randrange(9)
+                # only merge limbs of INPUT values (a copy between two produced partitions makes a second writer,
+                # covered below by the explicit double-write case)
+                if values.index(a) < 4 and values.index(b) < 4:
+                    w.copy(a[l], b[l])
+                    copies.append((a[l], b[l]))
+                continue
+            a, b = rng.choice(values), rng.choice(values)
+            if kind in ("add", "sub"):
+                out, ov = fresh(9), fresh(1)[0]
+                (w.nonnative_addition_generator if kind == "add" else w.nonnative_subtraction_generator)(rng.randrange(2), a, b, out, ov)
+                gens.append((a + b, out + [ov]))
+            elif kind == "inv":
+                inv, div = fresh(9), fresh(9)
+                w.nonnative_inverse_generator(rng.randrange(2), a, inv, div)
+                gens.append((list(a), inv + div))
+                out = inv
+            else:
+                row = 1000 * trial + len(gens)
+                for l in range(9):
+                    w.copy(a[l], wire(row, l))
+                    w.copy(b[l], wire(row, 9 + l))
+                    copies.append((a[l], wire(row, l)))
+                    copies.append((b[l], wire(row, 9 + l)))
+                w.mul_nonnative_generator(rng.randrange(2), row)
+                out = [wire(row, 18 + l) for l in range(9)]
+                gens.append(([wire(row, c) for c in range(18)], [wire(row, c) for c in range(18, 53)]))
+            values.append(out)
+        # an explicit second writer: an addition whose sum targets are an earlier generator's outputs
+        if len(values) > 6:
+            first = values[5]
+            w.nonnative_addition_generator(0, values[0], values[1], first, fresh(1)[0])
+            gens.append((values[0] + values[1], list(first)))
+        g = pkg.GeneratorStream(lib, w.bytes())
+        assert g.num_generators == len(gens)
+        lv = g.generator_levels
+        slot = g.slot
+        producer = {}
+        for k, (_, writes) in enumerate(gens):
+            for t in writes:
+                producer.setdefault(slot(t), k)
+        read_slots = set()
+        for k, (reads, writes) in enumerate(gens):
+            for t in reads:
+                read_slots.add(slot(t))
+                p = producer.get(slot(t))
+                if p is not None and p != k:
+                    assert lv[k] > lv[p], (trial, k, p)
+            for t in writes:
+                p = producer[slot(t)]
+                if p != k:
+                    assert lv[k] > lv[p]                      # the second writer checks after the first wrote
+        assert sorted(g.input_slots) == sorted(s for s in read_slots if s not in producer)
+        assert g.num_levels == max(lv) + 1
+        g.close()
+
+
 def test_loader_survives_corrupted_streams():
     """Random truncations / byte flips of a valid stream: the loader returns a handle or an error, never crashes, and
     a handle it returns answers its queries."""
