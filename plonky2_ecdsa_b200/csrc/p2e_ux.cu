@@ -88,6 +88,20 @@ template <int A>
 __device__ __forceinline__ u64 gl_shl(u64 v) { return gl_red_lazy(v << A, v >> (64 - A)); }     // any * 2^A -> any
 __device__ __forceinline__ u64 gl_shl_rt(u64 v, int a) { return gl_red_lazy(v << a, v >> (64 - a)); }
 
+// Horner recomposition sum_j a_j 2^(A j) (most significant limb first) on an un-reduced 128-bit accumulator: a constant
+// 128-bit shift and a 128-bit add per limb instead of a shift-reduce-add in the field (A n_aux < bits + A <= 52, so the
+// value stays below 2^116); reduced once per recomposition
+template <int A>
+struct Recomp {
+  u64 lo = 0, hi = 0;
+  __device__ __forceinline__ void push(u64 a) {
+    hi = (hi << A) | (lo >> (64 - A));
+    lo <<= A;
+    asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, 0;" : "+l"(lo), "+l"(hi) : "l"(a));
+  }
+  __device__ __forceinline__ u64 value() const { return gl_red_lazy(lo, hi); }          // any
+};
+
 // prod_{x < 2^A} (v - x) for a canonical wire v -> any
 template <int A>
 __device__ __forceinline__ u64 range_product(u64 v) {
@@ -130,14 +144,14 @@ __global__ void __launch_bounds__(UX_TPB)
 k_eval_ux_range_check(UxShape s, size_t n, const u64* __restrict__ wires, size_t is, u64* __restrict__ out, size_t os) {
   UX_ROW();
   const int aux0 = s.count + s.n_aux * u, c0 = u * (1 + s.n_aux);
-  u64 acc = 0;
+  Recomp<A> acc;
 #pragma unroll 4
   for (int j = s.n_aux - 1; j >= 0; j--) {
     const u64 a = W(aux0 + j);
     O(c0 + 1 + j) = glc(range_product<A>(a));
-    acc = gla(gl_shl<A>(acc), a);
+    acc.push(a);
   }
-  O(c0) = glc(gls(acc, W(u)));
+  O(c0) = glc(gls(acc.value(), W(u)));
 }
 
 template <int A>
@@ -404,14 +418,14 @@ k_eval_ux_range_check_fc(UxShape s, size_t n, const u64* __restrict__ wires, siz
   for (int u = 0; u < s.count; u++) {
     const int aux0 = s.count + s.n_aux * u, c0 = u * (1 + s.n_aux);
     const u64 input = W(u);
-    u64 acc = 0;
+    Recomp<A> acc;
 #pragma unroll 4
     for (int j = s.n_aux - 1; j >= 0; j--) {
       const u64 a = W(aux0 + j);
       fold(range_product<A>(a), c0 + 1 + j);
-      acc = gla(gl_shl<A>(acc), a);
+      acc.push(a);
     }
-    fold(gls(acc, input), c0);
+    fold(gls(acc.value(), input), c0);
   }
   const u64 f = compute_filter(F, i);
 #pragma unroll
