@@ -160,13 +160,13 @@ k_eval_ux_comparison(UxShape s, size_t n, const u64* __restrict__ wires, size_t 
   UX_ROW();
   (void)u;
   const int nc = s.n_aux;
-  u64 fa = 0, sa = 0;
+  Recomp<A> fa, sa;
   for (int c = nc - 1; c >= 0; c--) {
-    fa = gla(gl_shl<A>(fa), W(4 + c));
-    sa = gla(gl_shl<A>(sa), W(4 + nc + c));
+    fa.push(W(4 + c));
+    sa.push(W(4 + nc + c));
   }
-  O(0) = glc(gls(fa, W(0)));
-  O(1) = glc(gls(sa, W(1)));
+  O(0) = glc(gls(fa.value(), W(0)));
+  O(1) = glc(gls(sa.value(), W(1)));
   u64 msd = 0;                                     // canonical throughout
 #pragma unroll 2
   for (int c = 0; c < nc; c++) {
@@ -204,16 +204,16 @@ k_eval_ux_add_many(UxShape s, size_t n, const u64* __restrict__ wires, size_t is
   for (int j = 0; j < s.na; j++) computed = gla(computed, W(r0 + j));
   const u64 res = W(r0 + s.na + 1), car = W(r0 + s.na + 2);
   O(c0) = glc(gls(gla(gl_shl_rt(car, s.bits), res), glc(computed)));
-  u64 cres = 0, ccar = 0;
+  Recomp<A> cres, ccar;
 #pragma unroll 4
   for (int j = nl - 1; j >= 0; j--) {
     const u64 limb = W(l0 + j);
     O(c0 + 1 + (nl - 1 - j)) = glc(range_product<A>(limb));
-    if (j < s.n_aux) cres = gla(gl_shl<A>(cres), limb);
-    else ccar = gla(gl_shl<A>(ccar), limb);
+    if (j < s.n_aux) cres.push(limb);
+    else ccar.push(limb);
   }
-  O(c0 + 1 + nl) = glc(gls(cres, res));
-  O(c0 + 2 + nl) = glc(gls(ccar, car));
+  O(c0 + 1 + nl) = glc(gls(cres.value(), res));
+  O(c0 + 2 + nl) = glc(gls(ccar.value(), car));
 }
 
 template <int A>
@@ -224,14 +224,14 @@ k_eval_ux_subtraction(UxShape s, size_t n, const u64* __restrict__ wires, size_t
   const u64 x = W(5 * u), y = W(5 * u + 1), bin = W(5 * u + 2), res = W(5 * u + 3), bout = W(5 * u + 4);
   const u64 init = gls(gls(x, y), bin);            // canonical
   O(c0) = gls(res, glc(gla(gl_shl_rt(bout, s.bits), init)));
-  u64 comb = 0;
+  Recomp<A> comb;
 #pragma unroll 4
   for (int j = nl - 1; j >= 0; j--) {
     const u64 limb = W(l0 + j);
     O(c0 + 1 + (nl - 1 - j)) = glc(range_product<A>(limb));
-    comb = gla(gl_shl<A>(comb), limb);
+    comb.push(limb);
   }
-  O(c0 + 1 + nl) = glc(gls(comb, res));
+  O(c0 + 1 + nl) = glc(gls(comb.value(), res));
   O(c0 + 2 + nl) = glc(glm(bout, gls(1, bout)));
 }
 
@@ -246,16 +246,16 @@ k_eval_ux_arithmetic(UxShape s, size_t n, const u64* __restrict__ wires, size_t 
   const u64 hi_not_max = gls(glm(inv, gls(ux_max, hi)), 1);
   O(c0) = glc(glm(hi_not_max, lo));
   O(c0 + 1) = glc(gls(gla(gl_shl_rt(hi, s.bits), lo), computed));
-  u64 clo = 0, chi = 0;
+  Recomp<A> clo, chi;
 #pragma unroll 4
   for (int j = nl - 1; j >= 0; j--) {
     const u64 limb = W(l0 + j);
     O(c0 + 2 + (nl - 1 - j)) = glc(range_product<A>(limb));
-    if (j < half) clo = gla(gl_shl<A>(clo), limb);
-    else chi = gla(gl_shl<A>(chi), limb);
+    if (j < half) clo.push(limb);
+    else chi.push(limb);
   }
-  O(c0 + 2 + nl) = glc(gls(clo, lo));
-  O(c0 + 3 + nl) = glc(gls(chi, hi));
+  O(c0 + 2 + nl) = glc(gls(clo.value(), lo));
+  O(c0 + 3 + nl) = glc(gls(chi.value(), hi));
 }
 
 // ------------------------------------------------------------------------------------------
