@@ -212,6 +212,9 @@ int p2e_builder_finish(int builder);
 size_t p2e_tape_compact_layout(int tape, uint32_t* map, uint32_t* narrow_slots, uint32_t* wide_slots);
 int p2e_tape_witness_compact(int tape, size_t n, const uint64_t* const* inputs, uint32_t* narrow,
                              uint64_t* wide, uint32_t* err);
+/* Host-side decoder (pure format conversion, no device): plain out[slot][i] from the compact matrices; wide == NULL
+ * decodes the derived form (check_sum slots rebuilt from the carries). */
+int p2e_tape_compact_expand(int tape, size_t n, const uint32_t* narrow, const uint64_t* wide, uint64_t* out);
 
 /* ---- ECDSA verification circuit witness (tape) ----------------------------------------- */
 

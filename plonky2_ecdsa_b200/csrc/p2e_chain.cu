@@ -1687,6 +1687,58 @@ size_t p2e_tape_compact_layout(int tape, uint32_t* map, uint32_t* narrow_slots, 
   return t.n_slots;
 }
 
+// Host-side decoder of the compact formats (no device involved: a format conversion for hosts that want the plain
+// [slots][n] uint64 layout back, e.g. to fill plonky2's witness vector): out[slot][i] from narrow (+ wide, or, when
+// wide == NULL, the check_sum slots rebuilt from the carries -- the derived form described in include/p2e.h).
+int p2e_tape_compact_expand(int tape, size_t n, const uint32_t* narrow, const uint64_t* wide, uint64_t* out) {
+  if (bad_tape(tape)) return -1;
+  if (n && (!narrow || !out)) return set_error_msg("compact_expand: NULL buffer");
+  const Tape& t = get_tape(tape);
+  std::vector<uint32_t> map(t.n_slots);
+  uint32_t nn = 0, nw = 0;
+  p2e_tape_compact_layout(tape, map.data(), &nn, &nw);
+  const i64 off = (i64)1 << 33;
+  for (size_t s = 0; s < t.n_slots; s++) {
+    const uint32_t m = map[s];
+    uint64_t* o = out + s * n;
+    if (m >> 31) {
+      const size_t row = m & 0x7fffffffu;
+      if (wide) {
+        for (size_t i = 0; i < n; i++) o[i] = wide[row * n + i];
+      } else {
+        // check_sum_j = c_j 2^29 - c_{j-1}, c_j = b_j - 2^33 (c_{-1} = c_16 = 0); the carries sit 17 slots further on
+        // and are decoded below -- read them from the packed rows directly
+        const int j = (int)(row % 17);
+        auto carry = [&](size_t slot, size_t i) -> i64 {
+          const uint32_t mc = map[slot];
+          const size_t r = mc & 0x1fffffffu;
+          const int k = (int)(slot - (s - j + 17));                    // index of the carry inside its tuple
+          const uint64_t top = (narrow[(r - k + 16) * n + i] >> (2 * k)) & 3u;
+          return (i64)((uint64_t)narrow[r * n + i] | (top << 32)) - off;
+        };
+        for (size_t i = 0; i < n; i++) {
+          const i64 cur = j < 16 ? carry(s + 17, i) : 0;
+          const i64 prev = j > 0 ? carry(s + 16, i) : 0;
+          o[i] = gl_from_i64(cur * ((i64)1 << LB) - prev);
+        }
+      }
+    } else if (m & (1u << 30)) {
+      const size_t r = m & 0x1fffffffu;
+      // position of this carry inside its tuple: the tuple's first slot carries bit 29
+      size_t first = s;
+      while (!(map[first] & (1u << 29))) first--;
+      const int k = (int)(s - first);
+      for (size_t i = 0; i < n; i++) {
+        const uint64_t top = (narrow[(r - k + 16) * n + i] >> (2 * k)) & 3u;
+        o[i] = (uint64_t)narrow[r * n + i] | (top << 32);
+      }
+    } else {
+      for (size_t i = 0; i < n; i++) o[i] = narrow[(size_t)m * n + i];
+    }
+  }
+  return 0;
+}
+
 int p2e_tape_witness_compact(int tape, size_t n, const uint64_t* const* inputs, uint32_t* narrow, uint64_t* wide,
                              uint32_t* err) {
   if (bad_tape(tape)) return -1;

@@ -89,6 +89,7 @@ SIGNATURES = {
     "p2e_tape_witness": (_int, [_int, _sz, _vp, _vp, _vp]),
     "p2e_tape_compact_layout": (_sz, [_int, _vp, _vp, _vp]),
     "p2e_tape_witness_compact": (_int, [_int, _sz, _vp, _vp, _vp, _vp]),
+    "p2e_tape_compact_expand": (_int, [_int, _sz, _vp, _vp, _vp]),
     "p2e_builder_new": (_int, []),
     "p2e_builder_free": (_int, [_int]),
     "p2e_builder_input": (_int, [_int]),

@@ -139,3 +139,16 @@ def test_derived_compact_form_rebuilds_check_sum_slots_of_an_oracle_witness():
     got = pkg.Engine.expand_compact(m, narrow)
     assert np.array_equal(got[:, 0], flat)
     assert (flat[wide] >> np.uint64(62)).any()              # negative columns (P - |v|) are among them
+    # the C decoder of the library (p2e_tape_compact_expand: host code, no device) agrees, in both forms, for n > 1
+    n = 3
+    narrow3 = np.ascontiguousarray(np.repeat(narrow, n, axis=1))
+    narrow3[:, 1] = 0                                       # an all-zero instance next to the real ones
+    out = np.empty((slots, n), dtype=np.uint64)
+    assert lib.p2e_tape_compact_expand(0, n, narrow3.ctypes.data, None, out.ctypes.data) == 0
+    assert np.array_equal(out[:, 0], flat) and np.array_equal(out[:, 2], flat)
+    assert np.array_equal(out, pkg.Engine.expand_compact(m, narrow3))
+    wide3 = np.zeros((nw.value, n), dtype=np.uint64)
+    wide3[:, 0] = wide3[:, 2] = flat[wide]
+    assert lib.p2e_tape_compact_expand(0, n, narrow3.ctypes.data, wide3.ctypes.data, out.ctypes.data) == 0
+    assert np.array_equal(out[:, 0], flat) and np.array_equal(out, pkg.Engine.expand_compact(m, narrow3, wide3))
+    assert lib.p2e_tape_compact_expand(99, n, narrow3.ctypes.data, None, out.ctypes.data) != 0
