@@ -284,6 +284,9 @@ def test_compact_derived_form_rebuilds_check_sum_from_carries(engine):
     assert wide is None and narrow.shape == (nn, n)
     assert not e1.any() and not e2.any()                    # the device verified the identity for every row
     assert np.array_equal(engine.expand_compact(cmap, narrow), plain)
+    out = np.empty_like(plain)
+    assert engine.lib.p2e_tape_compact_expand(engine.TAPE_ECDSA, n, narrow.ctypes.data, None, out.ctypes.data) == 0
+    assert np.array_equal(out, plain)                       # the library's own host-side decoder
     # the generic tapes as well (curve_add: 3 products)
     wl = W.ecdsa_workload(5, seed=3)
     pts = [wl["pkx"], wl["pky"], np.roll(wl["pkx"], 1, axis=1), np.roll(wl["pky"], 1, axis=1)]
