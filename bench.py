@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 WORKLOAD_NAMES = {
     "ecdsa": "4096 independent verify_secp256k1_message_circuit witnesses per GPU (full tape: 82615 slots each)",
     "mulmod": "2^20 secp256k1 base-field nonnative mulmod witnesses (29-bit limbs): q, r, check_sum, carries",
+    "mulmod_n": "2^20 secp256k1 SCALAR-field nonnative mulmod witnesses (29-bit limbs): q, r, check_sum, carries",
     "eval": "MulNonnativeGate eval_unfiltered_base_batch over 2^20 Goldilocks LDE rows",
     "glv": "glv_mul witness chain (GLV decomposition + 2-scalar MSM) for 2^16 secp256k1 scalars, P = 7G",
     "evalcs": "CheckSumGate eval_unfiltered_base_batch over 2^20 Goldilocks LDE rows",
@@ -50,6 +51,7 @@ UX_WORKLOADS = {
 METRICS = {
     "ecdsa": ("ecdsa_circuit_witnesses_per_s", "witnesses/s"),
     "mulmod": ("nonnative_mulmod_witnesses_per_s", "mulmod/s"),
+    "mulmod_n": ("nonnative_scalar_field_mulmod_witnesses_per_s", "mulmod/s"),
     "eval": ("mul_nonnative_gate_rows_per_s", "rows/s"),
     "glv": ("glv_mul_witness_chains_per_s", "chains/s"),
     "evalcs": ("check_sum_gate_rows_per_s", "rows/s"),
@@ -235,28 +237,50 @@ class Bench:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
+    def d2h_probe(self, mb=512, reps=4):
+        """Plain pinned D2H ceiling of this box with all ranks copying at once (names the limiter of the e2e numbers at N > 1):
+        every rank copies `mb` MiB device -> pinned host `reps` times between barriers; returns per-rank and aggregate GB/s."""
+        torch = self.torch
+        n = mb << 20
+        src = torch.empty(n, dtype=torch.uint8, device="cuda")
+        dst = torch.empty(n, dtype=torch.uint8).pin_memory()
+        dst.copy_(src)
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            dst.copy_(src, non_blocking=True)
+        self.barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        gbs = n * reps / float(t[0]) / 1e9
+        return {"ranks": self.world, "per_rank_GBps": gbs, "aggregate_GBps": gbs * self.world, "bytes_per_rank": n * reps,
+                "how": "all ranks copy device -> pinned host concurrently; time = max over ranks"}
+
     def setup(self, wl):
         """Returns dict(step, step_e2e, units, h2d, d2h, alg_bytes, kernel, launches, errs)."""
         np, torch, pkg, W, lib, eng, sp = self.np, self.torch, self.pkg, self.W, self.lib, self.eng, self.sp
-        if wl == "mulmod":
+        if wl in ("mulmod", "mulmod_n"):
             n = 1 << 20
-            x, y = W.mulmod_workload(n, 0, seed=W.SEED + self.rank)
+            mod = 0 if wl == "mulmod" else 1
+            x, y = W.mulmod_workload(n, mod, seed=W.SEED + self.rank)
             xd, yd = self.dev(x), self.dev(y)
             od = torch.empty((pkg.MUL_OUT_ROWS, n), dtype=torch.int64, device="cuda")
             ed = torch.empty(n, dtype=torch.int32, device="cuda")
 
             def step():
-                rc = lib.p2e_mul_nonnative_witness_dev(0, n, xd.data_ptr(), yd.data_ptr(), n, od.data_ptr(), n, ed.data_ptr(), sp)
+                rc = lib.p2e_mul_nonnative_witness_dev(mod, n, xd.data_ptr(), yd.data_ptr(), n, od.data_ptr(), n, ed.data_ptr(), sp)
                 assert rc == 0, eng.last_error()
             hx, hy = self.pinned(x), self.pinned(y)
             ho = torch.empty((pkg.MUL_OUT_ROWS, n), dtype=torch.int64).pin_memory()
             he = torch.empty(n, dtype=torch.int32).pin_memory()
 
             def step_e2e():
-                rc = lib.p2e_mul_nonnative_witness(0, n, hx.data_ptr(), hy.data_ptr(), ho.data_ptr(), he.data_ptr())
+                rc = lib.p2e_mul_nonnative_witness(mod, n, hx.data_ptr(), hy.data_ptr(), ho.data_ptr(), he.data_ptr())
                 assert rc == 0, eng.last_error()
             return dict(step=step, step_e2e=step_e2e, units=n, h2d=2 * 9 * 8 * n, d2h=pkg.MUL_OUT_ROWS * 8 * n + 4 * n,
-                        alg_bytes=552 * n, kernel="k_mul_witness<ModP>", launches=1, err=ed, dtype="u32 limbs / u64 (int)",
+                        alg_bytes=552 * n, kernel="k_mul_witness<ModP>" if mod == 0 else "k_mul_witness<ModN>", launches=1, err=ed, dtype="u32 limbs / u64 (int)",
                         keep=(xd, yd, od, hx, hy, ho, he))
         if wl == "eval":
             n = 1 << LOG_ROWS
@@ -428,64 +452,109 @@ class Bench:
             return dict(step=step, step_e2e=step_e2e, units=n, e2e_units=m, h2d=3 * 9 * 8 * m, d2h=slots * 8 * m + 4 * m,
                         alg_bytes=slots * 8 * n, kernel="k_chain_expand", launches=9, err=ed,
                         dtype="u32 limbs / u64 (int)", keep=(ind, od, hin, ho, he), slots=slots)
-        n = 4096
+        # ---- ecdsa (configs[2]): 4096 signatures per step.  N > 1: strong scaling by default -- the 4096 signatures of a
+        # step are sharded [g N/G, (g+1) N/G) across the ranks (plonky2_ecdsa_b200.sharding), every rank runs its shard.
+        import ctypes
+        from plonky2_ecdsa_b200 import sharding
+        n_total = 4096
+        strong = self.args.scaling == "strong" and self.world > 1
+        if strong:
+            lo, hi = sharding.shard_range(n_total, self.rank, self.world)
+            d_all = W.ecdsa_workload(n_total, seed=W.SEED)               # every rank derives the same global batch
+            d = {k: np.ascontiguousarray(d_all[k][:, lo:hi]) for k in ("msg", "r", "s", "pkx", "pky")}
+            n = hi - lo
+        else:
+            d = W.ecdsa_workload(n_total, seed=W.SEED + self.rank)
+            n = n_total
         slots = int(lib.p2e_ecdsa_tape_slots())
-        d = W.ecdsa_workload(n, seed=W.SEED + self.rank)
+        _, nn, nw = eng.tape_compact_layout(eng.TAPE_ECDSA)
         ins = [d[k] for k in ("msg", "r", "s", "pkx", "pky")]
         ind = [self.dev(a) for a in ins]
-        od = torch.empty((slots, n), dtype=torch.int64, device="cuda")
-        ed = torch.empty(n, dtype=torch.int32, device="cuda")
-
-        # Independent batches are enqueued round-robin on S streams (async *_dev API, one output
-        # buffer + one scratch arena per stream) so the latency-bound per-signature kernels of one
-        # batch overlap the bandwidth-bound expansion of another.
-        S = max(1, int(os.environ.get("P2E_BENCH_STREAMS", "8")))
-        streams = [torch.cuda.Stream() for _ in range(S)]
-        ods = [od] + [torch.empty((slots, n), dtype=torch.int64, device="cuda") for _ in range(S - 1)]
-        eds = [ed] + [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(S - 1)]
         ptrs = [t.data_ptr() for t in ind]
+
+        # Independent batches are enqueued round-robin on S streams (async *_dev API, one output buffer + one scratch
+        # arena per stream) so the latency-bound per-signature kernels of one batch overlap the full-GPU kernels of
+        # another.  Strong scaling keeps the number of signatures in flight per GPU constant (S grows with N).
+        S = max(1, int(os.environ.get("P2E_BENCH_STREAMS", str(min(64, 8 * (n_total // max(n, 1)))))))
+        streams = [torch.cuda.Stream() for _ in range(S)]
+        nars = [torch.empty((nn, n), dtype=torch.int32, device="cuda") for _ in range(S)]
+        eds = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(S)]
+        ed = eds[0]
         state = {"k": 0}
 
+        # headline device-resident form: the derived compact witness (u32 narrow slots, CheckSum carries as low words +
+        # packed tops, check_sum columns not stored: rebuilt by the consumer from the carries, include/p2e.h)
         def step():
             j = state["k"] % S
+            state["k"] += 1
+            rc = lib.p2e_ecdsa_witness_compact_dev(n, *ptrs, n, nars[j].data_ptr(), None, n, eds[j].data_ptr(), streams[j].cuda_stream)
+            assert rc == 0, eng.last_error()
+
+        def step_single():
+            rc = lib.p2e_ecdsa_witness_compact_dev(n, *ptrs, n, nars[0].data_ptr(), None, n, ed.data_ptr(), sp)
+            assert rc == 0, eng.last_error()
+
+        # the two other device formats, measured the same way (secondary): compact with the check_sum columns, plain u64
+        S2 = min(S, 8)
+        wides = [torch.empty((nw, n), dtype=torch.int64, device="cuda") for _ in range(S2)]
+
+        def step_compact_wide():
+            j = state["k"] % S2
+            state["k"] += 1
+            rc = lib.p2e_ecdsa_witness_compact_dev(n, *ptrs, n, nars[j].data_ptr(), wides[j].data_ptr(), n, eds[j].data_ptr(), streams[j].cuda_stream)
+            assert rc == 0, eng.last_error()
+        ods = [torch.empty((slots, n), dtype=torch.int64, device="cuda") for _ in range(S2)]
+
+        def step_plain():
+            j = state["k"] % S2
             state["k"] += 1
             rc = lib.p2e_ecdsa_witness_dev(n, *ptrs, n, ods[j].data_ptr(), n, eds[j].data_ptr(), streams[j].cuda_stream)
             assert rc == 0, eng.last_error()
 
-        def step_single():
-            rc = lib.p2e_ecdsa_witness_dev(n, *ptrs, n, od.data_ptr(), n, ed.data_ptr(), sp)
-            assert rc == 0, eng.last_error()
         hin = [self.pinned(a) for a in ins]
-        ho = torch.empty((slots, n), dtype=torch.int64).pin_memory()
         he = torch.empty(n, dtype=torch.int32).pin_memory()
-
-        def step_e2e_plain():
-            rc = lib.p2e_ecdsa_witness(n, *[t.data_ptr() for t in hin], ho.data_ptr(), he.data_ptr())
-            assert rc == 0, eng.last_error()
-        # headline e2e goes through the compact host format (u32 narrow slots + u64 wide slots): same
-        # values, 28 % fewer PCIe bytes; the plain u64 path is reported next to it
-        import ctypes
-        _, nn, nw = eng.tape_compact_layout(eng.TAPE_ECDSA)
         hn = torch.empty((nn, n), dtype=torch.int32).pin_memory()
-        hw = torch.empty((nw, n), dtype=torch.int64).pin_memory()
         in_arr = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in hin])
         in_ptr = ctypes.cast(in_arr, ctypes.c_void_p)
 
-        def step_e2e_compact():
-            rc = lib.p2e_tape_witness_compact(eng.TAPE_ECDSA, n, in_ptr, hn.data_ptr(), hw.data_ptr(), he.data_ptr())
-            assert rc == 0, eng.last_error()
-
-        # headline: the derived compact form (wide == NULL) -- the check_sum slots are not shipped, the host rebuilds
-        # them from the CheckSum carries with two integer operations per slot (include/p2e.h); the device verifies the
-        # identity per row.  The two other host formats are timed next to it.
+        # e2e headline: host buffers in, derived compact witness out, through the host-pointer C-ABI call (every rank ships
+        # its shard to host memory over its own PCIe link: in the single-process host these are regions of one buffer)
         def step_e2e():
             rc = lib.p2e_tape_witness_compact(eng.TAPE_ECDSA, n, in_ptr, hn.data_ptr(), None, he.data_ptr())
             assert rc == 0, eng.last_error()
-        return dict(step=step, step_e2e=step_e2e, step_e2e_plain=step_e2e_plain, step_e2e_compact=step_e2e_compact, units=n,
+        extra = {}
+        if not strong:
+            ho = torch.empty((slots, n), dtype=torch.int64).pin_memory()
+            hw = torch.empty((nw, n), dtype=torch.int64).pin_memory()
+
+            def step_e2e_plain():
+                rc = lib.p2e_ecdsa_witness(n, *[t.data_ptr() for t in hin], ho.data_ptr(), he.data_ptr())
+                assert rc == 0, eng.last_error()
+
+            def step_e2e_compact():
+                rc = lib.p2e_tape_witness_compact(eng.TAPE_ECDSA, n, in_ptr, hn.data_ptr(), hw.data_ptr(), he.data_ptr())
+                assert rc == 0, eng.last_error()
+            extra = dict(step_e2e_plain=step_e2e_plain, step_e2e_compact=step_e2e_compact, e2e_keep2=(ho, hw))
+        gather = None
+        if strong:
+            # the final result gather of north_star: the compact shards to rank 0's HBM over NCCL / NVLink
+            sizes = [sharding.shard_range(n_total, r, self.world) for r in range(self.world)]
+            width = max(b - a for a, b in sizes)
+            full = [torch.empty((nn, width), dtype=torch.int32, device="cuda") for _ in range(self.world)] if self.rank == 0 else None
+            mine = torch.empty((nn, width), dtype=torch.int32, device="cuda")
+
+            def gather():
+                mine[:, :n].copy_(nars[0], non_blocking=True)
+                self.dist.gather(mine, full, dst=0)
+            extra["gather_keep"] = (full, mine)
+            extra["gather_bytes"] = nn * 4 * (n_total - (sizes[0][1] - sizes[0][0]))
+        return dict(step=step, step_e2e=step_e2e, units=n, units_total=n_total if strong else n * self.world,
                     h2d=5 * 9 * 8 * n, d2h=nn * 4 * n + 4 * n, d2h_compact=nn * 4 * n + nw * 8 * n + 4 * n,
-                    d2h_plain=slots * 8 * n + 4 * n, e2e_keep=(hn, hw, in_arr),
-                    alg_bytes=slots * 8 * n, kernel="k_chain_expand", launches=9, err=ed, dtype="u32 limbs / u64 (int)",
-                    keep=(ind, ods, eds, hin, ho, he), slots=slots, streams=streams, step_single=step_single)
+                    d2h_plain=slots * 8 * n + 4 * n, e2e_keep=(hn, in_arr),
+                    alg_bytes=(nn * 4) * n, alg_bytes_plain=slots * 8 * n, kernel="k_chain_expand", launches=9, err=ed,
+                    dtype="u32 words / 29-bit limbs (int)", keep=(ind, nars, eds, wides, ods, hin, he), slots=slots, streams=streams,
+                    step_single=step_single, step_compact_wide=step_compact_wide, step_plain=step_plain, gather=gather,
+                    narrow_rows=nn, wide_rows=nw, strong=strong, **extra)
 
     def measure(self, wl, steps, warmup, e2e_steps, sample_clocks=False):
         torch = self.torch
@@ -544,11 +613,37 @@ class Bench:
             sampler.stop()
             sampler.join(timeout=2.0)
         kernel_ms = None
+        formats = {}
+        gather_res = None
         if wl == "ecdsa":
             self.eng.set_profiling(True)
             s["step_single"]()
             kernel_ms = self.eng.last_kernel_times()
             self.eng.set_profiling(False)
+            # the other two device-resident formats, same pipelining
+            for nm, key, by in (("compact_with_check_sum", "step_compact_wide", (s["narrow_rows"] * 4 + s["wide_rows"] * 8)),
+                                ("plain_u64", "step_plain", s["slots"] * 8)):
+                fn = s[key]
+                for _ in range(8):
+                    fn()
+                self.barrier()
+                k2 = max(8, min(steps, 24))
+                t2 = timed(fn, k2) / k2
+                formats[nm] = {"ms_per_step": t2, "bytes_per_witness": by}
+            if s["gather"] is not None:
+                # strong scaling: the compact shards gathered into rank 0's HBM over NCCL (one gather per step, on the
+                # main stream after the shard's kernels)
+                def step_gather():
+                    s["step_single"]()
+                    s["gather"]()
+                step_gather()
+                self.barrier()
+                kg = max(4, min(steps, 10))
+                saved, streams[:] = list(streams), []
+                tg = timed(step_gather, kg) / kg
+                tg0 = timed(s["gather"], kg) / kg
+                streams[:] = saved
+                gather_res = {"ms_per_step_compute_plus_gather": tg, "ms_gather_alone": tg0, "bytes_into_rank0": s["gather_bytes"]}
         step_e2e()
         self.barrier()
         t0 = time.perf_counter()
@@ -574,33 +669,54 @@ class Bench:
             self.barrier()
             e2e_compact_ms = (time.perf_counter() - t0) * 1e3 / 2
         errs = int((s["err"] != 0).sum().item()) if s["err"] is not None else 0
-        t = torch.tensor([ms, e2e_ms, float(errs)], dtype=torch.float64, device="cuda")
+        fm = [formats[k]["ms_per_step"] for k in sorted(formats)]
+        gm = [gather_res["ms_per_step_compute_plus_gather"], gather_res["ms_gather_alone"]] if gather_res else []
+        t = torch.tensor([ms, e2e_ms, float(errs)] + fm + gm, dtype=torch.float64, device="cuda")
         if self.dist is not None:
             mx = t.clone()
             self.dist.all_reduce(mx, op=self.dist.ReduceOp.MAX)       # time = max over ranks
             sm = t.clone()
             self.dist.all_reduce(sm, op=self.dist.ReduceOp.SUM)       # final gather of the error counts
             ms, e2e_ms, errs = float(mx[0]), float(mx[1]), int(sm[2])
+            for i, k in enumerate(sorted(formats)):
+                formats[k]["ms_per_step"] = float(mx[3 + i])
+            if gather_res:
+                gather_res["ms_per_step_compute_plus_gather"] = float(mx[3 + len(fm)])
+                gather_res["ms_gather_alone"] = float(mx[4 + len(fm)])
         ms_per_step = ms / steps
-        value = s["units"] * self.world / (ms_per_step * 1e-3)
-        e2e_value = s.get("e2e_units", s["units"]) * self.world / (e2e_ms / e2e_steps * 1e-3)
+        units_total = s.get("units_total", s["units"] * self.world)          # units all ranks process per step
+        value = units_total / (ms_per_step * 1e-3)
+        e2e_units = s.get("e2e_units", s["units"]) * self.world if "units_total" not in s else units_total
+        e2e_value = e2e_units / (e2e_ms / e2e_steps * 1e-3)
         res = {
             "metric": METRICS[wl][0], "value": value, "unit": METRICS[wl][1], "ms_per_step": ms_per_step,
-            "dtype": s["dtype"], "units_per_step_per_gpu": s["units"], "error_rows": errs,
+            "dtype": s["dtype"], "units_per_step_per_gpu": s["units"], "units_per_step": units_total, "error_rows": errs,
             "e2e": {"value": e2e_value, "unit": METRICS[wl][1], "h2d_bytes_per_step": s["h2d"], "d2h_bytes_per_step": s["d2h"],
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
             "gpu_launches": s["launches"] * steps,
         }
-        if e2e_plain_ms is not None:
+        if wl == "ecdsa":
             res["e2e"]["format"] = ("derived compact (p2e_tape_witness_compact, wide == NULL: u32 narrow slots, 34-bit carries as u32 + packed "
-                                    "2-bit tops; check_sum slots rebuilt on the host from the carries, identity verified on the device)")
+                                    "2-bit tops; check_sum slots rebuilt on the host from the carries; written by the chain kernels directly)")
+            res["e2e"]["bytes_are"] = "per rank (every rank ships its shard over its own PCIe link)"
             if e2e_compact_ms is not None:
-                res["e2e_compact"] = {"value": s["units"] * self.world / (e2e_compact_ms * 1e-3), "unit": METRICS[wl][1],
+                res["e2e_compact"] = {"value": units_total / (e2e_compact_ms * 1e-3), "unit": METRICS[wl][1],
                                       "d2h_bytes_per_step": s["d2h_compact"], "ms_per_step": e2e_compact_ms,
                                       "format": "compact (u32 narrow slots, u64 check_sum slots shipped, packed carries)"}
-            res["e2e_u64"] = {"value": s["units"] * self.world / (e2e_plain_ms * 1e-3), "unit": METRICS[wl][1],
-                              "d2h_bytes_per_step": s["d2h_plain"], "ms_per_step": e2e_plain_ms,
-                              "format": "plain (p2e_ecdsa_witness: u64 per slot)"}
+            if e2e_plain_ms is not None:
+                res["e2e_u64"] = {"value": units_total / (e2e_plain_ms * 1e-3), "unit": METRICS[wl][1],
+                                  "d2h_bytes_per_step": s["d2h_plain"], "ms_per_step": e2e_plain_ms,
+                                  "format": "plain (p2e_ecdsa_witness: u64 per slot)"}
+            res["device_format"] = "derived compact (p2e_ecdsa_witness_compact_dev, wide == NULL): %d B / witness" % (s["narrow_rows"] * 4)
+            for k in formats:
+                formats[k]["value"] = units_total / (formats[k]["ms_per_step"] * 1e-3)
+            res["device_formats"] = formats
+            if gather_res:
+                gather_res["value_with_gather"] = units_total / (gather_res["ms_per_step_compute_plus_gather"] * 1e-3)
+                gather_res["gather_GBps_into_rank0"] = gather_res["bytes_into_rank0"] / (gather_res["ms_gather_alone"] * 1e-3) / 1e9
+                gather_res["note"] = ("one batch at a time (no pipelining across steps): shard kernels, then dist.gather of the compact shard "
+                                      "into rank 0's HBM; rank 0's NVLink ingress bounds a gathered witness stream at 900 GB/s / bytes per witness")
+                res["gather"] = gather_res
         if streams:
             res["streams"] = len(streams)
             res["single_stream_ms_per_step"] = latency_ms
@@ -608,21 +724,17 @@ class Bench:
             names = self.eng.CHAIN_KERNELS
             res["kernel_ms"] = {nm: round(v, 4) for nm, v in zip(names, kernel_ms)}
             k_expand = kernel_ms[names.index("k_chain_expand")]
-            k_replay = kernel_ms[names.index("k_chain_replay")]
             achieved = s["alg_bytes"] / (k_expand * 1e-3) / 1e9
-            res["roofline"] = {"bound": "hbm", "kernel": "k_chain_expand", "achieved": achieved, "peak": self.peak_gbs,
-                               "unit": "GB/s", "frac": achieved / self.peak_gbs, "peak_kind": self.peak_kind,
-                               "traffic": self.traffic.get("k_chain_expand"),
-                               "algorithmic_bytes_per_launch": s["alg_bytes"], "kernel_ms": k_expand,
-                               "share_of_step": k_expand / sum(kernel_ms)}
-            # INT32 roof of the replay kernel: algorithmic work = 3263 field mults per signature (batched-inversion
-            # algorithm) x 81 limb products
-            res["_replay"] = (k_replay, sum(kernel_ms))
+            res["roofline_hbm_expand"] = {"bound": "hbm", "kernel": "k_chain_expand<compact>", "achieved": achieved, "peak": self.peak_gbs,
+                                          "unit": "GB/s", "frac": achieved / self.peak_gbs, "peak_kind": self.peak_kind,
+                                          "algorithmic_bytes_per_launch": s["alg_bytes"], "kernel_ms": k_expand,
+                                          "share_of_step": k_expand / sum(kernel_ms)}
+            res["_kernel_ms"] = kernel_ms
         else:
             achieved = s["alg_bytes"] / (ms_per_step * 1e-3) / 1e9
             res["roofline"] = {"bound": "hbm", "kernel": s["kernel"], "achieved": achieved, "peak": self.peak_gbs, "unit": "GB/s",
                                "frac": achieved / self.peak_gbs, "peak_kind": self.peak_kind,
-                               "traffic": self.traffic.get(s["kernel"]),
+                               "traffic": None,
                                "algorithmic_bytes_per_launch": s["alg_bytes"]}
         if sampler is not None:
             res["clocks"] = sampler.summary()
@@ -631,17 +743,32 @@ class Bench:
         return res
 
 
+# Algorithmic integer work of one verify_secp256k1_message_circuit witness (batched-inversion
+# algorithm): explicit mul_nonnative 1087 x 2 (x*y and q*m) + ~311 curve ops x 14 (Jacobian replay) + 3 x 624
+# (Montgomery's trick over the Z's and denominators) + 503 (one Fermat ladder) = 8903 modmul-equivalents of 81 limb
+# products (one IMAD.WIDE each): 0.721 M IMAD.WIDE per signature.  The roofline divides THIS figure, not executed
+# instructions (the kernels execute fewer: 64 products per multiplication on 8 x 32-bit words).
+ALG_MODMUL_EQ_PER_WITNESS = 2174 + 311 * 14 + 3 * 624 + 503
+ALG_IMAD_WIDE_PER_WITNESS = ALG_MODMUL_EQ_PER_WITNESS * 81
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("P2E_BENCH_WORKLOAD", "ecdsa"), choices=list(WORKLOAD_NAMES))
+    ap.add_argument("--scaling", default=os.environ.get("P2E_BENCH_SCALING", "auto"), choices=["auto", "strong", "weak"],
+                    help="N > 1, ecdsa workload: strong = the 4096 signatures of a step are sharded across the ranks (BASELINE.json "
+                         "configs[2]; default), weak = 4096 per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.scaling == "auto":
+        args.scaling = "strong" if (world > 1 and args.workload == "ecdsa") else "weak"
     if args.impl == "reference":
         return run_reference(args)
 
@@ -652,58 +779,77 @@ def main():
     os.dup2(2, 1)
     b = Bench(args)
     wl = args.workload
+    strong = args.scaling == "strong" and b.world > 1 and wl == "ecdsa"
     main_res = b.measure(wl, args.steps, args.warmup, e2e_steps=max(2, min(args.steps, 5)), sample_clocks=True)
     secondary = {}
     if not args.no_secondary:
-        for w2 in ("mulmod", "eval", "evalcs", "evalfc", "evalcsfc", "evalrc", "evalrcfc", "evalcmp", "evaladd", "lde", "genstream", "glv", "ecdsa"):
-            if w2 != wl:
+        for w2 in ("mulmod", "mulmod_n", "eval", "evalcs", "evalfc", "evalcsfc", "evalrc", "evalrcfc", "evalcmp", "evaladd", "lde", "genstream", "glv", "ecdsa"):
+            if w2 != wl and w2 in WORKLOAD_NAMES:
                 try:
                     r2 = b.measure(w2, steps=min(args.steps, 20) if w2 != "glv" else 3, warmup=3, e2e_steps=2)
                 except Exception as e:      # noqa: BLE001  (e.g. not enough free HBM for the 32 GB glv witness)
                     secondary[w2] = {"error": str(e)[:200]}
                     continue
-                r2.pop("_replay", None)
+                r2.pop("_kernel_ms", None)
                 secondary[w2] = r2
+    d2h_probe = None
+    if wl == "ecdsa" and b.world > 1:
+        d2h_probe = b.d2h_probe()
     if b.rank == 0:
+        upg = main_res["units_per_step_per_gpu"]
         line = {
             "metric": main_res["metric"], "value": main_res["value"], "unit": main_res["unit"], "n_gpus": b.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": main_res["dtype"], "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAMES[wl].replace("2^20 Goldilocks", "2^%d Goldilocks" % LOG_ROWS), "units_per_step_per_gpu": main_res["units_per_step_per_gpu"],
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": main_res["dtype"], "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAMES[wl].replace("2^20 Goldilocks", "2^%d Goldilocks" % LOG_ROWS).replace(
+                           "per GPU", "per step, sharded %d per GPU (rank g owns [g N/G, (g+1) N/G))" % upg if strong else "per GPU"),
+                       "units_per_step": main_res["units_per_step"], "units_per_step_per_gpu": upg,
                        "seed": hex(b.W.SEED), "error_rows": main_res["error_rows"],
                        "l2": "per-step inputs+outputs exceed the 126 MB L2 (no flush needed)",
                        "streams": main_res.get("streams", 1),
                        "pipelining": "steps are independent batches enqueued round-robin on `streams` CUDA streams through the async *_dev "
                                      "entry point; ms_per_step = timed region / steps; single_stream_ms_per_step = one batch at a time",
-                       "single_stream_ms_per_step": main_res.get("single_stream_ms_per_step")},
+                       "single_stream_ms_per_step": main_res.get("single_stream_ms_per_step"),
+                       "device_format": main_res.get("device_format")},
             "e2e": main_res["e2e"], "e2e_compact": main_res.get("e2e_compact"), "e2e_u64": main_res.get("e2e_u64"), "gpu_launches": main_res["gpu_launches"],
             "clocks": main_res.get("clocks"),
-            "roofline": main_res["roofline"],
         }
-        if "kernel_ms" in main_res:
-            line["kernel_ms"] = main_res["kernel_ms"]
+        for k in ("kernel_ms", "device_formats", "gather", "roofline_hbm_expand"):
+            if k in main_res:
+                line[k] = main_res[k]
+        if d2h_probe is not None:
+            line["d2h_probe"] = d2h_probe
         try:
             imad = b.eng.bench_imad(False)
             imadw = b.eng.bench_imad(True)
             line["int32_peak"] = {"imad_gops": imad, "imad_wide_gops": imadw, "how": "p2e_bench_imad: 8 independent chains/thread, best of 5"}
-            if "_replay" in main_res:
-                k_replay, _ = main_res["_replay"]
-                work = 3263 * 81 * main_res["units_per_step_per_gpu"]      # limb products per launch
-                line["roofline_int32"] = {"bound": "int32", "kernel": "k_chain_replay", "achieved": work / (k_replay * 1e-3) / 1e9,
-                                          "peak": imadw, "unit": "G IMAD.WIDE/s", "frac": work / (k_replay * 1e-3) / 1e9 / imadw,
-                                          "algorithmic_ops_per_launch": work, "kernel_ms": k_replay}
-                # whole job, throughput mode: algorithmic limb products of the batched-inversion algorithm per signature
-                # (replay 3263 + inversion tree 1251 + affine 1866 + v_inv 622 + mul witnesses 2174 +
-                # inverse quotients 312 + scalar-field prep ~300 field multiplications, 81 limb products each) / ms_per_step
-                job = 9788 * 81 * main_res["units_per_step_per_gpu"]
-                line["roofline_int32_job"] = {"bound": "int32", "kernel": "all chain kernels (pipelined step)", "achieved": job / (main_res["ms_per_step"] * 1e-3) / 1e9,
-                                              "peak": imadw, "unit": "G IMAD.WIDE/s", "frac": job / (main_res["ms_per_step"] * 1e-3) / 1e9 / imadw,
-                                              "algorithmic_ops_per_step": job}
-            if "mulmod" in secondary or wl == "mulmod":
-                v = secondary["mulmod"]["value"] if "mulmod" in secondary else main_res["value"]
-                line.setdefault("secondary_notes", {})["mulmod_int32_frac"] = 162 * v / b.world / 1e9 / imadw
+            if wl == "ecdsa":
+                # THE roofline of the headline: whole job (all chain kernels, pipelined step) against the measured IMAD.WIDE
+                # peak, on the algorithmic limb products of SURVEY.md section 8d (0.721 M IMAD.WIDE per signature)
+                job = ALG_IMAD_WIDE_PER_WITNESS * upg
+                ach = job / (main_res["ms_per_step"] * 1e-3) / 1e9
+                km = main_res.get("_kernel_ms") or []
+                names = b.eng.CHAIN_KERNELS
+                line["roofline"] = {"bound": "int32", "kernel": "whole job: k_prep + k_chain_replay + k_chain_invert_* + k_chain_affine + k_chain_expand "
+                                    "(pipelined step)", "achieved": ach, "peak": imadw, "unit": "G IMAD.WIDE/s", "frac": ach / imadw,
+                                    "peak_kind": "measured in this run (p2e_bench_imad; not in MEASURED_PEAKS.json)", "traffic": None,
+                                    "algorithmic_ops_per_step_per_gpu": job, "algorithmic_imad_wide_per_witness": ALG_IMAD_WIDE_PER_WITNESS,
+                                    "single_batch_kernel_ms": {nm: round(v, 4) for nm, v in zip(names, km)},
+                                    "single_batch_frac": (job / (sum(km) * 1e-3) / 1e9 / imadw) if km else None}
+                if km:
+                    k_replay = km[names.index("k_chain_replay")]
+                    work = 3263 * 81 * upg
+                    line["roofline_int32_replay"] = {"bound": "int32", "kernel": "k_chain_replay (main launch, one batch alone)", "achieved": work / (k_replay * 1e-3) / 1e9,
+                                                     "peak": imadw, "unit": "G IMAD.WIDE/s", "frac": work / (k_replay * 1e-3) / 1e9 / imadw,
+                                                     "algorithmic_ops_per_launch": work, "kernel_ms": k_replay}
+            else:
+                line["roofline"] = main_res["roofline"]
+            for key, nm in (("mulmod", "mulmod_int32_frac"), ("mulmod_n", "mulmod_n_int32_frac")):
+                if key in secondary and "value" in secondary[key]:
+                    line.setdefault("secondary_notes", {})[nm] = 162 * secondary[key]["value"] / b.world / 1e9 / imadw
         except Exception as e:          # noqa: BLE001
             line["int32_peak"] = {"error": str(e)}
+            line.setdefault("roofline", main_res.get("roofline"))
         if secondary:
             line["secondary"] = secondary
         if not args.no_cpu_baseline and b.world == 1:
@@ -712,6 +858,8 @@ def main():
                 cb = cpu_baseline.run(wl, steps=1, warmup=0, budget_s=15.0)
                 line["cpu_baseline"] = {"value": cb["value"], "unit": cb["unit"], "cores": cb["cores"], "kind": cb["kind"],
                                         "sample": cb["sample"]}
+                if "batched" in cb:
+                    line["cpu_baseline_batched"] = cb["batched"]
             except Exception as e:      # noqa: BLE001
                 line["cpu_baseline"] = {"value": None, "error": str(e)}
         sys.stdout.flush()

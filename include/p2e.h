@@ -46,12 +46,41 @@ extern "C" {
 #define P2E_MUL_OUT_CARRY 35     /* 16 rows: CheckSumGate wires 17..32 (b_i + 2^33)   */
 #define P2E_MUL_OUT_ROWS 51
 
-/* ---- lifetime ------------------------------------------------------------------------- */
-int p2e_init(int device);      /* bind this process to CUDA device `device`, create the stream */
-void p2e_shutdown(void);
+/* ---- lifetime, devices, threads --------------------------------------------------------
+ * The reference is ONE Rust process; a drop-in host must be able to reach every GPU of the box from it.
+ *   p2e_init(device)         creates the context of CUDA device `device` (stream, scratch, device copies of the
+ *                            tapes / tables) and makes it the CALLING THREAD's current device.  May be called once
+ *                            per device; calling it again only re-selects the device.
+ *   p2e_init_devices(n)      = p2e_init(0 .. n-1); the calling thread keeps (or gets) device 0.
+ *   p2e_set_device(device)   selects the calling thread's current device (like cudaSetDevice).  Every other entry
+ *                            point works on the current device of the thread that calls it; a thread that never
+ *                            chose one uses the first device that was initialised.
+ * Threading contract:
+ *   - `*_dev` entry points are re-entrant per (device, stream): different host threads may enqueue on different
+ *     streams / devices concurrently.  They never block on the GPU.
+ *   - Host-pointer entry points (no `_dev`) share the context's stream and scratch buffers: the library
+ *     serialises them PER DEVICE with a mutex, so concurrent callers (plonky2 evaluates gates from rayon
+ *     workers) are safe but run one after another on one device; use one thread per device, or the `_dev`
+ *     forms with your own streams, for concurrency.
+ *   - p2e_last_error() is per thread. */
+int p2e_init(int device);
+int p2e_init_devices(int n_devices);
+int p2e_set_device(int device);
+int p2e_current_device(void);           /* -1: none */
+int p2e_shutdown_device(int device);    /* releases one device's context */
+void p2e_shutdown(void);                /* releases every context */
 const char* p2e_last_error(void);
 int p2e_device_count(void);
-int p2e_synchronize(void);
+int p2e_synchronize(void);              /* the current device's library stream */
+/* Tunables (process-wide; defaults in parentheses): "chain_chunk" (65536) signatures per scratch chunk of the chain
+ * kernels; "host_chunks" (4) D2H / compute pipeline depth of p2e_tape_witness_compact; "genstream_fused" (1) and
+ * "genstream_graph" (1) executor forms of p2e_genstream_run*; "ntt_log_tile" (12).  Nothing is read from the
+ * environment. */
+int p2e_set_option(const char* name, long value);
+long p2e_get_option(const char* name);
+/* The chain entry points keep one scratch arena per caller stream (up to 64 per device; an idle arena is recycled
+ * when a 65th stream shows up).  A host that is done with a stream can return its arena right away. */
+int p2e_stream_release(void* stream);
 
 /* device / pinned-host memory for callers that are not torch (Rust/C hosts) */
 int p2e_malloc(void** dptr, size_t bytes);
@@ -207,9 +236,13 @@ int p2e_builder_finish(int builder);
  *   check_sum_j = (b_j - 2^33) * 2^29 - (b_{j-1} - 2^33)   (j = 0: no second term; j = 16: -(b_15 - 2^33))
  * as a field element -- the CheckSumGate's own constraints (gates/mul_nonnative.rs:411-427) set to zero --
  * so the host rebuilds it with two integer operations per slot while it fills the wires.  The device
- * verifies the identity for every row before dropping the column and sets P2E_ERR_CARRY_RANGE in err[i]
- * otherwise (only rows whose generator already failed can be of another form). */
+ * kernels write the compact rows directly (no plain witness is materialised) from the same un-carried columns
+ * the carries come from; a row that is not of this form (only rows whose generator already failed) gets
+ * P2E_ERR_CARRY_RANGE in err[i]. */
 size_t p2e_tape_compact_layout(int tape, uint32_t* map, uint32_t* narrow_slots, uint32_t* wide_slots);
+/* device-resident compact witness: narrow [narrow_slots][stride] uint32, wide [wide_slots][stride] uint64 or NULL */
+int p2e_tape_witness_compact_dev(int tape, size_t n, const uint64_t* const* inputs, size_t in_stride,
+                                 uint32_t* narrow, uint64_t* wide, size_t out_stride, uint32_t* err, void* stream);
 int p2e_tape_witness_compact(int tape, size_t n, const uint64_t* const* inputs, uint32_t* narrow,
                              uint64_t* wide, uint32_t* err);
 /* Host-side decoder (pure format conversion, no device): plain out[slot][i] from the compact matrices; wide == NULL
@@ -234,6 +267,10 @@ int p2e_ecdsa_witness_dev(size_t n, const uint64_t* msg, const uint64_t* r, cons
                           uint64_t* out, size_t out_stride, uint32_t* err, void* stream);
 int p2e_ecdsa_witness(size_t n, const uint64_t* msg, const uint64_t* r, const uint64_t* s,
                       const uint64_t* pkx, const uint64_t* pky, uint64_t* out, uint32_t* err);
+/* the same witness in the compact device format (p2e_tape_witness_compact_dev on the ECDSA tape; wide may be NULL) */
+int p2e_ecdsa_witness_compact_dev(size_t n, const uint64_t* msg, const uint64_t* r, const uint64_t* s,
+                                  const uint64_t* pkx, const uint64_t* pky, size_t in_stride, uint32_t* narrow,
+                                  uint64_t* wide, size_t out_stride, uint32_t* err, void* stream);
 
 /* glv_mul(p, k) sub-circuit alone (gadgets/glv.rs:87-104): GLV decomposition + MSM chain. */
 size_t p2e_glv_mul_tape_slots(void);
@@ -387,6 +424,10 @@ int p2e_last_kernel_times(float* ms, int cap);
 /* Dependent-free IMAD / IMAD.WIDE throughput microbenchmark on the current device; returns
  * giga-ops per second (one op = one 32-bit lane multiply-add), or a negative error. */
 double p2e_bench_imad(int wide, int iters);
+/* Test hook: runs one operation of the saturated 8 x 32-bit field (csrc/p2e_f8.cuh, PTX carry-chain bodies) on the
+ * device for n operand pairs; a, b, out: [n][9] uint32, 8 words used.  op: 0 mul, 1 sqr, 2 add, 3 sub, 4..7 times
+ * 2 / 3 / 4 / 8, 8 canonical form, 11 inverse.  tests/test_gpu_f8.py compares with the portable bodies. */
+int p2e_debug_f8(int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out);
 
 #ifdef __cplusplus
 }

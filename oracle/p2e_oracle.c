@@ -175,6 +175,32 @@ void orc_mul_nonnative(int mod, size_t n, size_t i0, size_t i1, const u64* x, co
 /* ---- A7: Fermat ladder (square-and-multiply over order-2), BigUint mul + divrem per step */
 static void bn_mulmod(const bn* a, const bn* b, const bn* m, bn* r) { bn p, q; bn_mul(a, b, &p); bn_divrem(&p, m, &q, r); }
 
+/* "best-CPU" variant of the inverse: extended Euclid on the same BigUint primitives instead of
+ * the reference's Fermat ladder.  The inverse is unique, so every witness bit is unchanged; only the CPU time is
+ * (about 10x fewer word operations per inverse).  orc_set_inverse_mode(1) selects it for the timed baseline. */
+static int g_inverse_mode = 0;
+void orc_set_inverse_mode(int mode) { g_inverse_mode = mode; }
+static void bn_add(const bn* a, const bn* b, bn* r);
+static void bn_sub(const bn* a, const bn* b, bn* r);
+static void bn_inv_euclid(const bn* x, const bn* m, bn* inv) {
+  /* r0 = m, r1 = x; cofactors alternate in sign: |t_{i+1}| = |t_{i-1}| + q |t_i| */
+  bn r0 = *m, r1 = *x, t0, t1, q, r, p, s;
+  t0.n = 0;
+  t1.n = 1; t1.w[0] = 1;
+  int neg = 0;                                /* sign of t1 */
+  while (r1.n != 0) {
+    bn_divrem(&r0, &r1, &q, &r);
+    bn_mul(&q, &t1, &p);
+    bn_add(&t0, &p, &s);
+    t0 = t1; t1 = s;
+    r0 = r1; r1 = r;
+    neg = !neg;
+  }
+  /* gcd = r0 = 1; x * (+-t0) = 1 (mod m), sign of t0 is !neg */
+  if (!neg) { bn_sub(m, &t0, inv); } else { *inv = t0; }
+  bn_trim(inv);
+}
+
 static u32 inv_nonnative_one(int mod, const u64* xw, u64* out /*18: div inv*/) {
   bn m; bn_modulus(mod, &m);
   /* get_biguint_target (Horner) for in-range limbs, then from_noncanonical / canonical */
@@ -192,9 +218,13 @@ static u32 inv_nonnative_one(int mod, const u64* xw, u64* out /*18: div inv*/) {
   bn e = m; e.w[0] -= 2;                    /* order - 2 (no borrow for either modulus) */
   bn acc; acc.n = 1; acc.w[0] = 1;
   bn base = x, t;
-  for (int bit = 0; bit < 256; bit++) {     /* exp_biguint: LSB-first square and multiply */
-    if ((e.w[bit >> 5] >> (bit & 31)) & 1) { bn_mulmod(&acc, &base, &m, &t); acc = t; }
-    bn_mulmod(&base, &base, &m, &t); base = t;
+  if (g_inverse_mode == 1) {
+    bn_inv_euclid(&x, &m, &acc);
+  } else {
+    for (int bit = 0; bit < 256; bit++) {     /* exp_biguint: LSB-first square and multiply */
+      if ((e.w[bit >> 5] >> (bit & 31)) & 1) { bn_mulmod(&acc, &base, &m, &t); acc = t; }
+      bn_mulmod(&base, &base, &m, &t); base = t;
+    }
   }
   bn prod, div, rem;
   bn_mul(&x, &acc, &prod);

@@ -51,7 +51,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}")
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    # shared cudart: the artefact carries only the runtime symbols it imports (and shares the runtime instance of a
+    # torch host process); the rpath lets a plain C host (examples/host_demo.c) find it without torch
+    cuda_lib = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "lib64")
+    cmd = [nvcc, "-shared", "-cudart", "shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                                                    "-Xlinker", "-rpath=" + cuda_lib]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

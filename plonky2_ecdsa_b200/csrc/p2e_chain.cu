@@ -1,33 +1,36 @@
 // p2e_chain.cu -- witness generation for whole gadget chains (verify_secp256k1_message_circuit,
-// glv_mul) from the host-built tape (p2e_tape.h).
+// glv_mul, ...) from the host-built tape (p2e_tape.h).
 //
 // The reference runs 312 Fermat ladders per signature, one per curve_add / curve_double
 // (gadgets/curve.rs:160-223 -> gadgets/nonnative.rs:857-872).  Every one of those inverses is
 // unique mod p, so it can be obtained differently without changing a single witness bit:
 //   K0 k_prep          per signature: interpreter over the non-curve generators (prep ops)
-//   K1 k_chain_replay  per signature: replays all curve ops in Jacobian coordinates (no inversion)
-//   K2 k_chain_invert  per signature: ONE field inversion for all Z's (Montgomery's trick)
-//   K3 k_chain_affine  per (signature, point): affine x, y and Z^3
+//   K1 k_chain_replay  per (signature, chain), two lanes: replays the curve ops in Jacobian coordinates
+//   K2 k_chain_invert_up / _mid / _down: ONE field inversion per signature for all Z's (Montgomery's trick, tree)
+//   K3 k_chain_affine  per (signature, point): affine x, y (29-bit limbs) and Z^3
 //   K4 k_chain_expand  per (signature, curve op): v_inv = Z1^3 Z2^3 / Z3 (add) or Z1^4 / Z3 (double),
-//                      then every generator of that curve op with the cores of p2e_field.cuh
+//                      then every generator of that curve op (fast cores of p2e_f8.cuh / p2e_field.cuh)
 //   K5 k_chain_checks  per signature: the gadget's connect_* constraints -> ERR_CONNECT
-// Signatures are the fastest-varying index everywhere (coalesced wire-major accesses).
+// K1-K3 and the v_inv products of K4 run on 8 saturated 32-bit words (p2e_f8.cuh); 29-bit limbs appear only where
+// the witness has them.  K0 / K4 write either the plain witness (u64 per slot) or the compact host format directly
+// (u32 narrow slots, CheckSum carries as low words + packed tops, check_sum columns optional): 261 instead of 661 KB
+// of HBM writes per signature.  Signatures are the fastest-varying index everywhere (coalesced wire-major accesses).
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <vector>
 
 #include "../../include/p2e.h"
 #include "p2e_common.h"
+#include "p2e_f8.cuh"
 #include "p2e_field.cuh"
 #include "p2e_tape.h"
-
-#ifndef P2E_DEFAULT_REPLAY
-#define P2E_DEFAULT_REPLAY 2
-#endif
 
 namespace p2e {
 
 constexpr int32_t PID_INPUT_BASE = 1 << 19;
+constexpr int INV_GROUPS = 16;        // K2 tree: groups per signature (measured: 8 -> 0.29 ms, 16 -> 0.22 ms, 32 -> 0.25 ms)
+constexpr int NW = 8;                 // words per field element in scratch
 
 struct DevTape {
   const PrepOp* prep;
@@ -36,7 +39,11 @@ struct DevTape {
   const InputPoint* in_points;
   const Ref* extra_refs;
   const u32* const_limbs;
-  const u32* const_points;
+  const u32* const_points;      // 18 limbs (x[9], y[9]) per constant point: the witness side
+  const u32* const_points8;     // 16 words (x[8], y[8]) per constant point: the replay side
+  const u32* cmap;              // compact layout: slot -> narrow / wide row (p2e_tape_compact_layout)
+  const u32* pt_nrow;           // per curve op: narrow row of its first slot
+  const u32* pt_wrow;           // per curve op: wide row of its first check_sum slot
   int n_prep, n_ptops, n_checks, n_in_points;
   int32_t pre_pid[16];
   Ref fixed_scalar, msm_k1, msm_k2;
@@ -45,29 +52,39 @@ struct DevTape {
   int32_t chain_begin[N_CHAINS], chain_end[N_CHAINS];
 };
 
+enum : int { FMT_PLAIN = 0, FMT_COMPACT = 1 };
+
 struct ChainArgs {
   DevTape t;
   size_t n;                 // signatures in this chunk
   int round;                // dependency round being executed (Tape::n_rounds)
   const u64* in[MAX_TAPE_INPUTS];   // input nonnative values, [9][is] each
   size_t is;
-  u64* out;                 // [n_slots][os]
+  int fmt;
+  u64* out;                 // FMT_PLAIN: [n_slots][os]
+  u32* nar;                 // FMT_COMPACT: [narrow rows][os]
+  u64* wide;                // FMT_COMPACT: [wide rows][os] or NULL (derived form: check_sum columns not stored)
   size_t os;
   u32* err;
   // scratch (stride = cap)
   size_t cap;
-  u32 *JX, *JY, *JZ;        // [n_ptops + n_in_points][9][cap]
-  u32* ZINV;                // [n_ptops][9][cap]
-  u32 *AX, *AY, *ZC;        // [n_ptops + n_in_points][9][cap]
+  u32 *JX, *JY, *JZ;        // [n_ptops + n_in_points][8][cap]  weak words
+  u32* ZINV;                // [n_ptops][8][cap]
+  u32 *AX, *AY;             // [n_ptops + n_in_points][9][cap]  canonical 29-bit limbs
+  u32* ZC;                  // [n_ptops + n_in_points][8][cap]  Z^3, weak words
   int32_t *SRC1, *SRC2;     // [n_ptops][cap]
   uint8_t* FLG;             // [n_ptops][cap]
-  u32 *GP, *GI;             // [inversion groups][9][cap]: group products / their inverses (K2 tree form)
+  u32 *GP, *GI;             // [INV_GROUPS][8][cap]: group products / their inverses (K2 tree)
   u32* BAD;                 // [cap]: bit g set = group g contains a zero Z
 };
 
 // ------------------------------------------------------------------------------------------
+// witness access (both output formats).  Refs only ever name plain value / flag slots (checked at upload).
 __device__ __forceinline__ u64 load_wire(const ChainArgs& A, uint8_t space, u32 off, size_t i) {
-  if (space == SP_OUT) return A.out[(size_t)off * A.os + i];
+  if (space == SP_OUT) {
+    if (A.fmt == FMT_PLAIN) return A.out[(size_t)off * A.os + i];
+    return (u64)A.nar[(size_t)A.t.cmap[off] * A.os + i];
+  }
   if (space == SP_IN) return A.in[off / 9][(size_t)(off % 9) * A.is + i];
   return A.t.const_limbs[off];
 }
@@ -79,101 +96,112 @@ __device__ __forceinline__ void load_ref(const ChainArgs& A, const Ref& r, size_
   for (int l = 0; l < NL; l++) w[l] = (l < r.nl) ? load_wire(A, r.space, r.off + l, i) * bm : 0;
 }
 
+// plain value slots written by the prep interpreter
+__device__ __forceinline__ void st1(const ChainArgs& A, u32 slot, size_t i, u64 v) {
+  if (A.fmt == FMT_PLAIN) A.out[(size_t)slot * A.os + i] = v;
+  else A.nar[(size_t)A.t.cmap[slot] * A.os + i] = (u32)v;
+}
 __device__ __forceinline__ void st9(const ChainArgs& A, u32 slot, size_t i, const u32 (&v)[NL]) {
+  if (A.fmt == FMT_PLAIN) {
 #pragma unroll
-  for (int l = 0; l < NL; l++) A.out[(size_t)(slot + l) * A.os + i] = v[l];
-}
-__device__ __forceinline__ void st1(const ChainArgs& A, u32 slot, size_t i, u64 v) { A.out[(size_t)slot * A.os + i] = v; }
-
-// The generator cores are kept OUT OF LINE: a curve op expands to 3-4 full mul witnesses plus a dozen
-// small generators, and fully inlined that is ~130 KB of straight-line code per thread -- the
-// expansion kernel was instruction-fetch bound (ncu: stall_no_instruction 7.5 per issue).
-// `o` points at out[slot][i]; consecutive tuple elements are `os` apart.
-
-// Operands and results cross the call boundary BY VALUE (structs of 9 limbs): ptxas keeps them in
-// registers, whereas pointer arguments forced every operand through local memory (ncu: the
-// expansion kernel wrote 3.45 GB to DRAM for 2.63 GB of output).
-struct W9 { u32 v[NL]; };
-struct I9 { i32 v[NL]; };
-struct W9E { W9 r; u32 e; };
-__device__ __forceinline__ W9 w9(const u32 (&a)[NL]) { W9 r;
+    for (int l = 0; l < NL; l++) A.out[(size_t)(slot + l) * A.os + i] = v[l];
+  } else {
+    const u32 row = A.t.cmap[slot];                 // the rows of one tuple are consecutive
 #pragma unroll
-  for (int l = 0; l < NL; l++) r.v[l] = a[l];
-  return r; }
-__device__ __forceinline__ I9 i9(const i32 (&a)[NL]) { I9 r;
-#pragma unroll
-  for (int l = 0; l < NL; l++) r.v[l] = a[l];
-  return r; }
-
-// MulNonnative row tuple (r, q, check_sum) followed by the CheckSum tuple (b): 51 slots
-template <class MOD>
-__device__ __noinline__ W9E nl_mul(u64* __restrict__ o, size_t os, W9 x, W9 y) {
-  u32 r[NL], q[NL];
-  u64 cs[2 * NL - 1], b[2 * NL - 2];
-  W9E ret;
-  ret.e = mul_witness_core<MOD>(x.v, y.v, r, q, cs, b);
-#pragma unroll
-  for (int l = 0; l < NL; l++) {
-    o[(size_t)l * os] = r[l];
-    o[(size_t)(9 + l) * os] = q[l];
-    ret.r.v[l] = r[l];
+    for (int l = 0; l < NL; l++) A.nar[(size_t)(row + l) * A.os + i] = v[l];
   }
-#pragma unroll
-  for (int l = 0; l < 2 * NL - 1; l++) o[(size_t)(18 + l) * os] = cs[l];
-#pragma unroll
-  for (int l = 0; l < 2 * NL - 2; l++) o[(size_t)(35 + l) * os] = b[l];
-  return ret;
 }
-// ADD / SUB tuple: value[9], overflow
-template <class MOD, bool IS_SUB>
-__device__ __noinline__ W9 nl_addsub(u64* __restrict__ o, size_t os, W9 a, W9 b) {
-  W9 r;
-  u32 ov = IS_SUB ? sub_witness_core<MOD>(a.v, b.v, r.v) : add_witness_core<MOD>(a.v, b.v, r.v);
-#pragma unroll
-  for (int l = 0; l < NL; l++) o[(size_t)l * os] = r.v[l];
-  o[(size_t)9 * os] = ov;
-  return r;
-}
-// NonNativeInverseGenerator tuple (div, inv) when the inverse is already known
-template <class MOD>
-__device__ __noinline__ u32 nl_inv_known(u64* __restrict__ o, size_t os, W9 xc, W9 inv) {
-  u32 div[NL];
-  u32 e = inv_div_core<MOD>(xc.v, inv.v, div);
-#pragma unroll
-  for (int l = 0; l < NL; l++) { o[(size_t)l * os] = div[l]; o[(size_t)(9 + l) * os] = inv.v[l]; }
+// MulNonnative row tuple (r, q, check_sum) followed by the CheckSum tuple (b): 51 slots, from the generic core
+__device__ u32 st_mul_generic(const ChainArgs& A, u32 slot, size_t i, const u32 (&r)[NL], const u32 (&q)[NL],
+                              const u64 (&cs)[2 * NL - 1], const u64 (&b)[2 * NL - 2]) {
+  if (A.fmt == FMT_PLAIN) {
+    u64* o = A.out + (size_t)slot * A.os + i;
+    for (int l = 0; l < NL; l++) { o[(size_t)l * A.os] = r[l]; o[(size_t)(9 + l) * A.os] = q[l]; }
+    for (int l = 0; l < 2 * NL - 1; l++) o[(size_t)(18 + l) * A.os] = cs[l];
+    for (int l = 0; l < 2 * NL - 2; l++) o[(size_t)(35 + l) * A.os] = b[l];
+    return 0;
+  }
+  u32 e = 0;
+  u32* o = A.nar + (size_t)A.t.cmap[slot] * A.os + i;
+  for (int l = 0; l < NL; l++) { o[(size_t)l * A.os] = r[l]; o[(size_t)(9 + l) * A.os] = q[l]; }
+  u32 tops = 0;
+  for (int l = 0; l < 2 * NL - 2; l++) {
+    o[(size_t)(18 + l) * A.os] = (u32)b[l];
+    tops |= ((u32)(b[l] >> 32) & 3u) << (2 * l);
+    if (b[l] >> 34) e |= ERR_CARRY_RANGE;              // does not fit the packed form (the reference's assert, :527)
+  }
+  o[(size_t)34 * A.os] = tops;
+  if (A.wide) {
+    u64* w = A.wide + (size_t)(A.t.cmap[slot + 18] & 0x7fffffffu) * A.os + i;
+    for (int l = 0; l < 2 * NL - 1; l++) w[(size_t)l * A.os] = cs[l];
+  } else {
+    // derived form: the host rebuilds check_sum_j = 2^29 c_j - c_{j-1} from the carries (CheckSumGate's constraints,
+    // gates/mul_nonnative.rs:411-427, solved for a); a row that is not of this form is flagged
+    i64 prev = 0;
+    for (int l = 0; l < 2 * NL - 1; l++) {
+      const i64 cur = l < 2 * NL - 2 ? (i64)b[l] - ((i64)1 << 33) : 0;
+      if (gl_from_i64(cur * ((i64)1 << LB) - prev) != cs[l]) e |= ERR_CARRY_RANGE;
+      prev = cur;
+    }
+  }
   return e;
 }
 
-template <class MOD>
-__device__ __forceinline__ u32 do_mul(const ChainArgs& A, u32 slot, size_t i, const u32 (&x)[NL], const u32 (&y)[NL],
-                                      u32 (&r)[NL]) {
-  W9E t = nl_mul<MOD>(A.out + (size_t)slot * A.os + i, A.os, w9(x), w9(y));
+// ------------------------------------------------------------------------------------------
+// Emit policies of the expansion kernel: `f` = slot offset inside the curve op (plain format), `c` = narrow-row
+// offset inside the curve op (compact format), `m` = index of the MulNonnative row inside the curve op.
+struct W9 { u32 v[NL]; };
+struct EmPlain {
+  u64* o;          // -> out[op.slot][i]
+  size_t os;
+  __device__ __forceinline__ void val(int f, int, const u32 (&v)[NL], u32 flag) const {
 #pragma unroll
-  for (int l = 0; l < NL; l++) r[l] = t.r.v[l];
-  return t.e;
-}
-template <class MOD>
-__device__ __forceinline__ void do_add(const ChainArgs& A, u32 slot, size_t i, const u32 (&a)[NL], const u32 (&b)[NL],
-                                       u32 (&r)[NL]) {
-  W9 t = nl_addsub<MOD, false>(A.out + (size_t)slot * A.os + i, A.os, w9(a), w9(b));
+    for (int l = 0; l < NL; l++) o[(size_t)(f + l) * os] = v[l];
+    o[(size_t)(f + 9) * os] = flag;
+  }
+  __device__ __forceinline__ void inv(int f, int, const u32 (&div)[NL], const u32 (&iv)[NL]) const {
 #pragma unroll
-  for (int l = 0; l < NL; l++) r[l] = t.v[l];
-}
-template <class MOD>
-__device__ __forceinline__ void do_sub(const ChainArgs& A, u32 slot, size_t i, const u32 (&a)[NL], const u32 (&b)[NL],
-                                       u32 (&r)[NL]) {
-  W9 t = nl_addsub<MOD, true>(A.out + (size_t)slot * A.os + i, A.os, w9(a), w9(b));
+    for (int l = 0; l < NL; l++) { o[(size_t)(f + l) * os] = div[l]; o[(size_t)(f + 9 + l) * os] = iv[l]; }
+  }
+  __device__ __forceinline__ void mul(int f, int, int, const u32 (&r)[NL], const u32 (&q)[NL], const i64 (&v)[17],
+                                      const u32 (&blo)[16], u32 tops) const {
 #pragma unroll
-  for (int l = 0; l < NL; l++) r[l] = t.v[l];
-}
-template <class MOD>
-__device__ __forceinline__ u32 do_inv_known(const ChainArgs& A, u32 slot, size_t i, const u32 (&xc)[NL],
-                                            const u32 (&inv)[NL]) {
-  return nl_inv_known<MOD>(A.out + (size_t)slot * A.os + i, A.os, w9(xc), w9(inv));
-}
+    for (int l = 0; l < NL; l++) { o[(size_t)(f + l) * os] = r[l]; o[(size_t)(f + 9 + l) * os] = q[l]; }
+#pragma unroll
+    for (int l = 0; l < 17; l++) o[(size_t)(f + 18 + l) * os] = gl_from_i64(v[l]);
+#pragma unroll
+    for (int l = 0; l < 16; l++) o[(size_t)(f + 35 + l) * os] = (u64)blo[l] | ((u64)((tops >> (2 * l)) & 3u) << 32);
+  }
+};
+struct EmCompact {
+  u32* o;          // -> nar[pt_nrow][i]
+  u64* w;          // -> wide[pt_wrow][i] or NULL
+  size_t os;
+  __device__ __forceinline__ void val(int, int c, const u32 (&v)[NL], u32 flag) const {
+#pragma unroll
+    for (int l = 0; l < NL; l++) o[(size_t)(c + l) * os] = v[l];
+    o[(size_t)(c + 9) * os] = flag;
+  }
+  __device__ __forceinline__ void inv(int, int c, const u32 (&div)[NL], const u32 (&iv)[NL]) const {
+#pragma unroll
+    for (int l = 0; l < NL; l++) { o[(size_t)(c + l) * os] = div[l]; o[(size_t)(c + 9 + l) * os] = iv[l]; }
+  }
+  __device__ __forceinline__ void mul(int, int c, int m, const u32 (&r)[NL], const u32 (&q)[NL], const i64 (&v)[17],
+                                      const u32 (&blo)[16], u32 tops) const {
+#pragma unroll
+    for (int l = 0; l < NL; l++) { o[(size_t)(c + l) * os] = r[l]; o[(size_t)(c + 9 + l) * os] = q[l]; }
+#pragma unroll
+    for (int l = 0; l < 16; l++) o[(size_t)(c + 18 + l) * os] = blo[l];
+    o[(size_t)(c + 34) * os] = tops;
+    if (w) {
+#pragma unroll
+      for (int l = 0; l < 17; l++) w[(size_t)(17 * m + l) * os] = gl_from_i64(v[l]);
+    }
+  }
+};
 
 // ------------------------------------------------------------------------------------------
-// K0: prep-op interpreter
+// K0: prep-op interpreter (generic cores: operands are arbitrary wires, both moduli)
 template <class MOD>
 __device__ u32 prep_exec(const ChainArgs& A, const PrepOp& op, size_t i) {
   u64 aw[NL], bw[NL];
@@ -184,33 +212,41 @@ __device__ u32 prep_exec(const ChainArgs& A, const PrepOp& op, size_t i) {
   switch (op.opcode) {
     case OP_MUL: {
       e = load_mul_wires(aw, a) | load_mul_wires(bw, b);
+      u32 q[NL];
+      u64 cs[2 * NL - 1], cb[2 * NL - 2];
       if (e == 0) {
-        e = do_mul<MOD>(A, op.slot, i, a, b, r);
+        e = mul_witness_core<MOD>(a, b, r, q, cs, cb);
       } else {
-        for (int l = 0; l < 51; l++) st1(A, op.slot + l, i, 0);
+        set_zero9(r);
+        set_zero9(q);
+        for (int l = 0; l < 2 * NL - 1; l++) cs[l] = 0;
+        for (int l = 0; l < 2 * NL - 2; l++) cb[l] = 0;
       }
+      const u32 e2 = st_mul_generic(A, op.slot, i, r, q, cs, cb);
+      if (e == 0) e = e2;
       break;
     }
     case OP_ADD:
     case OP_SUB: {
       e = load_canon<MOD>(aw, a) | load_canon<MOD>(bw, b);
       if (e) { set_zero9(a); set_zero9(b); }
-      if (op.opcode == OP_ADD) do_add<MOD>(A, op.slot, i, a, b, r);
-      else do_sub<MOD>(A, op.slot, i, a, b, r);
+      const u32 ov = op.opcode == OP_ADD ? add_witness_core<MOD>(a, b, r) : sub_witness_core<MOD>(a, b, r);
+      st9(A, op.slot, i, r);
+      st1(A, op.slot + 9, i, ov);
       break;
     }
     case OP_INV: {
       e = load_canon<MOD>(aw, a);
       if (e == 0 && is_zero9(a)) e = ERR_INVERSE_ZERO;
-      u32 inv[NL];
+      u32 inv[NL], div[NL];
       set_zero9(inv);
+      set_zero9(div);
       if (e == 0) {
         inv_mod<MOD>(a, inv);
-        e |= do_inv_known<MOD>(A, op.slot, i, a, inv);
-      } else {
-        st9(A, op.slot, i, inv);
-        st9(A, op.slot + 9, i, inv);
+        e |= inv_div_core<MOD>(a, inv, div);
       }
+      st9(A, op.slot, i, div);
+      st9(A, op.slot + 9, i, inv);
       break;
     }
     default: break;
@@ -279,10 +315,9 @@ __global__ void __launch_bounds__(32) k_prep(ChainArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: Jacobian replay (secp256k1: a = 0) in lazy arithmetic.  x = X/Z^2, y = Y/Z^3.
-// One thread per (signature, chain); chains are independent op ranges of the tape.
-struct JacL {
-  i32 X[NL], Y[NL], Z[NL];
+// K1: Jacobian replay (secp256k1: a = 0).  x = X/Z^2, y = Y/Z^3.
+struct JacF {
+  u32 X[NW], Y[NW], Z[NW];
 };
 
 __device__ __forceinline__ int pt_index(const ChainArgs& A, int32_t pid) {
@@ -301,141 +336,84 @@ __device__ __forceinline__ int32_t resolve_pid(const ChainArgs& A, int32_t pid, 
   return pid;
 }
 
-template <class T>
-__device__ __forceinline__ void ld9(const u32* __restrict__ base, int idx, size_t cap, size_t i, T (&v)[NL]) {
+template <int N>
+__device__ __forceinline__ void ldw(const u32* __restrict__ base, int idx, size_t cap, size_t i, u32 (&v)[N]) {
 #pragma unroll
-  for (int l = 0; l < NL; l++) v[l] = (T)base[((size_t)idx * NL + l) * cap + i];
+  for (int l = 0; l < N; l++) v[l] = base[((size_t)idx * N + l) * cap + i];
 }
-template <class T>
-__device__ __forceinline__ void sv9(u32* __restrict__ base, int idx, size_t cap, size_t i, const T (&v)[NL]) {
+template <int N>
+__device__ __forceinline__ void stw(u32* __restrict__ base, int idx, size_t cap, size_t i, const u32 (&v)[N]) {
 #pragma unroll
-  for (int l = 0; l < NL; l++) base[((size_t)idx * NL + l) * cap + i] = (u32)v[l];
+  for (int l = 0; l < N; l++) base[((size_t)idx * N + l) * cap + i] = v[l];
 }
 
-__device__ __forceinline__ void load_jac(const ChainArgs& A, int32_t pid, size_t i, JacL& P) {
+__device__ __forceinline__ void load_jac(const ChainArgs& A, int32_t pid, size_t i, JacF& P) {
   if (pid >= PID_CONST_BASE) {
-    const u32* c = A.t.const_points + (size_t)(pid - PID_CONST_BASE) * 18;
+    const u32* c = A.t.const_points8 + (size_t)(pid - PID_CONST_BASE) * 16;
 #pragma unroll
-    for (int l = 0; l < NL; l++) {
-      P.X[l] = (i32)c[l];
-      P.Y[l] = (i32)c[NL + l];
-      P.Z[l] = (l == 0) ? 1 : 0;
+    for (int l = 0; l < NW; l++) {
+      P.X[l] = c[l];
+      P.Y[l] = c[NW + l];
+      P.Z[l] = (l == 0) ? 1u : 0u;
     }
   } else {
     int idx = pt_index(A, pid);
-    ld9(A.JX, idx, A.cap, i, P.X);
-    ld9(A.JY, idx, A.cap, i, P.Y);
-    ld9(A.JZ, idx, A.cap, i, P.Z);
+    ldw(A.JX, idx, A.cap, i, P.X);
+    ldw(A.JY, idx, A.cap, i, P.Y);
+    ldw(A.JZ, idx, A.cap, i, P.Z);
   }
 }
 
-// The replay kernels run ~1 warp per SM through thousands of multiplications: keep the multiply /
-// square bodies as real functions so the whole loop stays inside the instruction cache (fully
-// inlined, one point addition was ~64 KB of straight-line code and instruction-fetch bound).
-__device__ __noinline__ I9 lzm_v(I9 a, I9 b) {
-  I9 r;
-  lz_mul(a.v, b.v, r.v);
+// The latency-bound kernels run few warps per SM through thousands of multiplications: the multiply / square
+// bodies are real functions so that the loops stay inside the instruction cache.  Operands and results cross the
+// call boundary BY VALUE (structs of 8 words): ptxas keeps them in registers.
+__device__ __noinline__ F8 f8m_v(F8 a, F8 b) {
+  F8 r;
+  f8_mul(a.v, b.v, r.v);
   return r;
 }
-__device__ __noinline__ I9 lzs_v(I9 a) {
-  I9 r;
-  lz_sqr(a.v, r.v);
+__device__ __noinline__ F8 f8s_v(F8 a) {
+  F8 r;
+  f8_sqr(a.v, r.v);
   return r;
 }
-__device__ __forceinline__ void lzm(const i32 (&a)[NL], const i32 (&b)[NL], i32 (&r)[NL]) {
-  I9 t = lzm_v(i9(a), i9(b));
+__device__ __forceinline__ F8 f8w(const u32 (&a)[NW]) {
+  F8 r;
 #pragma unroll
-  for (int l = 0; l < NL; l++) r[l] = t.v[l];
+  for (int l = 0; l < NW; l++) r.v[l] = a[l];
+  return r;
 }
-__device__ __forceinline__ void lzs(const i32 (&a)[NL], i32 (&r)[NL]) {
-  I9 t = lzs_v(i9(a));
+__device__ __forceinline__ void fm(const u32 (&a)[NW], const u32 (&b)[NW], u32 (&r)[NW]) {
+  F8 t = f8m_v(f8w(a), f8w(b));
 #pragma unroll
-  for (int l = 0; l < NL; l++) r[l] = t.v[l];
+  for (int l = 0; l < NW; l++) r[l] = t.v[l];
 }
-#define lz_mul(a, b, r) lzm(a, b, r)
-#define lz_sqr(a, r) lzs(a, r)
-
-__device__ __forceinline__ void lzs_n(i32 (&x)[NL], int n) {
-  I9 t = i9(x);
-  for (int k = 0; k < n; k++) t = lzs_v(t);
+__device__ __forceinline__ void fs(const u32 (&a)[NW], u32 (&r)[NW]) {
+  F8 t = f8s_v(f8w(a));
 #pragma unroll
-  for (int l = 0; l < NL; l++) x[l] = t.v[l];
+  for (int l = 0; l < NW; l++) r[l] = t.v[l];
 }
-// x^(p-2) with the addition chain of p2e_field.cuh::lz_inv, through the out-of-line mul / sqr
-__device__ void lz_inv_calls(const i32 (&a)[NL], i32 (&r)[NL]) {
-  i32 x2[NL], x3[NL], x22[NL], x44[NL], x88[NL], t[NL], u[NL];
-  lzs(a, t); lzm(t, a, x2);
-  lzs(x2, t); lzm(t, a, x3);
-  lz_copy(x3, t); lzs_n(t, 3); lzm(t, x3, u);
-  lz_copy(u, t); lzs_n(t, 3); lzm(t, x3, u);
-  lz_copy(u, t); lzs_n(t, 2); lzm(t, x2, u);
-  lz_copy(u, t); lzs_n(t, 11); lzm(t, u, x22);
-  lz_copy(x22, t); lzs_n(t, 22); lzm(t, x22, x44);
-  lz_copy(x44, t); lzs_n(t, 44); lzm(t, x44, x88);
-  lz_copy(x88, t); lzs_n(t, 88); lzm(t, x88, u);
-  lz_copy(u, t); lzs_n(t, 44); lzm(t, x44, u);
-  lz_copy(u, t); lzs_n(t, 3); lzm(t, x3, u);
-  lz_copy(u, t); lzs_n(t, 23); lzm(t, x22, u);
-  lz_copy(u, t); lzs_n(t, 5); lzm(t, a, u);
-  lz_copy(u, t); lzs_n(t, 3); lzm(t, x2, u);
-  lz_copy(u, t); lzs_n(t, 2); lzm(t, a, r);
+__device__ __forceinline__ F8 f8s_n(F8 t, int n) {
+  for (int k = 0; k < n; k++) t = f8s_v(t);
+  return t;
 }
-
-// R = P + Q with Z3 = Z1*Z2*H, H = X2*Z1^2 - X1*Z2^2  (so x2 - x1 = Z3 / (Z1^3 Z2^3)).
-// Q_AFFINE: Z2 == 1 (mixed addition).
-template <bool Q_AFFINE>
-__device__ __forceinline__ void jac_add(const JacL& P, const JacL& Q, JacL& R) {
-  i32 z1z1[NL], u1[NL], u2[NL], s1[NL], s2[NL], h[NL], r[NL], t[NL], hh[NL], hhh[NL], v[NL];
-  lz_sqr(P.Z, z1z1);
-  if (Q_AFFINE) {
-    lz_copy(P.X, u1);
-    lz_copy(P.Y, s1);
-  } else {
-    i32 z2z2[NL];
-    lz_sqr(Q.Z, z2z2);
-    lz_mul(P.X, z2z2, u1);
-    lz_mul(P.Y, Q.Z, t);
-    lz_mul(t, z2z2, s1);
-  }
-  lz_mul(Q.X, z1z1, u2);
-  lz_mul(Q.Y, P.Z, t);
-  lz_mul(t, z1z1, s2);
-  lz_sub(u2, u1, h);
-  lz_sub(s2, s1, r);
-  lz_sqr(h, hh);
-  lz_mul(h, hh, hhh);
-  lz_mul(u1, hh, v);
-  lz_sqr(r, t);
-  lz_sub(t, hhh, u2);
-  lz_lin(u2, 1, v, 2, R.X);            // X3 = r^2 - hhh - 2v
-  lz_sub(v, R.X, t);
-  lz_mul(r, t, u2);
-  lz_mul(s1, hhh, t);
-  lz_sub(u2, t, R.Y);                  // Y3 = r (v - X3) - s1 hhh
-  if (Q_AFFINE) {
-    lz_mul(P.Z, h, R.Z);
-  } else {
-    lz_mul(P.Z, Q.Z, t);
-    lz_mul(t, h, R.Z);
-  }
-}
-
-// R = 2P with Z3 = 2*Y1*Z1  (so 2y = Z3 / Z1^4)
-__device__ __forceinline__ void jac_dbl(const JacL& P, JacL& R) {
-  i32 xx[NL], yy[NL], yyyy[NL], s[NL], m[NL], t[NL], t2[NL];
-  lz_sqr(P.X, xx);
-  lz_sqr(P.Y, yy);
-  lz_sqr(yy, yyyy);
-  lz_mul(P.X, yy, t);
-  lz_lin(t, 4, t, 0, s);               // S = 4 X YY
-  lz_lin(xx, 3, xx, 0, m);             // M = 3 XX
-  lz_sqr(m, t);
-  lz_lin(t, 1, s, 2, R.X);             // X3 = M^2 - 2S
-  lz_sub(s, R.X, t);
-  lz_mul(m, t, t2);
-  lz_lin(t2, 1, yyyy, 8, R.Y);         // Y3 = M (S - X3) - 8 YYYY
-  lz_mul(P.Y, P.Z, t);
-  lz_lin(t, 2, t, 0, R.Z);             // Z3 = 2 Y1 Z1
+// x^(p-2): 255 squarings + 15 multiplications (addition chain over the run structure of p - 2)
+__device__ F8 f8_inv_calls(F8 a) {
+  const F8 x2 = f8m_v(f8s_v(a), a);
+  const F8 x3 = f8m_v(f8s_v(x2), a);
+  F8 u = f8m_v(f8s_n(x3, 3), x3);                  // x6
+  u = f8m_v(f8s_n(u, 3), x3);                      // x9
+  u = f8m_v(f8s_n(u, 2), x2);                      // x11
+  const F8 x22 = f8m_v(f8s_n(u, 11), u);
+  const F8 x44 = f8m_v(f8s_n(x22, 22), x22);
+  const F8 x88 = f8m_v(f8s_n(x44, 44), x44);
+  u = f8m_v(f8s_n(x88, 88), x88);                  // x176
+  u = f8m_v(f8s_n(u, 44), x44);                    // x220
+  u = f8m_v(f8s_n(u, 3), x3);                      // x223
+  u = f8m_v(f8s_n(u, 23), x22);
+  u = f8m_v(f8s_n(u, 5), a);
+  u = f8m_v(f8s_n(u, 3), x2);
+  return f8m_v(f8s_n(u, 2), a);
 }
 
 // digit of `bits` bits at bit position `pos` of a little-endian 29-bit-limb value (nl limbs)
@@ -459,147 +437,92 @@ __device__ __forceinline__ u32 load_scalar_limbs(const ChainArgs& A, const Ref& 
   return e;
 }
 
-__global__ void __launch_bounds__(32) k_chain_replay(ChainArgs A, int chain0) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int chain = chain0 + blockIdx.y;
-  if (i >= A.n) return;
-  const int k_begin = A.t.chain_begin[chain], k_end = A.t.chain_end[chain];
-  if (k_begin == k_end) return;
-  u32 err = 0;
-  // per-signature affine input points (Z = 1); every chain writes the same values (benign)
-  for (int j = 0; j < A.t.n_in_points; j++) {
-    if ((int)A.t.in_points[j].round != A.round) continue;
-    u64 w[NL];
-    u32 x[NL], y[NL], one[NL];
-    load_ref(A, A.t.in_points[j].x, i, w);
-    err |= load_canon<ModP>(w, x);
-    load_ref(A, A.t.in_points[j].y, i, w);
-    err |= load_canon<ModP>(w, y);
-    set_zero9(one);
-    one[0] = 1;
-    int idx = A.t.n_ptops + j;
-    sv9(A.JX, idx, A.cap, i, x);
-    sv9(A.JY, idx, A.cap, i, y);
-    sv9(A.JZ, idx, A.cap, i, one);
-    sv9(A.AX, idx, A.cap, i, x);
-    sv9(A.AY, idx, A.cap, i, y);
-    sv9(A.ZC, idx, A.cap, i, one);
+// Two-lane form: lanes 2j and 2j+1 serve the same (signature, chain).  Both keep every value in registers; at
+// each step of the point formulas the two lanes compute the two products of an INDEPENDENT pair and swap the
+// results with an 8-word shfl_xor, so a general addition is 8 sequential multiplications instead of 16 (mixed:
+// 6 vs 11, doubling: 4 vs 7).  Static schedule, no shared memory; linear steps are done redundantly by both lanes.
+__device__ __forceinline__ void duo_mul2(bool odd, const u32 (&a)[NW], const u32 (&b)[NW], u32 (&r1)[NW],
+                                         const u32 (&c)[NW], const u32 (&d)[NW], u32 (&r2)[NW]) {
+  F8 x, y;
+#pragma unroll
+  for (int l = 0; l < NW; l++) { x.v[l] = odd ? c[l] : a[l]; y.v[l] = odd ? d[l] : b[l]; }
+  F8 mine = f8m_v(x, y);
+#pragma unroll
+  for (int l = 0; l < NW; l++) {
+    u32 other = __shfl_xor_sync(0xffffffffu, mine.v[l], 1);
+    r1[l] = odd ? other : mine.v[l];
+    r2[l] = odd ? mine.v[l] : other;
   }
-  u32 fs[NL], k1[NL], k2[NL];
-  err |= load_scalar_limbs(A, A.t.fixed_scalar, (int)A.t.fixed_round == A.round, i, fs);
-  err |= load_scalar_limbs(A, A.t.msm_k1, (int)A.t.msm_round == A.round, i, k1);
-  err |= load_scalar_limbs(A, A.t.msm_k2, (int)A.t.msm_round == A.round, i, k2);
-
-  int32_t cur = -1;
-  for (int k = k_begin; k < k_end; k++) {
-    const PtOp op = A.t.ptops[k];
-    if (((op.flags >> PF_CHAIN_SHIFT) & 3) != chain || (int)op.round != A.round) continue;   // chains / rounds interleave in op order
-    int32_t p1 = (op.flags & PF_P1_CUR) ? cur : resolve_pid(A, op.p1, i);
-    int32_t p2 = (op.flags & PF_P2_CUR) ? cur : resolve_pid(A, op.p2, i);
-    u32 flag = 1;
-    if (op.type == PT_CADD_FIXED) {
-      u32 d = digit_at(fs, NL, 4 * op.aux, 4);
-      p2 = PID_CONST_BASE + (int32_t)(A.t.fixed_table_base + 16u * op.aux + d);
-      flag = d != 0;
-    } else if (op.type == PT_CADD_MSM) {
-      u32 d = 4u * digit_at(k2, NL, 2 * op.aux, 2) + digit_at(k1, NL, 2 * op.aux, 2);
-      p2 = A.t.pre_pid[d];
-      flag = d != 0;
-    } else if (op.type == PT_CADD_BOOL) {
-      flag = load_wire(A, SP_IN, 9u * op.aux, i) != 0;      // BoolTarget input (0 / 1)
-    }
-    JacL P, R;
-    load_jac(A, p1, i, P);
-    if (op.type == PT_DBL) {
-      jac_dbl(P, R);
-      p2 = p1;
-    } else {
-      JacL Q;
-      load_jac(A, p2, i, Q);
-      if (op.flags & PF_P2_AFFINE) jac_add<true>(P, Q, R);
-      else jac_add<false>(P, Q, R);
-    }
-    sv9(A.JX, k, A.cap, i, R.X);
-    sv9(A.JY, k, A.cap, i, R.Y);
-    sv9(A.JZ, k, A.cap, i, R.Z);
-    A.SRC1[(size_t)k * A.cap + i] = p1;
-    A.SRC2[(size_t)k * A.cap + i] = p2;
-    A.FLG[(size_t)k * A.cap + i] = (uint8_t)flag;
-    if (op.flags & PF_SET_CUR) cur = flag ? k : p1;
-  }
-  if (err) atomicOr(&A.err[i], err);
 }
-
-// ------------------------------------------------------------------------------------------
-// K1 (two-lane form): lanes 2j and 2j+1 serve the same (signature, chain).  Both keep every value in
-// registers; at each step of the point formulas the two lanes compute the two products of an
-// INDEPENDENT pair and swap the results with a 9-word shfl_xor, so a general addition is 8
-// sequential multiplications instead of 16 (mixed: 6 vs 11, doubling: 4 vs 7).  Static schedule,
-// no shared memory; linear steps are done redundantly by both lanes.
-__device__ __forceinline__ void duo_mul2(bool odd, const i32 (&a)[NL], const i32 (&b)[NL], i32 (&r1)[NL],
-                                         const i32 (&c)[NL], const i32 (&d)[NL], i32 (&r2)[NL]) {
-  I9 x, y;
+__device__ __forceinline__ void duo_sqr2(bool odd, const u32 (&a)[NW], u32 (&r1)[NW], const u32 (&c)[NW], u32 (&r2)[NW]) {
+  F8 x;
 #pragma unroll
-  for (int l = 0; l < NL; l++) { x.v[l] = odd ? c[l] : a[l]; y.v[l] = odd ? d[l] : b[l]; }
-  I9 mine = lzm_v(x, y);
+  for (int l = 0; l < NW; l++) x.v[l] = odd ? c[l] : a[l];
+  F8 mine = f8s_v(x);
 #pragma unroll
-  for (int l = 0; l < NL; l++) {
-    i32 other = __shfl_xor_sync(0xffffffffu, mine.v[l], 1);
+  for (int l = 0; l < NW; l++) {
+    u32 other = __shfl_xor_sync(0xffffffffu, mine.v[l], 1);
     r1[l] = odd ? other : mine.v[l];
     r2[l] = odd ? mine.v[l] : other;
   }
 }
 
+// R = P + Q with Z3 = Z1*Z2*H, H = X2*Z1^2 - X1*Z2^2  (so x2 - x1 = Z3 / (Z1^3 Z2^3)).  Q_AFFINE: Z2 == 1.
 template <bool Q_AFFINE>
-__device__ __forceinline__ void duo_add(bool odd, const JacL& P, const JacL& Q, JacL& R) {
-  i32 z1z1[NL], u1[NL], u2[NL], s1[NL], s2[NL], h[NL], r[NL], t[NL], t2[NL], hh[NL], rr[NL], hhh[NL], v[NL], w[NL];
+__device__ __forceinline__ void duo_add(bool odd, const JacF& P, const JacF& Q, JacF& R) {
+  u32 z1z1[NW], u2[NW], s2[NW], h[NW], r[NW], t[NW], t2[NW], hh[NW], rr[NW], hhh[NW], v[NW], w[NW], v2[NW];
   if (Q_AFFINE) {
-    lzs(P.Z, z1z1);
+    fs(P.Z, z1z1);
     duo_mul2(odd, Q.Y, P.Z, t2, Q.X, z1z1, u2);
-    lz_sub(u2, P.X, h);
+    f8_sub(u2, P.X, h);
     duo_mul2(odd, t2, z1z1, s2, h, h, hh);
-    lz_sub(s2, P.Y, r);
+    f8_sub(s2, P.Y, r);
     duo_mul2(odd, r, r, rr, h, hh, hhh);
     duo_mul2(odd, P.X, hh, v, P.Z, h, R.Z);          // Z3 = Z1 h
-    lz_sub(rr, hhh, t);
-    lz_lin(t, 1, v, 2, R.X);                        // X3 = r^2 - hhh - 2v
-    lz_sub(v, R.X, w);
+    f8_sub(rr, hhh, t);
+    f8_add(v, v, v2);
+    f8_sub(t, v2, R.X);                              // X3 = r^2 - hhh - 2v
+    f8_sub(v, R.X, w);
     duo_mul2(odd, r, w, t, P.Y, hhh, t2);
-    lz_sub(t, t2, R.Y);                             // Y3 = r (v - X3) - Y1 hhh
+    f8_sub(t, t2, R.Y);                              // Y3 = r (v - X3) - Y1 hhh
   } else {
-    i32 z2z2[NL], zz[NL];
-    duo_mul2(odd, P.Z, P.Z, z1z1, Q.Z, Q.Z, z2z2);
+    u32 z2z2[NW], zz[NW], u1[NW], s1[NW];
+    duo_sqr2(odd, P.Z, z1z1, Q.Z, z2z2);
     duo_mul2(odd, P.Y, Q.Z, t, Q.Y, P.Z, t2);
     duo_mul2(odd, P.X, z2z2, u1, Q.X, z1z1, u2);
     duo_mul2(odd, t, z2z2, s1, t2, z1z1, s2);
-    lz_sub(u2, u1, h);
-    lz_sub(s2, s1, r);
-    duo_mul2(odd, h, h, hh, r, r, rr);
+    f8_sub(u2, u1, h);
+    f8_sub(s2, s1, r);
+    duo_sqr2(odd, h, hh, r, rr);
     duo_mul2(odd, P.Z, Q.Z, zz, h, hh, hhh);
     duo_mul2(odd, u1, hh, v, zz, h, R.Z);            // Z3 = Z1 Z2 h
-    lz_sub(rr, hhh, t);
-    lz_lin(t, 1, v, 2, R.X);
-    lz_sub(v, R.X, w);
+    f8_sub(rr, hhh, t);
+    f8_add(v, v, v2);
+    f8_sub(t, v2, R.X);
+    f8_sub(v, R.X, w);
     duo_mul2(odd, r, w, t, s1, hhh, t2);
-    lz_sub(t, t2, R.Y);
+    f8_sub(t, t2, R.Y);
   }
 }
 
-__device__ __forceinline__ void duo_dbl(bool odd, const JacL& P, JacL& R) {
-  i32 xx[NL], yy[NL], yyyy[NL], s[NL], m[NL], t[NL], t2[NL], yz[NL], mm[NL];
-  duo_mul2(odd, P.X, P.X, xx, P.Y, P.Y, yy);
-  lz_lin(xx, 3, xx, 0, m);             // M = 3 XX
+// R = 2P with Z3 = 2*Y1*Z1  (so 2y = Z3 / Z1^4)
+__device__ __forceinline__ void duo_dbl(bool odd, const JacF& P, JacF& R) {
+  u32 xx[NW], yy[NW], yyyy[NW], s[NW], s2[NW], m[NW], t[NW], t2[NW], yz[NW], mm[NW], y8[NW];
+  duo_sqr2(odd, P.X, xx, P.Y, yy);
+  f8_mul_small<3>(xx, m);              // M = 3 XX
   duo_mul2(odd, yy, yy, yyyy, P.X, yy, t);
-  lz_lin(t, 4, t, 0, s);               // S = 4 X YY
+  f8_mul_small<4>(t, s);               // S = 4 X YY
   duo_mul2(odd, P.Y, P.Z, yz, m, m, mm);
-  lz_lin(mm, 1, s, 2, R.X);            // X3 = M^2 - 2S
-  lz_sub(s, R.X, t);
-  lzm(m, t, t2);                       // both lanes (redundant): no partner product left
-  lz_lin(t2, 1, yyyy, 8, R.Y);         // Y3 = M (S - X3) - 8 YYYY
-  lz_lin(yz, 2, yz, 0, R.Z);           // Z3 = 2 Y1 Z1
+  f8_mul_small<8>(t, s2);              // 2 S
+  f8_sub(mm, s2, R.X);                 // X3 = M^2 - 2S
+  f8_sub(s, R.X, t);
+  fm(m, t, t2);                        // both lanes (redundant): no partner product left
+  f8_mul_small<8>(yyyy, y8);
+  f8_sub(t2, y8, R.Y);                 // Y3 = M (S - X3) - 8 YYYY
+  f8_add(yz, yz, R.Z);                 // Z3 = 2 Y1 Z1
 }
 
-__global__ void __launch_bounds__(64) k_chain_replay_duo(ChainArgs A, int chain0) {
+__global__ void __launch_bounds__(64) k_chain_replay(ChainArgs A, int chain0) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool odd = threadIdx.x & 1;
   const size_t i_raw = tid >> 1;
@@ -611,33 +534,35 @@ __global__ void __launch_bounds__(64) k_chain_replay_duo(ChainArgs A, int chain0
   if (k_begin == k_end) return;
   u32 err = 0;
   if (writer) {
+    // per-signature affine input points (Z = 1); every chain writes the same values (benign)
     for (int j = 0; j < A.t.n_in_points; j++) {
       if ((int)A.t.in_points[j].round != A.round) continue;
       u64 w[NL];
-      u32 x[NL], y[NL], one[NL];
+      u32 x[NL], y[NL], x8[NW], y8[NW], one[NW];
       load_ref(A, A.t.in_points[j].x, i, w);
       err |= load_canon<ModP>(w, x);
       load_ref(A, A.t.in_points[j].y, i, w);
       err |= load_canon<ModP>(w, y);
-      set_zero9(one);
-      one[0] = 1;
+      f8_from_l29(x, x8);
+      f8_from_l29(y, y8);
+      f8_one(one);
       int idx = A.t.n_ptops + j;
-      sv9(A.JX, idx, A.cap, i, x);
-      sv9(A.JY, idx, A.cap, i, y);
-      sv9(A.JZ, idx, A.cap, i, one);
-      sv9(A.AX, idx, A.cap, i, x);
-      sv9(A.AY, idx, A.cap, i, y);
-      sv9(A.ZC, idx, A.cap, i, one);
+      stw(A.JX, idx, A.cap, i, x8);
+      stw(A.JY, idx, A.cap, i, y8);
+      stw(A.JZ, idx, A.cap, i, one);
+      stw(A.AX, idx, A.cap, i, x);
+      stw(A.AY, idx, A.cap, i, y);
+      stw(A.ZC, idx, A.cap, i, one);
     }
   }
   __syncwarp();                                    // the partner lane reads the input points just written
-  u32 fs[NL], k1[NL], k2[NL];
-  err |= load_scalar_limbs(A, A.t.fixed_scalar, (int)A.t.fixed_round == A.round, i, fs);
+  u32 fsc[NL], k1[NL], k2[NL];
+  err |= load_scalar_limbs(A, A.t.fixed_scalar, (int)A.t.fixed_round == A.round, i, fsc);
   err |= load_scalar_limbs(A, A.t.msm_k1, (int)A.t.msm_round == A.round, i, k1);
   err |= load_scalar_limbs(A, A.t.msm_k2, (int)A.t.msm_round == A.round, i, k2);
 
   int32_t cur = -1, resident = -2;
-  JacL R;
+  JacF R;
   for (int k = k_begin; k < k_end; k++) {
     const PtOp op = A.t.ptops[k];
     if (((op.flags >> PF_CHAIN_SHIFT) & 3) != chain || (int)op.round != A.round) continue;   // chains / rounds interleave in op order
@@ -645,7 +570,7 @@ __global__ void __launch_bounds__(64) k_chain_replay_duo(ChainArgs A, int chain0
     int32_t p2 = (op.flags & PF_P2_CUR) ? cur : resolve_pid(A, op.p2, i);
     u32 flag = 1;
     if (op.type == PT_CADD_FIXED) {
-      u32 d = digit_at(fs, NL, 4 * op.aux, 4);
+      u32 d = digit_at(fsc, NL, 4 * op.aux, 4);
       p2 = PID_CONST_BASE + (int32_t)(A.t.fixed_table_base + 16u * op.aux + d);
       flag = d != 0;
     } else if (op.type == PT_CADD_MSM) {
@@ -653,11 +578,11 @@ __global__ void __launch_bounds__(64) k_chain_replay_duo(ChainArgs A, int chain0
       p2 = A.t.pre_pid[d];
       flag = d != 0;
     } else if (op.type == PT_CADD_BOOL) {
-      flag = load_wire(A, SP_IN, 9u * op.aux, i) != 0;
+      flag = load_wire(A, SP_IN, 9u * op.aux, i) != 0;      // BoolTarget input (0 / 1)
     }
     // operands: the previous result is still in registers; anything else comes from global scratch,
-    // which only the even lane writes -> make those stores visible to the odd lane first
-    JacL P, Q;
+    // which only the even lane writes (made visible to the odd lane by the __syncwarp below)
+    JacF P, Q;
     if (p1 == resident) P = R; else load_jac(A, p1, i, P);
     if (op.type == PT_DBL) {
       duo_dbl(odd, P, R);
@@ -668,9 +593,9 @@ __global__ void __launch_bounds__(64) k_chain_replay_duo(ChainArgs A, int chain0
       else duo_add<false>(odd, P, Q, R);
     }
     if (writer) {
-      sv9(A.JX, k, A.cap, i, R.X);
-      sv9(A.JY, k, A.cap, i, R.Y);
-      sv9(A.JZ, k, A.cap, i, R.Z);
+      stw(A.JX, k, A.cap, i, R.X);
+      stw(A.JY, k, A.cap, i, R.Y);
+      stw(A.JZ, k, A.cap, i, R.Z);
       A.SRC1[(size_t)k * A.cap + i] = p1;
       A.SRC2[(size_t)k * A.cap + i] = p2;
       A.FLG[(size_t)k * A.cap + i] = (uint8_t)flag;
@@ -683,232 +608,7 @@ __global__ void __launch_bounds__(64) k_chain_replay_duo(ChainArgs A, int chain0
 }
 
 // ------------------------------------------------------------------------------------------
-// K1 (cooperative form): 4 lanes per (signature, chain).  A Jacobian addition is 16 multiplications
-// but only 5 dependency levels deep (doubling: 7 -> 4), so the four lanes of a task execute the
-// independent multiplications of one level side by side; operands are staged in shared memory
-// (value registers of 9 lazy limbs each) and every level ends with a __syncwarp().  Each stage is
-// homogeneous (all MUL or all linear) so the lanes never diverge onto different code.
-enum : uint8_t { MO_NOP = 0, MO_MUL = 1, MO_LIN = 2 };
-struct MicroOp {
-  uint8_t opc, dst, a, b, ka, kb;
-};
-constexpr int SP_STAGES = 10, SP_LANES = 4, SP_REGS = 28, SP_TASKS = 32, SP_PITCH = SP_TASKS + 1;
-// value registers: 0-2 P (X1 Y1 Z1), 3-5 Q (X2 Y2 Z2), 6-8 result (X3 Y3 Z3), 9.. temporaries
-#define MUL_(d, a, b) {MO_MUL, d, a, b, 0, 0}
-#define LIN_(d, a, ka, b, kb) {MO_LIN, d, a, b, ka, kb}
-#define NOP_ {MO_NOP, 0, 0, 0, 0, 0}
-__constant__ MicroOp SP_TAB[3][SP_STAGES][SP_LANES] = {
-    // 0: general addition   A=9 B=10 C=11 D=12 U1=13 U2=14 S1=15 S2=16 H=17 R=18 HH=19 RR=20 ZZ=21 HHH=22 V=23 T=24 W=25 RW=26 SH=27
-    {{MUL_(9, 2, 2), MUL_(10, 5, 5), MUL_(11, 1, 5), MUL_(12, 4, 2)},
-     {MUL_(13, 0, 10), MUL_(14, 3, 9), MUL_(15, 11, 10), MUL_(16, 12, 9)},
-     {LIN_(17, 14, 1, 13, 1), LIN_(18, 16, 1, 15, 1), NOP_, NOP_},
-     {MUL_(19, 17, 17), MUL_(20, 18, 18), MUL_(21, 2, 5), NOP_},
-     {MUL_(22, 17, 19), MUL_(23, 13, 19), MUL_(8, 21, 17), NOP_},
-     {LIN_(24, 20, 1, 22, 1), NOP_, NOP_, NOP_},
-     {LIN_(6, 24, 1, 23, 2), NOP_, NOP_, NOP_},
-     {LIN_(25, 23, 1, 6, 1), NOP_, NOP_, NOP_},
-     {MUL_(26, 18, 25), MUL_(27, 15, 22), NOP_, NOP_},
-     {LIN_(7, 26, 1, 27, 1), NOP_, NOP_, NOP_}},
-    // 1: mixed addition (Z2 == 1): U1 = X1, S1 = Y1
-    {{MUL_(9, 2, 2), NOP_, NOP_, MUL_(12, 4, 2)},
-     {NOP_, MUL_(14, 3, 9), NOP_, MUL_(16, 12, 9)},
-     {LIN_(17, 14, 1, 0, 1), LIN_(18, 16, 1, 1, 1), NOP_, NOP_},
-     {MUL_(19, 17, 17), MUL_(20, 18, 18), NOP_, NOP_},
-     {MUL_(22, 17, 19), MUL_(23, 0, 19), MUL_(8, 2, 17), NOP_},
-     {LIN_(24, 20, 1, 22, 1), NOP_, NOP_, NOP_},
-     {LIN_(6, 24, 1, 23, 2), NOP_, NOP_, NOP_},
-     {LIN_(25, 23, 1, 6, 1), NOP_, NOP_, NOP_},
-     {MUL_(26, 18, 25), MUL_(27, 1, 22), NOP_, NOP_},
-     {LIN_(7, 26, 1, 27, 1), NOP_, NOP_, NOP_}},
-    // 2: doubling   XX=9 YY=10 YZ=11 YYYY=12 TT=13 S=14 M=15 MM=16 W=17 MW=18
-    {{MUL_(9, 0, 0), MUL_(10, 1, 1), MUL_(11, 1, 2), NOP_},
-     {MUL_(12, 10, 10), MUL_(13, 0, 10), NOP_, NOP_},
-     {LIN_(14, 13, 4, 13, 0), LIN_(15, 9, 3, 9, 0), LIN_(8, 11, 2, 11, 0), NOP_},
-     {MUL_(16, 15, 15), NOP_, NOP_, NOP_},
-     {LIN_(6, 16, 1, 14, 2), NOP_, NOP_, NOP_},
-     {LIN_(17, 14, 1, 6, 1), NOP_, NOP_, NOP_},
-     {MUL_(18, 15, 17), NOP_, NOP_, NOP_},
-     {LIN_(7, 18, 1, 12, 8), NOP_, NOP_, NOP_},
-     {NOP_, NOP_, NOP_, NOP_},
-     {NOP_, NOP_, NOP_, NOP_}}};
-__constant__ uint8_t SP_NSTAGE[3] = {10, 10, 8};
-#undef MUL_
-#undef LIN_
-#undef NOP_
-
-__device__ __forceinline__ void sp_ld(const i32* sh, int reg, int task, i32 (&v)[NL]) {
-#pragma unroll
-  for (int l = 0; l < NL; l++) v[l] = sh[(reg * NL + l) * SP_PITCH + task];
-}
-__device__ __forceinline__ void sp_st(i32* sh, int reg, int task, const i32 (&v)[NL]) {
-#pragma unroll
-  for (int l = 0; l < NL; l++) sh[(reg * NL + l) * SP_PITCH + task] = v[l];
-}
-
-// lane q in 0..2 loads coordinate q of point `pid` into value register base + q
-__device__ __forceinline__ void sp_load_point(const ChainArgs& A, i32* sh, int base, int32_t pid, int32_t resident_pid,
-                                              size_t i, int task, int q) {
-  if (q > 2) return;
-  i32 v[NL];
-  if (pid == resident_pid) {
-    sp_ld(sh, 6 + q, task, v);                         // the previous result is still in registers 6-8
-  } else if (pid >= PID_CONST_BASE) {
-    const u32* c = A.t.const_points + (size_t)(pid - PID_CONST_BASE) * 18;
-#pragma unroll
-    for (int l = 0; l < NL; l++) v[l] = (q == 0) ? (i32)c[l] : (q == 1) ? (i32)c[NL + l] : (l == 0);
-  } else {
-    int idx = pt_index(A, pid);
-    const u32* src = (q == 0) ? A.JX : (q == 1) ? A.JY : A.JZ;
-    ld9(src, idx, A.cap, i, v);
-  }
-  sp_st(sh, base + q, task, v);
-}
-
-__global__ void __launch_bounds__(128) k_chain_replay_coop(ChainArgs A, int chain0) {
-  __shared__ i32 sh[SP_REGS * NL * SP_PITCH];
-  const int q = threadIdx.x & 3;                       // lane role within the task
-  const int task = threadIdx.x >> 2;                   // 0..31
-  const size_t i_raw = (size_t)blockIdx.x * SP_TASKS + task;
-  const bool valid = i_raw < A.n;
-  const size_t i = valid ? i_raw : A.n - 1;            // out-of-range tasks shadow the last signature, store nothing
-  const int chain = chain0 + blockIdx.y;
-  const int k_begin = A.t.chain_begin[chain], k_end = A.t.chain_end[chain];
-  if (k_begin == k_end) return;
-  u32 err = 0;
-  if (q == 0 && valid) {
-    // per-signature affine input points (Z = 1); every chain writes the same values (benign)
-    for (int j = 0; j < A.t.n_in_points; j++) {
-      if ((int)A.t.in_points[j].round != A.round) continue;
-      u64 w[NL];
-      u32 x[NL], y[NL], one[NL];
-      load_ref(A, A.t.in_points[j].x, i, w);
-      err |= load_canon<ModP>(w, x);
-      load_ref(A, A.t.in_points[j].y, i, w);
-      err |= load_canon<ModP>(w, y);
-      set_zero9(one);
-      one[0] = 1;
-      int idx = A.t.n_ptops + j;
-      sv9(A.JX, idx, A.cap, i, x);
-      sv9(A.JY, idx, A.cap, i, y);
-      sv9(A.JZ, idx, A.cap, i, one);
-      sv9(A.AX, idx, A.cap, i, x);
-      sv9(A.AY, idx, A.cap, i, y);
-      sv9(A.ZC, idx, A.cap, i, one);
-    }
-  }
-  __syncwarp();
-  u32 fs[NL], k1[NL], k2[NL];
-  err |= load_scalar_limbs(A, A.t.fixed_scalar, (int)A.t.fixed_round == A.round, i, fs);
-  err |= load_scalar_limbs(A, A.t.msm_k1, (int)A.t.msm_round == A.round, i, k1);
-  err |= load_scalar_limbs(A, A.t.msm_k2, (int)A.t.msm_round == A.round, i, k2);
-
-  int32_t cur = -1, resident = -2;
-  for (int k = k_begin; k < k_end; k++) {
-    const PtOp op = A.t.ptops[k];
-    if (((op.flags >> PF_CHAIN_SHIFT) & 3) != chain || (int)op.round != A.round) continue;   // chains / rounds interleave in op order
-    int32_t p1 = (op.flags & PF_P1_CUR) ? cur : resolve_pid(A, op.p1, i);
-    int32_t p2 = (op.flags & PF_P2_CUR) ? cur : resolve_pid(A, op.p2, i);
-    u32 flag = 1;
-    if (op.type == PT_CADD_FIXED) {
-      u32 d = digit_at(fs, NL, 4 * op.aux, 4);
-      p2 = PID_CONST_BASE + (int32_t)(A.t.fixed_table_base + 16u * op.aux + d);
-      flag = d != 0;
-    } else if (op.type == PT_CADD_MSM) {
-      u32 d = 4u * digit_at(k2, NL, 2 * op.aux, 2) + digit_at(k1, NL, 2 * op.aux, 2);
-      p2 = A.t.pre_pid[d];
-      flag = d != 0;
-    } else if (op.type == PT_CADD_BOOL) {
-      flag = load_wire(A, SP_IN, 9u * op.aux, i) != 0;
-    }
-    const int kind = (op.type == PT_DBL) ? 2 : (op.flags & PF_P2_AFFINE) ? 1 : 0;
-    // stage operands (the just-computed result may be reused straight from shared memory)
-    sp_load_point(A, sh, 0, p1, resident, i, task, q);
-    if (kind != 2) sp_load_point(A, sh, 3, p2, resident, i, task, q);
-    else p2 = p1;
-    __syncwarp();
-    const int nst = SP_NSTAGE[kind];
-    for (int st = 0; st < nst; st++) {
-      const MicroOp m = SP_TAB[kind][st][q];
-      if (m.opc == MO_MUL) {
-        i32 a[NL], b[NL];
-        sp_ld(sh, m.a, task, a);
-        sp_ld(sh, m.b, task, b);
-        I9 r = lzm_v(i9(a), i9(b));
-        sp_st(sh, m.dst, task, r.v);
-      } else if (m.opc == MO_LIN) {
-        i32 a[NL], b[NL], r[NL];
-        sp_ld(sh, m.a, task, a);
-        sp_ld(sh, m.b, task, b);
-        lz_lin(a, m.ka, b, m.kb, r);
-        sp_st(sh, m.dst, task, r);
-      }
-      __syncwarp();
-    }
-    if (valid && q < 3) {
-      i32 v[NL];
-      sp_ld(sh, 6 + q, task, v);
-      u32* dst = (q == 0) ? A.JX : (q == 1) ? A.JY : A.JZ;
-      sv9(dst, k, A.cap, i, v);
-    }
-    if (valid && q == 3) {
-      A.SRC1[(size_t)k * A.cap + i] = p1;
-      A.SRC2[(size_t)k * A.cap + i] = p2;
-      A.FLG[(size_t)k * A.cap + i] = (uint8_t)flag;
-    }
-    resident = k;
-    if (op.flags & PF_SET_CUR) cur = flag ? k : p1;
-    __syncwarp();
-  }
-  if (err && valid && q == 0) atomicOr(&A.err[i], err);
-}
-
-// K2: Montgomery's trick over the Z3's of one signature, split in INV_GROUPS independent groups
-// (one field inversion per group) to shorten the dependency chain.
-__global__ void __launch_bounds__(32) k_chain_invert(ChainArgs A) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= A.n) return;
-  const int n = A.t.n_ptops;
-  const int per = (n + (int)gridDim.y - 1) / (int)gridDim.y;
-  const int k0 = blockIdx.y * per, k1 = (k0 + per < n) ? k0 + per : n;
-  if (k0 >= k1) return;
-  i32 run[NL], z[NL], t[NL];
-#pragma unroll
-  for (int l = 0; l < NL; l++) run[l] = (l == 0);
-  bool any = false;
-  for (int k = k0; k < k1; k++) any |= (int)A.t.ptops[k].round == A.round;
-  if (!any) return;                     // no curve op of this group in this round
-  for (int k = k0; k < k1; k++) {
-    if ((int)A.t.ptops[k].round != A.round) continue;
-    sv9(A.ZINV, k, A.cap, i, run);      // prefix product of this group's Z's
-    ld9(A.JZ, k, A.cap, i, z);
-    lz_mul(run, z, t);
-    lz_copy(t, run);
-  }
-  u32 rc[NL];
-  lz_canon(run, rc);
-  if (is_zero9(rc)) {
-    // some curve op had x1 == x2 (or y == 0): the reference's inverse() panics
-    atomicOr(&A.err[i], (u32)ERR_INVERSE_ZERO);
-    set_zero9(rc);
-    for (int k = k0; k < k1; k++)
-      if ((int)A.t.ptops[k].round == A.round) sv9(A.ZINV, k, A.cap, i, rc);
-    return;
-  }
-  i32 inv[NL];
-  lz_inv_calls(run, inv);
-  for (int k = k1 - 1; k >= k0; k--) {
-    if ((int)A.t.ptops[k].round != A.round) continue;
-    i32 pre[NL], zi[NL];
-    ld9(A.ZINV, k, A.cap, i, pre);
-    ld9(A.JZ, k, A.cap, i, z);
-    lz_mul(inv, pre, zi);
-    sv9(A.ZINV, k, A.cap, i, zi);
-    lz_mul(inv, z, t);
-    lz_copy(t, inv);
-  }
-}
-
-// K2, tree form (default): ONE field inversion per signature instead of one per group.
+// K2, tree form: ONE field inversion per signature.
 //   up   (signature, group): prefix products of the group's Z's -> ZINV, group product -> GP
 //   mid  (signature)       : prefix over the group products, one inversion, inverse of every group -> GI
 //   down (signature, group): back-substitution inside the group
@@ -928,63 +628,52 @@ __global__ void __launch_bounds__(32) k_chain_invert_up(ChainArgs A) {
   if (i >= A.n) return;
   int k0, k1;
   const bool any = group_range(A, k0, k1);
-  i32 run[NL], z[NL], t[NL];
-#pragma unroll
-  for (int l = 0; l < NL; l++) run[l] = (l == 0);
+  F8 run, z;
+  f8_one(run.v);
   if (any) {
     for (int k = k0; k < k1; k++) {
       if ((int)A.t.ptops[k].round != A.round) continue;
-      sv9(A.ZINV, k, A.cap, i, run);      // prefix product of this group's Z's
-      ld9(A.JZ, k, A.cap, i, z);
-      lz_mul(run, z, t);
-      lz_copy(t, run);
+      stw(A.ZINV, k, A.cap, i, run.v);    // prefix product of this group's Z's
+      ldw(A.JZ, k, A.cap, i, z.v);
+      run = f8m_v(run, z);
     }
   }
-  sv9(A.GP, blockIdx.y, A.cap, i, run);
+  stw(A.GP, blockIdx.y, A.cap, i, run.v);
 }
 
 __global__ void __launch_bounds__(32) k_chain_invert_mid(ChainArgs A, int G) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
-  i32 run[NL], gp[NL], t[NL];
-  u32 rc[NL];
-#pragma unroll
-  for (int l = 0; l < NL; l++) run[l] = (l == 0);
+  F8 run, gp;
+  f8_one(run.v);
   for (int g = 0; g < G; g++) {
-    sv9(A.GI, g, A.cap, i, run);          // product of the groups before g
-    ld9(A.GP, g, A.cap, i, gp);
-    lz_mul(run, gp, t);
-    lz_copy(t, run);
+    stw(A.GI, g, A.cap, i, run.v);        // product of the groups before g
+    ldw(A.GP, g, A.cap, i, gp.v);
+    run = f8m_v(run, gp);
   }
   u32 bad = 0;
-  lz_canon(run, rc);
-  if (is_zero9(rc)) {
+  if (f8_is_zero(run.v)) {
     // some curve op had x1 == x2 (or y == 0): the reference's inverse() panics.  Find the groups that
     // hold a zero, leave them out of the product (their ZINV rows are zeroed by the down pass).
-#pragma unroll
-    for (int l = 0; l < NL; l++) run[l] = (l == 0);
+    f8_one(run.v);
     for (int g = 0; g < G; g++) {
-      sv9(A.GI, g, A.cap, i, run);
-      ld9(A.GP, g, A.cap, i, gp);
-      lz_canon(gp, rc);
-      if (is_zero9(rc)) { bad |= 1u << g; continue; }
-      lz_mul(run, gp, t);
-      lz_copy(t, run);
+      stw(A.GI, g, A.cap, i, run.v);
+      ldw(A.GP, g, A.cap, i, gp.v);
+      if (f8_is_zero(gp.v)) { bad |= 1u << g; continue; }
+      run = f8m_v(run, gp);
     }
     atomicOr(&A.err[i], (u32)ERR_INVERSE_ZERO);
   }
   A.BAD[i] = bad;
-  i32 inv[NL];
-  lz_inv_calls(run, inv);
+  F8 inv = f8_inv_calls(run);
   for (int g = G - 1; g >= 0; g--) {
-    i32 pre[NL], gi[NL];
-    ld9(A.GI, g, A.cap, i, pre);
-    lz_mul(inv, pre, gi);
-    sv9(A.GI, g, A.cap, i, gi);
+    F8 pre;
+    ldw(A.GI, g, A.cap, i, pre.v);
+    F8 gi = f8m_v(inv, pre);
+    stw(A.GI, g, A.cap, i, gi.v);
     if ((bad >> g) & 1) continue;
-    ld9(A.GP, g, A.cap, i, gp);
-    lz_mul(inv, gp, t);
-    lz_copy(t, inv);
+    ldw(A.GP, g, A.cap, i, gp.v);
+    inv = f8m_v(inv, gp);
   }
 }
 
@@ -994,136 +683,174 @@ __global__ void __launch_bounds__(32) k_chain_invert_down(ChainArgs A) {
   int k0, k1;
   if (!group_range(A, k0, k1)) return;
   if ((A.BAD[i] >> blockIdx.y) & 1) {
-    u32 zero[NL];
-    set_zero9(zero);
+    u32 zero[NW];
+#pragma unroll
+    for (int l = 0; l < NW; l++) zero[l] = 0;
     for (int k = k0; k < k1; k++)
-      if ((int)A.t.ptops[k].round == A.round) sv9(A.ZINV, k, A.cap, i, zero);
+      if ((int)A.t.ptops[k].round == A.round) stw(A.ZINV, k, A.cap, i, zero);
     return;
   }
-  i32 inv[NL], z[NL], t[NL];
-  ld9(A.GI, blockIdx.y, A.cap, i, inv);
+  F8 inv, z;
+  ldw(A.GI, blockIdx.y, A.cap, i, inv.v);
   for (int k = k1 - 1; k >= k0; k--) {
     if ((int)A.t.ptops[k].round != A.round) continue;
-    i32 pre[NL], zi[NL];
-    ld9(A.ZINV, k, A.cap, i, pre);
-    ld9(A.JZ, k, A.cap, i, z);
-    lz_mul(inv, pre, zi);
-    sv9(A.ZINV, k, A.cap, i, zi);
-    lz_mul(inv, z, t);
-    lz_copy(t, inv);
+    F8 pre;
+    ldw(A.ZINV, k, A.cap, i, pre.v);
+    ldw(A.JZ, k, A.cap, i, z.v);
+    F8 zi = f8m_v(inv, pre);
+    stw(A.ZINV, k, A.cap, i, zi.v);
+    inv = f8m_v(inv, z);
   }
 }
 
-// K3: canonical affine coordinates of every computed point; Z^3 stays in lazy limbs (K4 folds it
-// into its own lazy product and canonicalises once)
+// K3: canonical affine coordinates (29-bit limbs) of every computed point, and Z^3 (weak words; K4 folds it into
+// its own product and canonicalises once)
 __global__ void __launch_bounds__(128) k_chain_affine(ChainArgs A) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int k = blockIdx.y;
   if (i >= A.n) return;
   // all four loads are addressed by (k, i) alone: issue them together, ahead of the tape lookup
-  i32 zi[NL], zi2[NL], zi3[NL], jx[NL], jy[NL], jz[NL], r[NL];
+  u32 zi[NW], zi2[NW], zi3[NW], jx[NW], jy[NW], jz[NW], r[NW];
   u32 c[NL];
-  ld9(A.ZINV, k, A.cap, i, zi);
-  ld9(A.JX, k, A.cap, i, jx);
-  ld9(A.JY, k, A.cap, i, jy);
-  ld9(A.JZ, k, A.cap, i, jz);
+  ldw(A.ZINV, k, A.cap, i, zi);
+  ldw(A.JX, k, A.cap, i, jx);
+  ldw(A.JY, k, A.cap, i, jy);
+  ldw(A.JZ, k, A.cap, i, jz);
   if ((int)A.t.ptops[k].round != A.round) return;
-  lz_sqr(zi, zi2);
-  lz_mul(zi2, zi, zi3);
-  lz_mul(jx, zi2, r);
-  lz_canon(r, c);
-  sv9(A.AX, k, A.cap, i, c);
-  lz_mul(jy, zi3, r);
-  lz_canon(r, c);
-  sv9(A.AY, k, A.cap, i, c);
-  lz_sqr(jz, zi2);
-  lz_mul(zi2, jz, r);
-  sv9(A.ZC, k, A.cap, i, r);
+  fs(zi, zi2);
+  fm(zi2, zi, zi3);
+  fm(jx, zi2, r);
+  f8_to_canon_l29(r, c);
+  stw(A.AX, k, A.cap, i, c);
+  fm(jy, zi3, r);
+  f8_to_canon_l29(r, c);
+  stw(A.AY, k, A.cap, i, c);
+  fs(jz, zi2);
+  fm(zi2, jz, r);
+  stw(A.ZC, k, A.cap, i, r);
 }
 
-#undef lz_mul
-#undef lz_sqr
-
-// K4: expand one curve op into all of its generators' output tuples
-__device__ __noinline__ I9 nl_lzmul_v(I9 a, I9 b) {
-  I9 r;
-  lz_mul(a.v, b.v, r.v);
-  return r;
-}
-__device__ __noinline__ W9 nl_lzcanon_v(I9 a) {
+// ------------------------------------------------------------------------------------------
+// K4: expand one curve op into all of its generators' output tuples.  Every operand here is a canonical generator
+// output (< 2^256), so the fast cores apply.  The cores are kept OUT OF LINE: fully inlined, a curve op is tens of
+// KB of straight-line code per thread and the kernel becomes instruction-fetch bound.
+struct W9E {
   W9 r;
-  lz_canon(a.v, r.v);
+  u32 e;
+};
+__device__ __forceinline__ W9 w9(const u32 (&a)[NL]) {
+  W9 r;
+#pragma unroll
+  for (int l = 0; l < NL; l++) r.v[l] = a[l];
   return r;
 }
-__device__ __forceinline__ void nl_lzmul(const i32 (&a)[NL], const i32 (&b)[NL], i32 (&r)[NL]) {
-  I9 t = nl_lzmul_v(i9(a), i9(b));
+// MulNonnative row + CheckSum row; the tuple is written from inside the call (only r and the error word return)
+template <class EM>
+__device__ __noinline__ W9E nl_mulw(EM em, int f, int c, int m, W9 x, W9 y) {
+  u32 r[NL], q[NL], blo[16], tops;
+  i64 v[17];
+  W9E ret;
+  ret.e = mulw_p_fast(x.v, y.v, r, q, v, blo, tops);
+  em.mul(f, c, m, r, q, v, blo, tops);
+#pragma unroll
+  for (int l = 0; l < NL; l++) ret.r.v[l] = r[l];
+  return ret;
+}
+template <class EM, bool IS_SUB>
+__device__ __noinline__ W9 nl_addsub(EM em, int f, int c, W9 a, W9 b) {
+  W9 r;
+  const u32 ov = IS_SUB ? sub_witness_core<ModP>(a.v, b.v, r.v) : add_witness_core<ModP>(a.v, b.v, r.v);
+  em.val(f, c, r.v, ov);
+  return r;
+}
+// NonNativeInverseGenerator tuple when the inverse is known: div = (x * inv - 1) / p, checked
+template <class EM>
+__device__ __noinline__ u32 nl_inv_known(EM em, int f, int c, W9 xc, F8 inv8, W9 inv) {
+  u32 x8[NW], t[16], r8[NW], q8[NW], div[NL];
+  f8_from_l29(xc.v, x8);
+  f8_mul_wide(x8, inv8.v, t);
+  u32 bad = f8_divmod16(t, r8, q8);
+  bad |= r8[0] ^ 1u;
+#pragma unroll
+  for (int l = 1; l < NW; l++) bad |= r8[l];
+  f8_to_l29(q8, div);
+  em.inv(f, c, div, inv.v);
+  return bad ? (u32)ERR_INTERNAL : 0u;
+}
+
+template <class EM>
+__device__ __forceinline__ u32 do_mul(const EM& em, int f, int c, int m, const u32 (&x)[NL], const u32 (&y)[NL], u32 (&r)[NL]) {
+  W9E t = nl_mulw<EM>(em, f, c, m, w9(x), w9(y));
+#pragma unroll
+  for (int l = 0; l < NL; l++) r[l] = t.r.v[l];
+  return t.e;
+}
+template <class EM>
+__device__ __forceinline__ void do_add(const EM& em, int f, int c, const u32 (&a)[NL], const u32 (&b)[NL], u32 (&r)[NL]) {
+  W9 t = nl_addsub<EM, false>(em, f, c, w9(a), w9(b));
 #pragma unroll
   for (int l = 0; l < NL; l++) r[l] = t.v[l];
 }
-__device__ __forceinline__ void nl_lzcanon(const i32 (&a)[NL], u32 (&r)[NL]) {
-  W9 t = nl_lzcanon_v(i9(a));
+template <class EM>
+__device__ __forceinline__ void do_sub(const EM& em, int f, int c, const u32 (&a)[NL], const u32 (&b)[NL], u32 (&r)[NL]) {
+  W9 t = nl_addsub<EM, true>(em, f, c, w9(a), w9(b));
 #pragma unroll
   for (int l = 0; l < NL; l++) r[l] = t.v[l];
+}
+template <class EM>
+__device__ __forceinline__ u32 do_inv_known(const EM& em, int f, int c, const u32 (&xc)[NL], const u32 (&vinv8)[NW],
+                                            const u32 (&vinv)[NL]) {
+  return nl_inv_known<EM>(em, f, c, w9(xc), f8w(vinv8), w9(vinv));
 }
 
 __device__ __forceinline__ void load_affine(const ChainArgs& A, int32_t pid, size_t i, u32 (&x)[NL], u32 (&y)[NL],
-                                            i32 (&zc)[NL]) {
+                                            u32 (&zc)[NW]) {
   if (pid >= PID_CONST_BASE) {
     const u32* c = A.t.const_points + (size_t)(pid - PID_CONST_BASE) * 18;
 #pragma unroll
     for (int l = 0; l < NL; l++) {
       x[l] = c[l];
       y[l] = c[NL + l];
-      zc[l] = (l == 0) ? 1 : 0;
     }
+    f8_one(zc);
   } else {
     int idx = pt_index(A, pid);
-    ld9(A.AX, idx, A.cap, i, x);
-    ld9(A.AY, idx, A.cap, i, y);
-    ld9(A.ZC, idx, A.cap, i, zc);
+    ldw(A.AX, idx, A.cap, i, x);
+    ldw(A.AY, idx, A.cap, i, y);
+    ldw(A.ZC, idx, A.cap, i, zc);
   }
 }
 
-// 3 CTAs / SM (<= 168 registers): measured best of {none, 2, 3, 4} on B200 (0.60 ms vs 0.66 ms for 4096 signatures)
-__global__ void __launch_bounds__(128, 3) k_chain_expand(ChainArgs A) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int k = blockIdx.y;
-  if (i >= A.n) return;
-  // Loads are issued in two dependent rounds, not five (ncu: a third of the stall samples sat on the
-  // chain tape -> SRC1 -> operand 1 -> SRC2 -> operand 2): everything addressed by (k, i) alone first ...
+template <class EM>
+__device__ __forceinline__ u32 expand_op(const ChainArgs& A, const EM& em, const PtOp& op, int k, size_t i) {
+  // Loads are issued in two dependent rounds: everything addressed by (k, i) alone first ...
   const size_t ki = (size_t)k * A.cap + i;
-  const PtOp op = A.t.ptops[k];
   const int32_t p1 = A.SRC1[ki];
   const int32_t p2_any = A.SRC2[ki];              // meaningless for a doubling (never dereferenced then)
   const u32 flg = A.FLG[ki];
-  i32 zinv[NL];
-  ld9(A.ZINV, k, A.cap, i, zinv);
-  if ((int)op.round != A.round) return;
-  const u32 s0 = op.slot;
+  u32 zinv[NW];
+  ldw(A.ZINV, k, A.cap, i, zinv);
   u32 e = 0;
   u32 x1[NL], y1[NL], vinv[NL], x2[NL], y2[NL];
-  i32 zc1[NL], zc2[NL], t[NL], t2[NL];
+  u32 zc1[NW], zc2[NW], t[NW], vinv8[NW];
   // ... then both operands
   load_affine(A, p1, i, x1, y1, zc1);
   if (op.type != PT_DBL) load_affine(A, p2_any, i, x2, y2, zc2);
   if (op.type == PT_DBL) {
     // (2y)^-1 = Z1^4 / Z3
-    i32 z1[NL];
-    if (p1 >= PID_CONST_BASE) {
-#pragma unroll
-      for (int l = 0; l < NL; l++) z1[l] = (l == 0);
-    } else {
-      ld9(A.JZ, pt_index(A, p1), A.cap, i, z1);
-    }
-    nl_lzmul(zc1, z1, t);
-    nl_lzmul(t, zinv, t2);
-    nl_lzcanon(t2, vinv);
+    u32 z1[NW];
+    if (p1 >= PID_CONST_BASE) f8_one(z1);
+    else ldw(A.JZ, pt_index(A, p1), A.cap, i, z1);
+    fm(zc1, z1, t);
+    fm(t, zinv, vinv8);
+    f8_canon(vinv8);
+    f8_to_l29(vinv8, vinv);
     u32 dy[NL], xx[NL], tr[NL], lam[NL], lam2[NL], xd[NL], x3[NL], xdiff[NL], lx[NL], y3[NL];
-    do_add<ModP>(A, s0 + 0, i, y1, y1, dy);                       // double_y
+    do_add(em, 0, 0, y1, y1, dy);                                 // double_y
     canon9<ModP>(dy);
     if (is_zero9(dy)) e |= ERR_INVERSE_ZERO;
-    e |= do_inv_known<ModP>(A, s0 + 10, i, dy, vinv);             // inv_double_y
-    e |= do_mul<ModP>(A, s0 + 28, i, x1, x1, xx);                 // x_squared
+    e |= do_inv_known(em, 10, 10, dy, vinv8, vinv);               // inv_double_y
+    e |= do_mul(em, 28, 28, 0, x1, x1, xx);                       // x_squared
     {                                                             // add_many([xx, xx, xx, A = 0])
       u32 acc[NL], sum[NL], ov = 0;
       copy9(xx, acc);
@@ -1134,43 +861,60 @@ __global__ void __launch_bounds__(128, 3) k_chain_expand(ChainArgs A) {
         else copy9(sum, acc);
       }
       copy9(acc, tr);
-      st9(A, s0 + 79, i, tr);
-      st1(A, s0 + 88, i, ov);
+      em.val(79, 63, tr, ov);
     }
-    e |= do_mul<ModP>(A, s0 + 89, i, tr, vinv, lam);              // lambda
-    e |= do_mul<ModP>(A, s0 + 140, i, lam, lam, lam2);            // lambda_squared
-    do_add<ModP>(A, s0 + 191, i, x1, x1, xd);                     // x_double
+    e |= do_mul(em, 89, 73, 1, tr, vinv, lam);                    // lambda
+    e |= do_mul(em, 140, 108, 2, lam, lam, lam2);                 // lambda_squared
+    do_add(em, 191, 143, x1, x1, xd);                             // x_double
     canon9<ModP>(xd);
-    do_sub<ModP>(A, s0 + 201, i, lam2, xd, x3);                   // x3
-    do_sub<ModP>(A, s0 + 211, i, x1, x3, xdiff);                  // x_diff
-    e |= do_mul<ModP>(A, s0 + 221, i, lam, xdiff, lx);            // lambda_x_diff
-    do_sub<ModP>(A, s0 + 272, i, lx, y1, y3);                     // y3
+    do_sub(em, 201, 153, lam2, xd, x3);                           // x3
+    do_sub(em, 211, 163, x1, x3, xdiff);                          // x_diff
+    e |= do_mul(em, 221, 173, 3, lam, xdiff, lx);                 // lambda_x_diff
+    do_sub(em, 272, 208, lx, y1, y3);                             // y3
   } else {
     // (x2 - x1)^-1 = Z1^3 Z2^3 / Z3
-    nl_lzmul(zc1, zc2, t);
-    nl_lzmul(t, zinv, t2);
-    nl_lzcanon(t2, vinv);
+    fm(zc1, zc2, t);
+    fm(t, zinv, vinv8);
+    f8_canon(vinv8);
+    f8_to_l29(vinv8, vinv);
     u32 u[NL], v[NL], s[NL], s2[NL], xs[NL], x3[NL], xd[NL], pr[NL], y3[NL];
-    do_sub<ModP>(A, s0 + 0, i, y2, y1, u);                        // u
-    do_sub<ModP>(A, s0 + 10, i, x2, x1, v);                       // v
+    do_sub(em, 0, 0, y2, y1, u);                                  // u
+    do_sub(em, 10, 10, x2, x1, v);                                // v
     if (is_zero9(v)) e |= ERR_INVERSE_ZERO;
-    e |= do_inv_known<ModP>(A, s0 + 20, i, v, vinv);              // v_inv
-    e |= do_mul<ModP>(A, s0 + 38, i, u, vinv, s);                 // s
-    e |= do_mul<ModP>(A, s0 + 89, i, s, s, s2);                   // s_squared
-    do_add<ModP>(A, s0 + 140, i, x2, x1, xs);                     // x_sum
+    e |= do_inv_known(em, 20, 20, v, vinv8, vinv);                // v_inv
+    e |= do_mul(em, 38, 38, 0, u, vinv, s);                       // s
+    e |= do_mul(em, 89, 73, 1, s, s, s2);                         // s_squared
+    do_add(em, 140, 108, x2, x1, xs);                             // x_sum
     canon9<ModP>(xs);
-    do_sub<ModP>(A, s0 + 150, i, s2, xs, x3);                     // x3
-    do_sub<ModP>(A, s0 + 160, i, x1, x3, xd);                     // x_diff
-    e |= do_mul<ModP>(A, s0 + 170, i, s, xd, pr);                 // prod
-    do_sub<ModP>(A, s0 + 221, i, pr, y1, y3);                     // y3
+    do_sub(em, 150, 118, s2, xs, x3);                             // x3
+    do_sub(em, 160, 128, x1, x3, xd);                             // x_diff
+    e |= do_mul(em, 170, 138, 2, s, xd, pr);                      // prod
+    do_sub(em, 221, 173, pr, y1, y3);                             // y3
     if (op.type != PT_ADD) {
       // curve_conditional_add: x = sum.x * b + p1.x * !b (curve.rs:235-240)
-      const u32 b = flg;
       u32 z[NL], r[NL];
       set_zero9(z);
-      if (b) { do_add<ModP>(A, s0 + 231, i, x3, z, r); do_add<ModP>(A, s0 + 241, i, y3, z, r); }
-      else { do_add<ModP>(A, s0 + 231, i, z, x1, r); do_add<ModP>(A, s0 + 241, i, z, y1, r); }
+      if (flg) { do_add(em, 231, 183, x3, z, r); do_add(em, 241, 193, y3, z, r); }
+      else { do_add(em, 231, 183, z, x1, r); do_add(em, 241, 193, z, y1, r); }
     }
+  }
+  return e;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(128, 3) k_chain_expand(ChainArgs A) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int k = blockIdx.y;
+  if (i >= A.n) return;
+  const PtOp op = A.t.ptops[k];
+  if ((int)op.round != A.round) return;
+  u32 e;
+  if (FMT == FMT_PLAIN) {
+    EmPlain em{A.out + (size_t)op.slot * A.os + i, A.os};
+    e = expand_op(A, em, op, k, i);
+  } else {
+    EmCompact em{A.nar + (size_t)A.t.pt_nrow[k] * A.os + i, A.wide ? A.wide + (size_t)A.t.pt_wrow[k] * A.os + i : nullptr, A.os};
+    e = expand_op(A, em, op, k, i);
   }
   if (e) atomicOr(&A.err[i], e);
 }
@@ -1189,114 +933,35 @@ __global__ void __launch_bounds__(32) k_chain_checks(ChainArgs A) {
   if (bad) A.err[i] |= ERR_CONNECT;
 }
 
-// ------------------------------------------------------------------------------------------
-// compact host format: split the [slots][n] u64 witness into a u32 matrix (narrow slots) and a u64
-// matrix (wide slots); map[slot] = (1u << 31 | wide row), (1u << 30 | narrow row) for a 34-bit carry
-// (bit 29 marks the first carry of a CheckSum tuple) or the narrow row
-__global__ void __launch_bounds__(256) k_pack_compact(size_t n, size_t n_slots, const u64* __restrict__ wit, size_t ws,
-                                                      const u32* __restrict__ map, u32* __restrict__ narrow,
-                                                      u64* __restrict__ wide, u32* __restrict__ err) {
+// test hook: the PTX bodies of p2e_f8.cuh on the device (op codes of tests/hostcheck hc_f8)
+__global__ void k_debug_f8(int op, size_t n, const u32* __restrict__ a, const u32* __restrict__ b, u32* __restrict__ out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  for (size_t s = blockIdx.y; s < n_slots; s += gridDim.y) {
-    const u32 m = map[s];
-    const u64 v = wit[s * ws + i];
-    if (m >> 31) {
-      if (wide) {
-        wide[(size_t)(m & 0x7fffffffu) * n + i] = v;
-      } else {
-        // derived form: check_sum column j of a MUL tuple is not shipped, the host rebuilds it from the carries of the
-        // CheckSum tuple that follows (a_j + c_{j-1} = 2^29 c_j exactly, c_j = b_j - 2^33; the last column is -c_15:
-        // gates/mul_nonnative.rs:411-427 with every constraint zero).  Verified here; a row that is not of this form
-        // (only rows whose generator already raised an error) is flagged.
-        const int j = (int)((m & 0x7fffffffu) % 17u);
-        const i64 cprev = j ? (i64)wit[(s + 16) * ws + i] - ((i64)1 << 33) : 0;
-        const i64 ccur = j < 16 ? (i64)wit[(s + 17) * ws + i] - ((i64)1 << 33) : 0;
-        const i64 expect = ccur * ((i64)1 << LB) - cprev;
-        if (gl_from_i64(expect) != v) atomicOr(&err[i], (u32)ERR_CARRY_RANGE);
-      }
-    } else if (m & (1u << 30)) {
-      // CheckSum carry b_j < 2^34: low word in its own narrow row; the 16 two-bit tops of the tuple share
-      // the narrow row after them, written by the thread that handles the tuple's first slot
-      const u32 row = m & 0x1fffffffu;
-      narrow[(size_t)row * n + i] = (u32)v;
-      if (m & (1u << 29)) {
-        u32 tops = 0;
-#pragma unroll
-        for (int j = 0; j < 16; j++) tops |= ((u32)(wit[(s + j) * ws + i] >> 32) & 3u) << (2 * j);
-        narrow[(size_t)(row + 16) * n + i] = tops;
-      }
-    } else {
-      narrow[(size_t)m * n + i] = (u32)v;
-    }
-  }
+  u32 x[NW], y[NW], r[NW];
+  for (int l = 0; l < NW; l++) { x[l] = a[9 * i + l]; y[l] = b[9 * i + l]; r[l] = 0; }
+  if (op == 0) f8_mul(x, y, r);
+  else if (op == 1) f8_sqr(x, r);
+  else if (op == 2) f8_add(x, y, r);
+  else if (op == 3) f8_sub(x, y, r);
+  else if (op == 4) f8_mul_small<2>(x, r);
+  else if (op == 5) f8_mul_small<3>(x, r);
+  else if (op == 6) f8_mul_small<4>(x, r);
+  else if (op == 7) f8_mul_small<8>(x, r);
+  else if (op == 8) { f8_copy(x, r); f8_canon(r); }
+  else if (op == 11) { F8 t = f8_inv_calls(f8w(x)); f8_copy(t.v, r); }
+  for (int l = 0; l < NW; l++) out[9 * i + l] = r[l];
+  out[9 * i + 8] = 0;
 }
 
 // ------------------------------------------------------------------------------------------
-// host side: device copies of the tapes, scratch, launch sequence
+// host side: per-device state (device copies of the tapes, scratch arenas, launch sequence)
 struct TapeOnDevice {
   bool ready = false;
-  int device = -1;
   DevTape d;
   void* blob = nullptr;
   size_t n_slots = 0;
+  u32 n_narrow = 0, n_wide = 0;
 };
-
-static std::map<int, TapeOnDevice> g_dev_tapes;
-static std::mutex g_mu;
-
-template <class T>
-static size_t align_up(size_t v) { return (v + alignof(T) - 1) / alignof(T) * alignof(T); }
-
-static int upload_tape(const Tape& t, TapeOnDevice& o) {
-  Context& c = ctx();
-  if (o.ready && o.device == c.device) return 0;
-  size_t off = 0;
-  auto reserve = [&](size_t bytes) { size_t at = (off + 15) / 16 * 16; off = at + bytes; return at; };
-  size_t o_prep = reserve(t.prep.size() * sizeof(PrepOp));
-  size_t o_pt = reserve(t.ptops.size() * sizeof(PtOp));
-  size_t o_chk = reserve(t.checks.size() * sizeof(Check));
-  size_t o_in = reserve(t.in_points.size() * sizeof(InputPoint));
-  size_t o_xr = reserve((t.extra_refs.size() + 1) * sizeof(Ref));
-  size_t o_cl = reserve((t.const_limbs.size() + 1) * sizeof(u32));
-  size_t o_cp = reserve((t.const_points.size() + 1) * sizeof(u32));
-  std::vector<unsigned char> host(off + 16, 0);
-  memcpy(&host[o_prep], t.prep.data(), t.prep.size() * sizeof(PrepOp));
-  memcpy(&host[o_pt], t.ptops.data(), t.ptops.size() * sizeof(PtOp));
-  memcpy(&host[o_chk], t.checks.data(), t.checks.size() * sizeof(Check));
-  memcpy(&host[o_in], t.in_points.data(), t.in_points.size() * sizeof(InputPoint));
-  memcpy(&host[o_xr], t.extra_refs.data(), t.extra_refs.size() * sizeof(Ref));
-  memcpy(&host[o_cl], t.const_limbs.data(), t.const_limbs.size() * sizeof(u32));
-  memcpy(&host[o_cp], t.const_points.data(), t.const_points.size() * sizeof(u32));
-  void* blob = nullptr;
-  P2E_CUDA(cudaMalloc(&blob, host.size()));
-  P2E_CUDA(cudaMemcpy(blob, host.data(), host.size(), cudaMemcpyHostToDevice));
-  unsigned char* b = (unsigned char*)blob;
-  o.d.prep = (const PrepOp*)(b + o_prep);
-  o.d.ptops = (const PtOp*)(b + o_pt);
-  o.d.checks = (const Check*)(b + o_chk);
-  o.d.in_points = (const InputPoint*)(b + o_in);
-  o.d.extra_refs = (const Ref*)(b + o_xr);
-  o.d.const_limbs = (const u32*)(b + o_cl);
-  o.d.const_points = (const u32*)(b + o_cp);
-  o.d.n_prep = (int)t.prep.size();
-  o.d.n_ptops = (int)t.ptops.size();
-  o.d.n_checks = (int)t.checks.size();
-  o.d.n_in_points = (int)t.in_points.size();
-  for (int i = 0; i < 16; i++) o.d.pre_pid[i] = t.pre_pid[i];
-  o.d.fixed_scalar = t.fixed_scalar;
-  o.d.msm_k1 = t.msm_k1;
-  o.d.msm_k2 = t.msm_k2;
-  o.d.fixed_round = t.fixed_round;
-  o.d.msm_round = t.msm_round;
-  o.d.fixed_table_base = t.fixed_table_base;
-  for (int c = 0; c < N_CHAINS; c++) { o.d.chain_begin[c] = t.chain_begin[c]; o.d.chain_end[c] = t.chain_end[c]; }
-  o.blob = blob;
-  o.n_slots = t.n_slots;
-  o.device = c.device;
-  o.ready = true;
-  return 0;
-}
 
 // One scratch arena per launching stream, so independent batches enqueued on different streams
 // can overlap (the per-signature kernels K0-K2 are latency-bound and leave most SMs idle).
@@ -1305,365 +970,35 @@ struct Arena {
   void* ptr = nullptr;
   size_t bytes = 0;
   bool used = false;
+  uint64_t last_use = 0;
   // internal streams: the latency-bound per-signature kernels (K0-K2) run at high priority so their
   // few small blocks are scheduled ahead of another batch's bandwidth-bound expansion (K3-K5)
   cudaStream_t hi = nullptr, lo = nullptr;
   cudaEvent_t ev_in = nullptr, ev_mid = nullptr, ev_out = nullptr;
 };
-constexpr int MAX_ARENAS = 16;
-static Arena g_arenas[MAX_ARENAS];
+constexpr int MAX_ARENAS = 64;
 
-static int get_arena(cudaStream_t st, size_t bytes, Arena** out) {
-  Arena* a = nullptr;
-  for (auto& x : g_arenas) if (x.used && x.stream == st) { a = &x; break; }
-  if (!a) {
-    for (auto& x : g_arenas) if (!x.used) { a = &x; break; }
-    if (!a) return set_error_msg("too many distinct streams in flight (max 16 chain arenas)");
-    int lo_p = 0, hi_p = 0;
-    P2E_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));     // numerically lower = higher priority
-    P2E_CUDA(cudaStreamCreateWithPriority(&a->hi, cudaStreamNonBlocking, hi_p));
-    P2E_CUDA(cudaStreamCreateWithPriority(&a->lo, cudaStreamNonBlocking, lo_p));
-    P2E_CUDA(cudaEventCreateWithFlags(&a->ev_in, cudaEventDisableTiming));
-    P2E_CUDA(cudaEventCreateWithFlags(&a->ev_mid, cudaEventDisableTiming));
-    P2E_CUDA(cudaEventCreateWithFlags(&a->ev_out, cudaEventDisableTiming));
-    a->used = true;
-    a->stream = st;
-  }
-  if (a->bytes < bytes) {
-    if (a->ptr) P2E_CUDA(cudaFree(a->ptr));
-    a->ptr = nullptr;
-    a->bytes = 0;
-    P2E_CUDA(cudaMalloc(&a->ptr, bytes));
-    a->bytes = bytes;
-  }
-  *out = a;
-  return 0;
+struct ChainState {
+  std::mutex mu;
+  std::map<int, TapeOnDevice> tapes;
+  Arena arenas[MAX_ARENAS];
+  uint64_t tick = 0;
+  bool profiling = false;
+  std::vector<cudaEvent_t> events;
+  // host-pointer compact path: copy stream + per-chunk events
+  cudaStream_t cp = nullptr;
+  cudaEvent_t ev_done[8] = {};
+};
+
+static ChainState& chain_state() {
+  Context& c = ctx();
+  static std::mutex create_mu;
+  std::lock_guard<std::mutex> lock(create_mu);
+  if (!c.chain) c.chain = new ChainState();
+  return *(ChainState*)c.chain;
 }
 
-void chain_release_device_tapes() {
-  for (auto& kv : g_dev_tapes) {
-    TapeOnDevice& o = kv.second;
-    if (o.ready && o.blob) cudaFree(o.blob);
-    o.ready = false;
-    o.blob = nullptr;
-  }
-  for (auto& a : g_arenas) {
-    if (a.ptr) cudaFree(a.ptr);
-    if (a.hi) cudaStreamDestroy(a.hi);
-    if (a.lo) cudaStreamDestroy(a.lo);
-    if (a.ev_in) cudaEventDestroy(a.ev_in);
-    if (a.ev_mid) cudaEventDestroy(a.ev_mid);
-    if (a.ev_out) cudaEventDestroy(a.ev_out);
-    a = Arena();
-  }
-}
-
-static bool g_profiling = false;
-static std::vector<cudaEvent_t> g_events;
-static cudaStream_t g_event_stream = nullptr;
-static void prof_mark(cudaStream_t st) {
-  if (!g_profiling) return;
-  cudaEvent_t e;
-  cudaEventCreate(&e);
-  cudaEventRecord(e, st);
-  g_events.push_back(e);
-  g_event_stream = st;
-}
-
-// replay kernel: 0 one thread per (signature, chain); 1 four lanes + shared memory (measured slower,
-// profiles/r01_notes.md); 2 two lanes + register shuffles.  P2E_CHAIN_REPLAY = serial | coop | duo.
-static int replay_mode() {
-  const char* e = getenv("P2E_CHAIN_REPLAY");
-  if (!e) return P2E_DEFAULT_REPLAY;
-  return e[0] == 'c' ? 1 : e[0] == 'd' ? 2 : 0;
-}
-
-// K2 form: tree (one inversion per signature, default) or groups (one inversion per group).
-// P2E_CHAIN_INVERT = tree | groups
-static bool invert_tree() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("P2E_CHAIN_INVERT");
-    v = (e && e[0] == 'g') ? 0 : 1;
-  }
-  return v == 1;
-}
-
-static unsigned inv_groups() {
-  static int g = 0;
-  if (!g) {
-    const char* e = getenv("P2E_CHAIN_INV_GROUPS");
-    g = e ? atoi(e) : (invert_tree() ? 16 : 8);
-    if (g < 1) g = 1;
-    if (g > 32) g = 32;
-  }
-  return (unsigned)g;
-}
-
-// threads per block of the two full-GPU kernels (K3, K4): smaller blocks pack better next to the
-// resident one-warp blocks of other batches' K0-K2 (register file granularity)
-static unsigned wide_tpb() {
-  static unsigned v = 0;
-  if (!v) {
-    const char* e = getenv("P2E_CHAIN_WIDE_TPB");
-    v = e ? (unsigned)atoi(e) : 128u;
-    if (v != 32 && v != 64 && v != 128) v = 128;
-  }
-  return v;
-}
-
-// dynamic shared memory (bytes, unused by the kernels) requested for K3 / K4 to cap their CTAs per SM; 0 = no cap
-__global__ void k_chain_affine(ChainArgs A);
-__global__ void k_chain_expand(ChainArgs A);
-static size_t wide_smem() {
-  static long v = -1;
-  if (v < 0) {
-    const char* e = getenv("P2E_CHAIN_WIDE_SMEM");
-    v = e ? atol(e) : 0;
-    if (v < 0 || v > 200 * 1024) v = 0;
-    if (v > 48 * 1024) {
-      cudaFuncSetAttribute(k_chain_affine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v);
-      cudaFuncSetAttribute(k_chain_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v);
-    }
-  }
-  return (size_t)v;
-}
-
-// diagnostic only (wrong results when not 63): bit mask of the kernels to launch
-// 1 prep, 2 replay + join, 4 invert, 8 affine, 16 expand, 32 checks
-static unsigned phase_mask() {
-  const char* e = getenv("P2E_CHAIN_PHASES");     // read per call: the diagnostic script flips it in-process
-  return e ? (unsigned)atoi(e) : 63u;
-}
-
-static size_t chunk_capacity() {
-  const char* e = getenv("P2E_CHAIN_CHUNK");
-  size_t v = e ? (size_t)atoll(e) : 0;
-  return v ? v : 65536;       // 81 KB of scratch per signature: 5.3 GB per arena at full chunks (180 GB HBM); larger chunks
-                              // give the one-warp-per-SM kernels more resident warps (glv, 2^16 chains: 21.1 -> 14.3 ms)
-}
-
-static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* ins, int n_in, size_t is, uint64_t* out,
-                    size_t os, uint32_t* err, void* stream) {
-  int rc = ensure_ready();
-  if (rc) return rc;
-  if (n == 0) return 0;
-  if (is < n || os < n) return set_error_msg("stride < n");
-  if (n_in > MAX_TAPE_INPUTS) return set_error_msg("tape has more than 16 inputs");
-  std::lock_guard<std::mutex> lock(g_mu);
-  TapeOnDevice& o = g_dev_tapes[which];
-  if ((rc = upload_tape(t, o))) return rc;
-  cudaStream_t st = pick_stream(stream);
-  const size_t cap = n < chunk_capacity() ? n : chunk_capacity();
-  const size_t np = (size_t)o.d.n_ptops + o.d.n_in_points, no = (size_t)o.d.n_ptops;
-  // scratch layout (u32 words)
-  size_t words = (np * 27 * 2 + no * 9) * cap;      // JX JY JZ AX AY ZC + ZINV
-  const unsigned G = inv_groups();
-  size_t bytes = words * 4 + no * cap * (4 + 4 + 1) + ((size_t)G * 18 + 1) * cap * 4 + 64;
-  Arena* arena = nullptr;
-  if ((rc = get_arena(st, bytes, &arena))) return rc;
-  void* scratch = arena->ptr;
-  // profiling keeps everything on the caller's stream so the events bracket each kernel
-  const bool split = !g_profiling && getenv("P2E_CHAIN_NO_PRIORITY") == nullptr;
-  cudaStream_t s_hi = split ? arena->hi : st, s_lo = split ? arena->lo : st;
-  if (split) {
-    P2E_CUDA(cudaEventRecord(arena->ev_in, st));
-    P2E_CUDA(cudaStreamWaitEvent(s_hi, arena->ev_in, 0));
-    P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_in, 0));    // orders this call after the previous one's K3-K5 reads
-  }
-  ChainArgs A;
-  A.t = o.d;
-  A.is = is;
-  A.os = os;
-  A.cap = cap;
-  u32* w = (u32*)scratch;
-  A.JX = w; w += np * 9 * cap;
-  A.JY = w; w += np * 9 * cap;
-  A.JZ = w; w += np * 9 * cap;
-  A.AX = w; w += np * 9 * cap;
-  A.AY = w; w += np * 9 * cap;
-  A.ZC = w; w += np * 9 * cap;
-  A.ZINV = w; w += no * 9 * cap;
-  A.SRC1 = (int32_t*)w; w += no * cap;
-  A.SRC2 = (int32_t*)w; w += no * cap;
-  A.FLG = (uint8_t*)w;
-  w += (no * cap + 3) / 4;
-  A.GP = w; w += (size_t)G * 9 * cap;
-  A.GI = w; w += (size_t)G * 9 * cap;
-  A.BAD = w;
-  for (size_t c0 = 0; c0 < n; c0 += cap) {
-    size_t cn = (n - c0 < cap) ? n - c0 : cap;
-    A.n = cn;
-    for (int k = 0; k < MAX_TAPE_INPUTS; k++) A.in[k] = (k < n_in) ? ins[k] + c0 : nullptr;
-    A.out = out + c0;
-    A.err = err + c0;
-    unsigned g32 = (unsigned)((cn + 31) / 32);
-    if (g_profiling && c0 == 0) {
-      for (auto e : g_events) cudaEventDestroy(e);
-      g_events.clear();
-    }
-    const bool prof = g_profiling && c0 == 0;
-    if (prof) prof_mark(st);
-    const int n_rounds = (int)t.n_rounds;
-    const unsigned pm = phase_mask();
-    for (int round = 0; round < n_rounds; round++) {
-      // Round r: generators of round r (K0), then the curve ops of round r (K1-K4).  A later round
-      // consumes coordinates written by this round's expansion, so it waits for the low-priority stream.
-      A.round = round;
-      if (split && round > 0) {
-        P2E_CUDA(cudaEventRecord(arena->ev_out, s_lo));
-        P2E_CUDA(cudaStreamWaitEvent(s_hi, arena->ev_out, 0));
-      }
-      if (pm & 1) k_prep<<<g32, 32, 0, s_hi>>>(A);
-      if (prof) prof_mark(st);
-      if (no) {
-        if (!(pm & 2)) {
-        } else if (replay_mode() == 2) {
-          const unsigned g_duo = (unsigned)((2 * cn + 63) / 64);
-          k_chain_replay_duo<<<dim3(g_duo, 2), 64, 0, s_hi>>>(A, 0);      // 2 lanes per (signature, chain)
-          if (prof) prof_mark(st);
-          if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay_duo<<<dim3(g_duo, 1), 64, 0, s_hi>>>(A, 2);   // join
-        } else if (replay_mode() == 1) {
-          k_chain_replay_coop<<<dim3(g32, 2), 128, 0, s_hi>>>(A, 0);    // 4 lanes per (signature, chain)
-          if (prof) prof_mark(st);
-          if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay_coop<<<dim3(g32, 1), 128, 0, s_hi>>>(A, 2);   // join
-        } else {
-          k_chain_replay<<<dim3(g32, 2), 32, 0, s_hi>>>(A, 0);    // fixed-base and msm chains side by side
-          if (prof) prof_mark(st);
-          if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g32, 1), 32, 0, s_hi>>>(A, 2);   // join
-        }
-        if (prof) prof_mark(st);
-        if (!(pm & 4)) {
-        } else if (invert_tree()) {
-          k_chain_invert_up<<<dim3(g32, G), 32, 0, s_hi>>>(A);
-          k_chain_invert_mid<<<g32, 32, 0, s_hi>>>(A, (int)G);
-          k_chain_invert_down<<<dim3(g32, G), 32, 0, s_hi>>>(A);
-        } else {
-          k_chain_invert<<<dim3(g32, G), 32, 0, s_hi>>>(A);
-        }
-        if (prof) prof_mark(st);
-        if (split) {
-          P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
-          P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
-        }
-        const unsigned tpb = wide_tpb(), gw = (unsigned)((cn + tpb - 1) / tpb);
-        // Occupancy throttle for the two full-GPU kernels: unused dynamic shared memory caps their CTAs per SM so
-        // that the latency-bound kernels of OTHER batches (high-priority streams) find registers on every SM and
-        // run next to them instead of after them (K4 at 3 CTAs / SM owns the whole register file).
-        const size_t wsm = wide_smem();
-        if (pm & 8) k_chain_affine<<<dim3(gw, (unsigned)no), tpb, wsm, s_lo>>>(A);
-        if (prof) prof_mark(st);
-        if (pm & 16) k_chain_expand<<<dim3(gw, (unsigned)no), tpb, wsm, s_lo>>>(A);
-        if (prof) prof_mark(st);
-      } else if (split) {
-        P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
-        P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
-      }
-    }
-    if (pm & 32) k_chain_checks<<<g32, 32, 0, s_lo>>>(A);
-    if (prof) prof_mark(st);
-    if (split && c0 + cap < n) {
-      // next chunk reuses the scratch: its K0-K2 must not start before this chunk's K3-K5 are done
-      P2E_CUDA(cudaEventRecord(arena->ev_out, s_lo));
-      P2E_CUDA(cudaStreamWaitEvent(s_hi, arena->ev_out, 0));
-    }
-    P2E_CUDA(cudaGetLastError());
-  }
-  if (split) {
-    P2E_CUDA(cudaEventRecord(arena->ev_out, s_lo));
-    P2E_CUDA(cudaStreamWaitEvent(st, arena->ev_out, 0));
-  }
-  return 0;
-}
-
-static size_t tape_layout(const Tape& t, uint32_t* kinds, uint32_t* offs) {
-  if (kinds && offs) {
-    for (size_t i = 0; i < t.gen_kind.size(); i++) {
-      kinds[i] = t.gen_kind[i];
-      offs[i] = t.gen_off[i];
-    }
-  }
-  return t.gen_kind.size();
-}
-
-template <class Launch>
-static int run_tape_host(const Tape& t, size_t n, const uint64_t* const* ins, int n_in, uint64_t* out, uint32_t* err,
-                         Launch launch) {
-  int rc = ensure_ready();
-  if (rc) return rc;
-  if (n == 0) return 0;
-  cudaStream_t st = ctx().stream;
-  void *din = nullptr, *dout = nullptr, *derr = nullptr;
-  if ((rc = get_scratch(0, (size_t)n_in * 9 * n * 8, &din))) return rc;
-  if ((rc = get_scratch(1, (size_t)t.n_slots * n * 8, &dout))) return rc;
-  if ((rc = get_scratch(2, n * 4, &derr))) return rc;
-  const uint64_t* dptr[MAX_TAPE_INPUTS];
-  for (int k = 0; k < n_in; k++) {
-    dptr[k] = (const uint64_t*)din + (size_t)k * 9 * n;
-    P2E_CUDA(cudaMemcpyAsync((uint64_t*)din + (size_t)k * 9 * n, ins[k], 9 * n * 8, cudaMemcpyHostToDevice, st));
-  }
-  if ((rc = launch(dptr, (uint64_t*)dout, (uint32_t*)derr, (void*)st))) return rc;
-  P2E_CUDA(cudaMemcpyAsync(out, dout, (size_t)t.n_slots * n * 8, cudaMemcpyDeviceToHost, st));
-  if (err) P2E_CUDA(cudaMemcpyAsync(err, derr, n * 4, cudaMemcpyDeviceToHost, st));
-  P2E_CUDA(cudaStreamSynchronize(st));
-  return 0;
-}
-
-}  // namespace p2e
-
-using namespace p2e;
-
-extern "C" {
-
-int p2e_set_profiling(int on) {
-  g_profiling = on != 0;
-  return 0;
-}
-
-int p2e_last_kernel_times(float* ms, int cap) {
-  int rc = ensure_ready();
-  if (rc) return rc;
-  if (g_events.size() < 2) return 0;
-  P2E_CUDA(cudaEventSynchronize(g_events.back()));
-  int k = 0;
-  for (size_t j = 0; j + 1 < g_events.size() && k < cap; j++, k++) {
-    float t = 0;
-    P2E_CUDA(cudaEventElapsedTime(&t, g_events[j], g_events[j + 1]));
-    ms[k] = t;
-  }
-  return k;
-}
-
-static int bad_tape(int tape) {
-  if (!tape_exists(tape)) return set_error_msg("unknown tape id");
-  return 0;
-}
-
-size_t p2e_tape_slots(int tape) { return bad_tape(tape) ? 0 : get_tape(tape).n_slots; }
-int p2e_tape_inputs(int tape) { return bad_tape(tape) ? -1 : (int)get_tape(tape).n_inputs; }
-size_t p2e_tape_layout(int tape, uint32_t* kinds, uint32_t* offsets) {
-  return bad_tape(tape) ? 0 : tape_layout(get_tape(tape), kinds, offsets);
-}
-
-int p2e_tape_witness_dev(int tape, size_t n, const uint64_t* const* inputs, size_t is, uint64_t* out, size_t os,
-                         uint32_t* err, void* stream) {
-  if (bad_tape(tape)) return -1;
-  const Tape& t = get_tape(tape);
-  return run_tape(tape, t, n, inputs, (int)t.n_inputs, is, out, os, err, stream);
-}
-
-int p2e_tape_witness(int tape, size_t n, const uint64_t* const* inputs, uint64_t* out, uint32_t* err) {
-  if (bad_tape(tape)) return -1;
-  const Tape& t = get_tape(tape);
-  const int n_in = (int)t.n_inputs;
-  return run_tape_host(t, n, inputs, n_in, out, err, [&](const uint64_t** d, uint64_t* o, uint32_t* e, void* st) {
-    return run_tape(tape, t, n, d, n_in, n, o, n, e, st);
-  });
-}
-
-size_t p2e_tape_compact_layout(int tape, uint32_t* map, uint32_t* narrow_slots, uint32_t* wide_slots) {
-  if (bad_tape(tape)) return 0;
-  const Tape& t = get_tape(tape);
+static void compact_layout(const Tape& t, uint32_t* map, uint32_t* narrow_slots, uint32_t* wide_slots) {
   uint32_t nn = 0, nw = 0;
   for (size_t g = 0; g < t.gen_kind.size(); g++) {
     const uint32_t kind = t.gen_kind[g], off = t.gen_off[g];
@@ -1684,6 +1019,412 @@ size_t p2e_tape_compact_layout(int tape, uint32_t* map, uint32_t* narrow_slots, 
   }
   if (narrow_slots) *narrow_slots = nn;
   if (wide_slots) *wide_slots = nw;
+}
+
+static int upload_tape(const Tape& t, TapeOnDevice& o) {
+  if (o.ready) return 0;
+  // compact layout + per-curve-op rows; every Ref must name plain value slots (they are read back as u32 rows)
+  std::vector<u32> cmap(t.n_slots + 1, 0), nrow(t.ptops.size() + 1, 0), wrow(t.ptops.size() + 1, 0);
+  compact_layout(t, cmap.data(), &o.n_narrow, &o.n_wide);
+  auto ref_ok = [&](const Ref& r) {
+    if (r.space == SP_OUT)
+      for (uint32_t l = 0; l < r.nl; l++) if (r.off + l >= t.n_slots || (cmap[r.off + l] >> 29)) return false;
+    if (r.bspace == SP_OUT && (r.boff >= t.n_slots || (cmap[r.boff] >> 29))) return false;
+    return true;
+  };
+  bool ok = ref_ok(t.fixed_scalar) && ref_ok(t.msm_k1) && ref_ok(t.msm_k2);
+  for (auto& p : t.prep) ok = ok && ref_ok(p.a) && ref_ok(p.b);
+  for (auto& r : t.extra_refs) ok = ok && ref_ok(r);
+  for (auto& c : t.checks) ok = ok && ref_ok(c.a) && ref_ok(c.b);
+  for (auto& p : t.in_points) ok = ok && ref_ok(p.x) && ref_ok(p.y);
+  if (!ok) return set_error_msg("tape: a reference names a check_sum / carry slot (not representable in the compact format)");
+  for (size_t k = 0; k < t.ptops.size(); k++) {
+    const PtOp& op = t.ptops[k];
+    nrow[k] = cmap[op.slot];
+    const uint32_t first_cs = op.slot + (op.type == PT_DBL ? 28u : 38u) + 18u;
+    wrow[k] = first_cs < t.n_slots ? (cmap[first_cs] & 0x7fffffffu) : 0u;
+  }
+  std::vector<u32> cp8(t.const_points.size() / 18 * 16 + 16, 0);
+  for (size_t p = 0; p < t.const_points.size() / 18; p++) {
+    u32 x[NL], y[NL], x8[NW], y8[NW];
+    for (int l = 0; l < NL; l++) { x[l] = t.const_points[p * 18 + l]; y[l] = t.const_points[p * 18 + NL + l]; }
+    f8_from_l29(x, x8);
+    f8_from_l29(y, y8);
+    for (int l = 0; l < NW; l++) { cp8[p * 16 + l] = x8[l]; cp8[p * 16 + NW + l] = y8[l]; }
+  }
+  size_t off = 0;
+  auto reserve = [&](size_t bytes) { size_t at = (off + 15) / 16 * 16; off = at + bytes; return at; };
+  size_t o_prep = reserve(t.prep.size() * sizeof(PrepOp));
+  size_t o_pt = reserve(t.ptops.size() * sizeof(PtOp));
+  size_t o_chk = reserve(t.checks.size() * sizeof(Check));
+  size_t o_in = reserve(t.in_points.size() * sizeof(InputPoint));
+  size_t o_xr = reserve((t.extra_refs.size() + 1) * sizeof(Ref));
+  size_t o_cl = reserve((t.const_limbs.size() + 1) * sizeof(u32));
+  size_t o_cp = reserve((t.const_points.size() + 1) * sizeof(u32));
+  size_t o_c8 = reserve(cp8.size() * sizeof(u32));
+  size_t o_cm = reserve(cmap.size() * sizeof(u32));
+  size_t o_nr = reserve(nrow.size() * sizeof(u32));
+  size_t o_wr = reserve(wrow.size() * sizeof(u32));
+  std::vector<unsigned char> host(off + 16, 0);
+  memcpy(&host[o_prep], t.prep.data(), t.prep.size() * sizeof(PrepOp));
+  memcpy(&host[o_pt], t.ptops.data(), t.ptops.size() * sizeof(PtOp));
+  memcpy(&host[o_chk], t.checks.data(), t.checks.size() * sizeof(Check));
+  memcpy(&host[o_in], t.in_points.data(), t.in_points.size() * sizeof(InputPoint));
+  memcpy(&host[o_xr], t.extra_refs.data(), t.extra_refs.size() * sizeof(Ref));
+  memcpy(&host[o_cl], t.const_limbs.data(), t.const_limbs.size() * sizeof(u32));
+  memcpy(&host[o_cp], t.const_points.data(), t.const_points.size() * sizeof(u32));
+  memcpy(&host[o_c8], cp8.data(), cp8.size() * sizeof(u32));
+  memcpy(&host[o_cm], cmap.data(), cmap.size() * sizeof(u32));
+  memcpy(&host[o_nr], nrow.data(), nrow.size() * sizeof(u32));
+  memcpy(&host[o_wr], wrow.data(), wrow.size() * sizeof(u32));
+  void* blob = nullptr;
+  P2E_CUDA(cudaMalloc(&blob, host.size()));
+  P2E_CUDA(cudaMemcpy(blob, host.data(), host.size(), cudaMemcpyHostToDevice));
+  unsigned char* b = (unsigned char*)blob;
+  o.d.prep = (const PrepOp*)(b + o_prep);
+  o.d.ptops = (const PtOp*)(b + o_pt);
+  o.d.checks = (const Check*)(b + o_chk);
+  o.d.in_points = (const InputPoint*)(b + o_in);
+  o.d.extra_refs = (const Ref*)(b + o_xr);
+  o.d.const_limbs = (const u32*)(b + o_cl);
+  o.d.const_points = (const u32*)(b + o_cp);
+  o.d.const_points8 = (const u32*)(b + o_c8);
+  o.d.cmap = (const u32*)(b + o_cm);
+  o.d.pt_nrow = (const u32*)(b + o_nr);
+  o.d.pt_wrow = (const u32*)(b + o_wr);
+  o.d.n_prep = (int)t.prep.size();
+  o.d.n_ptops = (int)t.ptops.size();
+  o.d.n_checks = (int)t.checks.size();
+  o.d.n_in_points = (int)t.in_points.size();
+  for (int i = 0; i < 16; i++) o.d.pre_pid[i] = t.pre_pid[i];
+  o.d.fixed_scalar = t.fixed_scalar;
+  o.d.msm_k1 = t.msm_k1;
+  o.d.msm_k2 = t.msm_k2;
+  o.d.fixed_round = t.fixed_round;
+  o.d.msm_round = t.msm_round;
+  o.d.fixed_table_base = t.fixed_table_base;
+  for (int c = 0; c < N_CHAINS; c++) { o.d.chain_begin[c] = t.chain_begin[c]; o.d.chain_end[c] = t.chain_end[c]; }
+  o.blob = blob;
+  o.n_slots = t.n_slots;
+  o.ready = true;
+  return 0;
+}
+
+static void arena_free(Arena& a) {
+  if (a.ptr) cudaFree(a.ptr);
+  if (a.hi) cudaStreamDestroy(a.hi);
+  if (a.lo) cudaStreamDestroy(a.lo);
+  if (a.ev_in) cudaEventDestroy(a.ev_in);
+  if (a.ev_mid) cudaEventDestroy(a.ev_mid);
+  if (a.ev_out) cudaEventDestroy(a.ev_out);
+  a = Arena();
+}
+
+// The arena of a caller stream; a stream never seen before takes a free entry or evicts the least recently used
+// arena whose work has completed (a long-running host that creates a stream per job must not run out).
+static int get_arena(ChainState& S, cudaStream_t st, size_t bytes, Arena** out) {
+  Arena* a = nullptr;
+  for (auto& x : S.arenas) if (x.used && x.stream == st) { a = &x; break; }
+  if (!a) {
+    for (auto& x : S.arenas) if (!x.used) { a = &x; break; }
+    if (!a) {
+      Arena* lru = nullptr;
+      for (auto& x : S.arenas)
+        if (cudaEventQuery(x.ev_out) == cudaSuccess && (!lru || x.last_use < lru->last_use)) lru = &x;
+      if (!lru) return set_error_msg("chain: 64 streams have work in flight (one scratch arena each); synchronise one of them or call p2e_stream_release");
+      arena_free(*lru);
+      a = lru;
+    }
+    int lo_p = 0, hi_p = 0;
+    P2E_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));     // numerically lower = higher priority
+    P2E_CUDA(cudaStreamCreateWithPriority(&a->hi, cudaStreamNonBlocking, hi_p));
+    P2E_CUDA(cudaStreamCreateWithPriority(&a->lo, cudaStreamNonBlocking, lo_p));
+    P2E_CUDA(cudaEventCreateWithFlags(&a->ev_in, cudaEventDisableTiming));
+    P2E_CUDA(cudaEventCreateWithFlags(&a->ev_mid, cudaEventDisableTiming));
+    P2E_CUDA(cudaEventCreateWithFlags(&a->ev_out, cudaEventDisableTiming));
+    a->used = true;
+    a->stream = st;
+  }
+  if (a->bytes < bytes) {
+    if (a->ptr) {
+      P2E_CUDA(cudaEventSynchronize(a->ev_out));   // the previous call on this stream may still read the old buffer
+      P2E_CUDA(cudaFree(a->ptr));
+    }
+    a->ptr = nullptr;
+    a->bytes = 0;
+    P2E_CUDA(cudaMalloc(&a->ptr, bytes));
+    a->bytes = bytes;
+  }
+  a->last_use = ++S.tick;
+  *out = a;
+  return 0;
+}
+
+void chain_release_device(Context& c) {
+  if (!c.chain) return;
+  ChainState* S = (ChainState*)c.chain;
+  for (auto& kv : S->tapes)
+    if (kv.second.ready && kv.second.blob) cudaFree(kv.second.blob);
+  for (auto& a : S->arenas) arena_free(a);
+  for (auto e : S->events) cudaEventDestroy(e);
+  if (S->cp) cudaStreamDestroy(S->cp);
+  for (auto& e : S->ev_done) if (e) cudaEventDestroy(e);
+  delete S;
+  c.chain = nullptr;
+}
+
+static void prof_mark(ChainState& S, cudaStream_t st) {
+  if (!S.profiling) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, st);
+  S.events.push_back(e);
+}
+
+static size_t chunk_capacity() {
+  long v = option(OPT_CHAIN_CHUNK);
+  return v > 0 ? (size_t)v : 65536;   // 75 KB of scratch per signature: 4.9 GB per arena at full chunks (180 GB HBM); larger chunks
+                                      // give the one-warp-per-SM kernels more resident warps
+}
+
+struct OutSpec {
+  int fmt;
+  uint64_t* out;      // plain
+  uint32_t* nar;      // compact
+  uint64_t* wide;
+  size_t os;
+};
+
+static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* ins, int n_in, size_t is, const OutSpec& os,
+                    uint32_t* err, void* stream) {
+  int rc = ensure_ready();
+  if (rc) return rc;
+  if (n == 0) return 0;
+  if (is < n || os.os < n) return set_error_msg("stride < n");
+  if (n_in > MAX_TAPE_INPUTS) return set_error_msg("tape has more than 16 inputs");
+  ChainState& S = chain_state();
+  std::lock_guard<std::mutex> lock(S.mu);
+  TapeOnDevice& o = S.tapes[which];
+  if ((rc = upload_tape(t, o))) return rc;
+  cudaStream_t st = pick_stream(stream);
+  const size_t cap = n < chunk_capacity() ? n : chunk_capacity();
+  const size_t np = (size_t)o.d.n_ptops + o.d.n_in_points, no = (size_t)o.d.n_ptops;
+  // scratch layout (u32 words)
+  size_t words = (np * (4 * NW + 2 * NL) + no * NW) * cap;      // JX JY JZ ZC + AX AY + ZINV
+  const unsigned G = INV_GROUPS;
+  size_t bytes = words * 4 + no * cap * (4 + 4 + 1) + ((size_t)G * 2 * NW + 1) * cap * 4 + 64;
+  Arena* arena = nullptr;
+  if ((rc = get_arena(S, st, bytes, &arena))) return rc;
+  void* scratch = arena->ptr;
+  // profiling keeps everything on the caller's stream so the events bracket each kernel
+  const bool split = !S.profiling;
+  cudaStream_t s_hi = split ? arena->hi : st, s_lo = split ? arena->lo : st;
+  if (split) {
+    P2E_CUDA(cudaEventRecord(arena->ev_in, st));
+    P2E_CUDA(cudaStreamWaitEvent(s_hi, arena->ev_in, 0));
+    P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_in, 0));    // orders this call after the previous one's K3-K5 reads
+  }
+  ChainArgs A;
+  A.t = o.d;
+  A.is = is;
+  A.fmt = os.fmt;
+  A.os = os.os;
+  A.cap = cap;
+  u32* w = (u32*)scratch;
+  A.JX = w; w += np * NW * cap;
+  A.JY = w; w += np * NW * cap;
+  A.JZ = w; w += np * NW * cap;
+  A.ZC = w; w += np * NW * cap;
+  A.AX = w; w += np * NL * cap;
+  A.AY = w; w += np * NL * cap;
+  A.ZINV = w; w += no * NW * cap;
+  A.SRC1 = (int32_t*)w; w += no * cap;
+  A.SRC2 = (int32_t*)w; w += no * cap;
+  A.FLG = (uint8_t*)w;
+  w += (no * cap + 3) / 4;
+  A.GP = w; w += (size_t)G * NW * cap;
+  A.GI = w; w += (size_t)G * NW * cap;
+  A.BAD = w;
+  for (size_t c0 = 0; c0 < n; c0 += cap) {
+    size_t cn = (n - c0 < cap) ? n - c0 : cap;
+    A.n = cn;
+    for (int k = 0; k < MAX_TAPE_INPUTS; k++) A.in[k] = (k < n_in) ? ins[k] + c0 : nullptr;
+    A.out = os.out ? os.out + c0 : nullptr;
+    A.nar = os.nar ? os.nar + c0 : nullptr;
+    A.wide = os.wide ? os.wide + c0 : nullptr;
+    A.err = err + c0;
+    unsigned g32 = (unsigned)((cn + 31) / 32);
+    const bool prof = S.profiling && c0 == 0;
+    if (prof) {
+      for (auto e : S.events) cudaEventDestroy(e);
+      S.events.clear();
+      prof_mark(S, st);
+    }
+    const int n_rounds = (int)t.n_rounds;
+    for (int round = 0; round < n_rounds; round++) {
+      // Round r: generators of round r (K0), then the curve ops of round r (K1-K4).  A later round
+      // consumes coordinates written by this round's expansion, so it waits for the low-priority stream.
+      A.round = round;
+      if (split && round > 0) {
+        P2E_CUDA(cudaEventRecord(arena->ev_out, s_lo));
+        P2E_CUDA(cudaStreamWaitEvent(s_hi, arena->ev_out, 0));
+      }
+      k_prep<<<g32, 32, 0, s_hi>>>(A);
+      if (prof) prof_mark(S, st);
+      if (no) {
+        const unsigned g_duo = (unsigned)((2 * cn + 63) / 64);
+        k_chain_replay<<<dim3(g_duo, 2), 64, 0, s_hi>>>(A, 0);      // fixed-base and msm chains side by side, 2 lanes each
+        if (prof) prof_mark(S, st);
+        if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g_duo, 1), 64, 0, s_hi>>>(A, 2);   // join
+        if (prof) prof_mark(S, st);
+        k_chain_invert_up<<<dim3(g32, G), 32, 0, s_hi>>>(A);
+        k_chain_invert_mid<<<g32, 32, 0, s_hi>>>(A, (int)G);
+        k_chain_invert_down<<<dim3(g32, G), 32, 0, s_hi>>>(A);
+        if (prof) prof_mark(S, st);
+        if (split) {
+          P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
+          P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
+        }
+        const unsigned tpb = 128, gw = (unsigned)((cn + tpb - 1) / tpb);
+        k_chain_affine<<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
+        if (prof) prof_mark(S, st);
+        if (A.fmt == FMT_PLAIN) k_chain_expand<FMT_PLAIN><<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
+        else k_chain_expand<FMT_COMPACT><<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
+        if (prof) prof_mark(S, st);
+      } else if (split) {
+        P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
+        P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
+      }
+    }
+    k_chain_checks<<<g32, 32, 0, s_lo>>>(A);
+    if (prof) prof_mark(S, st);
+    if (split && c0 + cap < n) {
+      // next chunk reuses the scratch: its K0-K2 must not start before this chunk's K3-K5 are done
+      P2E_CUDA(cudaEventRecord(arena->ev_out, s_lo));
+      P2E_CUDA(cudaStreamWaitEvent(s_hi, arena->ev_out, 0));
+    }
+    P2E_CUDA(cudaGetLastError());
+  }
+  if (split) {
+    P2E_CUDA(cudaEventRecord(arena->ev_out, s_lo));
+    P2E_CUDA(cudaStreamWaitEvent(st, arena->ev_out, 0));
+  } else {
+    P2E_CUDA(cudaEventRecord(arena->ev_out, st));
+  }
+  return 0;
+}
+
+static size_t tape_layout(const Tape& t, uint32_t* kinds, uint32_t* offs) {
+  if (kinds && offs) {
+    for (size_t i = 0; i < t.gen_kind.size(); i++) {
+      kinds[i] = t.gen_kind[i];
+      offs[i] = t.gen_off[i];
+    }
+  }
+  return t.gen_kind.size();
+}
+
+}  // namespace p2e
+
+using namespace p2e;
+
+extern "C" {
+
+int p2e_set_profiling(int on) {
+  int rc = ensure_ready();
+  if (rc) return rc;
+  chain_state().profiling = on != 0;
+  return 0;
+}
+
+int p2e_last_kernel_times(float* ms, int cap) {
+  int rc = ensure_ready();
+  if (rc) return rc;
+  ChainState& S = chain_state();
+  std::lock_guard<std::mutex> lock(S.mu);
+  if (S.events.size() < 2) return 0;
+  P2E_CUDA(cudaEventSynchronize(S.events.back()));
+  int k = 0;
+  for (size_t j = 0; j + 1 < S.events.size() && k < cap; j++, k++) {
+    float t = 0;
+    P2E_CUDA(cudaEventElapsedTime(&t, S.events[j], S.events[j + 1]));
+    ms[k] = t;
+  }
+  return k;
+}
+
+int p2e_stream_release(void* stream) {
+  int rc = ensure_ready();
+  if (rc) return rc;
+  ChainState& S = chain_state();
+  std::lock_guard<std::mutex> lock(S.mu);
+  cudaStream_t st = pick_stream(stream);
+  for (auto& a : S.arenas)
+    if (a.used && a.stream == st) {
+      P2E_CUDA(cudaEventSynchronize(a.ev_out));
+      arena_free(a);
+    }
+  return 0;
+}
+
+static int bad_tape(int tape) {
+  if (!tape_exists(tape)) return set_error_msg("unknown tape id");
+  return 0;
+}
+
+size_t p2e_tape_slots(int tape) { return bad_tape(tape) ? 0 : get_tape(tape).n_slots; }
+int p2e_tape_inputs(int tape) { return bad_tape(tape) ? -1 : (int)get_tape(tape).n_inputs; }
+size_t p2e_tape_layout(int tape, uint32_t* kinds, uint32_t* offsets) {
+  return bad_tape(tape) ? 0 : tape_layout(get_tape(tape), kinds, offsets);
+}
+
+int p2e_tape_witness_dev(int tape, size_t n, const uint64_t* const* inputs, size_t is, uint64_t* out, size_t os,
+                         uint32_t* err, void* stream) {
+  if (bad_tape(tape)) return -1;
+  const Tape& t = get_tape(tape);
+  OutSpec o{FMT_PLAIN, out, nullptr, nullptr, os};
+  return run_tape(tape, t, n, inputs, (int)t.n_inputs, is, o, err, stream);
+}
+
+int p2e_tape_witness_compact_dev(int tape, size_t n, const uint64_t* const* inputs, size_t is, uint32_t* narrow,
+                                 uint64_t* wide, size_t os, uint32_t* err, void* stream) {
+  if (bad_tape(tape)) return -1;
+  if (n && !narrow) return set_error_msg("tape_witness_compact_dev: NULL narrow matrix");
+  const Tape& t = get_tape(tape);
+  OutSpec o{FMT_COMPACT, nullptr, narrow, wide, os};
+  return run_tape(tape, t, n, inputs, (int)t.n_inputs, is, o, err, stream);
+}
+
+int p2e_tape_witness(int tape, size_t n, const uint64_t* const* inputs, uint64_t* out, uint32_t* err) {
+  if (bad_tape(tape)) return -1;
+  int rc = ensure_ready();
+  if (rc) return rc;
+  if (n == 0) return 0;
+  P2E_HOST_LOCK();
+  const Tape& t = get_tape(tape);
+  const int n_in = (int)t.n_inputs;
+  cudaStream_t st = ctx().stream;
+  void *din = nullptr, *dout = nullptr, *derr = nullptr;
+  if ((rc = get_scratch(0, (size_t)n_in * 9 * n * 8, &din))) return rc;
+  if ((rc = get_scratch(1, (size_t)t.n_slots * n * 8, &dout))) return rc;
+  if ((rc = get_scratch(2, n * 4, &derr))) return rc;
+  const uint64_t* dptr[MAX_TAPE_INPUTS];
+  for (int k = 0; k < n_in; k++) {
+    dptr[k] = (const uint64_t*)din + (size_t)k * 9 * n;
+    P2E_CUDA(cudaMemcpyAsync((uint64_t*)din + (size_t)k * 9 * n, inputs[k], 9 * n * 8, cudaMemcpyHostToDevice, st));
+  }
+  OutSpec o{FMT_PLAIN, (uint64_t*)dout, nullptr, nullptr, n};
+  if ((rc = run_tape(tape, t, n, dptr, n_in, n, o, (uint32_t*)derr, (void*)st))) return rc;
+  P2E_CUDA(cudaMemcpyAsync(out, dout, (size_t)t.n_slots * n * 8, cudaMemcpyDeviceToHost, st));
+  if (err) P2E_CUDA(cudaMemcpyAsync(err, derr, n * 4, cudaMemcpyDeviceToHost, st));
+  P2E_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+size_t p2e_tape_compact_layout(int tape, uint32_t* map, uint32_t* narrow_slots, uint32_t* wide_slots) {
+  if (bad_tape(tape)) return 0;
+  const Tape& t = get_tape(tape);
+  compact_layout(t, map, narrow_slots, wide_slots);
   return t.n_slots;
 }
 
@@ -1696,7 +1437,7 @@ int p2e_tape_compact_expand(int tape, size_t n, const uint32_t* narrow, const ui
   const Tape& t = get_tape(tape);
   std::vector<uint32_t> map(t.n_slots);
   uint32_t nn = 0, nw = 0;
-  p2e_tape_compact_layout(tape, map.data(), &nn, &nw);
+  compact_layout(t, map.data(), &nn, &nw);
   const i64 off = (i64)1 << 33;
   for (size_t s = 0; s < t.n_slots; s++) {
     const uint32_t m = map[s];
@@ -1745,46 +1486,32 @@ int p2e_tape_witness_compact(int tape, size_t n, const uint64_t* const* inputs, 
   int rc = ensure_ready();
   if (rc) return rc;
   if (n == 0) return 0;
+  P2E_HOST_LOCK();
   const Tape& t = get_tape(tape);
   const int n_in = (int)t.n_inputs;
-  static std::map<int, std::vector<uint32_t>> maps;
-  static std::map<int, void*> dmaps;
-  static std::map<int, int> dmap_device;
   uint32_t nn = 0, nw = 0;
-  if (maps[tape].empty()) maps[tape].resize(t.n_slots);
-  p2e_tape_compact_layout(tape, maps[tape].data(), &nn, &nw);
-  if (!dmaps[tape] || dmap_device[tape] != ctx().device) {
-    P2E_CUDA(cudaMalloc(&dmaps[tape], (size_t)t.n_slots * 4));
-    P2E_CUDA(cudaMemcpy(dmaps[tape], maps[tape].data(), (size_t)t.n_slots * 4, cudaMemcpyHostToDevice));
-    dmap_device[tape] = ctx().device;
-  }
+  compact_layout(t, nullptr, &nn, &nw);
   cudaStream_t st = ctx().stream;
   // The batch is processed in chunks of signatures so that the D2H copy of chunk c (on a second stream,
   // pitched copies into the caller's [rows][n] matrices) overlaps the kernels of chunk c + 1: the call
-  // costs about one chunk of compute plus the PCIe time instead of their sum.
-  static cudaStream_t cp = nullptr;
-  static int cp_device = -1;
-  static cudaEvent_t ev_done[8];
-  if (!cp || cp_device != ctx().device) {
-    P2E_CUDA(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
-    for (auto& e : ev_done) P2E_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    cp_device = ctx().device;
+  // costs about one chunk of compute plus the PCIe time instead of their sum.  The kernels write the compact
+  // rows themselves (no plain witness is materialised on this path).
+  ChainState& S = chain_state();
+  if (!S.cp) {
+    P2E_CUDA(cudaStreamCreateWithFlags(&S.cp, cudaStreamNonBlocking));
+    for (auto& e : S.ev_done) P2E_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  size_t n_chunks = 1;
-  {
-    const char* e = getenv("P2E_HOST_CHUNKS");
-    n_chunks = e ? (size_t)atoi(e) : 4;
-    if (n_chunks < 1) n_chunks = 1;
-    if (n_chunks > 8) n_chunks = 8;
-    if (n < 256 * n_chunks) n_chunks = 1;
-  }
-  const size_t cn = (n + n_chunks - 1) / n_chunks;
-  void *din = nullptr, *dout = nullptr, *derr = nullptr, *dpack = nullptr;
+  cudaStream_t cp = S.cp;
+  size_t n_chunks = (size_t)option(OPT_HOST_CHUNKS);
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_chunks > 8) n_chunks = 8;
+  if (n < 256 * n_chunks) n_chunks = 1;
+  const size_t cn = ((n + n_chunks - 1) / n_chunks + 31) / 32 * 32;      // chunk stride: 128-byte aligned rows
+  void *din = nullptr, *derr = nullptr, *dpack = nullptr;
   if ((rc = get_scratch(0, (size_t)n_in * 9 * n * 8, &din))) return rc;
-  if ((rc = get_scratch(1, (size_t)t.n_slots * cn * 8, &dout))) return rc;
   if ((rc = get_scratch(2, n * 4, &derr))) return rc;
   const size_t nbytes = (size_t)nn * cn * 4, wbytes = wide ? (size_t)nw * cn * 8 : 0;          // per chunk
-  const size_t region = ((nbytes + 15) / 16) * 16 + ((wbytes + 15) / 16) * 16;
+  const size_t region = ((nbytes + 255) / 256) * 256 + ((wbytes + 255) / 256) * 256;
   if ((rc = get_scratch(3, region * n_chunks, &dpack))) return rc;
   const uint64_t* dptr[MAX_TAPE_INPUTS];
   for (int k = 0; k < n_in; k++)
@@ -1794,21 +1521,38 @@ int p2e_tape_witness_compact(int tape, size_t n, const uint64_t* const* inputs, 
     if (c0 >= n) break;
     const size_t cc = (n - c0 < cn) ? n - c0 : cn;
     u32* dn = (u32*)((char*)dpack + region * c);
-    u64* dw = (u64*)((char*)dn + ((nbytes + 15) / 16) * 16);
+    u64* dw = (u64*)((char*)dn + ((nbytes + 255) / 256) * 256);
     for (int k = 0; k < n_in; k++) dptr[k] = (const uint64_t*)din + (size_t)k * 9 * n + c0;
-    if ((rc = run_tape(tape, t, cc, dptr, n_in, n, (uint64_t*)dout, cn, (uint32_t*)derr + c0, (void*)st))) return rc;
-    k_pack_compact<<<dim3((unsigned)((cc + 255) / 256), 1024), 256, 0, st>>>(cc, t.n_slots, (const u64*)dout, cn,
-                                                                            (const u32*)dmaps[tape], dn, wide ? dw : nullptr,
-                                                                            (uint32_t*)derr + c0);
-    P2E_CUDA(cudaGetLastError());
-    P2E_CUDA(cudaEventRecord(ev_done[c], st));
-    P2E_CUDA(cudaStreamWaitEvent(cp, ev_done[c], 0));
-    P2E_CUDA(cudaMemcpy2DAsync(narrow + c0, n * 4, dn, cc * 4, cc * 4, nn, cudaMemcpyDeviceToHost, cp));
-    if (wide) P2E_CUDA(cudaMemcpy2DAsync(wide + c0, n * 8, dw, cc * 8, cc * 8, nw, cudaMemcpyDeviceToHost, cp));
+    OutSpec o{FMT_COMPACT, nullptr, dn, wide ? dw : nullptr, cn};
+    if ((rc = run_tape(tape, t, cc, dptr, n_in, n, o, (uint32_t*)derr + c0, (void*)st))) return rc;
+    P2E_CUDA(cudaEventRecord(S.ev_done[c], st));
+    P2E_CUDA(cudaStreamWaitEvent(cp, S.ev_done[c], 0));
+    P2E_CUDA(cudaMemcpy2DAsync(narrow + c0, n * 4, dn, cn * 4, cc * 4, nn, cudaMemcpyDeviceToHost, cp));
+    if (wide) P2E_CUDA(cudaMemcpy2DAsync(wide + c0, n * 8, dw, cn * 8, cc * 8, nw, cudaMemcpyDeviceToHost, cp));
     if (err) P2E_CUDA(cudaMemcpyAsync(err + c0, (uint32_t*)derr + c0, cc * 4, cudaMemcpyDeviceToHost, cp));
   }
   P2E_CUDA(cudaStreamSynchronize(st));
   P2E_CUDA(cudaStreamSynchronize(cp));
+  return 0;
+}
+
+// test hook (tests/test_gpu_f8.py): PTX bodies of the saturated field on the device; a, b, out: [n][9] u32 (8 words used)
+int p2e_debug_f8(int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  int rc = ensure_ready();
+  if (rc) return rc;
+  if (n == 0) return 0;
+  P2E_HOST_LOCK();
+  cudaStream_t st = ctx().stream;
+  void *da = nullptr, *db = nullptr, *dout = nullptr;
+  if ((rc = get_scratch(0, n * 36, &da))) return rc;
+  if ((rc = get_scratch(1, n * 36, &db))) return rc;
+  if ((rc = get_scratch(2, n * 36, &dout))) return rc;
+  P2E_CUDA(cudaMemcpyAsync(da, a, n * 36, cudaMemcpyHostToDevice, st));
+  P2E_CUDA(cudaMemcpyAsync(db, b, n * 36, cudaMemcpyHostToDevice, st));
+  k_debug_f8<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(op, n, (const u32*)da, (const u32*)db, (u32*)dout);
+  P2E_CUDA(cudaGetLastError());
+  P2E_CUDA(cudaMemcpyAsync(out, dout, n * 36, cudaMemcpyDeviceToHost, st));
+  P2E_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -1818,6 +1562,12 @@ int p2e_ecdsa_witness_dev(size_t n, const uint64_t* msg, const uint64_t* r, cons
                           const uint64_t* pky, size_t is, uint64_t* out, size_t os, uint32_t* err, void* stream) {
   const uint64_t* ins[5] = {msg, r, s, pkx, pky};
   return p2e_tape_witness_dev(TAPE_ECDSA, n, ins, is, out, os, err, stream);
+}
+int p2e_ecdsa_witness_compact_dev(size_t n, const uint64_t* msg, const uint64_t* r, const uint64_t* s, const uint64_t* pkx,
+                                  const uint64_t* pky, size_t is, uint32_t* narrow, uint64_t* wide, size_t os, uint32_t* err,
+                                  void* stream) {
+  const uint64_t* ins[5] = {msg, r, s, pkx, pky};
+  return p2e_tape_witness_compact_dev(TAPE_ECDSA, n, ins, is, narrow, wide, os, err, stream);
 }
 int p2e_ecdsa_witness(size_t n, const uint64_t* msg, const uint64_t* r, const uint64_t* s, const uint64_t* pkx,
                       const uint64_t* pky, uint64_t* out, uint32_t* err) {

@@ -722,10 +722,10 @@ static bool finalize(GenStream& S) {
 }
 
 // p2e_shutdown(): device buffers and graphs of every loaded stream go with the context (the parsed streams stay)
-void genstream_release_device() {
+void genstream_release_device(Context& c) {
   std::lock_guard<std::mutex> lock(g_gs_mu);
   for (GenStream* S : g_streams)
-    if (S) S->release_device();
+    if (S && S->device == c.device) S->release_device();
 }
 
 static GenStream* get_stream(int h) {
@@ -759,10 +759,7 @@ static int ensure_device(GenStream& S) {
 }
 
 // 1 (default): one fused kernel per group; 0: gather -> standalone batched kernel -> scatter (BigUint div_rem always)
-static bool use_fused() {            // read per call: the tests run both paths in one process
-  const char* e = getenv("P2E_GENSTREAM_FUSED");
-  return !e || atoi(e) != 0;
-}
+static bool use_fused() { return option(OPT_GENSTREAM_FUSED) != 0; }   // p2e_set_option("genstream_fused", 0 | 1): the tests run both paths
 
 static int per_launch(size_t n) {
   int per = (int)std::max<size_t>(1, GS_MAX_STAGED / std::max<size_t>(n, 1));
@@ -862,10 +859,7 @@ static int run_groups(GenStream& S, size_t n, u64* V, size_t vs, u32* err, cudaS
   return 0;
 }
 
-static bool use_graph() {
-  const char* e = getenv("P2E_GENSTREAM_GRAPH");
-  return !e || atoi(e) != 0;
-}
+static bool use_graph() { return option(OPT_GENSTREAM_GRAPH) != 0; }
 
 // the launch sequence as a CUDA graph, re-used while (n, table, stride, err, staging) stay the same
 static int run_groups_graphed(GenStream& S, size_t n, u64* V, size_t vs, u32* err, cudaStream_t st) {
@@ -912,13 +906,13 @@ int p2e_genstream_load(const uint8_t* bytes, size_t len) {
   Reader R{bytes, len};
   while (R.pos < R.len) {
     if (!parse_record(*S, R)) {
-      ctx().last_error = S->error + " (record " + std::to_string(S->gens.size()) + ", byte " + std::to_string(R.pos) + ")";
+      set_error_msg((S->error + " (record " + std::to_string(S->gens.size()) + ", byte " + std::to_string(R.pos) + ")").c_str());
       delete S;
       return -1;
     }
   }
   if (!finalize(*S)) {
-    ctx().last_error = S->error;
+    set_error_msg(S->error.c_str());
     delete S;
     return -1;
   }
@@ -1031,6 +1025,7 @@ int p2e_genstream_run(int h, size_t n, const uint32_t* in_slots, int n_in, const
   for (int k = 0; k < n_out; k++)
     if (out_slots[k] >= (u32)n_slots) return set_error_msg("genstream: output slot out of range");
   if (n == 0) return 0;
+  P2E_HOST_LOCK();
   cudaStream_t st = ctx().stream;
   void *dV = nullptr, *din = nullptr, *derr = nullptr, *dout = nullptr;
   if ((rc = get_scratch(1, (size_t)n_slots * n * 8, &dV))) return rc;

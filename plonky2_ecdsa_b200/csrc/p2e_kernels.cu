@@ -1,6 +1,8 @@
 // p2e_kernels.cu -- batched witness-generator kernels (one instance per thread, limbs in
 // registers, wire-major coalesced loads/stores), the gate constraint evaluators over
 // Goldilocks LDE rows, and their extern "C" entry points (include/p2e.h).
+#include <string.h>
+#include <mutex>
 #include "../../include/p2e.h"
 #include "p2e_common.h"
 #include "p2e_field.cuh"
@@ -10,21 +12,34 @@
 namespace p2e {
 
 // ------------------------------------------------------------------------------------------
-// context
+// contexts: one per device, selected per thread
+static Context g_ctx[MAX_DEVICES];
+static Context g_none;                         // never ready: what ctx() answers before any p2e_init
+static std::mutex g_ctx_mu;                    // guards creation / destruction of contexts
+static int g_default_device = -1;              // first initialised device: current device of threads that never chose
+static thread_local int tls_device = -1;
+static thread_local std::string tls_error;
+static long g_options[N_OPTIONS] = {65536, 4, 1, 1, 12};
+
 Context& ctx() {
-  static Context c;
-  return c;
+  const int d = tls_device >= 0 ? tls_device : g_default_device;
+  if (d < 0 || d >= MAX_DEVICES) return g_none;
+  return g_ctx[d];
 }
+long option(int id) { return (id >= 0 && id < N_OPTIONS) ? g_options[id] : 0; }
 int set_error(const char* where, cudaError_t e) {
-  ctx().last_error = std::string(where) + ": " + cudaGetErrorString(e);
+  tls_error = std::string(where) + ": " + cudaGetErrorString(e);
   return -(int)e - 1000;
 }
 int set_error_msg(const char* msg) {
-  ctx().last_error = msg;
+  tls_error = msg;
   return -1;
 }
 int ensure_ready() {
-  if (!ctx().ready) return set_error_msg("p2e_init() has not been called (no CUDA device bound; there is no CPU fallback)");
+  Context& c = ctx();
+  if (!c.ready) return set_error_msg("p2e_init() has not been called (no CUDA device bound; there is no CPU fallback)");
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != c.device) P2E_CUDA(cudaSetDevice(c.device));
   return 0;
 }
 int get_scratch(int slot, size_t bytes, void** out) {
@@ -709,31 +724,54 @@ using namespace p2e;
 extern "C" {
 
 int p2e_init(int device) {
-  Context& c = ctx();
   int cnt = 0;
   cudaError_t e = cudaGetDeviceCount(&cnt);
   if (e != cudaSuccess) return set_error("cudaGetDeviceCount", e);
   if (cnt == 0) return set_error_msg("no CUDA device visible (there is no CPU fallback)");
-  if (device < 0 || device >= cnt) return set_error_msg("p2e_init: device index out of range");
+  if (device < 0 || device >= cnt || device >= MAX_DEVICES) return set_error_msg("p2e_init: device index out of range");
+  std::lock_guard<std::mutex> lock(g_ctx_mu);
   P2E_CUDA(cudaSetDevice(device));
-  if (c.ready && c.device == device) return 0;
-  if (c.ready) p2e_shutdown();
-  cudaDeviceProp prop;
-  P2E_CUDA(cudaGetDeviceProperties(&prop, device));
-  c.sm_count = prop.multiProcessorCount;
-  P2E_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-  c.device = device;
-  c.ready = true;
+  Context& c = g_ctx[device];
+  if (!c.ready) {
+    cudaDeviceProp prop;
+    P2E_CUDA(cudaGetDeviceProperties(&prop, device));
+    c.sm_count = prop.multiProcessorCount;
+    P2E_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.device = device;
+    c.ready = true;
+  }
+  if (g_default_device < 0) g_default_device = device;
+  tls_device = device;
   return 0;
 }
 
-void p2e_shutdown(void) {
-  Context& c = ctx();
+int p2e_init_devices(int n_devices) {
+  int cnt = p2e_device_count();
+  if (n_devices <= 0 || n_devices > cnt) return set_error_msg("p2e_init_devices: n_devices out of range");
+  const int keep = tls_device;
+  for (int d = 0; d < n_devices; d++) {
+    int rc = p2e_init(d);
+    if (rc) return rc;
+  }
+  tls_device = keep >= 0 ? keep : 0;
+  return ensure_ready();
+}
+
+int p2e_set_device(int device) {
+  if (device < 0 || device >= MAX_DEVICES || !g_ctx[device].ready) return set_error_msg("p2e_set_device: device not initialised (p2e_init)");
+  tls_device = device;
+  return ensure_ready();
+}
+
+int p2e_current_device(void) { return ctx().ready ? ctx().device : -1; }
+
+static void shutdown_one(Context& c) {
   if (!c.ready) return;
-  cudaStreamSynchronize(c.stream);
-  chain_release_device_tapes();
-  ntt_release_tables();
-  genstream_release_device();
+  cudaSetDevice(c.device);
+  cudaDeviceSynchronize();
+  chain_release_device(c);
+  ntt_release_device(c);
+  genstream_release_device(c);
   for (int i = 0; i < 4; i++) {
     if (c.scratch[i]) cudaFree(c.scratch[i]);
     c.scratch[i] = nullptr;
@@ -742,9 +780,44 @@ void p2e_shutdown(void) {
   cudaStreamDestroy(c.stream);
   c.stream = nullptr;
   c.ready = false;
+  c.device = -1;
 }
 
-const char* p2e_last_error(void) { return ctx().last_error.c_str(); }
+void p2e_shutdown(void) {
+  std::lock_guard<std::mutex> lock(g_ctx_mu);
+  for (auto& c : g_ctx) shutdown_one(c);
+  g_default_device = -1;
+  tls_device = -1;
+}
+
+int p2e_shutdown_device(int device) {
+  if (device < 0 || device >= MAX_DEVICES) return set_error_msg("p2e_shutdown_device: device index out of range");
+  std::lock_guard<std::mutex> lock(g_ctx_mu);
+  shutdown_one(g_ctx[device]);
+  if (g_default_device == device) {
+    g_default_device = -1;
+    for (int d = 0; d < MAX_DEVICES; d++) if (g_ctx[d].ready) { g_default_device = d; break; }
+  }
+  if (tls_device == device) tls_device = -1;
+  return 0;
+}
+
+const char* p2e_last_error(void) { return tls_error.c_str(); }
+
+static const char* const OPTION_NAMES[N_OPTIONS] = {"chain_chunk", "host_chunks", "genstream_fused", "genstream_graph", "ntt_log_tile"};
+int p2e_set_option(const char* name, long value) {
+  for (int i = 0; i < N_OPTIONS; i++)
+    if (name && !strcmp(name, OPTION_NAMES[i])) {
+      g_options[i] = value;
+      return 0;
+    }
+  return set_error_msg("p2e_set_option: unknown option");
+}
+long p2e_get_option(const char* name) {
+  for (int i = 0; i < N_OPTIONS; i++)
+    if (name && !strcmp(name, OPTION_NAMES[i])) return g_options[i];
+  return -1;
+}
 
 int p2e_device_count(void) {
   int cnt = 0;
@@ -1053,6 +1126,7 @@ template <class Launch>
 static int run_host(size_t n, const HostIn* ins, int n_in, void* out, size_t out_rows, uint32_t* err, Launch launch) {
   P2E_CHECK_READY();
   if (n == 0) return 0;
+  P2E_HOST_LOCK();
   cudaStream_t st = ctx().stream;
   size_t in_rows = 0;
   for (int k = 0; k < n_in; k++) in_rows += ins[k].rows;
@@ -1167,6 +1241,7 @@ int p2e_eval_filtered_combined(int gate, const int* params, int gate_index, int 
   if ((rc = gate_shape(gate, params, &nw, &nc))) return rc;
   if (n_alphas < 1 || n_alphas > MAX_ALPHAS) return set_error_msg("eval_filtered: n_alphas must be 1..4");
   if (n == 0) return 0;
+  P2E_HOST_LOCK();
   cudaStream_t st = ctx().stream;
   void *din = nullptr, *dout = nullptr, *dscr = nullptr;
   if ((rc = get_scratch(0, ((size_t)nw + 1) * n * 8, &din))) return rc;
@@ -1187,6 +1262,7 @@ int p2e_eval_filtered_combined(int gate, const int* params, int gate_index, int 
 
 double p2e_bench_imad(int wide, int iters) {
   if (ensure_ready()) return -1.0;
+  P2E_HOST_LOCK();
   Context& c = ctx();
   void* sink;
   if (get_scratch(3, 64, &sink)) return -1.0;

@@ -247,20 +247,27 @@ static u64 h_root(int log_n) { return h_pow(GL_TWO_ADIC_GEN, 1ull << (32 - log_n
 struct DevTable {
   u64* ptr = nullptr;
 };
-static std::map<std::vector<u64>, DevTable> g_tables;   // key: {base, count, premul}
-static std::mutex g_ntt_mu;
-static int g_tables_device = -1;
+// per-device state: twiddle / scaling tables and the "function attributes set" flag (function attributes are per device)
+struct NttState {
+  std::mutex mu;
+  std::map<std::vector<u64>, DevTable> tables;   // key: {base, count, premul}
+  bool attr_set = false;
+};
+static NttState& ntt_state() {
+  Context& c = ctx();
+  static std::mutex create_mu;
+  std::lock_guard<std::mutex> lock(create_mu);
+  if (!c.ntt) c.ntt = new NttState();
+  return *(NttState*)c.ntt;
+}
 
 // device table of premul * base^e, e < count
 static int power_table(u64 base, size_t count, u64 premul, const u64** out) {
-  Context& c = ctx();
-  if (g_tables_device != c.device) {
-    g_tables.clear();       // another device was bound: the old pointers died with its context
-    g_tables_device = c.device;
-  }
+  NttState& S = ntt_state();
+  std::lock_guard<std::mutex> lock(S.mu);
   std::vector<u64> key = {base, (u64)count, premul};
-  auto it = g_tables.find(key);
-  if (it == g_tables.end()) {
+  auto it = S.tables.find(key);
+  if (it == S.tables.end()) {
     std::vector<u64> h(count ? count : 1);
     u64 v = premul;
     for (size_t e = 0; e < count; e++) {
@@ -270,26 +277,24 @@ static int power_table(u64 base, size_t count, u64 premul, const u64** out) {
     DevTable t;
     P2E_CUDA(cudaMalloc(&t.ptr, h.size() * 8));
     P2E_CUDA(cudaMemcpy(t.ptr, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
-    it = g_tables.emplace(key, t).first;
+    it = S.tables.emplace(key, t).first;
   }
   *out = it->second.ptr;
   return 0;
 }
 
-void ntt_release_tables() {
-  for (auto& kv : g_tables)
+void ntt_release_device(Context& c) {
+  if (!c.ntt) return;
+  NttState* S = (NttState*)c.ntt;
+  for (auto& kv : S->tables)
     if (kv.second.ptr) cudaFree(kv.second.ptr);
-  g_tables.clear();
-  g_tables_device = -1;
+  delete S;
+  c.ntt = nullptr;
 }
 
 static int log_tile() {
-  static int v = 0;
-  if (!v) {
-    const char* e = getenv("P2E_NTT_LOG_TILE");
-    v = e ? atoi(e) : 12;          // measured on B200 (LDE 2^17 -> 2^20 x 135): 2^13 4.33 ms, 2^12 4.16 ms, 2^11 4.50 ms
-    if (v < 10 || v > 13) v = 12;
-  }
+  int v = (int)option(OPT_NTT_LOG_TILE);   // measured on B200 (LDE 2^17 -> 2^20 x 135): 2^13 4.33 ms, 2^12 4.16 ms, 2^11 4.50 ms
+  if (v < 10 || v > 13) v = 12;
   return v;
 }
 
@@ -337,14 +342,14 @@ static int ntt_run(int log_n, bool inverse, u64 scale_base, u64 scale_premul, in
       if ((rc = power_table(h_pow(scale_base, n2), n1, scale_premul, &shi))) return rc;
     }
   }
-  static bool attr_set = false;
+  NttState& NS = ntt_state();
   const size_t smem_max = (size_t)(NTT_TILE + 16) * 8;
-  if (!attr_set) {
+  if (!NS.attr_set) {
     P2E_CUDA(cudaFuncSetAttribute(k_ntt_cols<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     P2E_CUDA(cudaFuncSetAttribute(k_ntt_rows<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     P2E_CUDA(cudaFuncSetAttribute(k_ntt_cols<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     P2E_CUDA(cudaFuncSetAttribute(k_ntt_rows<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-    attr_set = true;
+    NS.attr_set = true;
   }
   // pass A
   A.in = in; A.out = tmp; A.in_stride = in_stride; A.out_stride = tmp_stride; A.n_in = n_in;
@@ -398,7 +403,6 @@ int p2e_ntt_dev(int log_n, int inverse, int n_polys, const uint64_t* in, size_t 
   if (n_polys == 0) return 0;
   const size_t n = (size_t)1 << log_n;
   if (in_stride < n || out_stride < n) return set_error_msg("ntt: stride < n");
-  std::lock_guard<std::mutex> lock(g_ntt_mu);
   if (inverse) return ntt_run(log_n, true, 1, h_inv((u64)n % GL_P), n_polys, in, in_stride, n, scratch, n, out, out_stride, pick_stream(stream));
   return ntt_run(log_n, false, 0, 0, n_polys, in, in_stride, n, scratch, n, out, out_stride, pick_stream(stream));
 }
@@ -412,7 +416,6 @@ int p2e_coset_lde_dev(int log_n, int rate_bits, int n_polys, const uint64_t* val
   if (n_polys == 0) return 0;
   const size_t n = (size_t)1 << log_n, m = n << rate_bits;
   if (in_stride < n || out_stride < m) return set_error_msg("coset_lde: stride too small");
-  std::lock_guard<std::mutex> lock(g_ntt_mu);
   cudaStream_t st = pick_stream(stream);
   u64* tmp_n = scratch;                               // [n_polys][n]
   u64* coeffs = scratch + (size_t)n_polys * n;        // [n_polys][n]: c_k * g^k
@@ -431,6 +434,7 @@ static int ntt_host(int log_in, int log_out, int rate_bits, int n_polys, const u
   int rc = ensure_ready();
   if (rc) return rc;
   if (n_polys <= 0) return n_polys < 0 ? set_error_msg("ntt: n_polys < 0") : 0;
+  P2E_HOST_LOCK();
   const size_t n_in = (size_t)1 << log_in, n_out = (size_t)1 << log_out;
   cudaStream_t st = ctx().stream;
   void *din = nullptr, *dout = nullptr, *dscr = nullptr;

@@ -550,6 +550,7 @@ static int ux_host(size_t n, const uint64_t* in, size_t in_rows, uint64_t* out, 
   int rc = ensure_ready();
   if (rc) return rc;
   if (n == 0) return 0;
+  P2E_HOST_LOCK();
   cudaStream_t st = ctx().stream;
   void *din = nullptr, *dout = nullptr, *derr = nullptr;
   if ((rc = get_scratch(0, in_rows * n * 8, &din))) return rc;

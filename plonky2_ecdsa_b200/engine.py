@@ -52,6 +52,14 @@ _u64 = ctypes.c_uint64
 # name -> (restype, argtypes); every symbol include/p2e.h declares
 SIGNATURES = {
     "p2e_init": (_int, [_int]),
+    "p2e_init_devices": (_int, [_int]),
+    "p2e_set_device": (_int, [_int]),
+    "p2e_current_device": (_int, []),
+    "p2e_shutdown_device": (_int, [_int]),
+    "p2e_set_option": (_int, [ctypes.c_char_p, ctypes.c_long]),
+    "p2e_get_option": (ctypes.c_long, [ctypes.c_char_p]),
+    "p2e_stream_release": (_int, [_vp]),
+    "p2e_debug_f8": (_int, [_int, _sz, _vp, _vp, _vp]),
     "p2e_shutdown": (None, []),
     "p2e_last_error": (ctypes.c_char_p, []),
     "p2e_device_count": (_int, []),
@@ -89,6 +97,8 @@ SIGNATURES = {
     "p2e_tape_witness": (_int, [_int, _sz, _vp, _vp, _vp]),
     "p2e_tape_compact_layout": (_sz, [_int, _vp, _vp, _vp]),
     "p2e_tape_witness_compact": (_int, [_int, _sz, _vp, _vp, _vp, _vp]),
+    "p2e_tape_witness_compact_dev": (_int, [_int, _sz, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
+    "p2e_ecdsa_witness_compact_dev": (_int, [_sz, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
     "p2e_tape_compact_expand": (_int, [_int, _sz, _vp, _vp, _vp]),
     "p2e_builder_new": (_int, []),
     "p2e_builder_free": (_int, [_int]),
@@ -288,7 +298,9 @@ class CircuitBuilder:
 
 
 class Engine:
-    """One process == one GPU.  `Engine(device)` binds the process to that CUDA device."""
+    """`Engine(device)` creates (or re-selects) the library context of that CUDA device and makes it the calling
+    thread's current device.  One process may hold several engines (one per GPU); call `select()` (p2e_set_device)
+    before using an engine from a thread whose current device is another one."""
 
     def __init__(self, device: int = 0, lib_path: str = LIB_PATH):
         self.lib = load_library(lib_path)
@@ -296,6 +308,16 @@ class Engine:
         if rc != 0:
             raise P2EError(f"p2e_init({device}) failed: {self.last_error()}")
         self.device = device
+
+    def select(self):
+        self._check(self.lib.p2e_set_device(self.device))
+        return self
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.p2e_set_option(name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        return int(self.lib.p2e_get_option(name.encode()))
 
     # ---------------------------------------------------------------- plumbing
     def last_error(self) -> str:
@@ -309,7 +331,7 @@ class Engine:
         self._check(self.lib.p2e_synchronize())
 
     def close(self):
-        self.lib.p2e_shutdown()
+        self.lib.p2e_shutdown_device(self.device)
 
     # ---------------------------------------------------------------- witness generation (host buffers)
     def mul_nonnative(self, modulus, x, y):

@@ -11,15 +11,16 @@ what = sys.argv[1] if len(sys.argv) > 1 else "ecdsa"
 eng = pkg.Engine(0); lib = eng.lib
 dev = lambda a: torch.from_numpy(a.view(np.int64)).cuda()
 if what == "ecdsa":
+    # one batch on the library stream with the per-kernel event marks on (keeps every kernel on ONE stream, in order)
     n = 4096
-    slots = int(lib.p2e_ecdsa_tape_slots())
+    _, nn, nw = eng.tape_compact_layout(eng.TAPE_ECDSA)
     d = W.ecdsa_workload(n, seed=W.SEED)
     ind = [dev(d[k]) for k in ("msg", "r", "s", "pkx", "pky")]
-    od = torch.empty((slots, n), dtype=torch.int64, device="cuda")
+    nar = torch.empty((nn, n), dtype=torch.int32, device="cuda")
     ed = torch.empty(n, dtype=torch.int32, device="cuda")
-    os.environ["P2E_CHAIN_NO_PRIORITY"] = "1"
+    eng.set_profiling(True)
     for _ in range(2):
-        assert lib.p2e_ecdsa_witness_dev(n, *[t.data_ptr() for t in ind], n, od.data_ptr(), n, ed.data_ptr(), None) == 0
+        assert lib.p2e_ecdsa_witness_compact_dev(n, *[t.data_ptr() for t in ind], n, nar.data_ptr(), None, n, ed.data_ptr(), None) == 0
     eng.synchronize()
     assert not bool(ed.any())
 elif what == "ux":

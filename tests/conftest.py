@@ -32,8 +32,8 @@ def hostcheck():
     d = os.path.join(ROOT, "tests", "hostcheck")
     so = os.path.join(d, "libhostcheck.so")
     src = os.path.join(d, "hostcheck.cpp")
-    hdr = os.path.join(ROOT, "plonky2_ecdsa_b200", "csrc", "p2e_field.cuh")
-    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(ROOT, "plonky2_ecdsa_b200", "csrc", h) for h in ("p2e_field.cuh", "p2e_f8.cuh")]
+    if (not os.path.exists(so)) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
     lib = ctypes.CDLL(so)
     for f in ("hc_gl_mul", "hc_gl_add", "hc_gl_sub", "hc_gl_reduce128"):

@@ -7,6 +7,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #include <stddef.h>
 #include "../../plonky2_ecdsa_b200/csrc/p2e_field.cuh"
+#include "../../plonky2_ecdsa_b200/csrc/p2e_f8.cuh"
 
 using namespace p2e;
 
@@ -126,6 +127,40 @@ void hc_lazy(int op, int ka, int kb, size_t n, const int32_t* a, const int32_t* 
     u32 c[NL];
     lz_canon(r, c);
     for (int l = 0; l < NL; l++) { canon[9 * i + l] = c[l]; raw[9 * i + l] = r[l]; }
+  }
+}
+
+// saturated 8 x 32-bit field (p2e_f8.cuh, portable bodies): out = raw weak words
+// op: 0 mul, 1 sqr, 2 add, 3 sub, 4 mul_small<2>, 5 <3>, 6 <4>, 7 <8>, 8 canon, 9 from_l29 (a = 9 limbs in a[0..8]) , 10 to_l29 (out 9 words)
+void hc_f8(int op, size_t n, const u32* a, const u32* b, u32* out) {
+  for (size_t i = 0; i < n; i++) {
+    u32 x[8], y[8], r[8];
+    for (int l = 0; l < 8; l++) { x[l] = a[9 * i + l]; y[l] = b[9 * i + l]; r[l] = 0; }
+    if (op == 0) f8_mul(x, y, r);
+    else if (op == 1) f8_sqr(x, r);
+    else if (op == 2) f8_add(x, y, r);
+    else if (op == 3) f8_sub(x, y, r);
+    else if (op == 4) f8_mul_small<2>(x, r);
+    else if (op == 5) f8_mul_small<3>(x, r);
+    else if (op == 6) f8_mul_small<4>(x, r);
+    else if (op == 7) f8_mul_small<8>(x, r);
+    else if (op == 8) { f8_copy(x, r); f8_canon(r); }
+    else if (op == 9) { u32 l9[NL]; for (int l = 0; l < NL; l++) l9[l] = a[9 * i + l]; f8_from_l29(l9, r); }
+    if (op == 10) { u32 l9[NL]; f8_to_l29(x, l9); for (int l = 0; l < NL; l++) out[9 * i + l] = l9[l]; }
+    else { for (int l = 0; l < 8; l++) out[9 * i + l] = r[l]; out[9 * i + 8] = 0; }
+  }
+}
+
+// fast mul-witness core of the chain expansion (ModP, factors < 2^256): out = r[9] q[9] cs[17] b[16] like hc_mul_witness
+void hc_mulw_fast(size_t n, const u64* x, const u64* y, u64* out, u32* err) {
+  for (size_t i = 0; i < n; i++) {
+    u32 xa[NL], ya[NL], r[NL], q[NL], blo[16], tops;
+    i64 v[17];
+    for (int l = 0; l < NL; l++) { xa[l] = (u32)x[9 * i + l]; ya[l] = (u32)y[9 * i + l]; }
+    err[i] = mulw_p_fast(xa, ya, r, q, v, blo, tops);
+    for (int l = 0; l < NL; l++) { out[51 * i + l] = r[l]; out[51 * i + 9 + l] = q[l]; }
+    for (int l = 0; l < 17; l++) out[51 * i + 18 + l] = gl_from_i64(v[l]);
+    for (int l = 0; l < 16; l++) out[51 * i + 35 + l] = (u64)blo[l] | ((u64)((tops >> (2 * l)) & 3u) << 32);
   }
 }
 

@@ -361,19 +361,15 @@ def _rand_point(rng):
 
 
 @pytest.fixture(params=["fused", "staged", "staged-nograph"])
-def gs_mode(request):
+def gs_mode(request, engine):
     """Both execution forms of a launch group (one fused kernel / gather -> batched kernel -> scatter), with and
-    without the CUDA graph."""
-    import os
-    old = {k: os.environ.get(k) for k in ("P2E_GENSTREAM_FUSED", "P2E_GENSTREAM_GRAPH")}
-    os.environ["P2E_GENSTREAM_FUSED"] = "1" if request.param == "fused" else "0"
-    os.environ["P2E_GENSTREAM_GRAPH"] = "0" if request.param.endswith("nograph") else "1"
+    without the CUDA graph (p2e_set_option)."""
+    old = {k: engine.get_option(k) for k in ("genstream_fused", "genstream_graph")}
+    engine.set_option("genstream_fused", 1 if request.param == "fused" else 0)
+    engine.set_option("genstream_graph", 0 if request.param.endswith("nograph") else 1)
     yield request.param
     for k, v in old.items():
-        if v is None:
-            os.environ.pop(k, None)
-        else:
-            os.environ[k] = v
+        engine.set_option(k, v)
 
 
 @pytest.mark.gpu

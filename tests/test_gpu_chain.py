@@ -1,4 +1,6 @@
 """GPU tier: whole-chain witnesses (verify_secp256k1_message_circuit, glv_mul) vs the oracle tape."""
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -126,7 +128,7 @@ def test_curve_add_equal_x_flags_inverse_zero(engine):
     assert err[0] & 8 and err[2] & 8 and err[1] == 0
 
 
-def test_chain_chunking_is_transparent(engine, monkeypatch):
+def test_chain_chunking_is_transparent(engine):
     """Batches above the scratch chunk capacity are processed chunk by chunk: same bits."""
     n = 300
     ks = [(j * 0x9E3779B97F4A7C15 + 12345) % S.SECP_N for j in range(n)]
@@ -135,30 +137,28 @@ def test_chain_chunking_is_transparent(engine, monkeypatch):
     px = W.ints_to_limbs([pts[j % 4][0] for j in range(n)])
     py = W.ints_to_limbs([pts[j % 4][1] for j in range(n)])
     w1, e1 = engine.glv_mul_witness(k, px, py)
-    monkeypatch.setenv("P2E_CHAIN_CHUNK", "128")
-    w2, e2 = engine.glv_mul_witness(k, px, py)
+    old = engine.get_option("chain_chunk")
+    engine.set_option("chain_chunk", 128)
+    try:
+        w2, e2 = engine.glv_mul_witness(k, px, py)
+    finally:
+        engine.set_option("chain_chunk", old)
     assert np.array_equal(w1, w2) and np.array_equal(e1, e2) and not e1.any()
     wb = S.WitnessBuilder()
     wb.glv_mul(wb.constant_affine_point(pts[299 % 4]), wb.constant_nonnative(ks[299], S.SECP_N))
     assert [int(v) for v in w2[:, 299]] == wb.flat()
 
 
-@pytest.mark.parametrize("mode", ["serial", "coop", "duo"])
-def test_replay_kernel_variants_are_bit_exact(engine, monkeypatch, mode):
-    """All replay kernels (one thread / two lanes + shuffles / four lanes + shared memory per
-    (signature, chain), P2E_CHAIN_REPLAY) must give the same witness; odd batch size on purpose."""
+def test_replay_kernel_odd_batch_is_bit_exact(engine):
+    """The two-lane replay kernel pairs lanes 2j / 2j+1: an odd batch size leaves a half-filled warp."""
     wl = W.ecdsa_workload(71, seed=31)
     args = (wl["msg"], wl["r"], wl["s"], wl["pkx"], wl["pky"])
-    monkeypatch.setenv("P2E_CHAIN_REPLAY", mode)
     w2, e2 = engine.verify_secp256k1_message_witness(*args)
     assert not e2.any()
     i = wl["ints"]
     for j in (0, 35, 70):
         ref = S.ecdsa_witness(i["msg"][j], i["r"][j], i["s"][j], (i["pkx"][j], i["pky"][j])).flat()
         assert [int(v) for v in w2[:, j]] == ref
-    monkeypatch.setenv("P2E_CHAIN_REPLAY", "serial")
-    w1, e1 = engine.verify_secp256k1_message_witness(*args)
-    assert np.array_equal(w1, w2) and np.array_equal(e1, e2)
 
 
 def test_ecdsa_edge_inputs_match_reference_panics(engine):
@@ -311,3 +311,30 @@ def test_ecdsa_batch_vs_c_oracle(engine):
     ref, ref_err = CB.ecdsa_witness(lib, *ins, threads=os.cpu_count() or 1)
     assert not err.any() and not ref_err.any()
     assert np.array_equal(wit, ref)
+
+
+def test_compact_device_format_is_written_directly(engine):
+    """p2e_tape_witness_compact_dev: the chain kernels write the compact rows themselves (with and without the
+    check_sum columns, padded stride); expanding them gives the plain device witness bit for bit."""
+    import torch
+    n, stride = 157, 192
+    wl = W.ecdsa_workload(n, seed=1234)
+    ins = [wl[k] for k in ("msg", "r", "s", "pkx", "pky")]
+    plain, e1 = engine.tape_witness(engine.TAPE_ECDSA, ins)
+    cmap, nn, nw = engine.tape_compact_layout(engine.TAPE_ECDSA)
+    dins = [torch.from_numpy(a.view(np.int64)).cuda() for a in ins]
+    arr = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in dins])
+    for with_wide in (True, False):
+        nar = torch.zeros((nn, stride), dtype=torch.int32, device="cuda")
+        wide = torch.zeros((nw, stride), dtype=torch.int64, device="cuda") if with_wide else None
+        err = torch.zeros(n, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        rc = engine.lib.p2e_tape_witness_compact_dev(engine.TAPE_ECDSA, n, ctypes.cast(arr, ctypes.c_void_p), n, nar.data_ptr(),
+                                                     wide.data_ptr() if with_wide else None, stride, err.data_ptr(), None)
+        assert rc == 0, engine.last_error()
+        engine.synchronize()
+        nh = nar.cpu().numpy().view(np.uint32)[:, :n]
+        wh = wide.cpu().numpy().view(np.uint64)[:, :n] if with_wide else None
+        assert not err.cpu().numpy().any()
+        assert np.array_equal(engine.expand_compact(cmap, np.ascontiguousarray(nh), None if wh is None else np.ascontiguousarray(wh)), plain)
+        assert not nar.cpu().numpy()[:, n:].any()          # nothing is written past n

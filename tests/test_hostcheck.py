@@ -121,3 +121,66 @@ def test_goldilocks_ops(hostcheck):
     for _ in range(2000):
         lo, hi = rng.getrandbits(64), rng.getrandbits(64)
         assert hostcheck.hc_gl_reduce128(lo, hi) == ((hi << 64) | lo) % p
+
+
+# ---------------------------------------------------------------------------- saturated 8 x 32-bit field (p2e_f8.cuh)
+P_SECP = S.MODULI[0]
+
+
+def _words(vals, width=9):
+    a = np.zeros((len(vals), width), dtype=np.uint32)
+    for i, v in enumerate(vals):
+        for k in range(8):
+            a[i, k] = (v >> (32 * k)) & 0xFFFFFFFF
+    return a
+
+
+def _from_words(a):
+    return [sum(int(a[i, k]) << (32 * k) for k in range(8)) for i in range(a.shape[0])]
+
+
+F8_EDGES = [0, 1, 2, P_SECP - 1, P_SECP, P_SECP + 1, (1 << 256) - 1, (1 << 256) - 2, (1 << 32) + 977, (1 << 32) + 976,
+            (1 << 255), (1 << 255) - 1, 0xFFFFFFFF, 1 << 32, (1 << 224) - 1, ((1 << 256) - 1) ^ 0xFFFFFFFF]
+
+
+@pytest.mark.parametrize("op", range(9))
+def test_f8_portable_ops(hostcheck, op):
+    rng = random.Random(4000 + op)
+    pairs = [(a, b) for a in F8_EDGES for b in F8_EDGES] + [(rng.randrange(1 << 256), rng.randrange(1 << 256)) for _ in range(3000)]
+    a, b = _words([p[0] for p in pairs]), _words([p[1] for p in pairs])
+    out = np.zeros_like(a)
+    hostcheck.hc_f8(op, ctypes.c_size_t(len(pairs)), P(a), P(b), P(out))
+    got = _from_words(out)
+    for (x, y), g in zip(pairs, got):
+        want = [x * y, x * x, x + y, x - y, 2 * x, 3 * x, 4 * x, 8 * x, x][op] % P_SECP
+        assert g % P_SECP == want and g < (1 << 256), (op, hex(x), hex(y), hex(g))
+        if op == 8:
+            assert g < P_SECP
+
+
+def test_f8_limb_conversions(hostcheck):
+    rng = random.Random(77)
+    vals = F8_EDGES + [rng.randrange(1 << 256) for _ in range(500)]
+    limbs = np.ascontiguousarray(W.ints_to_limbs(vals).T.astype(np.uint32))
+    out = np.zeros_like(limbs)
+    hostcheck.hc_f8(9, ctypes.c_size_t(len(vals)), P(limbs), P(limbs), P(out))
+    assert _from_words(out) == vals
+    back = np.zeros_like(limbs)
+    hostcheck.hc_f8(10, ctypes.c_size_t(len(vals)), P(out), P(out), P(back))
+    assert np.array_equal(back, limbs)
+
+
+def test_mulw_fast_core_matches_the_generic_core(hostcheck):
+    """K4's fast core (factors < 2^256, q < 2^256) against the oracle: r, q, check_sum columns, carries."""
+    rng = random.Random(91)
+    vals = [0, 1, 2, P_SECP - 1, P_SECP - 2, P_SECP, (P_SECP - 1) // 2, 1 << 255, (1 << 32) + 977, (1 << 128) - 1]
+    pairs = [(a, b) for a in vals for b in vals] + [(rng.randrange(P_SECP), rng.randrange(P_SECP)) for _ in range(3000)]
+    x = W.ints_to_limbs([p[0] for p in pairs])
+    y = W.ints_to_limbs([p[1] for p in pairs])
+    n = len(pairs)
+    out = np.zeros((n, 51), dtype=np.uint64)
+    err = np.zeros(n, dtype=np.uint32)
+    hostcheck.hc_mulw_fast(ctypes.c_size_t(n), P(aos(x)), P(aos(y)), P(out), P(err))
+    eo, ee = U.expect_mul(x, y, 0)
+    assert not ee.any() and not err.any()
+    assert np.array_equal(out.T, eo)

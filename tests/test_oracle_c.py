@@ -40,3 +40,28 @@ def test_c_gate_eval_vs_spec(lib):
     assert np.array_equal(CB.eval_mul_nonnative(lib, 1, w), U.expect_eval_mul(w, 1))
     w2 = W.random_goldilocks(5, 33, 700)
     assert np.array_equal(CB.eval_check_sum(lib, w2), U.expect_eval_check_sum(w2))
+
+
+def test_c_fast_inverse_mode_gives_the_same_bits(lib):
+    """The "best-CPU" baseline variant (extended Euclid instead of the Fermat ladder) must not change a witness bit."""
+    rng = random.Random(77)
+    for modulus in (0, 1):
+        M = S.MODULI[modulus]
+        xs = [1, 2, M - 1, M + 1, 0, M, 3] + [rng.randrange(1 << 256) for _ in range(200)]
+        x = W.ints_to_limbs(xs)
+        ref, e0 = CB.inv_nonnative(lib, modulus, x)
+        lib.orc_set_inverse_mode(1)
+        try:
+            got, e1 = CB.inv_nonnative(lib, modulus, x)
+        finally:
+            lib.orc_set_inverse_mode(0)
+        assert np.array_equal(ref, got) and np.array_equal(e0, e1)
+    wl = W.ecdsa_workload(3, seed=5)
+    args = [wl[k] for k in ("msg", "r", "s", "pkx", "pky")]
+    a, ea = CB.ecdsa_witness(lib, *args)
+    lib.orc_set_inverse_mode(1)
+    try:
+        b, eb = CB.ecdsa_witness(lib, *args)
+    finally:
+        lib.orc_set_inverse_mode(0)
+    assert np.array_equal(a, b) and np.array_equal(ea, eb)
