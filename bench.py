@@ -538,16 +538,12 @@ class Bench:
         gather = None
         if strong:
             # the final result gather of north_star: the compact shards to rank 0's HBM over NCCL / NVLink
-            sizes = [sharding.shard_range(n_total, r, self.world) for r in range(self.world)]
-            width = max(b - a for a, b in sizes)
-            full = [torch.empty((nn, width), dtype=torch.int32, device="cuda") for _ in range(self.world)] if self.rank == 0 else None
-            mine = torch.empty((nn, width), dtype=torch.int32, device="cuda")
+            rg = sharding.RootGather(n_total, nn, torch.int32, torch.device("cuda"), self.dist, dst=0)
 
             def gather():
-                mine[:, :n].copy_(nars[0], non_blocking=True)
-                self.dist.gather(mine, full, dst=0)
-            extra["gather_keep"] = (full, mine)
-            extra["gather_bytes"] = nn * 4 * (n_total - (sizes[0][1] - sizes[0][0]))
+                rg(nars[0])
+            extra["gather_keep"] = rg
+            extra["gather_bytes"] = rg.bytes_into_root
         return dict(step=step, step_e2e=step_e2e, units=n, units_total=n_total if strong else n * self.world,
                     h2d=5 * 9 * 8 * n, d2h=nn * 4 * n + 4 * n, d2h_compact=nn * 4 * n + nw * 8 * n + 4 * n,
                     d2h_plain=slots * 8 * n + 4 * n, e2e_keep=(hn, in_arr),

@@ -756,8 +756,19 @@ __device__ __noinline__ W9E nl_mulw(EM em, int f, int c, int m, W9 x, W9 y) {
   for (int l = 0; l < NL; l++) ret.r.v[l] = r[l];
   return ret;
 }
+#ifndef P2E_INLINE_ADDSUB
+#define P2E_INLINE_ADDSUB 0
+#endif
+#ifndef P2E_EXPAND_CTAS
+#define P2E_EXPAND_CTAS 3
+#endif
+#if P2E_INLINE_ADDSUB
+#define P2E_ADDSUB_ATTR __forceinline__
+#else
+#define P2E_ADDSUB_ATTR __noinline__
+#endif
 template <class EM, bool IS_SUB>
-__device__ __noinline__ W9 nl_addsub(EM em, int f, int c, W9 a, W9 b) {
+__device__ P2E_ADDSUB_ATTR W9 nl_addsub(EM em, int f, int c, W9 a, W9 b) {
   W9 r;
   const u32 ov = IS_SUB ? sub_witness_core<ModP>(a.v, b.v, r.v) : add_witness_core<ModP>(a.v, b.v, r.v);
   em.val(f, c, r.v, ov);
@@ -902,7 +913,7 @@ __device__ __forceinline__ u32 expand_op(const ChainArgs& A, const EM& em, const
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(128, 3) k_chain_expand(ChainArgs A) {
+__global__ void __launch_bounds__(128, P2E_EXPAND_CTAS) k_chain_expand(ChainArgs A) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int k = blockIdx.y;
   if (i >= A.n) return;

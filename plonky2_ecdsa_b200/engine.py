@@ -40,7 +40,7 @@ GATE_MUL_NONNATIVE, GATE_CHECK_SUM, GATE_UX = 0, 1, 2
 MUL_OUT_R, MUL_OUT_Q, MUL_OUT_CHECK_SUM, MUL_OUT_CARRY, MUL_OUT_ROWS = 0, 9, 18, 35, 51
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libp2e.so")
+LIB_PATH = os.environ.get("P2E_LIB") or os.path.join(_HERE, "libp2e.so")      # P2E_LIB: an experiment build (scripts/build_variant.sh)
 
 _u64p = ctypes.POINTER(ctypes.c_uint64)
 _u32p = ctypes.POINTER(ctypes.c_uint32)

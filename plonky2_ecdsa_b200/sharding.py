@@ -50,3 +50,32 @@ def run_sharded(n: int, compute, dist=None, gather_results: bool = False, device
     dist.all_gather(partsm, minem)
     full = np.concatenate([p.cpu().numpy()[:, : b - a] for p, (a, b) in zip(partsm, sizes)], axis=1).view(np.uint64)
     return full, err_all, (lo, hi)
+
+
+class RootGather:
+    """The final result gather of the path (north_star: "only a final result gather, NCCL over NVLink only for that"):
+    the column shards [rows][hi-lo] of every rank into rank `dst`'s memory as one [rows][n] matrix.  Buffers are
+    allocated once (padded to the widest shard: ragged sizes allowed) and reused by every call; `dist` is
+    torch.distributed (NCCL with CUDA tensors, gloo with CPU tensors)."""
+
+    def __init__(self, n: int, rows: int, dtype, device, dist, dst: int = 0):
+        import torch
+        self.dist, self.dst, self.n, self.rows = dist, dst, n, rows
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.sizes = [shard_range(n, r, self.world) for r in range(self.world)]
+        self.width = max(b - a for a, b in self.sizes)
+        self.mine = torch.zeros((rows, self.width), dtype=dtype, device=device)
+        self.parts = [torch.empty((rows, self.width), dtype=dtype, device=device) for _ in range(self.world)] if self.rank == dst else None
+        self.bytes_into_root = sum((b - a) for r, (a, b) in enumerate(self.sizes) if r != dst) * rows * self.mine.element_size()
+
+    def __call__(self, local):
+        """local: this rank's [rows][hi-lo] tensor.  Enqueues the copy + gather; on `dst` the shards are then in
+        `self.parts` (padded); `assemble()` returns the [rows][n] matrix."""
+        lo, hi = self.sizes[self.rank]
+        self.mine[:, : hi - lo].copy_(local, non_blocking=True)
+        self.dist.gather(self.mine, self.parts, dst=self.dst)
+
+    def assemble(self):
+        import torch
+        assert self.rank == self.dst
+        return torch.cat([p[:, : b - a] for p, (a, b) in zip(self.parts, self.sizes)], dim=1)

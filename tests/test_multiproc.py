@@ -34,7 +34,12 @@ def _worker(rank, world, port, n, q):
         return U.expect_mul(x[:, lo:hi], y[:, lo:hi], 0)
     full, err_all, (lo, hi) = sharding.run_sharded(n, compute, dist=dist, gather_results=True)
     local, err2, _ = sharding.run_sharded(n, compute, dist=dist, gather_results=False)
-    q.put((rank, lo, hi, full, err_all, local, err2))
+    # the bench's strong-scaling gather: column shards of a uint32 matrix into rank 0
+    g = sharding.RootGather(n, 51, torch.int64, torch.device("cpu"), dist, dst=0)
+    g(torch.from_numpy(local.view(np.int64).copy()))
+    g(torch.from_numpy(local.view(np.int64).copy()))          # buffers are reusable
+    rooted = g.assemble().numpy().view(np.uint64) if rank == 0 else None
+    q.put((rank, lo, hi, full, err_all, local, err2, rooted))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,8 +63,11 @@ def test_world_size_2_sharding_and_gather(n):
     x, y = W.mulmod_workload(n, 0, seed=11)
     eo, ee = U.expect_mul(x, y, 0)
     cover = []
-    for rank, lo, hi, full, err_all, local, err2 in res:
+    for rank, lo, hi, full, err_all, local, err2, rooted in res:
         assert np.array_equal(full, eo) and np.array_equal(err_all, ee) and np.array_equal(err2, ee)
+        assert (rooted is None) == (rank != 0)
+        if rooted is not None:
+            assert np.array_equal(rooted, eo)
         assert np.array_equal(local, eo[:, lo:hi])
         cover.append((lo, hi))
     assert sorted(cover) == [(0, n // 2), (n // 2, n)]

@@ -134,3 +134,30 @@ def test_lde_feeds_the_gate_evaluator(engine):
     # undo the coset: values of t on g*H_m -> coefficients of t(g x) -> high coefficients must be zero
     t_coeffs = engine.fft(t_vals, inverse=True)
     assert not t_coeffs[:, n:].any()
+
+
+@pytest.mark.gpu
+def test_lde_after_device_context_is_rebuilt(engine):
+    """Per-device library state (twiddle tables, the > 48 KB dynamic shared memory opt-in of the NTT kernels, chain arenas)
+    must follow the context: release the device's context, create it again (on the LAST visible device when there are
+    several -- a device the process has not used yet), run an LDE that needs the opt-in and a chain witness."""
+    import torch
+    from plonky2_ecdsa_b200 import workload as W
+    from tests import util as U
+    dev = torch.cuda.device_count() - 1
+    vals = [(i * i * 131 + 7) % P for i in range(1 << 13)]          # 2^13 -> 2^16: lines of 2^8, > 48 KB tiles
+    want = N.lde_onto_coset(vals, 3)
+    if dev == 0:
+        assert engine.lib.p2e_shutdown_device(0) == 0
+    e2 = pkg.Engine(dev)
+    try:
+        lde = e2.lde_onto_coset(np.array([vals], dtype=np.uint64), 3)
+        assert [int(v) for v in lde[0]] == want
+        x, y = W.mulmod_workload(64, 0, seed=5)
+        out, err = e2.mul_nonnative(0, x, y)
+        eo, ee = U.expect_mul(x, y, 0)
+        assert np.array_equal(out, eo) and np.array_equal(err, ee)
+    finally:
+        if dev != 0:
+            e2.close()
+        engine.select()
