@@ -219,6 +219,9 @@ class Bench:
             self.dist = dist
         self.eng = pkg.Engine(self.local_rank)
         self.lib = self.eng.lib
+        for opt in ("chain_split",):                       # experiment hook: P2E_OPT_CHAIN_SPLIT=0
+            if os.environ.get("P2E_OPT_" + opt.upper()) is not None:
+                self.eng.set_option(opt, int(os.environ["P2E_OPT_" + opt.upper()]))
         self.st = torch.cuda.Stream()          # a real (non-NULL) stream: NULL selects the library's own
         torch.cuda.set_stream(self.st)
         self.sp = self.st.cuda_stream

@@ -74,7 +74,8 @@ int p2e_device_count(void);
 int p2e_synchronize(void);              /* the current device's library stream */
 /* Tunables (process-wide; defaults in parentheses): "chain_chunk" (65536) signatures per scratch chunk of the chain
  * kernels; "host_chunks" (4) D2H / compute pipeline depth of p2e_tape_witness_compact; "genstream_fused" (1) and
- * "genstream_graph" (1) executor forms of p2e_genstream_run*; "ntt_log_tile" (12).  Nothing is read from the
+ * "genstream_graph" (1) executor forms of p2e_genstream_run*; "ntt_log_tile" (12); "chain_trace" (0) diagnostic timeline; "chain_split" (1) run the
+ * per-signature kernels of a chain call on an internal high-priority stream and the full-GPU kernels on a low-priority one.  Nothing is read from the
  * environment. */
 int p2e_set_option(const char* name, long value);
 long p2e_get_option(const char* name);
@@ -421,12 +422,18 @@ int p2e_coset_lde(int log_n, int rate_bits, int n_polys, const uint64_t* values,
  * Returns the number of kernels written (<= cap), or a negative error. */
 int p2e_set_profiling(int on);
 int p2e_last_kernel_times(float* ms, int cap);
+/* Timeline of pipelined chain calls: with p2e_set_option("chain_trace", 1) every chain call records a timing event
+ * after each of its kernels on the internal stream that ran it.  p2e_chain_trace_dump synchronises the device and
+ * returns (call index, kernel id, ms since the first event) triples, then clears the trace.  Kernel ids: 0 call start,
+ * 1 k_prep done, 2 k_chain_replay done, 3 join done, 4 k_chain_invert_* done, 5 full-GPU phase may start,
+ * 6 k_chain_affine done, 7 k_chain_expand done. */
+int p2e_chain_trace_dump(int* calls, int* kernels, float* ms, int cap);
 /* Dependent-free IMAD / IMAD.WIDE throughput microbenchmark on the current device; returns
  * giga-ops per second (one op = one 32-bit lane multiply-add), or a negative error. */
 double p2e_bench_imad(int wide, int iters);
 /* Test hook: runs one operation of the saturated 8 x 32-bit field (csrc/p2e_f8.cuh, PTX carry-chain bodies) on the
  * device for n operand pairs; a, b, out: [n][9] uint32, 8 words used.  op: 0 mul, 1 sqr, 2 add, 3 sub, 4..7 times
- * 2 / 3 / 4 / 8, 8 canonical form, 11 inverse.  tests/test_gpu_f8.py compares with the portable bodies. */
+ * 2 / 3 / 4 / 8, 8 canonical form, 11 inverse, 12 / 13 remainder / quotient of a * b by p.  tests/test_gpu_f8.py compares with the portable bodies. */
 int p2e_debug_f8(int op, size_t n, const uint32_t* a, const uint32_t* b, uint32_t* out);
 
 #ifdef __cplusplus

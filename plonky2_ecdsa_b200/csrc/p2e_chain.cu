@@ -756,19 +756,10 @@ __device__ __noinline__ W9E nl_mulw(EM em, int f, int c, int m, W9 x, W9 y) {
   for (int l = 0; l < NL; l++) ret.r.v[l] = r[l];
   return ret;
 }
-#ifndef P2E_INLINE_ADDSUB
-#define P2E_INLINE_ADDSUB 0
-#endif
-#ifndef P2E_EXPAND_CTAS
-#define P2E_EXPAND_CTAS 3
-#endif
-#if P2E_INLINE_ADDSUB
-#define P2E_ADDSUB_ATTR __forceinline__
-#else
-#define P2E_ADDSUB_ATTR __noinline__
-#endif
+// add / sub tuples are small (~80 instructions): inlined, the ~30 register moves of a by-value call disappear
+// (r02b: 0.807 -> 0.789 ms per batch); 3 CTAs per SM: 4 (128 registers) is faster alone but not in the pipelined mix
 template <class EM, bool IS_SUB>
-__device__ P2E_ADDSUB_ATTR W9 nl_addsub(EM em, int f, int c, W9 a, W9 b) {
+__device__ __forceinline__ W9 nl_addsub(EM em, int f, int c, W9 a, W9 b) {
   W9 r;
   const u32 ov = IS_SUB ? sub_witness_core<ModP>(a.v, b.v, r.v) : add_witness_core<ModP>(a.v, b.v, r.v);
   em.val(f, c, r.v, ov);
@@ -913,7 +904,7 @@ __device__ __forceinline__ u32 expand_op(const ChainArgs& A, const EM& em, const
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(128, P2E_EXPAND_CTAS) k_chain_expand(ChainArgs A) {
+__global__ void __launch_bounds__(128, 3) k_chain_expand(ChainArgs A) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int k = blockIdx.y;
   if (i >= A.n) return;
@@ -960,6 +951,12 @@ __global__ void k_debug_f8(int op, size_t n, const u32* __restrict__ a, const u3
   else if (op == 7) f8_mul_small<8>(x, r);
   else if (op == 8) { f8_copy(x, r); f8_canon(r); }
   else if (op == 11) { F8 t = f8_inv_calls(f8w(x)); f8_copy(t.v, r); }
+  else if (op == 12 || op == 13) {                     // divmod16 of the wide product: 12 -> remainder, 13 -> quotient
+    u32 t[16], rr[NW], qq[NW];
+    f8_mul_wide(x, y, t);
+    f8_divmod16(t, rr, qq);
+    f8_copy(op == 12 ? rr : qq, r);
+  }
   for (int l = 0; l < NW; l++) out[9 * i + l] = r[l];
   out[9 * i + 8] = 0;
 }
@@ -996,6 +993,11 @@ struct ChainState {
   uint64_t tick = 0;
   bool profiling = false;
   std::vector<cudaEvent_t> events;
+  // diagnostic timeline (p2e_set_option("chain_trace", 1)): a timing event after every kernel of every call, on the
+  // stream the kernel was launched on -- shows how the batches of a pipelined run interleave (p2e_chain_trace_dump)
+  struct TraceEv { int call, kernel; cudaEvent_t ev; };
+  std::vector<TraceEv> trace;
+  int trace_calls = 0;
   // host-pointer compact path: copy stream + per-chunk events
   cudaStream_t cp = nullptr;
   cudaEvent_t ev_done[8] = {};
@@ -1178,6 +1180,7 @@ void chain_release_device(Context& c) {
     if (kv.second.ready && kv.second.blob) cudaFree(kv.second.blob);
   for (auto& a : S->arenas) arena_free(a);
   for (auto e : S->events) cudaEventDestroy(e);
+  for (auto& t : S->trace) cudaEventDestroy(t.ev);
   if (S->cp) cudaStreamDestroy(S->cp);
   for (auto& e : S->ev_done) if (e) cudaEventDestroy(e);
   delete S;
@@ -1190,6 +1193,14 @@ static void prof_mark(ChainState& S, cudaStream_t st) {
   cudaEventCreate(&e);
   cudaEventRecord(e, st);
   S.events.push_back(e);
+}
+
+static void trace_mark(ChainState& S, bool on, int call, int kernel, cudaStream_t st) {
+  if (!on || S.trace.size() > 100000) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  S.trace.push_back({call, kernel, e});
 }
 
 static size_t chunk_capacity() {
@@ -1228,7 +1239,7 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
   if ((rc = get_arena(S, st, bytes, &arena))) return rc;
   void* scratch = arena->ptr;
   // profiling keeps everything on the caller's stream so the events bracket each kernel
-  const bool split = !S.profiling;
+  const bool split = !S.profiling && option(OPT_CHAIN_SPLIT) != 0;
   cudaStream_t s_hi = split ? arena->hi : st, s_lo = split ? arena->lo : st;
   if (split) {
     P2E_CUDA(cudaEventRecord(arena->ev_in, st));
@@ -1256,6 +1267,9 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
   A.GP = w; w += (size_t)G * NW * cap;
   A.GI = w; w += (size_t)G * NW * cap;
   A.BAD = w;
+  const bool tr = option(OPT_CHAIN_TRACE) != 0 && !S.profiling;
+  const int call_id = tr ? S.trace_calls++ : 0;
+  trace_mark(S, tr, call_id, 0, s_hi);
   for (size_t c0 = 0; c0 < n; c0 += cap) {
     size_t cn = (n - c0 < cap) ? n - c0 : cap;
     A.n = cn;
@@ -1282,26 +1296,33 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
       }
       k_prep<<<g32, 32, 0, s_hi>>>(A);
       if (prof) prof_mark(S, st);
+      trace_mark(S, tr, call_id, 1, s_hi);
       if (no) {
         const unsigned g_duo = (unsigned)((2 * cn + 63) / 64);
         k_chain_replay<<<dim3(g_duo, 2), 64, 0, s_hi>>>(A, 0);      // fixed-base and msm chains side by side, 2 lanes each
         if (prof) prof_mark(S, st);
+        trace_mark(S, tr, call_id, 2, s_hi);
         if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g_duo, 1), 64, 0, s_hi>>>(A, 2);   // join
         if (prof) prof_mark(S, st);
+        trace_mark(S, tr, call_id, 3, s_hi);
         k_chain_invert_up<<<dim3(g32, G), 32, 0, s_hi>>>(A);
         k_chain_invert_mid<<<g32, 32, 0, s_hi>>>(A, (int)G);
         k_chain_invert_down<<<dim3(g32, G), 32, 0, s_hi>>>(A);
         if (prof) prof_mark(S, st);
+        trace_mark(S, tr, call_id, 4, s_hi);
         if (split) {
           P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
           P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
         }
         const unsigned tpb = 128, gw = (unsigned)((cn + tpb - 1) / tpb);
+        trace_mark(S, tr, call_id, 5, s_lo);        // s_lo has waited for ev_mid here: start of the full-GPU phase
         k_chain_affine<<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
         if (prof) prof_mark(S, st);
+        trace_mark(S, tr, call_id, 6, s_lo);
         if (A.fmt == FMT_PLAIN) k_chain_expand<FMT_PLAIN><<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
         else k_chain_expand<FMT_COMPACT><<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
         if (prof) prof_mark(S, st);
+        trace_mark(S, tr, call_id, 7, s_lo);
       } else if (split) {
         P2E_CUDA(cudaEventRecord(arena->ev_mid, s_hi));
         P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
@@ -1361,6 +1382,32 @@ int p2e_last_kernel_times(float* ms, int cap) {
     P2E_CUDA(cudaEventElapsedTime(&t, S.events[j], S.events[j + 1]));
     ms[k] = t;
   }
+  return k;
+}
+
+// diagnostic: events of the traced calls as (call, kernel id, ms since the first event); kernel ids: 0 call start,
+// 1 k_prep done, 2 replay done, 3 join done, 4 invert done, 5 full-GPU phase may start, 6 affine done, 7 expand done.
+// Synchronises the device; clears the trace.  Returns the number of entries written.
+int p2e_chain_trace_dump(int* calls, int* kernels, float* ms, int cap) {
+  int rc = ensure_ready();
+  if (rc) return rc;
+  ChainState& S = chain_state();
+  std::lock_guard<std::mutex> lock(S.mu);
+  P2E_CUDA(cudaDeviceSynchronize());
+  int k = 0;
+  for (size_t j = 0; j < S.trace.size(); j++) {
+    if (k < cap) {
+      float t = 0;
+      cudaEventElapsedTime(&t, S.trace[0].ev, S.trace[j].ev);
+      calls[k] = S.trace[j].call;
+      kernels[k] = S.trace[j].kernel;
+      ms[k] = t;
+      k++;
+    }
+  }
+  for (auto& t : S.trace) cudaEventDestroy(t.ev);
+  S.trace.clear();
+  S.trace_calls = 0;
   return k;
 }
 

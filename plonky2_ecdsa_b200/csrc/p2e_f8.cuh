@@ -143,16 +143,10 @@ P2E_HD void f8p_canon(u32 (&r)[8]) {
 // (weight 2^(32 (i+j))), `o` those with i + j odd (array index = i + j - 1).  A row whose top pair has a fresh
 // (zero) high word cannot carry out (x + (2^32-1)^2 + 1 < 2^64); the other rows carry into a fresh word.
 #ifdef __CUDA_ARCH__
-#define F8_ROW4_FIRST(e0, e1, e2, e3, e4, e5, e6, e7, a0, a1, a2, a3, b)                                          \
-  asm("mul.lo.u32 %0, %8, %12;\n\tmul.hi.u32 %1, %8, %12;\n\tmul.lo.u32 %2, %9, %12;\n\tmul.hi.u32 %3, %9, %12;\n\t" \
-      "mul.lo.u32 %4, %10, %12;\n\tmul.hi.u32 %5, %10, %12;\n\tmul.lo.u32 %6, %11, %12;\n\tmul.hi.u32 %7, %11, %12;" \
-      : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3), "=r"(e4), "=r"(e5), "=r"(e6), "=r"(e7)                           \
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b))
-#define F8_ROW3_FIRST(e0, e1, e2, e3, e4, e5, a0, a1, a2, b)                                                      \
-  asm("mul.lo.u32 %0, %6, %9;\n\tmul.hi.u32 %1, %6, %9;\n\tmul.lo.u32 %2, %7, %9;\n\tmul.hi.u32 %3, %7, %9;\n\t"   \
-      "mul.lo.u32 %4, %8, %9;\n\tmul.hi.u32 %5, %8, %9;"                                                          \
-      : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3), "=r"(e4), "=r"(e5)                                               \
-      : "r"(a0), "r"(a1), "r"(a2), "r"(b))
+#define F8_ROW4_FIRST(e0, e1, e2, e3, e4, e5, e6, e7, a0, a1, a2, a3, b) \
+  asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %8, %12;\n\tmov.b64 {%0, %1}, t;\n\tmul.wide.u32 t, %9, %12;\n\tmov.b64 {%2, %3}, t;\n\tmul.wide.u32 t, %10, %12;\n\tmov.b64 {%4, %5}, t;\n\tmul.wide.u32 t, %11, %12;\n\tmov.b64 {%6, %7}, t;\n\t}" : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3), "=r"(e4), "=r"(e5), "=r"(e6), "=r"(e7) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b))
+#define F8_ROW3_FIRST(e0, e1, e2, e3, e4, e5, a0, a1, a2, b) \
+  asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %6, %9;\n\tmov.b64 {%0, %1}, t;\n\tmul.wide.u32 t, %7, %9;\n\tmov.b64 {%2, %3}, t;\n\tmul.wide.u32 t, %8, %9;\n\tmov.b64 {%4, %5}, t;\n\t}" : "=r"(e0), "=r"(e1), "=r"(e2), "=r"(e3), "=r"(e4), "=r"(e5) : "r"(a0), "r"(a1), "r"(a2), "r"(b))
 #define F8_ROW4_NC(e0, e1, e2, e3, e4, e5, e6, e7, a0, a1, a2, a3, b)                                             \
   asm("mad.lo.cc.u32 %0, %8, %12, %0;\n\tmadc.hi.cc.u32 %1, %8, %12, %1;\n\t"                                     \
       "madc.lo.cc.u32 %2, %9, %12, %2;\n\tmadc.hi.cc.u32 %3, %9, %12, %3;\n\t"                                    \
@@ -497,8 +491,71 @@ P2E_HD void l29_to_words(const u32 (&T)[18], u32 (&W)[NW]) {
   }
 }
 
-// (q, r) = divmod(W, p) for W < 2^512 with q < 2^256 (guaranteed when both factors are < p); portable body
+#ifdef __CUDA_ARCH__
+// PTX body of f8_divmod16 (same function as the portable one below: r canonical, q exact)
+__device__ __forceinline__ u32 f8d_divmod16(const u32 (&t)[16], u32 (&r)[8], u32 (&q)[8]) {
+  u32 e[9], o[9];
+  asm("mad.lo.cc.u32 %0, %9, %13, %14;\n\tmadc.hi.cc.u32 %1, %9, %13, %15;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %16;\n\tmadc.hi.cc.u32 %3, %10, %13, %17;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %18;\n\tmadc.hi.cc.u32 %5, %11, %13, %19;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %20;\n\tmadc.hi.cc.u32 %7, %12, %13, %21;\n\taddc.u32 %8, 0, 0;"
+      : "=&r"(e[0]), "=&r"(e[1]), "=&r"(e[2]), "=&r"(e[3]), "=&r"(e[4]), "=&r"(e[5]), "=&r"(e[6]), "=&r"(e[7]), "=&r"(e[8])
+      : "r"(t[8]), "r"(t[10]), "r"(t[12]), "r"(t[14]), "r"(F8_C), "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]),
+        "r"(t[5]), "r"(t[6]), "r"(t[7]));
+  asm("mad.lo.cc.u32 %0, %9, %13, %14;\n\tmadc.hi.cc.u32 %1, %9, %13, %15;\n\t"
+      "madc.lo.cc.u32 %2, %10, %13, %16;\n\tmadc.hi.cc.u32 %3, %10, %13, %17;\n\t"
+      "madc.lo.cc.u32 %4, %11, %13, %18;\n\tmadc.hi.cc.u32 %5, %11, %13, %19;\n\t"
+      "madc.lo.cc.u32 %6, %12, %13, %20;\n\tmadc.hi.cc.u32 %7, %12, %13, %21;\n\taddc.u32 %8, 0, 0;"
+      : "=&r"(o[0]), "=&r"(o[1]), "=&r"(o[2]), "=&r"(o[3]), "=&r"(o[4]), "=&r"(o[5]), "=&r"(o[6]), "=&r"(o[7]), "=&r"(o[8])
+      : "r"(t[9]), "r"(t[11]), "r"(t[13]), "r"(t[15]), "r"(F8_C), "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]),
+        "r"(t[13]), "r"(t[14]), "r"(t[15]));
+  u32 R[8], t8, t9;
+  R[0] = e[0];
+  asm("add.cc.u32 %0, %1, %2;" : "=r"(R[1]) : "r"(e[1]), "r"(o[0]));
+#pragma unroll
+  for (int k = 2; k < 8; k++) asm("addc.cc.u32 %0, %1, %2;" : "=r"(R[k]) : "r"(e[k]), "r"(o[k - 1]));
+  asm("addc.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(t8), "=r"(t9) : "r"(e[8]), "r"(o[7]), "r"(o[8]));
+  // S = R + (t8 + 2^32 t9)(2^32 + 977), then the wrap bit c8 once more (cannot carry past word 2)
+  u32 a0, a1, a2, c8, S[8];
+  asm("mul.lo.u32 %0, %3, %5;\n\tmul.hi.u32 %1, %3, %5;\n\tadd.cc.u32 %1, %1, %3;\n\taddc.u32 %2, %4, 0;\n\t"
+      "mad.lo.cc.u32 %1, %4, %5, %1;\n\taddc.u32 %2, %2, 0;"
+      : "=&r"(a0), "=&r"(a1), "=&r"(a2)
+      : "r"(t8), "r"(t9), "r"(F8_C));
+  asm("add.cc.u32 %0, %9, %17;\n\taddc.cc.u32 %1, %10, %18;\n\taddc.cc.u32 %2, %11, %19;\n\t"
+      "addc.cc.u32 %3, %12, 0;\n\taddc.cc.u32 %4, %13, 0;\n\taddc.cc.u32 %5, %14, 0;\n\t"
+      "addc.cc.u32 %6, %15, 0;\n\taddc.cc.u32 %7, %16, 0;\n\taddc.u32 %8, 0, 0;"
+      : "=r"(S[0]), "=r"(S[1]), "=r"(S[2]), "=r"(S[3]), "=r"(S[4]), "=r"(S[5]), "=r"(S[6]), "=r"(S[7]), "=r"(c8)
+      : "r"(R[0]), "r"(R[1]), "r"(R[2]), "r"(R[3]), "r"(R[4]), "r"(R[5]), "r"(R[6]), "r"(R[7]), "r"(a0), "r"(a1), "r"(a2));
+  asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\taddc.cc.u32 %1, %1, %3;\n\taddc.u32 %2, %2, 0;"
+      : "+r"(S[0]), "+r"(S[1]), "+r"(S[2])
+      : "r"(c8), "r"(F8_C));
+  // final conditional subtraction: S + (2^32 + 977) carries out iff S >= p
+  u32 w[8], fin;
+  asm("add.cc.u32 %0, %9, %17;\n\taddc.cc.u32 %1, %10, 1;\n\taddc.cc.u32 %2, %11, 0;\n\t"
+      "addc.cc.u32 %3, %12, 0;\n\taddc.cc.u32 %4, %13, 0;\n\taddc.cc.u32 %5, %14, 0;\n\t"
+      "addc.cc.u32 %6, %15, 0;\n\taddc.cc.u32 %7, %16, 0;\n\taddc.u32 %8, 0, 0;"
+      : "=&r"(w[0]), "=&r"(w[1]), "=&r"(w[2]), "=&r"(w[3]), "=&r"(w[4]), "=&r"(w[5]), "=&r"(w[6]), "=&r"(w[7]), "=&r"(fin)
+      : "r"(S[0]), "r"(S[1]), "r"(S[2]), "r"(S[3]), "r"(S[4]), "r"(S[5]), "r"(S[6]), "r"(S[7]), "r"(F8_C));
+#pragma unroll
+  for (int k = 0; k < 8; k++) r[k] = fin ? w[k] : S[k];
+  // q = H + t8 + 2^32 t9 + c8 + fin
+  u32 s0, s1, qov;
+  const u32 small = c8 + fin;
+  asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, 0;" : "=r"(s0), "=r"(s1) : "r"(t8), "r"(t9), "r"(small));
+  asm("add.cc.u32 %0, %9, %17;\n\taddc.cc.u32 %1, %10, %18;\n\taddc.cc.u32 %2, %11, 0;\n\t"
+      "addc.cc.u32 %3, %12, 0;\n\taddc.cc.u32 %4, %13, 0;\n\taddc.cc.u32 %5, %14, 0;\n\t"
+      "addc.cc.u32 %6, %15, 0;\n\taddc.cc.u32 %7, %16, 0;\n\taddc.u32 %8, 0, 0;"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(qov)
+      : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]), "r"(s0), "r"(s1));
+  return qov;
+}
+#endif
+
+// (q, r) = divmod(W, p) for W < 2^512 with q < 2^256 (guaranteed when both factors are < p)
 P2E_HD u32 f8_divmod16(const u32 (&t)[16], u32 (&r)[8], u32 (&q)[8]) {
+#ifdef __CUDA_ARCH__
+  return f8d_divmod16(t, r, q);
+#else
   u32 R[8];
   u64 c = 0;
 #pragma unroll
@@ -553,6 +610,7 @@ P2E_HD u32 f8_divmod16(const u32 (&t)[16], u32 (&r)[8], u32 (&q)[8]) {
     cc = v >> 32;
   }
   return (u32)cc;     // quotient overflow (never for factors < p)
+#endif
 }
 
 // A8 + A9 for factors below 2^256 with q < 2^256 (chain kernel K4: every operand is a canonical generator output).
@@ -561,8 +619,9 @@ P2E_HD u32 f8_divmod16(const u32 (&t)[16], u32 (&r)[8], u32 (&q)[8]) {
 P2E_HD u32 mulw_p_fast(const u32 (&x)[NL], const u32 (&y)[NL], u32 (&r)[NL], u32 (&q)[NL], i64 (&v)[17], u32 (&blo)[16], u32& tops) {
   u64 X[17];
   mul_cols(x, y, X);
-  u32 T[18];
+  u32 W[16], r8[8], q8[8];
   {
+    u32 T[18];
     u64 c = 0;
 #pragma unroll
     for (int i = 0; i < 17; i++) {
@@ -571,9 +630,8 @@ P2E_HD u32 mulw_p_fast(const u32 (&x)[NL], const u32 (&y)[NL], u32 (&r)[NL], u32
       c = s >> LB;
     }
     T[17] = (u32)c;
+    l29_to_words<16>(T, W);
   }
-  u32 W[16], r8[8], q8[8];
-  l29_to_words<16>(T, W);
   u32 bad = f8_divmod16(W, r8, q8);
   f8_to_l29(r8, r);
   f8_to_l29(q8, q);
@@ -591,20 +649,21 @@ P2E_HD u32 mulw_p_fast(const u32 (&x)[NL], const u32 (&y)[NL], u32 (&r)[NL], u32
     a += (u64)S * LMASK;
     v[i] = (i64)a;
   }
+  // exact carries c_i = (v_i + c_{i-1}) >> 29 (the partial sums are multiples of 2^29 because x y = q p + r holds as
+  // integers; the last column closes the chain, checked once); b_i = c_i + 2^33 as low word + two top bits
   i64 c = 0;
-  u32 low = 0, tp = 0;
+  u32 tp = 0, hacc = 0;
 #pragma unroll
   for (int i = 0; i < 16; i++) {
-    i64 s = v[i] + c;
-    low |= (u32)s;
+    const i64 s = v[i] + c;
     c = s >> LB;
-    u64 o = (u64)(c + ((i64)1 << 33));
-    blo[i] = (u32)o;
-    tp |= ((u32)(o >> 32)) << (2 * i);     // o < 2^34 for in-range carries (checked below through bit growth)
-    bad |= (u32)(o >> 34);
+    blo[i] = (u32)c;                               // + 2^33 does not touch the low word
+    const u32 h = (u32)((u64)c >> 32) + 2u;        // top word of c + 2^33: 0..3 for |c| <= 2^33
+    hacc |= h;
+    tp += h << (2 * i);
   }
   tops = tp;
-  bad |= (low & LMASK) | (u32)((u64)(v[16] + c) != 0);
+  bad |= (hacc >> 2) | (u32)((u64)(v[16] + c) != 0);
   return bad ? ERR_INTERNAL : 0u;
 }
 

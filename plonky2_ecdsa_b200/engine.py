@@ -158,6 +158,7 @@ SIGNATURES = {
     "p2e_coset_lde": (_int, [_int, _int, _int, _vp, _vp]),
     "p2e_set_profiling": (_int, [_int]),
     "p2e_last_kernel_times": (_int, [_vp, _int]),
+    "p2e_chain_trace_dump": (_int, [_vp, _vp, _vp, _int]),
     "p2e_bench_imad": (ctypes.c_double, [_int, _int]),
 }
 

@@ -37,3 +37,16 @@ def test_f8_inverse_ladder(engine):
     assert engine.lib.p2e_debug_f8(11, len(vals), a.ctypes.data, a.ctypes.data, out.ctypes.data) == 0
     for x, g in zip(vals, _from_words(out)):
         assert (g * x) % P_SECP == 1
+
+
+def test_f8_divmod16_ptx_body(engine):
+    """(q, r) = divmod(a * b, p) on the device (PTX body) against Python integers; factors below p so that q < 2^256."""
+    rng = random.Random(12)
+    vals = [0, 1, P_SECP - 1, P_SECP - 2, (1 << 32) + 977, 1 << 255, (1 << 128) - 1]
+    pairs = [(a, b) for a in vals for b in vals] + [(rng.randrange(P_SECP), rng.randrange(P_SECP)) for _ in range(20000)]
+    a, b = _words([p[0] for p in pairs]), _words([p[1] for p in pairs])
+    rem, quo = np.zeros_like(a), np.zeros_like(a)
+    assert engine.lib.p2e_debug_f8(12, len(pairs), a.ctypes.data, b.ctypes.data, rem.ctypes.data) == 0
+    assert engine.lib.p2e_debug_f8(13, len(pairs), a.ctypes.data, b.ctypes.data, quo.ctypes.data) == 0
+    for (x, y), r, q in zip(pairs, _from_words(rem), _from_words(quo)):
+        assert (q, r) == divmod(x * y, P_SECP)
