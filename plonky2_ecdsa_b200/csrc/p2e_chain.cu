@@ -935,6 +935,12 @@ __global__ void __launch_bounds__(32) k_chain_checks(ChainArgs A) {
   if (bad) A.err[i] |= ERR_CONNECT;
 }
 
+// diagnostic runs that skip kernels (option chain_phases != 63) never return a usable witness: every row is flagged
+__global__ void k_chain_poison(size_t n, u32* err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) err[i] |= (u32)ERR_INTERNAL;
+}
+
 // test hook: the PTX bodies of p2e_f8.cuh on the device (op codes of tests/hostcheck hc_f8)
 __global__ void k_debug_f8(int op, size_t n, const u32* __restrict__ a, const u32* __restrict__ b, u32* __restrict__ out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1286,6 +1292,9 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
       prof_mark(S, st);
     }
     const int n_rounds = (int)t.n_rounds;
+    // diagnostic (scripts/chain_phases.py): bit mask of the kernels to launch -- 1 prep, 2 replay + join, 4 invert, 8 affine,
+    // 16 expand, 32 checks.  Anything but 63 skips work: every row of the call is then flagged ERR_INTERNAL.
+    const unsigned pm = (unsigned)option(OPT_CHAIN_PHASES) & 63u;
     for (int round = 0; round < n_rounds; round++) {
       // Round r: generators of round r (K0), then the curve ops of round r (K1-K4).  A later round
       // consumes coordinates written by this round's expansion, so it waits for the low-priority stream.
@@ -1294,20 +1303,22 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
         P2E_CUDA(cudaEventRecord(arena->ev_out, s_lo));
         P2E_CUDA(cudaStreamWaitEvent(s_hi, arena->ev_out, 0));
       }
-      k_prep<<<g32, 32, 0, s_hi>>>(A);
+      if (pm & 1) k_prep<<<g32, 32, 0, s_hi>>>(A);
       if (prof) prof_mark(S, st);
       trace_mark(S, tr, call_id, 1, s_hi);
       if (no) {
         const unsigned g_duo = (unsigned)((2 * cn + 63) / 64);
-        k_chain_replay<<<dim3(g_duo, 2), 64, 0, s_hi>>>(A, 0);      // fixed-base and msm chains side by side, 2 lanes each
+        if (pm & 2) k_chain_replay<<<dim3(g_duo, 2), 64, 0, s_hi>>>(A, 0);      // fixed-base and msm chains side by side, 2 lanes each
         if (prof) prof_mark(S, st);
         trace_mark(S, tr, call_id, 2, s_hi);
-        if (o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g_duo, 1), 64, 0, s_hi>>>(A, 2);   // join
+        if ((pm & 2) && o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g_duo, 1), 64, 0, s_hi>>>(A, 2);   // join
         if (prof) prof_mark(S, st);
         trace_mark(S, tr, call_id, 3, s_hi);
-        k_chain_invert_up<<<dim3(g32, G), 32, 0, s_hi>>>(A);
-        k_chain_invert_mid<<<g32, 32, 0, s_hi>>>(A, (int)G);
-        k_chain_invert_down<<<dim3(g32, G), 32, 0, s_hi>>>(A);
+        if (pm & 4) {
+          k_chain_invert_up<<<dim3(g32, G), 32, 0, s_hi>>>(A);
+          k_chain_invert_mid<<<g32, 32, 0, s_hi>>>(A, (int)G);
+          k_chain_invert_down<<<dim3(g32, G), 32, 0, s_hi>>>(A);
+        }
         if (prof) prof_mark(S, st);
         trace_mark(S, tr, call_id, 4, s_hi);
         if (split) {
@@ -1316,10 +1327,11 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
         }
         const unsigned tpb = 128, gw = (unsigned)((cn + tpb - 1) / tpb);
         trace_mark(S, tr, call_id, 5, s_lo);        // s_lo has waited for ev_mid here: start of the full-GPU phase
-        k_chain_affine<<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
+        if (pm & 8) k_chain_affine<<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
         if (prof) prof_mark(S, st);
         trace_mark(S, tr, call_id, 6, s_lo);
-        if (A.fmt == FMT_PLAIN) k_chain_expand<FMT_PLAIN><<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
+        if (!(pm & 16)) {
+        } else if (A.fmt == FMT_PLAIN) k_chain_expand<FMT_PLAIN><<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
         else k_chain_expand<FMT_COMPACT><<<dim3(gw, (unsigned)no), tpb, 0, s_lo>>>(A);
         if (prof) prof_mark(S, st);
         trace_mark(S, tr, call_id, 7, s_lo);
@@ -1328,7 +1340,8 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
         P2E_CUDA(cudaStreamWaitEvent(s_lo, arena->ev_mid, 0));
       }
     }
-    k_chain_checks<<<g32, 32, 0, s_lo>>>(A);
+    if (pm & 32) k_chain_checks<<<g32, 32, 0, s_lo>>>(A);
+    if (pm != 63u) k_chain_poison<<<g32, 32, 0, s_lo>>>(cn, A.err);
     if (prof) prof_mark(S, st);
     if (split && c0 + cap < n) {
       // next chunk reuses the scratch: its K0-K2 must not start before this chunk's K3-K5 are done

@@ -12,10 +12,10 @@ eng = pkg.Engine(0); lib = eng.lib
 dev = lambda a: torch.from_numpy(a.view(np.int64)).cuda()
 if what == "ecdsa":
     # one batch on the library stream with the per-kernel event marks on (keeps every kernel on ONE stream, in order)
-    n = 4096
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096          # a multiple of 4096: the 4096-signature workload tiled
     _, nn, nw = eng.tape_compact_layout(eng.TAPE_ECDSA)
-    d = W.ecdsa_workload(n, seed=W.SEED)
-    ind = [dev(d[k]) for k in ("msg", "r", "s", "pkx", "pky")]
+    d = W.ecdsa_workload(4096, seed=W.SEED)
+    ind = [dev(np.ascontiguousarray(np.tile(d[k], (1, n // 4096)))) for k in ("msg", "r", "s", "pkx", "pky")]
     nar = torch.empty((nn, n), dtype=torch.int32, device="cuda")
     ed = torch.empty(n, dtype=torch.int32, device="cuda")
     eng.set_profiling(True)
