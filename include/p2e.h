@@ -356,6 +356,15 @@ int p2e_ux_witness(int gate, int bits, int limb_bits, int count, int num_addends
 #define P2E_GEN_COPY 13
 #define P2E_GEN_CONSTANT 14
 #define P2E_GEN_ARITHMETIC 15
+/* plonky2 glue generators of the gadgets' scalar handling (restated, parity unpinned against the dependency):
+ *   P2E_GEN_BASE_SPLIT     BaseSplitGenerator<2> { usize row, usize num_limbs }: split_le_base::<2> (gadgets/split_nonnative.rs:29-37)
+ *   P2E_GEN_RANDOM_ACCESS  RandomAccessGenerator { usize row, usize bits, usize num_copies, usize num_extra_constants,
+ *                          usize copy }: random_access (gadgets/curve_windowed_mul.rs:97-104)
+ *   P2E_GEN_EQUALITY       EqualityGenerator { Target x, Target y, Target equal, Target inv }: is_equal
+ *                          (gadgets/curve_msm.rs:69, gadgets/curve_fixed_base.rs:57) */
+#define P2E_GEN_BASE_SPLIT 16
+#define P2E_GEN_RANDOM_ACCESS 17
+#define P2E_GEN_EQUALITY 18
 int p2e_genstream_load(const uint8_t* bytes, size_t len);          /* handle >= 0, or < 0 (p2e_last_error) */
 int p2e_genstream_free(int handle);
 long p2e_genstream_info(int handle, int what); /* 0 slots, 1 generators, 2 levels, 3 launch groups, 4 input slots, 5 targets */

@@ -316,6 +316,50 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_glv(GsIO io, int j0) {
   io.fail(i, e);
 }
 
+// ---- plonky2 glue generators (out of tree, restated) -----------------------------------
+// BaseSplitGenerator<2> { row, num_limbs }: BaseSumGate<2> wire 0 = sum -> wires 1 .. num_limbs = its bits (LE).
+// plonky2 asserts that the integer is fully consumed: a sum that does not fit sets P2E_ERR_LIMB_RANGE.
+__global__ void __launch_bounds__(GS_TPB) k_gs_base_split(GsIO io, int j0, int nl) {
+  GS_THREAD();
+  const u64 v = io.in(0, j, i);
+  u32 e = (nl < 64 && (v >> nl)) ? (u32)P2E_ERR_LIMB_RANGE : 0u;
+  for (int r = 0; r < nl; r++) e |= io.out(r, j, i, (v >> r) & 1ull);
+  io.fail(i, e);
+}
+
+// RandomAccessGenerator of one copy of a RandomAccessGate { bits }: claimed_element = list[access_index] and the
+// little-endian bits of access_index.  An index outside the list is a panic upstream: P2E_ERR_LIMB_RANGE.
+__global__ void __launch_bounds__(GS_TPB) k_gs_random_access(GsIO io, int j0, int bits) {
+  GS_THREAD();
+  const u64 idx = io.in(0, j, i);
+  const u64 vs = 1ull << bits;
+  u32 e = idx >= vs ? (u32)P2E_ERR_LIMB_RANGE : 0u;
+  const int k = (int)(idx & (vs - 1));
+  e |= io.out(0, j, i, io.in(1 + k, j, i));
+  for (int b = 0; b < bits; b++) e |= io.out(1 + b, j, i, (idx >> b) & 1ull);
+  io.fail(i, e);
+}
+
+__device__ u64 gs_inv(u64 x) {       // x^(P-2)
+  u64 r = 1, b = x;
+  const u64 e = GS_P - 2;
+  for (int k = 0; k < 64; k++) {
+    if ((e >> k) & 1) r = gs_mul(r, b);
+    b = gs_mul(b, b);
+  }
+  return r;
+}
+// EqualityGenerator { x, y, equal, inv }: equal = [x == y], inv = (x - y)^-1 or 0
+__global__ void __launch_bounds__(GS_TPB) k_gs_equality(GsIO io, int j0) {
+  GS_THREAD();
+  const u64 x = io.in(0, j, i), y = io.in(1, j, i);
+  u64 d = x - y;
+  if (x < y) d += GS_P;
+  u32 e = io.out(0, j, i, x == y ? 1ull : 0ull);
+  e |= io.out(1, j, i, x == y ? 0ull : gs_inv(d));
+  io.fail(i, e);
+}
+
 // ---- host: stream parsing ---------------------------------------------------------------------------------
 struct TargetKey {
   u64 is_wire, a, b;
@@ -350,7 +394,7 @@ struct Reader {
   }
 };
 
-enum GsKind { K_MUL, K_CHECKSUM, K_ADD, K_MULTIADD, K_SUB, K_INV, K_DIVREM, K_GLV, K_ARITH, K_CONST };
+enum GsKind { K_MUL, K_CHECKSUM, K_ADD, K_MULTIADD, K_SUB, K_INV, K_DIVREM, K_GLV, K_ARITH, K_CONST, K_BASESPLIT, K_RANDACC, K_EQUAL };
 
 struct GsGen {
   int kind, modulus;
@@ -466,6 +510,9 @@ static int rows_of(const GsGen& g, int* in_rows, int* out_rows) {
     case K_GLV: *in_rows = 9; *out_rows = 12; return 0;
     case K_ARITH: *in_rows = 3; *out_rows = 1; return 0;
     case K_CONST: *in_rows = 0; *out_rows = 1; return 0;
+    case K_BASESPLIT: *in_rows = 1; *out_rows = g.shape_a; return 0;
+    case K_RANDACC: *in_rows = 1 + (1 << g.shape_a); *out_rows = 1 + g.shape_a; return 0;
+    case K_EQUAL: *in_rows = 2; *out_rows = 2; return 0;
   }
   return -1;
 }
@@ -602,6 +649,42 @@ static bool parse_record(GenStream& S, Reader& R) {
       for (int c = 0; c < 3; c++) g.ins.push_back(wire(S, row, 4 * i + c));
       g.outs.push_back(wire(S, row, 4 * i + 3));
       g.c0 = c0; g.c1 = c1;
+      break;
+    }
+    case P2E_GEN_BASE_SPLIT: {
+      // plonky2 BaseSplitGenerator<2> { row, num_limbs } (restated): BaseSumGate::WIRE_SUM = 0, limbs 1 .. num_limbs
+      const u64 row = R.u64le(), nl = R.u64le();
+      if (!R.ok) return bad("truncated BaseSplitGenerator");
+      if (nl < 1 || nl > 63) return bad("BaseSplitGenerator: num_limbs must be 1..63");
+      g.kind = K_BASESPLIT;
+      g.shape_a = (int)nl;
+      g.ins.push_back(wire(S, row, 0));
+      for (u64 c = 0; c < nl; c++) g.outs.push_back(wire(S, row, 1 + c));
+      break;
+    }
+    case P2E_GEN_RANDOM_ACCESS: {
+      // plonky2 RandomAccessGenerator { row, gate { bits, num_copies, num_extra_constants }, copy } (restated); wire map
+      // of RandomAccessGate: access_index (2 + 2^bits) copy, claimed_element + 1, list items + 2 .., bits after the
+      // routed wires: (2 + 2^bits) num_copies + num_extra_constants + bits copy + i
+      const u64 row = R.u64le(), bits = R.u64le(), copies = R.u64le(), extra = R.u64le(), copy = R.u64le();
+      if (!R.ok) return bad("truncated RandomAccessGenerator");
+      if (bits < 1 || bits > 6 || copy >= copies || copies > 64 || extra > 64) return bad("RandomAccessGenerator: bad gate parameters");
+      const u64 vs = 1ull << bits, base = (2 + vs) * copy, bit0 = (2 + vs) * copies + extra + bits * copy;
+      g.kind = K_RANDACC;
+      g.shape_a = (int)bits;
+      g.ins.push_back(wire(S, row, base));
+      for (u64 k = 0; k < vs; k++) g.ins.push_back(wire(S, row, base + 2 + k));
+      g.outs.push_back(wire(S, row, base + 1));
+      for (u64 b = 0; b < bits; b++) g.outs.push_back(wire(S, row, bit0 + b));
+      break;
+    }
+    case P2E_GEN_EQUALITY: {
+      // plonky2 EqualityGenerator { x, y, equal (BoolTarget), inv } (restated)
+      const u32 x = read_target(S, R), y = read_target(S, R), eq = read_target(S, R), inv = read_target(S, R);
+      if (!R.ok) return bad("truncated EqualityGenerator");
+      g.kind = K_EQUAL;
+      g.ins = {x, y};
+      g.outs = {eq, inv};
       break;
     }
     default:
@@ -771,7 +854,7 @@ static int size_staging(GenStream& S, size_t n) {
   size_t need = 16, need_err = 16;
   const int per = per_launch(n);
   for (const GsGroup& G : S.groups) {
-    if (G.kind == K_ARITH || G.kind == K_CONST) continue;
+    if (G.kind == K_ARITH || G.kind == K_CONST || G.kind == K_BASESPLIT || G.kind == K_RANDACC || G.kind == K_EQUAL) continue;
     const size_t M = (size_t)std::min(G.m, per) * n;
     need = std::max(need, (size_t)(G.in_rows + G.out_rows) * M * 8);
     need_err = std::max(need_err, M * 4);
@@ -798,6 +881,17 @@ static int run_groups(GenStream& S, size_t n, u64* V, size_t vs, u32* err, cudaS
           // the index rows m0, m1, addend ([3][m]) and the output row follow each other in the pool: one [4][m] block
           k_gs_arith<<<dim3(gx, mc), GS_TPB, 0, st>>>(n, G.m, idx + j0, S.d_consts + G.const_off + j0, V, vs, err);
         }
+      }
+      P2E_CUDA(cudaGetLastError());
+      continue;
+    }
+    if (G.kind == K_BASESPLIT || G.kind == K_RANDACC || G.kind == K_EQUAL) {
+      GsIO io = {idx, oidx, V, vs, n, err, G.m};
+      for (int j0 = 0; j0 < G.m; j0 += 65535) {
+        const dim3 grid(gx, (unsigned)std::min(G.m - j0, 65535));
+        if (G.kind == K_BASESPLIT) k_gs_base_split<<<grid, GS_TPB, 0, st>>>(io, j0, G.shape_a);
+        else if (G.kind == K_RANDACC) k_gs_random_access<<<grid, GS_TPB, 0, st>>>(io, j0, G.shape_a);
+        else k_gs_equality<<<grid, GS_TPB, 0, st>>>(io, j0);
       }
       P2E_CUDA(cudaGetLastError());
       continue;

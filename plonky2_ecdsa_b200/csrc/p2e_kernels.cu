@@ -1,6 +1,7 @@
 // p2e_kernels.cu -- batched witness-generator kernels (one instance per thread, limbs in
 // registers, wire-major coalesced loads/stores), the gate constraint evaluators over
 // Goldilocks LDE rows, and their extern "C" entry points (include/p2e.h).
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include "../../include/p2e.h"
@@ -724,6 +725,9 @@ using namespace p2e;
 extern "C" {
 
 int p2e_init(int device) {
+  // the chain entry points pipeline independent batches on many streams: ask for the maximum number of hardware work
+  // queues unless the host already chose (only effective when the CUDA context does not exist yet)
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int cnt = 0;
   cudaError_t e = cudaGetDeviceCount(&cnt);
   if (e != cudaSuccess) return set_error("cudaGetDeviceCount", e);
