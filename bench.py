@@ -44,6 +44,8 @@ WORKLOAD_NAMES = {
     "evalrcfc": "u29 range-check gate (9 limbs, 3-bit aux limbs; plonky2_ux spec unpinned) eval_filtered + alpha-combination (2 challenges, fused) over 2^20 Goldilocks LDE rows",
     "genstream": "serialized generator stream (8 x curve_add + curve_double chained: 224 in-tree generators, target-level wiring of "
                  "gadgets/curve.rs) run by the level-scheduled executor for 4096 circuits",
+    "genstream_ecdsa": "the complete verify_secp256k1_message_circuit as a serialized generator stream (30955 generators incl. the plonky2 glue, "
+                       "1862 dependency levels) run by the level-scheduled executor for 4096 circuits",
     "lde": "coset LDE (ifft 2^17 -> zero-pad -> coset fft 2^20, rate 8) of 135 wire polynomials: the matrix the gate evaluators read",
 }
 # plonky2_ux eval workloads: (gate, bits, limb_bits, count, num_addends, kernel)
@@ -66,6 +68,7 @@ METRICS = {
     "evalcsfc": ("check_sum_gate_filtered_combined_rows_per_s", "rows/s"),
     "evalrcfc": ("ux_range_check_gate_filtered_combined_rows_per_s", "rows/s"),
     "genstream": ("generator_stream_circuits_per_s", "circuits/s"),
+    "genstream_ecdsa": ("generator_stream_ecdsa_circuits_per_s", "circuits/s"),
     "lde": ("coset_lde_output_elements_per_s", "elements/s"),
 }
 
@@ -387,6 +390,40 @@ class Bench:
                                            len(out_slots), ho.data_ptr(), he.data_ptr())
                 assert rc == 0, eng.last_error()
             # algorithmic bytes: every slot of the value table is written once and read about once
+            return dict(step=step, step_e2e=step_e2e, units=n, h2d=len(in_slots) * 8 * n, d2h=len(out_slots) * 8 * n + 4 * n,
+                        alg_bytes=2 * n_slots * 8 * n, kernel="level schedule: %d generators, %d levels, %d launch groups (one fused kernel each), one CUDA graph"
+                        % (gs.num_generators, gs.num_levels, gs.num_groups), launches=gs.num_groups, err=ed, dtype="u32 limbs / u64 (int)",
+                        keep=(gs, vd, table, hv, ho, he, in_slots, out_slots))
+        if wl == "genstream_ecdsa":
+            from plonky2_ecdsa_b200 import engine as E, genstream as G
+            cb = G.EcdsaCircuitBuilder(E.blinding_scalar(lib))
+            msg_t, r_t, s_t, pk_t = cb.verify_secp256k1_message()
+            gs = eng.load_generator_stream(cb.bytes())
+            n = 4096
+            d = W.ecdsa_workload(n, seed=W.SEED + self.rank)
+            in_t = list(msg_t) + list(r_t) + list(s_t) + list(pk_t[0]) + list(pk_t[1])
+            vals = np.ascontiguousarray(np.concatenate([d["msg"], d["r"], d["s"], d["pkx"], d["pky"]], axis=0))
+            in_slots = np.array([gs.slot(t) for t in in_t], dtype=np.uint32)
+            out_t = cb.tape_targets[-10:-1]                 # y3 of the final curve_add stands for "the result" on the host path
+            out_slots = np.array([gs.slot(t) for t in out_t], dtype=np.uint32)
+            n_slots = gs.num_slots
+            vd = self.dev(vals)
+            table = torch.zeros((n_slots, n), dtype=torch.int64, device="cuda")
+            ed = torch.zeros(n, dtype=torch.int32, device="cuda")
+            torch.cuda.synchronize()
+
+            def step():
+                rc = lib.p2e_genstream_run_dev(gs.handle, n, in_slots.ctypes.data, len(in_slots), vd.data_ptr(), n, table.data_ptr(), n,
+                                               ed.data_ptr(), sp)
+                assert rc == 0, eng.last_error()
+            hv = self.pinned(vals)
+            ho = torch.empty((len(out_slots), n), dtype=torch.int64).pin_memory()
+            he = torch.empty(n, dtype=torch.int32).pin_memory()
+
+            def step_e2e():
+                rc = lib.p2e_genstream_run(gs.handle, n, in_slots.ctypes.data, len(in_slots), hv.data_ptr(), out_slots.ctypes.data,
+                                           len(out_slots), ho.data_ptr(), he.data_ptr())
+                assert rc == 0, eng.last_error()
             return dict(step=step, step_e2e=step_e2e, units=n, h2d=len(in_slots) * 8 * n, d2h=len(out_slots) * 8 * n + 4 * n,
                         alg_bytes=2 * n_slots * 8 * n, kernel="level schedule: %d generators, %d levels, %d launch groups (one fused kernel each), one CUDA graph"
                         % (gs.num_generators, gs.num_levels, gs.num_groups), launches=gs.num_groups, err=ed, dtype="u32 limbs / u64 (int)",
@@ -786,10 +823,10 @@ def main():
     main_res = b.measure(wl, args.steps, args.warmup, e2e_steps=max(2, min(args.steps, 5)), sample_clocks=True)
     secondary = {}
     if not args.no_secondary:
-        for w2 in ("mulmod", "mulmod_n", "eval", "evalcs", "evalfc", "evalcsfc", "evalrc", "evalrcfc", "evalcmp", "evaladd", "lde", "genstream", "glv", "ecdsa"):
+        for w2 in ("mulmod", "mulmod_n", "eval", "evalcs", "evalfc", "evalcsfc", "evalrc", "evalrcfc", "evalcmp", "evaladd", "lde", "genstream", "genstream_ecdsa", "glv", "ecdsa"):
             if w2 != wl and w2 in WORKLOAD_NAMES:
                 try:
-                    r2 = b.measure(w2, steps=min(args.steps, 20) if w2 != "glv" else 3, warmup=3, e2e_steps=2)
+                    r2 = b.measure(w2, steps=min(args.steps, 20) if w2 not in ("glv", "genstream_ecdsa") else 3, warmup=3, e2e_steps=2)
                 except Exception as e:      # noqa: BLE001  (e.g. not enough free HBM for the 32 GB glv witness)
                     secondary[w2] = {"error": str(e)[:200]}
                     continue

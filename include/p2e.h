@@ -356,6 +356,10 @@ int p2e_ux_witness(int gate, int bits, int limb_bits, int count, int num_addends
 #define P2E_GEN_COPY 13
 #define P2E_GEN_CONSTANT 14
 #define P2E_GEN_ARITHMETIC 15
+/* keccak(0u64) as a secp256k1 scalar -- the blinding constant of curve_msm_circuit / fixed_base_curve_mul_circuit
+ * (gadgets/curve_msm.rs:33-39), 4 little-endian 64-bit words; host-only. */
+int p2e_blinding_scalar(uint64_t* words4);
+
 /* plonky2 glue generators of the gadgets' scalar handling (restated, parity unpinned against the dependency):
  *   P2E_GEN_BASE_SPLIT     BaseSplitGenerator<2> { usize row, usize num_limbs }: split_le_base::<2> (gadgets/split_nonnative.rs:29-37)
  *   P2E_GEN_RANDOM_ACCESS  RandomAccessGenerator { usize row, usize bits, usize num_copies, usize num_extra_constants,
@@ -365,6 +369,10 @@ int p2e_ux_witness(int gate, int bits, int limb_bits, int count, int num_addends
 #define P2E_GEN_BASE_SPLIT 16
 #define P2E_GEN_RANDOM_ACCESS 17
 #define P2E_GEN_EQUALITY 18
+/* { Target }: a target the host sets before generation (plonky2 PartialWitness / public input).  Needed when a gadget
+ * connects a generator output to an input (connect_nonnative(r, point.x), gadgets/ecdsa.rs:48-52): the writer is then checked
+ * against the input (P2E_ERR_CONNECT) instead of producing it. */
+#define P2E_GEN_INPUT 19
 int p2e_genstream_load(const uint8_t* bytes, size_t len);          /* handle >= 0, or < 0 (p2e_last_error) */
 int p2e_genstream_free(int handle);
 long p2e_genstream_info(int handle, int what); /* 0 slots, 1 generators, 2 levels, 3 launch groups, 4 input slots, 5 targets */

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libp2e.so")
 SOURCES = ["p2e_kernels.cu", "p2e_chain.cu", "p2e_ux.cu", "p2e_ntt.cu", "p2e_genstream.cu", "p2e_tape.cpp"]
-HEADERS = ["p2e_field.cuh", "p2e_fold.cuh", "p2e_lzinv.cuh", "p2e_common.h", "p2e_tape.h", os.path.join("..", "..", "include", "p2e.h")]
+HEADERS = ["p2e_field.cuh", "p2e_f8.cuh", "p2e_f8inv.cuh", "p2e_fold.cuh", "p2e_common.h", "p2e_tape.h", os.path.join("..", "..", "include", "p2e.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -23,6 +23,7 @@
 #include "../../include/p2e.h"
 #include "p2e_common.h"
 #include "p2e_f8.cuh"
+#include "p2e_f8inv.cuh"
 #include "p2e_field.cuh"
 #include "p2e_tape.h"
 
@@ -365,18 +366,7 @@ __device__ __forceinline__ void load_jac(const ChainArgs& A, int32_t pid, size_t
 }
 
 // The latency-bound kernels run few warps per SM through thousands of multiplications: the multiply / square
-// bodies are real functions so that the loops stay inside the instruction cache.  Operands and results cross the
-// call boundary BY VALUE (structs of 8 words): ptxas keeps them in registers.
-__device__ __noinline__ F8 f8m_v(F8 a, F8 b) {
-  F8 r;
-  f8_mul(a.v, b.v, r.v);
-  return r;
-}
-__device__ __noinline__ F8 f8s_v(F8 a) {
-  F8 r;
-  f8_sqr(a.v, r.v);
-  return r;
-}
+// bodies (f8m_v / f8s_v, p2e_f8inv.cuh) are real functions so that the loops stay inside the instruction cache.
 __device__ __forceinline__ F8 f8w(const u32 (&a)[NW]) {
   F8 r;
 #pragma unroll
@@ -392,28 +382,6 @@ __device__ __forceinline__ void fs(const u32 (&a)[NW], u32 (&r)[NW]) {
   F8 t = f8s_v(f8w(a));
 #pragma unroll
   for (int l = 0; l < NW; l++) r[l] = t.v[l];
-}
-__device__ __forceinline__ F8 f8s_n(F8 t, int n) {
-  for (int k = 0; k < n; k++) t = f8s_v(t);
-  return t;
-}
-// x^(p-2): 255 squarings + 15 multiplications (addition chain over the run structure of p - 2)
-__device__ F8 f8_inv_calls(F8 a) {
-  const F8 x2 = f8m_v(f8s_v(a), a);
-  const F8 x3 = f8m_v(f8s_v(x2), a);
-  F8 u = f8m_v(f8s_n(x3, 3), x3);                  // x6
-  u = f8m_v(f8s_n(u, 3), x3);                      // x9
-  u = f8m_v(f8s_n(u, 2), x2);                      // x11
-  const F8 x22 = f8m_v(f8s_n(u, 11), u);
-  const F8 x44 = f8m_v(f8s_n(x22, 22), x22);
-  const F8 x88 = f8m_v(f8s_n(x44, 44), x44);
-  u = f8m_v(f8s_n(x88, 88), x88);                  // x176
-  u = f8m_v(f8s_n(u, 44), x44);                    // x220
-  u = f8m_v(f8s_n(u, 3), x3);                      // x223
-  u = f8m_v(f8s_n(u, 23), x22);
-  u = f8m_v(f8s_n(u, 5), a);
-  u = f8m_v(f8s_n(u, 3), x2);
-  return f8m_v(f8s_n(u, 2), a);
 }
 
 // digit of `bits` bits at bit position `pos` of a little-endian 29-bit-limb value (nl limbs)

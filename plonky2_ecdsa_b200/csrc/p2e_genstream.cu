@@ -29,7 +29,7 @@
 #include "../../include/p2e.h"
 #include "p2e_common.h"
 #include "p2e_field.cuh"
-#include "p2e_lzinv.cuh"
+#include "p2e_f8inv.cuh"
 
 namespace p2e {
 
@@ -273,9 +273,9 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_inv(GsIO io, int j0) {
   if (e == 0 && is_zero9(xc)) e = ERR_INVERSE_ZERO;
   if (e == 0) {
     if (MOD::ID == 0) {
-      // base field: the ladder in lazy limbs (limb-parallel carry passes, ~1/3 of the dependency chain of the exact
+      // base field: the ladder on saturated 8 x 32-bit words (p2e_f8inv.cuh; a fraction of the dependency chain of the exact
       // mulmod ladder -- this kernel is pure latency), one exact canonicalisation at the end; the inverse is unique
-      inv_p_lazy(xc, inv);
+      inv_p_f8(xc, inv);
     } else {
       inv_mod<MOD>(xc, inv);
     }
@@ -417,7 +417,8 @@ struct GenStream {
   std::vector<u32> slot_of_target;
   std::vector<GsGen> gens;
   std::vector<GsGroup> groups;
-  std::vector<u32> input_slots;          // slots read but never produced
+  std::vector<u32> input_slots;          // slots read but never produced, and the declared inputs
+  std::vector<u32> ext_targets;          // P2E_GEN_INPUT: targets the host sets before generation (PartialWitness)
   u32 n_slots = 0;
   int n_levels = 0;
   // device side (created lazily on the bound device)
@@ -628,6 +629,14 @@ static bool parse_record(GenStream& S, Reader& R) {
       if (ra != rb) S.parent[std::max(ra, rb)] = std::min(ra, rb);
       return true;
     }
+    case P2E_GEN_INPUT: {
+      // a target of the host's PartialWitness: set before generation; a generator that also writes its partition (a
+      // connect_* against a public input, gadgets/ecdsa.rs:48-52) is checked against it instead of producing it
+      const u32 t = read_target(S, R);
+      if (!R.ok) return bad("truncated input record");
+      S.ext_targets.push_back(t);
+      return true;
+    }
     case P2E_GEN_CONSTANT: {
       // plonky2 ConstantGenerator { row, constant_index, wire_index, constant }
       const u64 row = R.u64le();
@@ -708,9 +717,11 @@ static bool finalize(GenStream& S) {
   auto slot = [&](u32 t) { return t == GS_NONE ? GS_NONE : S.slot_of_target[t]; };
   const int ng = (int)S.gens.size();
   std::vector<int> producer(S.n_slots, -1);
+  std::vector<char> is_ext(S.n_slots, 0);
+  for (u32 t : S.ext_targets) is_ext[slot(t)] = 1;
   for (int gi = 0; gi < ng; gi++)
     for (u32 t : S.gens[gi].outs)
-      if (t != GS_NONE && producer[slot(t)] < 0) producer[slot(t)] = gi;
+      if (t != GS_NONE && !is_ext[slot(t)] && producer[slot(t)] < 0) producer[slot(t)] = gi;
   // levels: iterative DFS over the producer relation (a second writer of a slot also waits for the first)
   std::vector<int> state(ng, 0);
   for (int root = 0; root < ng; root++) {
@@ -729,7 +740,14 @@ static bool finalize(GenStream& S) {
         if (t == GS_NONE) continue;
         const int p = producer[slot(t)];
         if (p < 0 || p == gi) continue;
-        if (state[p] == 1) { S.error = "genstream: the generators' dependencies form a cycle"; return false; }
+        if (state[p] == 1) {
+          S.error = "genstream: the generators' dependencies form a cycle (generator #" + std::to_string(gi) + " of kind " +
+                    std::to_string(g.kind) + " waits for generator #" + std::to_string(p) + " of kind " + std::to_string(S.gens[p].kind) + "; chain:";
+          for (size_t q = stack.size() > 10 ? stack.size() - 10 : 0; q < stack.size(); q++)
+            S.error += " #" + std::to_string(stack[q].first) + "/k" + std::to_string(S.gens[stack[q].first].kind);
+          S.error += ")";
+          return false;
+        }
         if (state[p] == 0) {
           state[p] = 1;
           stack.push_back({p, 0});
@@ -756,7 +774,7 @@ static bool finalize(GenStream& S) {
     for (u32 t : g.ins)
       if (t != GS_NONE && producer[slot(t)] < 0) is_input[slot(t)] = 1;
   for (u32 s = 0; s < S.n_slots; s++)
-    if (is_input[s]) S.input_slots.push_back(s);
+    if (is_input[s] || is_ext[s]) S.input_slots.push_back(s);
   // groups: (level, kind, modulus, shape) in stream order inside a group
   std::vector<int> order(ng);
   for (int i = 0; i < ng; i++) order[i] = i;

@@ -8,7 +8,7 @@
 #include "p2e_common.h"
 #include "p2e_field.cuh"
 #include "p2e_fold.cuh"
-#include "p2e_lzinv.cuh"
+#include "p2e_f8inv.cuh"
 
 namespace p2e {
 
@@ -216,9 +216,9 @@ k_inv_witness(size_t n, const u64* __restrict__ x, size_t is, u64* __restrict__ 
   if (cnt == 0) return;
   u32 inv_run[NL];
   if (MOD::ID == 0) {
-    // base field: the ladder in lazy limbs (~1/3 of the dependency chain of the exact-mulmod ladder), out-of-line
+    // base field: the ladder on saturated 8 x 32-bit words (a fraction of the dependency chain of the exact-mulmod ladder), out-of-line
     // multiply / square bodies (inlined, this kernel is 28 k instructions and waits on instruction fetch)
-    inv_p_lazy(run, inv_run);
+    inv_p_f8(run, inv_run);
   } else {
     inv_mod<MOD>(run, inv_run);
   }

@@ -626,6 +626,16 @@ static std::mutex g_builder_mu;
 
 extern "C" {
 
+// the circuit constant keccak(0u64) as a scalar (gadgets/curve_msm.rs:33-36), 4 little-endian 64-bit words: hosts that
+// build generator streams of the reference's circuits (plonky2_ecdsa_b200.genstream.EcdsaCircuitBuilder) need it
+int p2e_blinding_scalar(uint64_t* words4) {
+  if (!words4) return set_error_msg("p2e_blinding_scalar: NULL");
+  u64 k[4];
+  blinding_scalar(k);
+  for (int i = 0; i < 4; i++) words4[i] = k[i];
+  return 0;
+}
+
 int p2e_builder_new(void) {
   std::lock_guard<std::mutex> lock(g_builder_mu);
   Builder* b = new Builder();

@@ -159,6 +159,7 @@ SIGNATURES = {
     "p2e_set_profiling": (_int, [_int]),
     "p2e_last_kernel_times": (_int, [_vp, _int]),
     "p2e_chain_trace_dump": (_int, [_vp, _vp, _vp, _int]),
+    "p2e_blinding_scalar": (_int, [_vp]),
     "p2e_bench_imad": (ctypes.c_double, [_int, _int]),
 }
 
@@ -179,6 +180,15 @@ def load_library(path: str = LIB_PATH) -> ctypes.CDLL:
         fn.restype = res
         fn.argtypes = args
     return lib
+
+
+def blinding_scalar(lib=None) -> int:
+    """keccak(0u64) as a secp256k1 scalar (gadgets/curve_msm.rs:33-39), from the library's own Keccak."""
+    lib = lib if lib is not None else load_library()
+    w = (ctypes.c_uint64 * 4)()
+    if lib.p2e_blinding_scalar(ctypes.addressof(w)) != 0:
+        raise P2EError("p2e_blinding_scalar failed")
+    return sum(int(w[i]) << (64 * i) for i in range(4))
 
 
 def _ptr(a):

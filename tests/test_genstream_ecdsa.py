@@ -1,0 +1,64 @@
+"""SURVEY 8f-2 closed over a real circuit: the complete verify_secp256k1_message_circuit (gadgets/ecdsa.rs:30-53) as a
+serialized generator stream -- in-tree generators plus the plonky2 glue between them (constants, arithmetic, base-2
+splits, random accesses, equality; restated, unpinned) -- run by the level-scheduled executor, against the chain
+kernels' witness of the same signatures, slot for slot."""
+import numpy as np
+import pytest
+
+import plonky2_ecdsa_b200 as pkg
+from oracle import spec as S
+from plonky2_ecdsa_b200 import genstream as G
+from plonky2_ecdsa_b200 import workload as W
+
+
+@pytest.fixture(scope="module")
+def circuit():
+    b = G.EcdsaCircuitBuilder(S.blinding_scalar())
+    ins = b.verify_secp256k1_message()
+    return b, ins
+
+
+def test_circuit_stream_shape(circuit):
+    """CPU tier: the stream parses, its in-tree generators are the tape's (SURVEY 3.1 counts), every tape slot has a target."""
+    b, _ = circuit
+    lib = pkg.load_library()
+    gs = G.GeneratorStream(lib, b.bytes())
+    try:
+        assert len(b.tape_targets) == lib.p2e_ecdsa_tape_slots() == 82615
+        assert len(gs.input_slots) == 45                       # msg, r, s, pk.x, pk.y: 5 x 9 limbs
+        # 4642 in-tree generators + glue; the curve chain makes the stream deep
+        assert gs.num_generators > 4642 + 139 * 18 and gs.num_levels > 311 * 4
+        assert constant_limbs_ok()
+    finally:
+        gs.close()
+
+
+def test_library_blinding_scalar_is_the_oracles():
+    from plonky2_ecdsa_b200 import engine
+    assert engine.blinding_scalar() == S.blinding_scalar()
+
+
+def constant_limbs_ok():
+    for v in (0, 1, 7, S.SECP_P - 1, S.GLV_S, S.GLV_BETA, 1 << 231, (1 << 232) - 1, 1 << 232):
+        if G.constant_limbs(v) != S.convert_base(S.to_u32_digits(v), 32, 29):
+            return False
+    return True
+
+
+@pytest.mark.gpu
+def test_circuit_stream_equals_the_tape_witness(engine, circuit):
+    b, (msg, r, s, pk) = circuit
+    gs = engine.load_generator_stream(b.bytes())
+    n = 24
+    wl = W.ecdsa_workload(n, seed=2718)
+    vals = {"msg": wl["msg"].copy(), "r": wl["r"].copy(), "s": wl["s"].copy(), "pkx": wl["pkx"].copy(), "pky": wl["pky"].copy()}
+    vals["r"][0, 5] ^= np.uint64(1)             # a wrong signature: every generator still has a witness, the final connect fails
+    inputs = {}
+    for tv, key in ((msg, "msg"), (r, "r"), (s, "s"), (pk[0], "pkx"), (pk[1], "pky")):
+        for l, t in enumerate(tv):
+            inputs[t] = vals[key][l]
+    got, err = gs.run(inputs, b.tape_targets)
+    want, werr = engine.verify_secp256k1_message_witness(vals["msg"], vals["r"], vals["s"], vals["pkx"], vals["pky"])
+    assert np.array_equal(got, want)
+    assert np.array_equal(err, werr) and err[5] == pkg.ERR_CONNECT and not np.delete(err, 5).any()
+    gs.close()
