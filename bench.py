@@ -24,8 +24,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# Independent batches are pipelined on many CUDA streams (8 per 4096 signatures, twice that inside the library): with the
-# default 8 hardware work queues they alias and serialise (N = 2, 2048-signature shards: 0.523 -> 0.386 ms per step with 32).
+# Independent batches are pipelined on many CUDA streams (16 per 4096 signatures, twice that inside the library): with the
+# default 8 hardware work queues they alias and serialise (N = 1: 0.79 -> 0.67 ms per step with 32 queues; N = 2,
+# 2048-signature shards: 0.523 -> 0.386 ms).
 # Must be set before the CUDA context exists.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
@@ -519,7 +520,7 @@ class Bench:
         # Independent batches are enqueued round-robin on S streams (async *_dev API, one output buffer + one scratch
         # arena per stream) so the latency-bound per-signature kernels of one batch overlap the full-GPU kernels of
         # another.  Strong scaling keeps the number of signatures in flight per GPU constant (S grows with N).
-        S = max(1, int(os.environ.get("P2E_BENCH_STREAMS", str(min(64, 8 * (n_total // max(n, 1)))))))
+        S = max(1, int(os.environ.get("P2E_BENCH_STREAMS", str(min(64, 16 * (n_total // max(n, 1)))))))
         streams = [torch.cuda.Stream() for _ in range(S)]
         nars = [torch.empty((nn, n), dtype=torch.int32, device="cuda") for _ in range(S)]
         eds = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(S)]

@@ -152,6 +152,12 @@ __device__ u32 st_mul_generic(const ChainArgs& A, u32 slot, size_t i, const u32 
 // Emit policies of the expansion kernel: `f` = slot offset inside the curve op (plain format), `c` = narrow-row
 // offset inside the curve op (compact format), `m` = index of the MulNonnative row inside the curve op.
 struct W9 { u32 v[NL]; };
+__device__ __forceinline__ W9 w9(const u32 (&a)[NL]) {
+  W9 r;
+#pragma unroll
+  for (int l = 0; l < NL; l++) r.v[l] = a[l];
+  return r;
+}
 struct EmPlain {
   u64* o;          // -> out[op.slot][i]
   size_t os;
@@ -202,7 +208,34 @@ struct EmCompact {
 };
 
 // ------------------------------------------------------------------------------------------
-// K0: prep-op interpreter (generic cores: operands are arbitrary wires, both moduli)
+// K0: prep-op interpreter (generic cores: operands are arbitrary wires, both moduli).  The heavy cores are real
+// functions: fully inlined the interpreter was 31 000 instructions (496 KB) of straight-line code, and a kernel that
+// runs one warp per SM next to every other batch's kernels then costs the whole mix its instruction cache
+// (r02f: 0.136 ms of the 0.79 ms pipelined step for 4.7 % of the instructions).
+struct MulTuple {
+  u32 r[NL], q[NL];
+  u64 cs[2 * NL - 1], cb[2 * NL - 2];
+};
+template <class MOD>
+__device__ __noinline__ u32 nl_prep_mul(const ChainArgs* A, u32 slot, size_t i, W9 a, W9 b) {
+  MulTuple t;
+  u32 e = mul_witness_core<MOD>(a.v, b.v, t.r, t.q, t.cs, t.cb);
+  const u32 e2 = st_mul_generic(*A, slot, i, t.r, t.q, t.cs, t.cb);
+  return e ? e : e2;
+}
+template <class MOD>
+__device__ __noinline__ W9 nl_prep_inv(W9 a) {
+  W9 r;
+  inv_mod<MOD>(a.v, r.v);
+  return r;
+}
+template <class MOD>
+__device__ __noinline__ W9 nl_prep_inv_div(W9 a, W9 inv, u32* e) {
+  W9 d;
+  *e = inv_div_core<MOD>(a.v, inv.v, d.v);
+  return d;
+}
+
 template <class MOD>
 __device__ u32 prep_exec(const ChainArgs& A, const PrepOp& op, size_t i) {
   u64 aw[NL], bw[NL];
@@ -213,18 +246,16 @@ __device__ u32 prep_exec(const ChainArgs& A, const PrepOp& op, size_t i) {
   switch (op.opcode) {
     case OP_MUL: {
       e = load_mul_wires(aw, a) | load_mul_wires(bw, b);
-      u32 q[NL];
-      u64 cs[2 * NL - 1], cb[2 * NL - 2];
       if (e == 0) {
-        e = mul_witness_core<MOD>(a, b, r, q, cs, cb);
+        e = nl_prep_mul<MOD>(&A, op.slot, i, w9(a), w9(b));
       } else {
-        set_zero9(r);
-        set_zero9(q);
+        u32 z[NL];
+        u64 cs[2 * NL - 1], cb[2 * NL - 2];
+        set_zero9(z);
         for (int l = 0; l < 2 * NL - 1; l++) cs[l] = 0;
         for (int l = 0; l < 2 * NL - 2; l++) cb[l] = 0;
+        st_mul_generic(A, op.slot, i, z, z, cs, cb);
       }
-      const u32 e2 = st_mul_generic(A, op.slot, i, r, q, cs, cb);
-      if (e == 0) e = e2;
       break;
     }
     case OP_ADD:
@@ -243,8 +274,12 @@ __device__ u32 prep_exec(const ChainArgs& A, const PrepOp& op, size_t i) {
       set_zero9(inv);
       set_zero9(div);
       if (e == 0) {
-        inv_mod<MOD>(a, inv);
-        e |= inv_div_core<MOD>(a, inv, div);
+        const W9 iv = nl_prep_inv<MOD>(w9(a));
+        u32 e2;
+        const W9 dv = nl_prep_inv_div<MOD>(w9(a), iv, &e2);
+        e |= e2;
+        copy9(iv.v, inv);
+        copy9(dv.v, div);
       }
       st9(A, op.slot, i, div);
       st9(A, op.slot + 9, i, inv);
@@ -253,6 +288,13 @@ __device__ u32 prep_exec(const ChainArgs& A, const PrepOp& op, size_t i) {
     default: break;
   }
   return e;
+}
+
+__device__ __noinline__ u32 nl_prep_glv(W9 kc, W9* k1, W9* k2, u32* n1, u32* n2) {
+  glv_decompose_core(kc.v, k1->v, k2->v, *n1, *n2);
+  u32 hi = 0;
+  for (int l = 5; l < NL; l++) hi |= k1->v[l] | k2->v[l];
+  return hi ? (u32)ERR_LIMBS_OVERFLOW : 0u;
 }
 
 // NonNativeMultipleAddsGenerator (nonnative.rs:696-728) over op.pad summands
@@ -286,16 +328,14 @@ __global__ void __launch_bounds__(32) k_prep(ChainArgs A) {
     if (op.opcode == OP_GLV) {
       u64 w[NL];
       load_ref(A, op.a, i, w);
-      u32 kc[NL], k1[NL], k2[NL], n1 = 0, n2 = 0;
+      u32 kc[NL], n1 = 0, n2 = 0;
+      W9 k1w, k2w;
       u32 e = load_canon<ModN>(w, kc);
-      set_zero9(k1);
-      set_zero9(k2);
-      if (e == 0) {
-        glv_decompose_core(kc, k1, k2, n1, n2);
-        u32 hi = 0;
-        for (int l = 5; l < NL; l++) hi |= k1[l] | k2[l];
-        if (hi) e |= ERR_LIMBS_OVERFLOW;
-      }
+      set_zero9(k1w.v);
+      set_zero9(k2w.v);
+      if (e == 0) e |= nl_prep_glv(w9(kc), &k1w, &k2w, &n1, &n2);
+      const u32 (&k1)[NL] = k1w.v;
+      const u32 (&k2)[NL] = k2w.v;
       for (int l = 0; l < 5; l++) {
         st1(A, op.slot + l, i, k1[l]);
         st1(A, op.slot + 5 + l, i, k2[l]);
@@ -706,12 +746,6 @@ struct W9E {
   W9 r;
   u32 e;
 };
-__device__ __forceinline__ W9 w9(const u32 (&a)[NL]) {
-  W9 r;
-#pragma unroll
-  for (int l = 0; l < NL; l++) r.v[l] = a[l];
-  return r;
-}
 // MulNonnative row + CheckSum row; the tuple is written from inside the call (only r and the error word return)
 template <class EM>
 __device__ __noinline__ W9E nl_mulw(EM em, int f, int c, int m, W9 x, W9 y) {

@@ -57,6 +57,10 @@ class GeneratorStreamWriter:
             self.write_bool(False)
             self.write_usize(t[1])
 
+    def write_target_bool(self, t):
+        """plonky2 Write::write_target_bool: the BoolTarget's target"""
+        self.write_target(t)
+
     def write_target_vec(self, ts):
         self.write_usize(len(ts))
         for t in ts:
@@ -81,7 +85,7 @@ class GeneratorStreamWriter:
         self.write_target_vec(a)
         self.write_target_vec(b)
         self.write_target_vec(total)
-        self.write_target(overflow)
+        self.write_target_bool(overflow)
 
     def nonnative_multiple_adds_generator(self, modulus, summands, total, overflow):
         """gadgets/nonnative.rs:730-740"""
@@ -98,7 +102,7 @@ class GeneratorStreamWriter:
         self.write_target_vec(a)
         self.write_target_vec(b)
         self.write_target_vec(diff)
-        self.write_target(overflow)
+        self.write_target_bool(overflow)
 
     def nonnative_inverse_generator(self, modulus, x, inv, div):
         """gadgets/nonnative.rs:874-878"""
@@ -119,8 +123,15 @@ class GeneratorStreamWriter:
         self.write_target_vec(k)
         self.write_target_vec(k1)
         self.write_target_vec(k2)
-        self.write_target(k1_neg)
-        self.write_target(k2_neg)
+        self.write_target_bool(k1_neg)
+        self.write_target_bool(k2_neg)
+
+    # the two in-tree GATES' own serialize bodies (gates/mul_nonnative.rs:181-183, 466-468): no tag, one usize
+    def mul_nonnative_gate(self, num_limbs=9):
+        self.write_usize(num_limbs)
+
+    def check_sum_gate(self, num_limbs=9):
+        self.write_usize(num_limbs)
 
     def copy(self, a, b):
         """CircuitBuilder::connect(a, b): one copy-constraint partition"""
@@ -169,6 +180,17 @@ class GeneratorStreamWriter:
 
     def bytes(self) -> bytes:
         return bytes(self.buf)
+
+
+def deserialize_gate(data: bytes) -> int:
+    """Gate::deserialize of MulNonnativeGate / CheckSumGate (gates/mul_nonnative.rs:185-195, 470-477): reads num_limbs.
+    The kernels implement num_limbs() == 9 (gates/mul_nonnative.rs:37-39, 353-355); anything else is refused."""
+    if len(data) != 8:
+        raise ValueError("gate record is one usize")
+    (nl,) = struct.unpack("<Q", data)
+    if nl != 9:
+        raise ValueError("num_limbs must be 9")
+    return nl
 
 
 class GeneratorStream:

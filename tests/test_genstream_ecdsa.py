@@ -59,6 +59,14 @@ def test_circuit_stream_equals_the_tape_witness(engine, circuit):
             inputs[t] = vals[key][l]
     got, err = gs.run(inputs, b.tape_targets)
     want, werr = engine.verify_secp256k1_message_witness(vals["msg"], vals["r"], vals["s"], vals["pkx"], vals["pky"])
-    assert np.array_equal(got, want)
+    # connect_nonnative(r, point.x) (gadgets/ecdsa.rs:48-52) makes r and the last curve_add's x3 ONE partition: for the wrong
+    # signature the stream keeps the input's value there and flags the mismatch (plonky2: "partition set twice with
+    # different values", generation stops); everything generated before that point still equals the tape's witness
+    x3 = 82615 - 231 + 150
+    ok = np.ones(n, dtype=bool)
+    ok[5] = False
+    assert np.array_equal(got[:, ok], want[:, ok])
+    assert np.array_equal(got[:x3, 5], want[:x3, 5])
+    assert np.array_equal(got[x3:x3 + 9, 5], vals["r"][:, 5]) and not np.array_equal(want[x3:x3 + 9, 5], vals["r"][:, 5])
     assert np.array_equal(err, werr) and err[5] == pkg.ERR_CONNECT and not np.delete(err, 5).any()
     gs.close()

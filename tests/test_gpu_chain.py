@@ -338,3 +338,33 @@ def test_compact_device_format_is_written_directly(engine):
         assert not err.cpu().numpy().any()
         assert np.array_equal(engine.expand_compact(cmap, np.ascontiguousarray(nh), None if wh is None else np.ascontiguousarray(wh)), plain)
         assert not nar.cpu().numpy()[:, n:].any()          # nothing is written past n
+
+
+def test_glv_mul_full_size_sampled_columns(engine):
+    """BASELINE config 4 at full size and across the scratch-chunk boundary: 2^16 + 96 glv_mul chains (chunks of 65 536) in the
+    derived compact device format; sampled columns on both sides of the boundary against the oracle tape."""
+    import torch
+    n = (1 << 16) + 96
+    tape = engine.TAPE_GLV_MUL
+    ks = W.random_field_limbs(W.SEED + 7, n, 1)
+    gx, gy = W._ec_mul_g(7)
+    px = np.repeat(W.ints_to_limbs([gx]), n, axis=1)
+    py = np.repeat(W.ints_to_limbs([gy]), n, axis=1)
+    cmap, nn, nw = engine.tape_compact_layout(tape)
+    dins = [torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda() for a in (ks, px, py)]
+    arr = (ctypes.c_void_p * 3)(*[t.data_ptr() for t in dins])
+    nar = torch.empty((nn, n), dtype=torch.int32, device="cuda")
+    err = torch.empty(n, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    rc = engine.lib.p2e_tape_witness_compact_dev(tape, n, ctypes.cast(arr, ctypes.c_void_p), n, nar.data_ptr(), None, n, err.data_ptr(), None)
+    assert rc == 0, engine.last_error()
+    engine.synchronize()
+    assert not bool(err.any())
+    cols = [0, 1, 4097, 65535, 65536, 65537, n - 1]
+    sub = np.ascontiguousarray(nar[:, cols].cpu().numpy().view(np.uint32))
+    wit = engine.expand_compact(cmap, sub)
+    for j, c in enumerate(cols):
+        k = sum(int(ks[l, c]) << (29 * l) for l in range(9))
+        wb = S.WitnessBuilder()
+        wb.glv_mul(wb.constant_affine_point((gx, gy)), wb.constant_nonnative(k, S.SECP_N))
+        assert [int(v) for v in wit[:, j]] == wb.flat(), f"column {c}"
