@@ -1,6 +1,6 @@
 # round-2 evidence: tests, bench lines, reference arm, launch list, ncu summaries (run under gpurun, one GPU)
 set -x
-TAG=${1:-r02a}
+TAG=${1:-r02n}
 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; tail -n 3 gpurun_out/${TAG}_pytest_gpu.log
 python bench.py --steps 64 --warmup 3 > gpurun_out/${TAG}_bench_n1.json 2> gpurun_out/${TAG}_bench_n1.err
 python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/${TAG}_bench_reference_n1.json 2> gpurun_out/${TAG}_bench_reference_n1.err
