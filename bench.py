@@ -180,6 +180,13 @@ class ClockSampler(threading.Thread):
                 "how": "nvml" if self.nvml is not None else "nvidia-smi --loop-ms"}
 
 
+def workload_label(wl, strong, per_gpu):
+    name = WORKLOAD_NAMES[wl].replace("2^20 Goldilocks", "2^%d Goldilocks" % LOG_ROWS)
+    if strong:
+        name = name.replace("per GPU", "per step, sharded %d per GPU (rank g owns [g N/G, (g+1) N/G))" % per_gpu)
+    return name
+
+
 # ----------------------------------------------------------------------------- reference arm (CPU)
 def run_reference(args):
     """Times the reference's CPU algorithms for the path on the box's host cores.  The Rust crate
@@ -191,11 +198,16 @@ def run_reference(args):
     from oracle import cpu_baseline
     res = cpu_baseline.run(args.workload, steps=args.steps, warmup=min(args.warmup, 1),
                            budget_s=float(os.environ.get("P2E_REF_BUDGET_S", "60")))
+    # same workload name / scaling label as our arm at this N (the CPU arm always runs on rank 0's host cores only)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    strong = args.scaling == "strong" and world > 1 and args.workload == "ecdsa"
+    cfg = dict(res["config"])
+    cfg["workload"] = workload_label(args.workload, strong, 4096 // max(world, 1))
     line = {
         "impl": "reference", "metric": res["metric"], "value": res["value"], "unit": res["unit"],
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": res["dtype"], "data": "synthetic",
-        "config": res["config"],
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": res["dtype"], "data": "synthetic",
+        "config": cfg,
         "cpu_baseline": {"value": res["value"], "unit": res["unit"], "cores": res["cores"], "kind": res["kind"],
                          "sample": res["sample"]},
         "e2e": {"value": res["value"], "unit": res["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -842,8 +854,7 @@ def main():
             "metric": main_res["metric"], "value": main_res["value"], "unit": main_res["unit"], "n_gpus": b.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": main_res["dtype"], "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAMES[wl].replace("2^20 Goldilocks", "2^%d Goldilocks" % LOG_ROWS).replace(
-                           "per GPU", "per step, sharded %d per GPU (rank g owns [g N/G, (g+1) N/G))" % upg if strong else "per GPU"),
+            "config": {"workload": workload_label(wl, strong, upg),
                        "units_per_step": main_res["units_per_step"], "units_per_step_per_gpu": upg,
                        "seed": hex(b.W.SEED), "error_rows": main_res["error_rows"],
                        "l2": "per-step inputs+outputs exceed the 126 MB L2 (no flush needed)",
