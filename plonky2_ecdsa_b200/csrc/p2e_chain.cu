@@ -649,6 +649,14 @@ __global__ void __launch_bounds__(32) k_chain_invert_up(ChainArgs A) {
   stw(A.GP, blockIdx.y, A.cap, i, run.v);
 }
 
+// inverse of a weak base-field value by division steps (p2e_modinv.cuh): canonical in, canonical out
+static __device__ __noinline__ F8 nl_modinv_p(F8 a) {
+  F8 r;
+  f8_canon(a.v);
+  modinv_words<ModP>(a.v, r.v);
+  return r;
+}
+
 __global__ void __launch_bounds__(32) k_chain_invert_mid(ChainArgs A, int G) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
@@ -673,7 +681,7 @@ __global__ void __launch_bounds__(32) k_chain_invert_mid(ChainArgs A, int G) {
     atomicOr(&A.err[i], (u32)ERR_INVERSE_ZERO);
   }
   A.BAD[i] = bad;
-  F8 inv = f8_inv_calls(run);
+  F8 inv = nl_modinv_p(run);
   for (int g = G - 1; g >= 0; g--) {
     F8 pre;
     ldw(A.GI, g, A.cap, i, pre.v);
@@ -958,7 +966,9 @@ __global__ void k_debug_f8(int op, size_t n, const u32* __restrict__ a, const u3
   else if (op == 6) f8_mul_small<4>(x, r);
   else if (op == 7) f8_mul_small<8>(x, r);
   else if (op == 8) { f8_copy(x, r); f8_canon(r); }
-  else if (op == 11) { F8 t = f8_inv_calls(f8w(x)); f8_copy(t.v, r); }
+  else if (op == 11) { F8 t = nl_modinv_p(f8w(x)); f8_copy(t.v, r); }       // division steps (what K2 runs)
+  else if (op == 14) { F8 t = f8_inv_calls(f8w(x)); f8_copy(t.v, r); }      // the ladder, as a cross-check
+  else if (op == 15) { u32 c[8]; f8_copy(x, c); modinv_words<ModN>(c, r); }   // division steps modulo the group order (x < n)
   else if (op == 12 || op == 13) {                     // divmod16 of the wide product: 12 -> remainder, 13 -> quotient
     u32 t[16], rr[NW], qq[NW];
     f8_mul_wide(x, y, t);

@@ -574,9 +574,25 @@ P2E_HD void inv_n_mont(const u32 (&a)[NL], u32 (&r)[NL]) {
   copy9(t, r);
 }
 
+// the reference's own algorithm (a ladder): kept as the cross-check of inv_mod in tests/hostcheck
+template <class MOD>
+P2E_HD void inv_mod_ladder(const u32 (&a)[NL], u32 (&r)[NL]) {
+  if (MOD::ID == 0) inv_p(a, r); else inv_n_mont(a, r);
+}
+}  // namespace p2e
+#include "p2e_modinv.cuh"
+namespace p2e {
+// canonical 29-bit limbs in (a < m), canonical 29-bit limbs out: division steps (p2e_modinv.cuh)
 template <class MOD>
 P2E_HD void inv_mod(const u32 (&a)[NL], u32 (&r)[NL]) {
-  if (MOD::ID == 0) inv_p(a, r); else inv_n_mont(a, r);
+  u32 w[8], o[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) w[k] = (a[k] >> (3 * k)) | (a[k + 1] << (LB - 3 * k));
+  modinv_words<MOD>(w, o);
+  r[0] = o[0] & LMASK;
+#pragma unroll
+  for (int i = 1; i < 8; i++) r[i] = ((o[i - 1] >> (32 - 3 * i)) | (o[i] << (3 * i))) & LMASK;
+  r[8] = o[7] >> 8;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_add_many(GsIO io, int j0, int k) 
   io.fail(i, e);
 }
 
-// one Fermat ladder per instance: the reference's own algorithm (nonnative.rs:863); a group is small, its instances
+// one inversion per instance (the reference runs a Fermat ladder, nonnative.rs:863); a group is small, its instances
 // run side by side
 template <class MOD>
 __global__ void __launch_bounds__(GS_TPB) k_gs_inv(GsIO io, int j0) {
@@ -272,13 +272,7 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_inv(GsIO io, int j0) {
   u32 e = load_canon<MOD>(w, xc);
   if (e == 0 && is_zero9(xc)) e = ERR_INVERSE_ZERO;
   if (e == 0) {
-    if (MOD::ID == 0) {
-      // base field: the ladder on saturated 8 x 32-bit words (p2e_f8inv.cuh; a fraction of the dependency chain of the exact
-      // mulmod ladder -- this kernel is pure latency), one exact canonicalisation at the end; the inverse is unique
-      inv_p_f8(xc, inv);
-    } else {
-      inv_mod<MOD>(xc, inv);
-    }
+    inv_mod<MOD>(xc, inv);     // division steps (p2e_modinv.cuh); the inverse is unique
     e |= inv_div_core<MOD>(xc, inv, div);
   }
 #pragma unroll

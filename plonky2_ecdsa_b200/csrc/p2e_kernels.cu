@@ -215,13 +215,7 @@ k_inv_witness(size_t n, const u64* __restrict__ x, size_t is, u64* __restrict__ 
   }
   if (cnt == 0) return;
   u32 inv_run[NL];
-  if (MOD::ID == 0) {
-    // base field: the ladder on saturated 8 x 32-bit words (a fraction of the dependency chain of the exact-mulmod ladder), out-of-line
-    // multiply / square bodies (inlined, this kernel is 28 k instructions and waits on instruction fetch)
-    inv_p_f8(run, inv_run);
-  } else {
-    inv_mod<MOD>(run, inv_run);
-  }
+  inv_mod<MOD>(run, inv_run);     // division steps (p2e_modinv.cuh), ~20 k instructions for the whole chunk
 #pragma unroll
   for (int c = INV_CHUNK - 1; c >= 0; c--) {
     size_t i = t0 + (size_t)c * T;

@@ -1,6 +1,6 @@
 """Timeline of pipelined ECDSA batches (diagnostic, never a bench number): S streams x K steps with the chain trace on
 (p2e_set_option("chain_trace", 1)); prints, per call, when each kernel finished and how long each phase took under
-contention.  Usage: python scripts/chain_timeline.py [streams] [steps]"""
+contention.  Usage: python scripts/chain_timeline.py [streams] [steps] [split] [n]"""
 import ctypes
 import os
 import sys
@@ -17,7 +17,7 @@ SPLIT = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 eng = pkg.Engine(0)
 lib = eng.lib
 eng.set_option("chain_split", SPLIT)
-n = 4096
+n = int(sys.argv[4]) if len(sys.argv) > 4 else 4096
 _, nn, nw = eng.tape_compact_layout(eng.TAPE_ECDSA)
 d = W.ecdsa_workload(n, seed=W.SEED)
 ind = [torch.from_numpy(d[k].view(np.int64)).cuda() for k in ("msg", "r", "s", "pkx", "pky")]
@@ -60,11 +60,16 @@ for i in range(cnt):
     t.setdefault(int(calls[i]), {})[int(kern[i])] = float(ms[i])
 names = ["start", "prep", "replay", "join", "invert", "gate", "affine", "expand"]
 print("call  " + " ".join("%8s" % x for x in names) + "   | phase durations: prep replay join invert wait affine expand")
-for c in sorted(t):
+allc = [c for c in sorted(t) if len(t[c]) >= 8]
+dus = []
+for c in allc:
     row = t[c]
-    if len(row) < 8:
-        continue
     ts = [row[k] for k in range(8)]
     du = [ts[k] - ts[k - 1] for k in range(1, 8)]
+    dus.append(du)
+    if len(allc) > 48 and c not in allc[-48:]:
+        continue
     print("%4d  " % c + " ".join("%8.3f" % x for x in ts) + "   | " + " ".join("%6.3f" % x for x in du))
+m = np.array(dus)[len(dus) // 4:]
+print("mean phase durations (ms): " + " ".join("%s %.3f" % (a, b) for a, b in zip(names[1:], m.mean(axis=0))) + "  | first->last kernel %.3f" % m.sum(axis=1).mean())
 eng.close()

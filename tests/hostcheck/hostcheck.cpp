@@ -164,6 +164,24 @@ void hc_mulw_fast(size_t n, const u64* x, const u64* y, u64* out, u32* err) {
   }
 }
 
+// division-step inverse (p2e_modinv.cuh) on 8 words x < m: out = x^-1 mod m; ladder != 0 -> the Fermat / Montgomery ladder
+// on the same value (through 29-bit limbs), the algorithm the reference runs
+void hc_modinv(int mod, int ladder, size_t n, const u32* a, u32* out) {
+  for (size_t i = 0; i < n; i++) {
+    u32 x[8], r[8];
+    for (int l = 0; l < 8; l++) x[l] = a[8 * i + l];
+    if (!ladder) {
+      if (mod == 0) modinv_words<ModP>(x, r); else modinv_words<ModN>(x, r);
+    } else {
+      u32 l9[NL], o9[NL];
+      f8_to_l29(x, l9);
+      if (mod == 0) inv_mod_ladder<ModP>(l9, o9); else inv_mod_ladder<ModN>(l9, o9);
+      f8_from_l29(o9, r);
+    }
+    for (int l = 0; l < 8; l++) out[8 * i + l] = r[l];
+  }
+}
+
 u64 hc_gl_mul(u64 a, u64 b) { return gl_mul(a, b); }
 u64 hc_gl_add(u64 a, u64 b) { return gl_add(a, b); }
 u64 hc_gl_sub(u64 a, u64 b) { return gl_sub(a, b); }

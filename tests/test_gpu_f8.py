@@ -29,14 +29,25 @@ def test_f8_ptx_ops_match_integers_and_the_portable_bodies(engine, hostcheck, op
         assert g % P_SECP == want and g < (1 << 256)
 
 
-def test_f8_inverse_ladder(engine):
+def test_f8_inverse_division_steps_and_ladder(engine):
+    """op 11: division steps on a weak value (what chain K2 runs); op 14: the Fermat ladder; op 15: division steps modulo
+    the group order (what K0 runs for s^-1).  0 -> 0."""
     rng = random.Random(11)
-    vals = [1, 2, P_SECP - 1, (1 << 256) - 1, P_SECP + 5] + [rng.randrange(1, 1 << 256) for _ in range(300)]
+    vals = [0, P_SECP, 1, 2, P_SECP - 1, (1 << 256) - 1, P_SECP + 5] + [rng.randrange(1, 1 << 256) for _ in range(3000)]
+    a = _words(vals)
+    out, lad = np.zeros_like(a), np.zeros_like(a)
+    assert engine.lib.p2e_debug_f8(11, len(vals), a.ctypes.data, a.ctypes.data, out.ctypes.data) == 0
+    assert engine.lib.p2e_debug_f8(14, len(vals), a.ctypes.data, a.ctypes.data, lad.ctypes.data) == 0
+    for x, g, l in zip(vals, _from_words(out), _from_words(lad)):
+        assert g == (pow(x, -1, P_SECP) if x % P_SECP else 0), hex(x)
+        assert l % P_SECP == g
+    N_SECP = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+    vals = [0, 1, 2, N_SECP - 1, (N_SECP + 1) // 2] + [rng.randrange(N_SECP) for _ in range(3000)]
     a = _words(vals)
     out = np.zeros_like(a)
-    assert engine.lib.p2e_debug_f8(11, len(vals), a.ctypes.data, a.ctypes.data, out.ctypes.data) == 0
+    assert engine.lib.p2e_debug_f8(15, len(vals), a.ctypes.data, a.ctypes.data, out.ctypes.data) == 0
     for x, g in zip(vals, _from_words(out)):
-        assert (g * x) % P_SECP == 1
+        assert g == (pow(x, -1, N_SECP) if x else 0), hex(x)
 
 
 def test_f8_divmod16_ptx_body(engine):

@@ -158,6 +158,27 @@ def test_f8_portable_ops(hostcheck, op):
             assert g < P_SECP
 
 
+@pytest.mark.parametrize("modulus", [0, 1])
+def test_division_step_inverse(hostcheck, modulus):
+    """p2e_modinv.cuh (what every inverse of the product path runs) against pow(x, -1, m) and against the ladder the
+    reference runs: 0 -> 0, the inverse is unique."""
+    M = S.MODULI[modulus]
+    rng = random.Random(900 + modulus)
+    vals = [0, 1, 2, 3, M - 1, M - 2, (M - 1) // 2, (M + 1) // 2, 1 << 255, (1 << 255) - 1, 1 << 30, (1 << 30) - 1, 1 << 60,
+            (1 << 240) + 1, M >> 1, M >> 30] + [1 << k for k in range(0, 256, 7)] + [M - (1 << k) for k in range(0, 255, 11)]
+    vals = [v % M for v in vals] + [rng.randrange(M) for _ in range(4000)] + [rng.randrange(1 << rng.randrange(1, 256)) for _ in range(500)]
+    a = np.array([[(v >> (32 * k)) & 0xFFFFFFFF for k in range(8)] for v in vals], dtype=np.uint32)
+    out = np.zeros_like(a)
+    hostcheck.hc_modinv(modulus, 0, ctypes.c_size_t(len(vals)), P(a), P(out))
+    got = [sum(int(w) << (32 * k) for k, w in enumerate(row)) for row in out]
+    for v, g in zip(vals, got):
+        assert g == (pow(v, -1, M) if v else 0), (hex(v), hex(g))
+    m = 300
+    lad = np.zeros((m, 8), dtype=np.uint32)
+    hostcheck.hc_modinv(modulus, 1, ctypes.c_size_t(m), P(np.ascontiguousarray(a[:m])), P(lad))
+    assert np.array_equal(lad, out[:m])
+
+
 def test_f8_limb_conversions(hostcheck):
     rng = random.Random(77)
     vals = F8_EDGES + [rng.randrange(1 << 256) for _ in range(500)]
