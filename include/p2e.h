@@ -75,7 +75,7 @@ int p2e_synchronize(void);              /* the current device's library stream *
 /* Tunables (process-wide; defaults in parentheses): "chain_chunk" (65536) signatures per scratch chunk of the chain
  * kernels; "host_chunks" (4) D2H / compute pipeline depth of p2e_tape_witness_compact; "genstream_fused" (1) and
  * "genstream_graph" (1) executor forms of p2e_genstream_run*; "ntt_log_tile" (12); "chain_trace" (0) diagnostic timeline; "chain_phases" (63) diagnostic bit mask of the chain kernels to launch
- * (anything else flags every row P2E_ERR_INTERNAL); "chain_split" (1) run the
+ * (anything else flags every row P2E_ERR_INTERNAL); "chain_split" (1: for calls of 2048 signatures or more; 2: always; 0: never) run the
  * per-signature kernels of a chain call on an internal high-priority stream and the full-GPU kernels on a low-priority one.  Nothing is read from the
  * environment. */
 int p2e_set_option(const char* name, long value);

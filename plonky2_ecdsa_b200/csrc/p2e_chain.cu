@@ -1257,7 +1257,10 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
   if ((rc = get_arena(S, st, bytes, &arena))) return rc;
   void* scratch = arena->ptr;
   // profiling keeps everything on the caller's stream so the events bracket each kernel
-  const bool split = !S.profiling && option(OPT_CHAIN_SPLIT) != 0;
+  // (measured: the split pays at >= 2048 signatures per call, 0.628 against 0.66 ms per 4096, and costs below -- its
+  // event hops are a fixed price per call: 0.122 against 0.109 ms per 512; profiles/r02_notes.md)
+  const long split_opt = option(OPT_CHAIN_SPLIT);
+  const bool split = !S.profiling && (split_opt == 2 || (split_opt == 1 && n >= 2048));
   cudaStream_t s_hi = split ? arena->hi : st, s_lo = split ? arena->lo : st;
   if (split) {
     P2E_CUDA(cudaEventRecord(arena->ev_in, st));
