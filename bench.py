@@ -180,6 +180,23 @@ class ClockSampler(threading.Thread):
                 "how": "nvml" if self.nvml is not None else "nvidia-smi --loop-ms"}
 
 
+def gs_walked(eng, gs):
+    """Whether p2e_genstream_run* takes the level walker for this stream (option genstream_walk; the bench streams hold no
+    BigUint div_rem group, the one kind the walker lacks)."""
+    w = eng.get_option("genstream_walk")
+    return w == 2 or (w == 1 and gs.num_levels >= 32)
+
+
+def gs_label(eng, gs):
+    how = ("k_gs_walk, ONE launch: a CTA owns 16-32 circuits and walks every level (warp = generator, __syncthreads per level)"
+           if gs_walked(eng, gs) else "one fused kernel per launch group, one CUDA graph")
+    return "level schedule: %d generators, %d levels, %d launch groups; %s" % (gs.num_generators, gs.num_levels, gs.num_groups, how)
+
+
+def gs_launches(eng, gs):
+    return 2 if gs_walked(eng, gs) else gs.num_groups + 1         # + k_gs_set_inputs
+
+
 def workload_label(wl, strong, per_gpu):
     name = WORKLOAD_NAMES[wl].replace("2^20 Goldilocks", "2^%d Goldilocks" % LOG_ROWS)
     if strong:
@@ -239,7 +256,7 @@ class Bench:
             self.dist = dist
         self.eng = pkg.Engine(self.local_rank)
         self.lib = self.eng.lib
-        for opt in ("chain_split",):                       # experiment hook: P2E_OPT_CHAIN_SPLIT=0
+        for opt in ("chain_split", "genstream_walk", "genstream_walk_shape"):   # experiment hooks of the bench (the library reads no environment): P2E_OPT_CHAIN_SPLIT=0, ...
             if os.environ.get("P2E_OPT_" + opt.upper()) is not None:
                 self.eng.set_option(opt, int(os.environ["P2E_OPT_" + opt.upper()]))
         self.st = torch.cuda.Stream()          # a real (non-NULL) stream: NULL selects the library's own
@@ -404,8 +421,7 @@ class Bench:
                 assert rc == 0, eng.last_error()
             # algorithmic bytes: every slot of the value table is written once and read about once
             return dict(step=step, step_e2e=step_e2e, units=n, h2d=len(in_slots) * 8 * n, d2h=len(out_slots) * 8 * n + 4 * n,
-                        alg_bytes=2 * n_slots * 8 * n, kernel="level schedule: %d generators, %d levels, %d launch groups (one fused kernel each), one CUDA graph"
-                        % (gs.num_generators, gs.num_levels, gs.num_groups), launches=gs.num_groups, err=ed, dtype="u32 limbs / u64 (int)",
+                        alg_bytes=2 * n_slots * 8 * n, kernel=gs_label(eng, gs), launches=gs_launches(eng, gs), err=ed, dtype="u32 limbs / u64 (int)",
                         keep=(gs, vd, table, hv, ho, he, in_slots, out_slots))
         if wl == "genstream_ecdsa":
             from plonky2_ecdsa_b200 import engine as E, genstream as G
@@ -438,8 +454,7 @@ class Bench:
                                            len(out_slots), ho.data_ptr(), he.data_ptr())
                 assert rc == 0, eng.last_error()
             return dict(step=step, step_e2e=step_e2e, units=n, h2d=len(in_slots) * 8 * n, d2h=len(out_slots) * 8 * n + 4 * n,
-                        alg_bytes=2 * n_slots * 8 * n, kernel="level schedule: %d generators, %d levels, %d launch groups (one fused kernel each), one CUDA graph"
-                        % (gs.num_generators, gs.num_levels, gs.num_groups), launches=gs.num_groups, err=ed, dtype="u32 limbs / u64 (int)",
+                        alg_bytes=2 * n_slots * 8 * n, kernel=gs_label(eng, gs), launches=gs_launches(eng, gs), err=ed, dtype="u32 limbs / u64 (int)",
                         keep=(gs, vd, table, hv, ho, he, in_slots, out_slots))
         if wl in UX_WORKLOADS:
             gate, bits, lb, count, na, kname = UX_WORKLOADS[wl]

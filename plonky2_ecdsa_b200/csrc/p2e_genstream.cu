@@ -29,7 +29,7 @@
 #include "../../include/p2e.h"
 #include "p2e_common.h"
 #include "p2e_field.cuh"
-#include "p2e_f8inv.cuh"
+#include "p2e_f8.cuh"
 
 namespace p2e {
 
@@ -38,6 +38,8 @@ constexpr u32 GS_CHECK = 0x80000000u;     // output slot already has a producer:
 constexpr u64 GS_P = 0xFFFFFFFF00000001ull;
 constexpr int GS_TPB = 128;
 constexpr size_t GS_MAX_STAGED = (size_t)1 << 21;   // staged instances per launch (bounds the staging buffers)
+
+enum GsKind { K_MUL, K_CHECKSUM, K_ADD, K_MULTIADD, K_SUB, K_INV, K_DIVREM, K_GLV, K_ARITH, K_CONST, K_BASESPLIT, K_RANDACC, K_EQUAL };
 
 // ---- kernels --------------------------------------------------------------------------------------------
 // staging[r][j * n + i] = V[idx[r * m + j0 + j]][i]   (GS_NONE -> 0)
@@ -169,14 +171,8 @@ struct GsIO {
     if (e) atomicOr(&err[i], e);
   }
 };
-#define GS_THREAD()                                              \
-  const size_t i = (size_t)blockIdx.x * GS_TPB + threadIdx.x;    \
-  const int j = j0 + blockIdx.y;                                 \
-  if (i >= io.n) return
-
 template <class MOD>
-__global__ void __launch_bounds__(GS_TPB) k_gs_mul(GsIO io, int j0) {
-  GS_THREAD();
+__device__ __forceinline__ void gsb_mul(const GsIO& io, int j, size_t i) {
   u64 xw[NL], yw[NL];
 #pragma unroll
   for (int l = 0; l < NL; l++) {
@@ -187,7 +183,19 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_mul(GsIO io, int j0) {
   u64 cs[2 * NL - 1], b[2 * NL - 2];
   u32 e = load_mul_wires(xw, xa) | load_mul_wires(yw, ya);
   if (e == 0) {
-    e = mul_witness_core<MOD>(xa, ya, r, q, cs, b);
+    // base field, factors below 2^256 (every canonical operand): the chain's fast core (p2e_f8.cuh, a quarter of the
+    // instructions); it reports a quotient that does not fit 256 bits and the generic core takes over
+    bool done = false;
+    if (MOD::ID == 0 && (xa[NL - 1] >> 24) == 0 && (ya[NL - 1] >> 24) == 0) {
+      i64 v[2 * NL - 1];
+      u32 blo[2 * NL - 2], tops;
+      if (mulw_p_fast(xa, ya, r, q, v, blo, tops) == 0) {
+#pragma unroll
+        for (int l = 0; l < 2 * NL - 1; l++) cs[l] = gl_from_i64(v[l]);
+        done = true;
+      }
+    }
+    if (!done) e = mul_witness_core<MOD>(xa, ya, r, q, cs, b);
   } else {
 #pragma unroll
     for (int l = 0; l < NL; l++) r[l] = q[l] = 0;
@@ -204,8 +212,7 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_mul(GsIO io, int j0) {
   io.fail(i, e);
 }
 
-__global__ void __launch_bounds__(GS_TPB) k_gs_check_sum(GsIO io, int j0) {
-  GS_THREAD();
+__device__ __forceinline__ void gsb_check_sum(const GsIO& io, int j, size_t i) {
   u64 aw[2 * NL - 1], b[2 * NL - 2];
 #pragma unroll
   for (int l = 0; l < 2 * NL - 1; l++) aw[l] = io.in(l, j, i);
@@ -216,8 +223,7 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_check_sum(GsIO io, int j0) {
 }
 
 template <class MOD, bool IS_SUB>
-__global__ void __launch_bounds__(GS_TPB) k_gs_addsub(GsIO io, int j0, int al, int bl) {
-  GS_THREAD();
+__device__ __forceinline__ void gsb_addsub(const GsIO& io, int j, size_t i, int al, int bl) {
   u64 aw[NL], bw[NL];
 #pragma unroll
   for (int l = 0; l < NL; l++) {
@@ -236,8 +242,7 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_addsub(GsIO io, int j0, int al, i
 }
 
 template <class MOD>
-__global__ void __launch_bounds__(GS_TPB) k_gs_add_many(GsIO io, int j0, int k) {
-  GS_THREAD();
+__device__ __forceinline__ void gsb_add_many(const GsIO& io, int j, size_t i, int k) {
   u32 acc[NL];
   set_zero9(acc);
   u32 ov = 0, e = 0;
@@ -261,8 +266,7 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_add_many(GsIO io, int j0, int k) 
 // one inversion per instance (the reference runs a Fermat ladder, nonnative.rs:863); a group is small, its instances
 // run side by side
 template <class MOD>
-__global__ void __launch_bounds__(GS_TPB) k_gs_inv(GsIO io, int j0) {
-  GS_THREAD();
+__device__ __forceinline__ void gsb_inv(const GsIO& io, int j, size_t i) {
   u64 w[NL];
 #pragma unroll
   for (int l = 0; l < NL; l++) w[l] = io.in(l, j, i);
@@ -283,8 +287,7 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_inv(GsIO io, int j0) {
   io.fail(i, e);
 }
 
-__global__ void __launch_bounds__(GS_TPB) k_gs_glv(GsIO io, int j0) {
-  GS_THREAD();
+__device__ __forceinline__ void gsb_glv(const GsIO& io, int j, size_t i) {
   u64 w[NL];
 #pragma unroll
   for (int l = 0; l < NL; l++) w[l] = io.in(l, j, i);
@@ -313,8 +316,7 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_glv(GsIO io, int j0) {
 // ---- plonky2 glue generators (out of tree, restated) -----------------------------------
 // BaseSplitGenerator<2> { row, num_limbs }: BaseSumGate<2> wire 0 = sum -> wires 1 .. num_limbs = its bits (LE).
 // plonky2 asserts that the integer is fully consumed: a sum that does not fit sets P2E_ERR_LIMB_RANGE.
-__global__ void __launch_bounds__(GS_TPB) k_gs_base_split(GsIO io, int j0, int nl) {
-  GS_THREAD();
+__device__ __forceinline__ void gsb_base_split(const GsIO& io, int j, size_t i, int nl) {
   const u64 v = io.in(0, j, i);
   u32 e = (nl < 64 && (v >> nl)) ? (u32)P2E_ERR_LIMB_RANGE : 0u;
   for (int r = 0; r < nl; r++) e |= io.out(r, j, i, (v >> r) & 1ull);
@@ -323,8 +325,7 @@ __global__ void __launch_bounds__(GS_TPB) k_gs_base_split(GsIO io, int j0, int n
 
 // RandomAccessGenerator of one copy of a RandomAccessGate { bits }: claimed_element = list[access_index] and the
 // little-endian bits of access_index.  An index outside the list is a panic upstream: P2E_ERR_LIMB_RANGE.
-__global__ void __launch_bounds__(GS_TPB) k_gs_random_access(GsIO io, int j0, int bits) {
-  GS_THREAD();
+__device__ __forceinline__ void gsb_random_access(const GsIO& io, int j, size_t i, int bits) {
   const u64 idx = io.in(0, j, i);
   const u64 vs = 1ull << bits;
   u32 e = idx >= vs ? (u32)P2E_ERR_LIMB_RANGE : 0u;
@@ -344,14 +345,126 @@ __device__ u64 gs_inv(u64 x) {       // x^(P-2)
   return r;
 }
 // EqualityGenerator { x, y, equal, inv }: equal = [x == y], inv = (x - y)^-1 or 0
-__global__ void __launch_bounds__(GS_TPB) k_gs_equality(GsIO io, int j0) {
-  GS_THREAD();
+__device__ __forceinline__ void gsb_equality(const GsIO& io, int j, size_t i) {
   const u64 x = io.in(0, j, i), y = io.in(1, j, i);
   u64 d = x - y;
   if (x < y) d += GS_P;
   u32 e = io.out(0, j, i, x == y ? 1ull : 0ull);
   e |= io.out(1, j, i, x == y ? 0ull : gs_inv(d));
   io.fail(i, e);
+}
+
+// the per-group launches of the bodies above: thread (i, j0 + blockIdx.y)
+#define GS_THREAD()                                              \
+  const size_t i = (size_t)blockIdx.x * GS_TPB + threadIdx.x;    \
+  const int j = j0 + blockIdx.y;                                 \
+  if (i >= io.n) return
+template <class MOD>
+__global__ void __launch_bounds__(GS_TPB) k_gs_mul(GsIO io, int j0) { GS_THREAD(); gsb_mul<MOD>(io, j, i); }
+__global__ void __launch_bounds__(GS_TPB) k_gs_check_sum(GsIO io, int j0) { GS_THREAD(); gsb_check_sum(io, j, i); }
+template <class MOD, bool IS_SUB>
+__global__ void __launch_bounds__(GS_TPB) k_gs_addsub(GsIO io, int j0, int al, int bl) { GS_THREAD(); gsb_addsub<MOD, IS_SUB>(io, j, i, al, bl); }
+template <class MOD>
+__global__ void __launch_bounds__(GS_TPB) k_gs_add_many(GsIO io, int j0, int k) { GS_THREAD(); gsb_add_many<MOD>(io, j, i, k); }
+template <class MOD>
+__global__ void __launch_bounds__(GS_TPB) k_gs_inv(GsIO io, int j0) { GS_THREAD(); gsb_inv<MOD>(io, j, i); }
+__global__ void __launch_bounds__(GS_TPB) k_gs_glv(GsIO io, int j0) { GS_THREAD(); gsb_glv(io, j, i); }
+__global__ void __launch_bounds__(GS_TPB) k_gs_base_split(GsIO io, int j0, int nl) { GS_THREAD(); gsb_base_split(io, j, i, nl); }
+__global__ void __launch_bounds__(GS_TPB) k_gs_random_access(GsIO io, int j0, int bits) { GS_THREAD(); gsb_random_access(io, j, i, bits); }
+__global__ void __launch_bounds__(GS_TPB) k_gs_equality(GsIO io, int j0) { GS_THREAD(); gsb_equality(io, j, i); }
+
+// ---- the level walker -------------------------------------------------------------------------------------
+// Circuits are independent, so a deep schedule needs no grid-wide ordering at all: a CTA owns 32 circuits (the lanes
+// of its warps) and walks ALL levels itself -- warp w runs generator w, w + W, ... of the level for those 32 circuits,
+// __syncthreads() closes the level.  One launch for the whole stream; a level costs the latency of its slowest
+// generator core instead of a kernel boundary per group (the ECDSA circuit: 1 862 levels, 4 397 groups).
+struct GsStep {
+  const u32* idx;
+  const u32* oidx;
+  const u64* consts;
+  int m, kind, modulus, shape_a, shape_b, item0;   // item0: generators of the level before this group (warp rotation)
+};
+
+__device__ __forceinline__ void gsb_arith(const GsStep& s, u64* V, size_t vs, u32* err, int j, size_t i) {
+  const int m = s.m;
+  const u64 a = V[(size_t)s.idx[j] * vs + i], b = V[(size_t)s.idx[m + j] * vs + i], c = V[(size_t)s.idx[2 * m + j] * vs + i];
+  const u64 v = gs_add(gs_mul(s.consts[j], gs_mul(a, b)), gs_mul(s.consts[m + j], c));
+  const u32 o = s.idx[3 * m + j];
+  if (o & GS_CHECK) {
+    if (V[(size_t)(o & ~GS_CHECK) * vs + i] != v) atomicOr(&err[i], (u32)P2E_ERR_CONNECT);
+  } else {
+    V[(size_t)o * vs + i] = v;
+  }
+}
+__device__ __forceinline__ void gsb_const(const GsStep& s, u64* V, size_t vs, u32* err, int j, size_t i) {
+  const u32 o = s.oidx[j];
+  const u64 v = s.consts[j];
+  if (o & GS_CHECK) {
+    if (V[(size_t)(o & ~GS_CHECK) * vs + i] != v) atomicOr(&err[i], (u32)P2E_ERR_CONNECT);
+  } else {
+    V[(size_t)o * vs + i] = v;
+  }
+}
+
+// out-of-line copies for the walker: one body resident per warp at a time, the interpreter itself stays small
+template <class MOD> __device__ __noinline__ void gsn_mul(GsIO io, int j, size_t i) { gsb_mul<MOD>(io, j, i); }
+template <class MOD> __device__ __noinline__ void gsn_inv(GsIO io, int j, size_t i) { gsb_inv<MOD>(io, j, i); }
+template <class MOD> __device__ __noinline__ void gsn_add(GsIO io, int j, size_t i, int al, int bl) { gsb_addsub<MOD, false>(io, j, i, al, bl); }
+template <class MOD> __device__ __noinline__ void gsn_sub(GsIO io, int j, size_t i, int al, int bl) { gsb_addsub<MOD, true>(io, j, i, al, bl); }
+template <class MOD> __device__ __noinline__ void gsn_add_many(GsIO io, int j, size_t i, int k) { gsb_add_many<MOD>(io, j, i, k); }
+__device__ __noinline__ void gsn_check_sum(GsIO io, int j, size_t i) { gsb_check_sum(io, j, i); }
+__device__ __noinline__ void gsn_glv(GsIO io, int j, size_t i) { gsb_glv(io, j, i); }
+__device__ __noinline__ void gsn_equality(GsIO io, int j, size_t i) { gsb_equality(io, j, i); }
+
+__device__ __forceinline__ void gs_exec(const GsStep& s, u64* V, size_t vs, size_t n, u32* err, int j, size_t i) {
+  const GsIO io = {s.idx, s.oidx, V, vs, n, err, s.m};
+  const bool base = s.modulus == P2E_SECP256K1_BASE;
+  switch (s.kind) {
+    case K_MUL: if (base) gsn_mul<ModP>(io, j, i); else gsn_mul<ModN>(io, j, i); break;
+    case K_CHECKSUM: gsn_check_sum(io, j, i); break;
+    case K_ADD: if (base) gsn_add<ModP>(io, j, i, s.shape_a, s.shape_b); else gsn_add<ModN>(io, j, i, s.shape_a, s.shape_b); break;
+    case K_SUB: if (base) gsn_sub<ModP>(io, j, i, s.shape_a, s.shape_b); else gsn_sub<ModN>(io, j, i, s.shape_a, s.shape_b); break;
+    case K_MULTIADD: if (base) gsn_add_many<ModP>(io, j, i, s.shape_a); else gsn_add_many<ModN>(io, j, i, s.shape_a); break;
+    case K_INV: if (base) gsn_inv<ModP>(io, j, i); else gsn_inv<ModN>(io, j, i); break;
+    case K_GLV: gsn_glv(io, j, i); break;
+    case K_ARITH: gsb_arith(s, V, vs, err, j, i); break;
+    case K_CONST: gsb_const(s, V, vs, err, j, i); break;
+    case K_BASESPLIT: gsb_base_split(io, j, i, s.shape_a); break;
+    case K_RANDACC: gsb_random_access(io, j, i, s.shape_a); break;
+    case K_EQUAL: gsn_equality(io, j, i); break;
+    default: break;                       // K_DIVREM: the host does not choose the walker for such a stream
+  }
+}
+
+// W warps per CTA, C circuits per CTA (a power of two <= 32): a warp runs 32 / C generators of one group side by side
+// (lane = sub * C + circuit), so a small batch still fills the machine with CTAs -- two to four of them per SM overlap
+// each other's long levels (an inverse is ~20 us of one warp) -- without idle lanes in the wide levels.
+template <int W, int C>
+__global__ void __launch_bounds__(32 * W) k_gs_walk(const GsStep* __restrict__ steps, const int* __restrict__ level_first, int n_levels,
+                                                    u64* V, size_t vs, size_t n, u32* err) {
+  constexpr int SUBS = 32 / C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / C;
+  const size_t i = (size_t)blockIdx.x * C + (lane % C);
+  const bool active = i < n;
+  int s0 = level_first[0];
+  for (int L = 0; L < n_levels; L++) {
+    const int s1 = level_first[L + 1];
+    for (int k = s0; k < s1; k++) {
+      const GsStep s = steps[k];
+      int w = warp - s.item0 % W;
+      if (w < 0) w += W;
+      if (active)
+        for (int j = w * SUBS + sub; j < s.m; j += W * SUBS) gs_exec(s, V, vs, n, err, j, i);
+    }
+    s0 = s1;
+    __syncthreads();
+  }
+}
+
+template <int W, int C>
+static void launch_walk(const GsStep* steps, const int* level_first, int n_levels, u64* V, size_t vs, size_t n, u32* err, cudaStream_t st) {
+  k_gs_walk<W, C><<<(unsigned)((n + C - 1) / C), 32 * W, 0, st>>>(steps, level_first, n_levels, V, vs, n, err);
 }
 
 // ---- host: stream parsing ---------------------------------------------------------------------------------
@@ -388,8 +501,6 @@ struct Reader {
   }
 };
 
-enum GsKind { K_MUL, K_CHECKSUM, K_ADD, K_MULTIADD, K_SUB, K_INV, K_DIVREM, K_GLV, K_ARITH, K_CONST, K_BASESPLIT, K_RANDACC, K_EQUAL };
-
 struct GsGen {
   int kind, modulus;
   int shape_a = 0, shape_b = 0;          // limb counts (ADD/SUB/DIVREM), summand count (MULTIADD)
@@ -419,6 +530,9 @@ struct GenStream {
   int device = -1;
   u32* d_idx = nullptr;
   u64* d_consts = nullptr;
+  GsStep* d_steps = nullptr;             // the walker's program: one step per group, level by level
+  int* d_level_first = nullptr;
+  bool walkable = false;                 // no group kind the walker lacks (BigUint div_rem)
   std::vector<u32> h_idx;
   std::vector<u64> h_consts;
   // grow-only staging
@@ -460,6 +574,9 @@ struct GenStream {
     drop_graph();
     if (d_idx) cudaFree(d_idx);
     if (d_consts) cudaFree(d_consts);
+    if (d_steps) cudaFree(d_steps);
+    if (d_level_first) cudaFree(d_level_first);
+    d_steps = nullptr; d_level_first = nullptr;
     if (d_stage) cudaFree(d_stage);
     if (d_stage_err) cudaFree(d_stage_err);
     if (d_io) cudaFree(d_io);
@@ -849,6 +966,30 @@ static int ensure_device(GenStream& S) {
   P2E_CUDA(cudaMemcpy(S.d_idx, S.h_idx.data(), S.h_idx.size() * 4, cudaMemcpyHostToDevice));
   P2E_CUDA(cudaMalloc((void**)&S.d_consts, std::max<size_t>(S.h_consts.size(), 1) * 8));
   P2E_CUDA(cudaMemcpy(S.d_consts, S.h_consts.data(), S.h_consts.size() * 8, cudaMemcpyHostToDevice));
+  // the walker's program (groups are sorted by level)
+  std::vector<GsStep> steps;
+  std::vector<int> first(S.n_levels + 1, 0);
+  S.walkable = true;
+  int level = -1, item0 = 0;
+  for (const GsGroup& G : S.groups) {
+    if (G.kind == K_DIVREM) S.walkable = false;
+    while (level < G.level) {
+      first[++level] = (int)steps.size();
+      item0 = 0;
+    }
+    GsStep st;
+    st.idx = S.d_idx + G.idx_off;
+    st.oidx = S.d_idx + G.oidx_off;
+    st.consts = S.d_consts + G.const_off;
+    st.m = G.m; st.kind = G.kind; st.modulus = G.modulus; st.shape_a = G.shape_a; st.shape_b = G.shape_b; st.item0 = item0;
+    item0 += G.m;
+    steps.push_back(st);
+  }
+  while (level < S.n_levels) first[++level] = (int)steps.size();
+  P2E_CUDA(cudaMalloc((void**)&S.d_steps, std::max<size_t>(steps.size(), 1) * sizeof(GsStep)));
+  P2E_CUDA(cudaMemcpy(S.d_steps, steps.data(), steps.size() * sizeof(GsStep), cudaMemcpyHostToDevice));
+  P2E_CUDA(cudaMalloc((void**)&S.d_level_first, first.size() * sizeof(int)));
+  P2E_CUDA(cudaMemcpy(S.d_level_first, first.data(), first.size() * sizeof(int), cudaMemcpyHostToDevice));
   S.device = c.device;
   return 0;
 }
@@ -970,6 +1111,29 @@ static bool use_graph() { return option(OPT_GENSTREAM_GRAPH) != 0; }
 // the launch sequence as a CUDA graph, re-used while (n, table, stride, err, staging) stay the same
 static int run_groups_graphed(GenStream& S, size_t n, u64* V, size_t vs, u32* err, cudaStream_t st) {
   int rc;
+  // deep schedules: one launch of the level walker (option "genstream_walk": 1 = when the stream has 32 levels or more,
+  // 2 = always, 0 = never)
+  const long walk = option(OPT_GENSTREAM_WALK);
+  if (S.walkable && S.n_levels > 0 && (walk == 2 || (walk == 1 && S.n_levels >= 32))) {
+    // shape: more CTAs than SMs for a small batch ("genstream_walk_shape" = 100 * warps + circuits per CTA overrides)
+    long shape = option(OPT_GENSTREAM_WALK_SHAPE);
+    if (shape == 0) {
+      // measured, ECDSA circuit x 4096: 832 20.1 ms, 816 19.2, 416 20.5, 408 26.7, 808 38.5 (idle lanes cost issue slots)
+      shape = n >= 48 * (size_t)ctx().sm_count ? 832 : 816;
+    }
+    switch (shape) {
+      case 832: launch_walk<8, 32>(S.d_steps, S.d_level_first, S.n_levels, V, vs, n, err, st); break;
+      case 816: launch_walk<8, 16>(S.d_steps, S.d_level_first, S.n_levels, V, vs, n, err, st); break;
+      case 808: launch_walk<8, 8>(S.d_steps, S.d_level_first, S.n_levels, V, vs, n, err, st); break;
+      case 416: launch_walk<4, 16>(S.d_steps, S.d_level_first, S.n_levels, V, vs, n, err, st); break;
+      case 408: launch_walk<4, 8>(S.d_steps, S.d_level_first, S.n_levels, V, vs, n, err, st); break;
+      case 404: launch_walk<4, 4>(S.d_steps, S.d_level_first, S.n_levels, V, vs, n, err, st); break;
+      case 208: launch_walk<2, 8>(S.d_steps, S.d_level_first, S.n_levels, V, vs, n, err, st); break;
+      default: return set_error_msg("genstream: option genstream_walk_shape: one of 832, 816, 808, 416, 408, 404, 208 (100 * warps + circuits per CTA), 0 = by batch size");
+    }
+    P2E_CUDA(cudaGetLastError());
+    return 0;
+  }
   if ((rc = size_staging(S, n))) return rc;
   if (!use_graph() || S.groups.size() < 8) return run_groups(S, n, V, vs, err, st);
   const bool fused = use_fused();

@@ -7,7 +7,7 @@
 //
 // The reference inverts by exp_biguint(x, p - 2) (nonnative.rs:863); the inverse of x != 0 modulo a prime is unique and
 // 0 maps to 0 in both algorithms, so the witness bits are the same (tests/test_hostcheck.py compares the two bodies,
-// tests/test_gpu_* compare with the oracle).  Included by p2e_field.cuh (needs ModP / ModN and the integer typedefs).
+// tests/test_gpu_* check it on the device).  Included by p2e_field.cuh (needs ModP / ModN and the integer typedefs).
 #pragma once
 
 namespace p2e {
@@ -39,7 +39,11 @@ constexpr mi32 MI_M30 = 0x3fffffff;
 // t = [u v; q r] with t * [f, g] = 2^30 * [f', g'].
 P2E_HD mi32 mi_divsteps30(mi32 zeta, u32 f, u32 g, mi32& tu, mi32& tv, mi32& tq, mi32& tr) {
   u32 u = 1, v = 0, q = 0, r = 1;
-#pragma unroll 6
+#ifndef MI_UNROLL
+#define MI_UNROLL 6
+#endif
+  constexpr int mi_unroll = MI_UNROLL;
+#pragma unroll mi_unroll
   for (int i = 0; i < 30; i++) {
     u32 c1 = (u32)(zeta >> 31);            // zeta < 0
     const u32 c2 = 0u - (g & 1u);          // g odd

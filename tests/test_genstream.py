@@ -360,12 +360,13 @@ def _rand_point(rng):
     return S.pt_mul(rng.randrange(1, N), S.G)
 
 
-@pytest.fixture(params=["fused", "staged", "staged-nograph"])
+@pytest.fixture(params=["walk", "fused", "staged", "staged-nograph"])
 def gs_mode(request, engine):
-    """Both execution forms of a launch group (one fused kernel / gather -> batched kernel -> scatter), with and
-    without the CUDA graph (p2e_set_option)."""
-    old = {k: engine.get_option(k) for k in ("genstream_fused", "genstream_graph")}
-    engine.set_option("genstream_fused", 1 if request.param == "fused" else 0)
+    """Every execution form of a stream: the level walker (one launch, a CTA walks all levels for its 32 circuits), one
+    fused kernel per launch group, gather -> batched kernel -> scatter, with and without the CUDA graph (p2e_set_option)."""
+    old = {k: engine.get_option(k) for k in ("genstream_fused", "genstream_graph", "genstream_walk")}
+    engine.set_option("genstream_walk", 2 if request.param == "walk" else 0)
+    engine.set_option("genstream_fused", 0 if request.param.startswith("staged") else 1)
     engine.set_option("genstream_graph", 0 if request.param.endswith("nograph") else 1)
     yield request.param
     for k, v in old.items():

@@ -46,10 +46,14 @@ def constant_limbs_ok():
 
 
 @pytest.mark.gpu
-def test_circuit_stream_equals_the_tape_witness(engine, circuit):
+@pytest.mark.parametrize("walk,n", [(1, 24), (1, 77), (0, 24)])
+def test_circuit_stream_equals_the_tape_witness(engine, circuit, walk, n):
+    """walk = 1: the level walker (what a stream of 1 862 levels runs by default: one launch); walk = 0: one fused kernel per
+    launch group in a CUDA graph.  n = 77: a ragged last CTA of the walker (32 circuits per CTA)."""
     b, (msg, r, s, pk) = circuit
+    old = engine.get_option("genstream_walk")
+    engine.set_option("genstream_walk", walk)
     gs = engine.load_generator_stream(b.bytes())
-    n = 24
     wl = W.ecdsa_workload(n, seed=2718)
     vals = {"msg": wl["msg"].copy(), "r": wl["r"].copy(), "s": wl["s"].copy(), "pkx": wl["pkx"].copy(), "pky": wl["pky"].copy()}
     vals["r"][0, 5] ^= np.uint64(1)             # a wrong signature: every generator still has a witness, the final connect fails
@@ -70,3 +74,4 @@ def test_circuit_stream_equals_the_tape_witness(engine, circuit):
     assert np.array_equal(got[x3:x3 + 9, 5], vals["r"][:, 5]) and not np.array_equal(want[x3:x3 + 9, 5], vals["r"][:, 5])
     assert np.array_equal(err, werr) and err[5] == pkg.ERR_CONNECT and not np.delete(err, 5).any()
     gs.close()
+    engine.set_option("genstream_walk", old)
