@@ -26,9 +26,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# Independent batches are pipelined on many CUDA streams (16 per 4096 signatures, twice that inside the library): with the
-# default 8 hardware work queues they alias and serialise (N = 1: 0.79 -> 0.67 ms per step with 32 queues; N = 2,
-# 2048-signature shards: 0.523 -> 0.386 ms).
+# Independent batches are pipelined on 32 CUDA streams: with the default 8 hardware work queues they alias and serialise
+# (measured with 16 streams: N = 1: 0.79 -> 0.67 ms per step with 32 queues; N = 2, 2048-signature shards: 0.523 -> 0.386 ms).
 # Must be set before the CUDA context exists.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
@@ -258,7 +257,7 @@ class Bench:
             self.dist = dist
         self.eng = pkg.Engine(self.local_rank)
         self.lib = self.eng.lib
-        for opt in ("chain_split", "genstream_walk", "genstream_walk_shape"):   # experiment hooks of the bench (the library reads no environment): P2E_OPT_CHAIN_SPLIT=0, ...
+        for opt in ("chain_split", "chain_replay_lanes", "genstream_walk", "genstream_walk_shape"):   # experiment hooks of the bench (the library reads no environment): P2E_OPT_CHAIN_SPLIT=0, ...
             if os.environ.get("P2E_OPT_" + opt.upper()) is not None:
                 self.eng.set_option(opt, int(os.environ["P2E_OPT_" + opt.upper()]))
         self.st = torch.cuda.Stream()          # a real (non-NULL) stream: NULL selects the library's own
@@ -548,8 +547,10 @@ class Bench:
 
         # Independent batches are enqueued round-robin on S streams (async *_dev API, one output buffer + one scratch
         # arena per stream) so the latency-bound per-signature kernels of one batch overlap the full-GPU kernels of
-        # another.  Strong scaling keeps the number of signatures in flight per GPU constant (S grows with N).
-        S = max(1, int(os.environ.get("P2E_BENCH_STREAMS", str(min(64, 16 * (n_total // max(n, 1)))))))
+        # another.  32 streams = the 32 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS): more alias, fewer leave the device
+        # short of batches in flight (4096 per call: 16 / 24 / 32 streams 0.620 / 0.606 / 0.600 ms; 512 per call: 16 / 32 / 64 /
+        # 128 streams 0.142 / 0.118 / 0.119 / 0.119 ms; scripts/small_batch.py)
+        S = max(1, int(os.environ.get("P2E_BENCH_STREAMS", "32")))
         streams = [torch.cuda.Stream() for _ in range(S)]
         nars = [torch.empty((nn, n), dtype=torch.int32, device="cuda") for _ in range(S)]
         eds = [torch.empty(n, dtype=torch.int32, device="cuda") for _ in range(S)]
@@ -569,7 +570,7 @@ class Bench:
             assert rc == 0, eng.last_error()
 
         # the two other device formats, measured the same way (secondary): compact with the check_sum columns, plain u64
-        S2 = min(S, 8)
+        S2 = min(S, 12)
         wides = [torch.empty((nw, n), dtype=torch.int64, device="cuda") for _ in range(S2)]
 
         def step_compact_wide():
@@ -671,10 +672,19 @@ class Bench:
         ms = timed(step, steps)
         stagger_cycles = 0
         latency_ms = None
+        latency2_ms = None
         if "step_single" in s:
             s["step_single"]()
             self.barrier()
             latency_ms = timed(s["step_single"], min(steps, 10)) / min(steps, 10)
+            if wl == "ecdsa":
+                # the same single batch with the two-lane (latency) form of the replay kernel, whatever the call size
+                old_lanes = self.eng.get_option("chain_replay_lanes")
+                self.eng.set_option("chain_replay_lanes", 2)
+                s["step_single"]()
+                self.barrier()
+                latency2_ms = timed(s["step_single"], min(steps, 10)) / min(steps, 10)
+                self.eng.set_option("chain_replay_lanes", old_lanes)
         if sampler is not None:
             t_end = time.time() + 0.7          # keep the load on until nvidia-smi has a few samples
             while time.time() < t_end:
@@ -790,6 +800,8 @@ class Bench:
         if streams:
             res["streams"] = len(streams)
             res["single_stream_ms_per_step"] = latency_ms
+            if latency2_ms is not None:
+                res["single_stream_ms_per_step_two_lane_replay"] = latency2_ms
         if wl == "ecdsa" and kernel_ms:
             names = self.eng.CHAIN_KERNELS
             res["kernel_ms"] = {nm: round(v, 4) for nm, v in zip(names, kernel_ms)}
@@ -890,6 +902,7 @@ def main():
                        "pipelining": "steps are independent batches enqueued round-robin on `streams` CUDA streams through the async *_dev "
                                      "entry point; ms_per_step = timed region / steps; single_stream_ms_per_step = one batch at a time",
                        "single_stream_ms_per_step": main_res.get("single_stream_ms_per_step"),
+                       "single_stream_ms_per_step_two_lane_replay": main_res.get("single_stream_ms_per_step_two_lane_replay"),
                        "device_format": main_res.get("device_format")},
             "e2e": main_res["e2e"], "e2e_compact": main_res.get("e2e_compact"), "e2e_u64": main_res.get("e2e_u64"), "gpu_launches": main_res["gpu_launches"],
             "clocks": main_res.get("clocks"),

@@ -449,8 +449,14 @@ __device__ __forceinline__ u32 load_scalar_limbs(const ChainArgs& A, const Ref& 
 // each step of the point formulas the two lanes compute the two products of an INDEPENDENT pair and swap the
 // results with an 8-word shfl_xor, so a general addition is 8 sequential multiplications instead of 16 (mixed:
 // 6 vs 11, doubling: 4 vs 7).  Static schedule, no shared memory; linear steps are done redundantly by both lanes.
+template <int LANES>
 __device__ __forceinline__ void duo_mul2(bool odd, const u32 (&a)[NW], const u32 (&b)[NW], u32 (&r1)[NW],
                                          const u32 (&c)[NW], const u32 (&d)[NW], u32 (&r2)[NW]) {
+  if (LANES == 1) {                                  // one lane per (signature, chain): both products here, no exchange
+    fm(a, b, r1);
+    fm(c, d, r2);
+    return;
+  }
   F8 x, y;
 #pragma unroll
   for (int l = 0; l < NW; l++) { x.v[l] = odd ? c[l] : a[l]; y.v[l] = odd ? d[l] : b[l]; }
@@ -462,7 +468,13 @@ __device__ __forceinline__ void duo_mul2(bool odd, const u32 (&a)[NW], const u32
     r2[l] = odd ? mine.v[l] : other;
   }
 }
+template <int LANES>
 __device__ __forceinline__ void duo_sqr2(bool odd, const u32 (&a)[NW], u32 (&r1)[NW], const u32 (&c)[NW], u32 (&r2)[NW]) {
+  if (LANES == 1) {
+    fs(a, r1);
+    fs(c, r2);
+    return;
+  }
   F8 x;
 #pragma unroll
   for (int l = 0; l < NW; l++) x.v[l] = odd ? c[l] : a[l];
@@ -476,51 +488,52 @@ __device__ __forceinline__ void duo_sqr2(bool odd, const u32 (&a)[NW], u32 (&r1)
 }
 
 // R = P + Q with Z3 = Z1*Z2*H, H = X2*Z1^2 - X1*Z2^2  (so x2 - x1 = Z3 / (Z1^3 Z2^3)).  Q_AFFINE: Z2 == 1.
-template <bool Q_AFFINE>
+template <int LANES, bool Q_AFFINE>
 __device__ __forceinline__ void duo_add(bool odd, const JacF& P, const JacF& Q, JacF& R) {
   u32 z1z1[NW], u2[NW], s2[NW], h[NW], r[NW], t[NW], t2[NW], hh[NW], rr[NW], hhh[NW], v[NW], w[NW], v2[NW];
   if (Q_AFFINE) {
     fs(P.Z, z1z1);
-    duo_mul2(odd, Q.Y, P.Z, t2, Q.X, z1z1, u2);
+    duo_mul2<LANES>(odd, Q.Y, P.Z, t2, Q.X, z1z1, u2);
     f8_sub(u2, P.X, h);
-    duo_mul2(odd, t2, z1z1, s2, h, h, hh);
+    duo_mul2<LANES>(odd, t2, z1z1, s2, h, h, hh);
     f8_sub(s2, P.Y, r);
-    duo_mul2(odd, r, r, rr, h, hh, hhh);
-    duo_mul2(odd, P.X, hh, v, P.Z, h, R.Z);          // Z3 = Z1 h
+    duo_mul2<LANES>(odd, r, r, rr, h, hh, hhh);
+    duo_mul2<LANES>(odd, P.X, hh, v, P.Z, h, R.Z);          // Z3 = Z1 h
     f8_sub(rr, hhh, t);
     f8_add(v, v, v2);
     f8_sub(t, v2, R.X);                              // X3 = r^2 - hhh - 2v
     f8_sub(v, R.X, w);
-    duo_mul2(odd, r, w, t, P.Y, hhh, t2);
+    duo_mul2<LANES>(odd, r, w, t, P.Y, hhh, t2);
     f8_sub(t, t2, R.Y);                              // Y3 = r (v - X3) - Y1 hhh
   } else {
     u32 z2z2[NW], zz[NW], u1[NW], s1[NW];
-    duo_sqr2(odd, P.Z, z1z1, Q.Z, z2z2);
-    duo_mul2(odd, P.Y, Q.Z, t, Q.Y, P.Z, t2);
-    duo_mul2(odd, P.X, z2z2, u1, Q.X, z1z1, u2);
-    duo_mul2(odd, t, z2z2, s1, t2, z1z1, s2);
+    duo_sqr2<LANES>(odd, P.Z, z1z1, Q.Z, z2z2);
+    duo_mul2<LANES>(odd, P.Y, Q.Z, t, Q.Y, P.Z, t2);
+    duo_mul2<LANES>(odd, P.X, z2z2, u1, Q.X, z1z1, u2);
+    duo_mul2<LANES>(odd, t, z2z2, s1, t2, z1z1, s2);
     f8_sub(u2, u1, h);
     f8_sub(s2, s1, r);
-    duo_sqr2(odd, h, hh, r, rr);
-    duo_mul2(odd, P.Z, Q.Z, zz, h, hh, hhh);
-    duo_mul2(odd, u1, hh, v, zz, h, R.Z);            // Z3 = Z1 Z2 h
+    duo_sqr2<LANES>(odd, h, hh, r, rr);
+    duo_mul2<LANES>(odd, P.Z, Q.Z, zz, h, hh, hhh);
+    duo_mul2<LANES>(odd, u1, hh, v, zz, h, R.Z);            // Z3 = Z1 Z2 h
     f8_sub(rr, hhh, t);
     f8_add(v, v, v2);
     f8_sub(t, v2, R.X);
     f8_sub(v, R.X, w);
-    duo_mul2(odd, r, w, t, s1, hhh, t2);
+    duo_mul2<LANES>(odd, r, w, t, s1, hhh, t2);
     f8_sub(t, t2, R.Y);
   }
 }
 
 // R = 2P with Z3 = 2*Y1*Z1  (so 2y = Z3 / Z1^4)
+template <int LANES>
 __device__ __forceinline__ void duo_dbl(bool odd, const JacF& P, JacF& R) {
   u32 xx[NW], yy[NW], yyyy[NW], s[NW], s2[NW], m[NW], t[NW], t2[NW], yz[NW], mm[NW], y8[NW];
-  duo_sqr2(odd, P.X, xx, P.Y, yy);
+  duo_sqr2<LANES>(odd, P.X, xx, P.Y, yy);
   f8_mul_small<3>(xx, m);              // M = 3 XX
-  duo_mul2(odd, yy, yy, yyyy, P.X, yy, t);
+  duo_mul2<LANES>(odd, yy, yy, yyyy, P.X, yy, t);
   f8_mul_small<4>(t, s);               // S = 4 X YY
-  duo_mul2(odd, P.Y, P.Z, yz, m, m, mm);
+  duo_mul2<LANES>(odd, P.Y, P.Z, yz, m, m, mm);
   f8_mul_small<8>(t, s2);              // 2 S
   f8_sub(mm, s2, R.X);                 // X3 = M^2 - 2S
   f8_sub(s, R.X, t);
@@ -530,10 +543,15 @@ __device__ __forceinline__ void duo_dbl(bool odd, const JacF& P, JacF& R) {
   f8_add(yz, yz, R.Z);                 // Z3 = 2 Y1 Z1
 }
 
+// LANES = 2: the two-lane form above (half the dependency chain: single batches, small shards).  LANES = 1: one lane
+// per (signature, chain) -- the same formulas without operand selects / shuffles / redundant linear steps (~25 % fewer
+// warp instructions for twice the latency): calls of 4096 signatures or more, where the pipelined rate is bound by
+// issued instructions (option "chain_replay_lanes").
+template <int LANES>
 __global__ void __launch_bounds__(64) k_chain_replay(ChainArgs A, int chain0) {
   const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool odd = threadIdx.x & 1;
-  const size_t i_raw = tid >> 1;
+  const bool odd = LANES == 2 && (threadIdx.x & 1);
+  const size_t i_raw = LANES == 2 ? tid >> 1 : tid;
   const bool valid = i_raw < A.n;
   const size_t i = valid ? i_raw : A.n - 1;       // the pair of an out-of-range task shadows the last signature
   const bool writer = valid && !odd;
@@ -593,12 +611,12 @@ __global__ void __launch_bounds__(64) k_chain_replay(ChainArgs A, int chain0) {
     JacF P, Q;
     if (p1 == resident) P = R; else load_jac(A, p1, i, P);
     if (op.type == PT_DBL) {
-      duo_dbl(odd, P, R);
+      duo_dbl<LANES>(odd, P, R);
       p2 = p1;
     } else {
       if (p2 == resident) Q = R; else load_jac(A, p2, i, Q);
-      if (op.flags & PF_P2_AFFINE) duo_add<true>(odd, P, Q, R);
-      else duo_add<false>(odd, P, Q, R);
+      if (op.flags & PF_P2_AFFINE) duo_add<LANES, true>(odd, P, Q, R);
+      else duo_add<LANES, false>(odd, P, Q, R);
     }
     if (writer) {
       stw(A.JX, k, A.cap, i, R.X);
@@ -1257,10 +1275,11 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
   if ((rc = get_arena(S, st, bytes, &arena))) return rc;
   void* scratch = arena->ptr;
   // profiling keeps everything on the caller's stream so the events bracket each kernel
-  // (measured: the split pays at >= 2048 signatures per call, 0.628 against 0.66 ms per 4096, and costs below -- its
-  // event hops are a fixed price per call: 0.122 against 0.109 ms per 512; profiles/r02_notes.md)
-  const long split_opt = option(OPT_CHAIN_SPLIT);
-  const bool split = !S.profiling && (split_opt == 2 || (split_opt == 1 && n >= 2048));
+  // internal high / low priority streams (option "chain_split", default off): they pay only for a host that keeps fewer
+  // caller streams in flight than the device has hardware queues (16 streams x 4096 signatures, two-lane replay: 0.628
+  // against 0.652 ms per call); with 32 caller streams they alias on the 32 queues (0.600 against 0.618 ms, one-lane
+  // replay) and below 2048 signatures per call their event hops cost more than they hide (profiles/r02_notes.md)
+  const bool split = !S.profiling && option(OPT_CHAIN_SPLIT) != 0;
   cudaStream_t s_hi = split ? arena->hi : st, s_lo = split ? arena->lo : st;
   if (split) {
     P2E_CUDA(cudaEventRecord(arena->ev_in, st));
@@ -1322,11 +1341,20 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
       if (prof) prof_mark(S, st);
       trace_mark(S, tr, call_id, 1, s_hi);
       if (no) {
-        const unsigned g_duo = (unsigned)((2 * cn + 63) / 64);
-        if (pm & 2) k_chain_replay<<<dim3(g_duo, 2), 64, 0, s_hi>>>(A, 0);      // fixed-base and msm chains side by side, 2 lanes each
+        const long lanes_opt = option(OPT_CHAIN_REPLAY_LANES);
+        const bool duo = lanes_opt == 2 || (lanes_opt == 0 && n < 4096);
+        const unsigned g_duo = (unsigned)(((duo ? 2 : 1) * cn + 63) / 64);
+        // fixed-base and msm chains side by side
+        if (pm & 2) {
+          if (duo) k_chain_replay<2><<<dim3(g_duo, 2), 64, 0, s_hi>>>(A, 0);
+          else k_chain_replay<1><<<dim3(g_duo, 2), 64, 0, s_hi>>>(A, 0);
+        }
         if (prof) prof_mark(S, st);
         trace_mark(S, tr, call_id, 2, s_hi);
-        if ((pm & 2) && o.d.chain_end[2] > o.d.chain_begin[2]) k_chain_replay<<<dim3(g_duo, 1), 64, 0, s_hi>>>(A, 2);   // join
+        if ((pm & 2) && o.d.chain_end[2] > o.d.chain_begin[2]) {                                             // join
+          if (duo) k_chain_replay<2><<<dim3(g_duo, 1), 64, 0, s_hi>>>(A, 2);
+          else k_chain_replay<1><<<dim3(g_duo, 1), 64, 0, s_hi>>>(A, 2);
+        }
         if (prof) prof_mark(S, st);
         trace_mark(S, tr, call_id, 3, s_hi);
         if (pm & 4) {

@@ -13,7 +13,7 @@ from plonky2_ecdsa_b200 import workload as W
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 32
-SPLIT = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+SPLIT = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 eng = pkg.Engine(0)
 lib = eng.lib
 eng.set_option("chain_split", SPLIT)

@@ -10,6 +10,16 @@ from plonky2_ecdsa_b200 import workload as W
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[1, 2])
+def replay_lanes(request, engine):
+    """Both forms of the Jacobian replay kernel (p2e_set_option("chain_replay_lanes")): one lane per (signature, chain) --
+    what calls of 4096 signatures or more run -- and the two-lane form of smaller calls."""
+    old = engine.get_option("chain_replay_lanes")
+    engine.set_option("chain_replay_lanes", request.param)
+    yield request.param
+    engine.set_option("chain_replay_lanes", old)
+
+
 def _first_diff(col, ref, kinds, offs):
     for idx, (a, b) in enumerate(zip(col, ref)):
         if int(a) != b:
@@ -18,7 +28,7 @@ def _first_diff(col, ref, kinds, offs):
     return None
 
 
-def test_ecdsa_witness_vs_oracle(engine):
+def test_ecdsa_witness_vs_oracle(engine, replay_lanes):
     n = 6
     wl = W.ecdsa_workload(n, seed=4242)
     wit, err = engine.verify_secp256k1_message_witness(wl["msg"], wl["r"], wl["s"], wl["pkx"], wl["pky"])
@@ -45,7 +55,7 @@ def test_ecdsa_bad_signature_flags_connect(engine):
     assert err[0] & 128 and err[1] == 0
 
 
-def test_glv_mul_witness_vs_oracle(engine):
+def test_glv_mul_witness_vs_oracle(engine, replay_lanes):
     n = 5
     ks = [(0x1357 << 240 | 12345), S.SECP_N - 2, 3, 1 << 200, 0xdeadbeef << 128]
     pts = [S.pt_mul(7 + j, S.G) for j in range(n)]
@@ -87,7 +97,7 @@ def _rand_points(n, seed):
     return [S.pt_mul(rng.randrange(1, S.SECP_N), S.G) for _ in range(n)]
 
 
-def test_curve_add_double_conditional_add_vs_oracle(engine):
+def test_curve_add_double_conditional_add_vs_oracle(engine, replay_lanes):
     """Mirrors the reference's test_curve_add / test_curve_double / test_curve_conditional_add
     (gadgets/curve.rs:359-456): random points, result must equal the native sum, and here the whole
     generator tape must equal the oracle's."""
@@ -116,7 +126,7 @@ def test_curve_add_double_conditional_add_vs_oracle(engine):
         assert (S.get_biguint(r[0].limbs), S.get_biguint(r[1].limbs)) == want
 
 
-def test_curve_add_equal_x_flags_inverse_zero(engine):
+def test_curve_add_equal_x_flags_inverse_zero(engine, replay_lanes):
     """Adding a point to itself with the incomplete formulas: x2 - x1 = 0, the reference's inverse() panics."""
     P = _rand_points(3, 3)
     x, y = W.ints_to_limbs([p[0] for p in P]), W.ints_to_limbs([p[1] for p in P])
@@ -149,7 +159,7 @@ def test_chain_chunking_is_transparent(engine):
     assert [int(v) for v in w2[:, 299]] == wb.flat()
 
 
-def test_replay_kernel_odd_batch_is_bit_exact(engine):
+def test_replay_kernel_odd_batch_is_bit_exact(engine, replay_lanes):
     """The two-lane replay kernel pairs lanes 2j / 2j+1: an odd batch size leaves a half-filled warp."""
     wl = W.ecdsa_workload(71, seed=31)
     args = (wl["msg"], wl["r"], wl["s"], wl["pkx"], wl["pky"])
@@ -161,7 +171,7 @@ def test_replay_kernel_odd_batch_is_bit_exact(engine):
         assert [int(v) for v in w2[:, j]] == ref
 
 
-def test_ecdsa_edge_inputs_match_reference_panics(engine):
+def test_ecdsa_edge_inputs_match_reference_panics(engine, replay_lanes):
     """Rows where the reference would panic get an error bit; neighbours in the same batch are untouched.
     s = 0 -> FF::inverse() of zero (nonnative.rs:863); s >= 2^256 -> from_noncanonical_biguint panics;
     msg limb >= 2^29 -> MulNonnativeGenerator's limb assert (mul_nonnative.rs:275-276); a non-canonical
@@ -202,7 +212,7 @@ def test_ecdsa_edge_inputs_match_reference_panics(engine):
             assert err[4] != 0
 
 
-def test_fixed_base_mul_vs_oracle(engine):
+def test_fixed_base_mul_vs_oracle(engine, replay_lanes):
     """Mirrors test_fixed_base (gadgets/curve_fixed_base.rs:86-116): result == scalar * G."""
     import random
     rng = random.Random(55)
@@ -216,7 +226,7 @@ def test_fixed_base_mul_vs_oracle(engine):
         assert (S.get_biguint(res[0].limbs), S.get_biguint(res[1].limbs)) == S.pt_mul(k, S.G)
 
 
-def test_curve_msm_vs_oracle(engine):
+def test_curve_msm_vs_oracle(engine, replay_lanes):
     """Mirrors test_curve_msm (gadgets/curve_msm.rs:98-136): result == n*p + m*q with full-width scalars."""
     import random
     rng = random.Random(56)
@@ -297,7 +307,7 @@ def test_compact_derived_form_rebuilds_check_sum_from_carries(engine):
 
 
 @pytest.mark.gpu
-def test_ecdsa_batch_vs_c_oracle(engine):
+def test_ecdsa_batch_vs_c_oracle(engine, replay_lanes):
     """Every slot of 768 complete witnesses against the C restatement of the reference's generators
     (oracle/p2e_oracle.c, itself pinned to the Python spec by tests/test_oracle_c.py): one Fermat ladder
     per curve op on the CPU side, batched inversion on the GPU side, identical bits."""
