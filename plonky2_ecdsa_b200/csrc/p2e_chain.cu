@@ -932,7 +932,10 @@ __device__ __forceinline__ u32 expand_op(const ChainArgs& A, const EM& em, const
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(128, 3) k_chain_expand(ChainArgs A) {
+#ifndef P2E_EXPAND_MINB
+#define P2E_EXPAND_MINB 3
+#endif
+__global__ void __launch_bounds__(128, P2E_EXPAND_MINB) k_chain_expand(ChainArgs A) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   int k = blockIdx.y;
   if (i >= A.n) return;
