@@ -46,6 +46,8 @@ WORKLOAD_NAMES = {
     "evalrcfc": "u29 range-check gate (9 limbs, 3-bit aux limbs; plonky2_ux spec unpinned) eval_filtered + alpha-combination (2 challenges, fused) over 2^20 Goldilocks LDE rows",
     "genstream": "serialized generator stream (8 x curve_add + curve_double chained: 224 in-tree generators, target-level wiring of "
                  "gadgets/curve.rs) run by the level-scheduled executor for 4096 circuits",
+    "rcrows": "the seven plonky2_ux range-check gate rows of every mul_nonnative of the ECDSA circuit (1087 instances x 7 rows x 512 signatures, "
+              "703 wires per instance, 3-bit aux limbs: spec unpinned) from the device-resident compact witness",
     "genstream_ecdsa": "the complete verify_secp256k1_message_circuit as a serialized generator stream (30955 generators incl. the plonky2 glue, "
                        "1862 dependency levels) run by the level-scheduled executor for 4096 circuits",
     "lde": "coset LDE (ifft 2^17 -> zero-pad -> coset fft 2^20, rate 8) of 135 wire polynomials: the matrix the gate evaluators read",
@@ -72,6 +74,7 @@ METRICS = {
     "genstream": ("generator_stream_circuits_per_s", "circuits/s"),
     "genstream_ecdsa": ("generator_stream_ecdsa_circuits_per_s", "circuits/s"),
     "lde": ("coset_lde_output_elements_per_s", "elements/s"),
+    "rcrows": ("ecdsa_mul_range_check_gate_rows_per_s", "rows/s"),
 }
 
 
@@ -457,6 +460,45 @@ class Bench:
             return dict(step=step, step_e2e=step_e2e, units=n, h2d=len(in_slots) * 8 * n, d2h=len(out_slots) * 8 * n + 4 * n,
                         alg_bytes=2 * n_slots * 8 * n, kernel=gs_label(eng, gs), launches=gs_launches(eng, gs), err=ed, dtype="u32 limbs / u64 (int)",
                         keep=(gs, vd, table, hv, ho, he, in_slots, out_slots))
+        if wl == "rcrows":
+            import ctypes
+            n = 512
+            d = W.ecdsa_workload(n, seed=W.SEED + self.rank)
+            ins = [d[k] for k in ("msg", "r", "s", "pkx", "pky")]
+            ind = [self.dev(a) for a in ins]
+            arr = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in ind])
+            inp = ctypes.cast(arr, ctypes.c_void_p)
+            _, nn, _ = eng.tape_compact_layout(eng.TAPE_ECDSA)
+            nm = int(lib.p2e_tape_num_mul(eng.TAPE_ECDSA))
+            per, _, _ = eng.tape_mul_range_rows_shape(3)
+            nar = torch.empty((nn, n), dtype=torch.int32, device="cuda")
+            ed = torch.empty(n, dtype=torch.int32, device="cuda")
+            ed2 = torch.empty(n, dtype=torch.int32, device="cuda")
+            rows = torch.empty((nm * per, n), dtype=torch.int64, device="cuda")
+            assert lib.p2e_tape_witness_compact_dev(eng.TAPE_ECDSA, n, inp, n, nar.data_ptr(), None, n, ed.data_ptr(), sp) == 0, eng.last_error()
+            torch.cuda.synchronize()
+            assert not bool(ed.any())
+
+            def step():
+                rc = lib.p2e_tape_mul_range_rows_dev(eng.TAPE_ECDSA, n, inp, n, None, nar.data_ptr(), n, 0, nm, 3, rows.data_ptr(), n,
+                                                     ed2.data_ptr(), sp)
+                assert rc == 0, eng.last_error()
+            hin = [self.pinned(a) for a in ins]
+            he = torch.empty(n, dtype=torch.int32).pin_memory()
+
+            def step_e2e():
+                # host inputs -> witness (compact, device) -> rows (device) -> the error vector back: the rows stay in HBM for
+                # their consumer (3.1 GB per 512 signatures -- shipping them would only measure the PCIe link)
+                for t, h in zip(ind, hin):
+                    t.copy_(h, non_blocking=True)
+                assert lib.p2e_tape_witness_compact_dev(eng.TAPE_ECDSA, n, inp, n, nar.data_ptr(), None, n, ed.data_ptr(), sp) == 0
+                step()
+                he.copy_(ed2, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            # per instance: 703 wires written (u64) + 5 x 9 + 17 u32 values read
+            return dict(step=step, step_e2e=step_e2e, units=7 * nm * n, h2d=5 * 9 * 8 * n, d2h=4 * n,
+                        alg_bytes=(per * 8 + (5 * 9 + 17) * 4) * nm * n, kernel="k_tape_mul_range_rows", launches=1, err=ed2,
+                        dtype="u32 / u64 (int)", keep=(ind, nar, ed, rows, hin, he, arr))
         if wl in UX_WORKLOADS:
             gate, bits, lb, count, na, kname = UX_WORKLOADS[wl]
             nw, nc, _ = eng.ux_gate_shape(gate, bits, lb, count, na)
@@ -865,7 +907,7 @@ def main():
     main_res = b.measure(wl, args.steps, args.warmup, e2e_steps=max(2, min(args.steps, 5)), sample_clocks=True)
     secondary = {}
     if not args.no_secondary:
-        for w2 in ("mulmod", "mulmod_n", "eval", "evalcs", "evalfc", "evalcsfc", "evalrc", "evalrcfc", "evalcmp", "evaladd", "lde", "genstream", "genstream_ecdsa", "glv", "ecdsa"):
+        for w2 in ("mulmod", "mulmod_n", "eval", "evalcs", "evalfc", "evalcsfc", "evalrc", "evalrcfc", "evalcmp", "evaladd", "lde", "genstream", "genstream_ecdsa", "rcrows", "glv", "ecdsa"):
             if w2 != wl and w2 in WORKLOAD_NAMES:
                 try:
                     r2 = b.measure(w2, steps=min(args.steps, 20) if w2 not in ("glv", "genstream_ecdsa") else 3, warmup=3, e2e_steps=2)

@@ -185,6 +185,27 @@ int p2e_eval_check_sum(size_t n_rows, const uint64_t* wires, uint64_t* out);
 size_t p2e_tape_slots(int tape);
 int p2e_tape_inputs(int tape);
 size_t p2e_tape_layout(int tape, uint32_t* kinds, uint32_t* offsets);
+/* The plonky2_ux rows UNDER the in-tree generators, first kind: every mul_nonnative instance adds seven
+ * range_check_ux_circuit gate rows (gadgets/nonnative.rs:453-460): x, y, r, q, r again -- one gate input per 29-bit limb
+ * the target has -- then b[0..8] and b[8..16] of its CheckSum row as 34-bit inputs.  The call list and its inputs are
+ * in-tree (pinned); the gate-row layout is the restated plonky2_ux one (inputs first, then ceil(bits / limb_bits) aux
+ * limbs of limb_bits bits per input: DESIGN.md section 9, PARITY UNPINNED -- limb_bits is an argument).
+ *   p2e_tape_num_mul:  mul_nonnative instances of the tape, gadget order (ECDSA: 1 087).
+ *   p2e_tape_mul_info: limbs of the two factors (a constant's leading zero limbs are dropped, biguint.rs:165-175), the
+ *                      first slot of the instance's MulNonnative tuple, the modulus.
+ *   p2e_tape_mul_range_rows_shape: wires reserved per instance (5 calls x 9 (1 + a29) + 2 calls x 8 (1 + a34); 703 for
+ *                      limb_bits = 3), the wire offset and width of each of the seven calls inside that block.
+ *   p2e_tape_mul_range_rows_dev: rows[((j - j0) * wires_per_mul + call_offset + w) * rs + i] for instances [j0, j1) of
+ *                      every signature i, read from the finished device witness -- the plain u64 matrix (witness) OR
+ *                      the compact narrow matrix (narrow), stride ws -- and the tape's inputs.  A factor with fewer than 9
+ *                      limbs fills count (1 + a29) wires, the rest of its block is zero.  err[i]: P2E_ERR_LIMB_RANGE when
+ *                      a value does not fit (the gate would be unsatisfiable). */
+int p2e_tape_num_mul(int tape);
+int p2e_tape_mul_info(int tape, int j, int* x_limbs, int* y_limbs, uint32_t* out_slot, int* modulus);
+int p2e_tape_mul_range_rows_shape(int limb_bits, int* wires_per_mul, int* call_offsets, int* call_wires);
+int p2e_tape_mul_range_rows_dev(int tape, size_t n, const uint64_t* const* inputs, size_t is, const uint64_t* witness,
+                                const uint32_t* narrow, size_t ws, int j0, int j1, int limb_bits, uint64_t* rows, size_t rs,
+                                uint32_t* err, void* stream);
 int p2e_tape_witness_dev(int tape, size_t n, const uint64_t* const* inputs, size_t in_stride,
                          uint64_t* out, size_t out_stride, uint32_t* err, void* stream);
 int p2e_tape_witness(int tape, size_t n, const uint64_t* const* inputs, uint64_t* out, uint32_t* err);

@@ -476,6 +476,7 @@ class WitnessBuilder:
     def __init__(self):
         self.tape = []          # list of (kind, [values])
         self.counts = {}
+        self.mul_ops = []       # (x limbs, y limbs) of every mul_nonnative, call order (nonnative.rs:453-455 range-checks them)
 
     def _emit(self, kind, vals):
         self.tape.append((kind, list(vals)))
@@ -513,6 +514,7 @@ class WitnessBuilder:
         """nonnative.rs:390-464: wires zero-padded to 9 (:406-424); MulNonnative row then CheckSum row."""
         xw = x.limbs + [0] * (NUM_LIMBS - len(x.limbs))
         yw = y.limbs + [0] * (NUM_LIMBS - len(y.limbs))
+        self.mul_ops.append((list(x.limbs), list(y.limbs)))
         q, r, cs = mul_nonnative_gen(xw, yw, m)
         self._emit(K_MUL, r + q + cs)
         self._emit(K_CHECKSUM, check_sum_gen(cs))

@@ -45,6 +45,8 @@ struct DevTape {
   const u32* cmap;              // compact layout: slot -> narrow / wide row (p2e_tape_compact_layout)
   const u32* pt_nrow;           // per curve op: narrow row of its first slot
   const u32* pt_wrow;           // per curve op: wide row of its first check_sum slot
+  const MulRec* muls;           // every mul_nonnative instance, gadget order
+  int n_muls;
   int n_prep, n_ptops, n_checks, n_in_points;
   int32_t pre_pid[16];
   Ref fixed_scalar, msm_k1, msm_k2;
@@ -952,6 +954,71 @@ __global__ void __launch_bounds__(128, P2E_EXPAND_MINB) k_chain_expand(ChainArgs
   if (e) atomicOr(&A.err[i], e);
 }
 
+// ------------------------------------------------------------------------------------------
+// The plonky2_ux range-check rows of mul_nonnative (nonnative.rs:453-460): every instance adds seven
+// range_check_ux_circuit gate rows -- x, y, r, q, r again (29-bit limbs, as many as the target has) and b[0..8], b[8..16]
+// (34-bit).  One thread per (signature, instance, call): reads the values from the finished witness (either device
+// format) and writes the gate row of the restated spec (p2e_ux.cu: inputs first, then n_aux aux limbs of `lb` bits per
+// input; DESIGN.md section 9, PARITY UNPINNED like every plonky2_ux row).  A value that does not fit sets ERR_LIMB_RANGE.
+struct MulRowsArgs {
+  int j0, lb, a29, a34;          // first instance, aux-limb width, aux limbs per 29- / 34-bit input
+  int w29, w34, per_mul;         // wires reserved per call (9 (1 + a29), 8 (1 + a34)) and per instance
+  u64* rows;
+  size_t rs;
+};
+__device__ __forceinline__ u64 load_mul_factor_limb(const ChainArgs& A, const Ref& r, u64 bm, int l, size_t i) {
+  if (l >= r.nl) return 0;
+  if (r.space == SP_CPOINT) return A.t.const_points[r.off + l];
+  return load_wire(A, r.space, r.off + l, i) * bm;
+}
+__global__ void __launch_bounds__(128) k_tape_mul_range_rows(ChainArgs A, MulRowsArgs M) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n) return;
+  const int jj = blockIdx.y / 7, c = blockIdx.y % 7;
+  const MulRec m = A.t.muls[M.j0 + jj];
+  const bool wide = c >= 5;
+  const int n_aux = wide ? M.a34 : M.a29;
+  int count = wide ? 8 : NL;
+  u64* row = M.rows + ((size_t)jj * M.per_mul + (wide ? 5 * M.w29 + (c - 5) * M.w34 : c * M.w29)) * M.rs + i;
+  const int width = wide ? M.w34 : M.w29;
+  u64 v[NL];
+  if (c < 2) {
+    const Ref& r = c == 0 ? m.x : m.y;
+    count = r.nl;
+    u64 bm = 1;
+    if (r.bspace != SP_NONE) bm = (load_wire(A, r.bspace, r.boff, i) ^ (u64)r.binv) & 1;
+    for (int l = 0; l < NL; l++) v[l] = load_mul_factor_limb(A, r, bm, l, i);
+  } else if (!wide) {
+    const u32 base = m.out + (c == 3 ? 9u : 0u);                      // r, q, r
+    for (int l = 0; l < NL; l++) v[l] = load_wire(A, SP_OUT, base + l, i);
+  } else {
+    // CheckSum carries b[8 (c - 5) ..]: plain slots out + 35 + l; compact: low words in the 16 rows after q, tops packed
+    const int l0 = 8 * (c - 5);
+    if (A.fmt == FMT_PLAIN) {
+      for (int l = 0; l < 8; l++) v[l] = A.out[(size_t)(m.out + 35 + l0 + l) * A.os + i];
+    } else {
+      const u32 r0 = A.t.cmap[m.out];
+      const u32 tops = A.nar[(size_t)(r0 + 34) * A.os + i];
+      for (int l = 0; l < 8; l++) v[l] = (u64)A.nar[(size_t)(r0 + 18 + l0 + l) * A.os + i] | ((u64)((tops >> (2 * (l0 + l))) & 3u) << 32);
+    }
+    v[8] = 0;
+  }
+  u32 e = 0;
+  const u64 mask = (1ull << M.lb) - 1;
+  int wdone = 0;
+  for (int u = 0; u < count; u++) row[(size_t)(wdone++) * M.rs] = v[u];
+  for (int u = 0; u < count; u++) {
+    u64 t = v[u];
+    for (int a = 0; a < n_aux; a++) {
+      row[(size_t)(wdone++) * M.rs] = t & mask;
+      t >>= M.lb;
+    }
+    if (t) e |= ERR_LIMB_RANGE;
+  }
+  for (; wdone < width; wdone++) row[(size_t)wdone * M.rs] = 0;     // a target with fewer limbs: a narrower gate, rest unused
+  if (e) atomicOr(&A.err[i], e);
+}
+
 // K5: connect_nonnative checks
 __global__ void __launch_bounds__(32) k_chain_checks(ChainArgs A) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1117,6 +1184,7 @@ static int upload_tape(const Tape& t, TapeOnDevice& o) {
   size_t o_cm = reserve(cmap.size() * sizeof(u32));
   size_t o_nr = reserve(nrow.size() * sizeof(u32));
   size_t o_wr = reserve(wrow.size() * sizeof(u32));
+  size_t o_mu = reserve((t.muls.size() + 1) * sizeof(MulRec));
   std::vector<unsigned char> host(off + 16, 0);
   memcpy(&host[o_prep], t.prep.data(), t.prep.size() * sizeof(PrepOp));
   memcpy(&host[o_pt], t.ptops.data(), t.ptops.size() * sizeof(PtOp));
@@ -1129,6 +1197,7 @@ static int upload_tape(const Tape& t, TapeOnDevice& o) {
   memcpy(&host[o_cm], cmap.data(), cmap.size() * sizeof(u32));
   memcpy(&host[o_nr], nrow.data(), nrow.size() * sizeof(u32));
   memcpy(&host[o_wr], wrow.data(), wrow.size() * sizeof(u32));
+  memcpy(&host[o_mu], t.muls.data(), t.muls.size() * sizeof(MulRec));
   void* blob = nullptr;
   P2E_CUDA(cudaMalloc(&blob, host.size()));
   P2E_CUDA(cudaMemcpy(blob, host.data(), host.size(), cudaMemcpyHostToDevice));
@@ -1144,6 +1213,8 @@ static int upload_tape(const Tape& t, TapeOnDevice& o) {
   o.d.cmap = (const u32*)(b + o_cm);
   o.d.pt_nrow = (const u32*)(b + o_nr);
   o.d.pt_wrow = (const u32*)(b + o_wr);
+  o.d.muls = (const MulRec*)(b + o_mu);
+  o.d.n_muls = (int)t.muls.size();
   o.d.n_prep = (int)t.prep.size();
   o.d.n_ptops = (int)t.ptops.size();
   o.d.n_checks = (int)t.checks.size();
@@ -1493,6 +1564,83 @@ size_t p2e_tape_slots(int tape) { return bad_tape(tape) ? 0 : get_tape(tape).n_s
 int p2e_tape_inputs(int tape) { return bad_tape(tape) ? -1 : (int)get_tape(tape).n_inputs; }
 size_t p2e_tape_layout(int tape, uint32_t* kinds, uint32_t* offsets) {
   return bad_tape(tape) ? 0 : tape_layout(get_tape(tape), kinds, offsets);
+}
+
+// ---- the range-check rows of mul_nonnative (the plonky2_ux rows under the in-tree generators) ----
+int p2e_tape_num_mul(int tape) { return bad_tape(tape) ? -1 : (int)get_tape(tape).muls.size(); }
+
+int p2e_tape_mul_info(int tape, int j, int* x_limbs, int* y_limbs, uint32_t* out_slot, int* modulus) {
+  if (bad_tape(tape)) return -1;
+  const Tape& t = get_tape(tape);
+  if (j < 0 || j >= (int)t.muls.size()) return set_error_msg("tape_mul_info: instance out of range");
+  if (x_limbs) *x_limbs = t.muls[j].x.nl;
+  if (y_limbs) *y_limbs = t.muls[j].y.nl;
+  if (out_slot) *out_slot = t.muls[j].out;
+  if (modulus) *modulus = (int)t.muls[j].mod;
+  return 0;
+}
+
+int p2e_tape_mul_range_rows_shape(int limb_bits, int* wires_per_mul, int* call_offsets, int* call_wires) {
+  if (limb_bits < 1 || limb_bits > 8) return set_error_msg("tape_mul_range_rows: limb_bits must be 1 .. 8");
+  const int a29 = (LB + limb_bits - 1) / limb_bits, a34 = (34 + limb_bits - 1) / limb_bits;
+  const int w29 = NL * (1 + a29), w34 = 8 * (1 + a34);
+  if (wires_per_mul) *wires_per_mul = 5 * w29 + 2 * w34;
+  for (int c = 0; c < 7; c++) {
+    if (call_offsets) call_offsets[c] = c < 5 ? c * w29 : 5 * w29 + (c - 5) * w34;
+    if (call_wires) call_wires[c] = c < 5 ? w29 : w34;
+  }
+  return 0;
+}
+
+int p2e_tape_mul_range_rows_dev(int tape, size_t n, const uint64_t* const* inputs, size_t is, const uint64_t* witness,
+                                const uint32_t* narrow, size_t ws, int j0, int j1, int limb_bits, uint64_t* rows, size_t rs,
+                                uint32_t* err, void* stream) {
+  if (bad_tape(tape)) return -1;
+  int rc = ensure_ready();
+  if (rc) return rc;
+  const Tape& t = get_tape(tape);
+  if (j0 < 0 || j1 < j0 || j1 > (int)t.muls.size()) return set_error_msg("tape_mul_range_rows: instance range out of bounds");
+  if (n == 0 || j0 == j1) return 0;
+  if ((witness == nullptr) == (narrow == nullptr)) return set_error_msg("tape_mul_range_rows: give the plain witness OR the compact narrow matrix");
+  if (!rows || !err) return set_error_msg("tape_mul_range_rows: NULL output");
+  if (is < n || ws < n || rs < n) return set_error_msg("stride < n");
+  if ((size_t)(j1 - j0) * 7 > 65535) return set_error_msg("tape_mul_range_rows: at most 9362 instances per call");
+  int per_mul = 0;
+  if ((rc = p2e_tape_mul_range_rows_shape(limb_bits, &per_mul, nullptr, nullptr))) return rc;
+  ChainState& S = chain_state();
+  TapeOnDevice* o;
+  {
+    std::lock_guard<std::mutex> lock(S.mu);
+    o = &S.tapes[tape];
+    if ((rc = upload_tape(t, *o))) return rc;
+  }
+  ChainArgs A;
+  memset(&A, 0, sizeof(A));
+  A.t = o->d;
+  A.n = n;
+  A.is = is;
+  for (int k = 0; k < (int)t.n_inputs && k < MAX_TAPE_INPUTS; k++) A.in[k] = inputs ? inputs[k] : nullptr;
+  if (t.n_inputs && !inputs) return set_error_msg("tape_mul_range_rows: NULL inputs");
+  A.fmt = witness ? FMT_PLAIN : FMT_COMPACT;
+  A.out = const_cast<u64*>(witness);
+  A.nar = const_cast<u32*>(narrow);
+  A.os = ws;
+  A.err = err;
+  MulRowsArgs M;
+  M.j0 = j0;
+  M.lb = limb_bits;
+  M.a29 = (LB + limb_bits - 1) / limb_bits;
+  M.a34 = (34 + limb_bits - 1) / limb_bits;
+  M.w29 = NL * (1 + M.a29);
+  M.w34 = 8 * (1 + M.a34);
+  M.per_mul = per_mul;
+  M.rows = rows;
+  M.rs = rs;
+  cudaStream_t st = pick_stream(stream);
+  P2E_CUDA(cudaMemsetAsync(err, 0, n * sizeof(uint32_t), st));
+  k_tape_mul_range_rows<<<dim3((unsigned)((n + 127) / 128), (unsigned)((j1 - j0) * 7)), 128, 0, st>>>(A, M);
+  P2E_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int p2e_tape_witness_dev(int tape, size_t n, const uint64_t* const* inputs, size_t is, uint64_t* out, size_t os,

@@ -183,6 +183,9 @@ class Builder {
   std::vector<int8_t> pt_chain;      // chain of the producing op, -1 for input / constant points
   int n_fixed = 0, n_msm = 0;
   std::string error;
+  // coordinates of every point as targets (for the factor references of MulRec)
+  std::vector<PtT> op_pts;           // result point of curve op k
+  PtT cur_pt[N_CHAINS];              // the running point of a chain (PF_*_CUR)
 
   Builder() {
     u64 k[4];
@@ -248,7 +251,25 @@ class Builder {
     uint32_t s = emit(G_MUL, 35);
     emit(G_CHECKSUM, 16);
     prep2(OP_MUL, mod, s, a, b);
+    mul_rec(a.r, b.r, s, mod);
     NNT r; r.r = mkref(SP_OUT, s, 9); return r;                     // r occupies the first 9 slots
+  }
+  void mul_rec(const Ref& x, const Ref& y, uint32_t out, int mod) {
+    MulRec m; m.x = x; m.y = y; m.out = out; m.mod = (uint32_t)mod;
+    t.muls.push_back(m);
+  }
+  Ref out9(uint32_t off) { return mkref(SP_OUT, off, 9); }
+  // the x coordinate of a point id as a target (the factor of curve_double's x_squared)
+  Ref coord_x(int32_t pid) {
+    if (pid >= PID_CONST_BASE) {
+      // constant_affine_point -> constant_nonnative (curve.rs:99-105, biguint.rs:165-175): leading zero limbs are dropped
+      const uint32_t base = (uint32_t)(pid - PID_CONST_BASE) * 18;
+      int nl = NL;
+      while (nl > 0 && t.const_points[base + nl - 1] == 0) nl--;
+      return mkref(SP_CPOINT, base, (uint8_t)nl);
+    }
+    if (pid >= PID_INPUT_BASE) return t.in_points[pid - PID_INPUT_BASE].x;
+    return op_pts[pid].x.r;
   }
   NNT inv_nonnative(const NNT& x, int mod) {                        // nonnative.rs:502-536
     uint32_t s = emit(G_INV, 18);
@@ -338,6 +359,9 @@ class Builder {
     emit(G_SUB, 10);
     emit(G_MUL, 35); emit(G_CHECKSUM, 16);
     emit(G_SUB, 10);
+    mul_rec(out9(s0), out9(s0 + 29), s0 + 38, 0);                   // s = u * v_inv
+    mul_rec(out9(s0 + 38), out9(s0 + 38), s0 + 89, 0);              // s^2
+    mul_rec(out9(s0 + 38), out9(s0 + 160), s0 + 170, 0);            // prod = s * x_diff
     return s0;
   }
   PtT point_of_op(int32_t k, uint32_t xoff, uint32_t yoff) {
@@ -358,7 +382,10 @@ class Builder {
     if (t.chain_end[cur_chain] == t.chain_begin[cur_chain]) t.chain_begin[cur_chain] = k;
     t.chain_end[cur_chain] = k + 1;
     t.ptops.push_back(o);
-    return point_of_op(k, slot + xo, slot + yo);
+    PtT res = point_of_op(k, slot + xo, slot + yo);
+    op_pts.push_back(res);
+    if (flags & PF_SET_CUR) cur_pt[cur_chain] = res;
+    return res;
   }
   PtT curve_add(int32_t p1, int32_t p2, uint8_t flags) {            // curve.rs:202-223
     uint32_t s = emit_curve_add();
@@ -376,6 +403,11 @@ class Builder {
     emit(G_SUB, 10);                                                 // x_diff
     emit(G_MUL, 35); emit(G_CHECKSUM, 16);                           // lambda_x_diff
     emit(G_SUB, 10);                                                 // y3
+    const Ref x1 = (flags & PF_P1_CUR) ? cur_pt[cur_chain].x.r : coord_x(p1);
+    mul_rec(x1, x1, s + 28, 0);                                      // x_squared
+    mul_rec(out9(s + 79), out9(s + 19), s + 89, 0);                  // lambda = triple_xx_a * inv_double_y
+    mul_rec(out9(s + 89), out9(s + 89), s + 140, 0);                 // lambda_squared
+    mul_rec(out9(s + 89), out9(s + 211), s + 221, 0);                // lambda_x_diff
     return push_ptop(PT_DBL, flags, 0, p1, -1, s, 201, 272);
   }
   PtT curve_conditional_add(PtOpType type, uint8_t flags, uint16_t aux, int32_t p1, int32_t p2 = -1) {   // curve.rs:225-243

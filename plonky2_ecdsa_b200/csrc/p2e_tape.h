@@ -15,7 +15,7 @@ namespace p2e {
 
 enum GenKind : uint32_t { G_ADD = 0, G_ADDMANY = 1, G_SUB = 2, G_INV = 3, G_MUL = 4, G_CHECKSUM = 5, G_GLV = 6 };
 
-enum Space : uint8_t { SP_NONE = 0, SP_OUT = 1, SP_IN = 2, SP_CONST = 3 };
+enum Space : uint8_t { SP_NONE = 0, SP_OUT = 1, SP_IN = 2, SP_CONST = 3, SP_CPOINT = 4 };   // SP_CPOINT: const_points pool (MulRec operands only)
 
 // A nonnative / BigUint target: `nl` limbs starting at `off` in `space`, optionally multiplied by
 // a bool target (mul_nonnative_by_bool, nonnative.rs:278-295), itself optionally negated (builder.not).
@@ -56,6 +56,15 @@ struct PtOp {
   uint32_t round;   // dependency round
 };
 
+// One mul_nonnative instance (nonnative.rs:390-464) in gadget order: its factors and the first slot of its MulNonnative
+// tuple (r[9] q[9] check_sum[17], followed by the CheckSum tuple b[16]).  What the seven range_check_ux_circuit calls of
+// nonnative.rs:453-460 read.
+struct MulRec {
+  Ref x, y;
+  uint32_t out;
+  uint32_t mod;
+};
+
 struct InputPoint {  // per-signature affine point whose coordinates are nonnative targets
   Ref x, y;
   uint32_t round;    // round from which the coordinates exist (loaded by that round's replay kernels)
@@ -75,6 +84,7 @@ struct Tape {
   std::vector<PrepOp> prep;
   std::vector<PtOp> ptops;
   std::vector<Check> checks;
+  std::vector<MulRec> muls;             // every mul_nonnative instance, gadget order
   std::vector<Ref> extra_refs;          // operand lists of OP_ADDMANY
   std::vector<InputPoint> in_points;    // pid = ptops.size() + index
   std::vector<uint32_t> const_limbs;    // SP_CONST pool (u32 limbs)

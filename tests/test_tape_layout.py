@@ -152,3 +152,32 @@ def test_derived_compact_form_rebuilds_check_sum_slots_of_an_oracle_witness():
     assert lib.p2e_tape_compact_expand(0, n, narrow3.ctypes.data, wide3.ctypes.data, out.ctypes.data) == 0
     assert np.array_equal(out[:, 0], flat) and np.array_equal(out, pkg.Engine.expand_compact(m, narrow3, wide3))
     assert lib.p2e_tape_compact_expand(99, n, narrow3.ctypes.data, None, out.ctypes.data) != 0
+
+
+def test_mul_nonnative_instances_of_the_ecdsa_tape():
+    """p2e_tape_num_mul / p2e_tape_mul_info: every mul_nonnative instance in gadget order, the first slot of its tuple and the
+    limb counts of its factors (what nonnative.rs:453-455 range-checks) -- against the oracle's call graph."""
+    import ctypes
+    lib = pkg.load_library()
+    kinds, offs, slots = _layout(lib.p2e_ecdsa_tape_layout, lib.p2e_ecdsa_tape_slots)
+    # the oracle builds its inputs with constant_nonnative (leading zero limbs dropped), the tape takes 9-limb targets: use
+    # values whose top limb is not zero
+    sk, msg, k = 0x1234567 << 200 | 99, 0xabcdef << 233 | 5, 0x777 << 222 | 1
+    pk = S.pt_mul(sk, S.G)
+    r, s = S.sign_message(msg, sk, k)
+    wb = S.ecdsa_witness(msg, r, s, pk)
+    lib.p2e_tape_num_mul.restype = ctypes.c_int
+    nm = lib.p2e_tape_num_mul(0)
+    mul_offs = [int(o) for kd, o in zip(kinds, offs) if kd == S.K_MUL]
+    assert nm == len(mul_offs) == len(wb.mul_ops) == 1087
+    xl, yl, md = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    sl = ctypes.c_uint32(0)
+    for j in range(nm):
+        assert lib.p2e_tape_mul_info(0, j, ctypes.byref(xl), ctypes.byref(yl), ctypes.byref(sl), ctypes.byref(md)) == 0
+        assert sl.value == mul_offs[j]
+        assert (xl.value, yl.value) == (len(wb.mul_ops[j][0]), len(wb.mul_ops[j][1])), j
+    assert lib.p2e_tape_mul_info(0, nm, None, None, None, None) != 0
+    per = ctypes.c_int(0)
+    offs7, wid7 = (ctypes.c_int * 7)(), (ctypes.c_int * 7)()
+    assert lib.p2e_tape_mul_range_rows_shape(3, ctypes.byref(per), offs7, wid7) == 0
+    assert per.value == 703 and list(wid7) == [99] * 5 + [104] * 2 and list(offs7) == [0, 99, 198, 297, 396, 495, 599]
