@@ -46,8 +46,8 @@ WORKLOAD_NAMES = {
     "evalrcfc": "u29 range-check gate (9 limbs, 3-bit aux limbs; plonky2_ux spec unpinned) eval_filtered + alpha-combination (2 challenges, fused) over 2^20 Goldilocks LDE rows",
     "genstream": "serialized generator stream (8 x curve_add + curve_double chained: 224 in-tree generators, target-level wiring of "
                  "gadgets/curve.rs) run by the level-scheduled executor for 4096 circuits",
-    "rcrows": "the seven plonky2_ux range-check gate rows of every mul_nonnative of the ECDSA circuit (1087 instances x 7 rows x 512 signatures, "
-              "703 wires per instance, 3-bit aux limbs: spec unpinned) from the device-resident compact witness",
+    "rcrows": "every plonky2_ux range-check gate row of the ECDSA circuit (9168 range_check_ux_circuit calls per signature: add_many, sub, "
+              "mul_nonnative; 512 signatures, 3-bit aux limbs: row layout unpinned) from the device-resident compact witness",
     "genstream_ecdsa": "the complete verify_secp256k1_message_circuit as a serialized generator stream (30955 generators incl. the plonky2 glue, "
                        "1862 dependency levels) run by the level-scheduled executor for 4096 circuits",
     "lde": "coset LDE (ifft 2^17 -> zero-pad -> coset fft 2^20, rate 8) of 135 wire polynomials: the matrix the gate evaluators read",
@@ -469,19 +469,19 @@ class Bench:
             arr = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in ind])
             inp = ctypes.cast(arr, ctypes.c_void_p)
             _, nn, _ = eng.tape_compact_layout(eng.TAPE_ECDSA)
-            nm = int(lib.p2e_tape_num_mul(eng.TAPE_ECDSA))
-            per, _, _ = eng.tape_mul_range_rows_shape(3)
+            gen_c, cnt_c, bits_c, off_c = eng.tape_range_checks(eng.TAPE_ECDSA, 3)
+            nc, wires = len(gen_c), int(off_c[-1])
             nar = torch.empty((nn, n), dtype=torch.int32, device="cuda")
             ed = torch.empty(n, dtype=torch.int32, device="cuda")
             ed2 = torch.empty(n, dtype=torch.int32, device="cuda")
-            rows = torch.empty((nm * per, n), dtype=torch.int64, device="cuda")
+            rows = torch.empty((wires, n), dtype=torch.int64, device="cuda")
             assert lib.p2e_tape_witness_compact_dev(eng.TAPE_ECDSA, n, inp, n, nar.data_ptr(), None, n, ed.data_ptr(), sp) == 0, eng.last_error()
             torch.cuda.synchronize()
             assert not bool(ed.any())
 
             def step():
-                rc = lib.p2e_tape_mul_range_rows_dev(eng.TAPE_ECDSA, n, inp, n, None, nar.data_ptr(), n, 0, nm, 3, rows.data_ptr(), n,
-                                                     ed2.data_ptr(), sp)
+                rc = lib.p2e_tape_range_check_rows_dev(eng.TAPE_ECDSA, n, inp, n, None, nar.data_ptr(), n, 0, nc, 3, rows.data_ptr(), n,
+                                                       ed2.data_ptr(), sp)
                 assert rc == 0, eng.last_error()
             hin = [self.pinned(a) for a in ins]
             he = torch.empty(n, dtype=torch.int32).pin_memory()
@@ -495,9 +495,9 @@ class Bench:
                 step()
                 he.copy_(ed2, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
-            # per instance: 703 wires written (u64) + 5 x 9 + 17 u32 values read
-            return dict(step=step, step_e2e=step_e2e, units=7 * nm * n, h2d=5 * 9 * 8 * n, d2h=4 * n,
-                        alg_bytes=(per * 8 + (5 * 9 + 17) * 4) * nm * n, kernel="k_tape_mul_range_rows", launches=1, err=ed2,
+            # every wire written once (u64), every input read once (u32 in the compact witness)
+            return dict(step=step, step_e2e=step_e2e, units=nc * n, h2d=5 * 9 * 8 * n, d2h=4 * n,
+                        alg_bytes=(wires * 8 + int(cnt_c.sum()) * 4) * n, kernel="k_tape_range_check_rows", launches=1, err=ed2,
                         dtype="u32 / u64 (int)", keep=(ind, nar, ed, rows, hin, he, arr))
         if wl in UX_WORKLOADS:
             gate, bits, lb, count, na, kname = UX_WORKLOADS[wl]

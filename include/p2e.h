@@ -185,27 +185,33 @@ int p2e_eval_check_sum(size_t n_rows, const uint64_t* wires, uint64_t* out);
 size_t p2e_tape_slots(int tape);
 int p2e_tape_inputs(int tape);
 size_t p2e_tape_layout(int tape, uint32_t* kinds, uint32_t* offsets);
-/* The plonky2_ux rows UNDER the in-tree generators, first kind: every mul_nonnative instance adds seven
- * range_check_ux_circuit gate rows (gadgets/nonnative.rs:453-460): x, y, r, q, r again -- one gate input per 29-bit limb
- * the target has -- then b[0..8] and b[8..16] of its CheckSum row as 34-bit inputs.  The call list and its inputs are
- * in-tree (pinned); the gate-row layout is the restated plonky2_ux one (inputs first, then ceil(bits / limb_bits) aux
- * limbs of limb_bits bits per input: DESIGN.md section 9, PARITY UNPINNED -- limb_bits is an argument).
- *   p2e_tape_num_mul:  mul_nonnative instances of the tape, gadget order (ECDSA: 1 087).
- *   p2e_tape_mul_info: limbs of the two factors (a constant's leading zero limbs are dropped, biguint.rs:165-175), the
- *                      first slot of the instance's MulNonnative tuple, the modulus.
- *   p2e_tape_mul_range_rows_shape: wires reserved per instance (5 calls x 9 (1 + a29) + 2 calls x 8 (1 + a34); 703 for
- *                      limb_bits = 3), the wire offset and width of each of the seven calls inside that block.
- *   p2e_tape_mul_range_rows_dev: rows[((j - j0) * wires_per_mul + call_offset + w) * rs + i] for instances [j0, j1) of
- *                      every signature i, read from the finished device witness -- the plain u64 matrix (witness) OR
- *                      the compact narrow matrix (narrow), stride ws -- and the tape's inputs.  A factor with fewer than 9
- *                      limbs fills count (1 + a29) wires, the rest of its block is zero.  err[i]: P2E_ERR_LIMB_RANGE when
- *                      a value does not fit (the gate would be unsatisfiable). */
+/* The plonky2_ux rows UNDER the in-tree generators: range checks.  Every range_check_ux_circuit call of the crate sits in
+ * gadgets/nonnative.rs and each is ONE gate row: add_many_nonnative (:330-331: the sum's limbs; the overflow as a single
+ * input), sub_nonnative (:373: the difference's limbs), mul_nonnative (:454-460: x, y, r, q, r again -- one 29-bit input
+ * per limb the target has -- then b[0..8] and b[8..16] of its CheckSum row as 34-bit inputs).  The call list and its
+ * inputs are in-tree (pinned); the gate-row layout is the restated plonky2_ux one (inputs first, then
+ * ceil(bits / limb_bits) aux limbs of limb_bits bits per input: DESIGN.md section 9, PARITY UNPINNED -- limb_bits is an
+ * argument).
+ *   p2e_tape_num_mul / p2e_tape_mul_info: the mul_nonnative instances of a tape in gadget order (ECDSA: 1 087): limbs of
+ *       the two factors (a constant's leading zero limbs are dropped, biguint.rs:165-175), first slot of the MulNonnative
+ *       tuple, modulus.
+ *   p2e_tape_num_range_checks: range_check_ux_circuit calls of the tape, gadget order (ECDSA: 9 168 per signature).
+ *   p2e_tape_range_check_info: for calls [first, first + count): index of the generator that makes the call (into
+ *       p2e_tape_layout), number of inputs, bits per input.
+ *   p2e_tape_range_check_layout: wire_offsets[c] = first wire of call c's row when the rows of all calls are laid end to
+ *       end ([num + 1] entries; inputs (1 + ceil(bits / limb_bits)) wires per call).
+ *   p2e_tape_range_check_rows_dev: rows[(wire_offsets[c] - wire_offsets[c0] + w) * rs + i] for calls [c0, c1) of every
+ *       signature i, read from the finished device witness -- the plain u64 matrix (witness) OR the compact narrow matrix
+ *       (narrow), stride ws -- and the tape's inputs.  err[i]: P2E_ERR_LIMB_RANGE when a value does not fit its aux limbs
+ *       (the row is unsatisfiable).  At most 65 535 calls per launch. */
 int p2e_tape_num_mul(int tape);
 int p2e_tape_mul_info(int tape, int j, int* x_limbs, int* y_limbs, uint32_t* out_slot, int* modulus);
-int p2e_tape_mul_range_rows_shape(int limb_bits, int* wires_per_mul, int* call_offsets, int* call_wires);
-int p2e_tape_mul_range_rows_dev(int tape, size_t n, const uint64_t* const* inputs, size_t is, const uint64_t* witness,
-                                const uint32_t* narrow, size_t ws, int j0, int j1, int limb_bits, uint64_t* rows, size_t rs,
-                                uint32_t* err, void* stream);
+int p2e_tape_num_range_checks(int tape);
+int p2e_tape_range_check_info(int tape, int first, int count, int32_t* generator, int32_t* inputs, int32_t* bits);
+int p2e_tape_range_check_layout(int tape, int limb_bits, uint64_t* wire_offsets);
+int p2e_tape_range_check_rows_dev(int tape, size_t n, const uint64_t* const* inputs, size_t is, const uint64_t* witness,
+                                  const uint32_t* narrow, size_t ws, int c0, int c1, int limb_bits, uint64_t* rows, size_t rs,
+                                  uint32_t* err, void* stream);
 int p2e_tape_witness_dev(int tape, size_t n, const uint64_t* const* inputs, size_t in_stride,
                          uint64_t* out, size_t out_stride, uint32_t* err, void* stream);
 int p2e_tape_witness(int tape, size_t n, const uint64_t* const* inputs, uint64_t* out, uint32_t* err);

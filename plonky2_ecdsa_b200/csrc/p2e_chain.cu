@@ -955,67 +955,65 @@ __global__ void __launch_bounds__(128, P2E_EXPAND_MINB) k_chain_expand(ChainArgs
 }
 
 // ------------------------------------------------------------------------------------------
-// The plonky2_ux range-check rows of mul_nonnative (nonnative.rs:453-460): every instance adds seven
-// range_check_ux_circuit gate rows -- x, y, r, q, r again (29-bit limbs, as many as the target has) and b[0..8], b[8..16]
-// (34-bit).  One thread per (signature, instance, call): reads the values from the finished witness (either device
-// format) and writes the gate row of the restated spec (p2e_ux.cu: inputs first, then n_aux aux limbs of `lb` bits per
-// input; DESIGN.md section 9, PARITY UNPINNED like every plonky2_ux row).  A value that does not fit sets ERR_LIMB_RANGE.
-struct MulRowsArgs {
-  int j0, lb, a29, a34;          // first instance, aux-limb width, aux limbs per 29- / 34-bit input
-  int w29, w34, per_mul;         // wires reserved per call (9 (1 + a29), 8 (1 + a34)) and per instance
+// The plonky2_ux range-check rows under the in-tree generators.  Every range_check_ux_circuit call of the crate sits in
+// gadgets/nonnative.rs: add_many_nonnative (:330-331: the sum's limbs, then the overflow as one input), sub_nonnative
+// (:373: the difference's limbs) and mul_nonnative (:454-460: x, y, r, q, r again -- 29-bit inputs, as many as the target
+// has limbs -- then b[0..8], b[8..16] of the CheckSum row as 34-bit inputs).  Each call is ONE gate row.  The call list
+// follows from the tape (generator list + Tape::muls); one thread per (signature, call) reads the values from the
+// finished witness (either device format) and writes the gate row of the restated spec (p2e_ux.cu: inputs first, then
+// ceil(bits / lb) aux limbs of lb bits per input; DESIGN.md section 9, PARITY UNPINNED like every plonky2_ux row).
+enum RcKind : uint8_t { RC_REF = 0, RC_SLOTS = 1, RC_CARRIES = 2 };
+struct RcCall {
+  Ref r;               // RC_REF: a mul factor
+  u32 slot;            // RC_SLOTS: first witness slot; RC_CARRIES: first carry slot of the CheckSum tuple (plain numbering)
+  u32 tuple;           // RC_CARRIES: first slot of the MulNonnative tuple (compact rows: low words at +18, tops at +34)
+  uint8_t kind, count, bits, first;   // first: index of the first carry (0 or 8)
+};
+struct RcArgs {
+  const RcCall* calls;
+  const u64* wire_off;  // [calls + 1] wire offset of each call's row for this aux-limb width
+  int c0, lb;
+  u64 base;             // wire_off[c0]
   u64* rows;
   size_t rs;
 };
-__device__ __forceinline__ u64 load_mul_factor_limb(const ChainArgs& A, const Ref& r, u64 bm, int l, size_t i) {
-  if (l >= r.nl) return 0;
-  if (r.space == SP_CPOINT) return A.t.const_points[r.off + l];
-  return load_wire(A, r.space, r.off + l, i) * bm;
-}
-__global__ void __launch_bounds__(128) k_tape_mul_range_rows(ChainArgs A, MulRowsArgs M) {
+__global__ void __launch_bounds__(128) k_tape_range_check_rows(ChainArgs A, RcArgs M) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= A.n) return;
-  const int jj = blockIdx.y / 7, c = blockIdx.y % 7;
-  const MulRec m = A.t.muls[M.j0 + jj];
-  const bool wide = c >= 5;
-  const int n_aux = wide ? M.a34 : M.a29;
-  int count = wide ? 8 : NL;
-  u64* row = M.rows + ((size_t)jj * M.per_mul + (wide ? 5 * M.w29 + (c - 5) * M.w34 : c * M.w29)) * M.rs + i;
-  const int width = wide ? M.w34 : M.w29;
+  const int c = M.c0 + blockIdx.y;
+  const RcCall call = M.calls[c];
+  const int count = call.count, n_aux = (call.bits + M.lb - 1) / M.lb;
+  u64* row = M.rows + (size_t)(M.wire_off[c] - M.base) * M.rs + i;
   u64 v[NL];
-  if (c < 2) {
-    const Ref& r = c == 0 ? m.x : m.y;
-    count = r.nl;
+#pragma unroll
+  for (int l = 0; l < NL; l++) v[l] = 0;
+  if (call.kind == RC_REF) {
+    const Ref& r = call.r;
     u64 bm = 1;
     if (r.bspace != SP_NONE) bm = (load_wire(A, r.bspace, r.boff, i) ^ (u64)r.binv) & 1;
-    for (int l = 0; l < NL; l++) v[l] = load_mul_factor_limb(A, r, bm, l, i);
-  } else if (!wide) {
-    const u32 base = m.out + (c == 3 ? 9u : 0u);                      // r, q, r
-    for (int l = 0; l < NL; l++) v[l] = load_wire(A, SP_OUT, base + l, i);
+    for (int l = 0; l < count; l++) v[l] = r.space == SP_CPOINT ? (u64)A.t.const_points[r.off + l] : load_wire(A, r.space, r.off + l, i) * bm;
+  } else if (call.kind == RC_SLOTS) {
+    for (int l = 0; l < count; l++) v[l] = load_wire(A, SP_OUT, call.slot + l, i);
+  } else if (A.fmt == FMT_PLAIN) {
+    for (int l = 0; l < count; l++) v[l] = A.out[(size_t)(call.slot + l) * A.os + i];
   } else {
-    // CheckSum carries b[8 (c - 5) ..]: plain slots out + 35 + l; compact: low words in the 16 rows after q, tops packed
-    const int l0 = 8 * (c - 5);
-    if (A.fmt == FMT_PLAIN) {
-      for (int l = 0; l < 8; l++) v[l] = A.out[(size_t)(m.out + 35 + l0 + l) * A.os + i];
-    } else {
-      const u32 r0 = A.t.cmap[m.out];
-      const u32 tops = A.nar[(size_t)(r0 + 34) * A.os + i];
-      for (int l = 0; l < 8; l++) v[l] = (u64)A.nar[(size_t)(r0 + 18 + l0 + l) * A.os + i] | ((u64)((tops >> (2 * (l0 + l))) & 3u) << 32);
-    }
-    v[8] = 0;
+    // compact: 16 low words after r and q, then one word with the 16 two-bit tops
+    const u32 r0 = A.t.cmap[call.tuple];
+    const u32 tops = A.nar[(size_t)(r0 + 34) * A.os + i];
+    for (int l = 0; l < count; l++)
+      v[l] = (u64)A.nar[(size_t)(r0 + 18 + call.first + l) * A.os + i] | ((u64)((tops >> (2 * (call.first + l))) & 3u) << 32);
   }
   u32 e = 0;
   const u64 mask = (1ull << M.lb) - 1;
-  int wdone = 0;
-  for (int u = 0; u < count; u++) row[(size_t)(wdone++) * M.rs] = v[u];
+  for (int u = 0; u < count; u++) row[(size_t)u * M.rs] = v[u];
   for (int u = 0; u < count; u++) {
     u64 t = v[u];
     for (int a = 0; a < n_aux; a++) {
-      row[(size_t)(wdone++) * M.rs] = t & mask;
+      row[(size_t)(count + n_aux * u + a) * M.rs] = t & mask;
       t >>= M.lb;
     }
-    if (t) e |= ERR_LIMB_RANGE;
+    if (t) e |= ERR_LIMB_RANGE;                      // does not fit its aux limbs: the row is unsatisfiable
   }
-  for (; wdone < width; wdone++) row[(size_t)wdone * M.rs] = 0;     // a target with fewer limbs: a narrower gate, rest unused
   if (e) atomicOr(&A.err[i], e);
 }
 
@@ -1075,6 +1073,10 @@ struct TapeOnDevice {
   void* blob = nullptr;
   size_t n_slots = 0;
   u32 n_narrow = 0, n_wide = 0;
+  // range_check_ux_circuit calls (built on first use): device call list, per aux-limb width the wire offsets
+  RcCall* rc_calls = nullptr;
+  int n_rc = 0;
+  std::map<int, u64*> rc_off;
 };
 
 // One scratch arena per launching stream, so independent batches enqueued on different streams
@@ -1286,8 +1288,11 @@ static int get_arena(ChainState& S, cudaStream_t st, size_t bytes, Arena** out) 
 void chain_release_device(Context& c) {
   if (!c.chain) return;
   ChainState* S = (ChainState*)c.chain;
-  for (auto& kv : S->tapes)
+  for (auto& kv : S->tapes) {
     if (kv.second.ready && kv.second.blob) cudaFree(kv.second.blob);
+    if (kv.second.rc_calls) cudaFree(kv.second.rc_calls);
+    for (auto& o : kv.second.rc_off) cudaFree(o.second);
+  }
   for (auto& a : S->arenas) arena_free(a);
   for (auto e : S->events) cudaEventDestroy(e);
   for (auto& t : S->trace) cudaEventDestroy(t.ev);
@@ -1476,6 +1481,43 @@ static int run_tape(int which, const Tape& t, size_t n, const uint64_t* const* i
   return 0;
 }
 
+// the range_check_ux_circuit calls of a tape in gadget order (see k_tape_range_check_rows)
+static void range_check_calls(const Tape& t, std::vector<RcCall>& calls, std::vector<int>* gens) {
+  size_t mi = 0;
+  auto push = [&](uint8_t kind, const Ref& r, u32 slot, u32 tuple, int count, int bits, int first, int g) {
+    RcCall c;
+    c.r = r; c.slot = slot; c.tuple = tuple; c.kind = kind; c.count = (uint8_t)count; c.bits = (uint8_t)bits; c.first = (uint8_t)first;
+    calls.push_back(c);
+    if (gens) gens->push_back(g);
+  };
+  Ref none;
+  memset(&none, 0, sizeof(none));
+  for (size_t g = 0; g < t.gen_kind.size(); g++) {
+    const u32 s = t.gen_off[g];
+    switch (t.gen_kind[g]) {
+      case G_ADDMANY:                                             // nonnative.rs:330-331
+        push(RC_SLOTS, none, s, 0, NL, LB, 0, (int)g);
+        push(RC_SLOTS, none, s + 9, 0, 1, LB, 0, (int)g);
+        break;
+      case G_SUB:                                                 // nonnative.rs:373
+        push(RC_SLOTS, none, s, 0, NL, LB, 0, (int)g);
+        break;
+      case G_MUL: {                                               // nonnative.rs:454-460
+        const MulRec& m = t.muls[mi++];
+        push(RC_REF, m.x, 0, 0, m.x.nl, LB, 0, (int)g);
+        push(RC_REF, m.y, 0, 0, m.y.nl, LB, 0, (int)g);
+        push(RC_SLOTS, none, s, 0, NL, LB, 0, (int)g);            // r
+        push(RC_SLOTS, none, s + 9, 0, NL, LB, 0, (int)g);        // q
+        push(RC_SLOTS, none, s, 0, NL, LB, 0, (int)g);            // r again
+        push(RC_CARRIES, none, s + 35, s, 8, 34, 0, (int)g);      // b[0..8]
+        push(RC_CARRIES, none, s + 43, s, 8, 34, 8, (int)g);      // b[8..16]
+        break;
+      }
+      default: break;
+    }
+  }
+}
+
 static size_t tape_layout(const Tape& t, uint32_t* kinds, uint32_t* offs) {
   if (kinds && offs) {
     for (size_t i = 0; i < t.gen_kind.size(); i++) {
@@ -1580,65 +1622,105 @@ int p2e_tape_mul_info(int tape, int j, int* x_limbs, int* y_limbs, uint32_t* out
   return 0;
 }
 
-int p2e_tape_mul_range_rows_shape(int limb_bits, int* wires_per_mul, int* call_offsets, int* call_wires) {
-  if (limb_bits < 1 || limb_bits > 8) return set_error_msg("tape_mul_range_rows: limb_bits must be 1 .. 8");
-  const int a29 = (LB + limb_bits - 1) / limb_bits, a34 = (34 + limb_bits - 1) / limb_bits;
-  const int w29 = NL * (1 + a29), w34 = 8 * (1 + a34);
-  if (wires_per_mul) *wires_per_mul = 5 * w29 + 2 * w34;
-  for (int c = 0; c < 7; c++) {
-    if (call_offsets) call_offsets[c] = c < 5 ? c * w29 : 5 * w29 + (c - 5) * w34;
-    if (call_wires) call_wires[c] = c < 5 ? w29 : w34;
+int p2e_tape_num_range_checks(int tape) {
+  if (bad_tape(tape)) return -1;
+  std::vector<RcCall> calls;
+  range_check_calls(get_tape(tape), calls, nullptr);
+  return (int)calls.size();
+}
+
+int p2e_tape_range_check_info(int tape, int first, int count, int32_t* generator, int32_t* inputs, int32_t* bits) {
+  if (bad_tape(tape)) return -1;
+  std::vector<RcCall> calls;
+  std::vector<int> gens;
+  range_check_calls(get_tape(tape), calls, &gens);
+  if (first < 0 || count < 0 || (size_t)first + count > calls.size()) return set_error_msg("tape_range_check_info: call range out of bounds");
+  for (int k = 0; k < count; k++) {
+    if (generator) generator[k] = gens[first + k];
+    if (inputs) inputs[k] = calls[first + k].count;
+    if (bits) bits[k] = calls[first + k].bits;
   }
   return 0;
 }
 
-int p2e_tape_mul_range_rows_dev(int tape, size_t n, const uint64_t* const* inputs, size_t is, const uint64_t* witness,
-                                const uint32_t* narrow, size_t ws, int j0, int j1, int limb_bits, uint64_t* rows, size_t rs,
-                                uint32_t* err, void* stream) {
+int p2e_tape_range_check_layout(int tape, int limb_bits, uint64_t* wire_offsets) {
+  if (bad_tape(tape)) return -1;
+  if (limb_bits < 1 || limb_bits > 8) return set_error_msg("tape_range_check: limb_bits must be 1 .. 8");
+  std::vector<RcCall> calls;
+  range_check_calls(get_tape(tape), calls, nullptr);
+  u64 off = 0;
+  for (size_t c = 0; c < calls.size(); c++) {
+    if (wire_offsets) wire_offsets[c] = off;
+    off += (u64)calls[c].count * (1 + (calls[c].bits + limb_bits - 1) / limb_bits);
+  }
+  if (wire_offsets) wire_offsets[calls.size()] = off;
+  return 0;
+}
+
+int p2e_tape_range_check_rows_dev(int tape, size_t n, const uint64_t* const* inputs, size_t is, const uint64_t* witness,
+                                  const uint32_t* narrow, size_t ws, int c0, int c1, int limb_bits, uint64_t* rows, size_t rs,
+                                  uint32_t* err, void* stream) {
   if (bad_tape(tape)) return -1;
   int rc = ensure_ready();
   if (rc) return rc;
   const Tape& t = get_tape(tape);
-  if (j0 < 0 || j1 < j0 || j1 > (int)t.muls.size()) return set_error_msg("tape_mul_range_rows: instance range out of bounds");
-  if (n == 0 || j0 == j1) return 0;
-  if ((witness == nullptr) == (narrow == nullptr)) return set_error_msg("tape_mul_range_rows: give the plain witness OR the compact narrow matrix");
-  if (!rows || !err) return set_error_msg("tape_mul_range_rows: NULL output");
+  if (limb_bits < 1 || limb_bits > 8) return set_error_msg("tape_range_check: limb_bits must be 1 .. 8");
+  if ((witness == nullptr) == (narrow == nullptr)) return set_error_msg("tape_range_check_rows: give the plain witness OR the compact narrow matrix");
+  if (n && (!rows || !err)) return set_error_msg("tape_range_check_rows: NULL output");
   if (is < n || ws < n || rs < n) return set_error_msg("stride < n");
-  if ((size_t)(j1 - j0) * 7 > 65535) return set_error_msg("tape_mul_range_rows: at most 9362 instances per call");
-  int per_mul = 0;
-  if ((rc = p2e_tape_mul_range_rows_shape(limb_bits, &per_mul, nullptr, nullptr))) return rc;
+  if (t.n_inputs && !inputs) return set_error_msg("tape_range_check_rows: NULL inputs");
   ChainState& S = chain_state();
   TapeOnDevice* o;
+  u64* d_off = nullptr;
+  u64 base = 0;
   {
     std::lock_guard<std::mutex> lock(S.mu);
     o = &S.tapes[tape];
     if ((rc = upload_tape(t, *o))) return rc;
+    if (!o->rc_calls) {
+      std::vector<RcCall> calls;
+      range_check_calls(t, calls, nullptr);
+      o->n_rc = (int)calls.size();
+      P2E_CUDA(cudaMalloc((void**)&o->rc_calls, (calls.size() + 1) * sizeof(RcCall)));
+      P2E_CUDA(cudaMemcpy(o->rc_calls, calls.data(), calls.size() * sizeof(RcCall), cudaMemcpyHostToDevice));
+    }
+    if (c0 < 0 || c1 < c0 || c1 > o->n_rc) return set_error_msg("tape_range_check_rows: call range out of bounds");
+    if (c1 - c0 > 65535) return set_error_msg("tape_range_check_rows: at most 65535 calls per launch");
+    std::vector<u64> off((size_t)o->n_rc + 1);
+    if ((rc = p2e_tape_range_check_layout(tape, limb_bits, off.data()))) return rc;
+    base = off[c0];
+    auto it = o->rc_off.find(limb_bits);
+    if (it == o->rc_off.end()) {
+      u64* p = nullptr;
+      P2E_CUDA(cudaMalloc((void**)&p, off.size() * 8));
+      P2E_CUDA(cudaMemcpy(p, off.data(), off.size() * 8, cudaMemcpyHostToDevice));
+      it = o->rc_off.emplace(limb_bits, p).first;
+    }
+    d_off = it->second;
   }
+  if (n == 0 || c0 == c1) return 0;
   ChainArgs A;
   memset(&A, 0, sizeof(A));
   A.t = o->d;
   A.n = n;
   A.is = is;
-  for (int k = 0; k < (int)t.n_inputs && k < MAX_TAPE_INPUTS; k++) A.in[k] = inputs ? inputs[k] : nullptr;
-  if (t.n_inputs && !inputs) return set_error_msg("tape_mul_range_rows: NULL inputs");
+  for (int k = 0; k < (int)t.n_inputs && k < MAX_TAPE_INPUTS; k++) A.in[k] = inputs[k];
   A.fmt = witness ? FMT_PLAIN : FMT_COMPACT;
   A.out = const_cast<u64*>(witness);
   A.nar = const_cast<u32*>(narrow);
   A.os = ws;
   A.err = err;
-  MulRowsArgs M;
-  M.j0 = j0;
+  RcArgs M;
+  M.calls = o->rc_calls;
+  M.wire_off = d_off;
+  M.c0 = c0;
   M.lb = limb_bits;
-  M.a29 = (LB + limb_bits - 1) / limb_bits;
-  M.a34 = (34 + limb_bits - 1) / limb_bits;
-  M.w29 = NL * (1 + M.a29);
-  M.w34 = 8 * (1 + M.a34);
-  M.per_mul = per_mul;
+  M.base = base;
   M.rows = rows;
   M.rs = rs;
   cudaStream_t st = pick_stream(stream);
   P2E_CUDA(cudaMemsetAsync(err, 0, n * sizeof(uint32_t), st));
-  k_tape_mul_range_rows<<<dim3((unsigned)((n + 127) / 128), (unsigned)((j1 - j0) * 7)), 128, 0, st>>>(A, M);
+  k_tape_range_check_rows<<<dim3((unsigned)((n + 127) / 128), (unsigned)(c1 - c0)), 128, 0, st>>>(A, M);
   P2E_CUDA(cudaGetLastError());
   return 0;
 }

@@ -98,8 +98,10 @@ SIGNATURES = {
     "p2e_tape_compact_layout": (_sz, [_int, _vp, _vp, _vp]),
     "p2e_tape_num_mul": (_int, [_int]),
     "p2e_tape_mul_info": (_int, [_int, _int, _vp, _vp, _vp, _vp]),
-    "p2e_tape_mul_range_rows_shape": (_int, [_int, _vp, _vp, _vp]),
-    "p2e_tape_mul_range_rows_dev": (_int, [_int, _sz, _vp, _sz, _vp, _vp, _sz, _int, _int, _int, _vp, _sz, _vp, _vp]),
+    "p2e_tape_num_range_checks": (_int, [_int]),
+    "p2e_tape_range_check_info": (_int, [_int, _int, _int, _vp, _vp, _vp]),
+    "p2e_tape_range_check_layout": (_int, [_int, _int, _vp]),
+    "p2e_tape_range_check_rows_dev": (_int, [_int, _sz, _vp, _sz, _vp, _vp, _sz, _int, _int, _int, _vp, _sz, _vp, _vp]),
     "p2e_tape_witness_compact": (_int, [_int, _sz, _vp, _vp, _vp, _vp]),
     "p2e_tape_witness_compact_dev": (_int, [_int, _sz, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
     "p2e_ecdsa_witness_compact_dev": (_int, [_sz, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
@@ -588,31 +590,35 @@ class Engine:
             out.append((xl.value, yl.value, sl.value, md.value))
         return out
 
-    def tape_mul_range_rows_shape(self, limb_bits=3):
-        """-> (wires per instance, [7] wire offsets of the calls x, y, r, q, r, b[0..8], b[8..16], [7] wires per call)."""
-        per = ctypes.c_int(0)
-        offs = (ctypes.c_int * 7)()
-        wid = (ctypes.c_int * 7)()
-        self._check(self.lib.p2e_tape_mul_range_rows_shape(limb_bits, ctypes.addressof(per), ctypes.addressof(offs), ctypes.addressof(wid)))
-        return per.value, list(offs), list(wid)
+    def tape_range_checks(self, tape, limb_bits=3):
+        """Every range_check_ux_circuit call of the tape, gadget order -> (generator index [c], inputs [c], bits [c],
+        wire offsets [c + 1]) as numpy arrays (p2e_tape_range_check_info / _layout)."""
+        nc = self.lib.p2e_tape_num_range_checks(tape)
+        gen = np.empty(nc, dtype=np.int32)
+        cnt = np.empty(nc, dtype=np.int32)
+        bits = np.empty(nc, dtype=np.int32)
+        off = np.empty(nc + 1, dtype=np.uint64)
+        self._check(self.lib.p2e_tape_range_check_info(tape, 0, nc, _ptr(gen), _ptr(cnt), _ptr(bits)))
+        self._check(self.lib.p2e_tape_range_check_layout(tape, limb_bits, _ptr(off)))
+        return gen, cnt, bits, off
 
-    def tape_mul_range_rows(self, tape, inputs, witness, j0, j1, limb_bits=3, compact=False):
-        """The seven range-check gate rows of mul_nonnative instances [j0, j1) for every signature, from a finished witness
-        (plain [slots][n] uint64, or with compact=True the narrow [rows][n] uint32 matrix of the compact format).
-        Host arrays in, (rows [(j1 - j0) * wires_per_mul][n] uint64, err [n]) out -- through device memory (torch)."""
+    def tape_range_check_rows(self, tape, inputs, witness, c0, c1, limb_bits=3, compact=False):
+        """The gate rows of range_check_ux_circuit calls [c0, c1) for every signature, from a finished witness (plain
+        [slots][n] uint64, or with compact=True the narrow [rows][n] uint32 matrix of the compact format).  Host arrays in,
+        (rows [wires of the calls][n] uint64, err [n]) out -- through device memory (torch)."""
         import torch
         ins = [torch.from_numpy(_host_u64(a, 9).view(np.int64)).cuda() for a in inputs]
         n = int(witness.shape[1])
         wd = torch.from_numpy(np.ascontiguousarray(witness).view(np.int32 if compact else np.int64)).cuda()
-        per, _, _ = self.tape_mul_range_rows_shape(limb_bits)
-        rows = torch.empty(((j1 - j0) * per, n), dtype=torch.int64, device="cuda")
+        off = self.tape_range_checks(tape, limb_bits)[3]
+        rows = torch.empty((max(int(off[c1] - off[c0]), 1), n), dtype=torch.int64, device="cuda")
         err = torch.empty(n, dtype=torch.int32, device="cuda")
         arr = (ctypes.c_void_p * max(len(ins), 1))(*[t.data_ptr() for t in ins])
-        self._check(self.lib.p2e_tape_mul_range_rows_dev(tape, n, ctypes.cast(arr, ctypes.c_void_p), n, None if compact else wd.data_ptr(),
-                                                         wd.data_ptr() if compact else None, n, j0, j1, limb_bits, rows.data_ptr(), n,
-                                                         err.data_ptr(), None))
+        self._check(self.lib.p2e_tape_range_check_rows_dev(tape, n, ctypes.cast(arr, ctypes.c_void_p), n, None if compact else wd.data_ptr(),
+                                                           wd.data_ptr() if compact else None, n, c0, c1, limb_bits, rows.data_ptr(), n,
+                                                           err.data_ptr(), None))
         self.synchronize()
-        return rows.cpu().numpy().view(np.uint64), err.cpu().numpy().view(np.uint32)
+        return rows.cpu().numpy().view(np.uint64)[: int(off[c1] - off[c0])], err.cpu().numpy().view(np.uint32)
 
     def tape_compact_layout(self, tape):
         """-> (map [slots] uint32, narrow_rows, wide_rows).  map[slot] = (1 << 31 | wide row) for a full field

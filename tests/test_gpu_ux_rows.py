@@ -1,7 +1,7 @@
-"""GPU tier: the plonky2_ux range-check rows UNDER the in-tree generators -- the seven range_check_ux_circuit rows every
-mul_nonnative adds (gadgets/nonnative.rs:453-460) -- produced from the finished device witness for every mul_nonnative
-instance of the ECDSA circuit, against the restated gate spec (oracle/ux_spec.py, PARITY UNPINNED for the row layout; the
-call list and its inputs are the reference's own)."""
+"""GPU tier: the plonky2_ux range-check rows UNDER the in-tree generators.  Every range_check_ux_circuit call of the crate is
+in gadgets/nonnative.rs (add_many :330-331, sub :373, mul :454-460) and each is one gate row; the engine produces them from
+the finished device witness for every call of the ECDSA circuit.  Checked against the oracle's call graph (pinned: the call
+list and its inputs are the reference's own) and the restated gate spec (oracle/ux_spec.py: the row layout is PARITY UNPINNED)."""
 import numpy as np
 import pytest
 
@@ -12,26 +12,29 @@ from plonky2_ecdsa_b200 import workload as W
 pytestmark = pytest.mark.gpu
 
 
-def _expected_rows(wb, limb_bits):
-    """[instances][7] -> (wire list, count) from the oracle's witness builder."""
-    muls = [v for k, v in wb.tape if k == S.K_MUL]
-    sums = [v for k, v in wb.tape if k == S.K_CHECKSUM]
-    assert len(muls) == len(sums) == len(wb.mul_ops)
-    out = []
-    for (x, y), mt, b in zip(wb.mul_ops, muls, sums):
-        r, q = mt[:9], mt[9:18]
-        calls = [(x, 29), (y, 29), (r, 29), (q, 29), (r, 29), (b[:8], 34), (b[8:], 34)]
-        rows = []
-        for limbs, bits in calls:
-            row, err = UX.UXRangeCheckGate(bits, limb_bits, len(limbs)).generate(limbs)
-            assert err == 0
-            rows.append(row)
-        out.append(rows)
-    return out
+def expected_calls(wb):
+    """The range_check_ux_circuit calls of one circuit instance in gadget order: (generator index, limbs, bits)."""
+    calls = []
+    mi = 0
+    for g, (kind, vals) in enumerate(wb.tape):
+        if kind == S.K_ADDMANY:                      # nonnative.rs:330-331
+            calls.append((g, vals[:9], 29))
+            calls.append((g, vals[9:10], 29))
+        elif kind == S.K_SUB:                        # nonnative.rs:373
+            calls.append((g, vals[:9], 29))
+        elif kind == S.K_MUL:                        # nonnative.rs:454-460
+            x, y = wb.mul_ops[mi]
+            mi += 1
+            r, q = vals[:9], vals[9:18]
+            b = wb.tape[g + 1][1]
+            assert wb.tape[g + 1][0] == S.K_CHECKSUM and len(b) == 16
+            calls += [(g, x, 29), (g, y, 29), (g, r, 29), (g, q, 29), (g, r, 29), (g, b[:8], 34), (g, b[8:], 34)]
+    assert mi == len(wb.mul_ops)
+    return calls
 
 
 @pytest.mark.parametrize("limb_bits", [3, 2])
-def test_mul_range_check_rows_of_the_ecdsa_circuit(engine, limb_bits):
+def test_range_check_rows_of_the_ecdsa_circuit(engine, limb_bits):
     n = 4
     wl = W.ecdsa_workload(n, seed=97)
     ins = [wl[k] for k in ("msg", "r", "s", "pkx", "pky")]
@@ -39,43 +42,67 @@ def test_mul_range_check_rows_of_the_ecdsa_circuit(engine, limb_bits):
     assert not err.any()
     narrow, _, err2 = engine.tape_witness_compact(engine.TAPE_ECDSA, ins, derive_check_sum=True)
     assert not err2.any()
-    info = engine.tape_mul_info(engine.TAPE_ECDSA)
-    per, offs, wid = engine.tape_mul_range_rows_shape(limb_bits)
-    a29, a34 = -(-29 // limb_bits), -(-34 // limb_bits)
-    assert per == 5 * 9 * (1 + a29) + 2 * 8 * (1 + a34) and wid == [9 * (1 + a29)] * 5 + [8 * (1 + a34)] * 2
-    nm = len(info)
-    rows_p, e_p = engine.tape_mul_range_rows(engine.TAPE_ECDSA, ins, wit, 0, nm, limb_bits)
-    rows_c, e_c = engine.tape_mul_range_rows(engine.TAPE_ECDSA, ins, narrow, 0, nm, limb_bits, compact=True)
+    gen, cnt, bits, off = engine.tape_range_checks(engine.TAPE_ECDSA, limb_bits)
+    nc = len(gen)
+    rows_p, e_p = engine.tape_range_check_rows(engine.TAPE_ECDSA, ins, wit, 0, nc, limb_bits)
+    rows_c, e_c = engine.tape_range_check_rows(engine.TAPE_ECDSA, ins, narrow, 0, nc, limb_bits, compact=True)
     assert not e_p.any() and not e_c.any()
-    assert np.array_equal(rows_p, rows_c), "plain and compact witness give different rows"
+    assert rows_p.shape[0] == int(off[nc]) and np.array_equal(rows_p, rows_c), "plain and compact witness give different rows"
     i = wl["ints"]
     for j in range(n):
         wb = S.ecdsa_witness(i["msg"][j], i["r"][j], i["s"][j], (i["pkx"][j], i["pky"][j]))
-        exp = _expected_rows(wb, limb_bits)
-        assert len(exp) == nm
-        for m, rows in enumerate(exp):
-            assert (len(wb.mul_ops[m][0]), len(wb.mul_ops[m][1])) == info[m][:2], f"instance {m}: factor limb counts"
-            for c, row in enumerate(rows):
-                got = rows_p[m * per + offs[c]: m * per + offs[c] + wid[c], j]
-                assert [int(v) for v in got[:len(row)]] == row, f"signature {j} instance {m} call {c}"
-                assert not got[len(row):].any()
+        exp = expected_calls(wb)
+        assert len(exp) == nc == 9168
+        for c, (g, limbs, b) in enumerate(exp):
+            assert (g, len(limbs), b) == (int(gen[c]), int(cnt[c]), int(bits[c])), f"call {c}"
+            row, bad = UX.UXRangeCheckGate(b, limb_bits, len(limbs)).generate(limbs)
+            assert not bad and len(row) == int(off[c + 1] - off[c])
+            got = rows_p[int(off[c]): int(off[c + 1]), j]
+            assert [int(v) for v in got] == row, f"signature {j} call {c} (generator {g})"
 
 
-def test_mul_range_check_rows_sub_range_and_errors(engine):
+def test_range_check_rows_sub_range_and_errors(engine):
     n = 3
     wl = W.ecdsa_workload(n, seed=5)
     ins = [wl[k] for k in ("msg", "r", "s", "pkx", "pky")]
     wit, _ = engine.verify_secp256k1_message_witness(*ins)
-    nm = len(engine.tape_mul_info(engine.TAPE_ECDSA))
-    per, _, _ = engine.tape_mul_range_rows_shape(3)
-    full, _ = engine.tape_mul_range_rows(engine.TAPE_ECDSA, ins, wit, 0, nm)
-    part, _ = engine.tape_mul_range_rows(engine.TAPE_ECDSA, ins, wit, 100, 140)
-    assert np.array_equal(part, full[100 * per: 140 * per])
+    gen, cnt, bits, off = engine.tape_range_checks(engine.TAPE_ECDSA)
+    nc = len(gen)
+    full, _ = engine.tape_range_check_rows(engine.TAPE_ECDSA, ins, wit, 0, nc)
+    part, _ = engine.tape_range_check_rows(engine.TAPE_ECDSA, ins, wit, 1000, 1400)
+    assert np.array_equal(part, full[int(off[1000]): int(off[1400])])
     with pytest.raises(Exception):
-        engine.tape_mul_range_rows(engine.TAPE_ECDSA, ins, wit, 0, nm + 1)
-    # a carry that does not fit 34 + limb padding bits makes its gate row unsatisfiable: flagged
+        engine.tape_range_check_rows(engine.TAPE_ECDSA, ins, wit, 0, nc + 1)
+    # a carry that does not fit its aux limbs makes its gate row unsatisfiable: flagged for that signature only
+    c = int(np.nonzero(bits == 34)[0][10])
+    kinds, offs, _ = engine.ecdsa_tape_layout()
     bad = wit.copy()
-    slot = engine.tape_mul_info(engine.TAPE_ECDSA)[7][2]
-    bad[slot + 35, 1] = np.uint64(1 << 40)
-    _, e = engine.tape_mul_range_rows(engine.TAPE_ECDSA, ins, bad, 7, 8)
+    bad[int(offs[gen[c]]) + 35, 1] = np.uint64(1 << 40)
+    _, e = engine.tape_range_check_rows(engine.TAPE_ECDSA, ins, bad, c, c + 1)
     assert e[1] != 0 and e[0] == 0 and e[2] == 0
+
+
+def test_range_check_rows_of_a_glv_mul_chain(engine):
+    """A second tape (glv_mul: GLV decomposition + msm, gadgets/glv.rs:87-104): factors with 5 limbs and constants."""
+    n = 3
+    ks = [0x1357 << 240 | 12345, S.SECP_N - 2, 77]
+    P = S.pt_mul(7, S.G)
+    k = W.ints_to_limbs(ks)
+    px, py = W.ints_to_limbs([P[0]] * n), W.ints_to_limbs([P[1]] * n)
+    wit, err = engine.glv_mul_witness(k, px, py)
+    assert not err.any()
+    gen, cnt, bits, off = engine.tape_range_checks(engine.TAPE_GLV_MUL)
+    rows, e = engine.tape_range_check_rows(engine.TAPE_GLV_MUL, [k, px, py], wit, 0, len(gen))
+    assert not e.any()
+    for j in range(n):
+        wb = S.WitnessBuilder()
+        wb.glv_mul(wb.constant_affine_point(P), wb.constant_nonnative(ks[j], S.SECP_N))
+        exp = expected_calls(wb)
+        assert len(exp) == len(gen)
+        for c, (g, limbs, b) in enumerate(exp):
+            assert (g, b) == (int(gen[c]), int(bits[c]))
+            # the oracle builds k and P as constants (leading zero limbs dropped), the tape takes 9-limb targets: compare the
+            # limbs the oracle has, the tape's extra ones must be zero
+            row, bad = UX.UXRangeCheckGate(b, 3, int(cnt[c])).generate(list(limbs) + [0] * (int(cnt[c]) - len(limbs)))
+            assert not bad and int(cnt[c]) >= len(limbs)
+            assert [int(v) for v in rows[int(off[c]): int(off[c + 1]), j]] == row, f"scalar {j} call {c}"

@@ -177,7 +177,18 @@ def test_mul_nonnative_instances_of_the_ecdsa_tape():
         assert sl.value == mul_offs[j]
         assert (xl.value, yl.value) == (len(wb.mul_ops[j][0]), len(wb.mul_ops[j][1])), j
     assert lib.p2e_tape_mul_info(0, nm, None, None, None, None) != 0
-    per = ctypes.c_int(0)
-    offs7, wid7 = (ctypes.c_int * 7)(), (ctypes.c_int * 7)()
-    assert lib.p2e_tape_mul_range_rows_shape(3, ctypes.byref(per), offs7, wid7) == 0
-    assert per.value == 703 and list(wid7) == [99] * 5 + [104] * 2 and list(offs7) == [0, 99, 198, 297, 396, 495, 599]
+    # every range_check_ux_circuit call: 2 per add_many, 1 per sub, 7 per mul (nonnative.rs:330-331, 373, 454-460)
+    lib.p2e_tape_num_range_checks.restype = ctypes.c_int
+    nc = lib.p2e_tape_num_range_checks(0)
+    want = sum({S.K_ADDMANY: 2, S.K_SUB: 1, S.K_MUL: 7}.get(int(kd), 0) for kd in kinds)
+    assert nc == want == 9168
+    gen = np.empty(nc, dtype=np.int32)
+    cnt = np.empty(nc, dtype=np.int32)
+    bits = np.empty(nc, dtype=np.int32)
+    assert lib.p2e_tape_range_check_info(0, 0, nc, gen.ctypes.data, cnt.ctypes.data, bits.ctypes.data) == 0
+    off = np.empty(nc + 1, dtype=np.uint64)
+    assert lib.p2e_tape_range_check_layout(0, 3, off.ctypes.data) == 0
+    widths = cnt * (1 + (bits + 2) // 3)
+    assert off[0] == 0 and np.array_equal(np.diff(off.astype(np.int64)), widths)
+    assert set(bits.tolist()) == {29, 34} and (gen[1:] >= gen[:-1]).all()
+    assert lib.p2e_tape_range_check_info(0, 0, nc + 1, None, None, None) != 0
