@@ -677,8 +677,9 @@ class Bench:
         if sample_clocks and self.rank == 0:
             # rank 0 only; created before the warm-up so that nothing forks inside the timed region
             sampler = ClockSampler(self.local_rank)
-        # every stream's scratch arena is allocated on its first batch: warm up at least one batch per stream
-        for _ in range(max(warmup, len(s.get("streams") or []))):
+        # every stream's scratch arena is allocated on its first batch and the library captures a repeated call as a CUDA graph
+        # on its second occurrence: warm up at least two batches per stream (plus one replay)
+        for _ in range(max(warmup, 3 * len(s.get("streams") or []))):
             step()
         self.barrier()
         if sampler is not None:
@@ -746,7 +747,7 @@ class Bench:
             for nm, key, by in (("compact_with_check_sum", "step_compact_wide", (s["narrow_rows"] * 4 + s["wide_rows"] * 8)),
                                 ("plain_u64", "step_plain", s["slots"] * 8)):
                 fn = s[key]
-                for _ in range(8):
+                for _ in range(36):                # 3 per stream (S2 <= 12): arena, graph capture, one replay
                     fn()
                 self.barrier()
                 k2 = max(8, min(steps, 24))

@@ -77,7 +77,7 @@ int p2e_synchronize(void);              /* the current device's library stream *
  * "genstream_graph" (1) executor forms of p2e_genstream_run*; "genstream_walk" (1: streams of 32 levels or more run as ONE launch of the level
  * walker -- a CTA owns 32 circuits and walks every level itself; 2: always; 0: never), "genstream_walk_shape" (0: by batch size; else 100 * warps + circuits per CTA); "ntt_log_tile" (12); "chain_trace" (0) diagnostic timeline; "chain_phases" (63) diagnostic bit mask of the chain kernels to launch
  * (anything else flags every row P2E_ERR_INTERNAL); "chain_replay_lanes" (0: two lanes per (signature, chain) below 4096 signatures per call, one lane from there; 1 / 2: always) lanes of
- * the Jacobian replay kernel; "chain_split" (0; 1: on -- for hosts that keep fewer than ~24 caller streams in flight) run the
+ * the Jacobian replay kernel; "chain_graph" (1) replay a repeated chain call (same tape, sizes, buffers, stream) as one CUDA graph launch; "chain_split" (0; 1: on -- for hosts that keep fewer than ~24 caller streams in flight) run the
  * per-signature kernels of a chain call on an internal high-priority stream and the full-GPU kernels on a low-priority one.  Nothing is read from the
  * environment. */
 int p2e_set_option(const char* name, long value);

@@ -37,7 +37,7 @@ int ensure_ready();                   // also makes the context's device the CUD
 int get_scratch(int slot, size_t bytes, void** out);
 // tunables that used to be environment variables (p2e_set_option / p2e_get_option)
 long option(int id);
-enum OptionId : int { OPT_CHAIN_CHUNK = 0, OPT_HOST_CHUNKS = 1, OPT_GENSTREAM_FUSED = 2, OPT_GENSTREAM_GRAPH = 3, OPT_NTT_LOG_TILE = 4, OPT_CHAIN_TRACE = 5, OPT_CHAIN_SPLIT = 6, OPT_CHAIN_PHASES = 7, OPT_GENSTREAM_WALK = 8, OPT_GENSTREAM_WALK_SHAPE = 9, OPT_CHAIN_REPLAY_LANES = 10, N_OPTIONS = 11 };
+enum OptionId : int { OPT_CHAIN_CHUNK = 0, OPT_HOST_CHUNKS = 1, OPT_GENSTREAM_FUSED = 2, OPT_GENSTREAM_GRAPH = 3, OPT_NTT_LOG_TILE = 4, OPT_CHAIN_TRACE = 5, OPT_CHAIN_SPLIT = 6, OPT_CHAIN_PHASES = 7, OPT_GENSTREAM_WALK = 8, OPT_GENSTREAM_WALK_SHAPE = 9, OPT_CHAIN_REPLAY_LANES = 10, OPT_CHAIN_GRAPH = 11, N_OPTIONS = 12 };
 
 #define P2E_CUDA(call)                                  \
   do {                                                  \

@@ -20,7 +20,7 @@ static std::mutex g_ctx_mu;                    // guards creation / destruction 
 static int g_default_device = -1;              // first initialised device: current device of threads that never chose
 static thread_local int tls_device = -1;
 static thread_local std::string tls_error;
-static long g_options[N_OPTIONS] = {65536, 4, 1, 1, 12, 0, 0, 63, 1, 0, 0};
+static long g_options[N_OPTIONS] = {65536, 4, 1, 1, 12, 0, 0, 63, 1, 0, 0, 1};
 
 Context& ctx() {
   const int d = tls_device >= 0 ? tls_device : g_default_device;
@@ -802,7 +802,7 @@ int p2e_shutdown_device(int device) {
 
 const char* p2e_last_error(void) { return tls_error.c_str(); }
 
-static const char* const OPTION_NAMES[N_OPTIONS] = {"chain_chunk", "host_chunks", "genstream_fused", "genstream_graph", "ntt_log_tile", "chain_trace", "chain_split", "chain_phases", "genstream_walk", "genstream_walk_shape", "chain_replay_lanes"};
+static const char* const OPTION_NAMES[N_OPTIONS] = {"chain_chunk", "host_chunks", "genstream_fused", "genstream_graph", "ntt_log_tile", "chain_trace", "chain_split", "chain_phases", "genstream_walk", "genstream_walk_shape", "chain_replay_lanes", "chain_graph"};
 int p2e_set_option(const char* name, long value) {
   for (int i = 0; i < N_OPTIONS; i++)
     if (name && !strcmp(name, OPTION_NAMES[i])) {

@@ -378,3 +378,37 @@ def test_glv_mul_full_size_sampled_columns(engine):
         wb = S.WitnessBuilder()
         wb.glv_mul(wb.constant_affine_point((gx, gy)), wb.constant_nonnative(k, S.SECP_N))
         assert [int(v) for v in wit[:, j]] == wb.flat(), f"column {c}"
+
+
+def test_repeated_call_replays_a_cuda_graph_with_the_same_bits(engine):
+    """A call repeated with the same tape, sizes, buffers and stream is captured on its second occurrence and replayed as
+    one CUDA graph launch from the third on (option "chain_graph"): every occurrence must write the same witness."""
+    import torch
+    n = 96
+    wl = W.ecdsa_workload(n, seed=123)
+    ins = [torch.from_numpy(wl[k].view(np.int64)).cuda() for k in ("msg", "r", "s", "pkx", "pky")]
+    _, nn, _ = engine.tape_compact_layout(engine.TAPE_ECDSA)
+    nar = torch.zeros((nn, n), dtype=torch.int32, device="cuda")
+    err = torch.zeros(n, dtype=torch.int32, device="cuda")
+    st = torch.cuda.Stream()
+    outs = []
+    for rep in range(5):
+        nar.zero_()
+        err.fill_(7)
+        torch.cuda.synchronize()
+        rc = engine.lib.p2e_ecdsa_witness_compact_dev(n, *[t.data_ptr() for t in ins], n, nar.data_ptr(), None, n, err.data_ptr(), st.cuda_stream)
+        assert rc == 0, engine.last_error()
+        st.synchronize()
+        assert not bool(err.any())
+        outs.append(nar.cpu().numpy().view(np.uint32).copy())
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])
+    old = engine.get_option("chain_graph")
+    engine.set_option("chain_graph", 0)
+    nar.zero_()
+    assert engine.lib.p2e_ecdsa_witness_compact_dev(n, *[t.data_ptr() for t in ins], n, nar.data_ptr(), None, n, err.data_ptr(), st.cuda_stream) == 0
+    st.synchronize()
+    engine.set_option("chain_graph", old)
+    assert np.array_equal(nar.cpu().numpy().view(np.uint32), outs[0])
+    narrow, _, e2 = engine.tape_witness_compact(engine.TAPE_ECDSA, [wl[k] for k in ("msg", "r", "s", "pkx", "pky")], derive_check_sum=True)
+    assert np.array_equal(narrow, outs[0]) and not e2.any()
