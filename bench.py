@@ -83,14 +83,6 @@ METRICS = {
 LOG_ROWS = int(os.environ.get("P2E_BENCH_LOG_ROWS", "20"))
 
 
-def load_traffic():
-    p = os.path.join(ROOT, "profiles", "traffic.json")
-    try:
-        return json.load(open(p))
-    except Exception:       # noqa: BLE001
-        return {}
-
-
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -268,7 +260,6 @@ class Bench:
         self.sp = self.st.cuda_stream
         assert self.sp != 0
         self.peak_gbs, self.peak_kind = load_peaks()
-        self.traffic = load_traffic()
 
     def dev(self, a):
         return self.torch.from_numpy(a.view(self.np.int64)).cuda()
@@ -850,7 +841,11 @@ class Bench:
             res["kernel_ms"] = {nm: round(v, 4) for nm, v in zip(names, kernel_ms)}
             k_expand = kernel_ms[names.index("k_chain_expand")]
             achieved = s["alg_bytes"] / (k_expand * 1e-3) / 1e9
+            # traffic: dram read + write of this kernel for 4096 signatures from the ncu --set full capture of this build
+            # (profiles/r02y_ncu_chain_kernels.txt: 219 MB + 1 003 MB), scaled to this launch's signatures
             res["roofline_hbm_expand"] = {"bound": "hbm", "kernel": "k_chain_expand<compact>", "achieved": achieved, "peak": self.peak_gbs,
+                                          "traffic": int((219.446e6 + 1003.401e6) * s["units"] / 4096),
+                                          "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02y_ncu_chain_kernels.txt",
                                           "unit": "GB/s", "frac": achieved / self.peak_gbs, "peak_kind": self.peak_kind,
                                           "algorithmic_bytes_per_launch": s["alg_bytes"], "kernel_ms": k_expand,
                                           "share_of_step": k_expand / sum(kernel_ms)}
