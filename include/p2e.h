@@ -206,6 +206,9 @@ size_t p2e_tape_layout(int tape, uint32_t* kinds, uint32_t* offsets);
  *       (the row is unsatisfiable).  At most 65 535 calls per launch. */
 int p2e_tape_num_mul(int tape);
 int p2e_tape_mul_info(int tape, int j, int* x_limbs, int* y_limbs, uint32_t* out_slot, int* modulus);
+/* host-side resolution of instance j's two factors for ONE signature (loads only; inputs: [n_inputs] x 9 wires, witness:
+ * [slots] plain values of that signature) -> 9 limbs each, zero-padded: what the rows of calls x and y hold */
+int p2e_tape_mul_factors_host(int tape, int j, const uint64_t* const* inputs, const uint64_t* witness, uint64_t* x9, uint64_t* y9);
 int p2e_tape_num_range_checks(int tape);
 int p2e_tape_range_check_info(int tape, int first, int count, int32_t* generator, int32_t* inputs, int32_t* bits);
 int p2e_tape_range_check_layout(int tape, int limb_bits, uint64_t* wire_offsets);

@@ -894,4 +894,31 @@ int p2e_builder_finish(int h) {
   return TAPE_USER_BASE + (int)user_tapes().size() - 1;
 }
 
+// Host-side resolution of one mul_nonnative instance's two factor references for ONE signature (a layout query with
+// values: loads only, no arithmetic) -- what the range-check rows of the factors contain.  inputs: [n_inputs] pointers to 9
+// wires each; witness: [n_slots] plain values of that signature.
+int p2e_tape_mul_factors_host(int tape, int j, const uint64_t* const* inputs, const uint64_t* witness, uint64_t* x9, uint64_t* y9) {
+  if (!tape_exists(tape)) return set_error_msg("unknown tape id");
+  const Tape& t = get_tape(tape);
+  if (j < 0 || j >= (int)t.muls.size()) return set_error_msg("tape_mul_factors_host: instance out of range");
+  if (!witness || !x9 || !y9 || (t.n_inputs && !inputs)) return set_error_msg("tape_mul_factors_host: NULL argument");
+  auto load = [&](uint8_t space, uint32_t off) -> uint64_t {
+    switch (space) {
+      case SP_OUT: return off < t.n_slots ? witness[off] : 0;
+      case SP_IN: return off / 9 < t.n_inputs ? inputs[off / 9][off % 9] : 0;
+      case SP_CONST: return off < t.const_limbs.size() ? t.const_limbs[off] : 0;
+      case SP_CPOINT: return off < t.const_points.size() ? t.const_points[off] : 0;
+      default: return 0;
+    }
+  };
+  for (int f = 0; f < 2; f++) {
+    const Ref& r = f ? t.muls[j].y : t.muls[j].x;
+    uint64_t bm = 1;
+    if (r.bspace != SP_NONE) bm = (load(r.bspace, r.boff) ^ (uint64_t)r.binv) & 1;
+    uint64_t* o = f ? y9 : x9;
+    for (int l = 0; l < 9; l++) o[l] = l < r.nl ? load(r.space, r.off + l) * bm : 0;
+  }
+  return 0;
+}
+
 }  // extern "C"

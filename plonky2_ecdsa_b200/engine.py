@@ -98,6 +98,7 @@ SIGNATURES = {
     "p2e_tape_compact_layout": (_sz, [_int, _vp, _vp, _vp]),
     "p2e_tape_num_mul": (_int, [_int]),
     "p2e_tape_mul_info": (_int, [_int, _int, _vp, _vp, _vp, _vp]),
+    "p2e_tape_mul_factors_host": (_int, [_int, _int, _vp, _vp, _vp, _vp]),
     "p2e_tape_num_range_checks": (_int, [_int]),
     "p2e_tape_range_check_info": (_int, [_int, _int, _int, _vp, _vp, _vp]),
     "p2e_tape_range_check_layout": (_int, [_int, _int, _vp]),

@@ -192,3 +192,34 @@ def test_mul_nonnative_instances_of_the_ecdsa_tape():
     assert off[0] == 0 and np.array_equal(np.diff(off.astype(np.int64)), widths)
     assert set(bits.tolist()) == {29, 34} and (gen[1:] >= gen[:-1]).all()
     assert lib.p2e_tape_range_check_info(0, 0, nc + 1, None, None, None) != 0
+
+
+def test_mul_factor_references_resolve_to_the_oracles_factors():
+    """Tape::muls on the CPU tier: the two factor references of every mul_nonnative instance (witness slots, inputs,
+    constants, constant-point coordinates, bool factors), resolved on the host against the oracle's witness of one
+    signature, are the factors the oracle multiplied -- and x * y = q * m + r holds for the tuple at the recorded slot."""
+    import ctypes
+    lib = pkg.load_library()
+    sk, msg, k = 0x7654321 << 200 | 3, 0x7dcba9 << 232 | 9, 0x555 << 222 | 7       # all below the group order, top limb not zero
+    pk = S.pt_mul(sk, S.G)
+    r, s = S.sign_message(msg, sk, k)
+    wb = S.ecdsa_witness(msg, r, s, pk)
+    flat = np.array(wb.flat(), dtype=np.uint64)
+    ins = [np.array(S.convert_base(S.to_u32_digits(v), 32, 29) + [0] * 9, dtype=np.uint64)[:9].copy() for v in (msg, r, s, pk[0], pk[1])]
+    arr = (ctypes.c_void_p * 5)(*[a.ctypes.data for a in ins])
+    x9, y9 = np.zeros(9, dtype=np.uint64), np.zeros(9, dtype=np.uint64)
+    xl, yl, md = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    sl = ctypes.c_uint32(0)
+    lib.p2e_tape_mul_factors_host.restype = ctypes.c_int
+    lib.p2e_tape_mul_factors_host.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 4
+    val = lambda limbs: sum(int(v) << (29 * i) for i, v in enumerate(limbs))
+    for j in range(lib.p2e_tape_num_mul(0)):
+        assert lib.p2e_tape_mul_factors_host(0, j, arr, flat.ctypes.data, x9.ctypes.data, y9.ctypes.data) == 0
+        ox, oy = wb.mul_ops[j]
+        assert [int(v) for v in x9] == list(ox) + [0] * (9 - len(ox)), j
+        assert [int(v) for v in y9] == list(oy) + [0] * (9 - len(oy)), j
+        assert lib.p2e_tape_mul_info(0, j, ctypes.byref(xl), ctypes.byref(yl), ctypes.byref(sl), ctypes.byref(md)) == 0
+        m = S.MODULI[md.value]
+        rr, qq = val(flat[sl.value: sl.value + 9]), val(flat[sl.value + 9: sl.value + 18])
+        assert val(x9) * val(y9) == qq * m + rr and rr < m, j
+    assert lib.p2e_tape_mul_factors_host(0, 99999, arr, flat.ctypes.data, x9.ctypes.data, y9.ctypes.data) != 0
