@@ -223,3 +223,35 @@ def test_mul_factor_references_resolve_to_the_oracles_factors():
         rr, qq = val(flat[sl.value: sl.value + 9]), val(flat[sl.value + 9: sl.value + 18])
         assert val(x9) * val(y9) == qq * m + rr and rr < m, j
     assert lib.p2e_tape_mul_factors_host(0, 99999, arr, flat.ctypes.data, x9.ctypes.data, y9.ctypes.data) != 0
+
+
+def test_range_check_call_lists_of_every_builtin_tape():
+    """2 calls per add_many, 1 per sub, 7 per mul_nonnative (nonnative.rs:330-331, 373, 454-460) on all seven built-in tapes;
+    generator indices point at those kinds; wire offsets are the running sum of inputs * (1 + aux limbs)."""
+    import ctypes
+    lib = pkg.load_library()
+    lib.p2e_tape_num_range_checks.restype = ctypes.c_int
+    lib.p2e_tape_num_mul.restype = ctypes.c_int
+    per_kind = {S.K_ADDMANY: 2, S.K_SUB: 1, S.K_MUL: 7}
+    for tape in range(7):
+        kinds, offs, slots, _ = _tape(lib, tape)
+        nc = lib.p2e_tape_num_range_checks(tape)
+        assert nc == sum(per_kind.get(int(k), 0) for k in kinds), tape
+        assert lib.p2e_tape_num_mul(tape) == sum(1 for k in kinds if k == S.K_MUL)
+        if nc == 0:
+            continue
+        gen = np.empty(nc, dtype=np.int32)
+        cnt = np.empty(nc, dtype=np.int32)
+        bits = np.empty(nc, dtype=np.int32)
+        assert lib.p2e_tape_range_check_info(tape, 0, nc, gen.ctypes.data, cnt.ctypes.data, bits.ctypes.data) == 0
+        seen = {}
+        for g in gen:
+            seen[int(g)] = seen.get(int(g), 0) + 1
+        for g, c in seen.items():
+            assert per_kind[int(kinds[g])] == c, (tape, g)
+        assert ((bits == 29) | (bits == 34)).all() and (cnt >= 0).all() and (cnt <= 9).all() and (cnt[bits == 34] == 8).all()
+        for lb in (1, 2, 3, 4):
+            off = np.empty(nc + 1, dtype=np.uint64)
+            assert lib.p2e_tape_range_check_layout(tape, lb, off.ctypes.data) == 0
+            assert np.array_equal(np.diff(off.astype(np.int64)), cnt * (1 + -(-bits // lb)))
+        assert lib.p2e_tape_range_check_layout(tape, 0, None) != 0 and lib.p2e_tape_range_check_layout(tape, 9, None) != 0
